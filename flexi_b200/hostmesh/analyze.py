@@ -1,0 +1,73 @@
+"""Host-side analysis of the synthetic FLEXI host (stand-in for MOD_Analyze / the TGV AnalyzeTestcase).
+
+The Fortran host keeps these routines; the GPU library only has to hand U (and the lifted gradients) back at analyze steps.
+Reference: src/analyze/analyze.f90:224-278 (InitAnalyzeBasis), :391-485 (CalcErrorNorms), :150-158 (Vol);
+           src/testcase/taylorgreenvortex/testcase.f90:241-480 (AnalyzeTestcase).
+"""
+import numpy as np
+
+from . import basis as B
+
+
+class AnalyzeBasis:
+    def __init__(self, basis, n_analyze=None):
+        N = basis.N
+        self.NAnalyze = 2 * (N + 1) if n_analyze is None else n_analyze
+        xa, wa, _ = B.get_nodes_and_weights(self.NAnalyze, B.NODE_GAUSS_LOBATTO)
+        self.Vdm = B.initialize_vandermonde(basis.xGP, basis.wBary, xa)
+        self.w3 = np.einsum("k,j,i->kji", wa, wa, wa)
+        self.wGP3 = np.einsum("k,j,i->kji", basis.wGP, basis.wGP, basis.wGP)
+
+    def volume(self, sJ):
+        return float(np.sum(self.wGP3[None] / sJ))
+
+
+def tgv_analyze(ab, eqn, mesh, U, gradUx, gradUy, gradUz, vol, rho0=1.0):
+    """AnalyzeTestcase for one rank; returns the un-normalised sums and the normalised CSV columns (single rank)."""
+    nvl = gradUx.shape[-1]
+    v0 = 1 if nvl == 5 else 0                                   # LIFT_VELV
+    sJ_A = B.change_basis_3d(ab.Vdm, mesh.sJ[..., None])[..., 0]
+    U_A = B.change_basis_3d(ab.Vdm, U)
+    gvx = B.change_basis_3d(ab.Vdm, gradUx[..., v0:v0 + 3])     # [..., c] = d v_c / dx
+    gvy = B.change_basis_3d(ab.Vdm, gradUy[..., v0:v0 + 3])
+    gvz = B.change_basis_3d(ab.Vdm, gradUz[..., v0:v0 + 3])
+    P = eqn.cons_to_prim(U_A)
+    GradVel = np.stack([gvx, gvy, gvz], axis=-1)                # GradVel[..., c, d] = d v_c / d x_d
+    divU = GradVel[..., 0, 0] + GradVel[..., 1, 1] + GradVel[..., 2, 2]
+    S = 0.5 * (GradVel + np.swapaxes(GradVel, -1, -2))
+    Sd = S.copy()
+    for i in range(3):
+        Sd[..., i, i] -= divU / 3.0
+    vort = np.stack([GradVel[..., 2, 1] - GradVel[..., 1, 2], GradVel[..., 0, 2] - GradVel[..., 2, 0],
+                     GradVel[..., 1, 0] - GradVel[..., 0, 1]], axis=-1)
+    w = ab.w3[None] / sJ_A
+    v2 = np.sum(P[..., 1:4] ** 2, axis=-1)
+    o2 = np.sum(vort ** 2, axis=-1)
+    mu = eqn.mu0
+    out = dict(
+        T_mean=np.sum(w * P[..., 5]) / vol,
+        Entropy=np.sum(w * (-1.0 / (eqn.kappa - 1.0)) * P[..., 0] * (np.log(P[..., 4]) - eqn.kappa * np.log(P[..., 0]))) / vol,
+        Ekin=np.sum(w * 0.5 * v2) / vol,
+        Ekin_comp=np.sum(w * 0.5 * P[..., 0] * v2) / vol / rho0,
+        Enstr=np.sum(w * 0.5 * P[..., 0] * o2) / (rho0 * vol),
+        DR_u=np.sum(w * np.sum(GradVel ** 2, axis=(-1, -2))) * mu / vol,
+        DR_S=np.sum(w * np.sum(S ** 2, axis=(-1, -2))) * 2.0 * mu / (rho0 * vol),
+        DR_Sd=np.sum(w * np.sum(Sd ** 2, axis=(-1, -2))) * 2.0 * mu / (rho0 * vol),
+        DR_p=-np.sum(w * P[..., 4] * divU) / (rho0 * vol),
+        Vorticity_max=np.sqrt(np.max(o2)),
+        ED_S=np.sum(w * mu * o2) / vol,
+        ED_D=np.sum(w * mu * divU ** 2) * 4.0 / 3.0 / vol,
+    )
+    out["uPrime"] = np.sqrt(2.0 / 3.0 * out["Ekin"])
+    return out
+
+
+def calc_error_norms(ab, mesh, U, exact_fn, vol):
+    """CalcErrorNorms (analyze.f90:391-485) for one rank: returns (sum of squared L2 contributions, Linf) per variable."""
+    X_A = B.change_basis_3d(ab.Vdm, mesh.Elem_xGP)
+    J_A = B.change_basis_3d(ab.Vdm, (1.0 / mesh.sJ)[..., None])[..., 0]
+    U_A = B.change_basis_3d(ab.Vdm, U)
+    err = U_A - exact_fn(X_A)
+    linf = np.max(np.abs(err).reshape(-1, err.shape[-1]), axis=0)
+    l2sq = np.einsum("ekjiv,ekji->v", err * err, ab.w3[None] * J_A)
+    return l2sq, linf

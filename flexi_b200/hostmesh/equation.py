@@ -1,0 +1,136 @@
+"""Equation-system / time-disc parameters of the synthetic FLEXI host (stand-in for InitEquation, InitTimeDisc, FillIni).
+
+Reference (under /root/reference/src):
+  equations/navierstokes/idealgas/eos.f90:110-190          InitEos (kappa, R, Pr, mu0; cp, cv)
+  timedisc/timedisc_vars.f90:109-214                        SetTimeDiscCoefs (carpenterrk4-5 and friends)
+  timedisc/timedisc_func.f90:463-527                        FillCFL_DFL
+  testcase/taylorgreenvortex/testcase.f90:102-107,176-219   InitTestcase / ExactFuncTestcase
+  equations/navierstokes/idealgas/exactfunc.f90:332-362     ExactFunc case 4 (oblique sine wave)
+"""
+import numpy as np
+
+# timedisc_vars.f90:175-214
+RK_TABLES = {
+    "carpenterrk4-5": dict(
+        RKA=[567301805773.0 / 1357537059087.0, 2404267990393.0 / 2016746695238.0, 3550918686646.0 / 2091501179385.0,
+             1275806237668.0 / 842570457699.0],
+        RKb=[1432997174477.0 / 9575080441755.0, 5161836677717.0 / 13612068292357.0, 1720146321549.0 / 2090206949498.0,
+             3134564353537.0 / 4481467310338.0, 2277821191437.0 / 14882151754819.0],
+        RKc=[1432997174477.0 / 9575080441755.0, 2526269341429.0 / 6820363962896.0, 2006345519317.0 / 3224310063776.0,
+             2802321613138.0 / 2924317926251.0],
+        CFLScaleAlpha_G=[2.0351, 1.7595, 1.5401, 1.3702, 1.2375, 1.1318, 1.0440, 0.9709, 0.9079, 0.8539, 0.8066, 0.7650,
+                         0.7290, 0.6952, 0.6660],
+        CFLScaleAlpha_GL=[4.7497, 3.4144, 2.8451, 2.4739, 2.2027, 1.9912, 1.8225, 1.6830, 1.5682, 1.4692, 1.3849, 1.3106,
+                          1.2454, 1.1880, 1.1362],
+        RelativeDFL=1.853,
+    ),
+    # timedisc_vars.f90:137-168 Williamson RK3-3
+    "standardrk3-3": dict(
+        RKA=[5.0 / 9.0, 153.0 / 128.0],
+        RKb=[1.0 / 3.0, 15.0 / 16.0, 8.0 / 15.0],
+        RKc=[1.0 / 3.0, 0.75],
+        CFLScaleAlpha_G=[1.2285, 1.0485, 0.9101, 0.8066, 0.7268, 0.6626, 0.6109, 0.5670, 0.5299, 0.4973, 0.4703, 0.4455,
+                         0.4230, 0.4039, 0.3859],
+        CFLScaleAlpha_GL=[3.1871, 2.2444, 1.7797, 1.5075, 1.3230, 1.1857, 1.0800, 0.9945, 0.9247, 0.8651, 0.8134, 0.7695,
+                          0.7301, 0.6952, 0.6649],
+        RelativeDFL=1.0,
+    ),
+}
+# timedisc_vars.f90:93-98
+DFL_SCALE_ALPHA_G = [1.12, 0.76, 0.55, 0.41, 0.32, 0.25, 0.20, 0.17, 0.14, 0.12]
+DFL_SCALE_ALPHA_GL = [4.50, 1.95, 1.18, 0.79, 0.56, 0.42, 0.32, 0.25, 0.20, 0.17]
+
+
+class Equation:
+    """The parsed ini-surface of the hot path (what `prms` + the CMake cache hold in the reference)."""
+
+    def __init__(self, N, node_type, *, parabolic=True, split_dg=False, split_dg_type="pi", riemann="roeentropyfix",
+                 riemann_bc="same", lifting=1, n_var_lifting=5, kappa=1.4, R=287.058, Pr=0.72, mu0=0.0,
+                 time_disc="carpenterrk4-5", cfl_scale=0.9, dfl_scale=0.9, eta_br2=2.0, eta_br2_wall=-1.0):
+        self.N = N
+        self.node_type = node_type.lower()
+        self.parabolic = parabolic
+        self.split_dg = split_dg
+        self.split_dg_type = split_dg_type.lower()
+        self.riemann = riemann.lower()
+        self.riemann_bc = riemann_bc.lower()
+        self.lifting = lifting
+        self.n_var_lifting = n_var_lifting
+        self.kappa, self.R, self.Pr, self.mu0 = float(kappa), float(R), float(Pr), float(mu0)
+        self.eta_br2, self.eta_br2_wall = eta_br2, eta_br2_wall
+        self.boundary_type = []      # rows (BC_TYPE, BC_STATE, BC_ALPHA)
+        self.ref_state_prim = []     # rows (rho,u,v,w,p,T)
+        self.do_calc_source = False
+        self.ini_exact_func = 0
+        self.ini_amplitude, self.ini_frequency = 0.1, 1.0
+        self.adv_vel = (0.0, 0.0, 0.0)
+        self.ini_ref_state_prim = (1.0, 0.0, 0.0, 0.0, 1.0, 1.0)
+        tab = RK_TABLES[time_disc]
+        self.RKA, self.RKb, self.RKc = np.array(tab["RKA"]), np.array(tab["RKb"]), np.array(tab["RKc"])
+        # FillCFL_DFL, timedisc_func.f90:491-519
+        gl = self.node_type == "gauss-lobatto"
+        alpha = (tab["CFLScaleAlpha_GL"] if gl else tab["CFLScaleAlpha_G"])[min(15, N) - 1]
+        self.CFLScale = cfl_scale * alpha / (2.0 * N + 1.0)
+        alpha_d = (DFL_SCALE_ALPHA_GL if gl else DFL_SCALE_ALPHA_G)[min(10, N) - 1] * tab["RelativeDFL"]
+        self.DFLScale = dfl_scale * alpha_d / (2.0 * N + 1.0) ** 2
+
+    # ---- EOS helpers (eos.f90:203-231, 308-330) on arrays [..., var] -------------------------------------------------
+    def prim_to_cons(self, prim):
+        cons = np.empty(prim.shape[:-1] + (5,))
+        cons[..., 0] = prim[..., 0]
+        cons[..., 1:4] = prim[..., 1:4] * prim[..., 0:1]
+        cons[..., 4] = prim[..., 4] / (self.kappa - 1.0) + 0.5 * np.sum(cons[..., 1:4] * prim[..., 1:4], axis=-1)
+        return cons
+
+    def cons_to_prim(self, cons):
+        prim = np.empty(cons.shape[:-1] + (6,))
+        srho = 1.0 / cons[..., 0]
+        prim[..., 0] = cons[..., 0]
+        prim[..., 1:4] = cons[..., 1:4] * srho[..., None]
+        prim[..., 4] = (self.kappa - 1.0) * (cons[..., 4] - 0.5 * np.sum(cons[..., 1:4] * prim[..., 1:4], axis=-1))
+        prim[..., 5] = prim[..., 4] * srho / self.R
+        return prim
+
+    # ---- initial states ------------------------------------------------------------------------------------------------
+    def tgv_state(self, x, mach=0.1, ini_const_dens=True):
+        """ExactFuncTestcase of the Taylor-Green vortex (testcase.f90:176-219), U0 = rho0 = 1."""
+        U0, rho0 = 1.0, 1.0
+        p0 = (U0 / mach) ** 2 / self.kappa * rho0
+        T0 = p0 / (rho0 * self.R)
+        prim = np.zeros(x.shape[:-1] + (6,))
+        X, Y, Z = x[..., 0], x[..., 1], x[..., 2]
+        prim[..., 1] = U0 * np.sin(X) * np.cos(Y) * np.cos(Z)
+        prim[..., 2] = -U0 * np.cos(X) * np.sin(Y) * np.cos(Z)
+        prim[..., 3] = 0.0
+        prim[..., 4] = p0 + (rho0 * U0 ** 2) / 16.0 * (np.cos(2 * X) * np.cos(2.0 * Z) + 2.0 * np.cos(2.0 * Y)
+                                                          + 2.0 * np.cos(2.0 * X) + np.cos(2 * Y) * np.cos(2.0 * Z))
+        if ini_const_dens:
+            prim[..., 0] = rho0
+            prim[..., 5] = prim[..., 4] / (prim[..., 0] * self.R)
+        else:
+            prim[..., 5] = T0
+            prim[..., 0] = prim[..., 4] / (prim[..., 5] * self.R)
+        return self.prim_to_cons(prim)
+
+    def random_state(self, shape, seed=1234):
+        """Random-field stress state: rho,p in [0.5,1.5], v in [-0.5,0.5]^3."""
+        rng = np.random.default_rng(seed)
+        prim = np.zeros(tuple(shape) + (6,))
+        prim[..., 0] = rng.uniform(0.5, 1.5, shape)
+        prim[..., 1:4] = rng.uniform(-0.5, 0.5, tuple(shape) + (3,))
+        prim[..., 4] = rng.uniform(0.5, 1.5, shape)
+        prim[..., 5] = prim[..., 4] / (prim[..., 0] * self.R)
+        return self.prim_to_cons(prim)
+
+    def smooth_state(self, x, length=2 * np.pi, amp=0.2):
+        """Smooth periodic non-trivial state for parity tests on (curved) periodic boxes."""
+        k = 2 * np.pi / length
+        X, Y, Z = k * x[..., 0], k * x[..., 1], k * x[..., 2]
+        prim = np.zeros(x.shape[:-1] + (6,))
+        prim[..., 0] = 1.0 + amp * np.sin(X + 0.3) * np.cos(Y) * np.cos(2 * Z + 0.1)
+        prim[..., 1] = 0.3 + amp * np.sin(X) * np.cos(Y + 0.2) * np.cos(Z)
+        prim[..., 2] = -0.2 + amp * np.cos(2 * X) * np.sin(Y) * np.cos(Z + 0.5)
+        prim[..., 3] = 0.1 + amp * np.cos(X + 0.7) * np.cos(Y) * np.sin(Z)
+        prim[..., 4] = 1.0 + amp * np.cos(X) * np.sin(2 * Y + 0.4) * np.cos(Z)
+        prim[..., 5] = prim[..., 4] / (prim[..., 0] * self.R)
+        return self.prim_to_cons(prim)

@@ -1,0 +1,218 @@
+/* flexi_gpu.h -- C ABI of the B200-native DGSEM right-hand side / LSERK time stepper for FLEXI.
+ *
+ * Drop-in boundary for ONE path of flexi-framework/flexi (file:line under /root/reference/src):
+ *
+ *   flexi_gpu_dg_time_derivative  replaces  DGTimeDerivative_weakForm(t)           dg/dg.f90:221-678
+ *   flexi_gpu_timestep            replaces  TimeStepByLSERKW2(t)                   timedisc/timestep.f90:82-152
+ *   flexi_gpu_calc_timestep       replaces  CalcTimeStep(errType)                  equations/navierstokes/calctimestep.f90:89-227
+ *   flexi_gpu_prolong_to_face     replaces  ProlongToFaceCons                      interpolation/prolongtoface.t90:21-144
+ *   flexi_gpu_surf_int            replaces  SurfIntCons                            dg/surfint.t90:21-239,475-616
+ *   halo exchange inside          replaces  Start{Receive,Send}MPIData/Finish...   mpi/mpi.f90:244-445  (NCCL send/recv)
+ *
+ * The Fortran host keeps everything else (ini parsing, mesh/metrics, HDF5 I/O) and hands its module arrays over ONCE through
+ * flexi_gpu_desc (INTEGRATION.md shows the ISO_C_BINDING shim).  All arrays are the host's contiguous ALLOCATABLEs, passed as
+ * base address + extents in Fortran (column-major) order with the shapes quoted below; INTEGER is 4 bytes, REAL is 8 bytes
+ * (cmake/SetCompiler.cmake:79).  The library COPIES everything at init, owns all device memory and keeps no host pointer.
+ *
+ * Every entry point returns 0 on success and a negative code on failure (flexi_gpu_last_error() gives the text; the shim
+ * turns it into CALL Abort(__STAMP__,...), globals/globals.f90:177-224).  No exception crosses this boundary.
+ * One rank <-> one OS thread <-> one GPU; calls are sequential per rank.
+ */
+#ifndef FLEXI_GPU_H
+#define FLEXI_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FLEXI_GPU_ABI_VERSION 1
+
+/* PP_NodeType (src/CMakeLists.txt) */
+#define FLEXI_NODETYPE_GAUSS 1
+#define FLEXI_NODETYPE_GAUSS_LOBATTO 2
+
+/* PRM_RIEMANN_* (equations/navierstokes/riemann.f90:50-62) */
+#define FLEXI_RIEMANN_SAME (-1)
+#define FLEXI_RIEMANN_LF 1
+#define FLEXI_RIEMANN_HLLC 2
+#define FLEXI_RIEMANN_ROE 3
+#define FLEXI_RIEMANN_ROEL2 32
+#define FLEXI_RIEMANN_ROEENTROPYFIX 33
+#define FLEXI_RIEMANN_HLL 4
+#define FLEXI_RIEMANN_HLLE 5
+#define FLEXI_RIEMANN_HLLEM 6
+
+/* PRM_SPLITDG_* (equations/navierstokes/splitflux.f90:63-69) */
+#define FLEXI_SPLITDG_SD 0
+#define FLEXI_SPLITDG_MO 1
+#define FLEXI_SPLITDG_DU 2
+#define FLEXI_SPLITDG_KG 3
+#define FLEXI_SPLITDG_PI 4
+
+/* error codes */
+#define FLEXI_GPU_OK 0
+#define FLEXI_GPU_ERR_ARG (-1)
+#define FLEXI_GPU_ERR_CUDA (-2)
+#define FLEXI_GPU_ERR_NCCL (-3)
+#define FLEXI_GPU_ERR_UNSUPPORTED (-4)
+
+#define FLEXI_GPU_NCCL_ID_BYTES 128
+
+typedef struct flexi_gpu_handle flexi_gpu_handle;
+
+/* Everything the path reads from MOD_*_Vars.  Shapes are Fortran shapes; np = N+1. */
+typedef struct flexi_gpu_desc {
+  int32_t abi_version; /* FLEXI_GPU_ABI_VERSION */
+  int32_t struct_bytes; /* sizeof(flexi_gpu_desc) as seen by the caller */
+
+  /* ---- build options of the reference, run-time here (src/CMakeLists.txt:23-230) ---- */
+  int32_t N;           /* PP_N, 1..9 */
+  int32_t nodeType;    /* PP_NodeType */
+  int32_t splitDG;     /* SPLIT_DG: 0 = weak form (VolInt_weakForm), 1 = split form (VolInt_splitForm) */
+  int32_t parabolic;   /* PARABOLIC: 0 = Euler, 1 = Navier-Stokes */
+  int32_t lifting;     /* PP_Lifting: 1 = BR1, 2 = BR2 */
+  int32_t nVarLifting; /* PP_nVarLifting: 5 (PP_OPTLIFT=0) or 4 (PP_OPTLIFT=1), idealgas/eos.h:108-127 */
+
+  /* ---- run-time options ---- */
+  int32_t splitDGType;           /* SplitDG, splitflux.f90:109-153 */
+  int32_t riemann;               /* Riemann, riemann.f90:140-259 */
+  int32_t riemannBC;             /* RiemannBC (FLEXI_RIEMANN_SAME = same as inner) */
+  int32_t doWeakLifting;         /* lifting.f90:122-125 (must be 0) */
+  int32_t doConservativeLifting; /* lifting.f90:122-129 (must be 0) */
+  double etaBR2, etaBR2_wall;    /* lifting.f90:130-133 */
+
+  /* ---- mesh extents and side ranges (mesh.f90:257-269); mortar counts must be 0 ---- */
+  int32_t nElems, nSides, nBCSides, nInnerSides, nMPISides_MINE, nMPISides_YOUR;
+
+  /* ---- volume geometry, mesh_vars.f90:62-78 ---- */
+  const double* Metrics_fTilde; /* (3,0:N,0:N,0:N,nElems) */
+  const double* Metrics_gTilde;
+  const double* Metrics_hTilde;
+  const double* sJ;       /* (0:N,0:N,0:N,nElems) */
+  const double* Elem_xGP; /* (3,0:N,0:N,0:N,nElems), only read when a source term / exact function needs it; may be NULL */
+  /* ---- surface geometry ---- */
+  const double* NormVec;  /* (3,0:N,0:N,nSides) */
+  const double* TangVec1;
+  const double* TangVec2;
+  const double* SurfElem; /* (0:N,0:N,nSides) */
+  const double* Face_xGP; /* (3,0:N,0:N,nSides); may be NULL without BCs */
+  /* ---- connectivity, mesh_vars.f90:85-119 ---- */
+  const int32_t* SideToElem; /* (5,nSides), 1-based ids, -1 = absent, flexi.h:98-102 */
+  const int32_t* ElemToSide; /* (2,6,nElems), flexi.h:105-106 */
+  const int32_t* S2V2;       /* (2,0:N,0:N,0:4,1:6), mappings.f90:389-397 */
+  const int32_t* BC;         /* (nBCSides) index into BoundaryType */
+  int32_t nBCs;
+  const int32_t* BoundaryType; /* (3,nBCs): BC_TYPE, BC_STATE, BC_ALPHA */
+  int32_t nRefState;
+  const double* RefStatePrim; /* (6,nRefState) */
+
+  /* ---- basis, interpolation_vars.f90 + dg_vars.f90:31-102 ---- */
+  const double* xGP;        /* (0:N) */
+  const double* wGP;        /* (0:N) */
+  const double* D;          /* (0:N,0:N) */
+  const double* D_T;        /* (0:N,0:N) */
+  const double* D_Hat_T;    /* (0:N,0:N) */
+  const double* DVolSurf;   /* (0:N,0:N), only read if splitDG */
+  const double* L_Minus;    /* (0:N) */
+  const double* L_Plus;     /* (0:N) */
+  const double* L_HatMinus; /* (0:N) */
+  const double* L_HatPlus;  /* (0:N) */
+
+  /* ---- equation of state, eos.f90:110-190 ---- */
+  double kappa, R, Pr, mu0;
+
+  /* ---- source term: IniExactFunc / doCalcSource, exactfunc.f90:727-815 (only case 4 is on the path) ---- */
+  int32_t doCalcSource;
+  int32_t iniExactFunc;
+  double iniAmplitude, iniFrequency;
+  double advVel[3];
+  double iniRefStatePrim[6]; /* RefStatePrim(:,IniRefState) */
+
+  /* ---- time discretisation, timedisc_vars.f90:109-214, timedisc_func.f90:463-527 ---- */
+  int32_t nRKStages;
+  const double* RKA; /* (2:nRKStages) -> nRKStages-1 values */
+  const double* RKb; /* (1:nRKStages) */
+  const double* RKc; /* (2:nRKStages) */
+  double CFLScale;   /* CFLScale(0) after FillCFL_DFL */
+  double DFLScale;   /* DFLScale(0) after FillCFL_DFL */
+
+  /* ---- partition, mpi_vars.f90:53-81 ---- */
+  int32_t myRank, nProcs, nNbProcs;
+  const int32_t* NbProc;              /* (nNbProcs) */
+  const int32_t* nMPISides_MINE_Proc; /* (nNbProcs) */
+  const int32_t* nMPISides_YOUR_Proc; /* (nNbProcs) */
+  const int32_t* offsetMPISides_MINE; /* (0:nNbProcs) */
+  const int32_t* offsetMPISides_YOUR; /* (0:nNbProcs) */
+  const void* ncclUniqueId;           /* FLEXI_GPU_NCCL_ID_BYTES from flexi_gpu_nccl_unique_id on rank 0, broadcast by the host
+                                         (MPI_Bcast in the shim); NULL when nProcs == 1 */
+  int32_t device;                     /* CUDA device ordinal for this rank (local rank) */
+  int32_t reserved;
+} flexi_gpu_desc;
+
+/* which array flexi_gpu_get_array returns (host receives the Fortran layout of the named module array) */
+enum flexi_gpu_array {
+  FLEXI_ARR_U = 0,            /* U(5,0:N,0:N,0:N,nElems)               dg_vars.f90 */
+  FLEXI_ARR_UT = 1,           /* Ut(5,...)                                          */
+  FLEXI_ARR_U_MASTER = 2,     /* U_master(5,0:N,0:N,nSides)                         */
+  FLEXI_ARR_U_SLAVE = 3,      /* U_slave                                            */
+  FLEXI_ARR_FLUX = 4,         /* Flux_master(5,0:N,0:N,nSides) (== Flux_slave, fillflux.f90:201) */
+  FLEXI_ARR_GRADUX = 5,       /* gradUx(nVarLifting,0:N,0:N,0:N,nElems) lifting_vars.f90 */
+  FLEXI_ARR_GRADUY = 6,
+  FLEXI_ARR_GRADUZ = 7,
+  FLEXI_ARR_GRADUX_MASTER = 8, /* gradUx_master(nVarLifting,0:N,0:N,nSides) */
+  FLEXI_ARR_GRADUY_MASTER = 9,
+  FLEXI_ARR_GRADUZ_MASTER = 10,
+  FLEXI_ARR_GRADUX_SLAVE = 11,
+  FLEXI_ARR_GRADUY_SLAVE = 12,
+  FLEXI_ARR_GRADUZ_SLAVE = 13
+};
+
+const char* flexi_gpu_last_error(void);
+int flexi_gpu_abi_version(void);
+
+/* rank 0: create the NCCL bootstrap id the host broadcasts (replaces MPI_COMM_FLEXI setup, mpi/mpi.f90:89-109) */
+int flexi_gpu_nccl_unique_id(void* out_id_bytes);
+
+/* InitDG/InitLifting/InitTimeDisc/InitMPIvars equivalent for the device side: call right after InitTimeDisc (flexilib.f90:216-245) */
+int flexi_gpu_init(const flexi_gpu_desc* desc, flexi_gpu_handle** out);
+int flexi_gpu_finalize(flexi_gpu_handle* h);
+
+/* U in Fortran order (5,0:N,0:N,0:N,nElems); U is authoritative on the device between set_state and get_state */
+int flexi_gpu_set_state(flexi_gpu_handle* h, const double* U);
+int flexi_gpu_get_state(flexi_gpu_handle* h, double* U);
+
+/* DGTimeDerivative_weakForm(t): U -> Ut (and all face / gradient arrays). If Ut != NULL the result is copied to the host. */
+int flexi_gpu_dg_time_derivative(flexi_gpu_handle* h, double t, double* Ut);
+
+/* TimeStepByLSERKW2(t): all nRKStages stages with the stage update fused into the last RHS kernel; t is advanced by the
+ * caller exactly like in timedisc.f90:190-212 (t is INOUT only to mirror the TimeIntegrator interface, timestep.f90:27-37). */
+int flexi_gpu_timestep(flexi_gpu_handle* h, double* t, double dt);
+/* n consecutive steps with the same dt without returning to the host in between (the host does this when nCalcTimeStepMax>1) */
+int flexi_gpu_timestep_n(flexi_gpu_handle* h, double* t, double dt, int32_t nSteps);
+
+/* CalcTimeStep: min over elements and ranks; errType as calctimestep.f90:157-222 */
+int flexi_gpu_calc_timestep(flexi_gpu_handle* h, double* dt_min, double* dt_conv, double* dt_visc, int32_t* errType);
+
+/* analysis access (TGV analysis reads GradUx/y/z, testcase.f90:249; Ut is needed at analyze steps, timedisc_func.f90:323-326) */
+int flexi_gpu_get_array(flexi_gpu_handle* h, int32_t which, double* out);
+
+/* Operator-level entry points (what the reference's own unit tests drive, unitTests/ProlongToFace.f90, SurfInt.f90).
+ * Host arrays in Fortran order; the handle supplies mesh + basis.  doMPISides selects the side range like the reference. */
+int flexi_gpu_prolong_to_face(flexi_gpu_handle* h, const double* Uvol, double* Uface_master, double* Uface_slave,
+                              int32_t doMPISides);
+int flexi_gpu_surf_int(flexi_gpu_handle* h, const double* Flux_master, const double* Flux_slave, double* Ut,
+                       int32_t doMPISides);
+
+/* counters for bench.py: kernels launched by this library since init, bytes moved by host<->device copies */
+int flexi_gpu_counters(flexi_gpu_handle* h, int64_t* kernel_launches, int64_t* h2d_bytes, int64_t* d2h_bytes);
+/* device time [ms] accumulated by CUDA events around each hot-path kernel class since the last reset (index = kernel class) */
+int flexi_gpu_kernel_times(flexi_gpu_handle* h, double* ms_out, int64_t* launches_out, int32_t n_classes, int32_t reset);
+int flexi_gpu_set_profiling(flexi_gpu_handle* h, int32_t on);
+int flexi_gpu_synchronize(flexi_gpu_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLEXI_GPU_H */

@@ -1,0 +1,1401 @@
+/* flexi_oracle.c -- CPU restatement of FLEXI's DGSEM right-hand side, LSERK stepping and time-step reduction.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This file is the checker the CUDA path is compared with; it is never part of the product
+ * path.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it.
+ *
+ * It is a loop-for-loop restatement (own code, same arithmetic and array layout) of the reference routines named in each
+ * function header; file:line refer to /root/reference/src.  Arrays are stored exactly like the Fortran module arrays
+ * (column-major, first index fastest), e.g. U(var,i,j,k,elem) -> U[(((e*np+k)*np+j)*np+i)*5+var].
+ *
+ * Parity status: ProlongToFace and SurfInt are pinned against the reference's unit-test fixtures (tests/golden/
+ * reference_unittests, see tests/test_oracle_golden.py).  VolInt, Riemann solvers, split fluxes, lifting, FillFlux, the RK update
+ * and CalcTimeStep have no function-level fixture in the reference ("parity unpinned" at function level);
+ * they are validated through identities (consistency, free-stream preservation, conservation, weak==split(SD) on LGL,
+ * partition invariance, convergence order) and through the analytic t=0 row of the TGV regression CSV.
+ *
+ * MPI is emulated inside one process: a "world" holds one oracle per rank; the non-blocking exchanges of mpi/mpi.f90:244-445
+ * become slice copies between ranks at the point where the reference calls FinishExchangeMPIData.  With OpenMP the ranks of
+ * a world advance in parallel (one rank per thread == the reference's one MPI rank per core).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../include/flexi_gpu.h"
+
+#define NVAR 5
+#define NPRIM 6
+
+/* conservative / primitive variable positions, idealgas/eos.h (0-based here) */
+enum { DENS = 0, MOM1 = 1, MOM2 = 2, MOM3 = 3, ENER = 4 };
+enum { VEL1 = 1, VEL2 = 2, VEL3 = 3, PRES = 4, TEMP = 5 };
+/* extended vector U(1:11): cons, 1/rho, v1,v2,v3, p, T   (eos.h:91-106) */
+enum { EXT_DENS = 0, EXT_MOM1 = 1, EXT_MOM2 = 2, EXT_MOM3 = 3, EXT_ENER = 4, EXT_SRHO = 5, EXT_VEL1 = 6, EXT_VEL2 = 7,
+       EXT_VEL3 = 8, EXT_PRES = 9, EXT_TEMP = 10 };
+/* local sides, flexi.h:90-95 */
+enum { ZETA_MINUS = 1, ETA_MINUS = 2, XI_PLUS = 3, ETA_PLUS = 4, XI_MINUS = 5, ZETA_PLUS = 6 };
+
+typedef struct oracle {
+  flexi_gpu_desc d; /* scalar fields valid; pointer fields re-pointed to owned copies */
+  int np, nvl;      /* N+1, PP_nVarLifting */
+  int lift_map[5];  /* PRIM_LIFT (0-based prim index of each lifting variable), eos.h:118,127 */
+  int lv_vel1, lv_temp;
+  /* derived constants, eos.f90:136-163 */
+  double kappaM1, sKappaM1, cp, cv, lambda_fac, KappasPr;
+  /* state */
+  double *U, *Ut, *UPrim, *Ut_tmp;
+  double *U_master, *U_slave, *UPrim_master, *UPrim_slave, *Flux_master, *Flux_slave;
+  double *gradUx, *gradUy, *gradUz;
+  double *gradUx_master, *gradUy_master, *gradUz_master, *gradUx_slave, *gradUy_slave, *gradUz_slave;
+  double *FluxX, *FluxY, *FluxZ; /* BR2 */
+  double *MetricsAdv, *MetricsVisc; /* InitCalctimestep */
+  /* owned copies of descriptor arrays */
+  void* owned[64];
+  int n_owned;
+  /* side ranges (1-based inclusive), mesh.f90:257-269 */
+  int firstBCSide, lastBCSide, firstInnerSide, lastInnerSide, firstMPISide_MINE, lastMPISide_MINE, firstMPISide_YOUR,
+      lastMPISide_YOUR;
+} oracle;
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* helpers                                                                                                            */
+/* ------------------------------------------------------------------------------------------------------------------ */
+static void* xcalloc(size_t n, size_t s) {
+  void* p = calloc(n ? n : 1, s);
+  if (!p) {
+    fprintf(stderr, "oracle: out of memory\n");
+    abort();
+  }
+  return p;
+}
+
+static void* own_copy(oracle* o, const void* src, size_t bytes) {
+  if (!src) return NULL;
+  void* p = xcalloc(bytes ? bytes : 1, 1);
+  memcpy(p, src, bytes);
+  o->owned[o->n_owned++] = p;
+  return p;
+}
+
+#define VOL(a, nv, v, i, j, k, e) (a)[((((size_t)(e)*np + (k)) * np + (j)) * np + (i)) * (nv) + (v)]
+#define SID(a, nv, v, p, q, s) (a)[(((size_t)(s)*np + (q)) * np + (p)) * (nv) + (v)]
+#define MAT(a, r, c) (a)[(size_t)(c)*np + (r)] /* Fortran (r,c) of an (0:N,0:N) matrix */
+/* S2V2(c,p,q,flip,locSide) with locSide 1..6 */
+#define S2V2(c, p, q, f, ls) o->d.S2V2[((((size_t)((ls)-1) * 5 + (f)) * np + (q)) * np + (p)) * 2 + (c)]
+#define S2E(c, s) o->d.SideToElem[(size_t)(s)*5 + (c)] /* c: 0 ELEM_ID,1 NB_ELEM_ID,2 LOC_SIDE_ID,3 NB_LOC_SIDE_ID,4 FLIP */
+
+/* eos.f90:203-231 ConsToPrim */
+static inline void cons_to_prim(const oracle* o, double* prim, const double* cons) {
+  double sRho = 1. / cons[DENS];
+  prim[DENS] = cons[DENS];
+  prim[VEL1] = cons[MOM1] * sRho;
+  prim[VEL2] = cons[MOM2] * sRho;
+  prim[VEL3] = cons[MOM3] * sRho;
+  prim[PRES] = o->kappaM1 * (cons[ENER] - 0.5 * (cons[MOM1] * prim[VEL1] + cons[MOM2] * prim[VEL2] + cons[MOM3] * prim[VEL3]));
+  prim[TEMP] = prim[PRES] * sRho / o->d.R;
+}
+
+/* eos.f90:308-330 PrimToCons */
+static inline void prim_to_cons(const oracle* o, const double* prim, double* cons) {
+  cons[DENS] = prim[DENS];
+  cons[MOM1] = prim[VEL1] * prim[DENS];
+  cons[MOM2] = prim[VEL2] * prim[DENS];
+  cons[MOM3] = prim[VEL3] * prim[DENS];
+  cons[ENER] = o->sKappaM1 * prim[PRES] + 0.5 * (cons[MOM1] * prim[VEL1] + cons[MOM2] * prim[VEL2] + cons[MOM3] * prim[VEL3]);
+}
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* fluxes: flux.f90                                                                                                   */
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* flux.f90:66-119 EvalFlux3D_Point */
+static inline void eval_flux3d(const double* U, const double* P, double* f, double* g, double* h) {
+  double Ep = U[ENER] + P[PRES];
+  f[DENS] = U[MOM1];
+  f[MOM1] = U[MOM1] * P[VEL1] + P[PRES];
+  f[MOM2] = U[MOM1] * P[VEL2];
+  f[MOM3] = U[MOM1] * P[VEL3];
+  f[ENER] = Ep * P[VEL1];
+  g[DENS] = U[MOM2];
+  g[MOM1] = f[MOM2];
+  g[MOM2] = U[MOM2] * P[VEL2] + P[PRES];
+  g[MOM3] = U[MOM2] * P[VEL3];
+  g[ENER] = Ep * P[VEL2];
+  h[DENS] = U[MOM3];
+  h[MOM1] = f[MOM3];
+  h[MOM2] = g[MOM3];
+  h[MOM3] = U[MOM3] * P[VEL3] + P[PRES];
+  h[ENER] = Ep * P[VEL3];
+}
+
+/* flux.f90:149-241 EvalDiffFlux3D_Point (PP_VISC=0: mu = mu0; lambda = mu*cp/Pr, eos.h:46) */
+static inline void eval_diff_flux3d(const oracle* o, const double* P, const double* gx, const double* gy, const double* gz,
+                                    double* f, double* g, double* h) {
+  const double s23 = 2. / 3., s43 = 4. / 3.;
+  const int V1 = o->lv_vel1, V2 = V1 + 1, V3 = V1 + 2, T = o->lv_temp;
+  double muS = o->d.mu0;
+  double lambda = muS * o->cp / o->d.Pr;
+  double v1 = P[VEL1], v2 = P[VEL2], v3 = P[VEL3];
+  double tau_xx = muS * (s43 * gx[V1] - s23 * gy[V2] - s23 * gz[V3]);
+  double tau_yy = muS * (-s23 * gx[V1] + s43 * gy[V2] - s23 * gz[V3]);
+  double tau_zz = muS * (-s23 * gx[V1] - s23 * gy[V2] + s43 * gz[V3]);
+  double tau_xy = muS * (gy[V1] + gx[V2]);
+  double tau_xz = muS * (gz[V1] + gx[V3]);
+  double tau_yz = muS * (gz[V2] + gy[V3]);
+  f[DENS] = 0.;
+  f[MOM1] = -tau_xx;
+  f[MOM2] = -tau_xy;
+  f[MOM3] = -tau_xz;
+  f[ENER] = -tau_xx * v1 - tau_xy * v2 - tau_xz * v3 - lambda * gx[T];
+  g[DENS] = 0.;
+  g[MOM1] = -tau_xy;
+  g[MOM2] = -tau_yy;
+  g[MOM3] = -tau_yz;
+  g[ENER] = -tau_xy * v1 - tau_yy * v2 - tau_yz * v3 - lambda * gy[T];
+  h[DENS] = 0.;
+  h[MOM1] = -tau_xz;
+  h[MOM2] = -tau_yz;
+  h[MOM3] = -tau_zz;
+  h[ENER] = -tau_xz * v1 - tau_yz * v2 - tau_zz * v3 - lambda * gz[T];
+}
+
+/* flux.f90:396-417 EvalEulerFlux1D_fast */
+static inline void eval_euler_flux1d_fast(const double* U, double* F) {
+  F[DENS] = U[EXT_MOM1];
+  F[MOM1] = U[EXT_MOM1] * U[EXT_VEL1] + U[EXT_PRES];
+  F[MOM2] = U[EXT_MOM1] * U[EXT_VEL2];
+  F[MOM3] = U[EXT_MOM1] * U[EXT_VEL3];
+  F[ENER] = (U[EXT_ENER] + U[EXT_PRES]) * U[EXT_VEL1];
+}
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* split fluxes: splitflux.f90                                                                                        */
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* physical-space two-point fluxes fT,gT,hT of the chosen split form (factor 2 folded in, splitflux.f90:21-22) */
+static void split_volume_flux(int type, const double* UR, const double* PR, const double* U, const double* P, const double* MR,
+                              const double* M, double* Flux) {
+  double fT[5], gT[5], hT[5];
+  switch (type) {
+    case FLEXI_SPLITDG_SD: { /* splitflux.f90:160-222 */
+      double rhoEpRef = UR[ENER] + PR[PRES], rhoEp = U[ENER] + P[PRES];
+      fT[DENS] = (UR[MOM1] + U[MOM1]);
+      fT[MOM1] = (UR[MOM1] * PR[VEL1] + PR[PRES] + U[MOM1] * P[VEL1] + P[PRES]);
+      fT[MOM2] = (UR[MOM1] * PR[VEL2] + U[MOM1] * P[VEL2]);
+      fT[MOM3] = (UR[MOM1] * PR[VEL3] + U[MOM1] * P[VEL3]);
+      fT[ENER] = (rhoEpRef * PR[VEL1] + rhoEp * P[VEL1]);
+      gT[DENS] = (UR[MOM2] + U[MOM2]);
+      gT[MOM1] = (UR[MOM1] * PR[VEL2] + U[MOM1] * P[VEL2]);
+      gT[MOM2] = (UR[MOM2] * PR[VEL2] + PR[PRES] + U[MOM2] * P[VEL2] + P[PRES]);
+      gT[MOM3] = (UR[MOM2] * PR[VEL3] + U[MOM2] * P[VEL3]);
+      gT[ENER] = (rhoEpRef * PR[VEL2] + rhoEp * P[VEL2]);
+      hT[DENS] = (UR[MOM3] + U[MOM3]);
+      hT[MOM1] = (UR[MOM1] * PR[VEL3] + U[MOM1] * P[VEL3]);
+      hT[MOM2] = (UR[MOM2] * PR[VEL3] + U[MOM2] * P[VEL3]);
+      hT[MOM3] = (UR[MOM3] * PR[VEL3] + PR[PRES] + U[MOM3] * P[VEL3] + P[PRES]);
+      hT[ENER] = (rhoEpRef * PR[VEL3] + rhoEp * P[VEL3]);
+    } break;
+    case FLEXI_SPLITDG_DU: { /* splitflux.f90:262-320 */
+      double su = PR[VEL1] + P[VEL1], sv = PR[VEL2] + P[VEL2], sw = PR[VEL3] + P[VEL3], sp = PR[PRES] + P[PRES];
+      double sE = UR[ENER] + U[ENER] + PR[PRES] + P[PRES];
+      fT[DENS] = 0.5 * (UR[DENS] + U[DENS]) * su;
+      fT[MOM1] = 0.5 * (UR[MOM1] + U[MOM1]) * su + sp;
+      fT[MOM2] = 0.5 * (UR[MOM2] + U[MOM2]) * su;
+      fT[MOM3] = 0.5 * (UR[MOM3] + U[MOM3]) * su;
+      fT[ENER] = 0.5 * sE * su;
+      gT[DENS] = 0.5 * (UR[DENS] + U[DENS]) * sv;
+      gT[MOM1] = 0.5 * (UR[MOM1] + U[MOM1]) * sv;
+      gT[MOM2] = 0.5 * (UR[MOM2] + U[MOM2]) * sv + sp;
+      gT[MOM3] = 0.5 * (UR[MOM3] + U[MOM3]) * sv;
+      gT[ENER] = 0.5 * sE * sv;
+      hT[DENS] = 0.5 * (UR[DENS] + U[DENS]) * sw;
+      hT[MOM1] = 0.5 * (UR[MOM1] + U[MOM1]) * sw;
+      hT[MOM2] = 0.5 * (UR[MOM2] + U[MOM2]) * sw;
+      hT[MOM3] = 0.5 * (UR[MOM3] + U[MOM3]) * sw + sp;
+      hT[ENER] = 0.5 * sE * sw;
+    } break;
+    case FLEXI_SPLITDG_KG:   /* splitflux.f90:359-425 */
+    case FLEXI_SPLITDG_PI: { /* splitflux.f90:603-666 */
+      double sr = UR[DENS] + U[DENS], su = PR[VEL1] + P[VEL1], sv = PR[VEL2] + P[VEL2], sw = PR[VEL3] + P[VEL3];
+      double sp = PR[PRES] + P[PRES];
+      fT[DENS] = 0.5 * sr * su;
+      fT[MOM1] = 0.25 * sr * (su * su) + sp;
+      fT[MOM2] = 0.25 * sr * su * sv;
+      fT[MOM3] = 0.25 * sr * su * sw;
+      gT[DENS] = 0.5 * sr * sv;
+      gT[MOM1] = fT[MOM2];
+      gT[MOM2] = 0.25 * sr * (sv * sv) + sp;
+      gT[MOM3] = 0.25 * sr * sv * sw;
+      hT[DENS] = 0.5 * sr * sw;
+      hT[MOM1] = fT[MOM3];
+      hT[MOM2] = gT[MOM3];
+      hT[MOM3] = 0.25 * sr * (sw * sw) + sp;
+      if (type == FLEXI_SPLITDG_KG) {
+        double ERef = UR[ENER] / UR[DENS], E = U[ENER] / U[DENS];
+        fT[ENER] = 0.25 * sr * su * (ERef + E) + 0.5 * sp * su;
+        gT[ENER] = 0.25 * sr * sv * (ERef + E) + 0.5 * sp * sv;
+        hT[ENER] = 0.25 * sr * sw * (ERef + E) + 0.5 * sp * sw;
+      } else {
+        double HRef = (UR[ENER] + PR[PRES]) / UR[DENS], H = (U[ENER] + P[PRES]) / U[DENS];
+        fT[ENER] = 0.25 * sr * su * (HRef + H);
+        gT[ENER] = 0.25 * sr * sv * (HRef + H);
+        hT[ENER] = 0.25 * sr * sw * (HRef + H);
+      }
+    } break;
+    default:
+      fprintf(stderr, "oracle: SplitDG formulation %d not restated\n", type);
+      abort();
+  }
+  for (int v = 0; v < 5; ++v)
+    Flux[v] = 0.5 * (MR[0] + M[0]) * fT[v] + 0.5 * (MR[2] + M[2]) * hT[v] + 0.5 * (MR[1] + M[1]) * gT[v];
+}
+
+static void split_surface_flux(int type, const double* L, const double* R, double* F) {
+  switch (type) {
+    case FLEXI_SPLITDG_SD: /* splitflux.f90:228-252 */
+      F[DENS] = 0.5 * (L[EXT_MOM1] + R[EXT_MOM1]);
+      F[MOM1] = 0.5 * (L[EXT_MOM1] * L[EXT_VEL1] + L[EXT_PRES] + R[EXT_MOM1] * R[EXT_VEL1] + R[EXT_PRES]);
+      F[MOM2] = 0.5 * (L[EXT_MOM1] * L[EXT_VEL2] + R[EXT_MOM1] * R[EXT_VEL2]);
+      F[MOM3] = 0.5 * (L[EXT_MOM1] * L[EXT_VEL3] + R[EXT_MOM1] * R[EXT_VEL3]);
+      F[ENER] = 0.5 * ((L[EXT_ENER] + L[EXT_PRES]) * L[EXT_VEL1] + (R[EXT_ENER] + R[EXT_PRES]) * R[EXT_VEL1]);
+      break;
+    case FLEXI_SPLITDG_DU: /* splitflux.f90:326-349 */
+      F[DENS] = 0.25 * (L[EXT_DENS] + R[EXT_DENS]) * (L[EXT_VEL1] + R[EXT_VEL1]);
+      F[MOM1] = 0.25 * (L[EXT_MOM1] + R[EXT_MOM1]) * (L[EXT_VEL1] + R[EXT_VEL1]) + 0.5 * (L[EXT_PRES] + R[EXT_PRES]);
+      F[MOM2] = 0.25 * (L[EXT_MOM2] + R[EXT_MOM2]) * (L[EXT_VEL1] + R[EXT_VEL1]);
+      F[MOM3] = 0.25 * (L[EXT_MOM3] + R[EXT_MOM3]) * (L[EXT_VEL1] + R[EXT_VEL1]);
+      F[ENER] = 0.25 * (L[EXT_ENER] + R[EXT_ENER] + L[EXT_PRES] + R[EXT_PRES]) * (L[EXT_VEL1] + R[EXT_VEL1]);
+      break;
+    case FLEXI_SPLITDG_KG:   /* splitflux.f90:431-460 */
+    case FLEXI_SPLITDG_PI: { /* splitflux.f90:672-700 */
+      double sr = L[EXT_DENS] + R[EXT_DENS], su = L[EXT_VEL1] + R[EXT_VEL1];
+      F[DENS] = 0.25 * sr * su;
+      F[MOM1] = 0.125 * sr * (su * su) + 0.5 * (L[EXT_PRES] + R[EXT_PRES]);
+      F[MOM2] = 0.125 * sr * su * (L[EXT_VEL2] + R[EXT_VEL2]);
+      F[MOM3] = 0.125 * sr * su * (L[EXT_VEL3] + R[EXT_VEL3]);
+      if (type == FLEXI_SPLITDG_KG) {
+        double E_LL = L[EXT_ENER] / L[EXT_DENS], E_RR = R[EXT_ENER] / R[EXT_DENS];
+        F[ENER] = 0.125 * sr * (E_LL + E_RR) * su + 0.25 * (L[EXT_PRES] + R[EXT_PRES]) * su;
+      } else {
+        double H_LL = (L[EXT_ENER] + L[EXT_PRES]) / L[EXT_DENS], H_RR = (R[EXT_ENER] + R[EXT_PRES]) / R[EXT_DENS];
+        F[ENER] = 0.125 * sr * (H_LL + H_RR) * su;
+      }
+    } break;
+    default:
+      fprintf(stderr, "oracle: SplitDG formulation %d not restated\n", type);
+      abort();
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* Riemann solvers: riemann.f90                                                                                       */
+/* ------------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+  double RoeVel[3], RoeH, Roec, absVel, H_L, H_R;
+} roe_mean;
+
+static inline roe_mean roe_average(const oracle* o, const double* L, const double* R) {
+  roe_mean m;
+  m.H_L = (L[EXT_ENER] + L[EXT_PRES]) * L[EXT_SRHO]; /* TOTALENTHALPY_HE */
+  m.H_R = (R[EXT_ENER] + R[EXT_PRES]) * R[EXT_SRHO];
+  double SqrtRho_L = sqrt(L[EXT_DENS]), SqrtRho_R = sqrt(R[EXT_DENS]);
+  double sSqrtRho = 1. / (SqrtRho_L + SqrtRho_R);
+  for (int c = 0; c < 3; ++c) m.RoeVel[c] = (SqrtRho_R * R[EXT_VEL1 + c] + SqrtRho_L * L[EXT_VEL1 + c]) * sSqrtRho;
+  m.RoeH = (SqrtRho_R * m.H_R + SqrtRho_L * m.H_L) * sSqrtRho;
+  m.absVel = m.RoeVel[0] * m.RoeVel[0] + m.RoeVel[1] * m.RoeVel[1] + m.RoeVel[2] * m.RoeVel[2];
+  m.Roec = sqrt(o->kappaM1 * (m.RoeH - 0.5 * m.absVel)); /* ROEC_RIEMANN_H, eos.h:50 */
+  return m;
+}
+
+static inline double speed_of_sound_he(const oracle* o, const double* UE) { return sqrt(o->d.kappa * UE[EXT_PRES] * UE[EXT_SRHO]); }
+
+static void roe_eigenvectors(const roe_mean* m, double* a, double* r1, double* r2, double* r3, double* r4, double* r5) {
+  const double* v = m->RoeVel;
+  a[0] = v[0] - m->Roec; a[1] = v[0]; a[2] = v[0]; a[3] = v[0]; a[4] = v[0] + m->Roec;
+  r1[0] = 1.; r1[1] = a[0]; r1[2] = v[1]; r1[3] = v[2]; r1[4] = m->RoeH - v[0] * m->Roec;
+  r2[0] = 1.; r2[1] = v[0]; r2[2] = v[1]; r2[3] = v[2]; r2[4] = 0.5 * m->absVel;
+  r3[0] = 0.; r3[1] = 0.; r3[2] = 1.; r3[3] = 0.; r3[4] = v[1];
+  r4[0] = 0.; r4[1] = 0.; r4[2] = 0.; r4[3] = 1.; r4[4] = v[2];
+  r5[0] = 1.; r5[1] = a[4]; r5[2] = v[1]; r5[3] = v[2]; r5[4] = m->RoeH + v[0] * m->Roec;
+}
+
+/* The solver proper. split != 0 selects the SPLIT_DG variants (central part = two-point surface flux). */
+static void riemann_solver(const oracle* o, int solver, const double* F_L, const double* F_R, const double* L, const double* R,
+                           double* F) {
+  const int split = o->d.splitDG;
+  const int stype = o->d.splitDGType;
+  switch (solver) {
+    case FLEXI_RIEMANN_LF: { /* riemann.f90:558-589 */
+      double LambdaMax = fmax(fabs(R[EXT_VEL1]), fabs(L[EXT_VEL1])) + fmax(speed_of_sound_he(o, L), speed_of_sound_he(o, R));
+      if (!split) {
+        for (int v = 0; v < 5; ++v) F[v] = 0.5 * ((F_L[v] + F_R[v]) - LambdaMax * (R[v] - L[v]));
+      } else {
+        split_surface_flux(stype, L, R, F);
+        for (int v = 0; v < 5; ++v) F[v] = F[v] - 0.5 * LambdaMax * (R[v] - L[v]);
+      }
+    } break;
+    case FLEXI_RIEMANN_HLLC: { /* riemann.f90:594-663 (Version C wave speeds) */
+      roe_mean m = roe_average(o, L, R);
+      double Ssl = m.RoeVel[0] - m.Roec, Ssr = m.RoeVel[0] + m.Roec;
+      if (Ssl >= 0.) {
+        for (int v = 0; v < 5; ++v) F[v] = F_L[v];
+      } else if (Ssr <= 0.) {
+        for (int v = 0; v < 5; ++v) F[v] = F_R[v];
+      } else {
+        double sMu_L = Ssl - L[EXT_VEL1], sMu_R = Ssr - R[EXT_VEL1];
+        double SStar = (R[EXT_PRES] - L[EXT_PRES] + L[EXT_MOM1] * sMu_L - R[EXT_MOM1] * sMu_R) /
+                       (L[EXT_DENS] * sMu_L - R[EXT_DENS] * sMu_R);
+        double U_Star[5];
+        if ((Ssl <= 0.) && (SStar >= 0.)) {
+          double EStar = L[EXT_ENER] * L[EXT_SRHO] + (SStar - L[EXT_VEL1]) * (SStar + L[EXT_PRES] * L[EXT_SRHO] / sMu_L);
+          double fac = L[EXT_DENS] * sMu_L / (Ssl - SStar);
+          U_Star[0] = fac * 1.; U_Star[1] = fac * SStar; U_Star[2] = fac * L[EXT_VEL2]; U_Star[3] = fac * L[EXT_VEL3];
+          U_Star[4] = fac * EStar;
+          for (int v = 0; v < 5; ++v) F[v] = F_L[v] + Ssl * (U_Star[v] - L[v]);
+        } else {
+          double EStar = R[EXT_ENER] * R[EXT_SRHO] + (SStar - R[EXT_VEL1]) * (SStar + R[EXT_PRES] * R[EXT_SRHO] / sMu_R);
+          double fac = R[EXT_DENS] * sMu_R / (Ssr - SStar);
+          U_Star[0] = fac * 1.; U_Star[1] = fac * SStar; U_Star[2] = fac * R[EXT_VEL2]; U_Star[3] = fac * R[EXT_VEL3];
+          U_Star[4] = fac * EStar;
+          for (int v = 0; v < 5; ++v) F[v] = F_R[v] + Ssr * (U_Star[v] - R[v]);
+        }
+      }
+    } break;
+    case FLEXI_RIEMANN_ROE:     /* riemann.f90:668-740 */
+    case FLEXI_RIEMANN_ROEL2: { /* riemann.f90:983-1061 */
+      roe_mean m = roe_average(o, L, R);
+      double a[5], r1[5], r2[5], r3[5], r4[5], r5[5], dU[6];
+      roe_eigenvectors(&m, a, r1, r2, r3, r4, r5);
+      for (int v = 0; v < 5; ++v) dU[v] = R[v] - L[v];
+      dU[5] = dU[4] - (dU[2] - m.RoeVel[1] * dU[0]) * m.RoeVel[1] - (dU[3] - m.RoeVel[2] * dU[0]) * m.RoeVel[2];
+      if (solver == FLEXI_RIEMANN_ROEL2) {
+        double Ma_loc = sqrt(m.absVel) / (m.Roec * sqrt(o->d.kappa));
+        dU[1] *= Ma_loc; dU[2] *= Ma_loc; dU[3] *= Ma_loc;
+      }
+      double Alpha3 = dU[2] - m.RoeVel[1] * dU[0];
+      double Alpha4 = dU[3] - m.RoeVel[2] * dU[0];
+      /* ALPHA2_RIEMANN_H, eos.h:51 */
+      double Alpha2 = o->kappaM1 / (m.Roec * m.Roec) * (dU[0] * (m.RoeH - m.RoeVel[0] * m.RoeVel[0]) - dU[5] + m.RoeVel[0] * dU[1]);
+      double Alpha1 = 0.5 / m.Roec * (dU[0] * (m.RoeVel[0] + m.Roec) - dU[1] - m.Roec * Alpha2);
+      double Alpha5 = dU[0] - Alpha1 - Alpha2;
+      if (!split) {
+        for (int v = 0; v < 5; ++v)
+          F[v] = 0.5 * ((F_L[v] + F_R[v]) - Alpha1 * fabs(a[0]) * r1[v] - Alpha2 * fabs(a[1]) * r2[v] - Alpha3 * fabs(a[2]) * r3[v] -
+                        Alpha4 * fabs(a[3]) * r4[v] - Alpha5 * fabs(a[4]) * r5[v]);
+      } else {
+        split_surface_flux(stype, L, R, F);
+        for (int v = 0; v < 5; ++v)
+          F[v] = F[v] - 0.5 * (Alpha1 * fabs(a[0]) * r1[v] + Alpha2 * fabs(a[1]) * r2[v] + Alpha3 * fabs(a[2]) * r3[v] +
+                               Alpha4 * fabs(a[3]) * r4[v] + Alpha5 * fabs(a[4]) * r5[v]);
+      }
+    } break;
+    case FLEXI_RIEMANN_ROEENTROPYFIX: { /* riemann.f90:748-855 */
+      double c_L = speed_of_sound_he(o, L), c_R = speed_of_sound_he(o, R);
+      roe_mean m = roe_average(o, L, R);
+      double RoeDens = sqrt(L[EXT_DENS] * R[EXT_DENS]);
+      double dU[5], a[5], r1[5], r2[5], r3[5], r4[5], r5[5], Alpha[5], al[5], ar[5];
+      dU[0] = R[EXT_DENS] - L[EXT_DENS];
+      dU[1] = R[EXT_VEL1] - L[EXT_VEL1];
+      dU[2] = R[EXT_VEL2] - L[EXT_VEL2];
+      dU[3] = R[EXT_VEL3] - L[EXT_VEL3];
+      dU[4] = R[EXT_PRES] - L[EXT_PRES];
+      roe_eigenvectors(&m, a, r1, r2, r3, r4, r5);
+      double tmp = 0.5 / (m.Roec * m.Roec);
+      Alpha[0] = tmp * (dU[4] - RoeDens * m.Roec * dU[1]);
+      Alpha[1] = dU[0] - dU[4] * 2. * tmp;
+      Alpha[2] = RoeDens * dU[2];
+      Alpha[3] = RoeDens * dU[3];
+      Alpha[4] = tmp * (dU[4] + RoeDens * m.Roec * dU[1]);
+      al[0] = L[EXT_VEL1] - c_L; al[1] = al[2] = al[3] = L[EXT_VEL1]; al[4] = L[EXT_VEL1] + c_L;
+      ar[0] = R[EXT_VEL1] - c_R; ar[1] = ar[2] = ar[3] = R[EXT_VEL1]; ar[4] = R[EXT_VEL1] + c_R;
+      for (int iVar = 0; iVar < 5; ++iVar) { /* Harten-Hyman 2 */
+        double da = fmax(0., fmax(a[iVar] - al[iVar], ar[iVar] - a[iVar]));
+        if (fabs(a[iVar]) < da)
+          a[iVar] = 0.5 * (a[iVar] * a[iVar] / da + da);
+        else
+          a[iVar] = fabs(a[iVar]);
+      }
+      if (!split) {
+        for (int v = 0; v < 5; ++v)
+          F[v] = 0.5 * ((F_L[v] + F_R[v]) - Alpha[0] * a[0] * r1[v] - Alpha[1] * a[1] * r2[v] - Alpha[2] * a[2] * r3[v] -
+                        Alpha[3] * a[3] * r4[v] - Alpha[4] * a[4] * r5[v]);
+      } else {
+        split_surface_flux(stype, L, R, F);
+        for (int v = 0; v < 5; ++v)
+          F[v] = F[v] - 0.5 * (Alpha[0] * a[0] * r1[v] + Alpha[1] * a[1] * r2[v] + Alpha[2] * a[2] * r3[v] + Alpha[3] * a[3] * r4[v] +
+                               Alpha[4] * a[4] * r5[v]);
+      }
+    } break;
+    case FLEXI_RIEMANN_HLL:     /* riemann.f90:1067-1113 */
+    case FLEXI_RIEMANN_HLLE:    /* riemann.f90:1119-1164 */
+    case FLEXI_RIEMANN_HLLEM: { /* riemann.f90:1170-1228 */
+      roe_mean m = roe_average(o, L, R);
+      double Ssl, Ssr;
+      if (solver == FLEXI_RIEMANN_HLL) {
+        Ssl = m.RoeVel[0] - m.Roec;
+        Ssr = m.RoeVel[0] + m.Roec;
+      } else {
+        double beta = sqrt(0.5 * o->kappaM1 / o->d.kappa); /* BETA_RIEMANN_H, eos.h:49 */
+        Ssl = fmin(fmin(m.RoeVel[0] - m.Roec, L[EXT_VEL1] - beta * speed_of_sound_he(o, L)), 0.);
+        Ssr = fmax(fmax(m.RoeVel[0] + m.Roec, R[EXT_VEL1] + beta * speed_of_sound_he(o, R)), 0.);
+      }
+      if (Ssl >= 0.) {
+        for (int v = 0; v < 5; ++v) F[v] = F_L[v];
+      } else if (Ssr <= 0.) {
+        for (int v = 0; v < 5; ++v) F[v] = F_R[v];
+      } else if (solver != FLEXI_RIEMANN_HLLEM) {
+        for (int v = 0; v < 5; ++v) F[v] = (Ssr * F_L[v] - Ssl * F_R[v] + Ssl * Ssr * (R[v] - L[v])) / (Ssr - Ssl);
+      } else {
+        double RoeDens = sqrt(L[EXT_DENS] * R[EXT_DENS]);
+        double delta = m.Roec / (m.Roec + fabs(0.5 * (Ssl + Ssr)));
+        double A2 = (R[EXT_DENS] - L[EXT_DENS]) - (R[EXT_PRES] - L[EXT_PRES]) / (m.Roec * m.Roec);
+        double A3 = RoeDens * (R[EXT_VEL2] - L[EXT_VEL2]), A4 = RoeDens * (R[EXT_VEL3] - L[EXT_VEL3]);
+        double r2[5] = {1., m.RoeVel[0], m.RoeVel[1], m.RoeVel[2], 0.5 * m.absVel};
+        double r3[5] = {0., 0., 1., 0., m.RoeVel[1]};
+        double r4[5] = {0., 0., 0., 1., m.RoeVel[2]};
+        for (int v = 0; v < 5; ++v)
+          F[v] = (Ssr * F_L[v] - Ssl * F_R[v] + Ssl * Ssr * (R[v] - L[v] - delta * (r2[v] * A2 + r3[v] * A3 + r4[v] * A4))) / (Ssr - Ssl);
+      }
+    } break;
+    default:
+      fprintf(stderr, "oracle: Riemann solver %d not restated\n", solver);
+      abort();
+  }
+}
+
+/* riemann.f90:360-440 Riemann_Point (rotation, solver, back rotation) */
+static void riemann_point(const oracle* o, int solver, double* FOut, const double* U_L, const double* U_R, const double* UPrim_L,
+                          const double* UPrim_R, const double* nv, const double* t1, const double* t2) {
+  double U_LL[11], U_RR[11], F_L[5] = {0, 0, 0, 0, 0}, F_R[5] = {0, 0, 0, 0, 0}, F[5];
+  U_LL[EXT_DENS] = U_L[DENS];
+  U_LL[EXT_SRHO] = 1. / U_LL[EXT_DENS];
+  U_LL[EXT_ENER] = U_L[ENER];
+  U_LL[EXT_PRES] = UPrim_L[PRES];
+  U_LL[EXT_VEL1] = UPrim_L[VEL1] * nv[0] + UPrim_L[VEL2] * nv[1] + UPrim_L[VEL3] * nv[2];
+  U_LL[EXT_VEL2] = UPrim_L[VEL1] * t1[0] + UPrim_L[VEL2] * t1[1] + UPrim_L[VEL3] * t1[2];
+  U_LL[EXT_MOM1] = U_LL[EXT_DENS] * U_LL[EXT_VEL1];
+  U_LL[EXT_MOM2] = U_LL[EXT_DENS] * U_LL[EXT_VEL2];
+  U_LL[EXT_VEL3] = UPrim_L[VEL1] * t2[0] + UPrim_L[VEL2] * t2[1] + UPrim_L[VEL3] * t2[2];
+  U_LL[EXT_MOM3] = U_LL[EXT_DENS] * U_LL[EXT_VEL3];
+  U_LL[EXT_TEMP] = 0.;
+  U_RR[EXT_DENS] = U_R[DENS];
+  U_RR[EXT_SRHO] = 1. / U_RR[EXT_DENS];
+  U_RR[EXT_ENER] = U_R[ENER];
+  U_RR[EXT_PRES] = UPrim_R[PRES];
+  U_RR[EXT_VEL1] = UPrim_R[VEL1] * nv[0] + UPrim_R[VEL2] * nv[1] + UPrim_R[VEL3] * nv[2];
+  U_RR[EXT_VEL2] = UPrim_R[VEL1] * t1[0] + UPrim_R[VEL2] * t1[1] + UPrim_R[VEL3] * t1[2];
+  U_RR[EXT_MOM1] = U_RR[EXT_DENS] * U_RR[EXT_VEL1];
+  U_RR[EXT_MOM2] = U_RR[EXT_DENS] * U_RR[EXT_VEL2];
+  U_RR[EXT_VEL3] = UPrim_R[VEL1] * t2[0] + UPrim_R[VEL2] * t2[1] + UPrim_R[VEL3] * t2[2];
+  U_RR[EXT_MOM3] = U_RR[EXT_DENS] * U_RR[EXT_VEL3];
+  U_RR[EXT_TEMP] = 0.;
+  if (!o->d.splitDG) { /* riemann.f90:333-336: F_L/F_R are only formed without SPLIT_DG */
+    eval_euler_flux1d_fast(U_LL, F_L);
+    eval_euler_flux1d_fast(U_RR, F_R);
+  }
+  riemann_solver(o, solver, F_L, F_R, U_LL, U_RR, F);
+  FOut[DENS] = F[DENS];
+  for (int c = 0; c < 3; ++c) FOut[MOM1 + c] = nv[c] * F[MOM1] + t1[c] * F[MOM2] + t2[c] * F[MOM3];
+  FOut[ENER] = F[ENER];
+}
+
+/* riemann.f90:506-551 ViscousFlux_Point */
+static void viscous_flux_point(const oracle* o, double* F, const double* UPrim_L, const double* UPrim_R, const double* gx_L,
+                               const double* gy_L, const double* gz_L, const double* gx_R, const double* gy_R, const double* gz_R,
+                               const double* nv) {
+  double fL[5], gL[5], hL[5], fR[5], gR[5], hR[5];
+  eval_diff_flux3d(o, UPrim_L, gx_L, gy_L, gz_L, fL, gL, hL);
+  eval_diff_flux3d(o, UPrim_R, gx_R, gy_R, gz_R, fR, gR, hR);
+  for (int v = 0; v < 5; ++v) F[v] = 0.5 * (nv[0] * (fL[v] + fR[v]) + nv[1] * (gL[v] + gR[v]) + nv[2] * (hL[v] + hR[v]));
+}
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* ProlongToFace: interpolation/prolongtoface.t90:21-303                                                              */
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* EvalElemFaceG (:211-264) / EvalElemFaceGL (:270-303): Uface(v,a,b) of one element and local side */
+static void eval_elem_face(const oracle* o, int nv, const double* Uvol_e, double* Uface, int locSide) {
+  const int np = o->np, N = np - 1;
+  const double* Lm = o->d.L_Minus;
+  const double* Lp = o->d.L_Plus;
+#define UE(v, i, j, k) Uvol_e[((((size_t)(k)) * np + (j)) * np + (i)) * nv + (v)]
+#define UF(v, a, b) Uface[(((size_t)(b)) * np + (a)) * nv + (v)]
+  if (o->d.nodeType == FLEXI_NODETYPE_GAUSS) {
+    const double* L = (locSide == XI_MINUS || locSide == ETA_MINUS || locSide == ZETA_MINUS) ? Lm : Lp;
+    for (int b = 0; b < np; ++b)
+      for (int a = 0; a < np; ++a)
+        for (int v = 0; v < nv; ++v) {
+          double s;
+          switch (locSide) {
+            case XI_MINUS: case XI_PLUS:
+              s = UE(v, 0, a, b) * L[0];
+              for (int l = 1; l <= N; ++l) s = s + UE(v, l, a, b) * L[l];
+              break;
+            case ETA_MINUS: case ETA_PLUS:
+              s = UE(v, a, 0, b) * L[0];
+              for (int l = 1; l <= N; ++l) s = s + UE(v, a, l, b) * L[l];
+              break;
+            default:
+              s = UE(v, a, b, 0) * L[0];
+              for (int l = 1; l <= N; ++l) s = s + UE(v, a, b, l) * L[l];
+          }
+          UF(v, a, b) = s;
+        }
+  } else {
+    for (int b = 0; b < np; ++b)
+      for (int a = 0; a < np; ++a)
+        for (int v = 0; v < nv; ++v) {
+          switch (locSide) {
+            case XI_MINUS: UF(v, a, b) = UE(v, 0, a, b); break;
+            case XI_PLUS: UF(v, a, b) = UE(v, N, a, b); break;
+            case ETA_MINUS: UF(v, a, b) = UE(v, a, 0, b); break;
+            case ETA_PLUS: UF(v, a, b) = UE(v, a, N, b); break;
+            case ZETA_MINUS: UF(v, a, b) = UE(v, a, b, 0); break;
+            default: UF(v, a, b) = UE(v, a, b, N);
+          }
+        }
+  }
+#undef UE
+}
+
+/* ProlongToFace (:21-144) */
+static void prolong_to_face(const oracle* o, int nv, const double* Uvol, double* Uface_master, double* Uface_slave, int doMPISides) {
+  const int np = o->np;
+  int firstSideID, lastSideID;
+  if (doMPISides) {
+    firstSideID = o->firstMPISide_YOUR;
+    lastSideID = o->d.nSides;
+  } else {
+    firstSideID = 1;
+    lastSideID = o->lastMPISide_MINE;
+  }
+  double* Uface = (double*)xcalloc((size_t)np * np * nv, sizeof(double));
+  const size_t esz = (size_t)np * np * np * nv;
+  for (int SideID = firstSideID; SideID <= lastSideID; ++SideID) {
+    const int s = SideID - 1;
+    int ElemID = S2E(0, s), nbElemID = S2E(1, s);
+    if (ElemID > 0) {
+      int locSide = S2E(2, s);
+      eval_elem_face(o, nv, Uvol + (size_t)(ElemID - 1) * esz, Uface, locSide);
+      for (int q = 0; q < np; ++q)
+        for (int p = 0; p < np; ++p)
+          for (int v = 0; v < nv; ++v) SID(Uface_master, nv, v, p, q, s) = UF(v, S2V2(0, p, q, 0, locSide), S2V2(1, p, q, 0, locSide));
+    }
+    if (nbElemID > 0) {
+      int nblocSide = S2E(3, s), flip = S2E(4, s);
+      eval_elem_face(o, nv, Uvol + (size_t)(nbElemID - 1) * esz, Uface, nblocSide);
+      for (int q = 0; q < np; ++q)
+        for (int p = 0; p < np; ++p)
+          for (int v = 0; v < nv; ++v)
+            SID(Uface_slave, nv, v, p, q, s) = UF(v, S2V2(0, p, q, flip, nblocSide), S2V2(1, p, q, flip, nblocSide));
+    }
+  }
+  free(Uface);
+}
+#undef UF
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* SurfInt: dg/surfint.t90 (non-split Gauss :21-239, Gauss-Lobatto :475-616, DoSurfInt :683-766)                      */
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* DoSurfInt: Flux in the volume system of the element; Ut_e = Ut(:,:,:,:,ElemID) */
+static void do_surf_int(const oracle* o, int nv, const double* Flux, const double* L_HatMinus, const double* L_HatPlus, int locSide,
+                        double* Ut_e, int full_line) {
+  const int np = o->np, N = np - 1;
+#define UTE(v, i, j, k) Ut_e[((((size_t)(k)) * np + (j)) * np + (i)) * nv + (v)]
+#define FL(v, a, b) Flux[(((size_t)(b)) * np + (a)) * nv + (v)]
+  if (full_line) { /* PP_NodeType==1 (or EXACT_MM): all nodes on the line, surfint.t90:713-737 */
+    const double* LH = (locSide == XI_MINUS || locSide == ETA_MINUS || locSide == ZETA_MINUS) ? L_HatMinus : L_HatPlus;
+    switch (locSide) {
+      case XI_MINUS: case XI_PLUS:
+        for (int k = 0; k < np; ++k) for (int j = 0; j < np; ++j) for (int l = 0; l < np; ++l)
+          for (int v = 0; v < nv; ++v) UTE(v, l, j, k) = UTE(v, l, j, k) + FL(v, j, k) * LH[l];
+        break;
+      case ETA_MINUS: case ETA_PLUS:
+        for (int k = 0; k < np; ++k) for (int l = 0; l < np; ++l) for (int i = 0; i < np; ++i)
+          for (int v = 0; v < nv; ++v) UTE(v, i, l, k) = UTE(v, i, l, k) + FL(v, i, k) * LH[l];
+        break;
+      default:
+        for (int l = 0; l < np; ++l) for (int j = 0; j < np; ++j) for (int i = 0; i < np; ++i)
+          for (int v = 0; v < nv; ++v) UTE(v, i, j, l) = UTE(v, i, j, l) + FL(v, i, j) * LH[l];
+    }
+  } else { /* PP_NodeType==2 without EXACT_MM: boundary node only, surfint.t90:738-762 */
+    const double lm = L_HatMinus[0], lp = L_HatPlus[N];
+    switch (locSide) {
+      case XI_MINUS:
+        for (int k = 0; k < np; ++k) for (int j = 0; j < np; ++j) for (int v = 0; v < nv; ++v) UTE(v, 0, j, k) = UTE(v, 0, j, k) + FL(v, j, k) * lm;
+        break;
+      case ETA_MINUS:
+        for (int k = 0; k < np; ++k) for (int i = 0; i < np; ++i) for (int v = 0; v < nv; ++v) UTE(v, i, 0, k) = UTE(v, i, 0, k) + FL(v, i, k) * lm;
+        break;
+      case ZETA_MINUS:
+        for (int j = 0; j < np; ++j) for (int i = 0; i < np; ++i) for (int v = 0; v < nv; ++v) UTE(v, i, j, 0) = UTE(v, i, j, 0) + FL(v, i, j) * lm;
+        break;
+      case XI_PLUS:
+        for (int k = 0; k < np; ++k) for (int j = 0; j < np; ++j) for (int v = 0; v < nv; ++v) UTE(v, N, j, k) = UTE(v, N, j, k) + FL(v, j, k) * lp;
+        break;
+      case ETA_PLUS:
+        for (int k = 0; k < np; ++k) for (int i = 0; i < np; ++i) for (int v = 0; v < nv; ++v) UTE(v, i, N, k) = UTE(v, i, N, k) + FL(v, i, k) * lp;
+        break;
+      default:
+        for (int j = 0; j < np; ++j) for (int i = 0; i < np; ++i) for (int v = 0; v < nv; ++v) UTE(v, i, j, N) = UTE(v, i, j, N) + FL(v, i, j) * lp;
+    }
+  }
+#undef UTE
+#undef FL
+}
+
+/* SurfInt for nv variables. slave_sign = -1 for the DG operator (surfint.t90:583), +1 for strong-form BR1 lifting
+ * (lifting_br1.t90:270-281). L_Hat* are passed in because the GL unit-test fixture feeds Gauss L_Hat. */
+static void surf_int(const oracle* o, int nv, const double* Flux_master, const double* Flux_slave, double* Ut, int doMPISides,
+                     const double* L_HatMinus, const double* L_HatPlus, double slave_sign) {
+  const int np = o->np;
+  int firstSideID, lastSideID;
+  if (doMPISides) {
+    firstSideID = o->firstMPISide_YOUR;
+    lastSideID = o->d.nSides;
+  } else {
+    firstSideID = 1;
+    lastSideID = o->lastMPISide_MINE;
+  }
+  const int full_line = (o->d.nodeType == FLEXI_NODETYPE_GAUSS);
+  double* FluxTmp = (double*)xcalloc((size_t)np * np * nv, sizeof(double));
+  const size_t esz = (size_t)np * np * np * nv;
+  for (int SideID = firstSideID; SideID <= lastSideID; ++SideID) {
+    const int s = SideID - 1;
+    int ElemID = S2E(0, s), nbElemID = S2E(1, s);
+    if (ElemID > 0) {
+      int locSideID = S2E(2, s);
+      for (int q = 0; q < np; ++q)
+        for (int p = 0; p < np; ++p)
+          for (int v = 0; v < nv; ++v)
+            FluxTmp[(((size_t)S2V2(1, p, q, 0, locSideID)) * np + S2V2(0, p, q, 0, locSideID)) * nv + v] = SID(Flux_master, nv, v, p, q, s);
+      do_surf_int(o, nv, FluxTmp, L_HatMinus, L_HatPlus, locSideID, Ut + (size_t)(ElemID - 1) * esz, full_line);
+    }
+    if (nbElemID > 0) {
+      int nblocSideID = S2E(3, s), flip = S2E(4, s);
+      for (int q = 0; q < np; ++q)
+        for (int p = 0; p < np; ++p)
+          for (int v = 0; v < nv; ++v)
+            FluxTmp[(((size_t)S2V2(1, p, q, flip, nblocSideID)) * np + S2V2(0, p, q, flip, nblocSideID)) * nv + v] =
+                slave_sign * SID(Flux_slave, nv, v, p, q, s);
+      do_surf_int(o, nv, FluxTmp, L_HatMinus, L_HatPlus, nblocSideID, Ut + (size_t)(nbElemID - 1) * esz, full_line);
+    }
+  }
+  free(FluxTmp);
+}
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* volume primitive state and face primitive state                                                                    */
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* eos.f90:280-300 ConsToPrim_Volume */
+static void cons_to_prim_volume(oracle* o) {
+  const size_t n = (size_t)o->d.nElems * o->np * o->np * o->np;
+  for (size_t i = 0; i < n; ++i) cons_to_prim(o, o->UPrim + i * NPRIM, o->U + i * NVAR);
+}
+
+/* equation.f90:189-216 GetPrimitiveStateSurface */
+static void get_primitive_state_surface(oracle* o) {
+  const int np = o->np;
+  const size_t fs = (size_t)np * np;
+  for (int iSide = 1; iSide <= o->d.nSides; ++iSide) {
+    if (iSide >= o->firstMPISide_YOUR && iSide <= o->lastMPISide_YOUR) continue;
+    for (size_t i = 0; i < fs; ++i)
+      cons_to_prim(o, o->UPrim_master + ((size_t)(iSide - 1) * fs + i) * NPRIM, o->U_master + ((size_t)(iSide - 1) * fs + i) * NVAR);
+  }
+  for (int iSide = o->firstInnerSide; iSide <= o->lastMPISide_YOUR; ++iSide)
+    for (size_t i = 0; i < fs; ++i)
+      cons_to_prim(o, o->UPrim_slave + ((size_t)(iSide - 1) * fs + i) * NPRIM, o->U_slave + ((size_t)(iSide - 1) * fs + i) * NVAR);
+}
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* Lifting: dg/lifting/ (.t90)                                                                                            */
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* lifting_volint.t90:26-118 Lifting_VolInt_Nonconservative */
+static void lifting_volint_nonconservative(oracle* o) {
+  const int np = o->np, N = np - 1, nvl = o->nvl;
+  const double* D_T = o->d.D_T;
+  for (int e = 0; e < o->d.nElems; ++e)
+    for (int k = 0; k < np; ++k)
+      for (int j = 0; j < np; ++j)
+        for (int i = 0; i < np; ++i) {
+          double gxi[5], geta[5], gzeta[5];
+          for (int v = 0; v < nvl; ++v) {
+            const int pv = o->lift_map[v];
+            gxi[v] = MAT(D_T, 0, i) * VOL(o->UPrim, NPRIM, pv, 0, j, k, e);
+            geta[v] = MAT(D_T, 0, j) * VOL(o->UPrim, NPRIM, pv, i, 0, k, e);
+            gzeta[v] = MAT(D_T, 0, k) * VOL(o->UPrim, NPRIM, pv, i, j, 0, e);
+            for (int l = 1; l <= N; ++l) {
+              gxi[v] = gxi[v] + MAT(D_T, l, i) * VOL(o->UPrim, NPRIM, pv, l, j, k, e);
+              geta[v] = geta[v] + MAT(D_T, l, j) * VOL(o->UPrim, NPRIM, pv, i, l, k, e);
+              gzeta[v] = gzeta[v] + MAT(D_T, l, k) * VOL(o->UPrim, NPRIM, pv, i, j, l, e);
+            }
+          }
+          const double* Mf = &VOL(o->d.Metrics_fTilde, 3, 0, i, j, k, e);
+          const double* Mg = &VOL(o->d.Metrics_gTilde, 3, 0, i, j, k, e);
+          const double* Mh = &VOL(o->d.Metrics_hTilde, 3, 0, i, j, k, e);
+          for (int v = 0; v < nvl; ++v) {
+            VOL(o->gradUx, nvl, v, i, j, k, e) = Mf[0] * gxi[v] + Mg[0] * geta[v] + Mh[0] * gzeta[v];
+            VOL(o->gradUy, nvl, v, i, j, k, e) = Mf[1] * gxi[v] + Mg[1] * geta[v] + Mh[1] * gzeta[v];
+            VOL(o->gradUz, nvl, v, i, j, k, e) = Mf[2] * gxi[v] + Mg[2] * geta[v] + Mh[2] * gzeta[v];
+          }
+        }
+}
+
+/* lifting_fillflux.t90:40-107 Lifting_FillFlux (dir=0: BR1; dir=1..3: BR2), strong form (sig=-1) */
+static void lifting_fill_flux(oracle* o, int dir, double* Flux, int doMPISides) {
+  const int np = o->np, nvl = o->nvl;
+  int firstSideID = doMPISides ? o->firstMPISide_MINE : o->firstInnerSide;
+  int lastSideID = doMPISides ? o->lastMPISide_MINE : o->lastInnerSide;
+  const double sig = -1.;
+  for (int SideID = firstSideID; SideID <= lastSideID; ++SideID) {
+    const int s = SideID - 1;
+    for (int q = 0; q < np; ++q)
+      for (int p = 0; p < np; ++p)
+        for (int v = 0; v < nvl; ++v) {
+          const int pv = o->lift_map[v];
+          double fl = sig * SID(o->UPrim_master, NPRIM, pv, p, q, s) + SID(o->UPrim_slave, NPRIM, pv, p, q, s);
+          double surf = o->d.SurfElem[((size_t)s * np + q) * np + p];
+          if (dir == 0)
+            SID(Flux, nvl, v, p, q, s) = 0.5 * fl * surf;
+          else
+            SID(Flux, nvl, v, p, q, s) = 0.5 * fl * SID(o->d.NormVec, 3, dir - 1, p, q, s) * surf;
+        }
+  }
+}
+
+/* lifting_fillflux.t90:189-239 Lifting_FillFlux_NormVec */
+static void lifting_fill_flux_normvec(oracle* o, const double* Flux, double* FluxX, double* FluxY, double* FluxZ, int doMPISides) {
+  const int np = o->np, nvl = o->nvl;
+  int firstSideID = doMPISides ? o->firstMPISide_YOUR : 1;
+  int lastSideID = doMPISides ? o->lastMPISide_YOUR : o->lastMPISide_MINE;
+  for (int SideID = firstSideID; SideID <= lastSideID; ++SideID) {
+    const int s = SideID - 1;
+    for (int q = 0; q < np; ++q)
+      for (int p = 0; p < np; ++p)
+        for (int v = 0; v < nvl; ++v) {
+          double f = SID(Flux, nvl, v, p, q, s);
+          SID(FluxX, nvl, v, p, q, s) = f * SID(o->d.NormVec, 3, 0, p, q, s);
+          SID(FluxY, nvl, v, p, q, s) = f * SID(o->d.NormVec, 3, 1, p, q, s);
+          SID(FluxZ, nvl, v, p, q, s) = f * SID(o->d.NormVec, 3, 2, p, q, s);
+        }
+  }
+}
+
+/* applyjacobian.t90:62-112 ApplyJacobian (toPhysical) */
+static void apply_jacobian(const oracle* o, int nv, double* A) {
+  const size_t n = (size_t)o->d.nElems * o->np * o->np * o->np;
+  for (size_t i = 0; i < n; ++i)
+    for (int v = 0; v < nv; ++v) A[i * nv + v] = A[i * nv + v] * o->d.sJ[i];
+}
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* VolInt: dg/volint.f90                                                                                              */
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* EvalFlux3D + EvalDiffFlux3D + VolInt_Metrics (volint.f90:378-422) of one element into f,g,h(5,i,j,k) */
+static void volint_fluxes(const oracle* o, int e, int advective, int viscous, double* f, double* g, double* h) {
+  const int np = o->np, nvl = o->nvl;
+  for (int k = 0; k < np; ++k)
+    for (int j = 0; j < np; ++j)
+      for (int i = 0; i < np; ++i) {
+        double fa[5] = {0, 0, 0, 0, 0}, ga[5] = {0, 0, 0, 0, 0}, ha[5] = {0, 0, 0, 0, 0};
+        const double* U = &VOL(o->U, NVAR, 0, i, j, k, e);
+        const double* P = &VOL(o->UPrim, NPRIM, 0, i, j, k, e);
+        if (advective) eval_flux3d(U, P, fa, ga, ha);
+        if (viscous) {
+          double fv[5], gv[5], hv[5];
+          eval_diff_flux3d(o, P, &VOL(o->gradUx, nvl, 0, i, j, k, e), &VOL(o->gradUy, nvl, 0, i, j, k, e),
+                           &VOL(o->gradUz, nvl, 0, i, j, k, e), fv, gv, hv);
+          for (int v = 0; v < 5; ++v) {
+            fa[v] = fa[v] + fv[v];
+            ga[v] = ga[v] + gv[v];
+            ha[v] = ha[v] + hv[v];
+          }
+        }
+        const double* Mf = &VOL(o->d.Metrics_fTilde, 3, 0, i, j, k, e);
+        const double* Mg = &VOL(o->d.Metrics_gTilde, 3, 0, i, j, k, e);
+        const double* Mh = &VOL(o->d.Metrics_hTilde, 3, 0, i, j, k, e);
+        const size_t n = (((size_t)k * np + j) * np + i) * 5;
+        for (int v = 0; v < 5; ++v) {
+          f[n + v] = fa[v] * Mf[0] + ga[v] * Mf[1] + ha[v] * Mf[2];
+          g[n + v] = fa[v] * Mg[0] + ga[v] * Mg[1] + ha[v] * Mg[2];
+          h[n + v] = fa[v] * Mh[0] + ga[v] * Mh[1] + ha[v] * Mh[2];
+        }
+      }
+}
+
+/* volint.f90:117-187 VolInt_weakForm */
+static void volint_weak_form(oracle* o) {
+  const int np = o->np, N = np - 1;
+  const double* DH = o->d.D_Hat_T;
+  const size_t esz = (size_t)np * np * np * 5;
+  double* f = (double*)xcalloc(3 * esz, sizeof(double));
+  double *g = f + esz, *h = g + esz;
+#define F3(a, v, i, j, k) a[((((size_t)(k)) * np + (j)) * np + (i)) * 5 + (v)]
+  for (int e = 0; e < o->d.nElems; ++e) {
+    volint_fluxes(o, e, 1, o->d.parabolic, f, g, h);
+    for (int k = 0; k < np; ++k)
+      for (int j = 0; j < np; ++j)
+        for (int i = 0; i < np; ++i)
+          for (int v = 0; v < 5; ++v) {
+            double ut = MAT(DH, 0, i) * F3(f, v, 0, j, k) + MAT(DH, 0, k) * F3(h, v, i, j, 0) + MAT(DH, 0, j) * F3(g, v, i, 0, k);
+            for (int l = 1; l <= N; ++l)
+              ut = ut + MAT(DH, l, i) * F3(f, v, l, j, k) + MAT(DH, l, k) * F3(h, v, i, j, l) + MAT(DH, l, j) * F3(g, v, i, l, k);
+            VOL(o->Ut, NVAR, v, i, j, k, e) = ut;
+          }
+  }
+  free(f);
+}
+
+/* volint.f90:211-371 VolInt_splitForm */
+static void volint_split_form(oracle* o) {
+  const int np = o->np, N = np - 1;
+  const double* DH = o->d.D_Hat_T;
+  const double* DV = o->d.DVolSurf;
+  const int st = o->d.splitDGType;
+  const size_t esz = (size_t)np * np * np * 5;
+  double* fv = (double*)xcalloc(3 * esz, sizeof(double));
+  double *gv = fv + esz, *hv = gv + esz;
+  for (int e = 0; e < o->d.nElems; ++e) {
+    if (o->d.parabolic) {
+      volint_fluxes(o, e, 0, 1, fv, gv, hv);
+      for (int k = 0; k < np; ++k)
+        for (int j = 0; j < np; ++j)
+          for (int i = 0; i < np; ++i)
+            for (int v = 0; v < 5; ++v)
+              VOL(o->Ut, NVAR, v, i, j, k, e) = MAT(DH, i, i) * F3(fv, v, i, j, k) + MAT(DH, j, j) * F3(gv, v, i, j, k) + MAT(DH, k, k) * F3(hv, v, i, j, k);
+    } else {
+      memset(&VOL(o->Ut, NVAR, 0, 0, 0, 0, e), 0, esz * sizeof(double));
+    }
+    for (int k = 0; k < np; ++k)
+      for (int j = 0; j < np; ++j)
+        for (int i = 0; i < np; ++i) {
+          double Flux[5];
+          for (int l = i + 1; l <= N; ++l) {
+            split_volume_flux(st, &VOL(o->U, NVAR, 0, i, j, k, e), &VOL(o->UPrim, NPRIM, 0, i, j, k, e), &VOL(o->U, NVAR, 0, l, j, k, e),
+                              &VOL(o->UPrim, NPRIM, 0, l, j, k, e), &VOL(o->d.Metrics_fTilde, 3, 0, i, j, k, e),
+                              &VOL(o->d.Metrics_fTilde, 3, 0, l, j, k, e), Flux);
+            for (int v = 0; v < 5; ++v) {
+              VOL(o->Ut, NVAR, v, i, j, k, e) = VOL(o->Ut, NVAR, v, i, j, k, e) + MAT(DV, l, i) * Flux[v];
+              VOL(o->Ut, NVAR, v, l, j, k, e) = VOL(o->Ut, NVAR, v, l, j, k, e) + MAT(DV, i, l) * Flux[v];
+            }
+            if (o->d.parabolic)
+              for (int v = 0; v < 5; ++v) {
+                VOL(o->Ut, NVAR, v, i, j, k, e) = VOL(o->Ut, NVAR, v, i, j, k, e) + MAT(DH, l, i) * F3(fv, v, l, j, k);
+                VOL(o->Ut, NVAR, v, l, j, k, e) = VOL(o->Ut, NVAR, v, l, j, k, e) + MAT(DH, i, l) * F3(fv, v, i, j, k);
+              }
+          }
+          for (int l = j + 1; l <= N; ++l) {
+            split_volume_flux(st, &VOL(o->U, NVAR, 0, i, j, k, e), &VOL(o->UPrim, NPRIM, 0, i, j, k, e), &VOL(o->U, NVAR, 0, i, l, k, e),
+                              &VOL(o->UPrim, NPRIM, 0, i, l, k, e), &VOL(o->d.Metrics_gTilde, 3, 0, i, j, k, e),
+                              &VOL(o->d.Metrics_gTilde, 3, 0, i, l, k, e), Flux);
+            for (int v = 0; v < 5; ++v) {
+              VOL(o->Ut, NVAR, v, i, j, k, e) = VOL(o->Ut, NVAR, v, i, j, k, e) + MAT(DV, l, j) * Flux[v];
+              VOL(o->Ut, NVAR, v, i, l, k, e) = VOL(o->Ut, NVAR, v, i, l, k, e) + MAT(DV, j, l) * Flux[v];
+            }
+            if (o->d.parabolic)
+              for (int v = 0; v < 5; ++v) {
+                VOL(o->Ut, NVAR, v, i, j, k, e) = VOL(o->Ut, NVAR, v, i, j, k, e) + MAT(DH, l, j) * F3(gv, v, i, l, k);
+                VOL(o->Ut, NVAR, v, i, l, k, e) = VOL(o->Ut, NVAR, v, i, l, k, e) + MAT(DH, j, l) * F3(gv, v, i, j, k);
+              }
+          }
+          for (int l = k + 1; l <= N; ++l) {
+            split_volume_flux(st, &VOL(o->U, NVAR, 0, i, j, k, e), &VOL(o->UPrim, NPRIM, 0, i, j, k, e), &VOL(o->U, NVAR, 0, i, j, l, e),
+                              &VOL(o->UPrim, NPRIM, 0, i, j, l, e), &VOL(o->d.Metrics_hTilde, 3, 0, i, j, k, e),
+                              &VOL(o->d.Metrics_hTilde, 3, 0, i, j, l, e), Flux);
+            for (int v = 0; v < 5; ++v) {
+              VOL(o->Ut, NVAR, v, i, j, k, e) = VOL(o->Ut, NVAR, v, i, j, k, e) + MAT(DV, l, k) * Flux[v];
+              VOL(o->Ut, NVAR, v, i, j, l, e) = VOL(o->Ut, NVAR, v, i, j, l, e) + MAT(DV, k, l) * Flux[v];
+            }
+            if (o->d.parabolic)
+              for (int v = 0; v < 5; ++v) {
+                VOL(o->Ut, NVAR, v, i, j, k, e) = VOL(o->Ut, NVAR, v, i, j, k, e) + MAT(DH, l, k) * F3(hv, v, i, j, l);
+                VOL(o->Ut, NVAR, v, i, j, l, e) = VOL(o->Ut, NVAR, v, i, j, l, e) + MAT(DH, k, l) * F3(hv, v, i, j, k);
+              }
+          }
+        }
+  }
+  free(fv);
+}
+#undef F3
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* FillFlux: dg/fillflux.f90:40-215 (inner and MPI_MINE sides; BC sides handled in fill_flux_bc)                      */
+/* ------------------------------------------------------------------------------------------------------------------ */
+static void fill_flux_bc(oracle* o, double t); /* getboundaryflux restatement, below */
+
+static void fill_flux(oracle* o, double t, int doMPISides) {
+  const int np = o->np, nvl = o->nvl;
+  int firstSideID_wo_BC, firstSideID, lastSideID;
+  if (doMPISides) {
+    firstSideID_wo_BC = o->firstMPISide_MINE;
+    firstSideID = o->firstMPISide_MINE;
+    lastSideID = o->lastMPISide_MINE;
+  } else {
+    firstSideID_wo_BC = o->firstInnerSide;
+    firstSideID = o->firstBCSide;
+    lastSideID = o->lastInnerSide;
+  }
+  for (int SideID = firstSideID_wo_BC; SideID <= lastSideID; ++SideID) {
+    const int s = SideID - 1;
+    for (int q = 0; q < np; ++q)
+      for (int p = 0; p < np; ++p) {
+        double F[5];
+        const double* nv = &SID(o->d.NormVec, 3, 0, p, q, s);
+        riemann_point(o, o->d.riemann, F, &SID(o->U_master, NVAR, 0, p, q, s), &SID(o->U_slave, NVAR, 0, p, q, s),
+                      &SID(o->UPrim_master, NPRIM, 0, p, q, s), &SID(o->UPrim_slave, NPRIM, 0, p, q, s), nv,
+                      &SID(o->d.TangVec1, 3, 0, p, q, s), &SID(o->d.TangVec2, 3, 0, p, q, s));
+        if (o->d.parabolic) {
+          double Fv[5];
+          viscous_flux_point(o, Fv, &SID(o->UPrim_master, NPRIM, 0, p, q, s), &SID(o->UPrim_slave, NPRIM, 0, p, q, s),
+                             &SID(o->gradUx_master, nvl, 0, p, q, s), &SID(o->gradUy_master, nvl, 0, p, q, s),
+                             &SID(o->gradUz_master, nvl, 0, p, q, s), &SID(o->gradUx_slave, nvl, 0, p, q, s),
+                             &SID(o->gradUy_slave, nvl, 0, p, q, s), &SID(o->gradUz_slave, nvl, 0, p, q, s), nv);
+          for (int v = 0; v < 5; ++v) F[v] = F[v] + Fv[v];
+        }
+        for (int v = 0; v < 5; ++v) SID(o->Flux_master, NVAR, v, p, q, s) = F[v];
+      }
+  }
+  if (!doMPISides && o->d.nBCSides > 0) fill_flux_bc(o, t);
+  for (int SideID = firstSideID; SideID <= lastSideID; ++SideID) {
+    const int s = SideID - 1;
+    for (int q = 0; q < np; ++q)
+      for (int p = 0; p < np; ++p) {
+        double surf = o->d.SurfElem[((size_t)s * np + q) * np + p];
+        for (int v = 0; v < 5; ++v) {
+          SID(o->Flux_master, NVAR, v, p, q, s) = SID(o->Flux_master, NVAR, v, p, q, s) * surf;
+          SID(o->Flux_slave, NVAR, v, p, q, s) = SID(o->Flux_master, NVAR, v, p, q, s);
+        }
+      }
+  }
+}
+
+static void fill_flux_bc(oracle* o, double t) {
+  (void)t;
+  if (o->d.nBCSides > 0) {
+    fprintf(stderr, "oracle: boundary conditions are not restated yet\n");
+    abort();
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* source term / sign / Jacobian: dg.f90:656-676                                                                      */
+/* ------------------------------------------------------------------------------------------------------------------ */
+static void finish_ut(oracle* o, double t) {
+  (void)t;
+  const size_t n = (size_t)o->d.nElems * o->np * o->np * o->np;
+  for (size_t i = 0; i < n * NVAR; ++i) o->Ut[i] = -o->Ut[i];
+  if (o->d.doCalcSource) {
+    fprintf(stderr, "oracle: CalcSource not restated yet\n");
+    abort();
+  }
+  apply_jacobian(o, NVAR, o->Ut);
+}
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* world = the ranks of one emulated MPI job                                                                          */
+/* ------------------------------------------------------------------------------------------------------------------ */
+typedef struct oracle_world {
+  int n;
+  oracle** r;
+} oracle_world;
+
+/* mpi.f90:244-445: SendID=1 sends MINE slices (received as YOUR), SendID=2 sends YOUR slices (received as MINE).
+ * `off` is the byte offset of the exchanged array inside struct oracle so that the same array is addressed on every rank. */
+static void exchange(oracle_world* w, size_t member_off, int dataSizeSide, int SendID) {
+  for (int r = 0; r < w->n; ++r) {
+    oracle* src = w->r[r];
+    double* a_src = *(double**)((char*)src + member_off);
+    for (int i = 0; i < src->d.nNbProcs; ++i) {
+      int nb = src->d.NbProc[i];
+      oracle* dst = w->r[nb];
+      double* a_dst = *(double**)((char*)dst + member_off);
+      int j = -1;
+      for (int jj = 0; jj < dst->d.nNbProcs; ++jj)
+        if (dst->d.NbProc[jj] == r) j = jj;
+      if (j < 0) {
+        fprintf(stderr, "oracle: asymmetric neighbour tables\n");
+        abort();
+      }
+      int s0, n, d0, nd;
+      if (SendID == 1) {
+        s0 = src->d.offsetMPISides_MINE[i];
+        n = src->d.nMPISides_MINE_Proc[i];
+        d0 = dst->d.offsetMPISides_YOUR[j];
+        nd = dst->d.nMPISides_YOUR_Proc[j];
+      } else {
+        s0 = src->d.offsetMPISides_YOUR[i];
+        n = src->d.nMPISides_YOUR_Proc[i];
+        d0 = dst->d.offsetMPISides_MINE[j];
+        nd = dst->d.nMPISides_MINE_Proc[j];
+      }
+      if (n != nd) {
+        fprintf(stderr, "oracle: message size mismatch %d vs %d\n", n, nd);
+        abort();
+      }
+      memcpy(a_dst + (size_t)d0 * dataSizeSide, a_src + (size_t)s0 * dataSizeSide, (size_t)n * dataSizeSide * sizeof(double));
+    }
+  }
+}
+#define OFF(m) ((size_t)((char*)&((oracle*)0)->m - (char*)0))
+#define FOR_RANKS _Pragma("omp parallel for schedule(static)") for (int r = 0; r < w->n; ++r)
+
+/* lifting_br1.t90:48-181 Lifting_BR1 (strong, non-conservative) */
+static void lifting_br1_world(oracle_world* w, double t) {
+  (void)t;
+  const int np = w->r[0]->np, nvl = w->r[0]->nvl;
+  const int szg = nvl * np * np;
+  FOR_RANKS lifting_fill_flux(w->r[r], 0, w->r[r]->gradUz_slave, 1);
+  exchange(w, OFF(gradUz_slave), szg, 1);
+  FOR_RANKS {
+    oracle* o = w->r[r];
+    lifting_volint_nonconservative(o);
+    /* Lifting_FillFlux_BC: no BC sides restated yet */
+    lifting_fill_flux(o, 0, o->gradUz_slave, 0);
+    lifting_fill_flux_normvec(o, o->gradUz_slave, o->gradUx_master, o->gradUy_master, o->gradUz_master, 0);
+    surf_int(o, nvl, o->gradUx_master, o->gradUx_master, o->gradUx, 0, o->d.L_HatMinus, o->d.L_HatPlus, 1.);
+    surf_int(o, nvl, o->gradUy_master, o->gradUy_master, o->gradUy, 0, o->d.L_HatMinus, o->d.L_HatPlus, 1.);
+    surf_int(o, nvl, o->gradUz_master, o->gradUz_master, o->gradUz, 0, o->d.L_HatMinus, o->d.L_HatPlus, 1.);
+    lifting_fill_flux_normvec(o, o->gradUz_slave, o->gradUx_master, o->gradUy_master, o->gradUz_master, 1);
+    surf_int(o, nvl, o->gradUx_master, o->gradUx_master, o->gradUx, 1, o->d.L_HatMinus, o->d.L_HatPlus, 1.);
+    surf_int(o, nvl, o->gradUy_master, o->gradUy_master, o->gradUy, 1, o->d.L_HatMinus, o->d.L_HatPlus, 1.);
+    surf_int(o, nvl, o->gradUz_master, o->gradUz_master, o->gradUz, 1, o->d.L_HatMinus, o->d.L_HatPlus, 1.);
+    apply_jacobian(o, nvl, o->gradUx);
+    apply_jacobian(o, nvl, o->gradUy);
+    apply_jacobian(o, nvl, o->gradUz);
+    prolong_to_face(o, nvl, o->gradUx, o->gradUx_master, o->gradUx_slave, 1);
+    prolong_to_face(o, nvl, o->gradUy, o->gradUy_master, o->gradUy_slave, 1);
+    prolong_to_face(o, nvl, o->gradUz, o->gradUz_master, o->gradUz_slave, 1);
+  }
+  exchange(w, OFF(gradUx_slave), szg, 2);
+  exchange(w, OFF(gradUy_slave), szg, 2);
+  exchange(w, OFF(gradUz_slave), szg, 2);
+  FOR_RANKS {
+    oracle* o = w->r[r];
+    prolong_to_face(o, nvl, o->gradUx, o->gradUx_master, o->gradUx_slave, 0);
+    prolong_to_face(o, nvl, o->gradUy, o->gradUy_master, o->gradUy_slave, 0);
+    prolong_to_face(o, nvl, o->gradUz, o->gradUz_master, o->gradUz_slave, 0);
+  }
+}
+
+/* dg.f90:221-678 DGTimeDerivative_weakForm */
+void oracle_world_dg_time_derivative(oracle_world* w, double t) {
+  const int np = w->r[0]->np;
+  const int szs = NVAR * np * np;
+  FOR_RANKS {
+    oracle* o = w->r[r];
+    cons_to_prim_volume(o);                                  /* 2. */
+    prolong_to_face(o, NVAR, o->U, o->U_master, o->U_slave, 1); /* 3. MPI YOUR sides first */
+  }
+  exchange(w, OFF(U_slave), szs, 2);
+  FOR_RANKS {
+    oracle* o = w->r[r];
+    prolong_to_face(o, NVAR, o->U, o->U_master, o->U_slave, 0);
+    get_primitive_state_surface(o); /* 4. */
+  }
+  if (w->r[0]->d.parabolic) { /* 6. */
+    if (w->r[0]->d.lifting == 1)
+      lifting_br1_world(w, t);
+    else {
+      fprintf(stderr, "oracle: BR2 not restated yet\n");
+      abort();
+    }
+  }
+  FOR_RANKS { /* 8. */
+    oracle* o = w->r[r];
+    if (o->d.splitDG)
+      volint_split_form(o);
+    else
+      volint_weak_form(o);
+    fill_flux(o, t, 1); /* 11. MPI MINE */
+  }
+  exchange(w, OFF(Flux_slave), szs, 1);
+  FOR_RANKS {
+    oracle* o = w->r[r];
+    fill_flux(o, t, 0);
+    surf_int(o, NVAR, o->Flux_master, o->Flux_slave, o->Ut, 0, o->d.L_HatMinus, o->d.L_HatPlus, -1.);
+    surf_int(o, NVAR, o->Flux_master, o->Flux_slave, o->Ut, 1, o->d.L_HatMinus, o->d.L_HatPlus, -1.);
+    finish_ut(o, t); /* 12.-14. */
+  }
+}
+
+/* timestep.f90:82-152 TimeStepByLSERKW2 */
+void oracle_world_timestep(oracle_world* w, double t, double dt) {
+  const flexi_gpu_desc* d0 = &w->r[0]->d;
+  for (int iStage = 1; iStage <= d0->nRKStages; ++iStage) {
+    double tStage = (iStage == 1) ? t : t + d0->RKc[iStage - 2] * dt;
+    oracle_world_dg_time_derivative(w, tStage);
+    FOR_RANKS {
+      oracle* o = w->r[r];
+      const size_t n = (size_t)o->d.nElems * o->np * o->np * o->np * NVAR;
+      const double b_dt = o->d.RKb[iStage - 1] * dt;
+      if (iStage == 1) {
+        for (size_t i = 0; i < n; ++i) o->Ut_tmp[i] = o->Ut[i];
+      } else {
+        const double mA = -o->d.RKA[iStage - 2];
+        for (size_t i = 0; i < n; ++i) o->Ut_tmp[i] = o->Ut_tmp[i] * mA + o->Ut[i];
+      }
+      for (size_t i = 0; i < n; ++i) o->U[i] = o->U[i] + o->Ut_tmp[i] * b_dt;
+    }
+  }
+}
+
+/* calctimestep.f90:42-83 InitCalctimestep */
+static void init_calc_timestep(oracle* o) {
+  const int np = o->np;
+  const size_t n = (size_t)o->d.nElems * np * np * np;
+  o->MetricsAdv = (double*)xcalloc(n * 3, sizeof(double));
+  o->MetricsVisc = (double*)xcalloc(n * 3, sizeof(double));
+  const double KappasPr_max = fmax(4. / 3., o->KappasPr);
+  for (size_t i = 0; i < n; ++i) {
+    const double* M[3] = {o->d.Metrics_fTilde + 3 * i, o->d.Metrics_gTilde + 3 * i, o->d.Metrics_hTilde + 3 * i};
+    const double sJ = o->d.sJ[i];
+    for (int dd = 0; dd < 3; ++dd) {
+      o->MetricsAdv[3 * i + dd] = sJ * sqrt(M[dd][0] * M[dd][0] + M[dd][1] * M[dd][1] + M[dd][2] * M[dd][2]);
+      o->MetricsVisc[3 * i + dd] =
+          KappasPr_max * ((M[dd][0] * sJ) * (M[dd][0] * sJ) + (M[dd][1] * sJ) * (M[dd][1] * sJ) + (M[dd][2] * sJ) * (M[dd][2] * sJ));
+    }
+  }
+}
+
+/* calctimestep.f90:89-227 CalcTimeStep (per rank part) */
+static void calc_timestep_rank(oracle* o, double* TimeStep3) {
+  const int np = o->np;
+  const size_t ne = (size_t)np * np * np;
+  int errType = 0;
+  double TimeStepConv = HUGE_VAL, TimeStepVisc = HUGE_VAL;
+  for (int e = 0; e < o->d.nElems; ++e) {
+    double Max_Lambda[3] = {0, 0, 0}, Max_Lambda_v[3] = {0, 0, 0};
+    for (size_t n = 0; n < ne; ++n) {
+      const size_t i = (size_t)e * ne + n;
+      double UE[11];
+      for (int v = 0; v < 5; ++v) UE[v] = o->U[i * 5 + v];
+      UE[EXT_SRHO] = 1. / UE[EXT_DENS];
+      UE[EXT_VEL1] = UE[EXT_MOM1] * UE[EXT_SRHO];
+      UE[EXT_VEL2] = UE[EXT_MOM2] * UE[EXT_SRHO];
+      UE[EXT_VEL3] = UE[EXT_MOM3] * UE[EXT_SRHO];
+      UE[EXT_PRES] = o->kappaM1 * (UE[EXT_ENER] - 0.5 * (UE[EXT_VEL1] * UE[EXT_MOM1] + UE[EXT_VEL2] * UE[EXT_MOM2] + UE[EXT_VEL3] * UE[EXT_MOM3]));
+      UE[EXT_TEMP] = UE[EXT_PRES] * UE[EXT_SRHO] / o->d.R;
+      if (isnan(UE[EXT_DENS])) errType = 1;
+      double c = speed_of_sound_he(o, UE);
+      double sJ = o->d.sJ[i];
+      double vsJ[3] = {UE[EXT_VEL1] * sJ, UE[EXT_VEL2] * sJ, UE[EXT_VEL3] * sJ};
+      const double* M[3] = {o->d.Metrics_fTilde + 3 * i, o->d.Metrics_gTilde + 3 * i, o->d.Metrics_hTilde + 3 * i};
+      for (int dd = 0; dd < 3; ++dd)
+        Max_Lambda[dd] = fmax(Max_Lambda[dd], fabs(M[dd][0] * vsJ[0] + M[dd][1] * vsJ[1] + M[dd][2] * vsJ[2]) + c * o->MetricsAdv[3 * i + dd]);
+      if (o->d.parabolic) {
+        double mu = o->d.mu0;
+        for (int dd = 0; dd < 3; ++dd) Max_Lambda_v[dd] = fmax(Max_Lambda_v[dd], mu * UE[EXT_SRHO] * o->MetricsVisc[3 * i + dd]);
+      }
+    }
+    double dtElem = o->d.CFLScale * 2. / (Max_Lambda[0] + Max_Lambda[1] + Max_Lambda[2]);
+    TimeStepConv = fmin(TimeStepConv, dtElem);
+    if (isnan(TimeStepConv) || isnan(dtElem)) errType = 2;
+    if (o->d.parabolic) {
+      double sv = Max_Lambda_v[0] + Max_Lambda_v[1] + Max_Lambda_v[2];
+      if (sv > 0.) TimeStepVisc = fmin(TimeStepVisc, o->d.DFLScale * 4. / sv);
+      if (isnan(TimeStepVisc) || isnan(sv)) errType = 3;
+    }
+  }
+  TimeStep3[0] = TimeStepConv;
+  TimeStep3[1] = TimeStepVisc;
+  TimeStep3[2] = -(double)errType;
+}
+
+double oracle_world_calc_timestep(oracle_world* w, double* dt_conv, double* dt_visc, int* errType) {
+  double ts[3] = {HUGE_VAL, HUGE_VAL, HUGE_VAL};
+  double* loc = (double*)xcalloc((size_t)3 * w->n, sizeof(double));
+  FOR_RANKS calc_timestep_rank(w->r[r], loc + 3 * r);
+  for (int r = 0; r < w->n; ++r) /* MPI_ALLREDUCE(MIN), calctimestep.f90:221 */
+    for (int c = 0; c < 3; ++c) ts[c] = fmin(ts[c], loc[3 * r + c]);
+  free(loc);
+  *errType = (int)(-ts[2]);
+  *dt_conv = ts[0];
+  *dt_visc = ts[1];
+  return fmin(ts[0], ts[1]);
+}
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* construction / access                                                                                              */
+/* ------------------------------------------------------------------------------------------------------------------ */
+oracle* oracle_create(const flexi_gpu_desc* d) {
+  if (d->abi_version != FLEXI_GPU_ABI_VERSION || d->struct_bytes != (int)sizeof(flexi_gpu_desc)) {
+    fprintf(stderr, "oracle: descriptor ABI mismatch (%d bytes vs %d)\n", d->struct_bytes, (int)sizeof(flexi_gpu_desc));
+    return NULL;
+  }
+  oracle* o = (oracle*)xcalloc(1, sizeof(oracle));
+  o->d = *d;
+  const int np = d->N + 1;
+  o->np = np;
+  o->nvl = d->nVarLifting;
+  if (o->nvl == 5) {
+    int m[5] = {0, 1, 2, 3, 5};
+    memcpy(o->lift_map, m, sizeof m);
+    o->lv_vel1 = 1;
+    o->lv_temp = 4;
+  } else {
+    int m[5] = {1, 2, 3, 5, 0};
+    memcpy(o->lift_map, m, sizeof m);
+    o->lv_vel1 = 0;
+    o->lv_temp = 3;
+  }
+  o->kappaM1 = d->kappa - 1.;
+  o->sKappaM1 = 1. / o->kappaM1;
+  o->cp = d->R * d->kappa / (d->kappa - 1.);
+  o->cv = d->R / (d->kappa - 1.);
+  o->KappasPr = d->kappa / d->Pr;
+  const size_t nvol = (size_t)d->nElems * np * np * np, nsid = (size_t)d->nSides * np * np;
+  /* own the descriptor arrays */
+  o->d.Metrics_fTilde = (const double*)own_copy(o, d->Metrics_fTilde, nvol * 3 * 8);
+  o->d.Metrics_gTilde = (const double*)own_copy(o, d->Metrics_gTilde, nvol * 3 * 8);
+  o->d.Metrics_hTilde = (const double*)own_copy(o, d->Metrics_hTilde, nvol * 3 * 8);
+  o->d.sJ = (const double*)own_copy(o, d->sJ, nvol * 8);
+  o->d.Elem_xGP = (const double*)own_copy(o, d->Elem_xGP, nvol * 3 * 8);
+  o->d.NormVec = (const double*)own_copy(o, d->NormVec, nsid * 3 * 8);
+  o->d.TangVec1 = (const double*)own_copy(o, d->TangVec1, nsid * 3 * 8);
+  o->d.TangVec2 = (const double*)own_copy(o, d->TangVec2, nsid * 3 * 8);
+  o->d.SurfElem = (const double*)own_copy(o, d->SurfElem, nsid * 8);
+  o->d.Face_xGP = (const double*)own_copy(o, d->Face_xGP, nsid * 3 * 8);
+  o->d.SideToElem = (const int32_t*)own_copy(o, d->SideToElem, (size_t)d->nSides * 5 * 4);
+  o->d.ElemToSide = (const int32_t*)own_copy(o, d->ElemToSide, (size_t)d->nElems * 12 * 4);
+  o->d.S2V2 = (const int32_t*)own_copy(o, d->S2V2, (size_t)2 * np * np * 5 * 6 * 4);
+  o->d.BC = (const int32_t*)own_copy(o, d->BC, (size_t)d->nBCSides * 4);
+  o->d.BoundaryType = (const int32_t*)own_copy(o, d->BoundaryType, (size_t)d->nBCs * 3 * 4);
+  o->d.RefStatePrim = (const double*)own_copy(o, d->RefStatePrim, (size_t)d->nRefState * 6 * 8);
+  o->d.xGP = (const double*)own_copy(o, d->xGP, np * 8);
+  o->d.wGP = (const double*)own_copy(o, d->wGP, np * 8);
+  o->d.D = (const double*)own_copy(o, d->D, (size_t)np * np * 8);
+  o->d.D_T = (const double*)own_copy(o, d->D_T, (size_t)np * np * 8);
+  o->d.D_Hat_T = (const double*)own_copy(o, d->D_Hat_T, (size_t)np * np * 8);
+  o->d.DVolSurf = (const double*)own_copy(o, d->DVolSurf, (size_t)np * np * 8);
+  o->d.L_Minus = (const double*)own_copy(o, d->L_Minus, np * 8);
+  o->d.L_Plus = (const double*)own_copy(o, d->L_Plus, np * 8);
+  o->d.L_HatMinus = (const double*)own_copy(o, d->L_HatMinus, np * 8);
+  o->d.L_HatPlus = (const double*)own_copy(o, d->L_HatPlus, np * 8);
+  o->d.RKA = (const double*)own_copy(o, d->RKA, (size_t)(d->nRKStages > 1 ? d->nRKStages - 1 : 1) * 8);
+  o->d.RKb = (const double*)own_copy(o, d->RKb, (size_t)(d->nRKStages > 0 ? d->nRKStages : 1) * 8);
+  o->d.RKc = (const double*)own_copy(o, d->RKc, (size_t)(d->nRKStages > 1 ? d->nRKStages - 1 : 1) * 8);
+  o->d.NbProc = (const int32_t*)own_copy(o, d->NbProc, (size_t)d->nNbProcs * 4);
+  o->d.nMPISides_MINE_Proc = (const int32_t*)own_copy(o, d->nMPISides_MINE_Proc, (size_t)d->nNbProcs * 4);
+  o->d.nMPISides_YOUR_Proc = (const int32_t*)own_copy(o, d->nMPISides_YOUR_Proc, (size_t)d->nNbProcs * 4);
+  o->d.offsetMPISides_MINE = (const int32_t*)own_copy(o, d->offsetMPISides_MINE, (size_t)(d->nNbProcs + 1) * 4);
+  o->d.offsetMPISides_YOUR = (const int32_t*)own_copy(o, d->offsetMPISides_YOUR, (size_t)(d->nNbProcs + 1) * 4);
+  o->d.ncclUniqueId = NULL;
+  /* side ranges, mesh.f90:257-269 */
+  o->firstBCSide = 1;
+  o->lastBCSide = d->nBCSides;
+  o->firstInnerSide = d->nBCSides + 1;
+  o->lastInnerSide = d->nBCSides + d->nInnerSides;
+  o->firstMPISide_MINE = o->lastInnerSide + 1;
+  o->lastMPISide_MINE = o->lastInnerSide + d->nMPISides_MINE;
+  o->firstMPISide_YOUR = o->lastMPISide_MINE + 1;
+  o->lastMPISide_YOUR = o->lastMPISide_MINE + d->nMPISides_YOUR;
+  /* state, dg.f90:73-111, lifting.f90:146-166 */
+  o->U = (double*)xcalloc(nvol * NVAR, 8);
+  o->Ut = (double*)xcalloc(nvol * NVAR, 8);
+  o->Ut_tmp = (double*)xcalloc(nvol * NVAR, 8);
+  o->UPrim = (double*)xcalloc(nvol * NPRIM, 8);
+  o->U_master = (double*)xcalloc(nsid * NVAR, 8);
+  o->U_slave = (double*)xcalloc(nsid * NVAR, 8);
+  o->UPrim_master = (double*)xcalloc(nsid * NPRIM, 8);
+  o->UPrim_slave = (double*)xcalloc(nsid * NPRIM, 8);
+  o->Flux_master = (double*)xcalloc(nsid * NVAR, 8);
+  o->Flux_slave = (double*)xcalloc(nsid * NVAR, 8);
+  if (d->parabolic) {
+    o->gradUx = (double*)xcalloc(nvol * o->nvl, 8);
+    o->gradUy = (double*)xcalloc(nvol * o->nvl, 8);
+    o->gradUz = (double*)xcalloc(nvol * o->nvl, 8);
+    o->gradUx_master = (double*)xcalloc(nsid * o->nvl, 8);
+    o->gradUy_master = (double*)xcalloc(nsid * o->nvl, 8);
+    o->gradUz_master = (double*)xcalloc(nsid * o->nvl, 8);
+    o->gradUx_slave = (double*)xcalloc(nsid * o->nvl, 8);
+    o->gradUy_slave = (double*)xcalloc(nsid * o->nvl, 8);
+    o->gradUz_slave = (double*)xcalloc(nsid * o->nvl, 8);
+    o->FluxX = (double*)xcalloc(nsid * o->nvl, 8);
+    o->FluxY = (double*)xcalloc(nsid * o->nvl, 8);
+    o->FluxZ = (double*)xcalloc(nsid * o->nvl, 8);
+  }
+  init_calc_timestep(o);
+  return o;
+}
+
+void oracle_destroy(oracle* o) {
+  if (!o) return;
+  for (int i = 0; i < o->n_owned; ++i) free(o->owned[i]);
+  double* st[] = {o->U, o->Ut, o->Ut_tmp, o->UPrim, o->U_master, o->U_slave, o->UPrim_master, o->UPrim_slave, o->Flux_master,
+                  o->Flux_slave, o->gradUx, o->gradUy, o->gradUz, o->gradUx_master, o->gradUy_master, o->gradUz_master,
+                  o->gradUx_slave, o->gradUy_slave, o->gradUz_slave, o->FluxX, o->FluxY, o->FluxZ, o->MetricsAdv, o->MetricsVisc};
+  for (size_t i = 0; i < sizeof st / sizeof st[0]; ++i) free(st[i]);
+  free(o);
+}
+
+oracle_world* oracle_world_create(oracle** ranks, int n) {
+  oracle_world* w = (oracle_world*)xcalloc(1, sizeof(oracle_world));
+  w->n = n;
+  w->r = (oracle**)xcalloc(n, sizeof(oracle*));
+  for (int i = 0; i < n; ++i) w->r[i] = ranks[i];
+  return w;
+}
+void oracle_world_destroy(oracle_world* w) {
+  if (!w) return;
+  free(w->r);
+  free(w);
+}
+
+/* pointer to a named module array of one rank (same numbering as enum flexi_gpu_array, plus oracle-only extras >= 100) */
+double* oracle_array(oracle* o, int which, int64_t* n_out) {
+  const int np = o->np;
+  const size_t nvol = (size_t)o->d.nElems * np * np * np, nsid = (size_t)o->d.nSides * np * np;
+  double* p = NULL;
+  size_t n = 0;
+  switch (which) {
+    case FLEXI_ARR_U: p = o->U; n = nvol * NVAR; break;
+    case FLEXI_ARR_UT: p = o->Ut; n = nvol * NVAR; break;
+    case FLEXI_ARR_U_MASTER: p = o->U_master; n = nsid * NVAR; break;
+    case FLEXI_ARR_U_SLAVE: p = o->U_slave; n = nsid * NVAR; break;
+    case FLEXI_ARR_FLUX: p = o->Flux_master; n = nsid * NVAR; break;
+    case FLEXI_ARR_GRADUX: p = o->gradUx; n = nvol * o->nvl; break;
+    case FLEXI_ARR_GRADUY: p = o->gradUy; n = nvol * o->nvl; break;
+    case FLEXI_ARR_GRADUZ: p = o->gradUz; n = nvol * o->nvl; break;
+    case FLEXI_ARR_GRADUX_MASTER: p = o->gradUx_master; n = nsid * o->nvl; break;
+    case FLEXI_ARR_GRADUY_MASTER: p = o->gradUy_master; n = nsid * o->nvl; break;
+    case FLEXI_ARR_GRADUZ_MASTER: p = o->gradUz_master; n = nsid * o->nvl; break;
+    case FLEXI_ARR_GRADUX_SLAVE: p = o->gradUx_slave; n = nsid * o->nvl; break;
+    case FLEXI_ARR_GRADUY_SLAVE: p = o->gradUy_slave; n = nsid * o->nvl; break;
+    case FLEXI_ARR_GRADUZ_SLAVE: p = o->gradUz_slave; n = nsid * o->nvl; break;
+    case 100: p = o->Flux_slave; n = nsid * NVAR; break;
+    case 101: p = o->UPrim; n = nvol * NPRIM; break;
+    case 102: p = o->Ut_tmp; n = nvol * NVAR; break;
+    default: break;
+  }
+  if (n_out) *n_out = (int64_t)n;
+  return p;
+}
+
+/* operator-level entry points used to replay the reference's unit tests (unitTests/ProlongToFace.f90, SurfInt.f90) */
+void oracle_prolong_to_face(oracle* o, int nv, const double* Uvol, double* Uface_master, double* Uface_slave, int doMPISides) {
+  prolong_to_face(o, nv, Uvol, Uface_master, Uface_slave, doMPISides);
+}
+void oracle_surf_int(oracle* o, int nv, const double* Flux_master, const double* Flux_slave, double* Ut, int doMPISides,
+                     const double* L_HatMinus, const double* L_HatPlus) {
+  surf_int(o, nv, Flux_master, Flux_slave, Ut, doMPISides, L_HatMinus, L_HatPlus, -1.);
+}
+
+/* point-level entry points for the identity tests (consistency / symmetry of fluxes) */
+void oracle_riemann_point(oracle* o, int solver, double* FOut, const double* U_L, const double* U_R, const double* nv, const double* t1,
+                          const double* t2) {
+  double PL[6], PR[6];
+  cons_to_prim(o, PL, U_L);
+  cons_to_prim(o, PR, U_R);
+  riemann_point(o, solver, FOut, U_L, U_R, PL, PR, nv, t1, t2);
+}
+void oracle_split_volume_flux(oracle* o, int type, const double* URef, const double* U, const double* MRef, const double* M, double* Flux) {
+  double PR[6], P[6];
+  cons_to_prim(o, PR, URef);
+  cons_to_prim(o, P, U);
+  split_volume_flux(type, URef, PR, U, P, MRef, M, Flux);
+}
+void oracle_eval_flux3d(oracle* o, const double* U, double* f, double* g, double* h) {
+  double P[6];
+  cons_to_prim(o, P, U);
+  eval_flux3d(U, P, f, g, h);
+}
+int oracle_desc_bytes(void) { return (int)sizeof(flexi_gpu_desc); }

@@ -1,0 +1,173 @@
+"""ctypes front-end of the CPU oracle (oracle/flexi_oracle.c).  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIBS = {}
+
+
+def build(force=False):
+    need = force or not all(os.path.exists(os.path.join(_HERE, n)) for n in ("liboracle.so", "liboracle_fast.so"))
+    if need:
+        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+
+
+def _load(fast=False):
+    name = "liboracle_fast.so" if fast else "liboracle.so"
+    if name in _LIBS:
+        return _LIBS[name]
+    path = os.path.join(_HERE, name)
+    if not os.path.exists(path):
+        build()
+    lib = C.CDLL(path)
+    P = C.c_void_p
+    PD = C.POINTER(C.c_double)
+    lib.oracle_create.restype = P
+    lib.oracle_create.argtypes = [P]
+    lib.oracle_destroy.argtypes = [P]
+    lib.oracle_world_create.restype = P
+    lib.oracle_world_create.argtypes = [C.POINTER(P), C.c_int]
+    lib.oracle_world_destroy.argtypes = [P]
+    lib.oracle_world_dg_time_derivative.argtypes = [P, C.c_double]
+    lib.oracle_world_timestep.argtypes = [P, C.c_double, C.c_double]
+    lib.oracle_world_calc_timestep.restype = C.c_double
+    lib.oracle_world_calc_timestep.argtypes = [P, PD, PD, C.POINTER(C.c_int)]
+    lib.oracle_array.restype = PD
+    lib.oracle_array.argtypes = [P, C.c_int, C.POINTER(C.c_int64)]
+    lib.oracle_prolong_to_face.argtypes = [P, C.c_int, PD, PD, PD, C.c_int]
+    lib.oracle_surf_int.argtypes = [P, C.c_int, PD, PD, PD, C.c_int, PD, PD]
+    lib.oracle_riemann_point.argtypes = [P, C.c_int, PD, PD, PD, PD, PD, PD]
+    lib.oracle_split_volume_flux.argtypes = [P, C.c_int, PD, PD, PD, PD, PD]
+    lib.oracle_eval_flux3d.argtypes = [P, PD, PD, PD, PD]
+    lib.oracle_desc_bytes.restype = C.c_int
+    _LIBS[name] = lib
+    return lib
+
+
+def _pd(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+ARR = dict(U=0, Ut=1, U_master=2, U_slave=3, Flux=4, gradUx=5, gradUy=6, gradUz=7, gradUx_master=8, gradUy_master=9,
+           gradUz_master=10, gradUx_slave=11, gradUy_slave=12, gradUz_slave=13, Flux_slave=100, UPrim=101, Ut_tmp=102)
+
+
+class OracleRank:
+    def __init__(self, lib, desc, keep):
+        self.lib = lib
+        self.keep = keep
+        self.desc = desc
+        self.h = lib.oracle_create(C.cast(C.byref(desc), C.c_void_p))
+        if not self.h:
+            raise RuntimeError("oracle_create failed")
+        self.np = desc.N + 1
+
+    def array(self, name):
+        """numpy VIEW of a module array (Fortran memory; shape is the reversed Fortran shape)."""
+        n = C.c_int64(0)
+        p = self.lib.oracle_array(self.h, ARR[name], C.byref(n))
+        if not p:
+            raise KeyError(name)
+        a = np.ctypeslib.as_array(p, shape=(n.value,))
+        np_ = self.np
+        d = self.desc
+        nvl = d.nVarLifting
+        if name in ("U", "Ut", "Ut_tmp"):
+            return a.reshape(d.nElems, np_, np_, np_, 5)
+        if name == "UPrim":
+            return a.reshape(d.nElems, np_, np_, np_, 6)
+        if name in ("gradUx", "gradUy", "gradUz"):
+            return a.reshape(d.nElems, np_, np_, np_, nvl)
+        if name in ("U_master", "U_slave", "Flux", "Flux_slave"):
+            return a.reshape(d.nSides, np_, np_, 5)
+        return a.reshape(d.nSides, np_, np_, nvl)
+
+    def close(self):
+        if self.h:
+            self.lib.oracle_destroy(self.h)
+            self.h = None
+
+
+class OracleWorld:
+    """The ranks of one emulated MPI job (one rank per OpenMP thread in the fast build)."""
+
+    def __init__(self, descs_and_keeps, fast=False):
+        self.lib = _load(fast)
+        assert self.lib.oracle_desc_bytes() == C.sizeof(type(descs_and_keeps[0][0]))
+        self.ranks = [OracleRank(self.lib, d, k) for d, k in descs_and_keeps]
+        arr = (C.c_void_p * len(self.ranks))(*[r.h for r in self.ranks])
+        self.w = self.lib.oracle_world_create(arr, len(self.ranks))
+
+    def set_state(self, Us):
+        for r, U in zip(self.ranks, Us):
+            r.array("U")[...] = U
+
+    def dg_time_derivative(self, t=0.0):
+        self.lib.oracle_world_dg_time_derivative(self.w, float(t))
+
+    def timestep(self, t, dt):
+        self.lib.oracle_world_timestep(self.w, float(t), float(dt))
+
+    def calc_timestep(self):
+        a, b, e = C.c_double(0), C.c_double(0), C.c_int(0)
+        dt = self.lib.oracle_world_calc_timestep(self.w, C.byref(a), C.byref(b), C.byref(e))
+        return dt, a.value, b.value, e.value
+
+    def close(self):
+        if self.w:
+            self.lib.oracle_world_destroy(self.w)
+            self.w = None
+        for r in self.ranks:
+            r.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+def riemann_point(rank, solver, U_L, U_R, nv, t1, t2):
+    F = np.zeros(5)
+    args = [np.ascontiguousarray(x, dtype=np.float64) for x in (U_L, U_R, nv, t1, t2)]
+    rank.lib.oracle_riemann_point(rank.h, int(solver), _pd(F), *[_pd(a) for a in args])
+    return F
+
+
+def split_volume_flux(rank, stype, URef, U, MRef, M):
+    F = np.zeros(5)
+    args = [np.ascontiguousarray(x, dtype=np.float64) for x in (URef, U, MRef, M)]
+    rank.lib.oracle_split_volume_flux(rank.h, int(stype), *[_pd(a) for a in args], _pd(F))
+    return F
+
+
+def eval_flux3d(rank, U):
+    f, g, h = np.zeros(5), np.zeros(5), np.zeros(5)
+    U = np.ascontiguousarray(U, dtype=np.float64)
+    rank.lib.oracle_eval_flux3d(rank.h, _pd(U), _pd(f), _pd(g), _pd(h))
+    return f, g, h
+
+
+def prolong_to_face(rank, nv, Uvol, doMPISides=False):
+    d = rank.desc
+    np_ = rank.np
+    Uvol = np.ascontiguousarray(Uvol, dtype=np.float64)
+    um = np.zeros((d.nSides, np_, np_, nv))
+    us = np.zeros((d.nSides, np_, np_, nv))
+    rank.lib.oracle_prolong_to_face(rank.h, nv, _pd(Uvol), _pd(um), _pd(us), int(doMPISides))
+    return um, us
+
+
+def surf_int(rank, nv, Flux_master, Flux_slave, Ut, L_HatMinus, L_HatPlus, doMPISides=False):
+    fm = np.ascontiguousarray(Flux_master, dtype=np.float64)
+    fs = np.ascontiguousarray(Flux_slave, dtype=np.float64)
+    lm = np.ascontiguousarray(L_HatMinus, dtype=np.float64)
+    lp = np.ascontiguousarray(L_HatPlus, dtype=np.float64)
+    rank.lib.oracle_surf_int(rank.h, nv, _pd(fm), _pd(fs), _pd(Ut), int(doMPISides), _pd(lm), _pd(lp))
+    return Ut

@@ -1,0 +1,176 @@
+"""Self-validation of the restated oracle through the identities listed in SURVEY.md 8(c) ("unpinned at function level")."""
+import numpy as np
+import pytest
+
+from flexi_b200.desc import RIEMANN, SPLITDG
+from flexi_b200.hostmesh import basis as B
+from flexi_b200.hostmesh.case import TGV_EQN, build_case, tgv_box
+from flexi_b200.hostmesh.mesh import BoxSpec
+from oracle import oracle as O
+
+
+def world(spec, N, node, eqn, nranks=1, **kw):
+    ranks = build_case(spec, N, node, eqn, nranks=nranks, **kw)
+    w = O.OracleWorld([(r.desc, r.keep) for r in ranks])
+    return ranks, w
+
+
+def frame(rng):
+    n = rng.normal(size=3)
+    n /= np.linalg.norm(n)
+    a = rng.normal(size=3)
+    t1 = a - np.dot(a, n) * n
+    t1 /= np.linalg.norm(t1)
+    return n, t1, np.cross(n, t1)
+
+
+@pytest.mark.parametrize("solver", ["lf", "hllc", "roe", "roeentropyfix", "roel2", "hll", "hlle", "hllem"])
+def test_riemann_consistency(solver):
+    """(1) F*(U,U) = F(U).n for every solver, in an arbitrary rotated frame."""
+    ranks, w = world(tgv_box(2), 2, B.NODE_GAUSS, dict(parabolic=False))
+    rng = np.random.default_rng(7)
+    eq = ranks[0].eqn
+    for _ in range(20):
+        U = eq.random_state((1,), seed=int(rng.integers(1 << 30)))[0]
+        n, t1, t2 = frame(rng)
+        F = O.riemann_point(w.ranks[0], RIEMANN[solver], U, U, n, t1, t2)
+        f, g, h = O.eval_flux3d(w.ranks[0], U)
+        ref = f * n[0] + g * n[1] + h * n[2]
+        assert np.max(np.abs(F - ref)) < 1e-13 * max(1.0, np.max(np.abs(ref)))
+    w.close()
+
+
+@pytest.mark.parametrize("solver", ["lf", "roe", "roeentropyfix", "hllc", "hll"])
+def test_riemann_conservation_under_flip(solver):
+    """F*(U_L,U_R;n) = -F*(U_R,U_L;-n): the property that makes Flux_slave = Flux_master with a sign in SurfInt correct."""
+    ranks, w = world(tgv_box(2), 2, B.NODE_GAUSS, dict(parabolic=False))
+    rng = np.random.default_rng(11)
+    eq = ranks[0].eqn
+    for _ in range(20):
+        UL = eq.random_state((1,), seed=int(rng.integers(1 << 30)))[0]
+        UR = eq.random_state((1,), seed=int(rng.integers(1 << 30)))[0]
+        n, t1, t2 = frame(rng)
+        F1 = O.riemann_point(w.ranks[0], RIEMANN[solver], UL, UR, n, t1, t2)
+        F2 = O.riemann_point(w.ranks[0], RIEMANN[solver], UR, UL, -n, -t1, t2)
+        assert np.max(np.abs(F1 + F2)) < 1e-12
+    w.close()
+
+
+@pytest.mark.parametrize("stype", ["sd", "du", "kg", "pi"])
+def test_split_flux_consistency_and_symmetry(stype):
+    """(2) f#_vol(U,U;M,M) = 2 M.F(U); symmetric in its arguments (splitflux.f90:21-22)."""
+    ranks, w = world(tgv_box(2), 2, B.NODE_GAUSS_LOBATTO, dict(parabolic=False, split_dg=True, split_dg_type=stype))
+    rng = np.random.default_rng(3)
+    eq = ranks[0].eqn
+    for _ in range(20):
+        U = eq.random_state((1,), seed=int(rng.integers(1 << 30)))[0]
+        V = eq.random_state((1,), seed=int(rng.integers(1 << 30)))[0]
+        M, M2 = rng.normal(size=3), rng.normal(size=3)
+        F = O.split_volume_flux(w.ranks[0], SPLITDG[stype], U, U, M, M)
+        f, g, h = O.eval_flux3d(w.ranks[0], U)
+        assert np.max(np.abs(F - 2 * (M[0] * f + M[1] * g + M[2] * h))) < 1e-12
+        Fa = O.split_volume_flux(w.ranks[0], SPLITDG[stype], U, V, M, M2)
+        Fb = O.split_volume_flux(w.ranks[0], SPLITDG[stype], V, U, M2, M)
+        assert np.max(np.abs(Fa - Fb)) < 1e-13
+    w.close()
+
+
+CURVED = dict(x0=(-1.0, -1.0, -1.0), length=(2.0, 2.0, 2.0), ngeo=2, deform=0.1)
+
+CONFIGS = [
+    (B.NODE_GAUSS, dict(parabolic=True, riemann="roe", mu0=1e-2)),
+    (B.NODE_GAUSS, dict(parabolic=True, riemann="hllc", mu0=1e-2)),
+    (B.NODE_GAUSS_LOBATTO, dict(parabolic=True, riemann="lf", mu0=1e-2)),
+    (B.NODE_GAUSS_LOBATTO, dict(parabolic=True, split_dg=True, split_dg_type="pi", riemann="lf", mu0=1e-2)),
+    (B.NODE_GAUSS_LOBATTO, dict(parabolic=True, split_dg=True, split_dg_type="kg", riemann="roeentropyfix", mu0=1e-2)),
+    (B.NODE_GAUSS, dict(parabolic=False, riemann="roeentropyfix")),
+]
+
+
+@pytest.mark.parametrize("node,eqn", CONFIGS)
+def test_freestream_preservation_curved(node, eqn):
+    """(3) constant state => Ut = 0, gradU = 0 on the sine-deformed periodic mesh (run_basic/freestream_3D: L2 <= 1e-12)."""
+    ranks, w = world(BoxSpec((3, 2, 2), **CURVED), 4, node, eqn)
+    eq = ranks[0].eqn
+    prim = np.array([1.1, 0.3, -0.2, 0.15, 0.9, 0.0])
+    prim[5] = prim[4] / (prim[0] * eq.R)
+    U = np.broadcast_to(eq.prim_to_cons(prim), ranks[0].mesh.Elem_xGP.shape[:-1] + (5,))
+    w.set_state([U])
+    w.dg_time_derivative(0.0)
+    assert np.max(np.abs(w.ranks[0].array("Ut"))) < 2e-12
+    if eqn.get("parabolic"):
+        for g in ("gradUx", "gradUy", "gradUz"):
+            assert np.max(np.abs(w.ranks[0].array(g))) < 2e-12
+    w.close()
+
+
+@pytest.mark.parametrize("node,eqn", CONFIGS)
+def test_discrete_conservation(node, eqn):
+    """(4) sum_elem sum_ijk w_ijk Ut / sJ = 0 on a periodic (curved) mesh."""
+    N = 4
+    ranks, w = world(BoxSpec((3, 2, 2), **CURVED), N, node, eqn)
+    r = ranks[0]
+    U = r.eqn.smooth_state(r.mesh.Elem_xGP, length=2.0)
+    w.set_state([U])
+    w.dg_time_derivative(0.0)
+    Ut = w.ranks[0].array("Ut")
+    w3 = np.einsum("k,j,i->kji", r.basis.wGP, r.basis.wGP, r.basis.wGP)
+    integ = np.einsum("ekjiv,ekji->v", Ut, w3[None] / r.mesh.sJ)
+    scale = np.einsum("ekjiv,ekji->v", np.abs(Ut), w3[None] / r.mesh.sJ)
+    assert np.max(np.abs(integ) / scale) < 1e-12
+    w.close()
+
+
+def test_weak_equals_split_sd_on_lgl_euler():
+    """(6) Euler weak form == split form with the SD flux on LGL nodes.
+
+    Algebraic identity for element-wise constant metrics (on curved elements the SD split averages the metrics, which is a
+    different -- metric-dealiased -- discretisation), so the box is Cartesian with anisotropic spacing."""
+    N = 5
+    spec = BoxSpec((2, 3, 2), x0=(-1.0, -1.0, -1.0), length=(2.0, 2.0, 2.0))
+    ra, wa = world(spec, N, B.NODE_GAUSS_LOBATTO, dict(parabolic=False, riemann="lf"))
+    rb, wb = world(spec, N, B.NODE_GAUSS_LOBATTO, dict(parabolic=False, riemann="lf", split_dg=True, split_dg_type="sd"))
+    U = ra[0].eqn.smooth_state(ra[0].mesh.Elem_xGP, length=2.0)
+    for w in (wa, wb):
+        w.set_state([U])
+        w.dg_time_derivative(0.0)
+    a, b = wa.ranks[0].array("Ut"), wb.ranks[0].array("Ut")
+    assert np.max(np.abs(a - b)) / np.max(np.abs(a)) < 1e-12
+    wa.close()
+    wb.close()
+
+
+@pytest.mark.parametrize("nranks,partition,blocks", [(2, "linear", None), (3, "linear", None), (4, "block", (2, 2, 1))])
+@pytest.mark.parametrize("node,eqn", [CONFIGS[0], CONFIGS[3]])
+def test_partition_invariance(node, eqn, nranks, partition, blocks):
+    """(7) 1-rank vs k-rank results agree to round-off (what reggie's MPI=1,2 runs assert with one reference file)."""
+    N = 3
+    spec = BoxSpec((4, 4, 2), **CURVED)
+    r1, w1 = world(spec, N, node, eqn)
+    rk, wk = world(spec, N, node, eqn, nranks=nranks, partition=partition, blocks=blocks)
+    U1 = r1[0].eqn.smooth_state(r1[0].mesh.Elem_xGP, length=2.0)
+    w1.set_state([U1])
+    wk.set_state([r.eqn.smooth_state(r.mesh.Elem_xGP, length=2.0) for r in rk])
+    dt1 = w1.calc_timestep()
+    dtk = wk.calc_timestep()
+    assert abs(dt1[0] - dtk[0]) <= 1e-15 * dt1[0] and dt1[3] == 0
+    for w in (w1, wk):
+        w.timestep(0.0, 0.5 * dt1[0])
+    full = w1.ranks[0].array("U")
+    for r, o in zip(rk, wk.ranks):
+        assert np.max(np.abs(o.array("U") - full[r.mesh.elem_gid])) < 1e-13
+    w1.close()
+    wk.close()
+
+
+def test_first_timestep_tgv_split_regression():
+    """8^3 box, GL N=7, CFLscale 0.8 -> first adaptive dt ~ 2.42e-3 (regression CSV row 2 Time / 10)."""
+    ranks, w = world(tgv_box(8), 7, B.NODE_GAUSS_LOBATTO,
+                     dict(parabolic=True, split_dg=True, split_dg_type="pi", riemann="roeentropyfix", cfl_scale=0.8,
+                          dfl_scale=0.8, **TGV_EQN))
+    r = ranks[0]
+    w.set_state([r.eqn.tgv_state(r.mesh.Elem_xGP)])
+    dt, dtc, dtv, err = w.calc_timestep()
+    assert err == 0
+    assert abs(dt - 0.24223660622174e-01 / 10) / dt < 2e-3
+    w.close()
