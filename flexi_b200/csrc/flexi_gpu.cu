@@ -1,0 +1,907 @@
+// flexi_gpu.cu -- host side of the C ABI declared in include/flexi_gpu.h: device data model, launch order of one
+// DGTimeDerivative_weakForm evaluation (dg/dg.f90:221-678), the LSERK loop (timedisc/timestep.f90:82-152), CalcTimeStep
+// (equations/navierstokes/calctimestep.f90:89-227) and the side-halo exchange (mpi/mpi.f90:244-445 -> NCCL send/recv).
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "common_kernels.cuh"
+#include "nccl_dyn.h"
+#include "np_ops.h"
+
+using namespace fx;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CK(call)                                                                                              \
+  do {                                                                                                        \
+    cudaError_t e_ = (call);                                                                                  \
+    if (e_ != cudaSuccess) return fail(FLEXI_GPU_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+  } while (0)
+#define CKN(call)                                                                                             \
+  do {                                                                                                        \
+    int e_ = (call);                                                                                          \
+    if (e_ != 0) return fail(FLEXI_GPU_ERR_NCCL, "%s:%d %s: %s", __FILE__, __LINE__, #call, nccl().GetErrorString(e_)); \
+  } while (0)
+#define CKR(call)            \
+  do {                       \
+    int r_ = (call);         \
+    if (r_ != 0) return r_;  \
+  } while (0)
+
+const NpOps* ops_for(int np) {
+  switch (np) {
+    case 2: return fx_ops_np2();
+    case 3: return fx_ops_np3();
+    case 4: return fx_ops_np4();
+    case 5: return fx_ops_np5();
+    case 6: return fx_ops_np6();
+    case 7: return fx_ops_np7();
+    case 8: return fx_ops_np8();
+    case 9: return fx_ops_np9();
+    case 10: return fx_ops_np10();
+    default: return nullptr;
+  }
+}
+
+struct TimedLaunch {
+  cudaEvent_t a, b;
+  int kc;
+};
+
+}  // namespace
+
+struct flexi_gpu_handle {
+  // configuration
+  int N = 0, np = 0, np2 = 0, np3 = 0;
+  bool gl = false, split = false, para = false;
+  int nvl = 5, lifting = 1;
+  int nElems = 0, nSides = 0, nBCSides = 0, nInnerSides = 0, nMINE = 0, nYOUR = 0;
+  int firstInner = 0, firstMINE = 0, firstYOUR = 0;  // 0-based
+  int device = 0;
+  const NpOps* ops = nullptr;
+  Eqn q{};
+  Mesh m{};
+  double CFLScale = 0, DFLScale = 0;
+  std::vector<double> RKA, RKb, RKc;
+  // partition
+  int myRank = 0, nProcs = 1;
+  std::vector<int> NbProc, nMINE_Proc, nYOUR_Proc, offMINE, offYOUR;
+  ncclComm_t comm = nullptr;
+  // device memory
+  std::vector<void*> owned;
+  double *U = nullptr, *UtVol = nullptr, *UtTmp = nullptr, *Ut = nullptr;
+  double *Um = nullptr, *Us = nullptr, *Flux = nullptr;
+  double *gm[3] = {nullptr, nullptr, nullptr}, *gs[3] = {nullptr, nullptr, nullptr}, *gvol[3] = {nullptr, nullptr, nullptr};
+  double *MetAdv = nullptr, *MetVisc = nullptr, *dtElem = nullptr, *dt3 = nullptr;
+  double* dt3_host = nullptr;  // pinned
+  double* stage = nullptr;     // AoS staging buffer
+  size_t stageDoubles = 0;
+  int32_t *elemsInner = nullptr, *elemsBnd = nullptr;
+  int nElemsInner = 0, nElemsBnd = 0;
+  bool keepGrad = false;
+  bool tracesValid = false;
+  // execution
+  cudaStream_t sc = nullptr, sx = nullptr;
+  cudaEvent_t evProd = nullptr, evX[3] = {nullptr, nullptr, nullptr};
+  // accounting
+  int64_t launches = 0, h2d = 0, d2h = 0;
+  bool profiling = false;
+  std::vector<TimedLaunch> timed;
+  double kc_ms[KC_COUNT] = {0};
+  int64_t kc_n[KC_COUNT] = {0};
+};
+
+namespace {
+
+typedef flexi_gpu_handle H;
+
+template <class T>
+int dalloc(H* h, T** p, size_t n) {
+  void* v = nullptr;
+  CK(cudaMalloc(&v, std::max<size_t>(n, 1) * sizeof(T)));
+  h->owned.push_back(v);
+  *p = (T*)v;
+  return 0;
+}
+
+int ensure_stage(H* h, size_t doubles) {
+  if (h->stageDoubles >= doubles) return 0;
+  if (h->stage) {
+    CK(cudaFree(h->stage));
+    h->stage = nullptr;
+    h->stageDoubles = 0;
+  }
+  CK(cudaMalloc((void**)&h->stage, doubles * sizeof(double)));
+  h->stageDoubles = doubles;
+  return 0;
+}
+
+struct Timer {
+  H* h;
+  int kc;
+  cudaStream_t s;
+  TimedLaunch t{};
+  Timer(H* h_, int kc_, cudaStream_t s_) : h(h_), kc(kc_), s(s_) {
+    h->launches++;
+    if (h->profiling) {
+      cudaEventCreate(&t.a);
+      cudaEventCreate(&t.b);
+      t.kc = kc;
+      cudaEventRecord(t.a, s);
+    }
+  }
+  ~Timer() {
+    if (h->profiling) {
+      cudaEventRecord(t.b, s);
+      h->timed.push_back(t);
+    }
+  }
+};
+
+int collect_times(H* h) {
+  for (auto& t : h->timed) {
+    CK(cudaEventSynchronize(t.b));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, t.a, t.b));
+    h->kc_ms[t.kc] += ms;
+    h->kc_n[t.kc]++;
+    cudaEventDestroy(t.a);
+    cudaEventDestroy(t.b);
+  }
+  h->timed.clear();
+  return 0;
+}
+
+// host AoS [item][n][v] -> device SoA [item][v][n]
+int upload_aos(H* h, const double* host, double* dev, int nv, int npts, long nItems) {
+  const size_t n = (size_t)nItems * nv * npts;
+  if (n == 0) return 0;
+  CKR(ensure_stage(h, n));
+  CK(cudaMemcpyAsync(h->stage, host, n * sizeof(double), cudaMemcpyHostToDevice, h->sc));
+  h->h2d += (int64_t)(n * sizeof(double));
+  {
+    Timer tm(h, KC_LAYOUT, h->sc);
+    k_aos_to_soa<<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 16), 256, 0, h->sc>>>(h->stage, dev, nv, npts, nItems);
+  }
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->sc));
+  return 0;
+}
+int download_aos(H* h, const double* dev, double* host, int nv, int npts, long nItems) {
+  const size_t n = (size_t)nItems * nv * npts;
+  if (n == 0) return 0;
+  CKR(ensure_stage(h, n));
+  {
+    Timer tm(h, KC_LAYOUT, h->sc);
+    k_soa_to_aos<<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 16), 256, 0, h->sc>>>(dev, h->stage, nv, npts, nItems);
+  }
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(host, h->stage, n * sizeof(double), cudaMemcpyDeviceToHost, h->sc));
+  h->d2h += (int64_t)(n * sizeof(double));
+  CK(cudaStreamSynchronize(h->sc));
+  return 0;
+}
+
+// ---- halo exchange: contiguous side slices per neighbour rank (mpi.f90:269-314) --------------------------------------------
+// sendMine: send my MINE slices and receive into my YOUR slices (SendID=1, master -> slave); otherwise the other direction.
+int exchange_group(H* h, double* const* arrs, int nArrs, int dataSizeSide, bool sendMine) {
+  Nccl& nc = nccl();
+  CKN(nc.GroupStart());
+  for (size_t i = 0; i < h->NbProc.size(); ++i) {
+    const int nb = h->NbProc[i];
+    const int sOff = sendMine ? h->offMINE[i] : h->offYOUR[i], sN = sendMine ? h->nMINE_Proc[i] : h->nYOUR_Proc[i];
+    const int rOff = sendMine ? h->offYOUR[i] : h->offMINE[i], rN = sendMine ? h->nYOUR_Proc[i] : h->nMINE_Proc[i];
+    for (int a = 0; a < nArrs; ++a) {
+      if (sN > 0) CKN(nc.Send(arrs[a] + (size_t)sOff * dataSizeSide, (size_t)sN * dataSizeSide, NCCL_DOUBLE, nb, h->comm, h->sx));
+      if (rN > 0) CKN(nc.Recv(arrs[a] + (size_t)rOff * dataSizeSide, (size_t)rN * dataSizeSide, NCCL_DOUBLE, nb, h->comm, h->sx));
+    }
+  }
+  CKN(nc.GroupEnd());
+  return 0;
+}
+
+enum { X_TRACE = 0, X_GRAD = 1, X_FLUX = 2 };
+
+int start_exchange(H* h, int kind) {
+  if (h->nProcs == 1) return 0;
+  CK(cudaEventRecord(h->evProd, h->sc));
+  CK(cudaStreamWaitEvent(h->sx, h->evProd, 0));
+  const int szU = 5 * h->np2, szG = h->nvl * h->np2;
+  if (kind == X_TRACE) {
+    // C1 (dg.f90:360-432): U_slave of YOUR sides -> master rank.  With parabolic terms the slave rank also needs U_master
+    // of its YOUR sides for the gathered lifting flux (replaces the lifting-flux message C2, lifting_br1.t90:79-83).
+    double* a1[1] = {h->Us};
+    CKR(exchange_group(h, a1, 1, szU, false));
+    if (h->para) {
+      double* a2[1] = {h->Um};
+      CKR(exchange_group(h, a2, 1, szU, true));
+    }
+  } else if (kind == X_GRAD) {  // C3 (lifting_br1.t90:150-165): gradU{x,y,z}_slave -> master rank
+    CKR(exchange_group(h, h->gs, 3, szG, false));
+  } else {  // C4 (dg.f90:607-641): Flux master -> slave rank
+    double* a1[1] = {h->Flux};
+    CKR(exchange_group(h, a1, 1, szU, true));
+  }
+  CK(cudaEventRecord(h->evX[kind], h->sx));
+  return 0;
+}
+int finish_exchange(H* h, int kind) {
+  if (h->nProcs == 1) return 0;
+  CK(cudaStreamWaitEvent(h->sc, h->evX[kind], 0));
+  return 0;
+}
+
+// ---- kernels in launch order ---------------------------------------------------------------------------------------------------
+int launch_prolong_U(H* h) {
+  ProArgs a{};
+  a.m = h->m;
+  a.V = h->U;
+  a.master = h->Um;
+  a.slave = h->Us;
+  a.nv = 5;
+  a.firstSide = 0;
+  a.lastSide = h->nSides - 1;
+  Timer tm(h, KC_PROLONG, h->sc);
+  CK(h->ops->prolong(h->gl, a, h->nElems, h->sc));
+  return 0;
+}
+
+int refresh_traces(H* h) {
+  CKR(launch_prolong_U(h));
+  CKR(start_exchange(h, X_TRACE));
+  CKR(finish_exchange(h, X_TRACE));
+  h->tracesValid = true;
+  return 0;
+}
+
+int launch_volume(H* h, const int32_t* list, int n) {
+  VolArgs a{};
+  a.m = h->m;
+  a.q = h->q;
+  a.elems = list;
+  a.nList = n;
+  a.U = h->U;
+  a.U_master = h->Um;
+  a.U_slave = h->Us;
+  a.Ut = h->UtVol;
+  for (int d = 0; d < 3; ++d) {
+    a.gm[d] = h->gm[d];
+    a.gs[d] = h->gs[d];
+    a.gvol[d] = h->keepGrad ? h->gvol[d] : nullptr;
+  }
+  Timer tm(h, KC_VOLUME, h->sc);
+  CK(h->ops->volume(h->gl, h->split, h->para, h->nvl, a, n, h->sc));
+  return 0;
+}
+
+int launch_flux(H* h, int first, int n) {
+  FluxArgs a{};
+  a.m = h->m;
+  a.q = h->q;
+  a.firstSide = first;
+  a.nSidesRange = n;
+  a.parabolic = h->para;
+  a.U_master = h->Um;
+  a.U_slave = h->Us;
+  for (int d = 0; d < 3; ++d) {
+    a.gm[d] = h->gm[d];
+    a.gs[d] = h->gs[d];
+  }
+  a.Flux = h->Flux;
+  if (n <= 0) return 0;
+  Timer tm(h, KC_FLUX, h->sc);
+  CK(h->ops->flux(a, h->sc));
+  return 0;
+}
+
+int launch_update(H* h, const int32_t* list, int n, int mode, double rkA, double b_dt) {
+  UpdArgs a{};
+  a.m = h->m;
+  a.elems = list;
+  a.nList = n;
+  a.UtVol = h->UtVol;
+  a.Flux = h->Flux;
+  a.U = h->U;
+  a.UtTmp = h->UtTmp;
+  a.UtOut = h->Ut;
+  a.U_master = h->Um;
+  a.U_slave = h->Us;
+  a.mode = mode;
+  a.rkA = rkA;
+  a.b_dt = b_dt;
+  if (n <= 0) return 0;
+  Timer tm(h, KC_UPDATE, h->sc);
+  CK(h->ops->update(h->gl, a, n, h->sc));
+  return 0;
+}
+
+// One DGTimeDerivative_weakForm evaluation (+ optional fused LSERK stage).  Launch order mirrors the reference's latency
+// hiding (dg.f90:360-651: "MPI sides first, start send, inner work, finish"): elements without MPI sides run while the
+// traces / gradients / fluxes of the MPI sides are in flight on the communication stream.
+int rhs(H* h, double t, int mode, double rkA, double b_dt) {
+  (void)t;
+  if (h->nBCSides > 0) return fail(FLEXI_GPU_ERR_UNSUPPORTED, "boundary conditions are not implemented yet (nBCSides=%d)", h->nBCSides);
+  if (!h->tracesValid) CKR(refresh_traces(h));
+  const bool multi = h->nProcs > 1;
+  if (!multi) {
+    CKR(launch_volume(h, nullptr, h->nElems));
+    CKR(launch_flux(h, h->firstInner, h->nInnerSides));
+    CKR(launch_update(h, nullptr, h->nElems, mode, rkA, b_dt));
+    return 0;
+  }
+  CKR(launch_volume(h, h->elemsInner, h->nElemsInner));
+  CKR(finish_exchange(h, X_TRACE));
+  CKR(launch_volume(h, h->elemsBnd, h->nElemsBnd));
+  if (h->para) CKR(start_exchange(h, X_GRAD));
+  CKR(launch_flux(h, h->firstInner, h->nInnerSides));
+  if (h->para) CKR(finish_exchange(h, X_GRAD));
+  CKR(launch_flux(h, h->firstMINE, h->nMINE));
+  CKR(start_exchange(h, X_FLUX));
+  CKR(launch_update(h, h->elemsInner, h->nElemsInner, mode, rkA, b_dt));
+  CKR(finish_exchange(h, X_FLUX));
+  CKR(launch_update(h, h->elemsBnd, h->nElemsBnd, mode, rkA, b_dt));
+  if (mode != 0) CKR(start_exchange(h, X_TRACE));  // traces of the updated state for the next stage
+  return 0;
+}
+
+}  // namespace
+
+// ================================================================================================================================
+extern "C" {
+
+const char* flexi_gpu_last_error(void) { return g_err.c_str(); }
+int flexi_gpu_abi_version(void) { return FLEXI_GPU_ABI_VERSION; }
+
+int flexi_gpu_nccl_unique_id(void* out) {
+  if (!out) return fail(FLEXI_GPU_ERR_ARG, "null id buffer");
+  const char* e = nccl().load();
+  if (e) return fail(FLEXI_GPU_ERR_NCCL, "%s", e);
+  ncclUniqueIdDyn id;
+  CKN(nccl().GetUniqueId(&id));
+  memcpy(out, &id, FLEXI_GPU_NCCL_ID_BYTES);
+  return 0;
+}
+
+int flexi_gpu_finalize(flexi_gpu_handle* h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  collect_times(h);
+  if (h->comm) nccl().CommDestroy(h->comm);
+  for (void* p : h->owned) cudaFree(p);
+  if (h->stage) cudaFree(h->stage);
+  if (h->dt3_host) cudaFreeHost(h->dt3_host);
+  if (h->sc) cudaStreamDestroy(h->sc);
+  if (h->sx) cudaStreamDestroy(h->sx);
+  if (h->evProd) cudaEventDestroy(h->evProd);
+  for (auto& e : h->evX)
+    if (e) cudaEventDestroy(e);
+  delete h;
+  return 0;
+}
+
+static int init_impl(const flexi_gpu_desc* d, H* h) {
+  if (d->N < 1 || d->N > 9) return fail(FLEXI_GPU_ERR_ARG, "N=%d outside 1..9", d->N);
+  if (d->nodeType != FLEXI_NODETYPE_GAUSS && d->nodeType != FLEXI_NODETYPE_GAUSS_LOBATTO) return fail(FLEXI_GPU_ERR_ARG, "bad nodeType %d", d->nodeType);
+  if (d->doWeakLifting || d->doConservativeLifting) return fail(FLEXI_GPU_ERR_UNSUPPORTED, "only the strong, non-conservative lifting (the reference default, lifting.f90:72-76) is implemented");
+  if (d->splitDG && d->nodeType != FLEXI_NODETYPE_GAUSS_LOBATTO) return fail(FLEXI_GPU_ERR_UNSUPPORTED, "split form on Gauss nodes is not implemented");
+  if (d->splitDG && !(d->splitDGType == FLEXI_SPLITDG_SD || d->splitDGType == FLEXI_SPLITDG_DU || d->splitDGType == FLEXI_SPLITDG_KG || d->splitDGType == FLEXI_SPLITDG_PI))
+    return fail(FLEXI_GPU_ERR_UNSUPPORTED, "SplitDG formulation %d is not implemented", d->splitDGType);
+  if (d->splitDG && d->riemann == FLEXI_RIEMANN_HLLC) return fail(FLEXI_GPU_ERR_ARG, "HLLC is not selectable with SPLIT_DG (riemann.f90:206-227)");
+  if (d->parabolic && d->lifting != 1) return fail(FLEXI_GPU_ERR_UNSUPPORTED, "BR2 lifting is not implemented yet");
+  if (d->parabolic && d->nVarLifting != 5 && d->nVarLifting != 4) return fail(FLEXI_GPU_ERR_ARG, "nVarLifting must be 4 or 5");
+  if (d->nElems < 1 || d->nSides < 1) return fail(FLEXI_GPU_ERR_ARG, "empty mesh");
+  if (d->nBCSides + d->nInnerSides + d->nMPISides_MINE + d->nMPISides_YOUR != d->nSides) return fail(FLEXI_GPU_ERR_ARG, "side ranges do not add up to nSides (mortars are not supported)");
+  if (d->nRKStages < 1 || !d->RKb || (d->nRKStages > 1 && (!d->RKA || !d->RKc))) return fail(FLEXI_GPU_ERR_ARG, "missing RK tables");
+  if (!d->Metrics_fTilde || !d->Metrics_gTilde || !d->Metrics_hTilde || !d->sJ || !d->NormVec || !d->TangVec1 || !d->TangVec2 || !d->SurfElem ||
+      !d->ElemToSide || !d->SideToElem || !d->S2V2 || !d->D_T || !d->D_Hat_T || !d->L_Minus || !d->L_Plus || !d->L_HatMinus || !d->L_HatPlus)
+    return fail(FLEXI_GPU_ERR_ARG, "missing mesh / basis arrays");
+  if (d->splitDG && !d->DVolSurf) return fail(FLEXI_GPU_ERR_ARG, "DVolSurf is required with splitDG");
+
+  h->N = d->N;
+  h->np = d->N + 1;
+  h->np2 = h->np * h->np;
+  h->np3 = h->np2 * h->np;
+  h->gl = d->nodeType == FLEXI_NODETYPE_GAUSS_LOBATTO;
+  h->split = d->splitDG != 0;
+  h->para = d->parabolic != 0;
+  h->nvl = h->para ? d->nVarLifting : 5;
+  h->lifting = d->lifting;
+  h->nElems = d->nElems;
+  h->nSides = d->nSides;
+  h->nBCSides = d->nBCSides;
+  h->nInnerSides = d->nInnerSides;
+  h->nMINE = d->nMPISides_MINE;
+  h->nYOUR = d->nMPISides_YOUR;
+  h->firstInner = d->nBCSides;
+  h->firstMINE = h->firstInner + d->nInnerSides;
+  h->firstYOUR = h->firstMINE + d->nMPISides_MINE;
+  h->device = d->device;
+  h->CFLScale = d->CFLScale;
+  h->DFLScale = d->DFLScale;
+  h->RKb.assign(d->RKb, d->RKb + d->nRKStages);
+  if (d->nRKStages > 1) {
+    h->RKA.assign(d->RKA, d->RKA + d->nRKStages - 1);
+    h->RKc.assign(d->RKc, d->RKc + d->nRKStages - 1);
+  }
+  h->ops = ops_for(h->np);
+  if (!h->ops) return fail(FLEXI_GPU_ERR_ARG, "no kernels for N=%d", d->N);
+
+  Eqn& q = h->q;
+  q.kappa = d->kappa;
+  q.kappaM1 = d->kappa - 1.;
+  q.sKappaM1 = 1. / q.kappaM1;
+  q.R = d->R;
+  q.sR = 1. / d->R;
+  q.mu0 = d->mu0;
+  const double cp = d->R * d->kappa / (d->kappa - 1.);  // eos.f90:136-163
+  q.lambda = d->mu0 * cp / d->Pr;
+  q.riemann = d->riemann;
+  q.splitDG = d->splitDG;
+  q.splitType = d->splitDGType;
+  q.nvl = h->nvl;
+  q.lv_vel1 = (h->nvl == 5) ? 1 : 0;
+  q.lv_temp = q.lv_vel1 + 3;
+  for (int v = 0; v < 5; ++v) q.lift_map[v] = lift_prim(h->nvl, v < h->nvl ? v : 0);
+  switch (q.riemann) {
+    case FLEXI_RIEMANN_LF: case FLEXI_RIEMANN_HLLC: case FLEXI_RIEMANN_ROE: case FLEXI_RIEMANN_ROEL2: case FLEXI_RIEMANN_ROEENTROPYFIX:
+    case FLEXI_RIEMANN_HLL: case FLEXI_RIEMANN_HLLE: case FLEXI_RIEMANN_HLLEM: break;
+    default: return fail(FLEXI_GPU_ERR_ARG, "unknown Riemann solver %d", q.riemann);
+  }
+
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  if (ndev < 1) return fail(FLEXI_GPU_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+  if (d->device < 0 || d->device >= ndev) return fail(FLEXI_GPU_ERR_ARG, "device %d not in 0..%d", d->device, ndev - 1);
+  CK(cudaSetDevice(d->device));
+  CK(h->ops->setup());
+  CK(cudaStreamCreateWithFlags(&h->sc, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&h->sx, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&h->evProd, cudaEventDisableTiming));
+  for (auto& e : h->evX) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+
+  const int np = h->np, np2 = h->np2, np3 = h->np3;
+  const size_t nE = (size_t)h->nElems, nS = (size_t)h->nSides;
+
+  // ---- geometry: AoS -> SoA on the device ----
+  double *Met = nullptr, *sJ = nullptr, *Geo = nullptr;
+  CKR(dalloc(h, &Met, nE * 9 * np3));
+  CKR(dalloc(h, &sJ, nE * np3));
+  CKR(dalloc(h, &Geo, nS * 10 * np2));
+  {
+    // metrics: three (3,i,j,k,e) arrays -> [e][9][n]; go through a temporary [3 arrays][e][3][n]
+    double* tmp = nullptr;
+    CK(cudaMalloc((void**)&tmp, nE * 3 * np3 * sizeof(double)));
+    const double* src[3] = {d->Metrics_fTilde, d->Metrics_gTilde, d->Metrics_hTilde};
+    for (int a = 0; a < 3; ++a) {
+      CKR(upload_aos(h, src[a], tmp, 3, np3, (long)nE));
+      CK(cudaMemcpy2DAsync(Met + (size_t)a * 3 * np3, (size_t)9 * np3 * sizeof(double), tmp, (size_t)3 * np3 * sizeof(double),
+                           (size_t)3 * np3 * sizeof(double), nE, cudaMemcpyDeviceToDevice, h->sc));
+      CK(cudaStreamSynchronize(h->sc));
+    }
+    CK(cudaFree(tmp));
+    CK(cudaMemcpy(sJ, d->sJ, nE * np3 * sizeof(double), cudaMemcpyHostToDevice));
+    h->h2d += (int64_t)(nE * np3 * sizeof(double));
+    CK(cudaMalloc((void**)&tmp, nS * 3 * np2 * sizeof(double)));
+    const double* vs[3] = {d->NormVec, d->TangVec1, d->TangVec2};
+    for (int a = 0; a < 3; ++a) {
+      CKR(upload_aos(h, vs[a], tmp, 3, np2, (long)nS));
+      CK(cudaMemcpy2DAsync(Geo + (size_t)a * 3 * np2, (size_t)10 * np2 * sizeof(double), tmp, (size_t)3 * np2 * sizeof(double),
+                           (size_t)3 * np2 * sizeof(double), nS, cudaMemcpyDeviceToDevice, h->sc));
+      CK(cudaStreamSynchronize(h->sc));
+    }
+    CK(cudaFree(tmp));
+    CK(cudaMemcpy2D(Geo + (size_t)9 * np2, (size_t)10 * np2 * sizeof(double), d->SurfElem, (size_t)np2 * sizeof(double), (size_t)np2 * sizeof(double), nS,
+                    cudaMemcpyHostToDevice));
+    h->h2d += (int64_t)(nS * np2 * sizeof(double));
+  }
+  h->m.nElems = h->nElems;
+  h->m.nSides = h->nSides;
+  h->m.Met = Met;
+  h->m.sJ = sJ;
+  h->m.Geo = Geo;
+
+  // ---- connectivity ----
+  {
+    std::vector<SideRef> e2s(nE * 6);
+    for (size_t e = 0; e < nE; ++e)
+      for (int ls = 0; ls < 6; ++ls) {
+        const int32_t sid = d->ElemToSide[(e * 6 + ls) * 2 + 0], flip = d->ElemToSide[(e * 6 + ls) * 2 + 1];
+        if (sid < 1 || sid > h->nSides || flip < 0 || flip > 4) return fail(FLEXI_GPU_ERR_ARG, "ElemToSide(%d,%d) out of range", ls + 1, (int)e + 1);
+        e2s[e * 6 + ls].side = sid - 1;
+        e2s[e * 6 + ls].flip = flip;
+      }
+    SideRef* de = nullptr;
+    CKR(dalloc(h, &de, e2s.size()));
+    CK(cudaMemcpy(de, e2s.data(), e2s.size() * sizeof(SideRef), cudaMemcpyHostToDevice));
+    h->m.e2s = de;
+    std::vector<int32_t> s2v(5 * 6 * np2), v2s(5 * 6 * np2);
+    for (int f = 0; f < 5; ++f)
+      for (int ls = 0; ls < 6; ++ls)
+        for (int qq = 0; qq < np; ++qq)
+          for (int p = 0; p < np; ++p) {
+            const size_t o = ((((size_t)ls * 5 + f) * np + qq) * np + p) * 2;
+            const int a = d->S2V2[o], b = d->S2V2[o + 1];
+            if (a < 0 || a >= np || b < 0 || b >= np) return fail(FLEXI_GPU_ERR_ARG, "S2V2 entry out of range");
+            s2v[(f * 6 + ls) * np2 + qq * np + p] = a + np * b;
+            v2s[(f * 6 + ls) * np2 + a + np * b] = qq * np + p;
+          }
+    int32_t *d1 = nullptr, *d2 = nullptr;
+    CKR(dalloc(h, &d1, s2v.size()));
+    CKR(dalloc(h, &d2, v2s.size()));
+    CK(cudaMemcpy(d1, s2v.data(), s2v.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d2, v2s.data(), v2s.size() * 4, cudaMemcpyHostToDevice));
+    h->m.s2v2 = d1;
+    h->m.v2s = d2;
+    // elements with / without MPI sides
+    std::vector<int32_t> inner, bnd;
+    for (size_t e = 0; e < nE; ++e) {
+      bool mpi = false;
+      for (int ls = 0; ls < 6; ++ls) mpi |= e2s[e * 6 + ls].side >= h->firstMINE;
+      (mpi ? bnd : inner).push_back((int32_t)e);
+    }
+    h->nElemsInner = (int)inner.size();
+    h->nElemsBnd = (int)bnd.size();
+    CKR(dalloc(h, &h->elemsInner, inner.size()));
+    CKR(dalloc(h, &h->elemsBnd, bnd.size()));
+    if (!inner.empty()) CK(cudaMemcpy(h->elemsInner, inner.data(), inner.size() * 4, cudaMemcpyHostToDevice));
+    if (!bnd.empty()) CK(cudaMemcpy(h->elemsBnd, bnd.data(), bnd.size() * 4, cudaMemcpyHostToDevice));
+  }
+  // ---- basis ----
+  {
+    std::vector<double> b(3 * np2 + 4 * np, 0.);
+    auto put = [&](int off, const double* Mf) {  // Fortran M(l,i) at Mf[i*np+l] -> b[l*np+i]
+      for (int l = 0; l < np; ++l)
+        for (int i = 0; i < np; ++i) b[off + l * np + i] = Mf[(size_t)i * np + l];
+    };
+    put(0, d->D_T);
+    put(np2, d->D_Hat_T);
+    if (d->DVolSurf) put(2 * np2, d->DVolSurf);
+    for (int l = 0; l < np; ++l) {
+      b[3 * np2 + l] = d->L_Minus[l];
+      b[3 * np2 + np + l] = d->L_Plus[l];
+      b[3 * np2 + 2 * np + l] = d->L_HatMinus[l];
+      b[3 * np2 + 3 * np + l] = d->L_HatPlus[l];
+    }
+    double* db = nullptr;
+    CKR(dalloc(h, &db, b.size()));
+    CK(cudaMemcpy(db, b.data(), b.size() * 8, cudaMemcpyHostToDevice));
+    h->m.basis = db;
+  }
+  h->m.sideBC = nullptr;
+
+  // ---- state ----
+  CKR(dalloc(h, &h->U, nE * 5 * np3));
+  CKR(dalloc(h, &h->UtVol, nE * 5 * np3));
+  CKR(dalloc(h, &h->UtTmp, nE * 5 * np3));
+  CKR(dalloc(h, &h->Um, nS * 5 * np2));
+  CKR(dalloc(h, &h->Us, nS * 5 * np2));
+  CKR(dalloc(h, &h->Flux, nS * 5 * np2));
+  CK(cudaMemset(h->U, 0, nE * 5 * np3 * 8));
+  CK(cudaMemset(h->UtTmp, 0, nE * 5 * np3 * 8));
+  CK(cudaMemset(h->Um, 0, nS * 5 * np2 * 8));
+  CK(cudaMemset(h->Us, 0, nS * 5 * np2 * 8));
+  CK(cudaMemset(h->Flux, 0, nS * 5 * np2 * 8));
+  if (h->para) {
+    for (int dd = 0; dd < 3; ++dd) {
+      CKR(dalloc(h, &h->gm[dd], nS * h->nvl * np2));
+      CKR(dalloc(h, &h->gs[dd], nS * h->nvl * np2));
+      CK(cudaMemset(h->gm[dd], 0, nS * h->nvl * np2 * 8));
+      CK(cudaMemset(h->gs[dd], 0, nS * h->nvl * np2 * 8));
+    }
+  }
+  // ---- CalcTimeStep tables ----
+  CKR(dalloc(h, &h->MetAdv, nE * 3 * np3));
+  CKR(dalloc(h, &h->MetVisc, nE * 3 * np3));
+  CKR(dalloc(h, &h->dtElem, nE * 3));
+  CKR(dalloc(h, &h->dt3, 3));
+  CK(cudaMallocHost((void**)&h->dt3_host, 3 * sizeof(double)));
+  {
+    DtInitArgs a{};
+    a.Met = Met;
+    a.sJ = sJ;
+    a.MetAdv = h->MetAdv;
+    a.MetVisc = h->MetVisc;
+    a.KappasPr_max = fmax(4. / 3., d->kappa / d->Pr);
+    a.nElems = h->nElems;
+    CK(h->ops->dt_init(a, h->sc));
+    h->launches++;
+  }
+  // ---- partition ----
+  h->myRank = d->myRank;
+  h->nProcs = d->nProcs < 1 ? 1 : d->nProcs;
+  if (h->nProcs > 1) {
+    if (d->nNbProcs < 0 || (d->nNbProcs > 0 && (!d->NbProc || !d->nMPISides_MINE_Proc || !d->nMPISides_YOUR_Proc || !d->offsetMPISides_MINE || !d->offsetMPISides_YOUR)))
+      return fail(FLEXI_GPU_ERR_ARG, "missing neighbour tables");
+    for (int i = 0; i < d->nNbProcs; ++i) {
+      h->NbProc.push_back(d->NbProc[i]);
+      h->nMINE_Proc.push_back(d->nMPISides_MINE_Proc[i]);
+      h->nYOUR_Proc.push_back(d->nMPISides_YOUR_Proc[i]);
+      h->offMINE.push_back(d->offsetMPISides_MINE[i]);
+      h->offYOUR.push_back(d->offsetMPISides_YOUR[i]);
+      if (d->NbProc[i] < 0 || d->NbProc[i] >= h->nProcs || d->NbProc[i] == h->myRank) return fail(FLEXI_GPU_ERR_ARG, "bad neighbour rank %d", d->NbProc[i]);
+      if (h->offMINE[i] < h->firstMINE || h->offMINE[i] + h->nMINE_Proc[i] > h->firstYOUR || h->offYOUR[i] < h->firstYOUR || h->offYOUR[i] + h->nYOUR_Proc[i] > h->nSides)
+        return fail(FLEXI_GPU_ERR_ARG, "neighbour %d: side slices outside the MPI side ranges", i);
+    }
+    if (!d->ncclUniqueId) return fail(FLEXI_GPU_ERR_ARG, "nProcs>1 needs the broadcast ncclUniqueId");
+    const char* e = nccl().load();
+    if (e) return fail(FLEXI_GPU_ERR_NCCL, "%s", e);
+    ncclUniqueIdDyn id;
+    memcpy(&id, d->ncclUniqueId, sizeof id);
+    CKN(nccl().CommInitRank(&h->comm, h->nProcs, id, h->myRank));
+  } else if (h->nMINE + h->nYOUR > 0) {
+    return fail(FLEXI_GPU_ERR_ARG, "MPI sides present but nProcs == 1");
+  }
+  CK(cudaStreamSynchronize(h->sc));
+  CK(cudaDeviceSynchronize());
+  return 0;
+}
+
+int flexi_gpu_init(const flexi_gpu_desc* d, flexi_gpu_handle** out) {
+  if (!d || !out) return fail(FLEXI_GPU_ERR_ARG, "null argument");
+  *out = nullptr;
+  if (d->abi_version != FLEXI_GPU_ABI_VERSION || d->struct_bytes != (int)sizeof(flexi_gpu_desc))
+    return fail(FLEXI_GPU_ERR_ARG, "descriptor ABI mismatch: version %d (library %d), %d bytes (library %d)", d->abi_version, FLEXI_GPU_ABI_VERSION,
+                d->struct_bytes, (int)sizeof(flexi_gpu_desc));
+  H* h = new H();
+  const int r = init_impl(d, h);
+  if (r != 0) {
+    const std::string keep = g_err;
+    flexi_gpu_finalize(h);
+    g_err = keep;
+    return r;
+  }
+  *out = h;
+  return 0;
+}
+
+#define ENTER(h)                                        \
+  if (!(h)) return fail(FLEXI_GPU_ERR_ARG, "null handle"); \
+  CK(cudaSetDevice((h)->device));
+
+int flexi_gpu_set_state(flexi_gpu_handle* h, const double* U) {
+  ENTER(h);
+  if (!U) return fail(FLEXI_GPU_ERR_ARG, "null U");
+  CKR(upload_aos(h, U, h->U, 5, h->np3, h->nElems));
+  h->tracesValid = false;
+  CKR(refresh_traces(h));
+  CK(cudaStreamSynchronize(h->sc));
+  return 0;
+}
+
+int flexi_gpu_get_state(flexi_gpu_handle* h, double* U) {
+  ENTER(h);
+  if (!U) return fail(FLEXI_GPU_ERR_ARG, "null U");
+  return download_aos(h, h->U, U, 5, h->np3, h->nElems);
+}
+
+int flexi_gpu_dg_time_derivative(flexi_gpu_handle* h, double t, double* Ut) {
+  ENTER(h);
+  if (!h->Ut) CKR(dalloc(h, &h->Ut, (size_t)h->nElems * 5 * h->np3));
+  CKR(rhs(h, t, 0, 0., 0.));
+  if (Ut) return download_aos(h, h->Ut, Ut, 5, h->np3, h->nElems);
+  return 0;
+}
+
+int flexi_gpu_timestep_n(flexi_gpu_handle* h, double* t, double dt, int32_t nSteps) {
+  ENTER(h);
+  if (!t) return fail(FLEXI_GPU_ERR_ARG, "null t");
+  const int nStages = (int)h->RKb.size();
+  double tt = *t;
+  for (int s = 0; s < nSteps; ++s) {
+    for (int iStage = 1; iStage <= nStages; ++iStage) {  // timestep.f90:115-133
+      const double tStage = (iStage == 1) ? tt : tt + h->RKc[iStage - 2] * dt;
+      CKR(rhs(h, tStage, iStage == 1 ? 1 : 2, iStage == 1 ? 0. : h->RKA[iStage - 2], h->RKb[iStage - 1] * dt));
+    }
+    tt += dt;
+  }
+  return 0;
+}
+
+int flexi_gpu_timestep(flexi_gpu_handle* h, double* t, double dt) { return flexi_gpu_timestep_n(h, t, dt, 1); }
+
+int flexi_gpu_calc_timestep(flexi_gpu_handle* h, double* dt_min, double* dt_conv, double* dt_visc, int32_t* errType) {
+  ENTER(h);
+  DtArgs a{};
+  a.m = h->m;
+  a.q = h->q;
+  a.U = h->U;
+  a.MetAdv = h->MetAdv;
+  a.MetVisc = h->MetVisc;
+  a.CFLScale = h->CFLScale;
+  a.DFLScale = h->DFLScale;
+  a.parabolic = h->para;
+  a.out = h->dtElem;
+  {
+    Timer tm(h, KC_DT, h->sc);
+    CK(h->ops->dt(a, h->nElems, h->sc));
+    k_dt_reduce<<<1, 256, 0, h->sc>>>(h->dtElem, h->nElems, h->dt3);
+    h->launches++;
+  }
+  CK(cudaGetLastError());
+  if (h->nProcs > 1) {  // MPI_ALLREDUCE(MIN) of (dtConv, dtVisc, -errType), calctimestep.f90:217-222
+    CKN(nccl().AllReduce(h->dt3, h->dt3, 3, NCCL_DOUBLE, NCCL_MIN, h->comm, h->sc));
+  }
+  CK(cudaMemcpyAsync(h->dt3_host, h->dt3, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->sc));
+  h->d2h += 24;
+  CK(cudaStreamSynchronize(h->sc));
+  const double c = h->dt3_host[0], v = h->dt3_host[1];
+  if (dt_conv) *dt_conv = c;
+  if (dt_visc) *dt_visc = v;
+  if (dt_min) *dt_min = fmin(c, v);
+  if (errType) *errType = (int32_t)(-h->dt3_host[2]);
+  return 0;
+}
+
+int flexi_gpu_keep_gradients(flexi_gpu_handle* h, int32_t on) {
+  ENTER(h);
+  if (on && !h->para) return fail(FLEXI_GPU_ERR_ARG, "no gradients without parabolic terms");
+  if (on && !h->gvol[0])
+    for (int d = 0; d < 3; ++d) {
+      CKR(dalloc(h, &h->gvol[d], (size_t)h->nElems * h->nvl * h->np3));
+      CK(cudaMemset(h->gvol[d], 0, (size_t)h->nElems * h->nvl * h->np3 * 8));
+    }
+  h->keepGrad = on != 0;
+  return 0;
+}
+
+int flexi_gpu_get_array(flexi_gpu_handle* h, int32_t which, double* out) {
+  ENTER(h);
+  if (!out) return fail(FLEXI_GPU_ERR_ARG, "null output");
+  const int np2 = h->np2, np3 = h->np3;
+  switch (which) {
+    case FLEXI_ARR_U: return download_aos(h, h->U, out, 5, np3, h->nElems);
+    case FLEXI_ARR_UT:
+      if (!h->Ut) return fail(FLEXI_GPU_ERR_ARG, "Ut is only available after flexi_gpu_dg_time_derivative");
+      return download_aos(h, h->Ut, out, 5, np3, h->nElems);
+    case FLEXI_ARR_U_MASTER: return download_aos(h, h->Um, out, 5, np2, h->nSides);
+    case FLEXI_ARR_U_SLAVE: return download_aos(h, h->Us, out, 5, np2, h->nSides);
+    case FLEXI_ARR_FLUX: return download_aos(h, h->Flux, out, 5, np2, h->nSides);
+    case FLEXI_ARR_GRADUX: case FLEXI_ARR_GRADUY: case FLEXI_ARR_GRADUZ: {
+      if (!h->para) return fail(FLEXI_GPU_ERR_ARG, "no gradients without parabolic terms");
+      if (!h->keepGrad) {
+        // volume gradients normally never leave the SM; on first request they are recomputed from the current U
+        // and kept from then on for every later evaluation
+        CKR(flexi_gpu_keep_gradients(h, 1));
+        if (!h->Ut) CKR(dalloc(h, &h->Ut, (size_t)h->nElems * 5 * h->np3));
+        CKR(rhs(h, 0., 0, 0., 0.));
+      }
+      return download_aos(h, h->gvol[which - FLEXI_ARR_GRADUX], out, h->nvl, np3, h->nElems);
+    }
+    case FLEXI_ARR_GRADUX_MASTER: case FLEXI_ARR_GRADUY_MASTER: case FLEXI_ARR_GRADUZ_MASTER:
+      if (!h->para) return fail(FLEXI_GPU_ERR_ARG, "no gradients without parabolic terms");
+      return download_aos(h, h->gm[which - FLEXI_ARR_GRADUX_MASTER], out, h->nvl, np2, h->nSides);
+    case FLEXI_ARR_GRADUX_SLAVE: case FLEXI_ARR_GRADUY_SLAVE: case FLEXI_ARR_GRADUZ_SLAVE:
+      if (!h->para) return fail(FLEXI_GPU_ERR_ARG, "no gradients without parabolic terms");
+      return download_aos(h, h->gs[which - FLEXI_ARR_GRADUX_SLAVE], out, h->nvl, np2, h->nSides);
+    default: return fail(FLEXI_GPU_ERR_ARG, "unknown array id %d", which);
+  }
+}
+
+int flexi_gpu_prolong_to_face(flexi_gpu_handle* h, const double* Uvol, double* Uface_master, double* Uface_slave, int32_t doMPISides) {
+  ENTER(h);
+  if (!Uvol || !Uface_master || !Uface_slave) return fail(FLEXI_GPU_ERR_ARG, "null argument");
+  const size_t nV = (size_t)h->nElems * 5 * h->np3, nF = (size_t)h->nSides * 5 * h->np2;
+  double *dV = nullptr, *dM = nullptr, *dS = nullptr;
+  CK(cudaMalloc((void**)&dV, nV * 8));
+  CK(cudaMalloc((void**)&dM, nF * 8));
+  CK(cudaMalloc((void**)&dS, nF * 8));
+  int r = upload_aos(h, Uvol, dV, 5, h->np3, h->nElems);
+  if (!r) r = upload_aos(h, Uface_master, dM, 5, h->np2, h->nSides);
+  if (!r) r = upload_aos(h, Uface_slave, dS, 5, h->np2, h->nSides);
+  if (!r) {
+    ProArgs a{};
+    a.m = h->m;
+    a.V = dV;
+    a.master = dM;
+    a.slave = dS;
+    a.nv = 5;
+    // prolongtoface.t90:75-81
+    a.firstSide = doMPISides ? h->firstYOUR : 0;
+    a.lastSide = doMPISides ? h->nSides - 1 : h->firstYOUR - 1;
+    Timer tm(h, KC_PROLONG, h->sc);
+    cudaError_t e = h->ops->prolong(h->gl, a, h->nElems, h->sc);
+    if (e != cudaSuccess) r = fail(FLEXI_GPU_ERR_CUDA, "prolong: %s", cudaGetErrorString(e));
+  }
+  if (!r) r = download_aos(h, dM, Uface_master, 5, h->np2, h->nSides);
+  if (!r) r = download_aos(h, dS, Uface_slave, 5, h->np2, h->nSides);
+  cudaFree(dV);
+  cudaFree(dM);
+  cudaFree(dS);
+  return r;
+}
+
+int flexi_gpu_surf_int(flexi_gpu_handle* h, const double* Flux_master, const double* Flux_slave, double* Ut, int32_t doMPISides) {
+  ENTER(h);
+  if (!Flux_master || !Flux_slave || !Ut) return fail(FLEXI_GPU_ERR_ARG, "null argument");
+  const size_t nV = (size_t)h->nElems * 5 * h->np3, nF = (size_t)h->nSides * 5 * h->np2;
+  double *dV = nullptr, *dM = nullptr, *dS = nullptr;
+  CK(cudaMalloc((void**)&dV, nV * 8));
+  CK(cudaMalloc((void**)&dM, nF * 8));
+  CK(cudaMalloc((void**)&dS, nF * 8));
+  int r = upload_aos(h, Ut, dV, 5, h->np3, h->nElems);
+  if (!r) r = upload_aos(h, Flux_master, dM, 5, h->np2, h->nSides);
+  if (!r) r = upload_aos(h, Flux_slave, dS, 5, h->np2, h->nSides);
+  if (!r) {
+    SurfArgs a{};
+    a.m = h->m;
+    a.Flux_master = dM;
+    a.Flux_slave = dS;
+    a.Ut = dV;
+    a.nv = 5;
+    // surfint.t90:60-66
+    a.firstSide = doMPISides ? h->firstYOUR : 0;
+    a.lastSide = doMPISides ? h->nSides - 1 : h->firstYOUR - 1;
+    Timer tm(h, KC_UPDATE, h->sc);
+    cudaError_t e = h->ops->surfint(h->gl, a, h->nElems, h->sc);
+    if (e != cudaSuccess) r = fail(FLEXI_GPU_ERR_CUDA, "surfint: %s", cudaGetErrorString(e));
+  }
+  if (!r) r = download_aos(h, dV, Ut, 5, h->np3, h->nElems);
+  cudaFree(dV);
+  cudaFree(dM);
+  cudaFree(dS);
+  return r;
+}
+
+int flexi_gpu_counters(flexi_gpu_handle* h, int64_t* kernel_launches, int64_t* h2d_bytes, int64_t* d2h_bytes) {
+  if (!h) return fail(FLEXI_GPU_ERR_ARG, "null handle");
+  if (kernel_launches) *kernel_launches = h->launches;
+  if (h2d_bytes) *h2d_bytes = h->h2d;
+  if (d2h_bytes) *d2h_bytes = h->d2h;
+  return 0;
+}
+
+int flexi_gpu_kernel_times(flexi_gpu_handle* h, double* ms_out, int64_t* launches_out, int32_t n_classes, int32_t reset) {
+  ENTER(h);
+  CKR(collect_times(h));
+  for (int i = 0; i < n_classes && i < KC_COUNT; ++i) {
+    if (ms_out) ms_out[i] = h->kc_ms[i];
+    if (launches_out) launches_out[i] = h->kc_n[i];
+  }
+  if (reset)
+    for (int i = 0; i < KC_COUNT; ++i) {
+      h->kc_ms[i] = 0;
+      h->kc_n[i] = 0;
+    }
+  return 0;
+}
+
+int flexi_gpu_set_profiling(flexi_gpu_handle* h, int32_t on) {
+  ENTER(h);
+  CKR(collect_times(h));
+  h->profiling = on != 0;
+  return 0;
+}
+
+int flexi_gpu_synchronize(flexi_gpu_handle* h) {
+  ENTER(h);
+  CK(cudaStreamSynchronize(h->sx));
+  CK(cudaStreamSynchronize(h->sc));
+  return 0;
+}
+
+int flexi_gpu_stream(flexi_gpu_handle* h, void** stream_out) {
+  if (!h || !stream_out) return fail(FLEXI_GPU_ERR_ARG, "null argument");
+  *stream_out = (void*)h->sc;
+  return 0;
+}
+
+}  // extern "C"

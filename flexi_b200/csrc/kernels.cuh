@@ -1,0 +1,637 @@
+// kernels.cuh -- the CUDA kernels of the DGSEM right-hand side, templated on NP = N+1.
+//
+// Kernel classes (one launch each per RK stage):
+//   k_volume  element kernel  : ConsToPrim + BR1/BR2 lifting (volume + gathered surface part) + ApplyJacobianLifting +
+//                               ProlongToFace of the gradients + VolInt (weak or split form).   dg.f90:334,523,546
+//   k_flux    side kernel     : GetPrimitiveStateSurface + Riemann + ViscousFlux + *SurfElem.   fillflux.f90:40-215
+//   k_update  element kernel  : SurfInt (gathered) + sign + ApplyJacobian + LSERK stage update + ProlongToFace of the new
+//                               state.                                           dg.f90:636-675, timestep.f90:126-131
+//   k_prolong element kernel  : ProlongToFace of U alone (after set_state).                      prolongtoface.t90:21-144
+//   k_dt      element kernel  : CalcTimeStep.                                                   calctimestep.f90:89-227
+#pragma once
+#include "layout.cuh"
+
+namespace fx {
+
+enum KernelClass { KC_VOLUME = 0, KC_FLUX = 1, KC_UPDATE = 2, KC_PROLONG = 3, KC_DT = 4, KC_LAYOUT = 5, KC_COUNT = 6 };
+
+struct VolArgs {
+  Mesh m;
+  Eqn q;
+  const int32_t* elems;  // element list (NULL = identity)
+  int nList;
+  const double* U;         // [e][5][NP3]
+  const double* U_master;  // [s][5][NP2]
+  const double* U_slave;
+  double* Ut;  // raw volume integral (before sign / Jacobian)
+  double* gm[3];  // gradU{x,y,z}_master [s][nvl][NP2]
+  double* gs[3];  // gradU{x,y,z}_slave
+  double* gvol[3];  // optional volume gradients [e][nvl][NP3] (NULL = not stored)
+};
+
+struct FluxArgs {
+  Mesh m;
+  Eqn q;
+  int firstSide, nSidesRange;  // 0-based range
+  int parabolic;
+  const double* U_master;
+  const double* U_slave;
+  const double* gm[3];
+  const double* gs[3];
+  double* Flux;  // [s][5][NP2]  (Flux_master == Flux_slave, fillflux.f90:201)
+};
+
+struct UpdArgs {
+  Mesh m;
+  const int32_t* elems;
+  int nList;
+  const double* UtVol;  // raw volume integral
+  const double* Flux;
+  double* U;
+  double* UtTmp;  // LSERK register (Ut_tmp, timedisc_vars)
+  double* UtOut;  // Ut when mode == 0
+  double* U_master;
+  double* U_slave;
+  int mode;    // 0: write Ut only (DGTimeDerivative_weakForm); 1: first RK stage; 2: later RK stage
+  double rkA;  // RKA(iStage)
+  double b_dt; // RKb(iStage)*dt
+};
+
+struct ProArgs {
+  Mesh m;
+  const double* V;  // [e][nv][NP3]
+  double* master;   // [s][nv][NP2]
+  double* slave;
+  int nv;
+  int firstSide, lastSide;  // inclusive 0-based side range that is written
+};
+
+// ---------------------------------------------------------------------------------------------------------------------------
+template <int NP>
+__device__ __forceinline__ void load_basis(double* sB, const double* g, int tid, int nthreads) {
+  for (int t = tid; t < Dim<NP>::NBASIS; t += nthreads) sB[t] = g[t];
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// k_prolong: ProlongToFace for nv variables, element gather.
+template <int NP, bool GL>
+__global__ void __launch_bounds__(Dim<NP>::NP3) k_prolong(ProArgs A) {
+  using D = Dim<NP>;
+  extern __shared__ double sm[];
+  double* sB = sm;
+  double* sV = sm + D::NBASIS;  // nv planes
+  const int tid = threadIdx.x;
+  const int e = blockIdx.x;
+  load_basis<NP>(sB, A.m.basis, tid, D::NP3);
+  for (int v = 0; v < A.nv; ++v) sV[v * D::NP3 + tid] = A.V[((size_t)e * A.nv + v) * D::NP3 + tid];
+  __syncthreads();
+  for (int t = tid; t < 6 * D::NP2; t += D::NP3) {
+    const int ls = t / D::NP2 + 1, pq = t % D::NP2;
+    const SideRef sr = A.m.e2s[e * 6 + ls - 1];
+    if (sr.side < A.firstSide || sr.side > A.lastSide) continue;
+    const int ab = A.m.s2v2[(sr.flip * 6 + ls - 1) * D::NP2 + pq];
+    const int a = ab % NP, b = ab / NP;
+    double* dst = (sr.flip == 0) ? A.master : A.slave;
+    for (int v = 0; v < A.nv; ++v)
+      dst[((size_t)sr.side * A.nv + v) * D::NP2 + pq] = face_eval<NP, GL>(sV + v * D::NP3, sB, ls, a, b);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// k_volume
+template <int NP, bool GL, bool SPLIT, bool PARA>
+struct VolSmem {
+  using D = Dim<NP>;
+  static constexpr int WORK_PLANES = (PARA || !SPLIT) ? 15 : 9;
+  static constexpr int FACE_DOUBLES = PARA ? 6 * 8 * D::NP2 : 0;
+  static constexpr int WORK = (WORK_PLANES * D::NP3 > FACE_DOUBLES) ? WORK_PLANES * D::NP3 : FACE_DOUBLES;
+  static constexpr int DOUBLES = D::NBASIS + 7 * D::NP3 + WORK;
+  static constexpr size_t BYTES = sizeof(double) * DOUBLES;
+};
+
+// pairwise two-point volume fluxes of one node along its three lines, volint.f90:211-371 (advective part)
+template <int NP, int STYPE>
+__device__ __forceinline__ void split_lines(const double* sP, const double* sM, const double* sB, int i, int j, int k, int n,
+                                            const double* M, double* ut) {
+  using D = Dim<NP>;
+  const double* dv = sB + D::O_DV;
+  Node a;
+  a.rho = sP[0 * D::NP3 + n];
+  a.v1 = sP[1 * D::NP3 + n];
+  a.v2 = sP[2 * D::NP3 + n];
+  a.v3 = sP[3 * D::NP3 + n];
+  a.p = sP[4 * D::NP3 + n];
+  a.E = sP[6 * D::NP3 + n];
+#pragma unroll
+  for (int dir = 0; dir < 3; ++dir) {
+    const int me = (dir == 0) ? i : (dir == 1) ? j : k;
+    const int stride = (dir == 0) ? 1 : (dir == 1) ? NP : D::NP2;
+    const int base = n - me * stride;
+#pragma unroll
+    for (int l = 0; l < NP; ++l) {
+      if (l == me) continue;
+      const int nl = base + l * stride;
+      Node b;
+      b.rho = sP[0 * D::NP3 + nl];
+      b.v1 = sP[1 * D::NP3 + nl];
+      b.v2 = sP[2 * D::NP3 + nl];
+      b.v3 = sP[3 * D::NP3 + nl];
+      b.p = sP[4 * D::NP3 + nl];
+      b.E = sP[6 * D::NP3 + nl];
+      const double Mb[3] = {sM[(3 * dir + 0) * D::NP3 + nl], sM[(3 * dir + 1) * D::NP3 + nl], sM[(3 * dir + 2) * D::NP3 + nl]};
+      double F[5];
+      split_volume_flux<STYPE>(a, b, M + 3 * dir, Mb, F);
+      const double d = dv[l * NP + me];  // DVolSurf(l,me)
+#pragma unroll
+      for (int v = 0; v < 5; ++v) ut[v] = ut[v] + d * F[v];
+    }
+  }
+}
+
+// prim index of lifting variable v (PRIM_LIFT, eos.h:118,127): nvl=5 -> (rho,v1,v2,v3,T), nvl=4 -> (v1,v2,v3,T)
+__host__ __device__ constexpr int lift_prim(int nvl, int v) { return nvl == 5 ? (v < 4 ? v : 5) : (v < 3 ? v + 1 : 5); }
+
+template <int NP, bool GL, bool SPLIT, bool PARA, int NVL>
+__global__ void __launch_bounds__(Dim<NP>::NP3) k_volume(VolArgs A) {
+  using D = Dim<NP>;
+  extern __shared__ double sm[];
+  double* sB = sm;
+  double* sP = sm + D::NBASIS;  // rho,v1,v2,v3,p,T,rhoE
+  double* sW = sP + 7 * D::NP3;
+  const int tid = threadIdx.x;
+  const int e = A.elems ? A.elems[blockIdx.x] : blockIdx.x;
+  const int i = tid % NP, j = (tid / NP) % NP, k = tid / D::NP2;
+  const int n = tid;
+  const Eqn& q = A.q;
+
+  load_basis<NP>(sB, A.m.basis, tid, D::NP3);
+  double U[5], P[6], M[9];
+#pragma unroll
+  for (int v = 0; v < 5; ++v) U[v] = A.U[((size_t)e * 5 + v) * D::NP3 + n];
+  cons_to_prim(q, U, P);
+#pragma unroll
+  for (int v = 0; v < 6; ++v) sP[v * D::NP3 + n] = P[v];
+  sP[6 * D::NP3 + n] = U[ENER];
+#pragma unroll
+  for (int c = 0; c < 9; ++c) M[c] = A.m.Met[((size_t)e * 9 + c) * D::NP3 + n];
+  const double sJ = A.m.sJ[(size_t)e * D::NP3 + n];
+  __syncthreads();
+
+  double ut[5] = {0., 0., 0., 0., 0.};
+  const double* dh = sB + D::O_DH;
+
+  if (PARA) {
+    constexpr int nvl = NVL;
+    constexpr int LV = (NVL == 5) ? 1 : 0;  // LIFT_VEL1
+    // ---- 1. lifting surface flux of the six sides, lifting_fillflux.t90:81-107 (strong form: 0.5*(U_slave-U_master)*SurfElem)
+    for (int t = tid; t < 6 * D::NP2; t += D::NP3) {
+      const int ls = t / D::NP2 + 1, pq = t % D::NP2;
+      const SideRef sr = A.m.e2s[e * 6 + ls - 1];
+      const int ab = A.m.s2v2[(sr.flip * 6 + ls - 1) * D::NP2 + pq];
+      const double* nbTrace = (sr.flip == 0) ? A.U_slave : A.U_master;
+      const double* myTrace = (sr.flip == 0) ? A.U_master : A.U_slave;
+      double Un[5], Um[5], Pn[6], Pm[6];
+#pragma unroll
+      for (int v = 0; v < 5; ++v) Un[v] = nbTrace[((size_t)sr.side * 5 + v) * D::NP2 + pq];
+#pragma unroll
+      for (int v = 0; v < 5; ++v) Um[v] = myTrace[((size_t)sr.side * 5 + v) * D::NP2 + pq];
+      cons_to_prim(q, Un, Pn);
+      cons_to_prim(q, Um, Pm);
+      const double* g = A.m.Geo + (size_t)sr.side * 10 * D::NP2 + pq;
+      const double surf = g[9 * D::NP2];
+      double* o = sW + (ls - 1) * 8 * D::NP2 + ab;
+      const double sgn = (sr.flip == 0) ? 1. : -1.;  // (slave - master) seen from this element
+#pragma unroll
+      for (int v = 0; v < nvl; ++v) {
+            const int pv = lift_prim(nvl, v);
+        o[v * D::NP2] = 0.5 * (sgn * (Pn[pv] - Pm[pv])) * surf;
+      }
+      o[5 * D::NP2] = g[0];
+      o[6 * D::NP2] = g[D::NP2];
+      o[7 * D::NP2] = g[2 * D::NP2];
+    }
+    // ---- 2. volume part, lifting_volint.t90:26-118 (non-conservative)
+    double gx[5], gy[5], gz[5];
+    {
+      const double* dt = sB + D::O_DT;
+#pragma unroll
+      for (int v = 0; v < nvl; ++v) {
+        const double* pl = sP + lift_prim(nvl, v) * D::NP3;
+        const int bx = n - i, by = n - j * NP, bz = n - k * D::NP2;
+        double gxi = dt[i] * pl[bx], geta = dt[j] * pl[by], gzeta = dt[k] * pl[bz];
+#pragma unroll
+        for (int l = 1; l < NP; ++l) {
+          gxi = gxi + dt[l * NP + i] * pl[bx + l];
+          geta = geta + dt[l * NP + j] * pl[by + l * NP];
+          gzeta = gzeta + dt[l * NP + k] * pl[bz + l * D::NP2];
+        }
+        gx[v] = M[0] * gxi + M[3] * geta + M[6] * gzeta;
+        gy[v] = M[1] * gxi + M[4] * geta + M[7] * gzeta;
+        gz[v] = M[2] * gxi + M[5] * geta + M[8] * gzeta;
+      }
+    }
+    __syncthreads();
+    // ---- 3. surface part, lifting_br1.t90:195-292 (same sign for master and slave element), then *sJ (applyjacobian.t90)
+    {
+      const double* lhm = sB + D::O_LHM;
+      const double* lhp = sB + D::O_LHP;
+#pragma unroll
+      for (int ls = 1; ls <= 6; ++ls) {
+        int ab, me;
+        if (ls == XI_MINUS || ls == XI_PLUS) {
+          ab = j + NP * k;
+          me = i;
+        } else if (ls == ETA_MINUS || ls == ETA_PLUS) {
+          ab = i + NP * k;
+          me = j;
+        } else {
+          ab = i + NP * j;
+          me = k;
+        }
+        const bool minus = is_minus_side(ls);
+        if (GL && me != (minus ? 0 : NP - 1)) continue;
+        const double lh = minus ? lhm[GL ? 0 : me] : lhp[GL ? NP - 1 : me];
+        const double* o = sW + (ls - 1) * 8 * D::NP2 + ab;
+        const double n0 = o[5 * D::NP2], n1 = o[6 * D::NP2], n2 = o[7 * D::NP2];
+#pragma unroll
+        for (int v = 0; v < nvl; ++v) {
+          const double f = o[v * D::NP2];
+          gx[v] = gx[v] + (f * n0) * lh;
+          gy[v] = gy[v] + (f * n1) * lh;
+          gz[v] = gz[v] + (f * n2) * lh;
+        }
+      }
+#pragma unroll
+      for (int v = 0; v < nvl; ++v) {
+        gx[v] = gx[v] * sJ;
+        gy[v] = gy[v] * sJ;
+        gz[v] = gz[v] * sJ;
+      }
+    }
+    __syncthreads();  // everyone is done with the face staging area
+#pragma unroll
+    for (int v = 0; v < nvl; ++v) {
+      sW[(0 * nvl + v) * D::NP3 + n] = gx[v];
+      sW[(1 * nvl + v) * D::NP3 + n] = gy[v];
+      sW[(2 * nvl + v) * D::NP3 + n] = gz[v];
+    }
+    if (A.gvol[0]) {
+#pragma unroll
+      for (int v = 0; v < nvl; ++v) {
+        A.gvol[0][((size_t)e * nvl + v) * D::NP3 + n] = gx[v];
+        A.gvol[1][((size_t)e * nvl + v) * D::NP3 + n] = gy[v];
+        A.gvol[2][((size_t)e * nvl + v) * D::NP3 + n] = gz[v];
+      }
+    }
+    __syncthreads();
+    // ---- 4. ProlongToFaceLifting, lifting_br1.t90:150-174
+    for (int t = tid; t < 6 * D::NP2; t += D::NP3) {
+      const int ls = t / D::NP2 + 1, pq = t % D::NP2;
+      const SideRef sr = A.m.e2s[e * 6 + ls - 1];
+      const int ab = A.m.s2v2[(sr.flip * 6 + ls - 1) * D::NP2 + pq];
+      const int a = ab % NP, b = ab / NP;
+      for (int d = 0; d < 3; ++d) {
+        double* dst = (sr.flip == 0) ? A.gm[d] : A.gs[d];
+        for (int v = 0; v < nvl; ++v)
+          dst[((size_t)sr.side * nvl + v) * D::NP2 + pq] = face_eval<NP, GL>(sW + (d * nvl + v) * D::NP3, sB, ls, a, b);
+      }
+    }
+    // ---- 5. viscous (+ advective in weak form) fluxes of this node in the reference element, volint.f90:378-422
+    double F[5], G[5], H[5];
+    {
+      double fv[4], gv[4], hv[4];
+      eval_diff_flux3d(q, P[VEL1], P[VEL2], P[VEL3], gx + LV, gy + LV, gz + LV, fv, gv, hv);
+      // eval_diff_flux3d reads g?[0..2] = velocity gradients and g?[3] = temperature gradient: lifting sets keep T right
+      // behind the velocities (eos.h:118,127), so the same pointer offset serves both.
+      double fa[5] = {0., fv[0], fv[1], fv[2], fv[3]}, ga[5] = {0., gv[0], gv[1], gv[2], gv[3]},
+             ha[5] = {0., hv[0], hv[1], hv[2], hv[3]};
+      if (!SPLIT) {
+        double fe[5], ge[5], he[5];
+        eval_flux3d(U, P, fe, ge, he);
+#pragma unroll
+        for (int v = 0; v < 5; ++v) {
+          fa[v] = fe[v] + fa[v];
+          ga[v] = ge[v] + ga[v];
+          ha[v] = he[v] + ha[v];
+        }
+      }
+#pragma unroll
+      for (int v = 0; v < 5; ++v) {
+        F[v] = fa[v] * M[0] + ga[v] * M[1] + ha[v] * M[2];
+        G[v] = fa[v] * M[3] + ga[v] * M[4] + ha[v] * M[5];
+        H[v] = fa[v] * M[6] + ga[v] * M[7] + ha[v] * M[8];
+      }
+    }
+    __syncthreads();  // face threads are done reading the gradients
+#pragma unroll
+    for (int v = 0; v < 5; ++v) {
+      sW[(0 + v) * D::NP3 + n] = F[v];
+      sW[(5 + v) * D::NP3 + n] = G[v];
+      sW[(10 + v) * D::NP3 + n] = H[v];
+    }
+    __syncthreads();
+  } else if (!SPLIT) {
+    double fe[5], ge[5], he[5];
+    eval_flux3d(U, P, fe, ge, he);
+#pragma unroll
+    for (int v = 0; v < 5; ++v) {
+      sW[(0 + v) * D::NP3 + n] = fe[v] * M[0] + ge[v] * M[1] + he[v] * M[2];
+      sW[(5 + v) * D::NP3 + n] = fe[v] * M[3] + ge[v] * M[4] + he[v] * M[5];
+      sW[(10 + v) * D::NP3 + n] = fe[v] * M[6] + ge[v] * M[7] + he[v] * M[8];
+    }
+    __syncthreads();
+  }
+
+  if (PARA || !SPLIT) {
+    // ---- 6. weak-form derivative, volint.f90:172-184 (term order xi, zeta, eta)
+    const int bx = n - i, by = n - j * NP, bz = n - k * D::NP2;
+    constexpr int V0 = (SPLIT ? 1 : 0);  // the viscous density flux is identically zero
+#pragma unroll
+    for (int v = V0; v < 5; ++v) {
+      const double* f = sW + (0 + v) * D::NP3;
+      const double* g = sW + (5 + v) * D::NP3;
+      const double* h = sW + (10 + v) * D::NP3;
+      double s = dh[i] * f[bx] + dh[k] * h[bz] + dh[j] * g[by];
+#pragma unroll
+      for (int l = 1; l < NP; ++l) s = s + dh[l * NP + i] * f[bx + l] + dh[l * NP + k] * h[bz + l * D::NP2] + dh[l * NP + j] * g[by + l * NP];
+      ut[v] = s;
+    }
+  }
+
+  if (SPLIT) {
+    if (PARA) __syncthreads();  // weak-form reads of the work area are done
+#pragma unroll
+    for (int c = 0; c < 9; ++c) sW[c * D::NP3 + n] = M[c];
+    __syncthreads();
+    switch (q.splitType) {
+      case FLEXI_SPLITDG_SD: split_lines<NP, FLEXI_SPLITDG_SD>(sP, sW, sB, i, j, k, n, M, ut); break;
+      case FLEXI_SPLITDG_DU: split_lines<NP, FLEXI_SPLITDG_DU>(sP, sW, sB, i, j, k, n, M, ut); break;
+      case FLEXI_SPLITDG_KG: split_lines<NP, FLEXI_SPLITDG_KG>(sP, sW, sB, i, j, k, n, M, ut); break;
+      default: split_lines<NP, FLEXI_SPLITDG_PI>(sP, sW, sB, i, j, k, n, M, ut);
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < 5; ++v) A.Ut[((size_t)e * 5 + v) * D::NP3 + n] = ut[v];
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// k_flux: one thread per face node of the side range.  fillflux.f90:40-215, riemann.f90:267-352,448-498
+template <int NP>
+__global__ void __launch_bounds__(128) k_flux(FluxArgs A) {
+  using D = Dim<NP>;
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)A.nSidesRange * D::NP2) return;
+  const int s = A.firstSide + (int)(idx / D::NP2);
+  const int pq = (int)(idx % D::NP2);
+  const Eqn& q = A.q;
+  double UL[5], UR[5], PL[6], PR[6];
+#pragma unroll
+  for (int v = 0; v < 5; ++v) {
+    UL[v] = A.U_master[((size_t)s * 5 + v) * D::NP2 + pq];
+    UR[v] = A.U_slave[((size_t)s * 5 + v) * D::NP2 + pq];
+  }
+  cons_to_prim(q, UL, PL);  // equation.f90:189-216: face primitives come from the conservative traces
+  cons_to_prim(q, UR, PR);
+  const double* g = A.m.Geo + (size_t)s * 10 * D::NP2 + pq;
+  const double nv[3] = {g[0], g[D::NP2], g[2 * D::NP2]};
+  const double t1[3] = {g[3 * D::NP2], g[4 * D::NP2], g[5 * D::NP2]};
+  const double t2[3] = {g[6 * D::NP2], g[7 * D::NP2], g[8 * D::NP2]};
+  const double surf = g[9 * D::NP2];
+  double F[5];
+  riemann_point(q, q.riemann, UL, UR, PL, PR, nv, t1, t2, F);
+  if (A.parabolic) {
+    const int nvl = q.nvl, o = q.lv_vel1;
+    double gL[3][4], gR[3][4];
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        gL[d][c] = A.gm[d][((size_t)s * nvl + o + c) * D::NP2 + pq];
+        gR[d][c] = A.gs[d][((size_t)s * nvl + o + c) * D::NP2 + pq];
+      }
+    double fL[4], gLf[4], hL[4], fR[4], gRf[4], hR[4];
+    eval_diff_flux3d(q, PL[VEL1], PL[VEL2], PL[VEL3], gL[0], gL[1], gL[2], fL, gLf, hL);
+    eval_diff_flux3d(q, PR[VEL1], PR[VEL2], PR[VEL3], gR[0], gR[1], gR[2], fR, gRf, hR);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) F[c + 1] = F[c + 1] + 0.5 * (nv[0] * (fL[c] + fR[c]) + nv[1] * (gLf[c] + gRf[c]) + nv[2] * (hL[c] + hR[c]));
+  }
+#pragma unroll
+  for (int v = 0; v < 5; ++v) A.Flux[((size_t)s * 5 + v) * D::NP2 + pq] = F[v] * surf;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// k_update: SurfInt gather + Ut=-Ut + ApplyJacobian + LSERK + ProlongToFace(new U)
+template <int NP, bool GL>
+__global__ void __launch_bounds__(Dim<NP>::NP3) k_update(UpdArgs A) {
+  using D = Dim<NP>;
+  extern __shared__ double sm[];
+  double* sB = sm;
+  double* sU = sm + D::NBASIS;  // 5 planes
+  const int tid = threadIdx.x;
+  const int e = A.elems ? A.elems[blockIdx.x] : blockIdx.x;
+  const int i = tid % NP, j = (tid / NP) % NP, k = tid / D::NP2;
+  const int n = tid;
+  load_basis<NP>(sB, A.m.basis, tid, D::NP3);
+  double ut[5];
+#pragma unroll
+  for (int v = 0; v < 5; ++v) ut[v] = A.UtVol[((size_t)e * 5 + v) * D::NP3 + n];
+  const double sJ = A.m.sJ[(size_t)e * D::NP3 + n];
+  __syncthreads();
+  const double* lhm = sB + D::O_LHM;
+  const double* lhp = sB + D::O_LHP;
+#pragma unroll
+  for (int ls = 1; ls <= 6; ++ls) {  // surfint.t90:475-616 / :21-239, DoSurfInt :683-766
+    int ab, me;
+    if (ls == XI_MINUS || ls == XI_PLUS) {
+      ab = j + NP * k;
+      me = i;
+    } else if (ls == ETA_MINUS || ls == ETA_PLUS) {
+      ab = i + NP * k;
+      me = j;
+    } else {
+      ab = i + NP * j;
+      me = k;
+    }
+    const bool minus = is_minus_side(ls);
+    if (GL && me != (minus ? 0 : NP - 1)) continue;
+    const double lh = minus ? lhm[GL ? 0 : me] : lhp[GL ? NP - 1 : me];
+    const SideRef sr = A.m.e2s[e * 6 + ls - 1];
+    const int pq = A.m.v2s[(sr.flip * 6 + ls - 1) * D::NP2 + ab];
+    const double sgn = (sr.flip == 0) ? 1. : -1.;  // surfint.t90:583: slave element sees -Flux_slave
+#pragma unroll
+    for (int v = 0; v < 5; ++v) ut[v] = ut[v] + (sgn * A.Flux[((size_t)sr.side * 5 + v) * D::NP2 + pq]) * lh;
+  }
+#pragma unroll
+  for (int v = 0; v < 5; ++v) ut[v] = (-ut[v]) * sJ;  // dg.f90:656,675
+  if (A.mode == 0) {
+#pragma unroll
+    for (int v = 0; v < 5; ++v) A.UtOut[((size_t)e * 5 + v) * D::NP3 + n] = ut[v];
+    return;
+  }
+  // timestep.f90:126-131
+#pragma unroll
+  for (int v = 0; v < 5; ++v) {
+    const size_t g = ((size_t)e * 5 + v) * D::NP3 + n;
+    double tmp = ut[v];
+    if (A.mode == 2) tmp = A.UtTmp[g] * (-A.rkA) + ut[v];
+    A.UtTmp[g] = tmp;
+    const double u = A.U[g] + tmp * A.b_dt;
+    A.U[g] = u;
+    sU[v * D::NP3 + n] = u;
+  }
+  __syncthreads();
+  for (int t = tid; t < 6 * D::NP2; t += D::NP3) {
+    const int ls = t / D::NP2 + 1, pq = t % D::NP2;
+    const SideRef sr = A.m.e2s[e * 6 + ls - 1];
+    const int ab = A.m.s2v2[(sr.flip * 6 + ls - 1) * D::NP2 + pq];
+    const int a = ab % NP, b = ab / NP;
+    double* dst = (sr.flip == 0) ? A.U_master : A.U_slave;
+#pragma unroll
+    for (int v = 0; v < 5; ++v) dst[((size_t)sr.side * 5 + v) * D::NP2 + pq] = face_eval<NP, GL>(sU + v * D::NP3, sB, ls, a, b);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// operator-level SurfInt (what unitTests/SurfInt.f90 drives): Ut += surface integral of the given side fluxes
+struct SurfArgs {
+  Mesh m;
+  const double* Flux_master;
+  const double* Flux_slave;
+  double* Ut;
+  int nv;
+  int firstSide, lastSide;
+};
+template <int NP, bool GL>
+__global__ void __launch_bounds__(Dim<NP>::NP3) k_surfint(SurfArgs A) {
+  using D = Dim<NP>;
+  extern __shared__ double sm[];
+  double* sB = sm;
+  const int tid = threadIdx.x, e = blockIdx.x;
+  const int i = tid % NP, j = (tid / NP) % NP, k = tid / D::NP2;
+  load_basis<NP>(sB, A.m.basis, tid, D::NP3);
+  __syncthreads();
+  const double* lhm = sB + D::O_LHM;
+  const double* lhp = sB + D::O_LHP;
+  for (int v = 0; v < A.nv; ++v) {
+    double ut = A.Ut[((size_t)e * A.nv + v) * D::NP3 + tid];
+    for (int ls = 1; ls <= 6; ++ls) {
+      int ab, me;
+      if (ls == XI_MINUS || ls == XI_PLUS) {
+        ab = j + NP * k;
+        me = i;
+      } else if (ls == ETA_MINUS || ls == ETA_PLUS) {
+        ab = i + NP * k;
+        me = j;
+      } else {
+        ab = i + NP * j;
+        me = k;
+      }
+      const bool minus = is_minus_side(ls);
+      if (GL && me != (minus ? 0 : NP - 1)) continue;
+      const SideRef sr = A.m.e2s[e * 6 + ls - 1];
+      if (sr.side < A.firstSide || sr.side > A.lastSide) continue;
+      const double lh = minus ? lhm[GL ? 0 : me] : lhp[GL ? NP - 1 : me];
+      const int pq = A.m.v2s[(sr.flip * 6 + ls - 1) * D::NP2 + ab];
+      const double f = (sr.flip == 0) ? A.Flux_master[((size_t)sr.side * A.nv + v) * D::NP2 + pq]
+                                      : -A.Flux_slave[((size_t)sr.side * A.nv + v) * D::NP2 + pq];
+      ut = ut + f * lh;
+    }
+    A.Ut[((size_t)e * A.nv + v) * D::NP3 + tid] = ut;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// k_dt: CalcTimeStep, calctimestep.f90:89-227.  One block per element; writes per-element (dtConv, dtVisc, errFlag).
+struct DtArgs {
+  Mesh m;
+  Eqn q;
+  const double* U;
+  const double* MetAdv;   // [e][3][NP3]  sJ*|Metrics_d|        (InitCalctimestep, calctimestep.f90:42-83)
+  const double* MetVisc;  // [e][3][NP3]
+  double CFLScale, DFLScale;
+  int parabolic;
+  double* out;  // [e][3]
+};
+
+__device__ __forceinline__ double block_max(double v, double* red, int tid, int nthreads) {
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();
+  if ((tid & 31) == 0) red[tid >> 5] = v;
+  __syncthreads();
+  const int nw = (nthreads + 31) >> 5;
+  double r = red[0];
+  for (int w = 1; w < nw; ++w) r = fmax(r, red[w]);
+  return r;
+}
+
+template <int NP>
+__global__ void __launch_bounds__(Dim<NP>::NP3) k_dt(DtArgs A) {
+  using D = Dim<NP>;
+  __shared__ double red[32];
+  const int tid = threadIdx.x, e = blockIdx.x, n = tid;
+  const Eqn& q = A.q;
+  double U[5], P[6], M[9];
+#pragma unroll
+  for (int v = 0; v < 5; ++v) U[v] = A.U[((size_t)e * 5 + v) * D::NP3 + n];
+  cons_to_prim(q, U, P);
+  const double srho = 1. / U[0];
+  const double c = sqrt(q.kappa * P[PRES] * srho);
+  const double sJ = A.m.sJ[(size_t)e * D::NP3 + n];
+#pragma unroll
+  for (int cI = 0; cI < 9; ++cI) M[cI] = A.m.Met[((size_t)e * 9 + cI) * D::NP3 + n];
+  const double vs[3] = {P[VEL1] * sJ, P[VEL2] * sJ, P[VEL3] * sJ};
+  double lam[3], lamv[3];
+  // NaN in the density flags errType 1 (calctimestep.f90:157-160); NaN propagates through fmax-free sums below
+  const double nanflag = (U[0] != U[0]) ? 1. : 0.;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    lam[d] = fabs(M[3 * d] * vs[0] + M[3 * d + 1] * vs[1] + M[3 * d + 2] * vs[2]) + c * A.MetAdv[((size_t)e * 3 + d) * D::NP3 + n];
+    lamv[d] = A.parabolic ? q.mu0 * srho * A.MetVisc[((size_t)e * 3 + d) * D::NP3 + n] : 0.;
+  }
+  // Fortran MAX ignores nothing: a NaN operand may or may not propagate; we flag NaN separately
+  double anynan = nanflag;
+#pragma unroll
+  for (int d = 0; d < 3; ++d)
+    if (lam[d] != lam[d] || lamv[d] != lamv[d]) anynan = fmax(anynan, 2.);
+  double mx[3], mv[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    mx[d] = block_max(lam[d], red, tid, D::NP3);
+    mv[d] = block_max(lamv[d], red, tid, D::NP3);
+  }
+  const double nn = block_max(anynan, red, tid, D::NP3);
+  if (tid == 0) {
+    const double dtc = A.CFLScale * 2. / (mx[0] + mx[1] + mx[2]);
+    double dtv = HUGE_VAL;
+    const double sv = mv[0] + mv[1] + mv[2];
+    if (A.parabolic && sv > 0.) dtv = A.DFLScale * 4. / sv;
+    A.out[(size_t)e * 3 + 0] = dtc;
+    A.out[(size_t)e * 3 + 1] = dtv;
+    A.out[(size_t)e * 3 + 2] = nn;
+  }
+}
+
+// InitCalctimestep, calctimestep.f90:42-83
+struct DtInitArgs {
+  const double* Met;
+  const double* sJ;
+  double* MetAdv;
+  double* MetVisc;
+  double KappasPr_max;
+  int nElems;
+};
+template <int NP>
+__global__ void k_dt_init(DtInitArgs A) {
+  using D = Dim<NP>;
+  const int e = blockIdx.x, n = threadIdx.x;
+  const double sJ = A.sJ[(size_t)e * D::NP3 + n];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const double m0 = A.Met[((size_t)e * 9 + 3 * d) * D::NP3 + n], m1 = A.Met[((size_t)e * 9 + 3 * d + 1) * D::NP3 + n],
+                 m2 = A.Met[((size_t)e * 9 + 3 * d + 2) * D::NP3 + n];
+    A.MetAdv[((size_t)e * 3 + d) * D::NP3 + n] = sJ * sqrt(m0 * m0 + m1 * m1 + m2 * m2);
+    A.MetVisc[((size_t)e * 3 + d) * D::NP3 + n] = A.KappasPr_max * ((m0 * sJ) * (m0 * sJ) + (m1 * sJ) * (m1 * sJ) + (m2 * sJ) * (m2 * sJ));
+  }
+}
+
+}  // namespace fx

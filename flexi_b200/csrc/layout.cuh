@@ -1,0 +1,81 @@
+// layout.cuh -- device data model of the DGSEM hot path.
+//
+// The Fortran host stores everything "variable fastest" (AoS): U(var,i,j,k,elem), U_master(var,p,q,side)
+// (dg_vars.f90:31-102, mesh_vars.f90:62-153).  On the device every array is element-major SoA:
+//
+//   volume   A[elem][var][n]     n  = i + NP*(j + NP*k)      one contiguous NP^3-double plane per variable and element
+//   side     S[side][var][pq]    pq = p + NP*q               one contiguous NP^2-double plane per variable and side
+//   metrics  Met[elem][9][n]     (f1,f2,f3, g1,g2,g3, h1,h2,h3) = Metrics_{f,g,h}Tilde(1:3), sJ[elem][n]
+//   facegeo  Geo[side][10][pq]   (NormVec 1:3, TangVec1 1:3, TangVec2 1:3, SurfElem)
+//
+// so that a warp reading consecutive nodes of one variable issues fully coalesced 256-byte requests.  Conversions happen
+// only at the C-ABI boundary (set_state / get_state / get_array / init).
+#pragma once
+#include <stdint.h>
+
+#include "physics.cuh"
+
+namespace fx {
+
+// local sides, flexi.h:90-95
+enum { ZETA_MINUS = 1, ETA_MINUS = 2, XI_PLUS = 3, ETA_PLUS = 4, XI_MINUS = 5, ZETA_PLUS = 6 };
+
+// per-element side table entry: ElemToSide(E2S_SIDE_ID,locSide,elem) (0-based here) and ElemToSide(E2S_FLIP,...)
+struct SideRef {
+  int32_t side;  // 0-based SideID
+  int32_t flip;  // 0 = this element is the master of the side
+};
+
+// read-only mesh + basis tables shared by all kernels
+struct Mesh {
+  int nElems, nSides;
+  const double* Met;   // [e][9][NP3]
+  const double* sJ;    // [e][NP3]
+  const double* Geo;   // [s][10][NP2]
+  const SideRef* e2s;  // [e][6]
+  const int32_t* s2v2; // [(flip*6+ls-1)*NP2 + pq] -> a + NP*b (volume-face coordinates), mappings.f90:389-397
+  const int32_t* v2s;  // inverse: [(flip*6+ls-1)*NP2 + ab] -> pq
+  const double* basis; // [dt | dh | dv | L_Minus | L_Plus | L_HatMinus | L_HatPlus], matrices as M[l*NP+i] = M(l,i)
+  const int32_t* sideBC; // [nSides]: 0 = no BC, else 1-based BC index (only sides < nBCSides are non-zero)
+};
+
+template <int NP>
+struct Dim {
+  static constexpr int NP2 = NP * NP;
+  static constexpr int NP3 = NP * NP * NP;
+  static constexpr int NBASIS = 3 * NP2 + 4 * NP;
+  static constexpr int O_DT = 0, O_DH = NP2, O_DV = 2 * NP2, O_LM = 3 * NP2, O_LP = 3 * NP2 + NP, O_LHM = 3 * NP2 + 2 * NP,
+                       O_LHP = 3 * NP2 + 3 * NP;
+};
+
+// volume node index of the face node (a,b) at depth l below local side ls (prolongtoface.t90:232-263):
+// xi faces carry (j,k), eta faces (i,k), zeta faces (i,j).
+template <int NP>
+__device__ __forceinline__ void face_line(int ls, int a, int b, int& base, int& stride) {
+  if (ls == XI_MINUS || ls == XI_PLUS) {
+    base = NP * (a + NP * b);
+    stride = 1;
+  } else if (ls == ETA_MINUS || ls == ETA_PLUS) {
+    base = a + NP * NP * b;
+    stride = NP;
+  } else {
+    base = a + NP * b;
+    stride = NP * NP;
+  }
+}
+__device__ __forceinline__ bool is_minus_side(int ls) { return ls == XI_MINUS || ls == ETA_MINUS || ls == ZETA_MINUS; }
+
+// EvalElemFaceG / EvalElemFaceGL (prolongtoface.t90:211-303) of one variable plane held in shared memory
+template <int NP, bool GL>
+__device__ __forceinline__ double face_eval(const double* plane, const double* sB, int ls, int a, int b) {
+  int base, stride;
+  face_line<NP>(ls, a, b, base, stride);
+  if (GL) return plane[base + (is_minus_side(ls) ? 0 : (NP - 1) * stride)];
+  const double* L = sB + (is_minus_side(ls) ? Dim<NP>::O_LM : Dim<NP>::O_LP);
+  double s = plane[base] * L[0];
+#pragma unroll
+  for (int l = 1; l < NP; ++l) s = s + plane[base + l * stride] * L[l];
+  return s;
+}
+
+}  // namespace fx

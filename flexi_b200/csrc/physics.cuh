@@ -1,0 +1,411 @@
+// physics.cuh -- point-wise Navier-Stokes physics of the FLEXI hot path as device functions.
+//
+// Each function names the reference routine it replaces (file:line under /root/reference/src).  Variable order follows
+// idealgas/eos.h: cons = (rho, rho*v1, rho*v2, rho*v3, rho*E), prim = (rho, v1, v2, v3, p, T).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "../../include/flexi_gpu.h"
+
+namespace fx {
+
+// scalar equation/solver parameters handed to every kernel by value (constant bank)
+struct Eqn {
+  double kappa, kappaM1, sKappaM1, R, sR, mu0, lambda;  // lambda = mu0*cp/Pr (eos.h:46, PP_VISC=0)
+  int riemann, splitDG, splitType;
+  int nvl;            // PP_nVarLifting
+  int lv_vel1, lv_temp;  // position of v1 / T inside the lifting variable set (eos.h:118,127)
+  int lift_map[5];       // prim index of each lifting variable
+};
+
+enum { DENS = 0, MOM1 = 1, MOM2 = 2, MOM3 = 3, ENER = 4 };
+enum { VEL1 = 1, VEL2 = 2, VEL3 = 3, PRES = 4, TEMP = 5 };
+
+// eos.f90:203-231 ConsToPrim
+__device__ __forceinline__ void cons_to_prim(const Eqn& q, const double* __restrict__ c, double* __restrict__ p) {
+  const double sRho = 1. / c[DENS];
+  p[DENS] = c[DENS];
+  p[VEL1] = c[MOM1] * sRho;
+  p[VEL2] = c[MOM2] * sRho;
+  p[VEL3] = c[MOM3] * sRho;
+  p[PRES] = q.kappaM1 * (c[ENER] - 0.5 * (c[MOM1] * p[VEL1] + c[MOM2] * p[VEL2] + c[MOM3] * p[VEL3]));
+  p[TEMP] = p[PRES] * sRho / q.R;
+}
+
+// flux.f90:66-119 EvalFlux3D_Point
+__device__ __forceinline__ void eval_flux3d(const double* U, const double* P, double* f, double* g, double* h) {
+  const double Ep = U[ENER] + P[PRES];
+  f[DENS] = U[MOM1];
+  f[MOM1] = U[MOM1] * P[VEL1] + P[PRES];
+  f[MOM2] = U[MOM1] * P[VEL2];
+  f[MOM3] = U[MOM1] * P[VEL3];
+  f[ENER] = Ep * P[VEL1];
+  g[DENS] = U[MOM2];
+  g[MOM1] = f[MOM2];
+  g[MOM2] = U[MOM2] * P[VEL2] + P[PRES];
+  g[MOM3] = U[MOM2] * P[VEL3];
+  g[ENER] = Ep * P[VEL2];
+  h[DENS] = U[MOM3];
+  h[MOM1] = f[MOM3];
+  h[MOM2] = g[MOM3];
+  h[MOM3] = U[MOM3] * P[VEL3] + P[PRES];
+  h[ENER] = Ep * P[VEL3];
+}
+
+// flux.f90:149-241 EvalDiffFlux3D_Point.  gv* = gradient of (v1,v2,v3), gT* = gradient of T; (x,y,z) components.
+// Only the four non-zero rows (momentum, energy) are returned: f[0..2] momentum, f[3] energy.
+__device__ __forceinline__ void eval_diff_flux3d(const Eqn& q, double v1, double v2, double v3, const double* gx, const double* gy,
+                                                 const double* gz, double* f, double* g, double* h) {
+  // gx = d(v1,v2,v3,T)/dx etc.
+  const double s23 = 2. / 3., s43 = 4. / 3.;
+  const double muS = q.mu0;
+  const double tau_xx = muS * (s43 * gx[0] - s23 * gy[1] - s23 * gz[2]);
+  const double tau_yy = muS * (-s23 * gx[0] + s43 * gy[1] - s23 * gz[2]);
+  const double tau_zz = muS * (-s23 * gx[0] - s23 * gy[1] + s43 * gz[2]);
+  const double tau_xy = muS * (gy[0] + gx[1]);
+  const double tau_xz = muS * (gz[0] + gx[2]);
+  const double tau_yz = muS * (gz[1] + gy[2]);
+  f[0] = -tau_xx;
+  f[1] = -tau_xy;
+  f[2] = -tau_xz;
+  f[3] = -tau_xx * v1 - tau_xy * v2 - tau_xz * v3 - q.lambda * gx[3];
+  g[0] = -tau_xy;
+  g[1] = -tau_yy;
+  g[2] = -tau_yz;
+  g[3] = -tau_xy * v1 - tau_yy * v2 - tau_yz * v3 - q.lambda * gy[3];
+  h[0] = -tau_xz;
+  h[1] = -tau_yz;
+  h[2] = -tau_zz;
+  h[3] = -tau_xz * v1 - tau_yz * v2 - tau_zz * v3 - q.lambda * gz[3];
+}
+
+// ---- split two-point fluxes, splitflux.f90 --------------------------------------------------------------------------------
+// node state used by the two-point fluxes: rho, v1, v2, v3, p, rhoE and the three cons momenta are rebuilt where needed
+struct Node {
+  double rho, v1, v2, v3, p, E;  // E = rho*E (cons energy)
+};
+
+// SplitVolumeFlux{SD,DU,KG,PI}: physical fluxes with the factor 2 folded in (splitflux.f90:21-22), then the metric
+// average contraction of splitflux.f90 (0.5*(MRef+M)).  Returns the contravariant two-point flux.
+template <int TYPE>
+__device__ __forceinline__ void split_volume_flux(const Node& a, const Node& b, const double* Ma, const double* Mb, double* Flux) {
+  double fT[5], gT[5], hT[5];
+  if (TYPE == FLEXI_SPLITDG_SD) {  // splitflux.f90:160-222
+    const double am1 = a.rho * a.v1, am2 = a.rho * a.v2, am3 = a.rho * a.v3;
+    const double bm1 = b.rho * b.v1, bm2 = b.rho * b.v2, bm3 = b.rho * b.v3;
+    const double aEp = a.E + a.p, bEp = b.E + b.p;
+    fT[0] = am1 + bm1;
+    fT[1] = am1 * a.v1 + a.p + bm1 * b.v1 + b.p;
+    fT[2] = am1 * a.v2 + bm1 * b.v2;
+    fT[3] = am1 * a.v3 + bm1 * b.v3;
+    fT[4] = aEp * a.v1 + bEp * b.v1;
+    gT[0] = am2 + bm2;
+    gT[1] = am1 * a.v2 + bm1 * b.v2;
+    gT[2] = am2 * a.v2 + a.p + bm2 * b.v2 + b.p;
+    gT[3] = am2 * a.v3 + bm2 * b.v3;
+    gT[4] = aEp * a.v2 + bEp * b.v2;
+    hT[0] = am3 + bm3;
+    hT[1] = am1 * a.v3 + bm1 * b.v3;
+    hT[2] = am2 * a.v3 + bm2 * b.v3;
+    hT[3] = am3 * a.v3 + a.p + bm3 * b.v3 + b.p;
+    hT[4] = aEp * a.v3 + bEp * b.v3;
+  } else if (TYPE == FLEXI_SPLITDG_DU) {  // splitflux.f90:262-320
+    const double su = a.v1 + b.v1, sv = a.v2 + b.v2, sw = a.v3 + b.v3, sp = a.p + b.p;
+    const double sE = a.E + b.E + a.p + b.p;
+    const double m0 = 0.5 * (a.rho + b.rho), m1 = 0.5 * (a.rho * a.v1 + b.rho * b.v1), m2 = 0.5 * (a.rho * a.v2 + b.rho * b.v2),
+                 m3 = 0.5 * (a.rho * a.v3 + b.rho * b.v3);
+    fT[0] = m0 * su; fT[1] = m1 * su + sp; fT[2] = m2 * su; fT[3] = m3 * su; fT[4] = 0.5 * sE * su;
+    gT[0] = m0 * sv; gT[1] = m1 * sv; gT[2] = m2 * sv + sp; gT[3] = m3 * sv; gT[4] = 0.5 * sE * sv;
+    hT[0] = m0 * sw; hT[1] = m1 * sw; hT[2] = m2 * sw; hT[3] = m3 * sw + sp; hT[4] = 0.5 * sE * sw;
+  } else {  // KG splitflux.f90:359-425, PI splitflux.f90:603-666
+    const double sr = a.rho + b.rho, su = a.v1 + b.v1, sv = a.v2 + b.v2, sw = a.v3 + b.v3, sp = a.p + b.p;
+    fT[0] = 0.5 * sr * su;
+    fT[1] = 0.25 * sr * (su * su) + sp;
+    fT[2] = 0.25 * sr * su * sv;
+    fT[3] = 0.25 * sr * su * sw;
+    gT[0] = 0.5 * sr * sv;
+    gT[1] = fT[2];
+    gT[2] = 0.25 * sr * (sv * sv) + sp;
+    gT[3] = 0.25 * sr * sv * sw;
+    hT[0] = 0.5 * sr * sw;
+    hT[1] = fT[3];
+    hT[2] = gT[3];
+    hT[3] = 0.25 * sr * (sw * sw) + sp;
+    if (TYPE == FLEXI_SPLITDG_KG) {
+      const double e = a.E / a.rho + b.E / b.rho;
+      fT[4] = 0.25 * sr * su * e + 0.5 * sp * su;
+      gT[4] = 0.25 * sr * sv * e + 0.5 * sp * sv;
+      hT[4] = 0.25 * sr * sw * e + 0.5 * sp * sw;
+    } else {
+      const double hh = (a.E + a.p) / a.rho + (b.E + b.p) / b.rho;
+      fT[4] = 0.25 * sr * su * hh;
+      gT[4] = 0.25 * sr * sv * hh;
+      hT[4] = 0.25 * sr * sw * hh;
+    }
+  }
+  const double m0 = 0.5 * (Ma[0] + Mb[0]), m1 = 0.5 * (Ma[1] + Mb[1]), m2 = 0.5 * (Ma[2] + Mb[2]);
+#pragma unroll
+  for (int v = 0; v < 5; ++v) Flux[v] = m0 * fT[v] + m2 * hT[v] + m1 * gT[v];
+}
+
+// extended state used by the Riemann solvers, eos.h:91-106 (rotated into the face-normal system)
+struct Ext {
+  double rho, m1, m2, m3, E, srho, v1, v2, v3, p;
+};
+
+// flux.f90:396-417 EvalEulerFlux1D_fast
+__device__ __forceinline__ void euler_flux1d(const Ext& U, double* F) {
+  F[0] = U.m1;
+  F[1] = U.m1 * U.v1 + U.p;
+  F[2] = U.m1 * U.v2;
+  F[3] = U.m1 * U.v3;
+  F[4] = (U.E + U.p) * U.v1;
+}
+
+// SplitSurfaceFlux{SD,DU,KG,PI}, splitflux.f90:228-252,326-349,431-460,672-700
+__device__ __forceinline__ void split_surface_flux(int type, const Ext& L, const Ext& R, double* F) {
+  switch (type) {
+    case FLEXI_SPLITDG_SD:
+      F[0] = 0.5 * (L.m1 + R.m1);
+      F[1] = 0.5 * (L.m1 * L.v1 + L.p + R.m1 * R.v1 + R.p);
+      F[2] = 0.5 * (L.m1 * L.v2 + R.m1 * R.v2);
+      F[3] = 0.5 * (L.m1 * L.v3 + R.m1 * R.v3);
+      F[4] = 0.5 * ((L.E + L.p) * L.v1 + (R.E + R.p) * R.v1);
+      break;
+    case FLEXI_SPLITDG_DU: {
+      const double su = L.v1 + R.v1;
+      F[0] = 0.25 * (L.rho + R.rho) * su;
+      F[1] = 0.25 * (L.m1 + R.m1) * su + 0.5 * (L.p + R.p);
+      F[2] = 0.25 * (L.m2 + R.m2) * su;
+      F[3] = 0.25 * (L.m3 + R.m3) * su;
+      F[4] = 0.25 * (L.E + R.E + L.p + R.p) * su;
+    } break;
+    default: {  // KG, PI
+      const double sr = L.rho + R.rho, su = L.v1 + R.v1;
+      F[0] = 0.25 * sr * su;
+      F[1] = 0.125 * sr * (su * su) + 0.5 * (L.p + R.p);
+      F[2] = 0.125 * sr * su * (L.v2 + R.v2);
+      F[3] = 0.125 * sr * su * (L.v3 + R.v3);
+      if (type == FLEXI_SPLITDG_KG)
+        F[4] = 0.125 * sr * (L.E / L.rho + R.E / R.rho) * su + 0.25 * (L.p + R.p) * su;
+      else
+        F[4] = 0.125 * sr * ((L.E + L.p) / L.rho + (R.E + R.p) / R.rho) * su;
+    }
+  }
+}
+
+struct RoeMean {
+  double v1, v2, v3, H, c, absVel;
+};
+// Roe averages as used by riemann.f90:613-627,688-700 (ROEC_RIEMANN_H, eos.h:50)
+__device__ __forceinline__ RoeMean roe_average(const Eqn& q, const Ext& L, const Ext& R) {
+  RoeMean m;
+  const double H_L = (L.E + L.p) * L.srho, H_R = (R.E + R.p) * R.srho;
+  const double sl = sqrt(L.rho), sr = sqrt(R.rho);
+  const double ss = 1. / (sl + sr);
+  m.v1 = (sr * R.v1 + sl * L.v1) * ss;
+  m.v2 = (sr * R.v2 + sl * L.v2) * ss;
+  m.v3 = (sr * R.v3 + sl * L.v3) * ss;
+  m.H = (sr * H_R + sl * H_L) * ss;
+  m.absVel = m.v1 * m.v1 + m.v2 * m.v2 + m.v3 * m.v3;
+  m.c = sqrt(q.kappaM1 * (m.H - 0.5 * m.absVel));
+  return m;
+}
+__device__ __forceinline__ double sound_speed(const Eqn& q, const Ext& U) { return sqrt(q.kappa * U.p * U.srho); }
+
+// sum_k alpha_k |a_k| r_k of the Roe decomposition (eigenvectors riemann.f90:705-711)
+__device__ __forceinline__ void roe_dissipation(const RoeMean& m, const double* al, const double* a, double* D) {
+  const double a1 = al[0] * a[0], a2 = al[1] * a[1], a3 = al[2] * a[2], a4 = al[3] * a[3], a5 = al[4] * a[4];
+  D[0] = a1 + a2 + a5;
+  D[1] = a1 * (m.v1 - m.c) + a2 * m.v1 + a5 * (m.v1 + m.c);
+  D[2] = a1 * m.v2 + a2 * m.v2 + a3 + a5 * m.v2;
+  D[3] = a1 * m.v3 + a2 * m.v3 + a4 + a5 * m.v3;
+  D[4] = a1 * (m.H - m.v1 * m.c) + a2 * 0.5 * m.absVel + a3 * m.v2 + a4 * m.v3 + a5 * (m.H + m.v1 * m.c);
+}
+
+// The solver proper in the rotated frame; riemann.f90:558-1228.  With SPLIT_DG the central part is the two-point
+// surface flux (riemann.f90:584-587,731-738) and F_L/F_R are never formed (riemann.f90:333-336).
+__device__ __forceinline__ void riemann_solver(const Eqn& q, int solver, const Ext& L, const Ext& R, double* F) {
+  const bool split = q.splitDG != 0;
+  const double dU[5] = {R.rho - L.rho, R.m1 - L.m1, R.m2 - L.m2, R.m3 - L.m3, R.E - L.E};
+  double FL[5], FR[5];
+  if (!split) {
+    euler_flux1d(L, FL);
+    euler_flux1d(R, FR);
+  }
+  switch (solver) {
+    case FLEXI_RIEMANN_LF: {  // riemann.f90:558-589
+      const double lam = fmax(fabs(R.v1), fabs(L.v1)) + fmax(sound_speed(q, L), sound_speed(q, R));
+      if (!split) {
+#pragma unroll
+        for (int v = 0; v < 5; ++v) F[v] = 0.5 * ((FL[v] + FR[v]) - lam * dU[v]);
+      } else {
+        split_surface_flux(q.splitType, L, R, F);
+#pragma unroll
+        for (int v = 0; v < 5; ++v) F[v] = F[v] - 0.5 * lam * dU[v];
+      }
+    } break;
+    case FLEXI_RIEMANN_HLLC: {  // riemann.f90:594-663 (not selectable with SPLIT_DG, riemann.f90:206-227)
+      const RoeMean m = roe_average(q, L, R);
+      const double Ssl = m.v1 - m.c, Ssr = m.v1 + m.c;
+      if (Ssl >= 0.) {
+#pragma unroll
+        for (int v = 0; v < 5; ++v) F[v] = FL[v];
+      } else if (Ssr <= 0.) {
+#pragma unroll
+        for (int v = 0; v < 5; ++v) F[v] = FR[v];
+      } else {
+        const double sMu_L = Ssl - L.v1, sMu_R = Ssr - R.v1;
+        const double SStar = (R.p - L.p + L.m1 * sMu_L - R.m1 * sMu_R) / (L.rho * sMu_L - R.rho * sMu_R);
+        if ((Ssl <= 0.) && (SStar >= 0.)) {
+          const double EStar = L.E * L.srho + (SStar - L.v1) * (SStar + L.p * L.srho / sMu_L);
+          const double fac = L.rho * sMu_L / (Ssl - SStar);
+          const double US[5] = {fac, fac * SStar, fac * L.v2, fac * L.v3, fac * EStar};
+          const double UL[5] = {L.rho, L.m1, L.m2, L.m3, L.E};
+#pragma unroll
+          for (int v = 0; v < 5; ++v) F[v] = FL[v] + Ssl * (US[v] - UL[v]);
+        } else {
+          const double EStar = R.E * R.srho + (SStar - R.v1) * (SStar + R.p * R.srho / sMu_R);
+          const double fac = R.rho * sMu_R / (Ssr - SStar);
+          const double US[5] = {fac, fac * SStar, fac * R.v2, fac * R.v3, fac * EStar};
+          const double UR[5] = {R.rho, R.m1, R.m2, R.m3, R.E};
+#pragma unroll
+          for (int v = 0; v < 5; ++v) F[v] = FR[v] + Ssr * (US[v] - UR[v]);
+        }
+      }
+    } break;
+    case FLEXI_RIEMANN_ROE:      // riemann.f90:668-740
+    case FLEXI_RIEMANN_ROEL2: {  // riemann.f90:983-1061
+      const RoeMean m = roe_average(q, L, R);
+      double d[6] = {dU[0], dU[1], dU[2], dU[3], dU[4], 0.};
+      d[5] = d[4] - (d[2] - m.v2 * d[0]) * m.v2 - (d[3] - m.v3 * d[0]) * m.v3;
+      if (solver == FLEXI_RIEMANN_ROEL2) {
+        const double Ma_loc = sqrt(m.absVel) / (m.c * sqrt(q.kappa));
+        d[1] *= Ma_loc;
+        d[2] *= Ma_loc;
+        d[3] *= Ma_loc;
+      }
+      double al[5], a[5], D[5];
+      al[2] = d[2] - m.v2 * d[0];
+      al[3] = d[3] - m.v3 * d[0];
+      al[1] = q.kappaM1 / (m.c * m.c) * (d[0] * (m.H - m.v1 * m.v1) - d[5] + m.v1 * d[1]);  // ALPHA2_RIEMANN_H, eos.h:51
+      al[0] = 0.5 / m.c * (d[0] * (m.v1 + m.c) - d[1] - m.c * al[1]);
+      al[4] = d[0] - al[0] - al[1];
+      a[0] = fabs(m.v1 - m.c);
+      a[1] = a[2] = a[3] = fabs(m.v1);
+      a[4] = fabs(m.v1 + m.c);
+      roe_dissipation(m, al, a, D);
+      if (!split) {
+#pragma unroll
+        for (int v = 0; v < 5; ++v) F[v] = 0.5 * ((FL[v] + FR[v]) - D[v]);
+      } else {
+        split_surface_flux(q.splitType, L, R, F);
+#pragma unroll
+        for (int v = 0; v < 5; ++v) F[v] = F[v] - 0.5 * D[v];
+      }
+    } break;
+    case FLEXI_RIEMANN_ROEENTROPYFIX: {  // riemann.f90:748-855
+      const double c_L = sound_speed(q, L), c_R = sound_speed(q, R);
+      const RoeMean m = roe_average(q, L, R);
+      const double RoeDens = sqrt(L.rho * R.rho);
+      const double dp[5] = {R.rho - L.rho, R.v1 - L.v1, R.v2 - L.v2, R.v3 - L.v3, R.p - L.p};
+      const double tmp = 0.5 / (m.c * m.c);
+      double al[5], a[5], D[5];
+      al[0] = tmp * (dp[4] - RoeDens * m.c * dp[1]);
+      al[1] = dp[0] - dp[4] * 2. * tmp;
+      al[2] = RoeDens * dp[2];
+      al[3] = RoeDens * dp[3];
+      al[4] = tmp * (dp[4] + RoeDens * m.c * dp[1]);
+      a[0] = m.v1 - m.c;
+      a[1] = a[2] = a[3] = m.v1;
+      a[4] = m.v1 + m.c;
+      const double aL[5] = {L.v1 - c_L, L.v1, L.v1, L.v1, L.v1 + c_L};
+      const double aR[5] = {R.v1 - c_R, R.v1, R.v1, R.v1, R.v1 + c_R};
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {  // Harten-Hyman 2, riemann.f90:826-834
+        const double da = fmax(0., fmax(a[i] - aL[i], aR[i] - a[i]));
+        if (fabs(a[i]) < da)
+          a[i] = 0.5 * (a[i] * a[i] / da + da);
+        else
+          a[i] = fabs(a[i]);
+      }
+      roe_dissipation(m, al, a, D);
+      if (!split) {
+#pragma unroll
+        for (int v = 0; v < 5; ++v) F[v] = 0.5 * ((FL[v] + FR[v]) - D[v]);
+      } else {
+        split_surface_flux(q.splitType, L, R, F);
+#pragma unroll
+        for (int v = 0; v < 5; ++v) F[v] = F[v] - 0.5 * D[v];
+      }
+    } break;
+    default: {  // HLL riemann.f90:1067-1113, HLLE :1119-1164, HLLEM :1170-1228
+      const RoeMean m = roe_average(q, L, R);
+      double Ssl, Ssr;
+      if (solver == FLEXI_RIEMANN_HLL) {
+        Ssl = m.v1 - m.c;
+        Ssr = m.v1 + m.c;
+      } else {
+        const double beta = sqrt(0.5 * q.kappaM1 / q.kappa);  // BETA_RIEMANN_H, eos.h:49
+        Ssl = fmin(fmin(m.v1 - m.c, L.v1 - beta * sound_speed(q, L)), 0.);
+        Ssr = fmax(fmax(m.v1 + m.c, R.v1 + beta * sound_speed(q, R)), 0.);
+      }
+      if (Ssl >= 0.) {
+#pragma unroll
+        for (int v = 0; v < 5; ++v) F[v] = FL[v];
+      } else if (Ssr <= 0.) {
+#pragma unroll
+        for (int v = 0; v < 5; ++v) F[v] = FR[v];
+      } else if (solver != FLEXI_RIEMANN_HLLEM) {
+#pragma unroll
+        for (int v = 0; v < 5; ++v) F[v] = (Ssr * FL[v] - Ssl * FR[v] + Ssl * Ssr * dU[v]) / (Ssr - Ssl);
+      } else {
+        const double RoeDens = sqrt(L.rho * R.rho);
+        const double delta = m.c / (m.c + fabs(0.5 * (Ssl + Ssr)));
+        const double A2 = (R.rho - L.rho) - (R.p - L.p) / (m.c * m.c);
+        const double A3 = RoeDens * (R.v2 - L.v2), A4 = RoeDens * (R.v3 - L.v3);
+        const double r2[5] = {1., m.v1, m.v2, m.v3, 0.5 * m.absVel};
+        const double r3[5] = {0., 0., 1., 0., m.v2};
+        const double r4[5] = {0., 0., 0., 1., m.v3};
+#pragma unroll
+        for (int v = 0; v < 5; ++v)
+          F[v] = (Ssr * FL[v] - Ssl * FR[v] + Ssl * Ssr * (dU[v] - delta * (r2[v] * A2 + r3[v] * A3 + r4[v] * A4))) / (Ssr - Ssl);
+      }
+    }
+  }
+}
+
+// riemann.f90:360-440 Riemann_Point: rotate into (n,t1,t2), solve, rotate back.  U_*: cons, P_*: prim of the traces.
+__device__ __forceinline__ void riemann_point(const Eqn& q, int solver, const double* U_L, const double* U_R, const double* P_L,
+                                              const double* P_R, const double* nv, const double* t1, const double* t2, double* FOut) {
+  Ext L, R;
+  L.rho = U_L[DENS];
+  L.srho = 1. / L.rho;
+  L.E = U_L[ENER];
+  L.p = P_L[PRES];
+  L.v1 = P_L[VEL1] * nv[0] + P_L[VEL2] * nv[1] + P_L[VEL3] * nv[2];
+  L.v2 = P_L[VEL1] * t1[0] + P_L[VEL2] * t1[1] + P_L[VEL3] * t1[2];
+  L.v3 = P_L[VEL1] * t2[0] + P_L[VEL2] * t2[1] + P_L[VEL3] * t2[2];
+  L.m1 = L.rho * L.v1;
+  L.m2 = L.rho * L.v2;
+  L.m3 = L.rho * L.v3;
+  R.rho = U_R[DENS];
+  R.srho = 1. / R.rho;
+  R.E = U_R[ENER];
+  R.p = P_R[PRES];
+  R.v1 = P_R[VEL1] * nv[0] + P_R[VEL2] * nv[1] + P_R[VEL3] * nv[2];
+  R.v2 = P_R[VEL1] * t1[0] + P_R[VEL2] * t1[1] + P_R[VEL3] * t1[2];
+  R.v3 = P_R[VEL1] * t2[0] + P_R[VEL2] * t2[1] + P_R[VEL3] * t2[2];
+  R.m1 = R.rho * R.v1;
+  R.m2 = R.rho * R.v2;
+  R.m3 = R.rho * R.v3;
+  double F[5];
+  riemann_solver(q, solver, L, R, F);
+  FOut[DENS] = F[0];
+  FOut[MOM1] = nv[0] * F[1] + t1[0] * F[2] + t2[0] * F[3];
+  FOut[MOM2] = nv[1] * F[1] + t1[1] * F[2] + t2[1] * F[3];
+  FOut[MOM3] = nv[2] * F[1] + t1[2] * F[2] + t2[2] * F[3];
+  FOut[ENER] = F[4];
+}
+
+}  // namespace fx

@@ -1,0 +1,202 @@
+"""Host-side mirror of the reference's operator interface for the hot path, on top of the C ABI (include/flexi_gpu.h).
+
+Method names follow the reference routines they replace (file:line under /root/reference/src):
+
+    FlexiGpu.DGTimeDerivative_weakForm(t)   dg/dg.f90:221
+    FlexiGpu.TimeStep(t, dt)                timedisc/timestep.f90:82   (TimeStepByLSERKW2)
+    FlexiGpu.CalcTimeStep()                 equations/navierstokes/calctimestep.f90:89
+    FlexiGpu.ProlongToFace / SurfInt        interpolation/prolongtoface.t90:21, dg/surfint.t90:21
+
+Arrays cross this boundary as numpy arrays with the memory layout of the Fortran module arrays (numpy shape = reversed
+Fortran shape, e.g. U[iElem, k, j, i, var]).  There is no CPU fallback: a missing library or a missing GPU raises.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from .desc import FlexiGpuDesc
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libflexi_gpu.so")
+_LIB = None
+
+ARRAYS = dict(U=0, Ut=1, U_master=2, U_slave=3, Flux=4, gradUx=5, gradUy=6, gradUz=7, gradUx_master=8, gradUy_master=9,
+              gradUz_master=10, gradUx_slave=11, gradUy_slave=12, gradUz_slave=13)
+KERNEL_CLASSES = ("volume", "flux", "update", "prolong", "calc_timestep", "layout")
+
+# every symbol include/flexi_gpu.h declares
+EXPORTS = ("flexi_gpu_last_error", "flexi_gpu_abi_version", "flexi_gpu_nccl_unique_id", "flexi_gpu_init", "flexi_gpu_finalize",
+           "flexi_gpu_set_state", "flexi_gpu_get_state", "flexi_gpu_dg_time_derivative", "flexi_gpu_timestep",
+           "flexi_gpu_timestep_n", "flexi_gpu_calc_timestep", "flexi_gpu_get_array", "flexi_gpu_keep_gradients",
+           "flexi_gpu_prolong_to_face", "flexi_gpu_surf_int", "flexi_gpu_counters", "flexi_gpu_kernel_times",
+           "flexi_gpu_set_profiling", "flexi_gpu_synchronize", "flexi_gpu_stream")
+
+
+class FlexiGpuError(RuntimeError):
+    pass
+
+
+def build(force=False):
+    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    cmd = ["make", "-C", os.path.join(_HERE, "csrc"), "-j", str(os.cpu_count() or 4), "-s"]
+    if force:
+        cmd.append("-B")
+    subprocess.check_call(cmd)
+
+
+def lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise FlexiGpuError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` (no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    P, PD, I32 = C.c_void_p, C.POINTER(C.c_double), C.c_int32
+    L.flexi_gpu_last_error.restype = C.c_char_p
+    L.flexi_gpu_abi_version.restype = C.c_int
+    L.flexi_gpu_nccl_unique_id.argtypes = [P]
+    L.flexi_gpu_init.argtypes = [C.POINTER(FlexiGpuDesc), C.POINTER(P)]
+    L.flexi_gpu_finalize.argtypes = [P]
+    L.flexi_gpu_set_state.argtypes = [P, PD]
+    L.flexi_gpu_get_state.argtypes = [P, PD]
+    L.flexi_gpu_dg_time_derivative.argtypes = [P, C.c_double, PD]
+    L.flexi_gpu_timestep.argtypes = [P, PD, C.c_double]
+    L.flexi_gpu_timestep_n.argtypes = [P, PD, C.c_double, I32]
+    L.flexi_gpu_calc_timestep.argtypes = [P, PD, PD, PD, C.POINTER(I32)]
+    L.flexi_gpu_get_array.argtypes = [P, I32, PD]
+    L.flexi_gpu_keep_gradients.argtypes = [P, I32]
+    L.flexi_gpu_prolong_to_face.argtypes = [P, PD, PD, PD, I32]
+    L.flexi_gpu_surf_int.argtypes = [P, PD, PD, PD, I32]
+    L.flexi_gpu_counters.argtypes = [P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.flexi_gpu_kernel_times.argtypes = [P, PD, C.POINTER(C.c_int64), I32, I32]
+    L.flexi_gpu_set_profiling.argtypes = [P, I32]
+    L.flexi_gpu_synchronize.argtypes = [P]
+    L.flexi_gpu_stream.argtypes = [P, C.POINTER(P)]
+    _LIB = L
+    return L
+
+
+def _pd(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def nccl_unique_id():
+    """Rank 0 creates the NCCL bootstrap id the host broadcasts (stands in for MPI_COMM_FLEXI, mpi/mpi.f90:89-109)."""
+    buf = C.create_string_buffer(128)
+    L = lib()
+    if L.flexi_gpu_nccl_unique_id(buf) != 0:
+        raise FlexiGpuError(L.flexi_gpu_last_error().decode())
+    return bytes(buf.raw)
+
+
+class FlexiGpu:
+    """One FLEXI rank's device-side DG operator + time stepper (InitDG/InitLifting/InitTimeDisc equivalent at construction)."""
+
+    def __init__(self, host_rank):
+        self.L = lib()
+        self.host = host_rank
+        d = host_rank.desc
+        self.np = d.N + 1
+        self.nElems, self.nSides, self.nvl = d.nElems, d.nSides, d.nVarLifting
+        self.h = C.c_void_p()
+        self._ck(self.L.flexi_gpu_init(C.byref(d), C.byref(self.h)))
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise FlexiGpuError(f"flexi_gpu error {rc}: {self.L.flexi_gpu_last_error().decode()}")
+
+    # ---- shapes of the module arrays (reversed Fortran shapes) ----
+    def _shape(self, name):
+        n = self.np
+        if name in ("U", "Ut"):
+            return (self.nElems, n, n, n, 5)
+        if name in ("gradUx", "gradUy", "gradUz"):
+            return (self.nElems, n, n, n, self.nvl)
+        if name in ("U_master", "U_slave", "Flux"):
+            return (self.nSides, n, n, 5)
+        return (self.nSides, n, n, self.nvl)
+
+    # ---- state ----
+    def set_state(self, U):
+        U = np.ascontiguousarray(U, dtype=np.float64)
+        assert U.shape == self._shape("U"), (U.shape, self._shape("U"))
+        self._ck(self.L.flexi_gpu_set_state(self.h, _pd(U)))
+
+    def get_state(self, out=None):
+        out = np.empty(self._shape("U")) if out is None else out
+        self._ck(self.L.flexi_gpu_get_state(self.h, _pd(out)))
+        return out
+
+    def get_array(self, name):
+        out = np.empty(self._shape(name))
+        self._ck(self.L.flexi_gpu_get_array(self.h, ARRAYS[name], _pd(out)))
+        return out
+
+    def keep_gradients(self, on=True):
+        self._ck(self.L.flexi_gpu_keep_gradients(self.h, int(on)))
+
+    # ---- the operator ----
+    def DGTimeDerivative_weakForm(self, t=0.0, want_ut=True):
+        if want_ut:
+            out = np.empty(self._shape("Ut"))
+            self._ck(self.L.flexi_gpu_dg_time_derivative(self.h, float(t), _pd(out)))
+            return out
+        self._ck(self.L.flexi_gpu_dg_time_derivative(self.h, float(t), None))
+        return None
+
+    def TimeStep(self, t, dt, n_steps=1):
+        tt = C.c_double(float(t))
+        self._ck(self.L.flexi_gpu_timestep_n(self.h, C.byref(tt), float(dt), int(n_steps)))
+
+    def CalcTimeStep(self):
+        a, b, c, e = C.c_double(0), C.c_double(0), C.c_double(0), C.c_int32(0)
+        self._ck(self.L.flexi_gpu_calc_timestep(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(e)))
+        return a.value, b.value, c.value, e.value
+
+    def ProlongToFace(self, Uvol, Uface_master, Uface_slave, doMPISides=False):
+        Uvol = np.ascontiguousarray(Uvol, dtype=np.float64)
+        self._ck(self.L.flexi_gpu_prolong_to_face(self.h, _pd(Uvol), _pd(Uface_master), _pd(Uface_slave), int(doMPISides)))
+        return Uface_master, Uface_slave
+
+    def SurfInt(self, Flux_master, Flux_slave, Ut, doMPISides=False):
+        fm = np.ascontiguousarray(Flux_master, dtype=np.float64)
+        fs = np.ascontiguousarray(Flux_slave, dtype=np.float64)
+        self._ck(self.L.flexi_gpu_surf_int(self.h, _pd(fm), _pd(fs), _pd(Ut), int(doMPISides)))
+        return Ut
+
+    # ---- accounting ----
+    def counters(self):
+        a, b, c = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        self._ck(self.L.flexi_gpu_counters(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return dict(kernel_launches=a.value, h2d_bytes=b.value, d2h_bytes=c.value)
+
+    def set_profiling(self, on):
+        self._ck(self.L.flexi_gpu_set_profiling(self.h, int(on)))
+
+    def kernel_times(self, reset=False):
+        n = len(KERNEL_CLASSES)
+        ms = (C.c_double * n)()
+        cnt = (C.c_int64 * n)()
+        self._ck(self.L.flexi_gpu_kernel_times(self.h, ms, cnt, n, int(reset)))
+        return {k: (ms[i], cnt[i]) for i, k in enumerate(KERNEL_CLASSES)}
+
+    def synchronize(self):
+        self._ck(self.L.flexi_gpu_synchronize(self.h))
+
+    def stream(self):
+        s = C.c_void_p()
+        self._ck(self.L.flexi_gpu_stream(self.h, C.byref(s)))
+        return s.value
+
+    def close(self):
+        if self.h:
+            self.L.flexi_gpu_finalize(self.h)
+            self.h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()

@@ -198,6 +198,11 @@ int flexi_gpu_calc_timestep(flexi_gpu_handle* h, double* dt_min, double* dt_conv
 /* analysis access (TGV analysis reads GradUx/y/z, testcase.f90:249; Ut is needed at analyze steps, timedisc_func.f90:323-326) */
 int flexi_gpu_get_array(flexi_gpu_handle* h, int32_t which, double* out);
 
+/* Volume gradients normally never leave the SM; with on != 0 every later evaluation also stores gradUx/y/z in device memory so
+ * that FLEXI_ARR_GRADU{X,Y,Z} return "the gradients left by the last DG operator call" like the module arrays do
+ * (testcase/taylorgreenvortex/testcase.f90:249).  Without it the first FLEXI_ARR_GRADU* request recomputes them from the current U. */
+int flexi_gpu_keep_gradients(flexi_gpu_handle* h, int32_t on);
+
 /* Operator-level entry points (what the reference's own unit tests drive, unitTests/ProlongToFace.f90, SurfInt.f90).
  * Host arrays in Fortran order; the handle supplies mesh + basis.  doMPISides selects the side range like the reference. */
 int flexi_gpu_prolong_to_face(flexi_gpu_handle* h, const double* Uvol, double* Uface_master, double* Uface_slave,
@@ -211,6 +216,8 @@ int flexi_gpu_counters(flexi_gpu_handle* h, int64_t* kernel_launches, int64_t* h
 int flexi_gpu_kernel_times(flexi_gpu_handle* h, double* ms_out, int64_t* launches_out, int32_t n_classes, int32_t reset);
 int flexi_gpu_set_profiling(flexi_gpu_handle* h, int32_t on);
 int flexi_gpu_synchronize(flexi_gpu_handle* h);
+/* the CUDA stream (cudaStream_t) all hot-path kernels of this handle are launched on, for event timing by the caller */
+int flexi_gpu_stream(flexi_gpu_handle* h, void** stream_out);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,205 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle on identical synthetic meshes and states.
+
+north_star gate: one Ut evaluation within relative 1e-12 (max|diff| / max|ref| per variable); the state after a fixed
+number of RK steps and the L2/Linf norms within 1e-10.
+"""
+import numpy as np
+import pytest
+
+from flexi_b200.gpu import FlexiGpu
+from flexi_b200.hostmesh import basis as B
+from flexi_b200.hostmesh.analyze import AnalyzeBasis, calc_error_norms
+from flexi_b200.hostmesh.case import TGV_EQN, build_case, tgv_box
+from flexi_b200.hostmesh.mesh import BoxSpec
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+CURVED = dict(x0=(-1.0, -1.0, -1.0), length=(2.0, 2.0, 2.0), ngeo=2, deform=0.1)
+TOL_UT = 1e-12
+G, GL = B.NODE_GAUSS, B.NODE_GAUSS_LOBATTO
+
+
+def rel(a, ref):
+    """max|a-ref| / max|ref| per last-axis variable."""
+    a2, r2 = a.reshape(-1, a.shape[-1]), ref.reshape(-1, ref.shape[-1])
+    den = np.maximum(np.max(np.abs(r2), axis=0), 1e-300)
+    return np.max(np.abs(a2 - r2), axis=0) / den
+
+
+def run_pair(spec, N, node, eqn, state="smooth"):
+    ranks = build_case(spec, N, node, eqn)
+    r = ranks[0]
+    if state == "smooth":
+        U0 = r.eqn.smooth_state(r.mesh.Elem_xGP, length=spec.length[0])
+    elif state == "tgv":
+        U0 = r.eqn.tgv_state(r.mesh.Elem_xGP)
+    else:
+        U0 = r.eqn.random_state(r.mesh.Elem_xGP.shape[:-1])
+    w = O.OracleWorld([(r.desc, r.keep)])
+    w.set_state([U0])
+    g = FlexiGpu(r)
+    g.set_state(U0)
+    return r, w, g, U0
+
+
+# (N, node, eqn overrides) -- weak form
+WEAK = [
+    (3, G, dict(parabolic=False, riemann="lf")),
+    (4, G, dict(parabolic=False, riemann="roe")),
+    (4, GL, dict(parabolic=False, riemann="hllc")),
+    (2, G, dict(parabolic=True, riemann="roeentropyfix", mu0=1e-2)),
+    (3, GL, dict(parabolic=True, riemann="lf", mu0=1e-2)),
+    (5, G, dict(parabolic=True, riemann="hllc", mu0=1e-2)),
+    (5, GL, dict(parabolic=True, riemann="roe", mu0=1e-2, n_var_lifting=4)),
+    (7, G, dict(parabolic=True, riemann="roe", mu0=1e-2, n_var_lifting=4)),
+    (7, GL, dict(parabolic=True, riemann="roeentropyfix", mu0=1e-2)),
+    (9, G, dict(parabolic=True, riemann="hll", mu0=1e-2)),
+    (9, GL, dict(parabolic=True, riemann="hllem", mu0=1e-2)),
+    (1, G, dict(parabolic=True, riemann="roel2", mu0=1e-2)),
+    (6, GL, dict(parabolic=True, riemann="hlle", mu0=1e-2)),
+    (8, G, dict(parabolic=False, riemann="roeentropyfix")),
+]
+SPLIT = [
+    (3, GL, dict(parabolic=False, split_dg=True, split_dg_type="sd", riemann="lf")),
+    (4, GL, dict(parabolic=False, split_dg=True, split_dg_type="pi", riemann="roe")),
+    (5, GL, dict(parabolic=True, split_dg=True, split_dg_type="du", riemann="roeentropyfix", mu0=1e-2)),
+    (5, GL, dict(parabolic=True, split_dg=True, split_dg_type="kg", riemann="lf", mu0=1e-2, n_var_lifting=4)),
+    (7, GL, dict(parabolic=True, split_dg=True, split_dg_type="pi", riemann="lf", mu0=1e-2)),
+    (7, GL, dict(parabolic=True, split_dg=True, split_dg_type="pi", riemann="roeentropyfix", mu0=1e-2, n_var_lifting=4)),
+    (9, GL, dict(parabolic=True, split_dg=True, split_dg_type="pi", riemann="roel2", mu0=1e-2)),
+]
+
+
+def _ids(cases):
+    return [f"N{n}-{'G' if nd == G else 'GL'}-" + "-".join(f"{k}={v}" for k, v in e.items() if k != "mu0") for n, nd, e in cases]
+
+
+@pytest.mark.parametrize("N,node,eqn", WEAK + SPLIT, ids=_ids(WEAK + SPLIT))
+def test_ut_and_side_arrays_match_oracle_on_curved_mesh(N, node, eqn):
+    """One DGTimeDerivative_weakForm on the sine-deformed periodic box: Ut, traces, fluxes and lifted gradients."""
+    r, w, g, _ = run_pair(BoxSpec((3, 2, 2), **CURVED), N, node, eqn)
+    try:
+        w.dg_time_derivative(0.0)
+        ut = g.DGTimeDerivative_weakForm(0.0)
+        o = w.ranks[0]
+        assert np.all(rel(ut, o.array("Ut")) < TOL_UT), rel(ut, o.array("Ut"))
+        for name in ("U_master", "U_slave"):
+            assert np.all(rel(g.get_array(name), o.array(name)) < 1e-14), name
+        assert np.all(rel(g.get_array("Flux"), o.array("Flux")) < TOL_UT)
+        if eqn.get("parabolic"):
+            for name in ("gradUx", "gradUy", "gradUz", "gradUx_master", "gradUy_master", "gradUz_master", "gradUx_slave",
+                         "gradUy_slave", "gradUz_slave"):
+                a, ref = g.get_array(name), o.array(name)
+                scale = max(np.max(np.abs(o.array(n2))) for n2 in ("gradUx", "gradUy", "gradUz"))
+                assert np.max(np.abs(a - ref)) < 1e-12 * scale, name
+    finally:
+        g.close()
+        w.close()
+
+
+@pytest.mark.parametrize("N,node,eqn", [WEAK[4], WEAK[7], SPLIT[4], SPLIT[5]], ids=_ids([WEAK[4], WEAK[7], SPLIT[4], SPLIT[5]]))
+def test_rk_steps_and_timestep_match_oracle(N, node, eqn):
+    """CalcTimeStep + 3 LSERK steps: dt to 1e-14, state to 1e-12, L2/Linf norms against the initial state to 1e-10."""
+    r, w, g, U0 = run_pair(BoxSpec((3, 2, 2), **CURVED), N, node, eqn)
+    try:
+        t = 0.0
+        for _ in range(3):
+            dt_o, c_o, v_o, e_o = w.calc_timestep()
+            dt_g, c_g, v_g, e_g = g.CalcTimeStep()
+            assert e_o == 0 and e_g == 0
+            assert abs(dt_g - dt_o) <= 1e-13 * dt_o and abs(c_g - c_o) <= 1e-13 * c_o
+            if eqn.get("parabolic"):
+                assert abs(v_g - v_o) <= 1e-13 * v_o
+            w.timestep(t, dt_o)
+            g.TimeStep(t, dt_o)
+            t += dt_o
+        Ug, Uo = g.get_state(), w.ranks[0].array("U")
+        assert np.all(rel(Ug, Uo) < 1e-12), rel(Ug, Uo)
+        ab = AnalyzeBasis(r.basis)
+        vol = ab.volume(r.mesh.sJ)
+        exact = lambda x: r.eqn.smooth_state(x, length=2.0)  # noqa: E731
+        l2g, lig = calc_error_norms(ab, r.mesh, Ug, exact, vol)
+        l2o, lio = calc_error_norms(ab, r.mesh, Uo, exact, vol)
+        assert np.all(np.abs(np.sqrt(l2g / vol) - np.sqrt(l2o / vol)) <= 1e-10 * np.maximum(np.sqrt(l2o / vol), 1e-30))
+        assert np.all(np.abs(lig - lio) <= 1e-10 * np.maximum(lio, 1e-30))
+    finally:
+        g.close()
+        w.close()
+
+
+def test_tgv_config1_flavour_small():
+    """BASELINE config 1 flavour (TGV, N=7, Gauss, Roe, BR1, weak form) on a 4^3 box: Ut to 1e-12, 2 steps to 1e-12."""
+    eqn = dict(parabolic=True, riemann="roe", cfl_scale=0.8, dfl_scale=0.8, **TGV_EQN)
+    r, w, g, _ = run_pair(tgv_box(4), 7, G, eqn, state="tgv")
+    try:
+        w.dg_time_derivative(0.0)
+        ut = g.DGTimeDerivative_weakForm(0.0)
+        assert np.all(rel(ut, w.ranks[0].array("Ut")) < TOL_UT), rel(ut, w.ranks[0].array("Ut"))
+        t = 0.0
+        for _ in range(2):
+            dt, *_ = w.calc_timestep()
+            w.timestep(t, dt)
+            g.TimeStep(t, dt)
+            t += dt
+        assert np.all(rel(g.get_state(), w.ranks[0].array("U")) < 1e-12)
+    finally:
+        g.close()
+        w.close()
+
+
+def test_tgv_config2_flavour_small():
+    """BASELINE config 2 flavour (TGV, N=7, split-form Gauss-Lobatto Pirozzoli + Lax-Friedrichs) on a 4^3 box."""
+    eqn = dict(parabolic=True, split_dg=True, split_dg_type="pi", riemann="lf", cfl_scale=0.8, dfl_scale=0.8, **TGV_EQN)
+    r, w, g, _ = run_pair(tgv_box(4), 7, GL, eqn, state="tgv")
+    try:
+        w.dg_time_derivative(0.0)
+        ut = g.DGTimeDerivative_weakForm(0.0)
+        assert np.all(rel(ut, w.ranks[0].array("Ut")) < TOL_UT), rel(ut, w.ranks[0].array("Ut"))
+        t = 0.0
+        for _ in range(2):
+            dt, *_ = w.calc_timestep()
+            w.timestep(t, dt)
+            g.TimeStep(t, dt)
+            t += dt
+        assert np.all(rel(g.get_state(), w.ranks[0].array("U")) < 1e-12)
+    finally:
+        g.close()
+        w.close()
+
+
+def test_random_field_stress():
+    """Discontinuous random state (SURVEY 8d stress input): every face has an O(1) jump, all Riemann branches are exercised."""
+    for riemann in ("hllc", "roeentropyfix", "hll"):
+        r, w, g, _ = run_pair(BoxSpec((2, 2, 3), **CURVED), 4, G, dict(parabolic=True, riemann=riemann, mu0=1e-3), state="random")
+        try:
+            w.dg_time_derivative(0.0)
+            ut = g.DGTimeDerivative_weakForm(0.0)
+            assert np.all(rel(ut, w.ranks[0].array("Ut")) < TOL_UT), (riemann, rel(ut, w.ranks[0].array("Ut")))
+        finally:
+            g.close()
+            w.close()
+
+
+def test_freestream_preservation_on_device():
+    """Constant state on the curved mesh => Ut = 0 (run_basic/freestream_3D: L2 <= 1e-12)."""
+    ranks = build_case(BoxSpec((3, 2, 2), **CURVED), 4, G, dict(parabolic=True, riemann="roe", mu0=1e-2))
+    r = ranks[0]
+    prim = np.zeros(r.mesh.Elem_xGP.shape[:-1] + (6,))
+    prim[...] = (1.0, 0.3, -0.2, 0.1, 0.7, 0.0)
+    U0 = r.eqn.prim_to_cons(prim)
+    with FlexiGpu(r) as g:
+        g.set_state(U0)
+        ut = g.DGTimeDerivative_weakForm(0.0)
+        assert np.max(np.abs(ut)) < 1e-11
+
+
+def test_nan_state_reports_errtype():
+    """calctimestep.f90:157-160: NaN density => errType != 0 instead of a silent dt."""
+    ranks = build_case(tgv_box(2), 3, G, dict(parabolic=True, **TGV_EQN))
+    r = ranks[0]
+    U0 = r.eqn.tgv_state(r.mesh.Elem_xGP)
+    U0[1, 2, 1, 0, 0] = np.nan
+    with FlexiGpu(r) as g:
+        g.set_state(U0)
+        assert g.CalcTimeStep()[3] != 0
