@@ -288,7 +288,7 @@ int launch_volume(H* h, const int32_t* list, int n) {
     a.gvol[d] = h->keepGrad ? h->gvol[d] : nullptr;
   }
   Timer tm(h, KC_VOLUME, h->sc);
-  CK(h->ops->volume(h->gl, h->split, h->para, h->nvl, a, n, h->sc));
+  CK(h->ops->volume(h->gl, h->split, h->q.splitType, h->para, h->nvl, a, n, h->sc));
   return 0;
 }
 

@@ -1,5 +1,6 @@
 // np_kernels.cu -- instantiates kernels.cuh for one polynomial degree (compile with -DFLEXI_NP=<N+1>).
 #include "np_ops.h"
+#include "volume_gl.cuh"
 
 #ifndef FLEXI_NP
 #error "compile with -DFLEXI_NP=<N+1>"
@@ -10,27 +11,49 @@ namespace {
 constexpr int NP = FLEXI_NP;
 using D = Dim<NP>;
 
-template <bool GL, bool SPLIT, bool PARA, int NVL>
+// k-block size of the Gauss-Lobatto element kernel: half a zeta column per thread for even NP, one node otherwise
+constexpr int KPT = (NP % 2 == 0) ? NP / 2 : 1;
+
+template <bool PARA, int NVL>
 cudaError_t volume_setup() {
-  return cudaFuncSetAttribute(k_volume<NP, GL, SPLIT, PARA, NVL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)VolSmem<NP, GL, SPLIT, PARA>::BYTES);
+  return cudaFuncSetAttribute(k_volume<NP, false, false, PARA, NVL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)VolSmem<NP, false, false, PARA>::BYTES);
 }
-template <bool GL, bool SPLIT, bool PARA, int NVL>
+template <bool PARA, int NVL>
 cudaError_t volume_launch(const VolArgs& a, int nBlocks, cudaStream_t s) {
-  k_volume<NP, GL, SPLIT, PARA, NVL><<<nBlocks, D::NP3, VolSmem<NP, GL, SPLIT, PARA>::BYTES, s>>>(a);
+  k_volume<NP, false, false, PARA, NVL><<<nBlocks, D::NP3, VolSmem<NP, false, false, PARA>::BYTES, s>>>(a);
+  return cudaGetLastError();
+}
+template <bool SPLIT, int STYPE, bool PARA, int NVL>
+cudaError_t volume_gl_setup() {
+  using C = VolGLCfg<NP, KPT, SPLIT, PARA>;
+  return cudaFuncSetAttribute(k_volume_gl<NP, KPT, SPLIT, STYPE, PARA, NVL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::BYTES);
+}
+template <bool SPLIT, int STYPE, bool PARA, int NVL>
+cudaError_t volume_gl_launch(const VolArgs& a, int nBlocks, cudaStream_t s) {
+  using C = VolGLCfg<NP, KPT, SPLIT, PARA>;
+  k_volume_gl<NP, KPT, SPLIT, STYPE, PARA, NVL><<<nBlocks, C::NT, C::BYTES, s>>>(a);
   return cudaGetLastError();
 }
 
 constexpr size_t upd_smem = sizeof(double) * (D::NBASIS + 5 * D::NP3);
 
+#define FX_SPLIT_TYPES(X) X(FLEXI_SPLITDG_SD) X(FLEXI_SPLITDG_DU) X(FLEXI_SPLITDG_KG) X(FLEXI_SPLITDG_PI)
+
 cudaError_t setup() {
   cudaError_t e;
-#define S(GL, SP, PA, NV) \
-  if ((e = volume_setup<GL, SP, PA, NV>()) != cudaSuccess) return e;
-  S(false, false, false, 5) S(false, false, true, 5) S(false, false, true, 4)
-  S(true, false, false, 5) S(true, false, true, 5) S(true, false, true, 4)
-  S(true, true, false, 5) S(true, true, true, 5) S(true, true, true, 4)
-#undef S
+  if ((e = volume_setup<false, 5>()) != cudaSuccess) return e;
+  if ((e = volume_setup<true, 5>()) != cudaSuccess) return e;
+  if ((e = volume_setup<true, 4>()) != cudaSuccess) return e;
+  if ((e = volume_gl_setup<false, 0, false, 5>()) != cudaSuccess) return e;
+  if ((e = volume_gl_setup<false, 0, true, 5>()) != cudaSuccess) return e;
+  if ((e = volume_gl_setup<false, 0, true, 4>()) != cudaSuccess) return e;
+#define X(T)                                                                     \
+  if ((e = volume_gl_setup<true, T, false, 5>()) != cudaSuccess) return e;       \
+  if ((e = volume_gl_setup<true, T, true, 5>()) != cudaSuccess) return e;        \
+  if ((e = volume_gl_setup<true, T, true, 4>()) != cudaSuccess) return e;
+  FX_SPLIT_TYPES(X)
+#undef X
   if ((e = cudaFuncSetAttribute(k_update<NP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(k_update<NP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem)) != cudaSuccess) return e;
   const int pro = (int)(sizeof(double) * (D::NBASIS + 6 * D::NP3));
@@ -49,24 +72,26 @@ cudaError_t prolong(bool gl, const ProArgs& a, int nElems, cudaStream_t s) {
   return cudaGetLastError();
 }
 
-cudaError_t volume(bool gl, bool split, bool para, int nvl, const VolArgs& a, int nBlocks, cudaStream_t s) {
+cudaError_t volume(bool gl, bool split, int stype, bool para, int nvl, const VolArgs& a, int nBlocks, cudaStream_t s) {
   if (nBlocks <= 0) return cudaSuccess;
   if (split && !gl) return cudaErrorNotSupported;
-#define L(GL, SP, PA, NV) return volume_launch<GL, SP, PA, NV>(a, nBlocks, s)
-  if (!para) {
-    if (!gl) L(false, false, false, 5);
-    if (!split) L(true, false, false, 5);
-    L(true, true, false, 5);
+  if (!gl) {
+    if (!para) return volume_launch<false, 5>(a, nBlocks, s);
+    return nvl == 5 ? volume_launch<true, 5>(a, nBlocks, s) : volume_launch<true, 4>(a, nBlocks, s);
   }
-  if (nvl == 5) {
-    if (!gl) L(false, false, true, 5);
-    if (!split) L(true, false, true, 5);
-    L(true, true, true, 5);
+  if (!split) {
+    if (!para) return volume_gl_launch<false, 0, false, 5>(a, nBlocks, s);
+    return nvl == 5 ? volume_gl_launch<false, 0, true, 5>(a, nBlocks, s) : volume_gl_launch<false, 0, true, 4>(a, nBlocks, s);
   }
-  if (!gl) L(false, false, true, 4);
-  if (!split) L(true, false, true, 4);
-  L(true, true, true, 4);
-#undef L
+  switch (stype) {
+#define X(T)                                                                                                     \
+  case T:                                                                                                        \
+    if (!para) return volume_gl_launch<true, T, false, 5>(a, nBlocks, s);                                        \
+    return nvl == 5 ? volume_gl_launch<true, T, true, 5>(a, nBlocks, s) : volume_gl_launch<true, T, true, 4>(a, nBlocks, s);
+    FX_SPLIT_TYPES(X)
+#undef X
+    default: return cudaErrorNotSupported;
+  }
 }
 
 cudaError_t flux(const FluxArgs& a, cudaStream_t s) {

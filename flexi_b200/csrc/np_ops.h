@@ -12,7 +12,7 @@ struct NpOps {
   int np;
   cudaError_t (*setup)();
   cudaError_t (*prolong)(bool gl, const ProArgs& a, int nElems, cudaStream_t s);
-  cudaError_t (*volume)(bool gl, bool split, bool para, int nvl, const VolArgs& a, int nBlocks, cudaStream_t s);
+  cudaError_t (*volume)(bool gl, bool split, int stype, bool para, int nvl, const VolArgs& a, int nBlocks, cudaStream_t s);
   cudaError_t (*flux)(const FluxArgs& a, cudaStream_t s);
   cudaError_t (*update)(bool gl, const UpdArgs& a, int nBlocks, cudaStream_t s);
   cudaError_t (*surfint)(bool gl, const SurfArgs& a, int nElems, cudaStream_t s);

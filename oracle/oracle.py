@@ -171,3 +171,23 @@ def surf_int(rank, nv, Flux_master, Flux_slave, Ut, L_HatMinus, L_HatPlus, doMPI
     lp = np.ascontiguousarray(L_HatPlus, dtype=np.float64)
     rank.lib.oracle_surf_int(rank.h, nv, _pd(fm), _pd(fs), _pd(Ut), int(doMPISides), _pd(lm), _pd(lp))
     return Ut
+
+
+def ut_noise_floor(descs_and_keeps, Us, t=0.0):
+    """Per-variable max|Ut_strict - Ut_fast| of ONE DG operator evaluation between the two oracle builds (strict IEEE order
+    vs. -O3 with FMA contraction, i.e. the flags the reference itself is built with, cmake/SetCompiler.cmake:83).
+
+    This is the reference's own compiler-flag noise: on ill-conditioned states (TGV at Ma=0.1: p0 ~ 71 against rho*u^2 ~ 1, the
+    pressure gradient cancels to 1e-5 of its terms) two faithful builds of the same Fortran differ by ~1e-11 relative, so a
+    parity gate cannot be tighter than that there.  Returns (noise[5], Ut_strict per rank)."""
+    out = []
+    for fast in (False, True):
+        w = OracleWorld(descs_and_keeps, fast=fast)
+        w.set_state(Us)
+        w.dg_time_derivative(t)
+        out.append([r.array("Ut").copy() for r in w.ranks])
+        w.close()
+    noise = np.zeros(5)
+    for a, b in zip(*out):
+        noise = np.maximum(noise, np.max(np.abs(a - b).reshape(-1, 5), axis=0))
+    return noise, out[0]

@@ -27,6 +27,16 @@ def rel(a, ref):
     return np.max(np.abs(a2 - r2), axis=0) / den
 
 
+def assert_ut_parity(ut, ref, noise=None):
+    """rel 1e-12 per variable; where the reference's own strict-vs-FMA builds differ by more (ill-conditioned TGV at Ma 0.1),
+    the gate is 4x that noise floor (oracle.ut_noise_floor)."""
+    d = np.max(np.abs(ut - ref).reshape(-1, 5), axis=0)
+    tol = TOL_UT * np.max(np.abs(ref).reshape(-1, 5), axis=0)
+    if noise is not None:
+        tol = np.maximum(tol, 4.0 * noise)
+    assert np.all(d <= tol), (d, tol)
+
+
 def run_pair(spec, N, node, eqn, state="smooth"):
     ranks = build_case(spec, N, node, eqn)
     r = ranks[0]
@@ -135,14 +145,19 @@ def test_tgv_config1_flavour_small():
     try:
         w.dg_time_derivative(0.0)
         ut = g.DGTimeDerivative_weakForm(0.0)
-        assert np.all(rel(ut, w.ranks[0].array("Ut")) < TOL_UT), rel(ut, w.ranks[0].array("Ut"))
+        noise, _ = O.ut_noise_floor([(r.desc, r.keep)], [r.eqn.tgv_state(r.mesh.Elem_xGP)])
+        assert_ut_parity(ut, w.ranks[0].array("Ut"), noise)
         t = 0.0
         for _ in range(2):
             dt, *_ = w.calc_timestep()
             w.timestep(t, dt)
             g.TimeStep(t, dt)
             t += dt
-        assert np.all(rel(g.get_state(), w.ranks[0].array("U")) < 1e-12)
+        # TGV: w-momentum is ~0 (max 1e-5), so momenta are judged against the common momentum scale
+        Ug, Uo = g.get_state(), w.ranks[0].array("U")
+        scale = np.array([np.abs(Uo[..., 0]).max(), np.abs(Uo[..., 1:4]).max(), np.abs(Uo[..., 1:4]).max(),
+                          np.abs(Uo[..., 1:4]).max(), np.abs(Uo[..., 4]).max()])
+        assert np.all(np.max(np.abs(Ug - Uo).reshape(-1, 5), axis=0) <= 1e-12 * scale)
     finally:
         g.close()
         w.close()
@@ -155,14 +170,19 @@ def test_tgv_config2_flavour_small():
     try:
         w.dg_time_derivative(0.0)
         ut = g.DGTimeDerivative_weakForm(0.0)
-        assert np.all(rel(ut, w.ranks[0].array("Ut")) < TOL_UT), rel(ut, w.ranks[0].array("Ut"))
+        noise, _ = O.ut_noise_floor([(r.desc, r.keep)], [r.eqn.tgv_state(r.mesh.Elem_xGP)])
+        assert_ut_parity(ut, w.ranks[0].array("Ut"), noise)
         t = 0.0
         for _ in range(2):
             dt, *_ = w.calc_timestep()
             w.timestep(t, dt)
             g.TimeStep(t, dt)
             t += dt
-        assert np.all(rel(g.get_state(), w.ranks[0].array("U")) < 1e-12)
+        # TGV: w-momentum is ~0 (max 1e-5), so momenta are judged against the common momentum scale
+        Ug, Uo = g.get_state(), w.ranks[0].array("U")
+        scale = np.array([np.abs(Uo[..., 0]).max(), np.abs(Uo[..., 1:4]).max(), np.abs(Uo[..., 1:4]).max(),
+                          np.abs(Uo[..., 1:4]).max(), np.abs(Uo[..., 4]).max()])
+        assert np.all(np.max(np.abs(Ug - Uo).reshape(-1, 5), axis=0) <= 1e-12 * scale)
     finally:
         g.close()
         w.close()
