@@ -129,7 +129,6 @@ __device__ __forceinline__ void split_lines(const double* sP, const double* sM, 
     const int base = n - me * stride;
 #pragma unroll
     for (int l = 0; l < NP; ++l) {
-      if (l == me) continue;
       const int nl = base + l * stride;
       Node b;
       b.rho = sP[0 * D::NP3 + nl];
@@ -141,7 +140,7 @@ __device__ __forceinline__ void split_lines(const double* sP, const double* sM, 
       const double Mb[3] = {sM[(3 * dir + 0) * D::NP3 + nl], sM[(3 * dir + 1) * D::NP3 + nl], sM[(3 * dir + 2) * D::NP3 + nl]};
       double F[5];
       split_volume_flux<STYPE>(a, b, M + 3 * dir, Mb, F);
-      const double d = dv[l * NP + me];  // DVolSurf(l,me)
+      const double d = (l == me) ? 0. : dv[l * NP + me];  // DVolSurf(l,me); self pair weighted with zero (no divergent skip)
 #pragma unroll
       for (int v = 0; v < 5; ++v) ut[v] = ut[v] + d * F[v];
     }

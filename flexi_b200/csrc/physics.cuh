@@ -29,7 +29,18 @@ __device__ __forceinline__ void cons_to_prim(const Eqn& q, const double* __restr
   p[VEL2] = c[MOM2] * sRho;
   p[VEL3] = c[MOM3] * sRho;
   p[PRES] = q.kappaM1 * (c[ENER] - 0.5 * (c[MOM1] * p[VEL1] + c[MOM2] * p[VEL2] + c[MOM3] * p[VEL3]));
-  p[TEMP] = p[PRES] * sRho / q.R;
+  p[TEMP] = p[PRES] * sRho * q.sR;  // the reference divides by R (eos.f90:229); 1/R is formed once on the host (<= 1 ulp)
+}
+// same, also returning 1/rho for callers that need it again
+__device__ __forceinline__ double cons_to_prim_srho(const Eqn& q, const double* __restrict__ c, double* __restrict__ p) {
+  const double sRho = 1. / c[DENS];
+  p[DENS] = c[DENS];
+  p[VEL1] = c[MOM1] * sRho;
+  p[VEL2] = c[MOM2] * sRho;
+  p[VEL3] = c[MOM3] * sRho;
+  p[PRES] = q.kappaM1 * (c[ENER] - 0.5 * (c[MOM1] * p[VEL1] + c[MOM2] * p[VEL2] + c[MOM3] * p[VEL3]));
+  p[TEMP] = p[PRES] * sRho * q.sR;
+  return sRho;
 }
 
 // flux.f90:66-119 EvalFlux3D_Point

@@ -51,17 +51,23 @@ struct VolGLCfg {
   static constexpr int NT = D::NP2 * KB;
   static constexpr bool BULK = (NP % 2 == 0);  // plane bytes must be a multiple of 16 for cp.async.bulk
   static constexpr int P_PLANES = 6;
-  static constexpr int M_PLANES = SPLIT ? 9 : 0;
+  // region X: first the staged lifting fluxes of the six faces (8 values per face node), later the 9 metric planes the
+  // two-point fluxes read from their line partners
+  static constexpr int X_FACE = PARA ? 6 * 8 * D::NP2 : 0;
+  static constexpr int X_MET = SPLIT ? 9 * D::NP3 : 0;
+  static constexpr int X_DOUBLES = ((X_FACE > X_MET ? X_FACE : X_MET) + 1) & ~1;
   static constexpr int W_PLANES = PARA ? (SPLIT ? 12 : 15) : (SPLIT ? 0 : 15);
   static constexpr int O_BASIS = 2;  // [0] = mbarrier
   static constexpr int NB = (D::NBASIS + 1) & ~1;
   static constexpr int O_P = O_BASIS + NB;
-  static constexpr int O_M = O_P + P_PLANES * D::NP3;
-  static constexpr int O_W = O_M + M_PLANES * D::NP3;
+  static constexpr int O_X = O_P + P_PLANES * D::NP3;
+  static constexpr int O_W = O_X + X_DOUBLES;
   static constexpr int DOUBLES = O_W + W_PLANES * D::NP3;
   static constexpr size_t BYTES = sizeof(double) * DOUBLES;
   static constexpr int MINB = (NT <= 256 && BYTES <= 113000) ? 2 : 1;  // two elements per SM when registers and smem allow
 };
+
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // raw two-point quantities of the Pirozzoli flux between nodes a and b with summed metrics m = Ma + Mb:
 //   contravariant flux (splitflux.f90:603-666 contracted with 0.5*(Ma+Mb)):
@@ -129,7 +135,8 @@ __global__ void __launch_bounds__(VolGLCfg<NP, KPT, SPLIT, PARA>::NT, VolGLCfg<N
   uint64_t* mbar = reinterpret_cast<uint64_t*>(sm);
   double* sB = sm + C::O_BASIS;
   double* sP = sm + C::O_P;  // rho,u,v,w,p, T (later H / rhoE / E for the split fluxes)
-  double* sM = sm + C::O_M;
+  double* sX = sm + C::O_X;  // lifting fluxes of the faces, then the metric planes
+  double* sM = sX;
   double* sW = sm + C::O_W;
   const int tid = threadIdx.x;
   const int e = A.elems ? A.elems[blockIdx.x] : blockIdx.x;
@@ -140,20 +147,21 @@ __global__ void __launch_bounds__(VolGLCfg<NP, KPT, SPLIT, PARA>::NT, VolGLCfg<N
   const double* dv = sB + D::O_DV;
   const double* gU = A.U + (size_t)e * 5 * D::NP3;
   const double* gM = A.m.Met + (size_t)e * 9 * D::NP3;
+  constexpr uint32_t bU = 5 * D::NP3 * 8, bM = 9 * D::NP3 * 8;
+  constexpr bool MET_EARLY = SPLIT && !PARA;  // without lifting region X is free from the start
 
-  // ---- stage the element ------------------------------------------------------------------------------------------------
+  // ---- stage the element: one TMA bulk copy for the 5 conservative planes (+ the 9 metric planes) ------------------------
   if (C::BULK) {
     if (tid == 0) mbar_init(mbar, 1);
     __syncthreads();
     if (tid == 0) {
-      constexpr uint32_t bU = 5 * D::NP3 * 8, bM = 9 * D::NP3 * 8;
-      mbar_expect_tx(mbar, bU + (SPLIT ? bM : 0));
+      mbar_expect_tx(mbar, bU + (MET_EARLY ? bM : 0));
       bulk_g2s(sP, gU, bU, mbar);
-      if (SPLIT) bulk_g2s(sM, gM, bM, mbar);
+      if (MET_EARLY) bulk_g2s(sM, gM, bM, mbar);
     }
   } else {
     for (int t = tid; t < 5 * D::NP3; t += NT) sP[t] = gU[t];
-    if (SPLIT)
+    if (MET_EARLY)
       for (int t = tid; t < 9 * D::NP3; t += NT) sM[t] = gM[t];
   }
   load_basis<NP>(sB, A.m.basis, tid, NT);
@@ -166,13 +174,13 @@ __global__ void __launch_bounds__(VolGLCfg<NP, KPT, SPLIT, PARA>::NT, VolGLCfg<N
     __syncthreads();
 
   // ---- ConsToPrim of the own nodes, in place ------------------------------------------------------------------------------
-  double Pn[KPT][6], Uc[KPT][5];
+  double Pn[KPT][6], Uc[KPT][5], sRho[KPT];
 #pragma unroll
   for (int c = 0; c < KPT; ++c) {
     const int n = ij + D::NP2 * (k0 + c);
 #pragma unroll
     for (int v = 0; v < 5; ++v) Uc[c][v] = sP[v * D::NP3 + n];
-    cons_to_prim(q, Uc[c], Pn[c]);
+    sRho[c] = cons_to_prim_srho(q, Uc[c], Pn[c]);
 #pragma unroll
     for (int v = 1; v < 6; ++v) sP[v * D::NP3 + n] = Pn[c][v];  // only the owner touches its nodes
   }
@@ -184,6 +192,37 @@ __global__ void __launch_bounds__(VolGLCfg<NP, KPT, SPLIT, PARA>::NT, VolGLCfg<N
 #pragma unroll
     for (int v = 0; v < 5; ++v) ut[c][v] = 0.;
 
+  if (PARA) {
+    // ---- lifting flux of the six faces, all lanes busy (lifting_fillflux.t90:81-107, strong form):
+    //      0.5*(UPrim_slave-UPrim_master)*SurfElem per lifting variable, plus the normal, in volume-face coordinates ----
+    for (int t = tid; t < 6 * D::NP2; t += NT) {
+      const int ls = t / D::NP2 + 1, pq = t % D::NP2;
+      const SideRef sr = A.m.e2s[e * 6 + ls - 1];
+      const int ab = A.m.s2v2[(sr.flip * 6 + ls - 1) * D::NP2 + pq];
+      int base, stride;
+      face_line<NP>(ls, ab % NP, ab / NP, base, stride);
+      const int nF = base + (is_minus_side(ls) ? 0 : N * stride);
+      const double* nbTrace = (sr.flip == 0) ? A.U_slave : A.U_master;
+      double Un[5], Pb[6];
+#pragma unroll
+      for (int v = 0; v < 5; ++v) Un[v] = nbTrace[((size_t)sr.side * 5 + v) * D::NP2 + pq];
+      const double* g = A.m.Geo + (size_t)sr.side * 10 * D::NP2 + pq;
+      const double n0 = g[0], n1 = g[D::NP2], n2 = g[2 * D::NP2], surf = g[9 * D::NP2];
+      cons_to_prim(q, Un, Pb);
+      const double sgn = (sr.flip == 0) ? 1. : -1.;
+      double* o = sX + (ls - 1) * 8 * D::NP2 + ab;
+#pragma unroll
+      for (int v = 0; v < NVL; ++v) {
+        const int pv = lift_prim(NVL, v);
+        o[v * D::NP2] = 0.5 * (sgn * (Pb[pv] - sP[pv * D::NP3 + nF])) * surf;
+      }
+      o[5 * D::NP2] = n0;
+      o[6 * D::NP2] = n1;
+      o[7 * D::NP2] = n2;
+    }
+    __syncthreads();
+  }
+
   if (PARA || !SPLIT) {
     constexpr int LV = (NVL == 5) ? 1 : 0;
 #pragma unroll
@@ -191,7 +230,7 @@ __global__ void __launch_bounds__(VolGLCfg<NP, KPT, SPLIT, PARA>::NT, VolGLCfg<N
       const int k = k0 + c, n = ij + D::NP2 * k;
       double M[9];
 #pragma unroll
-      for (int m = 0; m < 9; ++m) M[m] = SPLIT ? sM[m * D::NP3 + n] : gM[m * D::NP3 + n];
+      for (int m = 0; m < 9; ++m) M[m] = MET_EARLY ? sM[m * D::NP3 + n] : gM[m * D::NP3 + n];
       double F[5] = {0., 0., 0., 0., 0.}, G[5] = {0., 0., 0., 0., 0.}, H[5] = {0., 0., 0., 0., 0.};
       if (PARA) {
         // ---- lifting, volume part (lifting_volint.t90:26-118) ----
@@ -221,31 +260,22 @@ __global__ void __launch_bounds__(VolGLCfg<NP, KPT, SPLIT, PARA>::NT, VolGLCfg<N
           gy[v] = M[1] * gxi + M[4] * geta + M[7] * gzeta;
           gz[v] = M[2] * gxi + M[5] * geta + M[8] * gzeta;
         }
-        // ---- lifting, surface part: the owner of a boundary node gathers the neighbour trace
-        //      (lifting_fillflux.t90:81-107,189-239; lifting_br1.t90:195-292; strong form, same sign on both elements) ----
+        // ---- lifting, surface part (lifting_br1.t90:195-292): on LGL nodes only the boundary nodes receive it ----
         const bool onFace[6] = {k == 0, j == 0, i == N, j == N, i == 0, k == N};  // local sides 1..6 (flexi.h:90-95)
         const int abFace[6] = {i + NP * j, i + NP * k, j + NP * k, i + NP * k, j + NP * k, i + NP * j};
 #pragma unroll
         for (int ls = 1; ls <= 6; ++ls) {
-          if (!onFace[ls - 1]) continue;
-          const SideRef sr = A.m.e2s[e * 6 + ls - 1];
-          const int pq = A.m.v2s[(sr.flip * 6 + ls - 1) * D::NP2 + abFace[ls - 1]];
-          const double* nbTrace = (sr.flip == 0) ? A.U_slave : A.U_master;
-          double Un[5], Pb[6];
+          if (onFace[ls - 1]) {
+            const double* o = sX + (ls - 1) * 8 * D::NP2 + abFace[ls - 1];
+            const double n0 = o[5 * D::NP2], n1 = o[6 * D::NP2], n2 = o[7 * D::NP2];
+            const double lh = is_minus_side(ls) ? sB[D::O_LHM] : sB[D::O_LHP + N];
 #pragma unroll
-          for (int v = 0; v < 5; ++v) Un[v] = nbTrace[((size_t)sr.side * 5 + v) * D::NP2 + pq];
-          cons_to_prim(q, Un, Pb);
-          const double* g = A.m.Geo + (size_t)sr.side * 10 * D::NP2 + pq;
-          const double n0 = g[0], n1 = g[D::NP2], n2 = g[2 * D::NP2], surf = g[9 * D::NP2];
-          const double lh = is_minus_side(ls) ? sB[D::O_LHM] : sB[D::O_LHP + N];
-          const double sgn = (sr.flip == 0) ? 1. : -1.;
-#pragma unroll
-          for (int v = 0; v < NVL; ++v) {
-            const int pv = lift_prim(NVL, v);
-            const double f = 0.5 * (sgn * (Pb[pv] - Pn[c][pv])) * surf;
-            gx[v] = gx[v] + (f * n0) * lh;
-            gy[v] = gy[v] + (f * n1) * lh;
-            gz[v] = gz[v] + (f * n2) * lh;
+            for (int v = 0; v < NVL; ++v) {
+              const double f = o[v * D::NP2];
+              gx[v] = gx[v] + (f * n0) * lh;
+              gy[v] = gy[v] + (f * n1) * lh;
+              gz[v] = gz[v] + (f * n2) * lh;
+            }
           }
         }
 #pragma unroll
@@ -265,18 +295,19 @@ __global__ void __launch_bounds__(VolGLCfg<NP, KPT, SPLIT, PARA>::NT, VolGLCfg<N
         // ---- ProlongToFaceLifting on LGL nodes = copy of the boundary node (prolongtoface.t90:270-303) ----
 #pragma unroll
         for (int ls = 1; ls <= 6; ++ls) {
-          if (!onFace[ls - 1]) continue;
-          const SideRef sr = A.m.e2s[e * 6 + ls - 1];
-          const int pq = A.m.v2s[(sr.flip * 6 + ls - 1) * D::NP2 + abFace[ls - 1]];
-          double* const d0 = (sr.flip == 0) ? A.gm[0] : A.gs[0];
-          double* const d1 = (sr.flip == 0) ? A.gm[1] : A.gs[1];
-          double* const d2 = (sr.flip == 0) ? A.gm[2] : A.gs[2];
+          if (onFace[ls - 1]) {
+            const SideRef sr = A.m.e2s[e * 6 + ls - 1];
+            const int pq = A.m.v2s[(sr.flip * 6 + ls - 1) * D::NP2 + abFace[ls - 1]];
+            double* const d0 = (sr.flip == 0) ? A.gm[0] : A.gs[0];
+            double* const d1 = (sr.flip == 0) ? A.gm[1] : A.gs[1];
+            double* const d2 = (sr.flip == 0) ? A.gm[2] : A.gs[2];
 #pragma unroll
-          for (int v = 0; v < NVL; ++v) {
-            const size_t o = ((size_t)sr.side * NVL + v) * D::NP2 + pq;
-            d0[o] = gx[v];
-            d1[o] = gy[v];
-            d2[o] = gz[v];
+            for (int v = 0; v < NVL; ++v) {
+              const size_t o = ((size_t)sr.side * NVL + v) * D::NP2 + pq;
+              d0[o] = gx[v];
+              d1[o] = gy[v];
+              d2[o] = gz[v];
+            }
           }
         }
         // ---- viscous flux of this node (flux.f90:149-241) ----
@@ -309,7 +340,19 @@ __global__ void __launch_bounds__(VolGLCfg<NP, KPT, SPLIT, PARA>::NT, VolGLCfg<N
         sW[(2 * NV + v - V0) * D::NP3 + n] = F[v] * M[6] + G[v] * M[7] + H[v] * M[8];
       }
     }
-    __syncthreads();
+    __syncthreads();  // work planes complete; region X (face fluxes) and the T plane are free from here on
+    if (SPLIT && PARA) {
+      // the metric planes of the line partners arrive while the weak-form derivative below runs
+      if (C::BULK) {
+        if (tid == 0) {
+          fence_proxy_async();
+          mbar_expect_tx(mbar, bM);
+          bulk_g2s(sM, gM, bM, mbar);
+        }
+      } else {
+        for (int t = tid; t < 9 * D::NP3; t += NT) sM[t] = gM[t];
+      }
+    }
     // ---- weak-form derivative with D_Hat_T (volint.f90:172-184) ----
     {
       constexpr int V0 = SPLIT ? 1 : 0;
@@ -340,12 +383,13 @@ __global__ void __launch_bounds__(VolGLCfg<NP, KPT, SPLIT, PARA>::NT, VolGLCfg<N
     for (int c = 0; c < KPT; ++c) {
 #pragma unroll
       for (int v = 0; v < 5; ++v) a[c][v] = Pn[c][v];
-      a[c][5] = (STYPE == FLEXI_SPLITDG_PI) ? (Uc[c][ENER] + Pn[c][PRES]) / Pn[c][DENS] : (STYPE == FLEXI_SPLITDG_KG) ? Uc[c][ENER] / Pn[c][DENS] : Uc[c][ENER];
+      a[c][5] = (STYPE == FLEXI_SPLITDG_PI) ? (Uc[c][ENER] + Pn[c][PRES]) * sRho[c] : (STYPE == FLEXI_SPLITDG_KG) ? Uc[c][ENER] * sRho[c] : Uc[c][ENER];
     }
-    if (PARA) __syncthreads();  // every thread is done with the T plane (gradients) before it is overwritten
+    // (with lifting, the barrier after the flux loop already separated the last read of the T plane from this write)
 #pragma unroll
     for (int c = 0; c < KPT; ++c) sP[5 * D::NP3 + ij + D::NP2 * (k0 + c)] = a[c][5];
     __syncthreads();
+    if (PARA && C::BULK) mbar_wait(mbar, 1);
 
     constexpr bool PI = (STYPE == FLEXI_SPLITDG_PI);
     PiAcc acc[KPT];
@@ -363,9 +407,10 @@ __global__ void __launch_bounds__(VolGLCfg<NP, KPT, SPLIT, PARA>::NT, VolGLCfg<N
         const double Ma[3] = {sM[(3 * dir + 0) * D::NP3 + n], sM[(3 * dir + 1) * D::NP3 + n], sM[(3 * dir + 2) * D::NP3 + n]};
 #pragma unroll
         for (int l = 0; l < NP; ++l) {
-          if (l == me) continue;
+          // the self pair is computed and weighted with zero instead of being skipped: a per-lane `continue` would split
+          // the warp into NP paths that never reconverge inside the unrolled loop
           const int nl = base + l * stride;
-          const double dl = dv[l * NP + me];
+          const double dl = (l == me) ? 0. : dv[l * NP + me];
           if (PI) {
             PiPair pr;
             pr.form(a[c], Ma, sP[nl], sP[D::NP3 + nl], sP[2 * D::NP3 + nl], sP[3 * D::NP3 + nl], sP[4 * D::NP3 + nl], sP[5 * D::NP3 + nl],
