@@ -1,0 +1,115 @@
+"""Worker run under torchrun (world_size >= 2) by tests/test_multi_rank.py.
+
+mode "cpu": gloo only -- checks the host-side plumbing of the partitioned path: neighbour tables are symmetric, slice k of my
+            MINE<->nb block pairs with slice k of nb's YOUR<->me block (same master geometry on both ranks), the NCCL-id style
+            byte broadcast works, and the oracle world over the same partition is partition invariant.
+mode "gpu": one GPU per rank -- flexi_gpu with the NCCL side exchange against the oracle world (all ranks emulated in-process)."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from flexi_b200.hostmesh import basis as B  # noqa: E402
+from flexi_b200.hostmesh.case import build_case  # noqa: E402
+from flexi_b200.hostmesh.mesh import BoxSpec  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+
+CURVED = dict(x0=(-1.0, -1.0, -1.0), length=(2.0, 2.0, 2.0), ngeo=2, deform=0.1)
+CASES = {
+    "split": (5, B.NODE_GAUSS_LOBATTO, dict(parabolic=True, split_dg=True, split_dg_type="pi", riemann="lf", mu0=1e-2)),
+    "weakG": (4, B.NODE_GAUSS, dict(parabolic=True, riemann="roe", mu0=1e-2, n_var_lifting=4)),
+    "euler": (3, B.NODE_GAUSS_LOBATTO, dict(parabolic=False, riemann="hllc")),
+}
+
+
+def main():
+    mode, case = sys.argv[1], sys.argv[2]
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if mode == "gpu":
+        torch.cuda.set_device(local)
+        dist.init_process_group("cpu:gloo,cuda:nccl", rank=rank, world_size=world)
+    else:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    N, node, eqn = CASES[case]
+    spec = BoxSpec((4, 3, 2), **CURVED)
+    part = dict(partition="linear") if world != 4 else dict(partition="block", blocks=(2, 2, 1))
+    ranks = build_case(spec, N, node, eqn, nranks=world, **part)  # every rank builds all partitions (tiny mesh) for the oracle world
+    me = ranks[rank]
+    m = me.mesh
+
+    # ---- host plumbing checks (both modes) ----
+    tables = [None] * world
+    mine = dict(nb=m.NbProc.tolist(), nM=m.nMPISides_MINE_Proc.tolist(), nY=m.nMPISides_YOUR_Proc.tolist(),
+                oM=m.offsetMPISides_MINE.tolist(), oY=m.offsetMPISides_YOUR.tolist())
+    dist.all_gather_object(tables, mine)
+    for i, nb in enumerate(mine["nb"]):
+        t = tables[nb]
+        assert rank in t["nb"], "asymmetric neighbour tables"
+        j = t["nb"].index(rank)
+        assert mine["nM"][i] == t["nY"][j] and mine["nY"][i] == t["nM"][j], "message sizes differ"
+        # geometry of my MINE slice must be what the neighbour holds for its YOUR slice (master geometry on both ranks)
+        mb = ranks[nb].mesh
+        a = m.NormVec[mine["oM"][i]:mine["oM"][i] + mine["nM"][i]]
+        b = mb.NormVec[t["oY"][j]:t["oY"][j] + t["nY"][j]]
+        assert np.array_equal(a, b), "MINE/YOUR slices are not paired side by side"
+    idt = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        idt = torch.arange(128, dtype=torch.uint8)
+    dist.broadcast(idt, src=0)
+    assert bytes(idt.numpy().tobytes()) == bytes(range(128))
+
+    # ---- oracle world on this partition vs the single-rank oracle (partition invariance, SURVEY 8c identity 7) ----
+    U0s = [r.eqn.smooth_state(r.mesh.Elem_xGP, length=2.0) for r in ranks]
+    w = O.OracleWorld([(r.desc, r.keep) for r in ranks])
+    w.set_state(U0s)
+    w.dg_time_derivative(0.0)
+    ut_ref = w.ranks[rank].array("Ut").copy()
+    if rank == 0:
+        one = build_case(spec, N, node, eqn)[0]
+        w1 = O.OracleWorld([(one.desc, one.keep)])
+        w1.set_state([one.eqn.smooth_state(one.mesh.Elem_xGP, length=2.0)])
+        w1.dg_time_derivative(0.0)
+        full = w1.ranks[0].array("Ut")
+        for r, ow in zip(ranks, w.ranks):
+            assert np.max(np.abs(ow.array("Ut") - full[r.mesh.elem_gid])) < 1e-12 * np.max(np.abs(full))
+        w1.close()
+
+    if mode == "gpu":
+        from flexi_b200 import gpu as G
+
+        if rank == 0:
+            idt = torch.frombuffer(bytearray(G.nccl_unique_id()), dtype=torch.uint8).clone()
+        dist.broadcast(idt, src=0)
+        me.remake_desc(nccl_id=bytes(idt.numpy().tobytes()), device=local)
+        g = G.FlexiGpu(me)
+        g.set_state(U0s[rank])
+        ut = g.DGTimeDerivative_weakForm(0.0)
+        scale = np.max(np.abs(ut_ref).reshape(-1, 5), axis=0)
+        assert np.all(np.max(np.abs(ut - ut_ref).reshape(-1, 5), axis=0) <= 1e-12 * scale), "multi-rank Ut mismatch"
+        t = 0.0
+        for _ in range(3):
+            dt_o = w.calc_timestep()[0]
+            dt_g = g.CalcTimeStep()[0]
+            assert abs(dt_o - dt_g) <= 1e-13 * dt_o, (dt_o, dt_g)
+            w.timestep(t, dt_o)
+            g.TimeStep(t, dt_o)
+            t += dt_o
+        Ug, Uo = g.get_state(), w.ranks[rank].array("U")
+        sc = np.max(np.abs(Uo).reshape(-1, 5), axis=0)
+        assert np.all(np.max(np.abs(Ug - Uo).reshape(-1, 5), axis=0) <= 1e-12 * sc), "multi-rank state mismatch after 3 steps"
+        g.close()
+    w.close()
+    dist.barrier()
+    if rank == 0:
+        print(f"MULTI_RANK_OK mode={mode} case={case} world={world}")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
