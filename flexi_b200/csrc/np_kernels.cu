@@ -1,4 +1,6 @@
 // np_kernels.cu -- instantiates kernels.cuh for one polynomial degree (compile with -DFLEXI_NP=<N+1>).
+#include <stdlib.h>
+
 #include "np_ops.h"
 #include "volume_gl.cuh"
 
@@ -36,12 +38,32 @@ cudaError_t volume_gl_launch(const VolArgs& a, int nBlocks, cudaStream_t s) {
   return cudaGetLastError();
 }
 
+#if FLEXI_NP == 8
+// tuning hook for the headline configuration (N=7, split PI, Navier-Stokes, nVarLifting=5): FLEXI_GPU_KPT=2 selects a
+// quarter zeta column per thread (256 threads per element) instead of half a column (128 threads)
+int g_kpt_alt = 0;
+cudaError_t alt_setup() {
+  const char* e = getenv("FLEXI_GPU_KPT");
+  g_kpt_alt = e ? atoi(e) : 0;
+  using C = VolGLCfg<NP, 2, true, true>;
+  return cudaFuncSetAttribute(k_volume_gl<NP, 2, true, FLEXI_SPLITDG_PI, true, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::BYTES);
+}
+cudaError_t alt_launch(const VolArgs& a, int nBlocks, cudaStream_t s) {
+  using C = VolGLCfg<NP, 2, true, true>;
+  k_volume_gl<NP, 2, true, FLEXI_SPLITDG_PI, true, 5><<<nBlocks, C::NT, C::BYTES, s>>>(a);
+  return cudaGetLastError();
+}
+#endif
+
 constexpr size_t upd_smem = sizeof(double) * (D::NBASIS + 5 * D::NP3);
 
 #define FX_SPLIT_TYPES(X) X(FLEXI_SPLITDG_SD) X(FLEXI_SPLITDG_DU) X(FLEXI_SPLITDG_KG) X(FLEXI_SPLITDG_PI)
 
 cudaError_t setup() {
   cudaError_t e;
+#if FLEXI_NP == 8
+  if ((e = alt_setup()) != cudaSuccess) return e;
+#endif
   if ((e = volume_setup<false, 5>()) != cudaSuccess) return e;
   if ((e = volume_setup<true, 5>()) != cudaSuccess) return e;
   if ((e = volume_setup<true, 4>()) != cudaSuccess) return e;
@@ -83,6 +105,9 @@ cudaError_t volume(bool gl, bool split, int stype, bool para, int nvl, const Vol
     if (!para) return volume_gl_launch<false, 0, false, 5>(a, nBlocks, s);
     return nvl == 5 ? volume_gl_launch<false, 0, true, 5>(a, nBlocks, s) : volume_gl_launch<false, 0, true, 4>(a, nBlocks, s);
   }
+#if FLEXI_NP == 8
+  if (g_kpt_alt == 2 && stype == FLEXI_SPLITDG_PI && para && nvl == 5) return alt_launch(a, nBlocks, s);
+#endif
   switch (stype) {
 #define X(T)                                                                                                     \
   case T:                                                                                                        \

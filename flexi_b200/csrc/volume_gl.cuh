@@ -51,23 +51,30 @@ struct VolGLCfg {
   static constexpr int NT = D::NP2 * KB;
   static constexpr bool BULK = (NP % 2 == 0);  // plane bytes must be a multiple of 16 for cp.async.bulk
   static constexpr int P_PLANES = 6;
-  // region X: first the staged lifting fluxes of the six faces (8 values per face node), later the 9 metric planes the
-  // two-point fluxes read from their line partners
-  static constexpr int X_FACE = PARA ? 6 * 8 * D::NP2 : 0;
+  // region X: first the six faces' neighbour traces + face geometry (9 values per face node, prefetched with cp.async and
+  // turned into lifting fluxes in place), later the 9 metric planes the two-point fluxes read from their line partners
+  static constexpr int X_FACE = PARA ? 6 * 9 * D::NP2 : 0;
   static constexpr int X_MET = SPLIT ? 9 * D::NP3 : 0;
   static constexpr int X_DOUBLES = ((X_FACE > X_MET ? X_FACE : X_MET) + 1) & ~1;
   static constexpr int W_PLANES = PARA ? (SPLIT ? 12 : 15) : (SPLIT ? 0 : 15);
   static constexpr int O_BASIS = 2;  // [0] = mbarrier
   static constexpr int NB = (D::NBASIS + 1) & ~1;
-  static constexpr int O_P = O_BASIS + NB;
+  static constexpr int O_FDST = O_BASIS + NB;  // int table [6][NP2]: where a boundary node's gradient trace goes
+  static constexpr int NFD = PARA ? ((3 * D::NP2 + 1) & ~1) : 0;
+  static constexpr int O_P = O_FDST + NFD;
   static constexpr int O_X = O_P + P_PLANES * D::NP3;
   static constexpr int O_W = O_X + X_DOUBLES;
   static constexpr int DOUBLES = O_W + W_PLANES * D::NP3;
   static constexpr size_t BYTES = sizeof(double) * DOUBLES;
-  static constexpr int MINB = (NT <= 256 && BYTES <= 113000) ? 2 : 1;  // two elements per SM when registers and smem allow
+  static constexpr int MINB = (NT <= 256 && BYTES <= 115000) ? 2 : 1;  // two elements per SM when registers and smem allow
 };
 
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // raw two-point quantities of the Pirozzoli flux between nodes a and b with summed metrics m = Ma + Mb:
 //   contravariant flux (splitflux.f90:603-666 contracted with 0.5*(Ma+Mb)):
@@ -135,6 +142,7 @@ __global__ void __launch_bounds__(VolGLCfg<NP, KPT, SPLIT, PARA>::NT, VolGLCfg<N
   uint64_t* mbar = reinterpret_cast<uint64_t*>(sm);
   double* sB = sm + C::O_BASIS;
   double* sP = sm + C::O_P;  // rho,u,v,w,p, T (later H / rhoE / E for the split fluxes)
+  int* sFD = reinterpret_cast<int*>(sm + C::O_FDST);
   double* sX = sm + C::O_X;  // lifting fluxes of the faces, then the metric planes
   double* sM = sX;
   double* sW = sm + C::O_W;
@@ -149,15 +157,20 @@ __global__ void __launch_bounds__(VolGLCfg<NP, KPT, SPLIT, PARA>::NT, VolGLCfg<N
   const double* gM = A.m.Met + (size_t)e * 9 * D::NP3;
   constexpr uint32_t bU = 5 * D::NP3 * 8, bM = 9 * D::NP3 * 8;
   constexpr bool MET_EARLY = SPLIT && !PARA;  // without lifting region X is free from the start
+  // own-node metrics of the lifting / flux loop: staged into the first 9 work planes; each node's slot is consumed by its
+  // owner right before the owner overwrites it with the node's contravariant fluxes
+  constexpr bool MET_WORK = (PARA || !SPLIT) && C::BULK;
+  constexpr int FACE_IT = (6 * D::NP2 + NT - 1) / NT;
 
   // ---- stage the element: one TMA bulk copy for the 5 conservative planes (+ the 9 metric planes) ------------------------
   if (C::BULK) {
     if (tid == 0) mbar_init(mbar, 1);
     __syncthreads();
     if (tid == 0) {
-      mbar_expect_tx(mbar, bU + (MET_EARLY ? bM : 0));
+      mbar_expect_tx(mbar, bU + ((MET_EARLY || MET_WORK) ? bM : 0));
       bulk_g2s(sP, gU, bU, mbar);
       if (MET_EARLY) bulk_g2s(sM, gM, bM, mbar);
+      if (MET_WORK) bulk_g2s(sW, gM, bM, mbar);
     }
   } else {
     for (int t = tid; t < 5 * D::NP3; t += NT) sP[t] = gU[t];
@@ -165,6 +178,40 @@ __global__ void __launch_bounds__(VolGLCfg<NP, KPT, SPLIT, PARA>::NT, VolGLCfg<N
       for (int t = tid; t < 9 * D::NP3; t += NT) sM[t] = gM[t];
   }
   load_basis<NP>(sB, A.m.basis, tid, NT);
+  // neighbour traces + face geometry of the six sides: cp.async into region X at the face node's volume-face slot, in flight
+  // while the element itself is being staged
+  int faceSlot[FACE_IT];
+  double faceSgn[FACE_IT];
+  if (PARA) {
+#pragma unroll
+    for (int it = 0; it < FACE_IT; ++it) {
+      const int t = tid + it * NT;
+      faceSlot[it] = -1;
+      faceSgn[it] = 0.;
+      if (t < 6 * D::NP2) {
+        const int ls = t / D::NP2 + 1, pq = t % D::NP2;
+        const SideRef sr = A.m.e2s[e * 6 + ls - 1];
+        const int ab = A.m.s2v2[(sr.flip * 6 + ls - 1) * D::NP2 + pq];
+        const double* nbTrace = ((sr.flip == 0) ? A.U_slave : A.U_master) + (size_t)sr.side * 5 * D::NP2 + pq;
+        const double* g = A.m.Geo + (size_t)sr.side * 10 * D::NP2 + pq;
+        double* o = sX + (ls - 1) * 9 * D::NP2 + ab;
+#pragma unroll
+        for (int v = 0; v < 5; ++v) cp_async8(o + v * D::NP2, nbTrace + v * D::NP2);
+        cp_async8(o + 5 * D::NP2, g);
+        cp_async8(o + 6 * D::NP2, g + D::NP2);
+        cp_async8(o + 7 * D::NP2, g + 2 * D::NP2);
+        cp_async8(o + 8 * D::NP2, g + 9 * D::NP2);
+        faceSlot[it] = (ls - 1) * 9 * D::NP2 + ab;
+        // destination of this face node's gradient trace: (side*NVL*NP2 + pq), sign bit set for the slave arrays
+        sFD[(ls - 1) * D::NP2 + ab] = (sr.side * NVL * D::NP2 + pq) | (sr.flip == 0 ? 0 : (int)0x80000000);
+        int base, stride;
+        face_line<NP>(ls, ab % NP, ab / NP, base, stride);
+        faceSgn[it] = (sr.flip == 0) ? 1. : -1.;
+        faceSlot[it] |= (base + (is_minus_side(ls) ? 0 : N * stride)) << 16;  // volume node of this face node
+      }
+    }
+    cp_async_commit();
+  }
   double sJ[KPT];
 #pragma unroll
   for (int c = 0; c < KPT; ++c) sJ[c] = A.m.sJ[(size_t)e * D::NP3 + ij + D::NP2 * (k0 + c)];
@@ -194,31 +241,24 @@ __global__ void __launch_bounds__(VolGLCfg<NP, KPT, SPLIT, PARA>::NT, VolGLCfg<N
 
   if (PARA) {
     // ---- lifting flux of the six faces, all lanes busy (lifting_fillflux.t90:81-107, strong form):
-    //      0.5*(UPrim_slave-UPrim_master)*SurfElem per lifting variable, plus the normal, in volume-face coordinates ----
-    for (int t = tid; t < 6 * D::NP2; t += NT) {
-      const int ls = t / D::NP2 + 1, pq = t % D::NP2;
-      const SideRef sr = A.m.e2s[e * 6 + ls - 1];
-      const int ab = A.m.s2v2[(sr.flip * 6 + ls - 1) * D::NP2 + pq];
-      int base, stride;
-      face_line<NP>(ls, ab % NP, ab / NP, base, stride);
-      const int nF = base + (is_minus_side(ls) ? 0 : N * stride);
-      const double* nbTrace = (sr.flip == 0) ? A.U_slave : A.U_master;
-      double Un[5], Pb[6];
+    //      0.5*(UPrim_slave-UPrim_master)*SurfElem per lifting variable, in place of the prefetched neighbour trace ----
+    cp_async_wait_all();
 #pragma unroll
-      for (int v = 0; v < 5; ++v) Un[v] = nbTrace[((size_t)sr.side * 5 + v) * D::NP2 + pq];
-      const double* g = A.m.Geo + (size_t)sr.side * 10 * D::NP2 + pq;
-      const double n0 = g[0], n1 = g[D::NP2], n2 = g[2 * D::NP2], surf = g[9 * D::NP2];
-      cons_to_prim(q, Un, Pb);
-      const double sgn = (sr.flip == 0) ? 1. : -1.;
-      double* o = sX + (ls - 1) * 8 * D::NP2 + ab;
+    for (int it = 0; it < FACE_IT; ++it) {
+      if (faceSlot[it] >= 0) {
+        double* o = sX + (faceSlot[it] & 0xffff);
+        const int nF = faceSlot[it] >> 16;
+        double Un[5], Pb[6];
 #pragma unroll
-      for (int v = 0; v < NVL; ++v) {
-        const int pv = lift_prim(NVL, v);
-        o[v * D::NP2] = 0.5 * (sgn * (Pb[pv] - sP[pv * D::NP3 + nF])) * surf;
+        for (int v = 0; v < 5; ++v) Un[v] = o[v * D::NP2];
+        const double surf = o[8 * D::NP2];
+        cons_to_prim(q, Un, Pb);
+#pragma unroll
+        for (int v = 0; v < NVL; ++v) {
+          const int pv = lift_prim(NVL, v);
+          o[v * D::NP2] = 0.5 * (faceSgn[it] * (Pb[pv] - sP[pv * D::NP3 + nF])) * surf;
+        }
       }
-      o[5 * D::NP2] = n0;
-      o[6 * D::NP2] = n1;
-      o[7 * D::NP2] = n2;
     }
     __syncthreads();
   }
@@ -230,7 +270,7 @@ __global__ void __launch_bounds__(VolGLCfg<NP, KPT, SPLIT, PARA>::NT, VolGLCfg<N
       const int k = k0 + c, n = ij + D::NP2 * k;
       double M[9];
 #pragma unroll
-      for (int m = 0; m < 9; ++m) M[m] = MET_EARLY ? sM[m * D::NP3 + n] : gM[m * D::NP3 + n];
+      for (int m = 0; m < 9; ++m) M[m] = MET_EARLY ? sM[m * D::NP3 + n] : MET_WORK ? sW[m * D::NP3 + n] : gM[m * D::NP3 + n];
       double F[5] = {0., 0., 0., 0., 0.}, G[5] = {0., 0., 0., 0., 0.}, H[5] = {0., 0., 0., 0., 0.};
       if (PARA) {
         // ---- lifting, volume part (lifting_volint.t90:26-118) ----
@@ -266,7 +306,7 @@ __global__ void __launch_bounds__(VolGLCfg<NP, KPT, SPLIT, PARA>::NT, VolGLCfg<N
 #pragma unroll
         for (int ls = 1; ls <= 6; ++ls) {
           if (onFace[ls - 1]) {
-            const double* o = sX + (ls - 1) * 8 * D::NP2 + abFace[ls - 1];
+            const double* o = sX + (ls - 1) * 9 * D::NP2 + abFace[ls - 1];
             const double n0 = o[5 * D::NP2], n1 = o[6 * D::NP2], n2 = o[7 * D::NP2];
             const double lh = is_minus_side(ls) ? sB[D::O_LHM] : sB[D::O_LHP + N];
 #pragma unroll
@@ -296,14 +336,15 @@ __global__ void __launch_bounds__(VolGLCfg<NP, KPT, SPLIT, PARA>::NT, VolGLCfg<N
 #pragma unroll
         for (int ls = 1; ls <= 6; ++ls) {
           if (onFace[ls - 1]) {
-            const SideRef sr = A.m.e2s[e * 6 + ls - 1];
-            const int pq = A.m.v2s[(sr.flip * 6 + ls - 1) * D::NP2 + abFace[ls - 1]];
-            double* const d0 = (sr.flip == 0) ? A.gm[0] : A.gs[0];
-            double* const d1 = (sr.flip == 0) ? A.gm[1] : A.gs[1];
-            double* const d2 = (sr.flip == 0) ? A.gm[2] : A.gs[2];
+            const int fd = sFD[(ls - 1) * D::NP2 + abFace[ls - 1]];
+            const bool master = fd >= 0;
+            double* const d0 = master ? A.gm[0] : A.gs[0];
+            double* const d1 = master ? A.gm[1] : A.gs[1];
+            double* const d2 = master ? A.gm[2] : A.gs[2];
+            const size_t o0 = (size_t)(fd & 0x7fffffff);
 #pragma unroll
             for (int v = 0; v < NVL; ++v) {
-              const size_t o = ((size_t)sr.side * NVL + v) * D::NP2 + pq;
+              const size_t o = o0 + (size_t)v * D::NP2;
               d0[o] = gx[v];
               d1[o] = gy[v];
               d2[o] = gz[v];
