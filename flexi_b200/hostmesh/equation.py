@@ -46,7 +46,9 @@ class Equation:
 
     def __init__(self, N, node_type, *, parabolic=True, split_dg=False, split_dg_type="pi", riemann="roeentropyfix",
                  riemann_bc="same", lifting=1, n_var_lifting=5, kappa=1.4, R=287.058, Pr=0.72, mu0=0.0,
-                 time_disc="carpenterrk4-5", cfl_scale=0.9, dfl_scale=0.9, eta_br2=2.0, eta_br2_wall=-1.0):
+                 time_disc="carpenterrk4-5", cfl_scale=0.9, dfl_scale=0.9, eta_br2=2.0, eta_br2_wall=-1.0,
+                 boundary_type=(), ref_state_prim=(), ini_ref_state=1, ini_exact_func=0, do_calc_source=False,
+                 ini_amplitude=0.1, ini_frequency=1.0, adv_vel=(0.0, 0.0, 0.0)):
         self.N = N
         self.node_type = node_type.lower()
         self.parabolic = parabolic
@@ -58,13 +60,14 @@ class Equation:
         self.n_var_lifting = n_var_lifting
         self.kappa, self.R, self.Pr, self.mu0 = float(kappa), float(R), float(Pr), float(mu0)
         self.eta_br2, self.eta_br2_wall = eta_br2, eta_br2_wall
-        self.boundary_type = []      # rows (BC_TYPE, BC_STATE, BC_ALPHA)
-        self.ref_state_prim = []     # rows (rho,u,v,w,p,T)
-        self.do_calc_source = False
-        self.ini_exact_func = 0
-        self.ini_amplitude, self.ini_frequency = 0.1, 1.0
-        self.adv_vel = (0.0, 0.0, 0.0)
-        self.ini_ref_state_prim = (1.0, 0.0, 0.0, 0.0, 1.0, 1.0)
+        self.boundary_type = [tuple(b) for b in boundary_type]   # rows (BC_TYPE, BC_STATE, BC_ALPHA)
+        # RefState rows are given like in the ini file as (rho,u,v,w,p); T follows from the ideal gas law (equation.f90:121-133)
+        self.ref_state_prim = [tuple(r[:5]) + (r[4] / (r[0] * self.R),) for r in ref_state_prim]
+        self.do_calc_source = bool(do_calc_source)
+        self.ini_exact_func = int(ini_exact_func)
+        self.ini_amplitude, self.ini_frequency = float(ini_amplitude), float(ini_frequency)
+        self.adv_vel = tuple(adv_vel)
+        self.ini_ref_state_prim = self.ref_state_prim[ini_ref_state - 1] if self.ref_state_prim else (1.0, 0.0, 0.0, 0.0, 1.0, 1.0 / self.R)
         tab = RK_TABLES[time_disc]
         self.RKA, self.RKb, self.RKc = np.array(tab["RKA"]), np.array(tab["RKb"]), np.array(tab["RKc"])
         # FillCFL_DFL, timedisc_func.f90:491-519
@@ -111,6 +114,20 @@ class Equation:
             prim[..., 5] = T0
             prim[..., 0] = prim[..., 4] / (prim[..., 5] * self.R)
         return self.prim_to_cons(prim)
+
+    def exact_func4(self, x, t=0.0):
+        """ExactFunc case 4, oblique sine wave (exactfunc.f90:332-362)."""
+        omega, a = np.pi * self.ini_frequency, self.adv_vel[0] * 2.0 * np.pi
+        r = 2.0 + self.ini_amplitude * np.sin(omega * np.sum(x, axis=-1) - a * t)
+        cons = np.empty(x.shape[:-1] + (5,))
+        cons[..., 0:4] = r[..., None]
+        cons[..., 4] = r * r
+        return cons
+
+    def const_state(self, shape, prim):
+        p = np.zeros(tuple(shape) + (6,))
+        p[...] = tuple(prim[:5]) + (prim[4] / (prim[0] * self.R),)
+        return self.prim_to_cons(p)
 
     def random_state(self, shape, seed=1234):
         """Random-field stress state: rho,p in [0.5,1.5], v in [-0.5,0.5]^3."""

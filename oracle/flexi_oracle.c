@@ -917,10 +917,204 @@ static void volint_split_form(oracle* o) {
 }
 #undef F3
 
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* exact functions, boundary states and boundary fluxes: idealgas/exactfunc.f90, idealgas/getboundaryflux.f90         */
+/* ------------------------------------------------------------------------------------------------------------------ */
+#define BTYPE(ibc, c) o->d.BoundaryType[(size_t)(c)*o->d.nBCs + ((ibc)-1)] /* Fortran BoundaryType(ibc, c+1): c=0 BC_TYPE, 1 BC_STATE */
+
+/* exactfunc.f90:225-362 ExactFunc; cases on the hot path: 1 (constant RefState), 4 (oblique sine wave) */
+static void exact_func(const oracle* o, int func, double t, const double* x, double* cons) {
+  switch (func) {
+    case 1: prim_to_cons(o, o->d.iniRefStatePrim, cons); break;
+    case 4: {
+      const double Omega = M_PI * o->d.iniFrequency, a = o->d.advVel[0] * 2. * M_PI;
+      const double r = 2. + o->d.iniAmplitude * sin(Omega * (x[0] + x[1] + x[2]) - a * t);
+      cons[DENS] = cons[MOM1] = cons[MOM2] = cons[MOM3] = r;
+      cons[ENER] = cons[DENS] * cons[DENS];
+    } break;
+    default:
+      fprintf(stderr, "oracle: ExactFunc %d not restated\n", func);
+      abort();
+  }
+}
+
+/* eos.f90:561-583 PRESSURE_RIEMANN (state in the face-normal system) */
+static double pressure_riemann(const oracle* o, const double* P) {
+  const double kappa = o->d.kappa, kappaFac = 2. * kappa * o->sKappaM1, sKappaP1 = 1. / (kappa + 1.);
+  if (P[VEL1] <= 0.) return P[PRES] * pow(fmax(0.0001, (1. + 0.5 * o->kappaM1 * P[VEL1] / sqrt(kappa * P[PRES] / P[DENS]))), kappaFac);
+  const double ar = 2. * sKappaP1 / P[DENS], br = o->kappaM1 * sKappaP1 * P[PRES];
+  return P[PRES] + P[VEL1] / ar * 0.5 * (P[VEL1] + sqrt(P[VEL1] * P[VEL1] + 4. * ar * (P[PRES] + br)));
+}
+
+/* getboundaryflux.f90:224-470 GetBoundaryState for one face node; types 2 (Dirichlet), 3/4 (no-slip walls), 9 (slip wall) */
+static void get_boundary_state(const oracle* o, int SideID, double t, const double* Pm, const double* nv, const double* t1,
+                               const double* t2, const double* xf, double* Pb) {
+  const int ibc = o->d.BC[SideID - 1], BCType = BTYPE(ibc, 0), BCState = BTYPE(ibc, 1);
+  switch (BCType) {
+    case 2:
+      if (BCState == 0) {
+        double cons[5];
+        exact_func(o, o->d.iniExactFunc, t, xf, cons);
+        cons_to_prim(o, Pb, cons);
+      } else {
+        for (int v = 0; v < 6; ++v) Pb[v] = o->d.RefStatePrim[(size_t)(BCState - 1) * 6 + v];
+      }
+      break;
+    case 3: case 4: case 9: {
+      Pb[DENS] = Pm[DENS];
+      Pb[VEL1] = Pm[VEL1] * nv[0] + Pm[VEL2] * nv[1] + Pm[VEL3] * nv[2];
+      Pb[VEL2] = Pm[VEL1] * t1[0] + Pm[VEL2] * t1[1] + Pm[VEL3] * t1[2];
+      Pb[VEL3] = Pm[VEL1] * t2[0] + Pm[VEL2] * t2[1] + Pm[VEL3] * t2[2];
+      Pb[PRES] = Pm[PRES];
+      Pb[TEMP] = Pm[TEMP];
+      if (BCType == 3) {
+        Pb[PRES] = pressure_riemann(o, Pb);
+        Pb[VEL1] = Pb[VEL2] = Pb[VEL3] = 0.;
+        Pb[TEMP] = Pm[TEMP];
+        Pb[DENS] = Pb[PRES] / (Pb[TEMP] * o->d.R);
+      } else if (BCType == 4) {
+        Pb[PRES] = pressure_riemann(o, Pb);
+        Pb[VEL1] = Pb[VEL2] = Pb[VEL3] = 0.;
+        Pb[TEMP] = o->d.RefStatePrim[(size_t)(BCState - 1) * 6 + TEMP];
+        Pb[DENS] = Pb[PRES] / (Pb[TEMP] * o->d.R);
+      } else {
+        Pb[PRES] = pressure_riemann(o, Pb);
+        Pb[VEL1] = 0.;
+        Pb[DENS] = Pm[DENS];
+        Pb[TEMP] = Pb[PRES] / (Pb[DENS] * o->d.R);
+      }
+      const double vn = Pb[VEL1], vt1 = Pb[VEL2], vt2 = Pb[VEL3];
+      for (int c = 0; c < 3; ++c) Pb[VEL1 + c] = vn * nv[c] + vt1 * t1[c] + vt2 * t2[c];
+    } break;
+    default:
+      fprintf(stderr, "oracle: boundary type %d not restated\n", BCType);
+      abort();
+  }
+}
+
+/* getboundaryflux.f90:480-790 GetBoundaryFlux for all BC sides (before the SurfElem scaling of fillflux.f90:179-186) */
+static void fill_flux_bc(oracle* o, double t) {
+  const int np = o->np, nvl = o->nvl;
+  const int solver = (o->d.riemannBC == FLEXI_RIEMANN_SAME) ? o->d.riemann : o->d.riemannBC;
+  for (int SideID = 1; SideID <= o->d.nBCSides; ++SideID) {
+    const int s = SideID - 1;
+    const int BCType = BTYPE(o->d.BC[s], 0);
+    for (int q = 0; q < np; ++q)
+      for (int p = 0; p < np; ++p) {
+        const double* Pm = &SID(o->UPrim_master, NPRIM, 0, p, q, s);
+        const double* nv = &SID(o->d.NormVec, 3, 0, p, q, s);
+        const double* t1 = &SID(o->d.TangVec1, 3, 0, p, q, s);
+        const double* t2 = &SID(o->d.TangVec2, 3, 0, p, q, s);
+        const double* xf = o->d.Face_xGP ? &SID(o->d.Face_xGP, 3, 0, p, q, s) : NULL;
+        double Pb[6], F[5];
+        get_boundary_state(o, SideID, t, Pm, nv, t1, t2, xf, Pb);
+        if (BCType == 2) {
+          double Ucm[5], Ucb[5];
+          prim_to_cons(o, Pm, Ucm);
+          prim_to_cons(o, Pb, Ucb);
+          riemann_point(o, solver, F, Ucm, Ucb, Pm, Pb, nv, t1, t2);
+          if (o->d.parabolic) {
+            double Fv[5];
+            const double *gx = &SID(o->gradUx_master, nvl, 0, p, q, s), *gy = &SID(o->gradUy_master, nvl, 0, p, q, s),
+                         *gz = &SID(o->gradUz_master, nvl, 0, p, q, s);
+            viscous_flux_point(o, Fv, Pm, Pb, gx, gy, gz, gx, gy, gz, nv);
+            for (int v = 0; v < 5; ++v) F[v] = F[v] + Fv[v];
+          }
+        } else { /* walls 3,4,9 */
+          F[DENS] = 0.;
+          for (int c = 0; c < 3; ++c) F[MOM1 + c] = Pb[PRES] * nv[c];
+          F[ENER] = 0.;
+          if (o->d.parabolic) {
+            double f[5], g[5], h[5], gxl[5], gyl[5], gzl[5];
+            const double *gx = &SID(o->gradUx_master, nvl, 0, p, q, s), *gy = &SID(o->gradUy_master, nvl, 0, p, q, s),
+                         *gz = &SID(o->gradUz_master, nvl, 0, p, q, s);
+            if (BCType == 9) { /* BCGradMat = I - n n^T */
+              const double B11 = 1. - nv[0] * nv[0], B22 = 1. - nv[1] * nv[1], B33 = 1. - nv[2] * nv[2];
+              const double B12 = -nv[0] * nv[1], B13 = -nv[0] * nv[2], B32 = -nv[2] * nv[1];
+              for (int v = 0; v < nvl; ++v) {
+                gxl[v] = B11 * gx[v] + B12 * gy[v] + B13 * gz[v];
+                gyl[v] = B12 * gx[v] + B22 * gy[v] + B32 * gz[v];
+                gzl[v] = B13 * gx[v] + B32 * gy[v] + B33 * gz[v];
+              }
+              gx = gxl; gy = gyl; gz = gzl;
+            }
+            eval_diff_flux3d(o, Pb, gx, gy, gz, f, g, h);
+            if (BCType == 3) f[ENER] = g[ENER] = h[ENER] = 0.;
+            for (int v = 1; v < 5; ++v) F[v] = F[v] + nv[0] * f[v] + nv[1] * g[v] + nv[2] * h[v];
+          }
+        }
+        for (int v = 0; v < 5; ++v) SID(o->Flux_master, NVAR, v, p, q, s) = F[v];
+      }
+  }
+}
+
+/* getboundaryflux.f90:855-940 Lifting_GetBoundaryFlux (strong form) into Flux (dir=0) or FluxX/Y/Z (lifting_fillflux.t90:137-186) */
+static void lifting_fill_flux_bc(oracle* o, double t, double* Flux, double* FluxX, double* FluxY, double* FluxZ) {
+  const int np = o->np, nvl = o->nvl;
+  for (int SideID = 1; SideID <= o->d.nBCSides; ++SideID) {
+    const int s = SideID - 1;
+    const int BCType = BTYPE(o->d.BC[s], 0);
+    for (int q = 0; q < np; ++q)
+      for (int p = 0; p < np; ++p) {
+        const double* Pm = &SID(o->UPrim_master, NPRIM, 0, p, q, s);
+        const double* nv = &SID(o->d.NormVec, 3, 0, p, q, s);
+        const double* xf = o->d.Face_xGP ? &SID(o->d.Face_xGP, 3, 0, p, q, s) : NULL;
+        double Pb[6], Fl[5];
+        get_boundary_state(o, SideID, t, Pm, nv, &SID(o->d.TangVec1, 3, 0, p, q, s), &SID(o->d.TangVec2, 3, 0, p, q, s), xf, Pb);
+        for (int v = 0; v < nvl; ++v) {
+          const int pv = o->lift_map[v];
+          if (BCType == 2)
+            Fl[v] = 0.5 * (Pm[pv] + Pb[pv]);
+          else if (BCType == 3 || BCType == 4)
+            Fl[v] = (pv == DENS) ? Pb[DENS] : (pv == TEMP) ? Pb[TEMP] : 0.;
+          else
+            Fl[v] = (pv == DENS) ? Pm[DENS] : (pv == TEMP) ? Pm[TEMP] : Pb[pv];
+          Fl[v] = Fl[v] - Pm[pv];
+          Fl[v] = Fl[v] * o->d.SurfElem[((size_t)s * np + q) * np + p];
+          if (Flux) SID(Flux, nvl, v, p, q, s) = Fl[v];
+          if (FluxX) {
+            SID(FluxX, nvl, v, p, q, s) = Fl[v] * nv[0];
+            SID(FluxY, nvl, v, p, q, s) = Fl[v] * nv[1];
+            SID(FluxZ, nvl, v, p, q, s) = Fl[v] * nv[2];
+          }
+        }
+      }
+  }
+}
+
+/* exactfunc.f90:727-815 CalcSource, case 4 (manufactured solution of the oblique sine wave): Ut += src/sJ */
+static void calc_source(oracle* o, double t) {
+  if (o->d.iniExactFunc != 4) {
+    fprintf(stderr, "oracle: CalcSource for IniExactFunc %d not restated\n", o->d.iniExactFunc);
+    abort();
+  }
+  const double kappa = o->d.kappa, Amplitude = o->d.iniAmplitude, Omega = M_PI * o->d.iniFrequency, a = o->d.advVel[0] * 2. * M_PI;
+  double tmp[6];
+  tmp[0] = -a + 3. * Omega;
+  tmp[1] = -a + 0.5 * Omega * (1. + kappa * 5.);
+  tmp[2] = Amplitude * Omega * o->kappaM1;
+  tmp[3] = 0.5 * ((9. + kappa * 15.) * Omega - 8. * a);
+  tmp[4] = Amplitude * (3. * Omega * kappa - a);
+  tmp[5] = o->d.parabolic ? 3. * o->d.mu0 * kappa * Omega * Omega / o->d.Pr : 0.;
+  for (int i = 0; i < 6; ++i) tmp[i] = tmp[i] * Amplitude;
+  const double at = a * t;
+  const size_t n = (size_t)o->d.nElems * o->np * o->np * o->np;
+  for (size_t i = 0; i < n; ++i) {
+    const double* x = o->d.Elem_xGP + 3 * i;
+    const double arg = Omega * (x[0] + x[1] + x[2]) - at;
+    const double cosX = cos(arg), sinX = sin(arg), sinX2 = 2. * sinX * cosX;
+    double src[5];
+    src[DENS] = tmp[0] * cosX;
+    src[MOM1] = src[MOM2] = src[MOM3] = tmp[1] * cosX + tmp[2] * sinX2;
+    src[ENER] = tmp[3] * cosX + tmp[4] * sinX2 + tmp[5] * sinX;
+    for (int v = 0; v < 5; ++v) o->Ut[i * 5 + v] = o->Ut[i * 5 + v] + src[v] / o->d.sJ[i];
+  }
+}
+
 /* ------------------------------------------------------------------------------------------------------------------ */
 /* FillFlux: dg/fillflux.f90:40-215 (inner and MPI_MINE sides; BC sides handled in fill_flux_bc)                      */
 /* ------------------------------------------------------------------------------------------------------------------ */
-static void fill_flux_bc(oracle* o, double t); /* getboundaryflux restatement, below */
 
 static void fill_flux(oracle* o, double t, int doMPISides) {
   const int np = o->np, nvl = o->nvl;
@@ -968,25 +1162,14 @@ static void fill_flux(oracle* o, double t, int doMPISides) {
   }
 }
 
-static void fill_flux_bc(oracle* o, double t) {
-  (void)t;
-  if (o->d.nBCSides > 0) {
-    fprintf(stderr, "oracle: boundary conditions are not restated yet\n");
-    abort();
-  }
-}
 
 /* ------------------------------------------------------------------------------------------------------------------ */
 /* source term / sign / Jacobian: dg.f90:656-676                                                                      */
 /* ------------------------------------------------------------------------------------------------------------------ */
 static void finish_ut(oracle* o, double t) {
-  (void)t;
   const size_t n = (size_t)o->d.nElems * o->np * o->np * o->np;
   for (size_t i = 0; i < n * NVAR; ++i) o->Ut[i] = -o->Ut[i];
-  if (o->d.doCalcSource) {
-    fprintf(stderr, "oracle: CalcSource not restated yet\n");
-    abort();
-  }
+  if (o->d.doCalcSource) calc_source(o, t);
   apply_jacobian(o, NVAR, o->Ut);
 }
 
@@ -1040,7 +1223,6 @@ static void exchange(oracle_world* w, size_t member_off, int dataSizeSide, int S
 
 /* lifting_br1.t90:48-181 Lifting_BR1 (strong, non-conservative) */
 static void lifting_br1_world(oracle_world* w, double t) {
-  (void)t;
   const int np = w->r[0]->np, nvl = w->r[0]->nvl;
   const int szg = nvl * np * np;
   FOR_RANKS lifting_fill_flux(w->r[r], 0, w->r[r]->gradUz_slave, 1);
@@ -1048,7 +1230,7 @@ static void lifting_br1_world(oracle_world* w, double t) {
   FOR_RANKS {
     oracle* o = w->r[r];
     lifting_volint_nonconservative(o);
-    /* Lifting_FillFlux_BC: no BC sides restated yet */
+    lifting_fill_flux_bc(o, t, o->gradUz_slave, NULL, NULL, NULL);
     lifting_fill_flux(o, 0, o->gradUz_slave, 0);
     lifting_fill_flux_normvec(o, o->gradUz_slave, o->gradUx_master, o->gradUy_master, o->gradUz_master, 0);
     surf_int(o, nvl, o->gradUx_master, o->gradUx_master, o->gradUx, 0, o->d.L_HatMinus, o->d.L_HatPlus, 1.);
@@ -1076,6 +1258,95 @@ static void lifting_br1_world(oracle_world* w, double t) {
   }
 }
 
+
+/* lifting_br2.t90:194-311 Lifting_SurfInt_BR2 for one gradient direction */
+static void lifting_surf_int_br2(oracle* o, const double* Flux, double* gradU, double* gradU_master, double* gradU_slave, int doMPISides) {
+  const int np = o->np, N = np - 1, nvl = o->nvl;
+  const int gl = (o->d.nodeType == FLEXI_NODETYPE_GAUSS_LOBATTO);
+  const int lmax = gl ? 0 : N;
+  for (int pass = 0; pass < 2; ++pass) { /* 0: slave sides, 1: master sides */
+    int firstSideID, lastSideID;
+    if (pass == 0) {
+      firstSideID = doMPISides ? o->firstMPISide_YOUR : o->firstInnerSide;
+      lastSideID = doMPISides ? o->lastMPISide_YOUR : o->lastInnerSide;
+    } else {
+      if (doMPISides) continue; /* only mortar MPI sides: none */
+      firstSideID = o->firstBCSide;
+      lastSideID = o->lastMPISide_MINE;
+    }
+    for (int SideID = firstSideID; SideID <= lastSideID; ++SideID) {
+      const int s = SideID - 1;
+      double eta = o->d.etaBR2;
+      if (pass == 1 && SideID <= o->d.nBCSides) {
+        const int bt = BTYPE(o->d.BC[s], 0);
+        if (bt == 3 || bt == 4) eta = o->d.etaBR2_wall;
+      }
+      const int ElemID = (pass == 0) ? S2E(1, s) : S2E(0, s);
+      if (ElemID <= 0) continue;
+      const int locSide = (pass == 0) ? S2E(3, s) : S2E(2, s);
+      const int flip = (pass == 0) ? S2E(4, s) : 0;
+      double* gface = (pass == 0) ? gradU_slave : gradU_master;
+      const int minus = (locSide == XI_MINUS || locSide == ETA_MINUS || locSide == ZETA_MINUS);
+      for (int q = 0; q < np; ++q)
+        for (int p = 0; p < np; ++p) {
+          const int a = S2V2(0, p, q, flip, locSide), b = S2V2(1, p, q, flip, locSide);
+          for (int l = 0; l <= lmax; ++l) {
+            const int d = minus ? l : N - l; /* S2V(:,l,p,q,flip,locSide), mappings.f90:336-387 */
+            int i, j, k;
+            if (locSide == XI_MINUS || locSide == XI_PLUS) { i = d; j = a; k = b; }
+            else if (locSide == ETA_MINUS || locSide == ETA_PLUS) { i = a; j = d; k = b; }
+            else { i = a; j = b; k = d; }
+            const double sJ = o->d.sJ[(((size_t)(ElemID - 1) * np + k) * np + j) * np + i];
+            for (int v = 0; v < nvl; ++v) {
+              const double F_loc = sJ * SID(Flux, nvl, v, p, q, s) * o->d.L_HatMinus[l];
+              VOL(gradU, nvl, v, i, j, k, ElemID - 1) = VOL(gradU, nvl, v, i, j, k, ElemID - 1) + F_loc;
+              SID(gface, nvl, v, p, q, s) = SID(gface, nvl, v, p, q, s) + eta * o->d.L_Minus[l] * F_loc;
+            }
+          }
+        }
+    }
+  }
+}
+
+/* lifting_br2.t90:44-185 Lifting_BR2 */
+static void lifting_br2_world(oracle_world* w, double t) {
+  const int np = w->r[0]->np, nvl = w->r[0]->nvl;
+  const int szg = nvl * np * np;
+  FOR_RANKS {
+    oracle* o = w->r[r];
+    lifting_fill_flux(o, 1, o->FluxX, 1);
+    lifting_fill_flux(o, 2, o->FluxY, 1);
+    lifting_fill_flux(o, 3, o->FluxZ, 1);
+  }
+  exchange(w, OFF(FluxX), szg, 1);
+  exchange(w, OFF(FluxY), szg, 1);
+  exchange(w, OFF(FluxZ), szg, 1);
+  FOR_RANKS {
+    oracle* o = w->r[r];
+    lifting_fill_flux_bc(o, t, NULL, o->FluxX, o->FluxY, o->FluxZ);
+    lifting_fill_flux(o, 1, o->FluxX, 0);
+    lifting_fill_flux(o, 2, o->FluxY, 0);
+    lifting_fill_flux(o, 3, o->FluxZ, 0);
+    lifting_volint_nonconservative(o);
+    apply_jacobian(o, nvl, o->gradUx);
+    apply_jacobian(o, nvl, o->gradUy);
+    apply_jacobian(o, nvl, o->gradUz);
+    for (int mpi = 1; mpi >= 0; --mpi) {
+      prolong_to_face(o, nvl, o->gradUx, o->gradUx_master, o->gradUx_slave, mpi);
+      prolong_to_face(o, nvl, o->gradUy, o->gradUy_master, o->gradUy_slave, mpi);
+      prolong_to_face(o, nvl, o->gradUz, o->gradUz_master, o->gradUz_slave, mpi);
+    }
+    for (int mpi = 1; mpi >= 0; --mpi) {
+      lifting_surf_int_br2(o, o->FluxX, o->gradUx, o->gradUx_master, o->gradUx_slave, mpi);
+      lifting_surf_int_br2(o, o->FluxY, o->gradUy, o->gradUy_master, o->gradUy_slave, mpi);
+      lifting_surf_int_br2(o, o->FluxZ, o->gradUz, o->gradUz_master, o->gradUz_slave, mpi);
+    }
+  }
+  exchange(w, OFF(gradUx_slave), szg, 2);
+  exchange(w, OFF(gradUy_slave), szg, 2);
+  exchange(w, OFF(gradUz_slave), szg, 2);
+}
+
 /* dg.f90:221-678 DGTimeDerivative_weakForm */
 void oracle_world_dg_time_derivative(oracle_world* w, double t) {
   const int np = w->r[0]->np;
@@ -1094,10 +1365,8 @@ void oracle_world_dg_time_derivative(oracle_world* w, double t) {
   if (w->r[0]->d.parabolic) { /* 6. */
     if (w->r[0]->d.lifting == 1)
       lifting_br1_world(w, t);
-    else {
-      fprintf(stderr, "oracle: BR2 not restated yet\n");
-      abort();
-    }
+    else
+      lifting_br2_world(w, t);
   }
   FOR_RANKS { /* 8. */
     oracle* o = w->r[r];
