@@ -79,6 +79,8 @@ struct flexi_gpu_handle {
   const NpOps* ops = nullptr;
   Eqn q{};
   Mesh m{};
+  BCData bc{};
+  double* xGP = nullptr;  // Elem_xGP [e][3][NP3], only with a source term
   double CFLScale = 0, DFLScale = 0;
   std::vector<double> RKA, RKb, RKc;
   // partition
@@ -98,6 +100,7 @@ struct flexi_gpu_handle {
   int nElemsInner = 0, nElemsBnd = 0;
   bool keepGrad = false;
   bool tracesValid = false;
+  double lastT = 0.;  // time of the last DG operator evaluation (boundary states / source are time dependent)
   // execution
   cudaStream_t sc = nullptr, sx = nullptr;
   cudaEvent_t evProd = nullptr, evX[3] = {nullptr, nullptr, nullptr};
@@ -312,8 +315,14 @@ int launch_flux(H* h, int first, int n) {
   return 0;
 }
 
-int launch_update(H* h, const int32_t* list, int n, int mode, double rkA, double b_dt) {
+int launch_update(H* h, const int32_t* list, int n, int mode, double rkA, double b_dt, double t) {
   UpdArgs a{};
+  a.doSource = h->bc.doCalcSource;
+  a.xGP = h->xGP;
+  a.t = t;
+  a.srcOmega = h->bc.srcOmega;
+  a.srcA = h->bc.srcA;
+  for (int i = 0; i < 6; ++i) a.srcTmp[i] = h->bc.srcTmp[i];
   a.m = h->m;
   a.elems = list;
   a.nList = n;
@@ -336,28 +345,48 @@ int launch_update(H* h, const int32_t* list, int n, int mode, double rkA, double
 // One DGTimeDerivative_weakForm evaluation (+ optional fused LSERK stage).  Launch order mirrors the reference's latency
 // hiding (dg.f90:360-651: "MPI sides first, start send, inner work, finish"): elements without MPI sides run while the
 // traces / gradients / fluxes of the MPI sides are in flight on the communication stream.
+int launch_bc(H* h, bool pre, double t) {
+  if (h->nBCSides <= 0) return 0;
+  BCArgs a{};
+  a.m = h->m;
+  a.q = h->q;
+  a.bc = h->bc;
+  a.t = t;
+  a.parabolic = h->para;
+  a.U_master = h->Um;
+  a.U_slave = h->Us;
+  for (int d = 0; d < 3; ++d) a.gm[d] = h->gm[d];
+  a.Flux = h->Flux;
+  Timer tm(h, KC_FLUX, h->sc);
+  CK(pre ? h->ops->bc_pre(a, h->sc) : h->ops->flux_bc(a, h->sc));
+  return 0;
+}
+
 int rhs(H* h, double t, int mode, double rkA, double b_dt) {
-  (void)t;
-  if (h->nBCSides > 0) return fail(FLEXI_GPU_ERR_UNSUPPORTED, "boundary conditions are not implemented yet (nBCSides=%d)", h->nBCSides);
+  h->lastT = t;
   if (!h->tracesValid) CKR(refresh_traces(h));
   const bool multi = h->nProcs > 1;
+  // boundary sides: the lifting boundary flux enters the element kernel as a virtual slave trace (k_bc_pre)
+  if (h->para) CKR(launch_bc(h, true, t));
   if (!multi) {
     CKR(launch_volume(h, nullptr, h->nElems));
+    CKR(launch_bc(h, false, t));
     CKR(launch_flux(h, h->firstInner, h->nInnerSides));
-    CKR(launch_update(h, nullptr, h->nElems, mode, rkA, b_dt));
+    CKR(launch_update(h, nullptr, h->nElems, mode, rkA, b_dt, t));
     return 0;
   }
   CKR(launch_volume(h, h->elemsInner, h->nElemsInner));
   CKR(finish_exchange(h, X_TRACE));
   CKR(launch_volume(h, h->elemsBnd, h->nElemsBnd));
   if (h->para) CKR(start_exchange(h, X_GRAD));
+  CKR(launch_bc(h, false, t));
   CKR(launch_flux(h, h->firstInner, h->nInnerSides));
   if (h->para) CKR(finish_exchange(h, X_GRAD));
   CKR(launch_flux(h, h->firstMINE, h->nMINE));
   CKR(start_exchange(h, X_FLUX));
-  CKR(launch_update(h, h->elemsInner, h->nElemsInner, mode, rkA, b_dt));
+  CKR(launch_update(h, h->elemsInner, h->nElemsInner, mode, rkA, b_dt, t));
   CKR(finish_exchange(h, X_FLUX));
-  CKR(launch_update(h, h->elemsBnd, h->nElemsBnd, mode, rkA, b_dt));
+  CKR(launch_update(h, h->elemsBnd, h->nElemsBnd, mode, rkA, b_dt, t));
   if (mode != 0) CKR(start_exchange(h, X_TRACE));  // traces of the updated state for the next stage
   return 0;
 }
@@ -406,7 +435,7 @@ static int init_impl(const flexi_gpu_desc* d, H* h) {
   if (d->splitDG && !(d->splitDGType == FLEXI_SPLITDG_SD || d->splitDGType == FLEXI_SPLITDG_DU || d->splitDGType == FLEXI_SPLITDG_KG || d->splitDGType == FLEXI_SPLITDG_PI))
     return fail(FLEXI_GPU_ERR_UNSUPPORTED, "SplitDG formulation %d is not implemented", d->splitDGType);
   if (d->splitDG && d->riemann == FLEXI_RIEMANN_HLLC) return fail(FLEXI_GPU_ERR_ARG, "HLLC is not selectable with SPLIT_DG (riemann.f90:206-227)");
-  if (d->parabolic && d->lifting != 1) return fail(FLEXI_GPU_ERR_UNSUPPORTED, "BR2 lifting is not implemented yet");
+  if (d->parabolic && d->lifting != 1 && d->lifting != 2) return fail(FLEXI_GPU_ERR_ARG, "lifting must be 1 (BR1) or 2 (BR2)");
   if (d->parabolic && d->nVarLifting != 5 && d->nVarLifting != 4) return fail(FLEXI_GPU_ERR_ARG, "nVarLifting must be 4 or 5");
   if (d->nElems < 1 || d->nSides < 1) return fail(FLEXI_GPU_ERR_ARG, "empty mesh");
   if (d->nBCSides + d->nInnerSides + d->nMPISides_MINE + d->nMPISides_YOUR != d->nSides) return fail(FLEXI_GPU_ERR_ARG, "side ranges do not add up to nSides (mortars are not supported)");
@@ -461,6 +490,9 @@ static int init_impl(const flexi_gpu_desc* d, H* h) {
   q.lv_vel1 = (h->nvl == 5) ? 1 : 0;
   q.lv_temp = q.lv_vel1 + 3;
   for (int v = 0; v < 5; ++v) q.lift_map[v] = lift_prim(h->nvl, v < h->nvl ? v : 0);
+  q.lifting = h->para ? d->lifting : 1;
+  q.etaBR2 = d->etaBR2;
+  q.etaBR2_wall = d->etaBR2_wall;
   switch (q.riemann) {
     case FLEXI_RIEMANN_LF: case FLEXI_RIEMANN_HLLC: case FLEXI_RIEMANN_ROE: case FLEXI_RIEMANN_ROEL2: case FLEXI_RIEMANN_ROEENTROPYFIX:
     case FLEXI_RIEMANN_HLL: case FLEXI_RIEMANN_HLLE: case FLEXI_RIEMANN_HLLEM: break;
@@ -586,7 +618,91 @@ static int init_impl(const flexi_gpu_desc* d, H* h) {
     CK(cudaMemcpy(db, b.data(), b.size() * 8, cudaMemcpyHostToDevice));
     h->m.basis = db;
   }
-  h->m.sideBC = nullptr;
+  // ---- boundary conditions (mesh_vars.f90:96-100; getboundaryflux.f90) and the manufactured-solution source ----
+  {
+    BCData& bc = h->bc;
+    bc.nBCSides = h->nBCSides;
+    bc.riemannBC = (d->riemannBC == FLEXI_RIEMANN_SAME) ? d->riemann : d->riemannBC;
+    bc.iniExactFunc = d->iniExactFunc;
+    bc.iniAmplitude = d->iniAmplitude;
+    bc.iniFrequency = d->iniFrequency;
+    bc.advVel0 = d->advVel[0];
+    for (int i = 0; i < 6; ++i) bc.iniRefPrim[i] = d->iniRefStatePrim[i];
+    if (h->nBCSides > 0) {
+      if (!d->BC || !d->BoundaryType || d->nBCs < 1) return fail(FLEXI_GPU_ERR_ARG, "BC sides without BC / BoundaryType tables");
+      std::vector<int32_t> bt(h->nBCSides), bs(h->nBCSides);
+      bool needX = false;
+      for (int s = 0; s < h->nBCSides; ++s) {
+        const int ibc = d->BC[s];
+        if (ibc < 1 || ibc > d->nBCs) return fail(FLEXI_GPU_ERR_ARG, "BC(%d)=%d outside 1..nBCs", s + 1, ibc);
+        bt[s] = d->BoundaryType[(size_t)0 * d->nBCs + (ibc - 1)];
+        bs[s] = d->BoundaryType[(size_t)1 * d->nBCs + (ibc - 1)];
+        switch (bt[s]) {
+          case 2:
+            if (bs[s] == 0) {
+              if (d->iniExactFunc != 1 && d->iniExactFunc != 4)
+                return fail(FLEXI_GPU_ERR_UNSUPPORTED, "BC type 2 with BCState 0 needs IniExactFunc 1 or 4 (got %d)", d->iniExactFunc);
+              needX = true;
+            } else if (bs[s] < 0 || bs[s] > d->nRefState) {
+              return fail(FLEXI_GPU_ERR_ARG, "BC state %d outside the RefState table", bs[s]);
+            }
+            break;
+          case 4:
+            if (bs[s] < 1 || bs[s] > d->nRefState) return fail(FLEXI_GPU_ERR_ARG, "isothermal wall needs a RefState");
+            break;
+          case 3: case 9: break;
+          default: return fail(FLEXI_GPU_ERR_UNSUPPORTED, "boundary type %d is not implemented (2, 3, 4, 9 are)", bt[s]);
+        }
+      }
+      switch (bc.riemannBC) {
+        case FLEXI_RIEMANN_LF: case FLEXI_RIEMANN_HLLC: case FLEXI_RIEMANN_ROE: case FLEXI_RIEMANN_ROEL2: case FLEXI_RIEMANN_ROEENTROPYFIX:
+        case FLEXI_RIEMANN_HLL: case FLEXI_RIEMANN_HLLE: case FLEXI_RIEMANN_HLLEM: break;
+        default: return fail(FLEXI_GPU_ERR_ARG, "unknown RiemannBC %d", bc.riemannBC);
+      }
+      int32_t *dbt = nullptr, *dbs = nullptr;
+      CKR(dalloc(h, &dbt, bt.size()));
+      CKR(dalloc(h, &dbs, bs.size()));
+      CK(cudaMemcpy(dbt, bt.data(), bt.size() * 4, cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(dbs, bs.data(), bs.size() * 4, cudaMemcpyHostToDevice));
+      bc.bcType = dbt;
+      bc.bcState = dbs;
+      if (d->nRefState > 0 && d->RefStatePrim) {
+        double* dr = nullptr;
+        CKR(dalloc(h, &dr, (size_t)d->nRefState * 6));
+        CK(cudaMemcpy(dr, d->RefStatePrim, (size_t)d->nRefState * 6 * 8, cudaMemcpyHostToDevice));
+        bc.refState = dr;
+      }
+      if (needX) {
+        if (!d->Face_xGP) return fail(FLEXI_GPU_ERR_ARG, "Face_xGP is required for exact-function boundary states");
+        double* dx = nullptr;
+        CKR(dalloc(h, &dx, (size_t)h->nBCSides * 3 * np2));
+        CKR(upload_aos(h, d->Face_xGP, dx, 3, np2, h->nBCSides));  // BC sides come first in the side list
+        bc.faceX = dx;
+      }
+    }
+    h->m.nBCSides = h->nBCSides;
+    h->m.bcType = bc.bcType;
+    bc.doCalcSource = 0;
+    if (d->doCalcSource) {
+      if (d->iniExactFunc != 4) return fail(FLEXI_GPU_ERR_UNSUPPORTED, "CalcSource is implemented for IniExactFunc 4 only (got %d)", d->iniExactFunc);
+      if (!d->Elem_xGP) return fail(FLEXI_GPU_ERR_ARG, "Elem_xGP is required for the source term");
+      CKR(dalloc(h, &h->xGP, nE * 3 * np3));
+      CKR(upload_aos(h, d->Elem_xGP, h->xGP, 3, np3, (long)nE));
+      // exactfunc.f90:762-785 (PP_dim = 3)
+      const double kappa = d->kappa, Amp = d->iniAmplitude, Omega = M_PI * d->iniFrequency, a = d->advVel[0] * 2. * M_PI;
+      double* t = bc.srcTmp;
+      t[0] = -a + 3. * Omega;
+      t[1] = -a + 0.5 * Omega * (1. + kappa * 5.);
+      t[2] = Amp * Omega * (kappa - 1.);
+      t[3] = 0.5 * ((9. + kappa * 15.) * Omega - 8. * a);
+      t[4] = Amp * (3. * Omega * kappa - a);
+      t[5] = h->para ? 3. * d->mu0 * kappa * Omega * Omega / d->Pr : 0.;
+      for (int i = 0; i < 6; ++i) t[i] = t[i] * Amp;
+      bc.srcOmega = Omega;
+      bc.srcA = a;
+      bc.doCalcSource = 1;
+    }
+  }
 
   // ---- state ----
   CKR(dalloc(h, &h->U, nE * 5 * np3));
@@ -782,7 +898,7 @@ int flexi_gpu_get_array(flexi_gpu_handle* h, int32_t which, double* out) {
         // and kept from then on for every later evaluation
         CKR(flexi_gpu_keep_gradients(h, 1));
         if (!h->Ut) CKR(dalloc(h, &h->Ut, (size_t)h->nElems * 5 * h->np3));
-        CKR(rhs(h, 0., 0, 0., 0.));
+        CKR(rhs(h, h->lastT, 0, 0., 0.));
       }
       return download_aos(h, h->gvol[which - FLEXI_ARR_GRADUX], out, h->nvl, np3, h->nElems);
     }

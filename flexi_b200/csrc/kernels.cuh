@@ -55,6 +55,10 @@ struct UpdArgs {
   int mode;    // 0: write Ut only (DGTimeDerivative_weakForm); 1: first RK stage; 2: later RK stage
   double rkA;  // RKA(iStage)
   double b_dt; // RKb(iStage)*dt
+  // CalcSource, exactfunc.f90:727-815 (case 4), evaluated at the stage time t
+  int doSource;
+  const double* xGP;  // Elem_xGP as [e][3][NP3]
+  double t, srcOmega, srcA, srcTmp[6];
 };
 
 struct ProArgs {
@@ -99,13 +103,15 @@ __global__ void __launch_bounds__(Dim<NP>::NP3) k_prolong(ProArgs A) {
 
 // ---------------------------------------------------------------------------------------------------------------------------
 // k_volume
-template <int NP, bool GL, bool SPLIT, bool PARA>
+template <int NP, bool GL, bool SPLIT, bool PARA, int LIFT = 1>
 struct VolSmem {
   using D = Dim<NP>;
   static constexpr int WORK_PLANES = (PARA || !SPLIT) ? 15 : 9;
   static constexpr int FACE_DOUBLES = PARA ? 6 * 8 * D::NP2 : 0;
-  static constexpr int WORK = (WORK_PLANES * D::NP3 > FACE_DOUBLES) ? WORK_PLANES * D::NP3 : FACE_DOUBLES;
-  static constexpr int DOUBLES = D::NBASIS + 7 * D::NP3 + WORK;
+  // BR1: the staged face fluxes alias the work planes; BR2 needs them next to the volume-only gradients
+  static constexpr int WORK = (LIFT == 2) ? WORK_PLANES * D::NP3 : ((WORK_PLANES * D::NP3 > FACE_DOUBLES) ? WORK_PLANES * D::NP3 : FACE_DOUBLES);
+  static constexpr int O_FACE2 = D::NBASIS + 7 * D::NP3 + WORK;
+  static constexpr int DOUBLES = O_FACE2 + ((LIFT == 2 && PARA) ? FACE_DOUBLES : 0);
   static constexpr size_t BYTES = sizeof(double) * DOUBLES;
 };
 
@@ -150,13 +156,14 @@ __device__ __forceinline__ void split_lines(const double* sP, const double* sM, 
 // prim index of lifting variable v (PRIM_LIFT, eos.h:118,127): nvl=5 -> (rho,v1,v2,v3,T), nvl=4 -> (v1,v2,v3,T)
 __host__ __device__ constexpr int lift_prim(int nvl, int v) { return nvl == 5 ? (v < 4 ? v : 5) : (v < 3 ? v + 1 : 5); }
 
-template <int NP, bool GL, bool SPLIT, bool PARA, int NVL>
+template <int NP, bool GL, bool SPLIT, bool PARA, int NVL, int LIFT>
 __global__ void __launch_bounds__(Dim<NP>::NP3) k_volume(VolArgs A) {
   using D = Dim<NP>;
   extern __shared__ double sm[];
   double* sB = sm;
   double* sP = sm + D::NBASIS;  // rho,v1,v2,v3,p,T,rhoE
   double* sW = sP + 7 * D::NP3;
+  double* sLF = (LIFT == 2) ? sm + VolSmem<NP, GL, SPLIT, PARA, LIFT>::O_FACE2 : sW;  // staged lifting fluxes of the faces
   const int tid = threadIdx.x;
   const int e = A.elems ? A.elems[blockIdx.x] : blockIdx.x;
   const int i = tid % NP, j = (tid / NP) % NP, k = tid / D::NP2;
@@ -198,7 +205,7 @@ __global__ void __launch_bounds__(Dim<NP>::NP3) k_volume(VolArgs A) {
       cons_to_prim(q, Um, Pm);
       const double* g = A.m.Geo + (size_t)sr.side * 10 * D::NP2 + pq;
       const double surf = g[9 * D::NP2];
-      double* o = sW + (ls - 1) * 8 * D::NP2 + ab;
+      double* o = sLF + (ls - 1) * 8 * D::NP2 + ab;
       const double sgn = (sr.flip == 0) ? 1. : -1.;  // (slave - master) seen from this element
 #pragma unroll
       for (int v = 0; v < nvl; ++v) {
@@ -230,6 +237,90 @@ __global__ void __launch_bounds__(Dim<NP>::NP3) k_volume(VolArgs A) {
       }
     }
     __syncthreads();
+    if (LIFT == 2) {
+      // BR2 (lifting_br2.t90:111-131): Jacobian first, faces are prolonged from the volume-only gradients
+#pragma unroll
+      for (int v = 0; v < nvl; ++v) {
+        gx[v] = gx[v] * sJ;
+        gy[v] = gy[v] * sJ;
+        gz[v] = gz[v] * sJ;
+        sW[(0 * nvl + v) * D::NP3 + n] = gx[v];
+        sW[(1 * nvl + v) * D::NP3 + n] = gy[v];
+        sW[(2 * nvl + v) * D::NP3 + n] = gz[v];
+      }
+      __syncthreads();
+      // face gradients: prolonged value + eta * sum_l L_Minus(l) * sJ_l * Flux * L_HatMinus(l)   (lifting_br2.t90:253-307)
+      for (int t = tid; t < 6 * D::NP2; t += D::NP3) {
+        const int ls = t / D::NP2 + 1, pq = t % D::NP2;
+        const SideRef sr = A.m.e2s[e * 6 + ls - 1];
+        const int ab = A.m.s2v2[(sr.flip * 6 + ls - 1) * D::NP2 + pq];
+        const int a = ab % NP, b = ab / NP;
+        int base, stride;
+        face_line<NP>(ls, a, b, base, stride);
+        const bool minus = is_minus_side(ls);
+        double eta = q.etaBR2;
+        if (sr.side < A.m.nBCSides) {
+          const int bt = A.m.bcType[sr.side];
+          if (bt == 3 || bt == 4) eta = q.etaBR2_wall;
+        }
+        double wsum = 0.;  // sum_l L_Minus(l) * sJ_l * L_HatMinus(l)
+        {
+          const double* lm = sB + D::O_LM;
+          const double* lhm = sB + D::O_LHM;
+          const int lmax = GL ? 0 : NP - 1;
+          for (int l = 0; l <= lmax; ++l) {
+            const int d = minus ? l : NP - 1 - l;
+            wsum = wsum + lm[l] * (A.m.sJ[(size_t)e * D::NP3 + base + d * stride] * lhm[l]);
+          }
+        }
+        const double* o = sLF + (ls - 1) * 8 * D::NP2 + ab;
+        for (int d = 0; d < 3; ++d) {
+          double* dst = (sr.flip == 0) ? A.gm[d] : A.gs[d];
+          const double nd = o[(5 + d) * D::NP2];
+          for (int v = 0; v < nvl; ++v)
+            dst[((size_t)sr.side * nvl + v) * D::NP2 + pq] =
+                face_eval<NP, GL>(sW + (d * nvl + v) * D::NP3, sB, ls, a, b) + eta * ((o[v * D::NP2] * nd) * wsum);
+        }
+      }
+      // volume gradients: + sJ * Flux * L_HatMinus(depth)
+      {
+        const double* lhm = sB + D::O_LHM;
+#pragma unroll
+        for (int ls = 1; ls <= 6; ++ls) {
+          int ab, me;
+          if (ls == XI_MINUS || ls == XI_PLUS) {
+            ab = j + NP * k;
+            me = i;
+          } else if (ls == ETA_MINUS || ls == ETA_PLUS) {
+            ab = i + NP * k;
+            me = j;
+          } else {
+            ab = i + NP * j;
+            me = k;
+          }
+          const int depth = is_minus_side(ls) ? me : NP - 1 - me;
+          if (GL && depth != 0) continue;
+          const double lh = lhm[depth];
+          const double* o = sLF + (ls - 1) * 8 * D::NP2 + ab;
+          const double n0 = o[5 * D::NP2], n1 = o[6 * D::NP2], n2 = o[7 * D::NP2];
+#pragma unroll
+          for (int v = 0; v < nvl; ++v) {
+            const double f = o[v * D::NP2];
+            gx[v] = gx[v] + sJ * (f * n0) * lh;
+            gy[v] = gy[v] + sJ * (f * n1) * lh;
+            gz[v] = gz[v] + sJ * (f * n2) * lh;
+          }
+        }
+      }
+      if (A.gvol[0]) {
+#pragma unroll
+        for (int v = 0; v < nvl; ++v) {
+          A.gvol[0][((size_t)e * nvl + v) * D::NP3 + n] = gx[v];
+          A.gvol[1][((size_t)e * nvl + v) * D::NP3 + n] = gy[v];
+          A.gvol[2][((size_t)e * nvl + v) * D::NP3 + n] = gz[v];
+        }
+      }
+    } else {
     // ---- 3. surface part, lifting_br1.t90:195-292 (same sign for master and slave element), then *sJ (applyjacobian.t90)
     {
       const double* lhm = sB + D::O_LHM;
@@ -295,6 +386,7 @@ __global__ void __launch_bounds__(Dim<NP>::NP3) k_volume(VolArgs A) {
           dst[((size_t)sr.side * nvl + v) * D::NP2 + pq] = face_eval<NP, GL>(sW + (d * nvl + v) * D::NP3, sB, ls, a, b);
       }
     }
+    }  // BR1
     // ---- 5. viscous (+ advective in weak form) fluxes of this node in the reference element, volint.f90:378-422
     double F[5], G[5], H[5];
     {
@@ -419,6 +511,139 @@ __global__ void __launch_bounds__(128) k_flux(FluxArgs A) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
+// Boundary sides.  k_bc_pre turns the lifting boundary flux of Lifting_GetBoundaryFlux (getboundaryflux.f90:855-940, strong form)
+// into a virtual slave trace: the element kernels evaluate 0.5*(UPrim(U_slave)-UPrim_master)*SurfElem on every side, so U_slave of
+// a BC side is set to the conservative state whose primitives are 2*F_bc - UPrim_master (for Riemann-type BCs that is the
+// boundary state itself).  k_flux_bc is GetBoundaryFlux (getboundaryflux.f90:480-790) * SurfElem (fillflux.f90:179-186).
+struct BCArgs {
+  Mesh m;
+  Eqn q;
+  BCData bc;
+  double t;
+  int parabolic;
+  const double* U_master;
+  double* U_slave;
+  const double* gm[3];
+  double* Flux;
+};
+
+template <int NP>
+__device__ __forceinline__ void bc_load(const BCArgs& A, int s, int pq, double* Um, double* Pm, double* nv, double* t1, double* t2,
+                                        double* xf, double& surf) {
+  using D = Dim<NP>;
+#pragma unroll
+  for (int v = 0; v < 5; ++v) Um[v] = A.U_master[((size_t)s * 5 + v) * D::NP2 + pq];
+  cons_to_prim(A.q, Um, Pm);
+  const double* g = A.m.Geo + (size_t)s * 10 * D::NP2 + pq;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    nv[c] = g[c * D::NP2];
+    t1[c] = g[(3 + c) * D::NP2];
+    t2[c] = g[(6 + c) * D::NP2];
+    xf[c] = A.bc.faceX ? A.bc.faceX[((size_t)s * 3 + c) * D::NP2 + pq] : 0.;
+  }
+  surf = g[9 * D::NP2];
+}
+
+template <int NP>
+__global__ void __launch_bounds__(128) k_bc_pre(BCArgs A) {
+  using D = Dim<NP>;
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)A.bc.nBCSides * D::NP2) return;
+  const int s = (int)(idx / D::NP2), pq = (int)(idx % D::NP2);
+  const int type = A.bc.bcType[s], state = A.bc.bcState[s];
+  double Um[5], Pm[6], Pb[6], nv[3], t1[3], t2[3], xf[3], surf;
+  bc_load<NP>(A, s, pq, Um, Pm, nv, t1, t2, xf, surf);
+  boundary_state(A.q, A.bc, type, state, A.t, Pm, nv, t1, t2, xf, Pb);
+  double V[6];
+  if (type == 2) {
+#pragma unroll
+    for (int v = 0; v < 6; ++v) V[v] = Pb[v];
+  } else if (type == 3 || type == 4) {  // F = (rho_b, 0, T_b)
+    V[DENS] = 2. * Pb[DENS] - Pm[DENS];
+    V[VEL1] = -Pm[VEL1];
+    V[VEL2] = -Pm[VEL2];
+    V[VEL3] = -Pm[VEL3];
+    V[TEMP] = 2. * Pb[TEMP] - Pm[TEMP];
+    V[PRES] = V[DENS] * A.q.R * V[TEMP];
+  } else {  // 9: F = (rho_m, v_b, T_m)
+    V[DENS] = Pm[DENS];
+    V[VEL1] = 2. * Pb[VEL1] - Pm[VEL1];
+    V[VEL2] = 2. * Pb[VEL2] - Pm[VEL2];
+    V[VEL3] = 2. * Pb[VEL3] - Pm[VEL3];
+    V[TEMP] = Pm[TEMP];
+    V[PRES] = V[DENS] * A.q.R * V[TEMP];
+  }
+  double Uv[5];
+  prim_to_cons(A.q, V, Uv);
+#pragma unroll
+  for (int v = 0; v < 5; ++v) A.U_slave[((size_t)s * 5 + v) * D::NP2 + pq] = Uv[v];
+}
+
+template <int NP>
+__global__ void __launch_bounds__(128) k_flux_bc(BCArgs A) {
+  using D = Dim<NP>;
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)A.bc.nBCSides * D::NP2) return;
+  const int s = (int)(idx / D::NP2), pq = (int)(idx % D::NP2);
+  const int type = A.bc.bcType[s], state = A.bc.bcState[s];
+  const Eqn& q = A.q;
+  double Um[5], Pm[6], Pb[6], nv[3], t1[3], t2[3], xf[3], surf;
+  bc_load<NP>(A, s, pq, Um, Pm, nv, t1, t2, xf, surf);
+  boundary_state(q, A.bc, type, state, A.t, Pm, nv, t1, t2, xf, Pb);
+  double F[5];
+  double gx[4], gy[4], gz[4];
+  if (A.parabolic) {
+    const int nvl = q.nvl, o = q.lv_vel1;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      gx[c] = A.gm[0][((size_t)s * nvl + o + c) * D::NP2 + pq];
+      gy[c] = A.gm[1][((size_t)s * nvl + o + c) * D::NP2 + pq];
+      gz[c] = A.gm[2][((size_t)s * nvl + o + c) * D::NP2 + pq];
+    }
+  }
+  if (type == 2) {  // Riemann-type BC: getboundaryflux.f90:561-578
+    double Ucm[5], Ucb[5];
+    prim_to_cons(q, Pm, Ucm);
+    prim_to_cons(q, Pb, Ucb);
+    riemann_point(q, A.bc.riemannBC, Ucm, Ucb, Pm, Pb, nv, t1, t2, F);
+    if (A.parabolic) {
+      double fL[4], gL[4], hL[4], fR[4], gR[4], hR[4];
+      eval_diff_flux3d(q, Pm[VEL1], Pm[VEL2], Pm[VEL3], gx, gy, gz, fL, gL, hL);
+      eval_diff_flux3d(q, Pb[VEL1], Pb[VEL2], Pb[VEL3], gx, gy, gz, fR, gR, hR);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) F[c + 1] = F[c + 1] + 0.5 * (nv[0] * (fL[c] + fR[c]) + nv[1] * (gL[c] + gR[c]) + nv[2] * (hL[c] + hR[c]));
+    }
+  } else {  // walls: getboundaryflux.f90:580-780
+    F[0] = 0.;
+    F[1] = Pb[PRES] * nv[0];
+    F[2] = Pb[PRES] * nv[1];
+    F[3] = Pb[PRES] * nv[2];
+    F[4] = 0.;
+    if (A.parabolic) {
+      if (type == 9) {  // BCGradMat = I - n n^T: no normal derivatives
+        const double B11 = 1. - nv[0] * nv[0], B22 = 1. - nv[1] * nv[1], B33 = 1. - nv[2] * nv[2];
+        const double B12 = -nv[0] * nv[1], B13 = -nv[0] * nv[2], B32 = -nv[2] * nv[1];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const double x = gx[c], y = gy[c], z = gz[c];
+          gx[c] = B11 * x + B12 * y + B13 * z;
+          gy[c] = B12 * x + B22 * y + B32 * z;
+          gz[c] = B13 * x + B32 * y + B33 * z;
+        }
+      }
+      double f[4], g[4], h[4];
+      eval_diff_flux3d(q, Pb[VEL1], Pb[VEL2], Pb[VEL3], gx, gy, gz, f, g, h);
+      if (type == 3) f[3] = g[3] = h[3] = 0.;  // adiabatic wall: no energy flux
+#pragma unroll
+      for (int c = 0; c < 4; ++c) F[c + 1] = F[c + 1] + nv[0] * f[c] + nv[1] * g[c] + nv[2] * h[c];
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < 5; ++v) A.Flux[((size_t)s * 5 + v) * D::NP2 + pq] = F[v] * surf;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
 // k_update: SurfInt gather + Ut=-Ut + ApplyJacobian + LSERK + ProlongToFace(new U)
 template <int NP, bool GL>
 __global__ void __launch_bounds__(Dim<NP>::NP3) k_update(UpdArgs A) {
@@ -460,8 +685,20 @@ __global__ void __launch_bounds__(Dim<NP>::NP3) k_update(UpdArgs A) {
 #pragma unroll
     for (int v = 0; v < 5; ++v) ut[v] = ut[v] + (sgn * A.Flux[((size_t)sr.side * 5 + v) * D::NP2 + pq]) * lh;
   }
+  if (A.doSource) {  // Ut = -Ut; Ut += src/sJ; Ut *= sJ  (dg.f90:656-675, exactfunc.f90:809-813)
+    const double* x = A.xGP + (size_t)e * 3 * D::NP3 + n;
+    const double arg = A.srcOmega * (x[0] + x[D::NP3] + x[2 * D::NP3]) - A.srcA * A.t;
+    const double cosX = cos(arg), sinX = sin(arg), sinX2 = 2. * sinX * cosX;
+    double src[5];
+    src[0] = A.srcTmp[0] * cosX;
+    src[1] = src[2] = src[3] = A.srcTmp[1] * cosX + A.srcTmp[2] * sinX2;
+    src[4] = A.srcTmp[3] * cosX + A.srcTmp[4] * sinX2 + A.srcTmp[5] * sinX;
 #pragma unroll
-  for (int v = 0; v < 5; ++v) ut[v] = (-ut[v]) * sJ;  // dg.f90:656,675
+    for (int v = 0; v < 5; ++v) ut[v] = ((-ut[v]) + src[v] / sJ) * sJ;
+  } else {
+#pragma unroll
+    for (int v = 0; v < 5; ++v) ut[v] = (-ut[v]) * sJ;  // dg.f90:656,675
+  }
   if (A.mode == 0) {
 #pragma unroll
     for (int v = 0; v < 5; ++v) A.UtOut[((size_t)e * 5 + v) * D::NP3 + n] = ut[v];

@@ -36,7 +36,8 @@ struct Mesh {
   const int32_t* s2v2; // [(flip*6+ls-1)*NP2 + pq] -> a + NP*b (volume-face coordinates), mappings.f90:389-397
   const int32_t* v2s;  // inverse: [(flip*6+ls-1)*NP2 + ab] -> pq
   const double* basis; // [dt | dh | dv | L_Minus | L_Plus | L_HatMinus | L_HatPlus], matrices as M[l*NP+i] = M(l,i)
-  const int32_t* sideBC; // [nSides]: 0 = no BC, else 1-based BC index (only sides < nBCSides are non-zero)
+  int nBCSides;           // BC sides are sides 0..nBCSides-1 (mesh.f90:257-269)
+  const int32_t* bcType;  // [nBCSides] BC_TYPE of each BC side (needed by BR2: etaBR2_wall on types 3/4)
 };
 
 template <int NP>

@@ -16,25 +16,40 @@ using D = Dim<NP>;
 // k-block size of the Gauss-Lobatto element kernel: half a zeta column per thread for even NP, one node otherwise
 constexpr int KPT = (NP % 2 == 0) ? NP / 2 : 1;
 
-template <bool PARA, int NVL>
-cudaError_t volume_setup() {
-  return cudaFuncSetAttribute(k_volume<NP, false, false, PARA, NVL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)VolSmem<NP, false, false, PARA>::BYTES);
+template <bool PARA, int NVL, int LIFT>
+cudaError_t volume_setup1() {
+  return cudaFuncSetAttribute(k_volume<NP, false, false, PARA, NVL, LIFT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)VolSmem<NP, false, false, PARA, LIFT>::BYTES);
 }
 template <bool PARA, int NVL>
-cudaError_t volume_launch(const VolArgs& a, int nBlocks, cudaStream_t s) {
-  k_volume<NP, false, false, PARA, NVL><<<nBlocks, D::NP3, VolSmem<NP, false, false, PARA>::BYTES, s>>>(a);
+cudaError_t volume_setup() {
+  cudaError_t e = volume_setup1<PARA, NVL, 1>();
+  if (e == cudaSuccess && PARA) e = volume_setup1<PARA, NVL, 2>();
+  return e;
+}
+template <bool PARA, int NVL>
+cudaError_t volume_launch(int lift, const VolArgs& a, int nBlocks, cudaStream_t s) {
+  if (PARA && lift == 2)
+    k_volume<NP, false, false, PARA, NVL, 2><<<nBlocks, D::NP3, VolSmem<NP, false, false, PARA, 2>::BYTES, s>>>(a);
+  else
+    k_volume<NP, false, false, PARA, NVL, 1><<<nBlocks, D::NP3, VolSmem<NP, false, false, PARA, 1>::BYTES, s>>>(a);
   return cudaGetLastError();
 }
 template <bool SPLIT, int STYPE, bool PARA, int NVL>
 cudaError_t volume_gl_setup() {
   using C = VolGLCfg<NP, KPT, SPLIT, PARA>;
-  return cudaFuncSetAttribute(k_volume_gl<NP, KPT, SPLIT, STYPE, PARA, NVL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::BYTES);
+  cudaError_t e = cudaFuncSetAttribute(k_volume_gl<NP, KPT, SPLIT, STYPE, PARA, NVL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::BYTES);
+  if (e == cudaSuccess && PARA)
+    e = cudaFuncSetAttribute(k_volume_gl<NP, KPT, SPLIT, STYPE, PARA, NVL, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::BYTES);
+  return e;
 }
 template <bool SPLIT, int STYPE, bool PARA, int NVL>
-cudaError_t volume_gl_launch(const VolArgs& a, int nBlocks, cudaStream_t s) {
+cudaError_t volume_gl_launch(int lift, const VolArgs& a, int nBlocks, cudaStream_t s) {
   using C = VolGLCfg<NP, KPT, SPLIT, PARA>;
-  k_volume_gl<NP, KPT, SPLIT, STYPE, PARA, NVL><<<nBlocks, C::NT, C::BYTES, s>>>(a);
+  if (PARA && lift == 2)
+    k_volume_gl<NP, KPT, SPLIT, STYPE, PARA, NVL, 2><<<nBlocks, C::NT, C::BYTES, s>>>(a);
+  else
+    k_volume_gl<NP, KPT, SPLIT, STYPE, PARA, NVL, 1><<<nBlocks, C::NT, C::BYTES, s>>>(a);
   return cudaGetLastError();
 }
 
@@ -46,11 +61,11 @@ cudaError_t alt_setup() {
   const char* e = getenv("FLEXI_GPU_KPT");
   g_kpt_alt = e ? atoi(e) : 0;
   using C = VolGLCfg<NP, 2, true, true>;
-  return cudaFuncSetAttribute(k_volume_gl<NP, 2, true, FLEXI_SPLITDG_PI, true, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::BYTES);
+  return cudaFuncSetAttribute(k_volume_gl<NP, 2, true, FLEXI_SPLITDG_PI, true, 5, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::BYTES);
 }
 cudaError_t alt_launch(const VolArgs& a, int nBlocks, cudaStream_t s) {
   using C = VolGLCfg<NP, 2, true, true>;
-  k_volume_gl<NP, 2, true, FLEXI_SPLITDG_PI, true, 5><<<nBlocks, C::NT, C::BYTES, s>>>(a);
+  k_volume_gl<NP, 2, true, FLEXI_SPLITDG_PI, true, 5, 1><<<nBlocks, C::NT, C::BYTES, s>>>(a);
   return cudaGetLastError();
 }
 #endif
@@ -97,13 +112,14 @@ cudaError_t prolong(bool gl, const ProArgs& a, int nElems, cudaStream_t s) {
 cudaError_t volume(bool gl, bool split, int stype, bool para, int nvl, const VolArgs& a, int nBlocks, cudaStream_t s) {
   if (nBlocks <= 0) return cudaSuccess;
   if (split && !gl) return cudaErrorNotSupported;
+  const int lift = a.q.lifting;
   if (!gl) {
-    if (!para) return volume_launch<false, 5>(a, nBlocks, s);
-    return nvl == 5 ? volume_launch<true, 5>(a, nBlocks, s) : volume_launch<true, 4>(a, nBlocks, s);
+    if (!para) return volume_launch<false, 5>(lift, a, nBlocks, s);
+    return nvl == 5 ? volume_launch<true, 5>(lift, a, nBlocks, s) : volume_launch<true, 4>(lift, a, nBlocks, s);
   }
   if (!split) {
-    if (!para) return volume_gl_launch<false, 0, false, 5>(a, nBlocks, s);
-    return nvl == 5 ? volume_gl_launch<false, 0, true, 5>(a, nBlocks, s) : volume_gl_launch<false, 0, true, 4>(a, nBlocks, s);
+    if (!para) return volume_gl_launch<false, 0, false, 5>(lift, a, nBlocks, s);
+    return nvl == 5 ? volume_gl_launch<false, 0, true, 5>(lift, a, nBlocks, s) : volume_gl_launch<false, 0, true, 4>(lift, a, nBlocks, s);
   }
 #if FLEXI_NP == 8
   if (g_kpt_alt == 2 && stype == FLEXI_SPLITDG_PI && para && nvl == 5) return alt_launch(a, nBlocks, s);
@@ -111,12 +127,25 @@ cudaError_t volume(bool gl, bool split, int stype, bool para, int nvl, const Vol
   switch (stype) {
 #define X(T)                                                                                                     \
   case T:                                                                                                        \
-    if (!para) return volume_gl_launch<true, T, false, 5>(a, nBlocks, s);                                        \
-    return nvl == 5 ? volume_gl_launch<true, T, true, 5>(a, nBlocks, s) : volume_gl_launch<true, T, true, 4>(a, nBlocks, s);
+    if (!para) return volume_gl_launch<true, T, false, 5>(lift, a, nBlocks, s);                                  \
+    return nvl == 5 ? volume_gl_launch<true, T, true, 5>(lift, a, nBlocks, s) : volume_gl_launch<true, T, true, 4>(lift, a, nBlocks, s);
     FX_SPLIT_TYPES(X)
 #undef X
     default: return cudaErrorNotSupported;
   }
+}
+
+cudaError_t bc_pre(const BCArgs& a, cudaStream_t s) {
+  const long n = (long)a.bc.nBCSides * D::NP2;
+  if (n <= 0) return cudaSuccess;
+  k_bc_pre<NP><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(a);
+  return cudaGetLastError();
+}
+cudaError_t flux_bc(const BCArgs& a, cudaStream_t s) {
+  const long n = (long)a.bc.nBCSides * D::NP2;
+  if (n <= 0) return cudaSuccess;
+  k_flux_bc<NP><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(a);
+  return cudaGetLastError();
 }
 
 cudaError_t flux(const FluxArgs& a, cudaStream_t s) {
@@ -154,7 +183,7 @@ cudaError_t dt_init(const DtInitArgs& a, cudaStream_t s) {
   return cudaGetLastError();
 }
 
-const NpOps ops = {NP, setup, prolong, volume, flux, update, surfint, dt, dt_init};
+const NpOps ops = {NP, setup, prolong, volume, flux, update, surfint, dt, dt_init, bc_pre, flux_bc};
 }  // namespace
 }  // namespace fx
 

@@ -16,6 +16,24 @@ struct Eqn {
   int nvl;            // PP_nVarLifting
   int lv_vel1, lv_temp;  // position of v1 / T inside the lifting variable set (eos.h:118,127)
   int lift_map[5];       // prim index of each lifting variable
+  int lifting;           // PP_Lifting: 1 = BR1, 2 = BR2
+  double etaBR2, etaBR2_wall;  // lifting.f90:130-133
+};
+
+// boundary-condition data (mesh_vars.f90:96-100, equation_vars: RefStatePrim, exactfunc parameters)
+struct BCData {
+  int nBCSides;
+  const int32_t* bcType;   // [nBCSides] BoundaryType(BC(SideID),BC_TYPE)
+  const int32_t* bcState;  // [nBCSides] BoundaryType(BC(SideID),BC_STATE)
+  const double* refState;  // [nRefState][6] RefStatePrim
+  const double* faceX;     // [nBCSides][3][NP2] Face_xGP of the BC sides
+  int riemannBC;           // resolved solver id for boundary sides (riemann.f90:178-199)
+  int iniExactFunc;
+  double iniAmplitude, iniFrequency, advVel0;
+  double iniRefPrim[6];
+  int doCalcSource;
+  double srcTmp[6];  // CalcSource case 4 coefficients (exactfunc.f90:762-785)
+  double srcOmega, srcA;
 };
 
 enum { DENS = 0, MOM1 = 1, MOM2 = 2, MOM3 = 3, ENER = 4 };
@@ -41,6 +59,15 @@ __device__ __forceinline__ double cons_to_prim_srho(const Eqn& q, const double* 
   p[PRES] = q.kappaM1 * (c[ENER] - 0.5 * (c[MOM1] * p[VEL1] + c[MOM2] * p[VEL2] + c[MOM3] * p[VEL3]));
   p[TEMP] = p[PRES] * sRho * q.sR;
   return sRho;
+}
+
+// eos.f90:308-330 PrimToCons
+__device__ __forceinline__ void prim_to_cons(const Eqn& q, const double* __restrict__ p, double* __restrict__ c) {
+  c[DENS] = p[DENS];
+  c[MOM1] = p[VEL1] * p[DENS];
+  c[MOM2] = p[VEL2] * p[DENS];
+  c[MOM3] = p[VEL3] * p[DENS];
+  c[ENER] = q.sKappaM1 * p[PRES] + 0.5 * (c[MOM1] * p[VEL1] + c[MOM2] * p[VEL2] + c[MOM3] * p[VEL3]);
 }
 
 // flux.f90:66-119 EvalFlux3D_Point
@@ -417,6 +444,66 @@ __device__ __forceinline__ void riemann_point(const Eqn& q, int solver, const do
   FOut[MOM2] = nv[1] * F[1] + t1[1] * F[2] + t2[1] * F[3];
   FOut[MOM3] = nv[2] * F[1] + t1[2] * F[2] + t2[2] * F[3];
   FOut[ENER] = F[4];
+}
+
+// ---- boundary conditions: idealgas/exactfunc.f90, idealgas/getboundaryflux.f90 -------------------------------------------------
+// exactfunc.f90:225-362 ExactFunc, cases 1 (constant RefState) and 4 (oblique sine wave)
+__device__ __forceinline__ void exact_func(const Eqn& q, const BCData& bc, double t, const double* x, double* cons) {
+  if (bc.iniExactFunc == 4) {
+    const double Omega = 3.14159265358979323846 * bc.iniFrequency, a = bc.advVel0 * 2. * 3.14159265358979323846;
+    const double r = 2. + bc.iniAmplitude * sin(Omega * (x[0] + x[1] + x[2]) - a * t);
+    cons[0] = cons[1] = cons[2] = cons[3] = r;
+    cons[4] = r * r;
+  } else {
+    prim_to_cons(q, bc.iniRefPrim, cons);
+  }
+}
+
+// eos.f90:561-583 PRESSURE_RIEMANN (state in the face-normal system)
+__device__ __forceinline__ double pressure_riemann(const Eqn& q, const double* P) {
+  const double kappaFac = 2. * q.kappa * q.sKappaM1, sKappaP1 = 1. / (q.kappa + 1.);
+  if (P[VEL1] <= 0.) return P[PRES] * pow(fmax(0.0001, (1. + 0.5 * q.kappaM1 * P[VEL1] / sqrt(q.kappa * P[PRES] / P[DENS]))), kappaFac);
+  const double ar = 2. * sKappaP1 / P[DENS], br = q.kappaM1 * sKappaP1 * P[PRES];
+  return P[PRES] + P[VEL1] / ar * 0.5 * (P[VEL1] + sqrt(P[VEL1] * P[VEL1] + 4. * ar * (P[PRES] + br)));
+}
+
+// getboundaryflux.f90:224-470 GetBoundaryState for one face node: types 2, 3, 4, 9
+__device__ __forceinline__ void boundary_state(const Eqn& q, const BCData& bc, int type, int state, double t, const double* Pm,
+                                               const double* nv, const double* t1, const double* t2, const double* xf, double* Pb) {
+  if (type == 2) {
+    if (state == 0) {
+      double cons[5];
+      exact_func(q, bc, t, xf, cons);
+      cons_to_prim(q, cons, Pb);
+    } else {
+#pragma unroll
+      for (int v = 0; v < 6; ++v) Pb[v] = bc.refState[(size_t)(state - 1) * 6 + v];
+    }
+    return;
+  }
+  Pb[DENS] = Pm[DENS];
+  Pb[VEL1] = Pm[VEL1] * nv[0] + Pm[VEL2] * nv[1] + Pm[VEL3] * nv[2];
+  Pb[VEL2] = Pm[VEL1] * t1[0] + Pm[VEL2] * t1[1] + Pm[VEL3] * t1[2];
+  Pb[VEL3] = Pm[VEL1] * t2[0] + Pm[VEL2] * t2[1] + Pm[VEL3] * t2[2];
+  Pb[PRES] = Pm[PRES];
+  Pb[TEMP] = Pm[TEMP];
+  Pb[PRES] = pressure_riemann(q, Pb);
+  if (type == 3) {
+    Pb[VEL1] = Pb[VEL2] = Pb[VEL3] = 0.;
+    Pb[TEMP] = Pm[TEMP];
+    Pb[DENS] = Pb[PRES] / (Pb[TEMP] * q.R);
+  } else if (type == 4) {
+    Pb[VEL1] = Pb[VEL2] = Pb[VEL3] = 0.;
+    Pb[TEMP] = bc.refState[(size_t)(state - 1) * 6 + TEMP];
+    Pb[DENS] = Pb[PRES] / (Pb[TEMP] * q.R);
+  } else {  // 9: slip wall
+    Pb[VEL1] = 0.;
+    Pb[DENS] = Pm[DENS];
+    Pb[TEMP] = Pb[PRES] / (Pb[DENS] * q.R);
+  }
+  const double vn = Pb[VEL1], vt1 = Pb[VEL2], vt2 = Pb[VEL3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) Pb[VEL1 + c] = vn * nv[c] + vt1 * t1[c] + vt2 * t2[c];
 }
 
 }  // namespace fx

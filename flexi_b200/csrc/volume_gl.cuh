@@ -61,7 +61,8 @@ struct VolGLCfg {
   static constexpr int NB = (D::NBASIS + 1) & ~1;
   static constexpr int O_FDST = O_BASIS + NB;  // int table [6][NP2]: where a boundary node's gradient trace goes
   static constexpr int NFD = PARA ? ((3 * D::NP2 + 1) & ~1) : 0;
-  static constexpr int O_P = O_FDST + NFD;
+  static constexpr int O_ETA = O_FDST + NFD;  // BR2 penalty eta of the six sides
+  static constexpr int O_P = O_ETA + (PARA ? 6 : 0);
   static constexpr int O_X = O_P + P_PLANES * D::NP3;
   static constexpr int O_W = O_X + X_DOUBLES;
   static constexpr int DOUBLES = O_W + W_PLANES * D::NP3;
@@ -131,7 +132,7 @@ __device__ __forceinline__ void split_pair_generic(const double* a, const double
   split_volume_flux<STYPE>(na, nb, Ma, Mb, F);
 }
 
-template <int NP, int KPT, bool SPLIT, int STYPE, bool PARA, int NVL>
+template <int NP, int KPT, bool SPLIT, int STYPE, bool PARA, int NVL, int LIFT>
 __global__ void __launch_bounds__(VolGLCfg<NP, KPT, SPLIT, PARA>::NT, VolGLCfg<NP, KPT, SPLIT, PARA>::MINB)
     k_volume_gl(VolArgs A) {
   using D = Dim<NP>;
@@ -143,6 +144,7 @@ __global__ void __launch_bounds__(VolGLCfg<NP, KPT, SPLIT, PARA>::NT, VolGLCfg<N
   double* sB = sm + C::O_BASIS;
   double* sP = sm + C::O_P;  // rho,u,v,w,p, T (later H / rhoE / E for the split fluxes)
   int* sFD = reinterpret_cast<int*>(sm + C::O_FDST);
+  double* sEta = sm + C::O_ETA;
   double* sX = sm + C::O_X;  // lifting fluxes of the faces, then the metric planes
   double* sM = sX;
   double* sW = sm + C::O_W;
@@ -204,6 +206,14 @@ __global__ void __launch_bounds__(VolGLCfg<NP, KPT, SPLIT, PARA>::NT, VolGLCfg<N
         faceSlot[it] = (ls - 1) * 9 * D::NP2 + ab;
         // destination of this face node's gradient trace: (side*NVL*NP2 + pq), sign bit set for the slave arrays
         sFD[(ls - 1) * D::NP2 + ab] = (sr.side * NVL * D::NP2 + pq) | (sr.flip == 0 ? 0 : (int)0x80000000);
+        if (LIFT == 2 && pq == 0) {  // lifting_br2.t90:277-288: etaBR2_wall on no-slip wall sides
+          double eta = q.etaBR2;
+          if (sr.side < A.m.nBCSides) {
+            const int bt = A.m.bcType[sr.side];
+            if (bt == 3 || bt == 4) eta = q.etaBR2_wall;
+          }
+          sEta[ls - 1] = eta;
+        }
         int base, stride;
         face_line<NP>(ls, ab % NP, ab / NP, base, stride);
         faceSgn[it] = (sr.flip == 0) ? 1. : -1.;
@@ -300,29 +310,57 @@ __global__ void __launch_bounds__(VolGLCfg<NP, KPT, SPLIT, PARA>::NT, VolGLCfg<N
           gy[v] = M[1] * gxi + M[4] * geta + M[7] * gzeta;
           gz[v] = M[2] * gxi + M[5] * geta + M[8] * gzeta;
         }
-        // ---- lifting, surface part (lifting_br1.t90:195-292): on LGL nodes only the boundary nodes receive it ----
+        // ---- lifting, surface part: on LGL nodes only the boundary nodes receive it ----
         const bool onFace[6] = {k == 0, j == 0, i == N, j == N, i == 0, k == N};  // local sides 1..6 (flexi.h:90-95)
         const int abFace[6] = {i + NP * j, i + NP * k, j + NP * k, i + NP * k, j + NP * k, i + NP * j};
+        double gxo[NVL], gyo[NVL], gzo[NVL];  // BR2: gradients without the surface part (what the faces are prolonged from)
+        if (LIFT == 1) {  // BR1 (lifting_br1.t90:195-292), then ApplyJacobianLifting
 #pragma unroll
-        for (int ls = 1; ls <= 6; ++ls) {
-          if (onFace[ls - 1]) {
-            const double* o = sX + (ls - 1) * 9 * D::NP2 + abFace[ls - 1];
-            const double n0 = o[5 * D::NP2], n1 = o[6 * D::NP2], n2 = o[7 * D::NP2];
-            const double lh = is_minus_side(ls) ? sB[D::O_LHM] : sB[D::O_LHP + N];
+          for (int ls = 1; ls <= 6; ++ls) {
+            if (onFace[ls - 1]) {
+              const double* o = sX + (ls - 1) * 9 * D::NP2 + abFace[ls - 1];
+              const double n0 = o[5 * D::NP2], n1 = o[6 * D::NP2], n2 = o[7 * D::NP2];
+              const double lh = is_minus_side(ls) ? sB[D::O_LHM] : sB[D::O_LHP + N];
 #pragma unroll
-            for (int v = 0; v < NVL; ++v) {
-              const double f = o[v * D::NP2];
-              gx[v] = gx[v] + (f * n0) * lh;
-              gy[v] = gy[v] + (f * n1) * lh;
-              gz[v] = gz[v] + (f * n2) * lh;
+              for (int v = 0; v < NVL; ++v) {
+                const double f = o[v * D::NP2];
+                gx[v] = gx[v] + (f * n0) * lh;
+                gy[v] = gy[v] + (f * n1) * lh;
+                gz[v] = gz[v] + (f * n2) * lh;
+              }
             }
           }
-        }
 #pragma unroll
-        for (int v = 0; v < NVL; ++v) {  // ApplyJacobianLifting
-          gx[v] = gx[v] * sJ[c];
-          gy[v] = gy[v] * sJ[c];
-          gz[v] = gz[v] * sJ[c];
+          for (int v = 0; v < NVL; ++v) {
+            gx[v] = gx[v] * sJ[c];
+            gy[v] = gy[v] * sJ[c];
+            gz[v] = gz[v] * sJ[c];
+          }
+        } else {  // BR2 (lifting_br2.t90:111-131,194-311): Jacobian first, then sJ*Flux*L_HatMinus(0) on the boundary node
+#pragma unroll
+          for (int v = 0; v < NVL; ++v) {
+            gx[v] = gx[v] * sJ[c];
+            gy[v] = gy[v] * sJ[c];
+            gz[v] = gz[v] * sJ[c];
+            gxo[v] = gx[v];
+            gyo[v] = gy[v];
+            gzo[v] = gz[v];
+          }
+#pragma unroll
+          for (int ls = 1; ls <= 6; ++ls) {
+            if (onFace[ls - 1]) {
+              const double* o = sX + (ls - 1) * 9 * D::NP2 + abFace[ls - 1];
+              const double n0 = o[5 * D::NP2], n1 = o[6 * D::NP2], n2 = o[7 * D::NP2];
+              const double lh = sB[D::O_LHM];
+#pragma unroll
+              for (int v = 0; v < NVL; ++v) {
+                const double f = o[v * D::NP2];
+                gx[v] = gx[v] + sJ[c] * (f * n0) * lh;
+                gy[v] = gy[v] + sJ[c] * (f * n1) * lh;
+                gz[v] = gz[v] + sJ[c] * (f * n2) * lh;
+              }
+            }
+          }
         }
         if (A.gvol[0]) {
 #pragma unroll
@@ -332,7 +370,8 @@ __global__ void __launch_bounds__(VolGLCfg<NP, KPT, SPLIT, PARA>::NT, VolGLCfg<N
             A.gvol[2][((size_t)e * NVL + v) * D::NP3 + n] = gz[v];
           }
         }
-        // ---- ProlongToFaceLifting on LGL nodes = copy of the boundary node (prolongtoface.t90:270-303) ----
+        // ---- ProlongToFaceLifting on LGL nodes = copy of the boundary node (prolongtoface.t90:270-303);
+        //      BR2 adds eta*L_Minus(0)*sJ*Flux*L_HatMinus(0) of the side itself to the volume-only value ----
 #pragma unroll
         for (int ls = 1; ls <= 6; ++ls) {
           if (onFace[ls - 1]) {
@@ -342,12 +381,27 @@ __global__ void __launch_bounds__(VolGLCfg<NP, KPT, SPLIT, PARA>::NT, VolGLCfg<N
             double* const d1 = master ? A.gm[1] : A.gs[1];
             double* const d2 = master ? A.gm[2] : A.gs[2];
             const size_t o0 = (size_t)(fd & 0x7fffffff);
+            if (LIFT == 1) {
 #pragma unroll
-            for (int v = 0; v < NVL; ++v) {
-              const size_t o = o0 + (size_t)v * D::NP2;
-              d0[o] = gx[v];
-              d1[o] = gy[v];
-              d2[o] = gz[v];
+              for (int v = 0; v < NVL; ++v) {
+                const size_t o = o0 + (size_t)v * D::NP2;
+                d0[o] = gx[v];
+                d1[o] = gy[v];
+                d2[o] = gz[v];
+              }
+            } else {
+              const double* of = sX + (ls - 1) * 9 * D::NP2 + abFace[ls - 1];
+              const double n0 = of[5 * D::NP2], n1 = of[6 * D::NP2], n2 = of[7 * D::NP2];
+              const double w = sEta[ls - 1] * sB[D::O_LM];
+              const double lh = sB[D::O_LHM];
+#pragma unroll
+              for (int v = 0; v < NVL; ++v) {
+                const size_t o = o0 + (size_t)v * D::NP2;
+                const double f = of[v * D::NP2];
+                d0[o] = gxo[v] + w * (sJ[c] * (f * n0) * lh);
+                d1[o] = gyo[v] + w * (sJ[c] * (f * n1) * lh);
+                d2[o] = gzo[v] + w * (sJ[c] * (f * n2) * lh);
+              }
             }
           }
         }

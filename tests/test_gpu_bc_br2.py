@@ -1,0 +1,111 @@
+"""CUDA path vs oracle for the rows of SURVEY.md 8(a) beyond the periodic BR1 case: BR2 lifting (a7), boundary conditions
+(a21: Dirichlet/exact function, adiabatic / isothermal no-slip walls, slip wall) and the manufactured-solution source (a16),
+incl. BASELINE config 4 flavour (curved mesh with walls + far field, N=5, HLLC + BR2) and config 3 flavour (convtest)."""
+import numpy as np
+import pytest
+
+from flexi_b200.gpu import FlexiGpu
+from flexi_b200.hostmesh import basis as B
+from flexi_b200.hostmesh.case import build_case
+from flexi_b200.hostmesh.mesh import BoxSpec
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+G, GL = B.NODE_GAUSS, B.NODE_GAUSS_LOBATTO
+BOX = dict(x0=(-1.0, -1.0, -1.0), length=(2.0, 2.0, 2.0))
+CURVED = dict(ngeo=2, deform=0.1, **BOX)
+REF = (1.0, 0.3, 0.0, 0.0, 0.71428571)
+
+
+def check(ranks, U0, t=0.0, steps=2, tol=1e-12):
+    r = ranks[0]
+    w = O.OracleWorld([(r.desc, r.keep)])
+    w.set_state([U0])
+    g = FlexiGpu(r)
+    try:
+        g.set_state(U0)
+        w.dg_time_derivative(t)
+        ut = g.DGTimeDerivative_weakForm(t)
+        o = w.ranks[0]
+        ref = o.array("Ut")
+        d = np.max(np.abs(ut - ref).reshape(-1, 5), axis=0)
+        scale = np.max(np.abs(ref).reshape(-1, 5), axis=0)
+        scale[1:4] = scale[1:4].max()
+        assert np.all(d <= tol * np.maximum(scale, 1e-3 * scale.max())), (d, scale)
+        nbc = r.mesh.nBCSides
+        fs = np.max(np.abs(o.array("Flux")))
+        assert np.max(np.abs(g.get_array("Flux") - o.array("Flux"))) <= tol * fs
+        if r.desc.parabolic:
+            gs = max(np.max(np.abs(o.array(n))) for n in ("gradUx", "gradUy", "gradUz"))
+            for name in ("gradUx", "gradUy", "gradUz", "gradUx_master", "gradUy_master", "gradUz_master"):
+                assert np.max(np.abs(g.get_array(name) - o.array(name))) <= tol * gs, name
+            for name in ("gradUx_slave", "gradUy_slave", "gradUz_slave"):
+                assert np.max(np.abs(g.get_array(name)[nbc:] - o.array(name)[nbc:])) <= tol * gs, name
+        tt = t
+        for _ in range(steps):
+            dt = w.calc_timestep()[0]
+            assert abs(g.CalcTimeStep()[0] - dt) <= 1e-13 * dt
+            w.timestep(tt, dt)
+            g.TimeStep(tt, dt)
+            tt += dt
+        Ug, Uo = g.get_state(), o.array("U")
+        sc = np.max(np.abs(Uo).reshape(-1, 5), axis=0)
+        assert np.all(np.max(np.abs(Ug - Uo).reshape(-1, 5), axis=0) <= tol * sc)
+    finally:
+        g.close()
+        w.close()
+
+
+@pytest.mark.parametrize("N,node,eqn", [
+    (3, G, dict(riemann="roe")),
+    (4, GL, dict(riemann="lf")),
+    (5, G, dict(riemann="hllc", n_var_lifting=4)),
+    (7, GL, dict(riemann="roeentropyfix", split_dg=True, split_dg_type="pi")),
+    (5, GL, dict(riemann="lf", split_dg=True, split_dg_type="kg", n_var_lifting=4, eta_br2=1.5)),
+    (9, G, dict(riemann="hll")),
+])
+def test_br2_periodic_curved(N, node, eqn):
+    ranks = build_case(BoxSpec((3, 2, 2), **CURVED), N, node, dict(parabolic=True, lifting=2, mu0=1e-2, **eqn))
+    r = ranks[0]
+    check(ranks, r.eqn.smooth_state(r.mesh.Elem_xGP, length=2.0))
+
+
+def wall_farfield_box(curved=True):
+    """config 4 flavour: curved box, no-slip walls at y=-1 / slip wall at y=+1, Dirichlet far field in x, periodic in z."""
+    bc = {(1, -1): 1, (1, 1): 2, (0, -1): 3, (0, 1): 3}
+    kw = CURVED if curved else BOX
+    return BoxSpec((3, 2, 2), periodic=(False, False, True), bc_of_face=bc, **kw)
+
+
+@pytest.mark.parametrize("N,node,lifting,wall,riemann", [
+    (5, G, 2, 3, "hllc"),     # BASELINE config 4: N=5, HLLC + BR2, adiabatic wall
+    (5, GL, 2, 4, "roe"),     # isothermal wall
+    (4, G, 1, 4, "lf"),
+    (3, GL, 1, 3, "roeentropyfix"),
+])
+def test_walls_and_farfield_on_curved_mesh(N, node, lifting, wall, riemann):
+    eqn = dict(parabolic=True, lifting=lifting, riemann=riemann, mu0=1e-2, eta_br2=2.0, eta_br2_wall=3.0,
+               boundary_type=[(wall, 2, 0), (9, 0, 0), (2, 1, 0)], ref_state_prim=[REF, (1.0, 0.0, 0.0, 0.0, 0.9)])
+    ranks = build_case(wall_farfield_box(), N, node, eqn)
+    r = ranks[0]
+    check(ranks, r.eqn.smooth_state(r.mesh.Elem_xGP, length=2.0))
+
+
+@pytest.mark.parametrize("N,node,parabolic,lifting", [(3, G, True, 1), (5, GL, True, 2), (7, G, False, 1), (9, GL, True, 1), (4, GL, False, 1)])
+def test_convtest_exactfunc4_with_source(N, node, parabolic, lifting):
+    """config 3 flavour (convtest/p_3D): ExactFunc 4 + CalcSource with exact-function Dirichlet BCs, Gauss and Gauss-Lobatto,
+    Euler and Navier-Stokes, at a stage time t != 0."""
+    bc = {(a, s): 1 for a in range(3) for s in (-1, 1)}
+    eqn = dict(parabolic=parabolic, lifting=lifting, riemann="roeentropyfix", mu0=1e-3, boundary_type=[(2, 0, 0)], ref_state_prim=[REF],
+               ini_exact_func=4, do_calc_source=True, adv_vel=(0.3, 0.3, 0.3))
+    ranks = build_case(BoxSpec((2, 2, 2), periodic=(False,) * 3, bc_of_face=bc, **BOX), N, node, eqn)
+    r = ranks[0]
+    check(ranks, r.eqn.exact_func4(r.mesh.Elem_xGP, 0.05), t=0.05)
+
+
+def test_unsupported_boundary_type_is_refused():
+    bc = {(0, -1): 1, (0, 1): 1}
+    eqn = dict(parabolic=False, boundary_type=[(27, 1, 0)], ref_state_prim=[REF])
+    r = build_case(BoxSpec((2, 2, 2), periodic=(False, True, True), bc_of_face=bc, **BOX), 2, G, eqn)[0]
+    with pytest.raises(Exception, match="boundary type 27"):
+        FlexiGpu(r)
