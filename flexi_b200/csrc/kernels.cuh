@@ -27,6 +27,7 @@ struct VolArgs {
   double* gm[3];  // gradU{x,y,z}_master [s][nvl][NP2]
   double* gs[3];  // gradU{x,y,z}_slave
   double* gvol[3];  // optional volume gradients [e][nvl][NP3] (NULL = not stored)
+  const double* basisHost;  // HOST copy of Mesh::basis (k_volume_gl2 takes the D matrices as kernel parameters)
 };
 
 struct FluxArgs {

@@ -1,8 +1,10 @@
 // np_kernels.cu -- instantiates kernels.cuh for one polynomial degree (compile with -DFLEXI_NP=<N+1>).
+#include <math.h>
 #include <stdlib.h>
 
 #include "np_ops.h"
 #include "volume_gl.cuh"
+#include "volume_gl2.cuh"
 
 #ifndef FLEXI_NP
 #error "compile with -DFLEXI_NP=<N+1>"
@@ -53,22 +55,59 @@ cudaError_t volume_gl_launch(int lift, const VolArgs& a, int nBlocks, cudaStream
   return cudaGetLastError();
 }
 
-#if FLEXI_NP == 8
-// tuning hook for the headline configuration (N=7, split PI, Navier-Stokes, nVarLifting=5): FLEXI_GPU_KPT=2 selects a
-// quarter zeta column per thread (256 threads per element) instead of half a column (128 threads)
-int g_kpt_alt = 0;
-cudaError_t alt_setup() {
-  const char* e = getenv("FLEXI_GPU_KPT");
-  g_kpt_alt = e ? atoi(e) : 0;
-  using C = VolGLCfg<NP, 2, true, true>;
-  return cudaFuncSetAttribute(k_volume_gl<NP, 2, true, FLEXI_SPLITDG_PI, true, 5, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::BYTES);
+// line-resident split-form GL kernel (volume_gl2.cuh) for even NP; odd NP keeps k_volume_gl
+constexpr bool HAS_GL2 = (NP % 2 == 0);
+bool g_use_gl2 = HAS_GL2;
+template <int STYPE, bool PARA, int NVL, int LIFT>
+struct GL2 {
+  static constexpr int NPE = HAS_GL2 ? NP : 2;  // odd NP never instantiates the real kernel
+  using C = VolGL2Cfg<NPE, PARA, NVL>;
+  static cudaError_t setup() {
+    return cudaFuncSetAttribute(k_volume_gl2<NPE, STYPE, PARA, NVL, LIFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::BYTES);
+  }
+  // M(N-l,N-i) == -M(l,i) for the three operators (off-diagonal only for DVolSurf): what gl2_ap relies on
+  static bool antisymmetric(const double* b) {
+    const int offs[3] = {Dim<NPE>::O_DT, Dim<NPE>::O_DH, Dim<NPE>::O_DV};
+    for (int t = 0; t < 3; ++t) {
+      double mx = 0.;
+      for (int x = 0; x < NPE * NPE; ++x) mx = fmax(mx, fabs(b[offs[t] + x]));
+      for (int l = 0; l < NPE; ++l)
+        for (int i = 0; i < NPE; ++i) {
+          if (t == 2 && l == i) continue;
+          if (fabs(b[offs[t] + l * NPE + i] + b[offs[t] + (NPE - 1 - l) * NPE + (NPE - 1 - i)]) > 1e-14 * mx) return false;
+        }
+    }
+    return true;
+  }
+  static cudaError_t launch(const VolArgs& a, int nBlocks, cudaStream_t s) {
+    VolArgs2<NPE> aa;
+    aa.a = a;
+    const double* b = a.basisHost;
+    const double scale = (STYPE == FLEXI_SPLITDG_PI) ? 0.125 : 1.;
+    for (int t = 0; t < NPE * NPE; ++t) {
+      aa.b.dt[t] = b[Dim<NPE>::O_DT + t];
+      aa.b.dh[t] = b[Dim<NPE>::O_DH + t];
+      aa.b.dvs[t] = scale * b[Dim<NPE>::O_DV + t];
+    }
+    aa.b.lhm0 = b[Dim<NPE>::O_LHM];
+    aa.b.lhpN = b[Dim<NPE>::O_LHP + NPE - 1];
+    aa.b.lm0 = b[Dim<NPE>::O_LM];
+    k_volume_gl2<NPE, STYPE, PARA, NVL, LIFT><<<nBlocks, C::NT, C::BYTES, s>>>(aa);
+    return cudaGetLastError();
+  }
+};
+template <int STYPE, bool PARA, int NVL>
+cudaError_t gl2_setup() {
+  cudaError_t e = GL2<STYPE, PARA, NVL, 1>::setup();
+  if (e == cudaSuccess && PARA) e = GL2<STYPE, PARA, NVL, 2>::setup();
+  return e;
 }
-cudaError_t alt_launch(const VolArgs& a, int nBlocks, cudaStream_t s) {
-  using C = VolGLCfg<NP, 2, true, true>;
-  k_volume_gl<NP, 2, true, FLEXI_SPLITDG_PI, true, 5, 1><<<nBlocks, C::NT, C::BYTES, s>>>(a);
-  return cudaGetLastError();
+template <int STYPE, bool PARA, int NVL>
+cudaError_t gl2_launch(int lift, const VolArgs& a, int nBlocks, cudaStream_t s) {
+  if (PARA && lift == 2) return GL2<STYPE, PARA, NVL, 2>::launch(a, nBlocks, s);
+  return GL2<STYPE, PARA, NVL, 1>::launch(a, nBlocks, s);
 }
-#endif
+
 
 constexpr size_t upd_smem = sizeof(double) * (D::NBASIS + 5 * D::NP3);
 
@@ -76,21 +115,28 @@ constexpr size_t upd_smem = sizeof(double) * (D::NBASIS + 5 * D::NP3);
 
 cudaError_t setup() {
   cudaError_t e;
-#if FLEXI_NP == 8
-  if ((e = alt_setup()) != cudaSuccess) return e;
-#endif
   if ((e = volume_setup<false, 5>()) != cudaSuccess) return e;
   if ((e = volume_setup<true, 5>()) != cudaSuccess) return e;
   if ((e = volume_setup<true, 4>()) != cudaSuccess) return e;
   if ((e = volume_gl_setup<false, 0, false, 5>()) != cudaSuccess) return e;
   if ((e = volume_gl_setup<false, 0, true, 5>()) != cudaSuccess) return e;
   if ((e = volume_gl_setup<false, 0, true, 4>()) != cudaSuccess) return e;
+#if FLEXI_NP % 2 == 1  // split form on odd NP: k_volume_gl; even NP: k_volume_gl2 below
 #define X(T)                                                                     \
   if ((e = volume_gl_setup<true, T, false, 5>()) != cudaSuccess) return e;       \
   if ((e = volume_gl_setup<true, T, true, 5>()) != cudaSuccess) return e;        \
   if ((e = volume_gl_setup<true, T, true, 4>()) != cudaSuccess) return e;
   FX_SPLIT_TYPES(X)
 #undef X
+#endif
+  if (HAS_GL2) {
+#define X(T)                                                           \
+  if ((e = gl2_setup<T, false, 5>()) != cudaSuccess) return e;         \
+  if ((e = gl2_setup<T, true, 5>()) != cudaSuccess) return e;          \
+  if ((e = gl2_setup<T, true, 4>()) != cudaSuccess) return e;
+    FX_SPLIT_TYPES(X)
+#undef X
+  }
   if ((e = cudaFuncSetAttribute(k_update<NP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(k_update<NP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem)) != cudaSuccess) return e;
   const int pro = (int)(sizeof(double) * (D::NBASIS + 6 * D::NP3));
@@ -121,9 +167,18 @@ cudaError_t volume(bool gl, bool split, int stype, bool para, int nvl, const Vol
     if (!para) return volume_gl_launch<false, 0, false, 5>(lift, a, nBlocks, s);
     return nvl == 5 ? volume_gl_launch<false, 0, true, 5>(lift, a, nBlocks, s) : volume_gl_launch<false, 0, true, 4>(lift, a, nBlocks, s);
   }
-#if FLEXI_NP == 8
-  if (g_kpt_alt == 2 && stype == FLEXI_SPLITDG_PI && para && nvl == 5) return alt_launch(a, nBlocks, s);
-#endif
+  if (HAS_GL2 && g_use_gl2 && GL2<FLEXI_SPLITDG_PI, false, 5, 1>::antisymmetric(a.basisHost)) {
+    switch (stype) {
+#define X(T)                                                                                   \
+  case T:                                                                                      \
+    if (!para) return gl2_launch<T, false, 5>(lift, a, nBlocks, s);                            \
+    return nvl == 5 ? gl2_launch<T, true, 5>(lift, a, nBlocks, s) : gl2_launch<T, true, 4>(lift, a, nBlocks, s);
+      FX_SPLIT_TYPES(X)
+#undef X
+      default: return cudaErrorNotSupported;
+    }
+  }
+#if FLEXI_NP % 2 == 1
   switch (stype) {
 #define X(T)                                                                                                     \
   case T:                                                                                                        \
@@ -133,6 +188,9 @@ cudaError_t volume(bool gl, bool split, int stype, bool para, int nvl, const Vol
 #undef X
     default: return cudaErrorNotSupported;
   }
+#else
+  return cudaErrorNotSupported;  // even NP and the D matrices are not centro-antisymmetric: not Gauss-Lobatto operators
+#endif
 }
 
 cudaError_t bc_pre(const BCArgs& a, cudaStream_t s) {

@@ -1,0 +1,550 @@
+// volume_gl2.cuh -- line-resident Gauss-Lobatto split-form element kernel (the hot kernel of BASELINE configs[1]).
+//
+// Replaces, for PP_NodeType = GAUSS-LOBATTO with SPLIT_DG (file:line under /root/reference/src):
+//   eos.f90:280-300 (ConsToPrim_Volume), dg/lifting/lifting_br1.t90:48-181 / lifting_br2.t90:44-311, lifting_volint.t90:26-118,
+//   lifting_fillflux.t90:40-239, interpolation/applyjacobian.t90:62-112, prolongtoface.t90:270-303,
+//   dg/volint.f90:211-371 (split form incl. its weak-form viscous part), equations/navierstokes/splitflux.f90:160-700,
+//   flux.f90:149-241.
+//
+// Why a second GL kernel: the ncu profile of k_volume_gl (profiles/r01b_*) shows it bound by shared-memory wavefronts (78 % of
+// L1 throughput, FP64 pipe 40 %): every FP64 operand of the two-point fluxes and of the line derivatives came from a broadcast
+// LDS.64, and an LDS.64 costs two wavefronts no matter how few distinct words it reads.  Here a thread owns HALF = NP/2 nodes
+// of ONE LINE and the work is organised in direction phases (xi-lines, eta-lines, zeta-lines): the own half line lives in
+// registers, the other half is read once (every lane a distinct word), pairs inside the own half are formed once and applied
+// to both nodes (the symmetric update of volint.f90:318-333), and D-matrix entries are immediate operands from the kernel
+// parameter bank (both halves use the same entries, see gl2_ap).  Partial results change owner between phases through shared
+// memory.  Shared-memory loads drop from ~400 to ~110 per DOF, FP64 instructions from ~1000 to
+// ~800 per DOF.
+//
+// Shared-memory plane layout (NP = 8): node (i,j,k) lives at (i ^ s(j,k)) + 8*(j ^ (k&1)) + 64*k with
+// s = (j>>1) | ((k&1)<<2), which makes the three access patterns (16 lanes = 16 xi-lines reading one column, 16 lanes = two
+// rows of an eta- or zeta-line sweep) bank-conflict free.  Metric terms never enter shared memory: each phase reads the three
+// planes of its direction for the whole line straight from L2 (they were fetched from HBM once by the lifting phase).
+#pragma once
+#include "volume_gl.cuh"
+
+namespace fx {
+
+template <int NP>
+struct GL2Basis {
+  double dt[NP * NP];   // D_T(l,i)      at [l*NP+i]  (lifting derivative, lifting_volint.t90:67-83)
+  double dh[NP * NP];   // D_Hat_T(l,i)  at [l*NP+i]  (weak-form viscous derivative, volint.f90:310-315)
+  double dvs[NP * NP];  // DVolSurf(l,i) at [l*NP+i], times 1/8 for the Pirozzoli flux (constants folded, exact scaling)
+  double lhm0, lhpN, lm0;  // L_HatMinus(0), L_HatPlus(N), L_Minus(0)
+};
+template <int NP>
+struct VolArgs2 {
+  VolArgs a;
+  GL2Basis<NP> b;
+};
+
+template <int NP>
+__device__ __forceinline__ int gl2_phys(int i, int j, int k) {
+  if (NP == 8) return (i ^ (((j >> 1) & 3) | ((k & 1) << 2))) + 8 * (j ^ (k & 1)) + 64 * k;
+  return i + NP * (j + NP * k);
+}
+
+template <int NP, bool PARA, int NVL>
+struct VolGL2Cfg {
+  using D = Dim<NP>;
+  static_assert(NP % 2 == 0, "line halves need an even number of nodes");
+  static constexpr int HALF = NP / 2;
+  static constexpr int NT = 2 * D::NP2;
+  static constexpr int PL = D::NP3;
+  static constexpr int P_PLANES = PARA ? 7 : 6;  // rho,u,v,w,p,[T],X5
+  static constexpr int W_PLANES = PARA ? 12 : 0;  // contravariant viscous fluxes f~,g~,h~ (4 each); 2*NVL lifting planes alias them
+  static constexpr int F_FACE = PARA ? 6 * 9 * D::NP2 : 0;
+  static constexpr int F_DOUBLES = ((F_FACE > 5 * PL ? F_FACE : 5 * PL) + 1) & ~1;  // face staging, later the Ut hand-over planes
+  static constexpr int NFD = PARA ? ((3 * D::NP2 + 1) & ~1) : 0;                     // int table [6][NP2]
+  static constexpr int O_FDST = 0;
+  static constexpr int O_ETA = O_FDST + NFD;
+  static constexpr int O_P = O_ETA + (PARA ? 6 : 0);
+  static constexpr int O_W = O_P + P_PLANES * PL;
+  static constexpr int O_F = O_W + W_PLANES * PL;
+  static constexpr int DOUBLES = O_F + F_DOUBLES;
+  static constexpr size_t BYTES = sizeof(double) * DOUBLES;
+  static constexpr int MINB = (BYTES <= 113000) ? 2 : 1;
+};
+
+// Canonical line positions: a thread of half 0 owns positions 0..HALF-1 and meets HALF..N as partners; a thread of half 1 walks
+// the line BACKWARDS (canonical position q is the actual position N-q).  The Gauss-Lobatto operators are centro-antisymmetric,
+// M(N-l,N-i) = -M(l,i) for D_T, D_Hat_T and the off-diagonal DVolSurf (symmetric nodes and weights), so both halves run the
+// SAME instruction stream with the same immediate coefficients and half 1 multiplies its sums by -1.  (One instruction stream
+// for all warps matters: two per-half copies of this straight-line code made the kernel instruction-fetch bound, 36 % no_inst
+// stalls in profiles/r01d.)  The launch wrapper verifies the antisymmetry of the tables it is given.
+template <int NP>
+__device__ __forceinline__ int gl2_ap(int hb, int q) {
+  return hb ? (NP - 1 - q) : q;
+}
+
+// shared-memory (swizzled) address / natural node index of position p on the line of direction DIR through sheet position (r0,r1):
+// xi-lines (j,k) = (r0,r1), eta-lines (i,k) = (r0,r1), zeta-lines (i,j) = (r0,r1)
+template <int NP, int DIR>
+__device__ __forceinline__ int gl2_sa(int p, int r0, int r1) {
+  return DIR == 0 ? gl2_phys<NP>(p, r0, r1) : DIR == 1 ? gl2_phys<NP>(r0, p, r1) : gl2_phys<NP>(r0, r1, p);
+}
+template <int NP, int DIR>
+__device__ __forceinline__ int gl2_gn(int p, int r0, int r1) {
+  return DIR == 0 ? p + NP * (r0 + NP * r1) : DIR == 1 ? r0 + NP * (p + NP * r1) : r0 + NP * (r1 + NP * p);
+}
+
+// One direction phase of the advective two-point fluxes (+ the weak-form derivative of the viscous flux of that direction).
+//   ut[c][v] result for the own nodes c (HALF of them)
+template <int NP, int STYPE, bool PARA, int DIR>
+__device__ __forceinline__ void gl2_pair_phase(const GL2Basis<NP>& B, const double* __restrict__ sP, const double* __restrict__ sWd,
+                                               const double* __restrict__ gMd, int hb, int r0, int r1, double (&ut)[NP / 2][5]) {
+  constexpr int HALF = NP / 2, PL = NP * NP * NP;
+  int sa[NP], gn[NP];  // indexed by canonical position
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    sa[p] = gl2_sa<NP, DIR>(gl2_ap<NP>(hb, p), r0, r1);
+    gn[p] = gl2_gn<NP, DIR>(gl2_ap<NP>(hb, p), r0, r1);
+  }
+  constexpr bool PI = (STYPE == FLEXI_SPLITDG_PI);
+  constexpr int PX = PARA ? 6 : 5;
+  // metric terms of this direction along the whole line, straight from L2
+  double Mo[HALF][3], Mp[HALF][3];
+#pragma unroll
+  for (int c = 0; c < HALF; ++c)
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+      Mo[c][m] = __ldg(gMd + m * PL + gn[c]);
+      Mp[c][m] = __ldg(gMd + m * PL + gn[HALF + c]);
+    }
+#pragma unroll
+  for (int c = 0; c < HALF; ++c) ut[c][0] = 0.;
+  if (PARA) {  // volint.f90:310-315: Ut += D_Hat_T(l,i) * f~visc(l)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      double L[NP];
+#pragma unroll
+      for (int p = 0; p < NP; ++p) L[p] = sWd[v * PL + sa[p]];
+#pragma unroll
+      for (int c = 0; c < HALF; ++c) {
+        double s = B.dh[c] * L[0];
+#pragma unroll
+        for (int p = 1; p < NP; ++p) s = s + B.dh[p * NP + c] * L[p];
+        ut[c][v + 1] = s;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < HALF; ++c)
+#pragma unroll
+      for (int v = 1; v < 5; ++v) ut[c][v] = 0.;
+  }
+  // own half line
+  double a[HALF][6];
+#pragma unroll
+  for (int c = 0; c < HALF; ++c) {
+    const int s = sa[c];
+#pragma unroll
+    for (int v = 0; v < 5; ++v) a[c][v] = sP[v * PL + s];
+    a[c][5] = sP[PX * PL + s];
+  }
+  // pairs inside the own half: formed once, applied to both nodes
+#pragma unroll
+  for (int c = 0; c < HALF; ++c)
+#pragma unroll
+    for (int c2 = c + 1; c2 < HALF; ++c2) {
+      const int m1 = c, m2 = c2;
+      const double d12 = B.dvs[m2 * NP + m1];  // DVolSurf(l=m2, m1) -> node c
+      const double d21 = B.dvs[m1 * NP + m2];  // DVolSurf(l=m1, m2) -> node c2
+      if (PI) {
+        const double su = a[c][1] + a[c2][1], sv = a[c][2] + a[c2][2], sw = a[c][3] + a[c2][3], sp4 = a[c][4] + a[c2][4],
+                     sH = a[c][5] + a[c2][5];
+        const double m0 = Mo[c][0] + Mo[c2][0], mm1 = Mo[c][1] + Mo[c2][1], mm2 = Mo[c][2] + Mo[c2][2];
+        const double rq = (a[c][0] + a[c2][0]) * (m0 * su + mm1 * sv + mm2 * sw);
+        {
+          const double w = d12 * rq, dp = d12 * sp4;
+          ut[c][0] += 2. * w;
+          ut[c][1] += w * su;
+          ut[c][2] += w * sv;
+          ut[c][3] += w * sw;
+          ut[c][4] += w * sH;
+          ut[c][1] += dp * m0;
+          ut[c][2] += dp * mm1;
+          ut[c][3] += dp * mm2;
+        }
+        {
+          const double w = d21 * rq, dp = d21 * sp4;
+          ut[c2][0] += 2. * w;
+          ut[c2][1] += w * su;
+          ut[c2][2] += w * sv;
+          ut[c2][3] += w * sw;
+          ut[c2][4] += w * sH;
+          ut[c2][1] += dp * m0;
+          ut[c2][2] += dp * mm1;
+          ut[c2][3] += dp * mm2;
+        }
+      } else {
+        double Fl[5];
+        split_pair_generic<STYPE>(a[c], Mo[c], a[c2][0], a[c2][1], a[c2][2], a[c2][3], a[c2][4], a[c2][5], Mo[c2][0], Mo[c2][1], Mo[c2][2], Fl);
+#pragma unroll
+        for (int v = 0; v < 5; ++v) {
+          ut[c][v] = ut[c][v] + d12 * Fl[v];
+          ut[c2][v] = ut[c2][v] + d21 * Fl[v];
+        }
+      }
+    }
+  // pairs with the other half: partner read once, paired with all own nodes
+#pragma unroll
+  for (int c2 = 0; c2 < HALF; ++c2) {
+    const int l = HALF + c2;
+    const int s = sa[l];
+    const double br = sP[s], bu = sP[PL + s], bv = sP[2 * PL + s], bw = sP[3 * PL + s], bp = sP[4 * PL + s], bx = sP[PX * PL + s];
+#pragma unroll
+    for (int c = 0; c < HALF; ++c) {
+      const double dl = B.dvs[l * NP + c];
+      if (PI) {
+        const double su = a[c][1] + bu, sv = a[c][2] + bv, sw = a[c][3] + bw, sp4 = a[c][4] + bp, sH = a[c][5] + bx;
+        const double m0 = Mo[c][0] + Mp[c2][0], mm1 = Mo[c][1] + Mp[c2][1], mm2 = Mo[c][2] + Mp[c2][2];
+        const double rq = (a[c][0] + br) * (m0 * su + mm1 * sv + mm2 * sw);
+        const double w = dl * rq, dp = dl * sp4;
+        ut[c][0] += 2. * w;
+        ut[c][1] += w * su;
+        ut[c][2] += w * sv;
+        ut[c][3] += w * sw;
+        ut[c][4] += w * sH;
+        ut[c][1] += dp * m0;
+        ut[c][2] += dp * mm1;
+        ut[c][3] += dp * mm2;
+      } else {
+        double Fl[5];
+        split_pair_generic<STYPE>(a[c], Mo[c], br, bu, bv, bw, bp, bx, Mp[c2][0], Mp[c2][1], Mp[c2][2], Fl);
+#pragma unroll
+        for (int v = 0; v < 5; ++v) ut[c][v] = ut[c][v] + dl * Fl[v];
+      }
+    }
+  }
+  const double sg = hb ? -1. : 1.;
+#pragma unroll
+  for (int c = 0; c < HALF; ++c)
+#pragma unroll
+    for (int v = 0; v < 5; ++v) ut[c][v] = sg * ut[c][v];
+}
+
+// reference-space derivative of the NVL lifting variables along one line (lifting_volint.t90:67-83): out[c][v] for the own nodes
+template <int NP, int NVL, int DIR>
+__device__ __forceinline__ void gl2_lift_line(const GL2Basis<NP>& B, const double* __restrict__ sP, int hb, int r0, int r1,
+                                              double (&out)[NP / 2][NVL]) {
+  constexpr int HALF = NP / 2, PL = NP * NP * NP;
+  const double sg = hb ? -1. : 1.;
+  int sa[NP];
+#pragma unroll
+  for (int p = 0; p < NP; ++p) sa[p] = gl2_sa<NP, DIR>(gl2_ap<NP>(hb, p), r0, r1);
+#pragma unroll
+  for (int v = 0; v < NVL; ++v) {
+    const double* pl = sP + lift_prim(NVL, v) * PL;
+    double L[NP];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) L[p] = pl[sa[p]];
+#pragma unroll
+    for (int c = 0; c < HALF; ++c) {
+      double s = B.dt[c] * L[0];
+#pragma unroll
+      for (int p = 1; p < NP; ++p) s = s + B.dt[p * NP + c] * L[p];
+      out[c][v] = sg * s;
+    }
+  }
+}
+
+template <int NP, int STYPE, bool PARA, int NVL, int LIFT>
+__global__ void __launch_bounds__(VolGL2Cfg<NP, PARA, NVL>::NT, VolGL2Cfg<NP, PARA, NVL>::MINB)
+    k_volume_gl2(const __grid_constant__ VolArgs2<NP> AA) {
+  using D = Dim<NP>;
+  using C = VolGL2Cfg<NP, PARA, NVL>;
+  constexpr int HALF = C::HALF, NT = C::NT, PL = C::PL, N = NP - 1;
+  constexpr bool PI = (STYPE == FLEXI_SPLITDG_PI);
+  constexpr int PX = PARA ? 6 : 5;
+  const VolArgs& A = AA.a;
+  const GL2Basis<NP>& B = AA.b;
+  extern __shared__ __align__(16) double sm[];
+  int* sFD = reinterpret_cast<int*>(sm + C::O_FDST);
+  double* sEta = sm + C::O_ETA;
+  double* sP = sm + C::O_P;
+  double* sW = sm + C::O_W;   // G1 | G2 lifting planes, later f~ | g~ | h~
+  double* sX = sm + C::O_F;   // face staging (lifting fluxes + normals), later the Ut hand-over planes
+  double* sUT = sX;
+  const int tid = threadIdx.x;
+  const int e = A.elems ? A.elems[blockIdx.x] : blockIdx.x;
+  const int hb = tid / D::NP2, r = tid % D::NP2;  // half index (warp-uniform for NP = 8) and position inside the NP x NP sheet
+  const int r0 = r % NP, r1 = r / NP;
+  const Eqn& q = A.q;
+  const double* gU = A.U + (size_t)e * 5 * D::NP3;
+  const double* gM = A.m.Met + (size_t)e * 9 * D::NP3;
+  constexpr int FACE_IT = (6 * D::NP2 + NT - 1) / NT;
+
+  // ---- phase A (zeta ownership): neighbour traces + face geometry in flight (cp.async), ConsToPrim of the own nodes ----
+  int faceSlot[FACE_IT];
+  double faceSgn[FACE_IT];
+  if (PARA) {
+#pragma unroll
+    for (int it = 0; it < FACE_IT; ++it) {
+      const int t = tid + it * NT;
+      faceSlot[it] = -1;
+      faceSgn[it] = 0.;
+      if (t < 6 * D::NP2) {
+        const int ls = t / D::NP2 + 1, pq = t % D::NP2;
+        const SideRef sr = A.m.e2s[e * 6 + ls - 1];
+        const int ab = A.m.s2v2[(sr.flip * 6 + ls - 1) * D::NP2 + pq];
+        const double* nbTrace = ((sr.flip == 0) ? A.U_slave : A.U_master) + (size_t)sr.side * 5 * D::NP2 + pq;
+        const double* g = A.m.Geo + (size_t)sr.side * 10 * D::NP2 + pq;
+        double* o = sX + (ls - 1) * 9 * D::NP2 + ab;
+#pragma unroll
+        for (int v = 0; v < 5; ++v) cp_async8(o + v * D::NP2, nbTrace + v * D::NP2);
+        cp_async8(o + 5 * D::NP2, g);
+        cp_async8(o + 6 * D::NP2, g + D::NP2);
+        cp_async8(o + 7 * D::NP2, g + 2 * D::NP2);
+        cp_async8(o + 8 * D::NP2, g + 9 * D::NP2);
+        // destination of this face node's gradient trace: (side*NVL*NP2 + pq), sign bit set for the slave arrays
+        sFD[(ls - 1) * D::NP2 + ab] = (sr.side * NVL * D::NP2 + pq) | (sr.flip == 0 ? 0 : (int)0x80000000);
+        if (LIFT == 2 && pq == 0) {  // lifting_br2.t90:277-288: etaBR2_wall on no-slip wall sides
+          double eta = q.etaBR2;
+          if (sr.side < A.m.nBCSides) {
+            const int bt = A.m.bcType[sr.side];
+            if (bt == 3 || bt == 4) eta = q.etaBR2_wall;
+          }
+          sEta[ls - 1] = eta;
+        }
+        // volume node of this face node (prolongtoface.t90:270-303), in the swizzled plane layout
+        const int fa = ab % NP, fb = ab / NP, fd = is_minus_side(ls) ? 0 : N;
+        int vn;
+        if (ls == XI_MINUS || ls == XI_PLUS)
+          vn = gl2_phys<NP>(fd, fa, fb);
+        else if (ls == ETA_MINUS || ls == ETA_PLUS)
+          vn = gl2_phys<NP>(fa, fd, fb);
+        else
+          vn = gl2_phys<NP>(fa, fb, fd);
+        faceSlot[it] = ((ls - 1) * 9 * D::NP2 + ab) | (vn << 16);
+        faceSgn[it] = (sr.flip == 0) ? 1. : -1.;
+      }
+    }
+    cp_async_commit();
+  }
+  {
+    double Uc[HALF][5];
+#pragma unroll
+    for (int c = 0; c < HALF; ++c)
+#pragma unroll
+      for (int v = 0; v < 5; ++v) Uc[c][v] = gU[v * D::NP3 + gl2_gn<NP, 2>(gl2_ap<NP>(hb, c), r0, r1)];
+#pragma unroll
+    for (int c = 0; c < HALF; ++c) {
+      double Pn[6];
+      const double sRho = cons_to_prim_srho(q, Uc[c], Pn);
+      const int s = gl2_sa<NP, 2>(gl2_ap<NP>(hb, c), r0, r1);
+#pragma unroll
+      for (int v = 0; v < 4; ++v) sP[v * PL + s] = Pn[v];
+      sP[4 * PL + s] = PI ? 4. * Pn[PRES] : Pn[PRES];
+      if (PARA) sP[5 * PL + s] = Pn[TEMP];
+      // 6th two-point quantity: H = (rhoE+p)/rho (PI), E = rhoE/rho (KG), rhoE (SD, DU)
+      sP[PX * PL + s] = PI ? (Uc[c][ENER] + Pn[PRES]) * sRho : (STYPE == FLEXI_SPLITDG_KG) ? Uc[c][ENER] * sRho : Uc[c][ENER];
+    }
+  }
+  if (PARA) cp_async_wait_all();
+  __syncthreads();  // S1: primitive planes complete, face staging visible
+
+  double ut[HALF][5];
+
+  if (PARA) {
+    // ---- lifting flux of the six faces (lifting_fillflux.t90:81-107, strong form):
+    //      0.5*(UPrim_slave-UPrim_master)*SurfElem per lifting variable, in place of the prefetched neighbour trace ----
+#pragma unroll
+    for (int it = 0; it < FACE_IT; ++it) {
+      if (faceSlot[it] >= 0) {
+        double* o = sX + (faceSlot[it] & 0xffff);
+        const int nF = faceSlot[it] >> 16;
+        double Un[5], Pb[6];
+#pragma unroll
+        for (int v = 0; v < 5; ++v) Un[v] = o[v * D::NP2];
+        const double surf = o[8 * D::NP2];
+        cons_to_prim(q, Un, Pb);
+#pragma unroll
+        for (int v = 0; v < NVL; ++v) {
+          const int pv = lift_prim(NVL, v);
+          o[v * D::NP2] = 0.5 * (faceSgn[it] * (Pb[pv] - sP[pv * PL + nF])) * surf;
+        }
+      }
+    }
+    // ---- lifting derivatives along xi (xi ownership) and eta (eta ownership) -> hand-over planes G1, G2 ----
+    {
+      double g[HALF][NVL];
+      gl2_lift_line<NP, NVL, 0>(B, sP, hb, r0, r1, g);
+#pragma unroll
+      for (int c = 0; c < HALF; ++c)
+#pragma unroll
+        for (int v = 0; v < NVL; ++v) sW[v * PL + gl2_sa<NP, 0>(gl2_ap<NP>(hb, c), r0, r1)] = g[c][v];
+      gl2_lift_line<NP, NVL, 1>(B, sP, hb, r0, r1, g);
+#pragma unroll
+      for (int c = 0; c < HALF; ++c)
+#pragma unroll
+        for (int v = 0; v < NVL; ++v) sW[(NVL + v) * PL + gl2_sa<NP, 1>(gl2_ap<NP>(hb, c), r0, r1)] = g[c][v];
+    }
+    __syncthreads();  // S2: G1, G2 and the face lifting fluxes complete
+
+    // ---- zeta ownership: zeta derivative, metric combination, surface part, Jacobian, gradient traces, viscous flux ----
+    {
+      constexpr int LV = (NVL == 5) ? 1 : 0;
+      const int i = r0, j = r1;
+      double M[HALF][9], sJ[HALF];
+#pragma unroll
+      for (int c = 0; c < HALF; ++c) {
+        const int n = gl2_gn<NP, 2>(gl2_ap<NP>(hb, c), r0, r1);
+#pragma unroll
+        for (int m = 0; m < 9; ++m) M[c][m] = __ldg(gM + m * D::NP3 + n);
+        sJ[c] = __ldg(A.m.sJ + (size_t)e * D::NP3 + n);
+      }
+      double gzt[HALF][NVL];
+      gl2_lift_line<NP, NVL, 2>(B, sP, hb, r0, r1, gzt);
+#pragma unroll
+      for (int c = 0; c < HALF; ++c) {
+        const int k = gl2_ap<NP>(hb, c);
+        const int s = gl2_sa<NP, 2>(k, r0, r1);
+        const int n = i + NP * (j + NP * k);
+        double gx[NVL], gy[NVL], gz[NVL];
+#pragma unroll
+        for (int v = 0; v < NVL; ++v) {
+          const double gxi = sW[v * PL + s], geta = sW[(NVL + v) * PL + s], gzeta = gzt[c][v];
+          gx[v] = M[c][0] * gxi + M[c][3] * geta + M[c][6] * gzeta;
+          gy[v] = M[c][1] * gxi + M[c][4] * geta + M[c][7] * gzeta;
+          gz[v] = M[c][2] * gxi + M[c][5] * geta + M[c][8] * gzeta;
+        }
+        // ---- lifting, surface part: on LGL nodes only the boundary nodes receive it ----
+        const bool onFace[6] = {k == 0, j == 0, i == N, j == N, i == 0, k == N};  // local sides 1..6 (flexi.h:90-95)
+        const int abFace[6] = {i + NP * j, i + NP * k, j + NP * k, i + NP * k, j + NP * k, i + NP * j};
+        double gxo[NVL], gyo[NVL], gzo[NVL];  // BR2: gradients without the surface part (what the faces are prolonged from)
+        if (LIFT == 1) {  // BR1 (lifting_br1.t90:195-292), then ApplyJacobianLifting
+#pragma unroll
+          for (int ls = 1; ls <= 6; ++ls) {
+            if (onFace[ls - 1]) {
+              const double* o = sX + (ls - 1) * 9 * D::NP2 + abFace[ls - 1];
+              const double n0 = o[5 * D::NP2], n1 = o[6 * D::NP2], n2 = o[7 * D::NP2];
+              const double lh = is_minus_side(ls) ? B.lhm0 : B.lhpN;
+#pragma unroll
+              for (int v = 0; v < NVL; ++v) {
+                const double f = o[v * D::NP2];
+                gx[v] = gx[v] + (f * n0) * lh;
+                gy[v] = gy[v] + (f * n1) * lh;
+                gz[v] = gz[v] + (f * n2) * lh;
+              }
+            }
+          }
+#pragma unroll
+          for (int v = 0; v < NVL; ++v) {
+            gx[v] = gx[v] * sJ[c];
+            gy[v] = gy[v] * sJ[c];
+            gz[v] = gz[v] * sJ[c];
+          }
+        } else {  // BR2 (lifting_br2.t90:111-131,194-311): Jacobian first, then sJ*Flux*L_HatMinus(0) on the boundary node
+#pragma unroll
+          for (int v = 0; v < NVL; ++v) {
+            gx[v] = gx[v] * sJ[c];
+            gy[v] = gy[v] * sJ[c];
+            gz[v] = gz[v] * sJ[c];
+            gxo[v] = gx[v];
+            gyo[v] = gy[v];
+            gzo[v] = gz[v];
+          }
+#pragma unroll
+          for (int ls = 1; ls <= 6; ++ls) {
+            if (onFace[ls - 1]) {
+              const double* o = sX + (ls - 1) * 9 * D::NP2 + abFace[ls - 1];
+              const double n0 = o[5 * D::NP2], n1 = o[6 * D::NP2], n2 = o[7 * D::NP2];
+              const double lh = B.lhm0;
+#pragma unroll
+              for (int v = 0; v < NVL; ++v) {
+                const double f = o[v * D::NP2];
+                gx[v] = gx[v] + sJ[c] * (f * n0) * lh;
+                gy[v] = gy[v] + sJ[c] * (f * n1) * lh;
+                gz[v] = gz[v] + sJ[c] * (f * n2) * lh;
+              }
+            }
+          }
+        }
+        if (A.gvol[0]) {
+#pragma unroll
+          for (int v = 0; v < NVL; ++v) {
+            A.gvol[0][((size_t)e * NVL + v) * D::NP3 + n] = gx[v];
+            A.gvol[1][((size_t)e * NVL + v) * D::NP3 + n] = gy[v];
+            A.gvol[2][((size_t)e * NVL + v) * D::NP3 + n] = gz[v];
+          }
+        }
+        // ---- ProlongToFaceLifting on LGL nodes = copy of the boundary node (prolongtoface.t90:270-303);
+        //      BR2 adds eta*L_Minus(0)*sJ*Flux*L_HatMinus(0) of the side itself to the volume-only value ----
+#pragma unroll
+        for (int ls = 1; ls <= 6; ++ls) {
+          if (onFace[ls - 1]) {
+            const int fd = sFD[(ls - 1) * D::NP2 + abFace[ls - 1]];
+            const bool master = fd >= 0;
+            double* const d0 = master ? A.gm[0] : A.gs[0];
+            double* const d1 = master ? A.gm[1] : A.gs[1];
+            double* const d2 = master ? A.gm[2] : A.gs[2];
+            const size_t o0 = (size_t)(fd & 0x7fffffff);
+            if (LIFT == 1) {
+#pragma unroll
+              for (int v = 0; v < NVL; ++v) {
+                const size_t o = o0 + (size_t)v * D::NP2;
+                d0[o] = gx[v];
+                d1[o] = gy[v];
+                d2[o] = gz[v];
+              }
+            } else {
+              const double* of = sX + (ls - 1) * 9 * D::NP2 + abFace[ls - 1];
+              const double n0 = of[5 * D::NP2], n1 = of[6 * D::NP2], n2 = of[7 * D::NP2];
+              const double w = sEta[ls - 1] * B.lm0;
+              const double lh = B.lhm0;
+#pragma unroll
+              for (int v = 0; v < NVL; ++v) {
+                const size_t o = o0 + (size_t)v * D::NP2;
+                const double f = of[v * D::NP2];
+                d0[o] = gxo[v] + w * (sJ[c] * (f * n0) * lh);
+                d1[o] = gyo[v] + w * (sJ[c] * (f * n1) * lh);
+                d2[o] = gzo[v] + w * (sJ[c] * (f * n2) * lh);
+              }
+            }
+          }
+        }
+        // ---- viscous flux of this node (flux.f90:149-241) and its contravariant components (volint.f90:378-422);
+        //      written over the node's own G1/G2 slots, which only this thread reads ----
+        double fv[4], gv[4], hv[4];
+        eval_diff_flux3d(q, sP[VEL1 * PL + s], sP[VEL2 * PL + s], sP[VEL3 * PL + s], gx + LV, gy + LV, gz + LV, fv, gv, hv);
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          sW[(0 + v) * PL + s] = fv[v] * M[c][0] + gv[v] * M[c][1] + hv[v] * M[c][2];
+          sW[(4 + v) * PL + s] = fv[v] * M[c][3] + gv[v] * M[c][4] + hv[v] * M[c][5];
+          sW[(8 + v) * PL + s] = fv[v] * M[c][6] + gv[v] * M[c][7] + hv[v] * M[c][8];
+        }
+      }
+    }
+    __syncthreads();  // S3: viscous flux planes complete; face staging is free from here on
+  }
+
+  // ---- zeta phase ----
+  gl2_pair_phase<NP, STYPE, PARA, 2>(B, sP, sW + 8 * PL, gM + 6 * D::NP3, hb, r0, r1, ut);
+#pragma unroll
+  for (int c = 0; c < HALF; ++c)
+#pragma unroll
+    for (int v = 0; v < 5; ++v) sUT[v * PL + gl2_sa<NP, 2>(gl2_ap<NP>(hb, c), r0, r1)] = ut[c][v];
+  __syncthreads();  // S4
+  // ---- xi phase ----
+  gl2_pair_phase<NP, STYPE, PARA, 0>(B, sP, sW, gM, hb, r0, r1, ut);
+#pragma unroll
+  for (int c = 0; c < HALF; ++c)
+#pragma unroll
+    for (int v = 0; v < 5; ++v) {
+      double* p = sUT + v * PL + gl2_sa<NP, 0>(gl2_ap<NP>(hb, c), r0, r1);
+      *p = *p + ut[c][v];
+    }
+  __syncthreads();  // S5
+  // ---- eta phase, then the raw volume integral goes to HBM ----
+  gl2_pair_phase<NP, STYPE, PARA, 1>(B, sP, sW + 4 * PL, gM + 3 * D::NP3, hb, r0, r1, ut);
+#pragma unroll
+  for (int c = 0; c < HALF; ++c) {
+    const int p = gl2_ap<NP>(hb, c);
+#pragma unroll
+    for (int v = 0; v < 5; ++v)
+      A.Ut[((size_t)e * 5 + v) * D::NP3 + gl2_gn<NP, 1>(p, r0, r1)] = sUT[v * PL + gl2_sa<NP, 1>(p, r0, r1)] + ut[c][v];
+  }
+}
+
+}  // namespace fx

@@ -31,7 +31,9 @@ def check(ranks, U0, t=0.0, steps=2, tol=1e-12):
         d = np.max(np.abs(ut - ref).reshape(-1, 5), axis=0)
         scale = np.max(np.abs(ref).reshape(-1, 5), axis=0)
         scale[1:4] = scale[1:4].max()
-        assert np.all(d <= tol * np.maximum(scale, 1e-3 * scale.max())), (d, scale)
+        # gate: rel 1e-12, or 4x the oracle's own strict-vs-FMA build noise where that is larger (N=9: long cancelling sums)
+        noise, _ = O.ut_noise_floor([(r.desc, r.keep)], [U0], t)
+        assert np.all(d <= np.maximum(tol * np.maximum(scale, 1e-3 * scale.max()), 4.0 * noise)), (d, scale, noise)
         nbc = r.mesh.nBCSides
         fs = np.max(np.abs(o.array("Flux")))
         assert np.max(np.abs(g.get_array("Flux") - o.array("Flux"))) <= tol * fs
