@@ -101,6 +101,9 @@ struct flexi_gpu_handle {
   int nElemsInner = 0, nElemsBnd = 0;
   bool keepGrad = false;
   bool bcTablesMissing = false;
+  bool vt = false;             // viscous-trace protocol between k_volume_gl2 and k_flux (kernels.cuh: VolArgs::fvm)
+  bool gradTracesFull = true;  // gradU?_master/slave hold the traces of every side (else only of the BC sides)
+  double *fvm = nullptr, *fvs = nullptr;
   bool tracesValid = false;
   double lastT = 0.;  // time of the last DG operator evaluation (boundary states / source are time dependent)
   // execution
@@ -240,7 +243,12 @@ int start_exchange(H* h, int kind) {
       CKR(exchange_group(h, a2, 1, szU, true));
     }
   } else if (kind == X_GRAD) {  // C3 (lifting_br1.t90:150-165): gradU{x,y,z}_slave -> master rank
-    CKR(exchange_group(h, h->gs, 3, szG, false));
+    if (h->vt) {  // viscous-trace protocol: the slave element's n.F_v replaces the three gradient messages
+      double* a1[1] = {h->fvs};
+      CKR(exchange_group(h, a1, 1, 4 * h->np2, false));
+    } else {
+      CKR(exchange_group(h, h->gs, 3, szG, false));
+    }
   } else {  // C4 (dg.f90:607-641): Flux master -> slave rank
     double* a1[1] = {h->Flux};
     CKR(exchange_group(h, a1, 1, szU, true));
@@ -277,7 +285,7 @@ int refresh_traces(H* h) {
   return 0;
 }
 
-int launch_volume(H* h, const int32_t* list, int n) {
+int launch_volume(H* h, const int32_t* list, int n, bool fullGrad) {
   VolArgs a{};
   a.m = h->m;
   a.q = h->q;
@@ -293,6 +301,9 @@ int launch_volume(H* h, const int32_t* list, int n) {
     a.gvol[d] = h->keepGrad ? h->gvol[d] : nullptr;
   }
   a.basisHost = h->basisHost.data();
+  a.fvm = h->fvm;
+  a.fvs = h->fvs;
+  a.fullGrad = fullGrad ? 1 : 0;
   Timer tm(h, KC_VOLUME, h->sc);
   CK(h->ops->volume(h->gl, h->split, h->q.splitType, h->para, h->nvl, a, n, h->sc));
   return 0;
@@ -312,6 +323,9 @@ int launch_flux(H* h, int first, int n) {
     a.gs[d] = h->gs[d];
   }
   a.Flux = h->Flux;
+  a.fvm = h->fvm;
+  a.fvs = h->fvs;
+  a.vt = h->vt ? 1 : 0;
   if (n <= 0) return 0;
   Timer tm(h, KC_FLUX, h->sc);
   CK(h->ops->flux(a, h->sc));
@@ -370,18 +384,20 @@ int rhs(H* h, double t, int mode, double rkA, double b_dt) {
   h->lastT = t;
   if (!h->tracesValid) CKR(refresh_traces(h));
   const bool multi = h->nProcs > 1;
+  const bool fullGrad = !h->vt || mode == 0 || h->keepGrad;
+  h->gradTracesFull = fullGrad;
   // boundary sides: the lifting boundary flux enters the element kernel as a virtual slave trace (k_bc_pre)
   if (h->para) CKR(launch_bc(h, true, t));
   if (!multi) {
-    CKR(launch_volume(h, nullptr, h->nElems));
+    CKR(launch_volume(h, nullptr, h->nElems, fullGrad));
     CKR(launch_bc(h, false, t));
     CKR(launch_flux(h, h->firstInner, h->nInnerSides));
     CKR(launch_update(h, nullptr, h->nElems, mode, rkA, b_dt, t));
     return 0;
   }
-  CKR(launch_volume(h, h->elemsInner, h->nElemsInner));
+  CKR(launch_volume(h, h->elemsInner, h->nElemsInner, fullGrad));
   CKR(finish_exchange(h, X_TRACE));
-  CKR(launch_volume(h, h->elemsBnd, h->nElemsBnd));
+  CKR(launch_volume(h, h->elemsBnd, h->nElemsBnd, fullGrad));
   if (h->para) CKR(start_exchange(h, X_GRAD));
   CKR(launch_bc(h, false, t));
   CKR(launch_flux(h, h->firstInner, h->nInnerSides));
@@ -393,6 +409,14 @@ int rhs(H* h, double t, int mode, double rkA, double b_dt) {
   CKR(launch_update(h, h->elemsBnd, h->nElemsBnd, mode, rkA, b_dt, t));
   if (mode != 0) CKR(start_exchange(h, X_TRACE));  // traces of the updated state for the next stage
   return 0;
+}
+
+// RK stages under the viscous-trace protocol leave gradient traces on the BC sides only; like the volume gradients
+// (FLEXI_ARR_GRADU*) the full set is recomputed from the current U on request
+int ensure_grad_traces(H* h) {
+  if (h->gradTracesFull) return 0;
+  if (!h->Ut) CKR(dalloc(h, &h->Ut, (size_t)h->nElems * 5 * h->np3));
+  return rhs(h, h->lastT, 0, 0., 0.);
 }
 
 }  // namespace
@@ -730,6 +754,14 @@ static int init_impl(const flexi_gpu_desc* d, H* h) {
       CK(cudaMemset(h->gm[dd], 0, nS * h->nvl * np2 * 8));
       CK(cudaMemset(h->gs[dd], 0, nS * h->nvl * np2 * 8));
     }
+    // the line-resident GL split kernel (even NP) talks to k_flux through n.F_v traces instead of gradient traces
+    h->vt = h->gl && h->split && (h->np % 2 == 0);
+    if (h->vt) {
+      CKR(dalloc(h, &h->fvm, nS * 4 * np2));
+      CKR(dalloc(h, &h->fvs, nS * 4 * np2));
+      CK(cudaMemset(h->fvm, 0, nS * 4 * np2 * 8));
+      CK(cudaMemset(h->fvs, 0, nS * 4 * np2 * 8));
+    }
   }
   // ---- CalcTimeStep tables ----
   CKR(dalloc(h, &h->MetAdv, nE * 3 * np3));
@@ -911,9 +943,11 @@ int flexi_gpu_get_array(flexi_gpu_handle* h, int32_t which, double* out) {
     }
     case FLEXI_ARR_GRADUX_MASTER: case FLEXI_ARR_GRADUY_MASTER: case FLEXI_ARR_GRADUZ_MASTER:
       if (!h->para) return fail(FLEXI_GPU_ERR_ARG, "no gradients without parabolic terms");
+      CKR(ensure_grad_traces(h));
       return download_aos(h, h->gm[which - FLEXI_ARR_GRADUX_MASTER], out, h->nvl, np2, h->nSides);
     case FLEXI_ARR_GRADUX_SLAVE: case FLEXI_ARR_GRADUY_SLAVE: case FLEXI_ARR_GRADUZ_SLAVE:
       if (!h->para) return fail(FLEXI_GPU_ERR_ARG, "no gradients without parabolic terms");
+      CKR(ensure_grad_traces(h));
       return download_aos(h, h->gs[which - FLEXI_ARR_GRADUX_SLAVE], out, h->nvl, np2, h->nSides);
     default: return fail(FLEXI_GPU_ERR_ARG, "unknown array id %d", which);
   }

@@ -28,6 +28,11 @@ struct VolArgs {
   double* gs[3];  // gradU{x,y,z}_slave
   double* gvol[3];  // optional volume gradients [e][nvl][NP3] (NULL = not stored)
   const double* basisHost;  // HOST copy of Mesh::basis (k_volume_gl2 takes the D matrices as kernel parameters)
+  // viscous-trace protocol (k_volume_gl2 only): n.F_v(U,gradU) of the element's own side, [s][4][NP2]; gradient traces are then
+  // written for boundary-condition sides only, unless fullGrad asks for all of them
+  double* fvm;
+  double* fvs;
+  int fullGrad;
 };
 
 struct FluxArgs {
@@ -40,6 +45,9 @@ struct FluxArgs {
   const double* gm[3];
   const double* gs[3];
   double* Flux;  // [s][5][NP2]  (Flux_master == Flux_slave, fillflux.f90:201)
+  const double* fvm;  // viscous-trace protocol (vt != 0): n.F_v of the master / slave element's side, [s][4][NP2]
+  const double* fvs;
+  int vt;
 };
 
 struct UpdArgs {
@@ -491,7 +499,12 @@ __global__ void __launch_bounds__(128) k_flux(FluxArgs A) {
   const double surf = g[9 * D::NP2];
   double F[5];
   riemann_point(q, q.riemann, UL, UR, PL, PR, nv, t1, t2, F);
-  if (A.parabolic) {
+  if (A.parabolic && A.vt) {
+    // ViscousFlux_Side (riemann.f90:448-498) with the normal contraction already done by the two element kernels
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      F[c + 1] = F[c + 1] + 0.5 * (A.fvm[((size_t)s * 4 + c) * D::NP2 + pq] + A.fvs[((size_t)s * 4 + c) * D::NP2 + pq]);
+  } else if (A.parabolic) {
     const int nvl = q.nvl, o = q.lv_vel1;
     double gL[3][4], gR[3][4];
 #pragma unroll

@@ -275,7 +275,13 @@ __global__ void __launch_bounds__(VolGL2Cfg<NP, PARA, NVL>::NT, VolGL2Cfg<NP, PA
   const double* gM = A.m.Met + (size_t)e * 9 * D::NP3;
   constexpr int FACE_IT = (6 * D::NP2 + NT - 1) / NT;
 
-  // ---- phase A (zeta ownership): neighbour traces + face geometry in flight (cp.async), ConsToPrim of the own nodes ----
+  // ---- phase A (zeta ownership): own conservative state on its way first, then neighbour traces + face geometry (cp.async),
+  //      then ConsToPrim of the own nodes ----
+  double Uc[HALF][5];
+#pragma unroll
+  for (int c = 0; c < HALF; ++c)
+#pragma unroll
+    for (int v = 0; v < 5; ++v) Uc[c][v] = __ldg(gU + v * D::NP3 + gl2_gn<NP, 2>(gl2_ap<NP>(hb, c), r0, r1));
   int faceSlot[FACE_IT];
   double faceSgn[FACE_IT];
   if (PARA) {
@@ -297,8 +303,9 @@ __global__ void __launch_bounds__(VolGL2Cfg<NP, PARA, NVL>::NT, VolGL2Cfg<NP, PA
         cp_async8(o + 6 * D::NP2, g + D::NP2);
         cp_async8(o + 7 * D::NP2, g + 2 * D::NP2);
         cp_async8(o + 8 * D::NP2, g + 9 * D::NP2);
-        // destination of this face node's gradient trace: (side*NVL*NP2 + pq), sign bit set for the slave arrays
-        sFD[(ls - 1) * D::NP2 + ab] = (sr.side * NVL * D::NP2 + pq) | (sr.flip == 0 ? 0 : (int)0x80000000);
+        // destination of this face node's traces: side*NP2 + pq, bit 31 = slave arrays, bit 30 = boundary-condition side
+        sFD[(ls - 1) * D::NP2 + ab] =
+            (sr.side * D::NP2 + pq) | (sr.flip == 0 ? 0 : (int)0x80000000) | (sr.side < A.m.nBCSides ? 0x40000000 : 0);
         if (LIFT == 2 && pq == 0) {  // lifting_br2.t90:277-288: etaBR2_wall on no-slip wall sides
           double eta = q.etaBR2;
           if (sr.side < A.m.nBCSides) {
@@ -323,11 +330,6 @@ __global__ void __launch_bounds__(VolGL2Cfg<NP, PARA, NVL>::NT, VolGL2Cfg<NP, PA
     cp_async_commit();
   }
   {
-    double Uc[HALF][5];
-#pragma unroll
-    for (int c = 0; c < HALF; ++c)
-#pragma unroll
-      for (int v = 0; v < 5; ++v) Uc[c][v] = gU[v * D::NP3 + gl2_gn<NP, 2>(gl2_ap<NP>(hb, c), r0, r1)];
 #pragma unroll
     for (int c = 0; c < HALF; ++c) {
       double Pn[6];
@@ -386,13 +388,13 @@ __global__ void __launch_bounds__(VolGL2Cfg<NP, PARA, NVL>::NT, VolGL2Cfg<NP, PA
     {
       constexpr int LV = (NVL == 5) ? 1 : 0;
       const int i = r0, j = r1;
-      double M[HALF][9], sJ[HALF];
+      // metric terms + Jacobian of the own nodes straight from HBM, one node ahead of the arithmetic
+      double Mn[9], sJn;
+      {
+        const int n = gl2_gn<NP, 2>(gl2_ap<NP>(hb, 0), r0, r1);
 #pragma unroll
-      for (int c = 0; c < HALF; ++c) {
-        const int n = gl2_gn<NP, 2>(gl2_ap<NP>(hb, c), r0, r1);
-#pragma unroll
-        for (int m = 0; m < 9; ++m) M[c][m] = __ldg(gM + m * D::NP3 + n);
-        sJ[c] = __ldg(A.m.sJ + (size_t)e * D::NP3 + n);
+        for (int m = 0; m < 9; ++m) Mn[m] = __ldg(gM + m * D::NP3 + n);
+        sJn = __ldg(A.m.sJ + (size_t)e * D::NP3 + n);
       }
       double gzt[HALF][NVL];
       gl2_lift_line<NP, NVL, 2>(B, sP, hb, r0, r1, gzt);
@@ -401,65 +403,73 @@ __global__ void __launch_bounds__(VolGL2Cfg<NP, PARA, NVL>::NT, VolGL2Cfg<NP, PA
         const int k = gl2_ap<NP>(hb, c);
         const int s = gl2_sa<NP, 2>(k, r0, r1);
         const int n = i + NP * (j + NP * k);
+        double Mc[9];
+#pragma unroll
+        for (int m = 0; m < 9; ++m) Mc[m] = Mn[m];
+        const double sJc = sJn;
+        if (c + 1 < HALF) {
+          const int n1 = gl2_gn<NP, 2>(gl2_ap<NP>(hb, c + 1), r0, r1);
+#pragma unroll
+          for (int m = 0; m < 9; ++m) Mn[m] = __ldg(gM + m * D::NP3 + n1);
+          sJn = __ldg(A.m.sJ + (size_t)e * D::NP3 + n1);
+        }
         double gx[NVL], gy[NVL], gz[NVL];
 #pragma unroll
         for (int v = 0; v < NVL; ++v) {
           const double gxi = sW[v * PL + s], geta = sW[(NVL + v) * PL + s], gzeta = gzt[c][v];
-          gx[v] = M[c][0] * gxi + M[c][3] * geta + M[c][6] * gzeta;
-          gy[v] = M[c][1] * gxi + M[c][4] * geta + M[c][7] * gzeta;
-          gz[v] = M[c][2] * gxi + M[c][5] * geta + M[c][8] * gzeta;
+          gx[v] = Mc[0] * gxi + Mc[3] * geta + Mc[6] * gzeta;
+          gy[v] = Mc[1] * gxi + Mc[4] * geta + Mc[7] * gzeta;
+          gz[v] = Mc[2] * gxi + Mc[5] * geta + Mc[8] * gzeta;
         }
-        // ---- lifting, surface part: on LGL nodes only the boundary nodes receive it ----
-        const bool onFace[6] = {k == 0, j == 0, i == N, j == N, i == 0, k == N};  // local sides 1..6 (flexi.h:90-95)
-        const int abFace[6] = {i + NP * j, i + NP * k, j + NP * k, i + NP * k, j + NP * k, i + NP * j};
+        // ---- boundary nodes.  One (partially active) block per sheet direction instead of one per local side: the lanes of a
+        //      warp that sit on xi- and xi+ run the same code with their own side index.  The zeta faces belong to the line
+        //      end c == 0 of every thread (k = 0 for half 0, k = N for half 1), a warp-uniform condition. ----
+        const bool onI = (i == 0) | (i == N), onJ = (j == 0) | (j == N), onK = (c == 0);
+        const int lsI = (i == 0) ? XI_MINUS : XI_PLUS, lsJ = (j == 0) ? ETA_MINUS : ETA_PLUS, lsK = hb ? ZETA_PLUS : ZETA_MINUS;
+        const int abI = j + NP * k, abJ = i + NP * k, abK = i + NP * j;
         double gxo[NVL], gyo[NVL], gzo[NVL];  // BR2: gradients without the surface part (what the faces are prolonged from)
-        if (LIFT == 1) {  // BR1 (lifting_br1.t90:195-292), then ApplyJacobianLifting
+        // lifting, surface part (BR1 lifting_br1.t90:195-292; BR2 lifting_br2.t90:194-311)
+        auto surf_in = [&](int ls, int ab) {
+          const double* o = sX + (ls - 1) * 9 * D::NP2 + ab;
+          const double n0 = o[5 * D::NP2], n1 = o[6 * D::NP2], n2 = o[7 * D::NP2];
+          const double lh = (LIFT == 1) ? (is_minus_side(ls) ? B.lhm0 : B.lhpN) : B.lhm0;
 #pragma unroll
-          for (int ls = 1; ls <= 6; ++ls) {
-            if (onFace[ls - 1]) {
-              const double* o = sX + (ls - 1) * 9 * D::NP2 + abFace[ls - 1];
-              const double n0 = o[5 * D::NP2], n1 = o[6 * D::NP2], n2 = o[7 * D::NP2];
-              const double lh = is_minus_side(ls) ? B.lhm0 : B.lhpN;
-#pragma unroll
-              for (int v = 0; v < NVL; ++v) {
-                const double f = o[v * D::NP2];
-                gx[v] = gx[v] + (f * n0) * lh;
-                gy[v] = gy[v] + (f * n1) * lh;
-                gz[v] = gz[v] + (f * n2) * lh;
-              }
+          for (int v = 0; v < NVL; ++v) {
+            const double f = o[v * D::NP2];
+            if (LIFT == 1) {
+              gx[v] = gx[v] + (f * n0) * lh;
+              gy[v] = gy[v] + (f * n1) * lh;
+              gz[v] = gz[v] + (f * n2) * lh;
+            } else {
+              gx[v] = gx[v] + sJc * (f * n0) * lh;
+              gy[v] = gy[v] + sJc * (f * n1) * lh;
+              gz[v] = gz[v] + sJc * (f * n2) * lh;
             }
           }
+        };
+        if (LIFT == 1) {  // BR1: surface part, then ApplyJacobianLifting
+          if (onI) surf_in(lsI, abI);
+          if (onJ) surf_in(lsJ, abJ);
+          if (onK) surf_in(lsK, abK);
 #pragma unroll
           for (int v = 0; v < NVL; ++v) {
-            gx[v] = gx[v] * sJ[c];
-            gy[v] = gy[v] * sJ[c];
-            gz[v] = gz[v] * sJ[c];
+            gx[v] = gx[v] * sJc;
+            gy[v] = gy[v] * sJc;
+            gz[v] = gz[v] * sJc;
           }
-        } else {  // BR2 (lifting_br2.t90:111-131,194-311): Jacobian first, then sJ*Flux*L_HatMinus(0) on the boundary node
+        } else {  // BR2: Jacobian first, then sJ*Flux*L_HatMinus(0) on the boundary node
 #pragma unroll
           for (int v = 0; v < NVL; ++v) {
-            gx[v] = gx[v] * sJ[c];
-            gy[v] = gy[v] * sJ[c];
-            gz[v] = gz[v] * sJ[c];
+            gx[v] = gx[v] * sJc;
+            gy[v] = gy[v] * sJc;
+            gz[v] = gz[v] * sJc;
             gxo[v] = gx[v];
             gyo[v] = gy[v];
             gzo[v] = gz[v];
           }
-#pragma unroll
-          for (int ls = 1; ls <= 6; ++ls) {
-            if (onFace[ls - 1]) {
-              const double* o = sX + (ls - 1) * 9 * D::NP2 + abFace[ls - 1];
-              const double n0 = o[5 * D::NP2], n1 = o[6 * D::NP2], n2 = o[7 * D::NP2];
-              const double lh = B.lhm0;
-#pragma unroll
-              for (int v = 0; v < NVL; ++v) {
-                const double f = o[v * D::NP2];
-                gx[v] = gx[v] + sJ[c] * (f * n0) * lh;
-                gy[v] = gy[v] + sJ[c] * (f * n1) * lh;
-                gz[v] = gz[v] + sJ[c] * (f * n2) * lh;
-              }
-            }
-          }
+          if (onI) surf_in(lsI, abI);
+          if (onJ) surf_in(lsJ, abJ);
+          if (onK) surf_in(lsK, abK);
         }
         if (A.gvol[0]) {
 #pragma unroll
@@ -469,50 +479,67 @@ __global__ void __launch_bounds__(VolGL2Cfg<NP, PARA, NVL>::NT, VolGL2Cfg<NP, PA
             A.gvol[2][((size_t)e * NVL + v) * D::NP3 + n] = gz[v];
           }
         }
-        // ---- ProlongToFaceLifting on LGL nodes = copy of the boundary node (prolongtoface.t90:270-303);
-        //      BR2 adds eta*L_Minus(0)*sJ*Flux*L_HatMinus(0) of the side itself to the volume-only value ----
+        // ---- viscous flux of this node (flux.f90:149-241) ----
+        const double v1 = sP[VEL1 * PL + s], v2 = sP[VEL2 * PL + s], v3 = sP[VEL3 * PL + s];
+        double fv[4], gv[4], hv[4];
+        eval_diff_flux3d(q, v1, v2, v3, gx + LV, gy + LV, gz + LV, fv, gv, hv);
+        // ---- what the side kernel needs from this element.  ViscousFlux_Side (riemann.f90:448-498) forms
+        //      0.5*n.(F_v(U_L,gradU_L) + F_v(U_R,gradU_R)); each half depends on one element only, and on LGL nodes the face
+        //      state and (BR1) the face gradient are copies of the boundary node's (prolongtoface.t90:270-303), so the element
+        //      writes n.F_v of its own side (4 doubles per face node) instead of the 3*nVarLifting gradient traces.  The
+        //      gradient traces themselves are still written for boundary-condition sides (GetBoundaryFlux needs them) and, when
+        //      the host asked for a full DG operator evaluation, for every side. ----
+        auto face_out = [&](int ls, int ab) {
+          const int fd = sFD[(ls - 1) * D::NP2 + ab];
+          const bool master = fd >= 0;
+          const int fl = fd & 0x3fffffff, side = fl / D::NP2, pq = fl % D::NP2;
+          const double* of = sX + (ls - 1) * 9 * D::NP2 + ab;
+          const double n0 = of[5 * D::NP2], n1 = of[6 * D::NP2], n2 = of[7 * D::NP2];
+          double gfx[NVL], gfy[NVL], gfz[NVL];
+          if (LIFT == 2) {  // BR2 face gradient: volume-only value + eta*L_Minus(0)*sJ*Flux*L_HatMinus(0) of the side itself
+            const double w = sEta[ls - 1] * B.lm0;
 #pragma unroll
-        for (int ls = 1; ls <= 6; ++ls) {
-          if (onFace[ls - 1]) {
-            const int fd = sFD[(ls - 1) * D::NP2 + abFace[ls - 1]];
-            const bool master = fd >= 0;
+            for (int v = 0; v < NVL; ++v) {
+              const double f = of[v * D::NP2];
+              gfx[v] = gxo[v] + w * (sJc * (f * n0) * B.lhm0);
+              gfy[v] = gyo[v] + w * (sJc * (f * n1) * B.lhm0);
+              gfz[v] = gzo[v] + w * (sJc * (f * n2) * B.lhm0);
+            }
+          }
+          if (A.fullGrad || (fd & 0x40000000)) {
             double* const d0 = master ? A.gm[0] : A.gs[0];
             double* const d1 = master ? A.gm[1] : A.gs[1];
             double* const d2 = master ? A.gm[2] : A.gs[2];
-            const size_t o0 = (size_t)(fd & 0x7fffffff);
-            if (LIFT == 1) {
+            const size_t o0 = (size_t)side * NVL * D::NP2 + pq;
 #pragma unroll
-              for (int v = 0; v < NVL; ++v) {
-                const size_t o = o0 + (size_t)v * D::NP2;
-                d0[o] = gx[v];
-                d1[o] = gy[v];
-                d2[o] = gz[v];
-              }
-            } else {
-              const double* of = sX + (ls - 1) * 9 * D::NP2 + abFace[ls - 1];
-              const double n0 = of[5 * D::NP2], n1 = of[6 * D::NP2], n2 = of[7 * D::NP2];
-              const double w = sEta[ls - 1] * B.lm0;
-              const double lh = B.lhm0;
-#pragma unroll
-              for (int v = 0; v < NVL; ++v) {
-                const size_t o = o0 + (size_t)v * D::NP2;
-                const double f = of[v * D::NP2];
-                d0[o] = gxo[v] + w * (sJ[c] * (f * n0) * lh);
-                d1[o] = gyo[v] + w * (sJ[c] * (f * n1) * lh);
-                d2[o] = gzo[v] + w * (sJ[c] * (f * n2) * lh);
-              }
+            for (int v = 0; v < NVL; ++v) {
+              const size_t o = o0 + (size_t)v * D::NP2;
+              d0[o] = (LIFT == 2) ? gfx[v] : gx[v];
+              d1[o] = (LIFT == 2) ? gfy[v] : gy[v];
+              d2[o] = (LIFT == 2) ? gfz[v] : gz[v];
             }
           }
-        }
-        // ---- viscous flux of this node (flux.f90:149-241) and its contravariant components (volint.f90:378-422);
-        //      written over the node's own G1/G2 slots, which only this thread reads ----
-        double fv[4], gv[4], hv[4];
-        eval_diff_flux3d(q, sP[VEL1 * PL + s], sP[VEL2 * PL + s], sP[VEL3 * PL + s], gx + LV, gy + LV, gz + LV, fv, gv, hv);
+          double* const dv = (master ? A.fvm : A.fvs) + (size_t)side * 4 * D::NP2 + pq;
+          if (LIFT == 2) {
+            double ff[4], gf[4], hf[4];
+            eval_diff_flux3d(q, v1, v2, v3, gfx + LV, gfy + LV, gfz + LV, ff, gf, hf);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) dv[v * D::NP2] = n0 * ff[v] + n1 * gf[v] + n2 * hf[v];
+          } else {
+#pragma unroll
+            for (int v = 0; v < 4; ++v) dv[v * D::NP2] = n0 * fv[v] + n1 * gv[v] + n2 * hv[v];
+          }
+        };
+        if (onI) face_out(lsI, abI);
+        if (onJ) face_out(lsJ, abJ);
+        if (onK) face_out(lsK, abK);
+        // ---- contravariant components (volint.f90:378-422), written over the node's own G1/G2 slots (only this thread reads
+        //      them) ----
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
-          sW[(0 + v) * PL + s] = fv[v] * M[c][0] + gv[v] * M[c][1] + hv[v] * M[c][2];
-          sW[(4 + v) * PL + s] = fv[v] * M[c][3] + gv[v] * M[c][4] + hv[v] * M[c][5];
-          sW[(8 + v) * PL + s] = fv[v] * M[c][6] + gv[v] * M[c][7] + hv[v] * M[c][8];
+          sW[(0 + v) * PL + s] = fv[v] * Mc[0] + gv[v] * Mc[1] + hv[v] * Mc[2];
+          sW[(4 + v) * PL + s] = fv[v] * Mc[3] + gv[v] * Mc[4] + hv[v] * Mc[5];
+          sW[(8 + v) * PL + s] = fv[v] * Mc[6] + gv[v] * Mc[7] + hv[v] * Mc[8];
         }
       }
     }
