@@ -104,6 +104,7 @@ struct flexi_gpu_handle {
   bool vt = false;             // viscous-trace protocol between k_volume_gl2 and k_flux (kernels.cuh: VolArgs::fvm)
   bool gradTracesFull = true;  // gradU?_master/slave hold the traces of every side (else only of the BC sides)
   double *fvm = nullptr, *fvs = nullptr;
+  int prefetchAhead = 0;  // resident CTAs of the element kernel (2 per SM): distance of its L2 prefetch
   bool tracesValid = false;
   double lastT = 0.;  // time of the last DG operator evaluation (boundary states / source are time dependent)
   // execution
@@ -304,6 +305,7 @@ int launch_volume(H* h, const int32_t* list, int n, bool fullGrad) {
   a.fvm = h->fvm;
   a.fvs = h->fvs;
   a.fullGrad = fullGrad ? 1 : 0;
+  a.prefetchAhead = h->prefetchAhead;
   Timer tm(h, KC_VOLUME, h->sc);
   CK(h->ops->volume(h->gl, h->split, h->q.splitType, h->para, h->nvl, a, n, h->sc));
   return 0;
@@ -533,6 +535,12 @@ static int init_impl(const flexi_gpu_desc* d, H* h) {
   if (d->device < 0 || d->device >= ndev) return fail(FLEXI_GPU_ERR_ARG, "device %d not in 0..%d", d->device, ndev - 1);
   CK(cudaSetDevice(d->device));
   CK(h->ops->setup());
+  {
+    int nsm = 0;
+    CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, d->device));
+    const char* pf = getenv("FLEXI_GPU_PREFETCH");  // tuning hook: L2 prefetch distance of the element kernel in CTAs, 0 = off
+    h->prefetchAhead = pf ? atoi(pf) : 2 * nsm;
+  }
   CK(cudaStreamCreateWithFlags(&h->sc, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&h->sx, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&h->evProd, cudaEventDisableTiming));

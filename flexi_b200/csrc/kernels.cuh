@@ -33,6 +33,7 @@ struct VolArgs {
   double* fvm;
   double* fvs;
   int fullGrad;
+  int prefetchAhead;  // k_volume_gl2: CTA b prefetches the element of CTA b+prefetchAhead into L2 (0 = off)
 };
 
 struct FluxArgs {

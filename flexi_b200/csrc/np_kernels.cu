@@ -58,26 +58,12 @@ cudaError_t volume_gl_launch(int lift, const VolArgs& a, int nBlocks, cudaStream
 // line-resident split-form GL kernel (volume_gl2.cuh) for even NP; odd NP keeps k_volume_gl
 constexpr bool HAS_GL2 = (NP % 2 == 0);
 bool g_use_gl2 = HAS_GL2;
-template <int STYPE, bool PARA, int NVL, int LIFT>
+template <int STYPE, bool PARA, int NVL, int NVC, int LIFT>
 struct GL2 {
   static constexpr int NPE = HAS_GL2 ? NP : 2;  // odd NP never instantiates the real kernel
-  using C = VolGL2Cfg<NPE, PARA, NVL>;
+  using C = VolGL2Cfg<NPE, PARA>;
   static cudaError_t setup() {
-    return cudaFuncSetAttribute(k_volume_gl2<NPE, STYPE, PARA, NVL, LIFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::BYTES);
-  }
-  // M(N-l,N-i) == -M(l,i) for the three operators (off-diagonal only for DVolSurf): what gl2_ap relies on
-  static bool antisymmetric(const double* b) {
-    const int offs[3] = {Dim<NPE>::O_DT, Dim<NPE>::O_DH, Dim<NPE>::O_DV};
-    for (int t = 0; t < 3; ++t) {
-      double mx = 0.;
-      for (int x = 0; x < NPE * NPE; ++x) mx = fmax(mx, fabs(b[offs[t] + x]));
-      for (int l = 0; l < NPE; ++l)
-        for (int i = 0; i < NPE; ++i) {
-          if (t == 2 && l == i) continue;
-          if (fabs(b[offs[t] + l * NPE + i] + b[offs[t] + (NPE - 1 - l) * NPE + (NPE - 1 - i)]) > 1e-14 * mx) return false;
-        }
-    }
-    return true;
+    return cudaFuncSetAttribute(k_volume_gl2<NPE, STYPE, PARA, NVL, NVC, LIFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::BYTES);
   }
   static cudaError_t launch(const VolArgs& a, int nBlocks, cudaStream_t s) {
     VolArgs2<NPE> aa;
@@ -92,20 +78,38 @@ struct GL2 {
     aa.b.lhm0 = b[Dim<NPE>::O_LHM];
     aa.b.lhpN = b[Dim<NPE>::O_LHP + NPE - 1];
     aa.b.lm0 = b[Dim<NPE>::O_LM];
-    k_volume_gl2<NPE, STYPE, PARA, NVL, LIFT><<<nBlocks, C::NT, C::BYTES, s>>>(aa);
+    k_volume_gl2<NPE, STYPE, PARA, NVL, NVC, LIFT><<<nBlocks, C::NT, C::BYTES, s>>>(aa);
     return cudaGetLastError();
   }
 };
+// M(N-l,N-i) == -M(l,i) for the three operators (off-diagonal only for DVolSurf): what gl2_ap relies on
+bool gl2_antisymmetric(const double* b) {
+  const int offs[3] = {D::O_DT, D::O_DH, D::O_DV};
+  for (int t = 0; t < 3; ++t) {
+    double mx = 0.;
+    for (int x = 0; x < NP * NP; ++x) mx = fmax(mx, fabs(b[offs[t] + x]));
+    for (int l = 0; l < NP; ++l)
+      for (int i = 0; i < NP; ++i) {
+        if (t == 2 && l == i) continue;
+        if (fabs(b[offs[t] + l * NP + i] + b[offs[t] + (NP - 1 - l) * NP + (NP - 1 - i)]) > 1e-14 * mx) return false;
+      }
+  }
+  return true;
+}
+// all nVarLifting variables are lifted when gradients are handed out; the time-stepping path lifts (v1,v2,v3,T) only
 template <int STYPE, bool PARA, int NVL>
 cudaError_t gl2_setup() {
-  cudaError_t e = GL2<STYPE, PARA, NVL, 1>::setup();
-  if (e == cudaSuccess && PARA) e = GL2<STYPE, PARA, NVL, 2>::setup();
+  cudaError_t e = GL2<STYPE, PARA, NVL, NVL, 1>::setup();
+  if (e == cudaSuccess && PARA) e = GL2<STYPE, PARA, NVL, NVL, 2>::setup();
+  if (e == cudaSuccess && PARA && NVL == 5) e = GL2<STYPE, PARA, NVL, 4, 1>::setup();
+  if (e == cudaSuccess && PARA && NVL == 5) e = GL2<STYPE, PARA, NVL, 4, 2>::setup();
   return e;
 }
 template <int STYPE, bool PARA, int NVL>
 cudaError_t gl2_launch(int lift, const VolArgs& a, int nBlocks, cudaStream_t s) {
-  if (PARA && lift == 2) return GL2<STYPE, PARA, NVL, 2>::launch(a, nBlocks, s);
-  return GL2<STYPE, PARA, NVL, 1>::launch(a, nBlocks, s);
+  const bool all = !PARA || NVL == 4 || a.fullGrad || a.gvol[0];
+  if (PARA && lift == 2) return all ? GL2<STYPE, PARA, NVL, NVL, 2>::launch(a, nBlocks, s) : GL2<STYPE, PARA, NVL, 4, 2>::launch(a, nBlocks, s);
+  return all ? GL2<STYPE, PARA, NVL, NVL, 1>::launch(a, nBlocks, s) : GL2<STYPE, PARA, NVL, 4, 1>::launch(a, nBlocks, s);
 }
 
 
@@ -167,7 +171,7 @@ cudaError_t volume(bool gl, bool split, int stype, bool para, int nvl, const Vol
     if (!para) return volume_gl_launch<false, 0, false, 5>(lift, a, nBlocks, s);
     return nvl == 5 ? volume_gl_launch<false, 0, true, 5>(lift, a, nBlocks, s) : volume_gl_launch<false, 0, true, 4>(lift, a, nBlocks, s);
   }
-  if (HAS_GL2 && g_use_gl2 && GL2<FLEXI_SPLITDG_PI, false, 5, 1>::antisymmetric(a.basisHost)) {
+  if (HAS_GL2 && g_use_gl2 && gl2_antisymmetric(a.basisHost)) {
     switch (stype) {
 #define X(T)                                                                                   \
   case T:                                                                                      \

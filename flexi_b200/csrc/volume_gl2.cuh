@@ -25,6 +25,8 @@
 
 namespace fx {
 
+__device__ __forceinline__ void cp_async_wait_group1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+
 template <int NP>
 struct GL2Basis {
   double dt[NP * NP];   // D_T(l,i)      at [l*NP+i]  (lifting derivative, lifting_volint.t90:67-83)
@@ -44,7 +46,7 @@ __device__ __forceinline__ int gl2_phys(int i, int j, int k) {
   return i + NP * (j + NP * k);
 }
 
-template <int NP, bool PARA, int NVL>
+template <int NP, bool PARA>
 struct VolGL2Cfg {
   using D = Dim<NP>;
   static_assert(NP % 2 == 0, "line halves need an even number of nodes");
@@ -52,7 +54,7 @@ struct VolGL2Cfg {
   static constexpr int NT = 2 * D::NP2;
   static constexpr int PL = D::NP3;
   static constexpr int P_PLANES = PARA ? 7 : 6;  // rho,u,v,w,p,[T],X5
-  static constexpr int W_PLANES = PARA ? 12 : 0;  // contravariant viscous fluxes f~,g~,h~ (4 each); 2*NVL lifting planes alias them
+  static constexpr int W_PLANES = PARA ? 12 : 0;  // contravariant viscous fluxes f~,g~,h~ (4 each); the 2*nVarLift lifting planes alias them
   static constexpr int F_FACE = PARA ? 6 * 9 * D::NP2 : 0;
   static constexpr int F_DOUBLES = ((F_FACE > 5 * PL ? F_FACE : 5 * PL) + 1) & ~1;  // face staging, later the Ut hand-over planes
   static constexpr int NFD = PARA ? ((3 * D::NP2 + 1) & ~1) : 0;                     // int table [6][NP2]
@@ -77,29 +79,28 @@ __device__ __forceinline__ int gl2_ap(int hb, int q) {
   return hb ? (NP - 1 - q) : q;
 }
 
-// shared-memory (swizzled) address / natural node index of position p on the line of direction DIR through sheet position (r0,r1):
-// xi-lines (j,k) = (r0,r1), eta-lines (i,k) = (r0,r1), zeta-lines (i,j) = (r0,r1)
-template <int NP, int DIR>
-__device__ __forceinline__ int gl2_sa(int p, int r0, int r1) {
-  return DIR == 0 ? gl2_phys<NP>(p, r0, r1) : DIR == 1 ? gl2_phys<NP>(r0, p, r1) : gl2_phys<NP>(r0, r1, p);
+// shared-memory (swizzled) address / natural node index of position p on the line of direction dir through sheet position (r0,r1):
+// xi-lines (j,k) = (r0,r1), eta-lines (i,k) = (r0,r1), zeta-lines (i,j) = (r0,r1).  dir is a run-time value: the three direction
+// sweeps share ONE copy of the (long, straight-line) sweep code, which keeps the instruction footprint of the kernel small.
+template <int NP>
+__device__ __forceinline__ int gl2_sa(int dir, int p, int r0, int r1) {
+  const int i = (dir == 0) ? p : r0, j = (dir == 0) ? r0 : (dir == 1) ? p : r1, k = (dir == 2) ? p : r1;
+  return gl2_phys<NP>(i, j, k);
 }
-template <int NP, int DIR>
-__device__ __forceinline__ int gl2_gn(int p, int r0, int r1) {
-  return DIR == 0 ? p + NP * (r0 + NP * r1) : DIR == 1 ? r0 + NP * (p + NP * r1) : r0 + NP * (r1 + NP * p);
+template <int NP>
+__device__ __forceinline__ int gl2_gn(int dir, int p, int r0, int r1) {
+  const int i = (dir == 0) ? p : r0, j = (dir == 0) ? r0 : (dir == 1) ? p : r1, k = (dir == 2) ? p : r1;
+  return i + NP * (j + NP * k);
 }
 
-// One direction phase of the advective two-point fluxes (+ the weak-form derivative of the viscous flux of that direction).
-//   ut[c][v] result for the own nodes c (HALF of them)
-template <int NP, int STYPE, bool PARA, int DIR>
-__device__ __forceinline__ void gl2_pair_phase(const GL2Basis<NP>& B, const double* __restrict__ sP, const double* __restrict__ sWd,
-                                               const double* __restrict__ gMd, int hb, int r0, int r1, double (&ut)[NP / 2][5]) {
+// One direction sweep of the advective two-point fluxes (+ the weak-form derivative of the viscous flux of that direction).
+//   sa[q] / gn[q]  shared-memory address / natural node index of canonical line position q
+//   ut[c][v]       result for the own nodes c (HALF of them), WITHOUT the half sign (the caller applies it)
+template <int NP, int STYPE, bool PARA>
+__device__ __forceinline__ void gl2_pair_sweep(const GL2Basis<NP>& B, const double* __restrict__ sP, const double* __restrict__ sWd,
+                                               const double* __restrict__ gMd, const int (&sa)[NP], const int (&gn)[NP],
+                                               double (&ut)[NP / 2][5]) {
   constexpr int HALF = NP / 2, PL = NP * NP * NP;
-  int sa[NP], gn[NP];  // indexed by canonical position
-#pragma unroll
-  for (int p = 0; p < NP; ++p) {
-    sa[p] = gl2_sa<NP, DIR>(gl2_ap<NP>(hb, p), r0, r1);
-    gn[p] = gl2_gn<NP, DIR>(gl2_ap<NP>(hb, p), r0, r1);
-  }
   constexpr bool PI = (STYPE == FLEXI_SPLITDG_PI);
   constexpr int PX = PARA ? 6 : 5;
   // metric terms of this direction along the whole line, straight from L2
@@ -120,11 +121,14 @@ __device__ __forceinline__ void gl2_pair_phase(const GL2Basis<NP>& B, const doub
 #pragma unroll
       for (int p = 0; p < NP; ++p) L[p] = sWd[v * PL + sa[p]];
 #pragma unroll
-      for (int c = 0; c < HALF; ++c) {
-        double s = B.dh[c] * L[0];
+      for (int c = 0; c < HALF; ++c) {  // two partial sums per node: twice the independent FP64 chains
+        double s0 = B.dh[c] * L[0], s1 = B.dh[HALF * NP + c] * L[HALF];
 #pragma unroll
-        for (int p = 1; p < NP; ++p) s = s + B.dh[p * NP + c] * L[p];
-        ut[c][v + 1] = s;
+        for (int p = 1; p < HALF; ++p) {
+          s0 = s0 + B.dh[p * NP + c] * L[p];
+          s1 = s1 + B.dh[(HALF + p) * NP + c] * L[HALF + p];
+        }
+        ut[c][v + 1] = s0 + s1;
       }
     }
   } else {
@@ -147,9 +151,8 @@ __device__ __forceinline__ void gl2_pair_phase(const GL2Basis<NP>& B, const doub
   for (int c = 0; c < HALF; ++c)
 #pragma unroll
     for (int c2 = c + 1; c2 < HALF; ++c2) {
-      const int m1 = c, m2 = c2;
-      const double d12 = B.dvs[m2 * NP + m1];  // DVolSurf(l=m2, m1) -> node c
-      const double d21 = B.dvs[m1 * NP + m2];  // DVolSurf(l=m1, m2) -> node c2
+      const double d12 = B.dvs[c2 * NP + c];  // DVolSurf(l=c2, c) -> node c
+      const double d21 = B.dvs[c * NP + c2];  // DVolSurf(l=c, c2) -> node c2
       if (PI) {
         const double su = a[c][1] + a[c2][1], sv = a[c][2] + a[c2][2], sw = a[c][3] + a[c2][3], sp4 = a[c][4] + a[c2][4],
                      sH = a[c][5] + a[c2][5];
@@ -217,46 +220,20 @@ __device__ __forceinline__ void gl2_pair_phase(const GL2Basis<NP>& B, const doub
       }
     }
   }
-  const double sg = hb ? -1. : 1.;
-#pragma unroll
-  for (int c = 0; c < HALF; ++c)
-#pragma unroll
-    for (int v = 0; v < 5; ++v) ut[c][v] = sg * ut[c][v];
 }
 
-// reference-space derivative of the NVL lifting variables along one line (lifting_volint.t90:67-83): out[c][v] for the own nodes
-template <int NP, int NVL, int DIR>
-__device__ __forceinline__ void gl2_lift_line(const GL2Basis<NP>& B, const double* __restrict__ sP, int hb, int r0, int r1,
-                                              double (&out)[NP / 2][NVL]) {
-  constexpr int HALF = NP / 2, PL = NP * NP * NP;
-  const double sg = hb ? -1. : 1.;
-  int sa[NP];
-#pragma unroll
-  for (int p = 0; p < NP; ++p) sa[p] = gl2_sa<NP, DIR>(gl2_ap<NP>(hb, p), r0, r1);
-#pragma unroll
-  for (int v = 0; v < NVL; ++v) {
-    const double* pl = sP + lift_prim(NVL, v) * PL;
-    double L[NP];
-#pragma unroll
-    for (int p = 0; p < NP; ++p) L[p] = pl[sa[p]];
-#pragma unroll
-    for (int c = 0; c < HALF; ++c) {
-      double s = B.dt[c] * L[0];
-#pragma unroll
-      for (int p = 1; p < NP; ++p) s = s + B.dt[p * NP + c] * L[p];
-      out[c][v] = sg * s;
-    }
-  }
-}
-
-template <int NP, int STYPE, bool PARA, int NVL, int LIFT>
-__global__ void __launch_bounds__(VolGL2Cfg<NP, PARA, NVL>::NT, VolGL2Cfg<NP, PARA, NVL>::MINB)
+// Template parameters: NVL = nVarLifting of the gradient arrays (their layout), NVC = number of lifting variables actually
+// lifted: NVL, or 4 = (v1,v2,v3,T) on the time-stepping path, where nothing reads the density gradient (EvalDiffFlux3D does
+// not use it and no gradient array is handed out).
+template <int NP, int STYPE, bool PARA, int NVL, int NVC, int LIFT>
+__global__ void __launch_bounds__(VolGL2Cfg<NP, PARA>::NT, VolGL2Cfg<NP, PARA>::MINB)
     k_volume_gl2(const __grid_constant__ VolArgs2<NP> AA) {
   using D = Dim<NP>;
-  using C = VolGL2Cfg<NP, PARA, NVL>;
+  using C = VolGL2Cfg<NP, PARA>;
   constexpr int HALF = C::HALF, NT = C::NT, PL = C::PL, N = NP - 1;
   constexpr bool PI = (STYPE == FLEXI_SPLITDG_PI);
   constexpr int PX = PARA ? 6 : 5;
+  constexpr int VOFF = NVL - NVC;  // slot of the first lifted variable inside the nVarLifting layout
   const VolArgs& A = AA.a;
   const GL2Basis<NP>& B = AA.b;
   extern __shared__ __align__(16) double sm[];
@@ -270,6 +247,7 @@ __global__ void __launch_bounds__(VolGL2Cfg<NP, PARA, NVL>::NT, VolGL2Cfg<NP, PA
   const int e = A.elems ? A.elems[blockIdx.x] : blockIdx.x;
   const int hb = tid / D::NP2, r = tid % D::NP2;  // half index (warp-uniform for NP = 8) and position inside the NP x NP sheet
   const int r0 = r % NP, r1 = r / NP;
+  const double sg = hb ? -1. : 1.;
   const Eqn& q = A.q;
   const double* gU = A.U + (size_t)e * 5 * D::NP3;
   const double* gM = A.m.Met + (size_t)e * 9 * D::NP3;
@@ -281,14 +259,36 @@ __global__ void __launch_bounds__(VolGL2Cfg<NP, PARA, NVL>::NT, VolGL2Cfg<NP, PA
 #pragma unroll
   for (int c = 0; c < HALF; ++c)
 #pragma unroll
-    for (int v = 0; v < 5; ++v) Uc[c][v] = __ldg(gU + v * D::NP3 + gl2_gn<NP, 2>(gl2_ap<NP>(hb, c), r0, r1));
+    for (int v = 0; v < 5; ++v) Uc[c][v] = __ldg(gU + v * D::NP3 + gl2_gn<NP>(2, gl2_ap<NP>(hb, c), r0, r1));
+  // metric terms + Jacobian of the first own node of the lifting phase: a first touch of HBM, so it starts here
+  double Mn[9], sJn;
+  if (PARA) {
+    const int n = gl2_gn<NP>(2, gl2_ap<NP>(hb, 0), r0, r1);
+#pragma unroll
+    for (int m = 0; m < 9; ++m) Mn[m] = __ldg(gM + m * D::NP3 + n);
+    sJn = __ldg(A.m.sJ + (size_t)e * D::NP3 + n);
+  }
+  if (A.prefetchAhead > 0 && (int)blockIdx.x + A.prefetchAhead < A.nList) {
+    // pull the element that will run in this CTA slot one wave later (U, metrics, Jacobian: 60 KB) from HBM into L2 now
+    const int en = A.elems ? A.elems[blockIdx.x + A.prefetchAhead] : (int)blockIdx.x + A.prefetchAhead;
+    const char* pu = reinterpret_cast<const char*>(A.U + (size_t)en * 5 * D::NP3);
+    const char* pm = reinterpret_cast<const char*>(A.m.Met + (size_t)en * 9 * D::NP3);
+    const char* pj = reinterpret_cast<const char*>(A.m.sJ + (size_t)en * D::NP3);
+    constexpr int LU = 5 * D::NP3 * 8 / 128, LM = 9 * D::NP3 * 8 / 128, LJ = D::NP3 * 8 / 128;
+    for (int l = tid; l < LU + LM + LJ; l += NT) {
+      const char* p = l < LU ? pu + (size_t)l * 128 : l < LU + LM ? pm + (size_t)(l - LU) * 128 : pj + (size_t)(l - LU - LM) * 128;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+    }
+  }
   int faceSlot[FACE_IT];
+  bool faceLh[FACE_IT];  // plus side: L_HatPlus(N) (BR1)
   double faceSgn[FACE_IT];
   if (PARA) {
 #pragma unroll
     for (int it = 0; it < FACE_IT; ++it) {
       const int t = tid + it * NT;
       faceSlot[it] = -1;
+      faceLh[it] = false;
       faceSgn[it] = 0.;
       if (t < 6 * D::NP2) {
         const int ls = t / D::NP2 + 1, pq = t % D::NP2;
@@ -325,32 +325,64 @@ __global__ void __launch_bounds__(VolGL2Cfg<NP, PARA, NVL>::NT, VolGL2Cfg<NP, PA
           vn = gl2_phys<NP>(fa, fb, fd);
         faceSlot[it] = ((ls - 1) * 9 * D::NP2 + ab) | (vn << 16);
         faceSgn[it] = (sr.flip == 0) ? 1. : -1.;
+        faceLh[it] = !is_minus_side(ls);
       }
     }
     cp_async_commit();
   }
-  {
 #pragma unroll
-    for (int c = 0; c < HALF; ++c) {
-      double Pn[6];
-      const double sRho = cons_to_prim_srho(q, Uc[c], Pn);
-      const int s = gl2_sa<NP, 2>(gl2_ap<NP>(hb, c), r0, r1);
+  for (int c = 0; c < HALF; ++c) {
+    double Pn[6];
+    const double* const Ucc = Uc[c];
+    const double sRho = cons_to_prim_srho(q, Ucc, Pn);
+    const int s = gl2_sa<NP>(2, gl2_ap<NP>(hb, c), r0, r1);
 #pragma unroll
-      for (int v = 0; v < 4; ++v) sP[v * PL + s] = Pn[v];
-      sP[4 * PL + s] = PI ? 4. * Pn[PRES] : Pn[PRES];
-      if (PARA) sP[5 * PL + s] = Pn[TEMP];
-      // 6th two-point quantity: H = (rhoE+p)/rho (PI), E = rhoE/rho (KG), rhoE (SD, DU)
-      sP[PX * PL + s] = PI ? (Uc[c][ENER] + Pn[PRES]) * sRho : (STYPE == FLEXI_SPLITDG_KG) ? Uc[c][ENER] * sRho : Uc[c][ENER];
-    }
+    for (int v = 0; v < 4; ++v) sP[v * PL + s] = Pn[v];
+    sP[4 * PL + s] = PI ? 4. * Pn[PRES] : Pn[PRES];
+    if (PARA) sP[5 * PL + s] = Pn[TEMP];
+    // 6th two-point quantity: H = (rhoE+p)/rho (PI), E = rhoE/rho (KG), rhoE (SD, DU)
+    sP[PX * PL + s] = PI ? (Ucc[ENER] + Pn[PRES]) * sRho : (STYPE == FLEXI_SPLITDG_KG) ? Ucc[ENER] * sRho : Ucc[ENER];
   }
-  if (PARA) cp_async_wait_all();
-  __syncthreads();  // S1: primitive planes complete, face staging visible
-
-  double ut[HALF][5];
+  __syncthreads();  // S1: primitive planes complete
 
   if (PARA) {
+    // ---- reference-space derivatives of the lifting variables (lifting_volint.t90:67-83), one line sweep per direction:
+    //      xi and eta results change owner through the planes G1, G2; the zeta result stays with this thread ----
+    double gzt[HALF][NVC];
+#pragma unroll 1
+    for (int dir = 0; dir < 3; ++dir) {
+      int sa[NP];
+#pragma unroll
+      for (int p = 0; p < NP; ++p) sa[p] = gl2_sa<NP>(dir, gl2_ap<NP>(hb, p), r0, r1);
+#pragma unroll
+      for (int v = 0; v < NVC; ++v) {
+        const double* pl = sP + lift_prim(NVC, v) * PL;
+        double L[NP];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) L[p] = pl[sa[p]];
+#pragma unroll
+        for (int c = 0; c < HALF; ++c) {  // two partial sums per node: twice the independent FP64 chains
+          double s0 = B.dt[c] * L[0], s1 = B.dt[HALF * NP + c] * L[HALF];
+#pragma unroll
+          for (int p = 1; p < HALF; ++p) {
+            s0 = s0 + B.dt[p * NP + c] * L[p];
+            s1 = s1 + B.dt[(HALF + p) * NP + c] * L[HALF + p];
+          }
+          gzt[c][v] = sg * (s0 + s1);
+        }
+      }
+      if (dir < 2) {
+#pragma unroll
+        for (int c = 0; c < HALF; ++c)
+#pragma unroll
+          for (int v = 0; v < NVC; ++v) sW[(dir * NVC + v) * PL + sa[c]] = gzt[c][v];
+      }
+    }
     // ---- lifting flux of the six faces (lifting_fillflux.t90:81-107, strong form):
-    //      0.5*(UPrim_slave-UPrim_master)*SurfElem per lifting variable, in place of the prefetched neighbour trace ----
+    //      0.5*(UPrim_slave-UPrim_master)*SurfElem per lifting variable, already times L_Hat of the face, in place of the
+    //      prefetched neighbour trace.  Every thread converts the face nodes it fetched itself, so its own wait is enough; the
+    //      loads had the line sweeps above to arrive. ----
+    cp_async_wait_all();
 #pragma unroll
     for (int it = 0; it < FACE_IT; ++it) {
       if (faceSlot[it] >= 0) {
@@ -360,63 +392,40 @@ __global__ void __launch_bounds__(VolGL2Cfg<NP, PARA, NVL>::NT, VolGL2Cfg<NP, PA
 #pragma unroll
         for (int v = 0; v < 5; ++v) Un[v] = o[v * D::NP2];
         const double surf = o[8 * D::NP2];
+        const double lh = (LIFT == 1 && faceLh[it]) ? B.lhpN : B.lhm0;
         cons_to_prim(q, Un, Pb);
 #pragma unroll
-        for (int v = 0; v < NVL; ++v) {
-          const int pv = lift_prim(NVL, v);
-          o[v * D::NP2] = 0.5 * (faceSgn[it] * (Pb[pv] - sP[pv * PL + nF])) * surf;
+        for (int v = 0; v < NVC; ++v) {
+          const int pv = lift_prim(NVC, v);
+          o[v * D::NP2] = (0.5 * (faceSgn[it] * (Pb[pv] - sP[pv * PL + nF])) * surf) * lh;
         }
       }
     }
-    // ---- lifting derivatives along xi (xi ownership) and eta (eta ownership) -> hand-over planes G1, G2 ----
-    {
-      double g[HALF][NVL];
-      gl2_lift_line<NP, NVL, 0>(B, sP, hb, r0, r1, g);
-#pragma unroll
-      for (int c = 0; c < HALF; ++c)
-#pragma unroll
-        for (int v = 0; v < NVL; ++v) sW[v * PL + gl2_sa<NP, 0>(gl2_ap<NP>(hb, c), r0, r1)] = g[c][v];
-      gl2_lift_line<NP, NVL, 1>(B, sP, hb, r0, r1, g);
-#pragma unroll
-      for (int c = 0; c < HALF; ++c)
-#pragma unroll
-        for (int v = 0; v < NVL; ++v) sW[(NVL + v) * PL + gl2_sa<NP, 1>(gl2_ap<NP>(hb, c), r0, r1)] = g[c][v];
-    }
     __syncthreads();  // S2: G1, G2 and the face lifting fluxes complete
 
-    // ---- zeta ownership: zeta derivative, metric combination, surface part, Jacobian, gradient traces, viscous flux ----
+    // ---- zeta ownership: metric combination, surface part, Jacobian, traces for the side kernel, viscous flux ----
     {
-      constexpr int LV = (NVL == 5) ? 1 : 0;
+      constexpr int LV = (NVC == 5) ? 1 : 0;
       const int i = r0, j = r1;
-      // metric terms + Jacobian of the own nodes straight from HBM, one node ahead of the arithmetic
-      double Mn[9], sJn;
-      {
-        const int n = gl2_gn<NP, 2>(gl2_ap<NP>(hb, 0), r0, r1);
-#pragma unroll
-        for (int m = 0; m < 9; ++m) Mn[m] = __ldg(gM + m * D::NP3 + n);
-        sJn = __ldg(A.m.sJ + (size_t)e * D::NP3 + n);
-      }
-      double gzt[HALF][NVL];
-      gl2_lift_line<NP, NVL, 2>(B, sP, hb, r0, r1, gzt);
 #pragma unroll
       for (int c = 0; c < HALF; ++c) {
         const int k = gl2_ap<NP>(hb, c);
-        const int s = gl2_sa<NP, 2>(k, r0, r1);
+        const int s = gl2_sa<NP>(2, k, r0, r1);
         const int n = i + NP * (j + NP * k);
         double Mc[9];
 #pragma unroll
         for (int m = 0; m < 9; ++m) Mc[m] = Mn[m];
         const double sJc = sJn;
-        if (c + 1 < HALF) {
-          const int n1 = gl2_gn<NP, 2>(gl2_ap<NP>(hb, c + 1), r0, r1);
+        if (c + 1 < HALF) {  // metric terms + Jacobian straight from HBM, one node ahead of the arithmetic
+          const int n1 = gl2_gn<NP>(2, gl2_ap<NP>(hb, c + 1), r0, r1);
 #pragma unroll
           for (int m = 0; m < 9; ++m) Mn[m] = __ldg(gM + m * D::NP3 + n1);
           sJn = __ldg(A.m.sJ + (size_t)e * D::NP3 + n1);
         }
-        double gx[NVL], gy[NVL], gz[NVL];
+        double gx[NVC], gy[NVC], gz[NVC];
 #pragma unroll
-        for (int v = 0; v < NVL; ++v) {
-          const double gxi = sW[v * PL + s], geta = sW[(NVL + v) * PL + s], gzeta = gzt[c][v];
+        for (int v = 0; v < NVC; ++v) {
+          const double gxi = sW[v * PL + s], geta = sW[(NVC + v) * PL + s], gzeta = gzt[c][v];
           gx[v] = Mc[0] * gxi + Mc[3] * geta + Mc[6] * gzeta;
           gy[v] = Mc[1] * gxi + Mc[4] * geta + Mc[7] * gzeta;
           gz[v] = Mc[2] * gxi + Mc[5] * geta + Mc[8] * gzeta;
@@ -427,23 +436,22 @@ __global__ void __launch_bounds__(VolGL2Cfg<NP, PARA, NVL>::NT, VolGL2Cfg<NP, PA
         const bool onI = (i == 0) | (i == N), onJ = (j == 0) | (j == N), onK = (c == 0);
         const int lsI = (i == 0) ? XI_MINUS : XI_PLUS, lsJ = (j == 0) ? ETA_MINUS : ETA_PLUS, lsK = hb ? ZETA_PLUS : ZETA_MINUS;
         const int abI = j + NP * k, abJ = i + NP * k, abK = i + NP * j;
-        double gxo[NVL], gyo[NVL], gzo[NVL];  // BR2: gradients without the surface part (what the faces are prolonged from)
+        double gxo[NVC], gyo[NVC], gzo[NVC];  // BR2: gradients without the surface part (what the faces are prolonged from)
         // lifting, surface part (BR1 lifting_br1.t90:195-292; BR2 lifting_br2.t90:194-311)
         auto surf_in = [&](int ls, int ab) {
           const double* o = sX + (ls - 1) * 9 * D::NP2 + ab;
           const double n0 = o[5 * D::NP2], n1 = o[6 * D::NP2], n2 = o[7 * D::NP2];
-          const double lh = (LIFT == 1) ? (is_minus_side(ls) ? B.lhm0 : B.lhpN) : B.lhm0;
 #pragma unroll
-          for (int v = 0; v < NVL; ++v) {
-            const double f = o[v * D::NP2];
+          for (int v = 0; v < NVC; ++v) {
+            const double f = o[v * D::NP2];  // Flux * L_Hat
             if (LIFT == 1) {
-              gx[v] = gx[v] + (f * n0) * lh;
-              gy[v] = gy[v] + (f * n1) * lh;
-              gz[v] = gz[v] + (f * n2) * lh;
+              gx[v] = gx[v] + f * n0;
+              gy[v] = gy[v] + f * n1;
+              gz[v] = gz[v] + f * n2;
             } else {
-              gx[v] = gx[v] + sJc * (f * n0) * lh;
-              gy[v] = gy[v] + sJc * (f * n1) * lh;
-              gz[v] = gz[v] + sJc * (f * n2) * lh;
+              gx[v] = gx[v] + sJc * (f * n0);
+              gy[v] = gy[v] + sJc * (f * n1);
+              gz[v] = gz[v] + sJc * (f * n2);
             }
           }
         };
@@ -452,14 +460,14 @@ __global__ void __launch_bounds__(VolGL2Cfg<NP, PARA, NVL>::NT, VolGL2Cfg<NP, PA
           if (onJ) surf_in(lsJ, abJ);
           if (onK) surf_in(lsK, abK);
 #pragma unroll
-          for (int v = 0; v < NVL; ++v) {
+          for (int v = 0; v < NVC; ++v) {
             gx[v] = gx[v] * sJc;
             gy[v] = gy[v] * sJc;
             gz[v] = gz[v] * sJc;
           }
         } else {  // BR2: Jacobian first, then sJ*Flux*L_HatMinus(0) on the boundary node
 #pragma unroll
-          for (int v = 0; v < NVL; ++v) {
+          for (int v = 0; v < NVC; ++v) {
             gx[v] = gx[v] * sJc;
             gy[v] = gy[v] * sJc;
             gz[v] = gz[v] * sJc;
@@ -473,10 +481,10 @@ __global__ void __launch_bounds__(VolGL2Cfg<NP, PARA, NVL>::NT, VolGL2Cfg<NP, PA
         }
         if (A.gvol[0]) {
 #pragma unroll
-          for (int v = 0; v < NVL; ++v) {
-            A.gvol[0][((size_t)e * NVL + v) * D::NP3 + n] = gx[v];
-            A.gvol[1][((size_t)e * NVL + v) * D::NP3 + n] = gy[v];
-            A.gvol[2][((size_t)e * NVL + v) * D::NP3 + n] = gz[v];
+          for (int v = 0; v < NVC; ++v) {
+            A.gvol[0][((size_t)e * NVL + v + VOFF) * D::NP3 + n] = gx[v];
+            A.gvol[1][((size_t)e * NVL + v + VOFF) * D::NP3 + n] = gy[v];
+            A.gvol[2][((size_t)e * NVL + v + VOFF) * D::NP3 + n] = gz[v];
           }
         }
         // ---- viscous flux of this node (flux.f90:149-241) ----
@@ -495,15 +503,15 @@ __global__ void __launch_bounds__(VolGL2Cfg<NP, PARA, NVL>::NT, VolGL2Cfg<NP, PA
           const int fl = fd & 0x3fffffff, side = fl / D::NP2, pq = fl % D::NP2;
           const double* of = sX + (ls - 1) * 9 * D::NP2 + ab;
           const double n0 = of[5 * D::NP2], n1 = of[6 * D::NP2], n2 = of[7 * D::NP2];
-          double gfx[NVL], gfy[NVL], gfz[NVL];
+          double gfx[NVC], gfy[NVC], gfz[NVC];
           if (LIFT == 2) {  // BR2 face gradient: volume-only value + eta*L_Minus(0)*sJ*Flux*L_HatMinus(0) of the side itself
             const double w = sEta[ls - 1] * B.lm0;
 #pragma unroll
-            for (int v = 0; v < NVL; ++v) {
+            for (int v = 0; v < NVC; ++v) {
               const double f = of[v * D::NP2];
-              gfx[v] = gxo[v] + w * (sJc * (f * n0) * B.lhm0);
-              gfy[v] = gyo[v] + w * (sJc * (f * n1) * B.lhm0);
-              gfz[v] = gzo[v] + w * (sJc * (f * n2) * B.lhm0);
+              gfx[v] = gxo[v] + w * (sJc * (f * n0));
+              gfy[v] = gyo[v] + w * (sJc * (f * n1));
+              gfz[v] = gzo[v] + w * (sJc * (f * n2));
             }
           }
           if (A.fullGrad || (fd & 0x40000000)) {
@@ -512,8 +520,8 @@ __global__ void __launch_bounds__(VolGL2Cfg<NP, PARA, NVL>::NT, VolGL2Cfg<NP, PA
             double* const d2 = master ? A.gm[2] : A.gs[2];
             const size_t o0 = (size_t)side * NVL * D::NP2 + pq;
 #pragma unroll
-            for (int v = 0; v < NVL; ++v) {
-              const size_t o = o0 + (size_t)v * D::NP2;
+            for (int v = 0; v < NVC; ++v) {
+              const size_t o = o0 + (size_t)(v + VOFF) * D::NP2;
               d0[o] = (LIFT == 2) ? gfx[v] : gx[v];
               d1[o] = (LIFT == 2) ? gfy[v] : gy[v];
               d2[o] = (LIFT == 2) ? gfz[v] : gz[v];
@@ -546,31 +554,35 @@ __global__ void __launch_bounds__(VolGL2Cfg<NP, PARA, NVL>::NT, VolGL2Cfg<NP, PA
     __syncthreads();  // S3: viscous flux planes complete; face staging is free from here on
   }
 
-  // ---- zeta phase ----
-  gl2_pair_phase<NP, STYPE, PARA, 2>(B, sP, sW + 8 * PL, gM + 6 * D::NP3, hb, r0, r1, ut);
+  // ---- three direction sweeps (zeta, xi, eta) of ONE copy of the sweep code; the partial sums change owner through the Ut
+  //      hand-over planes, the last sweep sends the raw volume integral to HBM ----
+#pragma unroll 1
+  for (int it = 0; it < 3; ++it) {
+    const int dir = (it == 0) ? 2 : it - 1;
+    int sa[NP], gn[NP];  // indexed by canonical position
 #pragma unroll
-  for (int c = 0; c < HALF; ++c)
-#pragma unroll
-    for (int v = 0; v < 5; ++v) sUT[v * PL + gl2_sa<NP, 2>(gl2_ap<NP>(hb, c), r0, r1)] = ut[c][v];
-  __syncthreads();  // S4
-  // ---- xi phase ----
-  gl2_pair_phase<NP, STYPE, PARA, 0>(B, sP, sW, gM, hb, r0, r1, ut);
-#pragma unroll
-  for (int c = 0; c < HALF; ++c)
-#pragma unroll
-    for (int v = 0; v < 5; ++v) {
-      double* p = sUT + v * PL + gl2_sa<NP, 0>(gl2_ap<NP>(hb, c), r0, r1);
-      *p = *p + ut[c][v];
+    for (int p = 0; p < NP; ++p) {
+      sa[p] = gl2_sa<NP>(dir, gl2_ap<NP>(hb, p), r0, r1);
+      gn[p] = gl2_gn<NP>(dir, gl2_ap<NP>(hb, p), r0, r1);
     }
-  __syncthreads();  // S5
-  // ---- eta phase, then the raw volume integral goes to HBM ----
-  gl2_pair_phase<NP, STYPE, PARA, 1>(B, sP, sW + 4 * PL, gM + 3 * D::NP3, hb, r0, r1, ut);
+    double ut[HALF][5];
+    gl2_pair_sweep<NP, STYPE, PARA>(B, sP, sW + dir * 4 * PL, gM + dir * 3 * D::NP3, sa, gn, ut);
+    if (it < 2) {
 #pragma unroll
-  for (int c = 0; c < HALF; ++c) {
-    const int p = gl2_ap<NP>(hb, c);
+      for (int c = 0; c < HALF; ++c)
 #pragma unroll
-    for (int v = 0; v < 5; ++v)
-      A.Ut[((size_t)e * 5 + v) * D::NP3 + gl2_gn<NP, 1>(p, r0, r1)] = sUT[v * PL + gl2_sa<NP, 1>(p, r0, r1)] + ut[c][v];
+        for (int v = 0; v < 5; ++v) {
+          double* p = sUT + v * PL + sa[c];
+          const double prev = (it == 0) ? 0. : *p;
+          *p = prev + sg * ut[c][v];
+        }
+      __syncthreads();  // S4, S5
+    } else {
+#pragma unroll
+      for (int c = 0; c < HALF; ++c)
+#pragma unroll
+        for (int v = 0; v < 5; ++v) A.Ut[((size_t)e * 5 + v) * D::NP3 + gn[c]] = sUT[v * PL + sa[c]] + sg * ut[c][v];
+    }
   }
 }
 
