@@ -141,7 +141,6 @@ cudaError_t setup() {
     FX_SPLIT_TYPES(X)
 #undef X
   }
-  if ((e = cudaFuncSetAttribute(k_update<NP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(k_update<NP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem)) != cudaSuccess) return e;
   const int pro = (int)(sizeof(double) * (D::NBASIS + 6 * D::NP3));
   if ((e = cudaFuncSetAttribute(k_prolong<NP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pro)) != cudaSuccess) return e;
@@ -213,14 +212,17 @@ cudaError_t flux_bc(const BCArgs& a, cudaStream_t s) {
 cudaError_t flux(const FluxArgs& a, cudaStream_t s) {
   if (a.nSidesRange <= 0) return cudaSuccess;
   const long n = (long)a.nSidesRange * D::NP2;
-  k_flux<NP><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(a);
+  if (a.q.riemann == FLEXI_RIEMANN_LF)
+    k_flux<NP, FLEXI_RIEMANN_LF><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(a);
+  else
+    k_flux<NP, 0><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(a);
   return cudaGetLastError();
 }
 
 cudaError_t update(bool gl, const UpdArgs& a, int nBlocks, cudaStream_t s) {
   if (nBlocks <= 0) return cudaSuccess;
   if (gl)
-    k_update<NP, true><<<nBlocks, D::NP3, upd_smem, s>>>(a);
+    k_update_gl<NP><<<nBlocks, D::NP3, 0, s>>>(a);
   else
     k_update<NP, false><<<nBlocks, D::NP3, upd_smem, s>>>(a);
   return cudaGetLastError();

@@ -16,7 +16,11 @@ def f(r, k):
 phase = 0
 agg = collections.defaultdict(collections.Counter)
 ST = ("wait", "long_sb", "short_sb", "mio", "barrier", "no_inst", "lg", "math", "selected")
+seen = set()
 for r in d:
+    if r[ix["Address"]] in seen:  # a report with several captures lists the kernel once per capture: keep the first
+        break
+    seen.add(r[ix["Address"]])
     s = r[ix["Source"]]
     a = agg[phase]
     a["samples"] += f(r, "# Samples")
