@@ -58,12 +58,22 @@ cudaError_t volume_gl_launch(int lift, const VolArgs& a, int nBlocks, cudaStream
 // line-resident split-form GL kernel (volume_gl2.cuh) for even NP; odd NP keeps k_volume_gl
 constexpr bool HAS_GL2 = (NP % 2 == 0);
 bool g_use_gl2 = HAS_GL2;
+// measurement hook: FLEXI_GPU_SMEM_PAD=<bytes> of extra dynamic shared memory per CTA of k_volume_gl2 (forces 1 CTA/SM to
+// separate what the second resident element buys from what contention costs; profiles/README.md)
+int gl2_smem_pad() {
+  static int pad = -1;
+  if (pad < 0) {
+    const char* v = getenv("FLEXI_GPU_SMEM_PAD");
+    pad = v ? atoi(v) : 0;
+  }
+  return pad;
+}
 template <int STYPE, bool PARA, int NVL, int NVC, int LIFT>
 struct GL2 {
   static constexpr int NPE = HAS_GL2 ? NP : 2;  // odd NP never instantiates the real kernel
   using C = VolGL2Cfg<NPE, PARA>;
   static cudaError_t setup() {
-    return cudaFuncSetAttribute(k_volume_gl2<NPE, STYPE, PARA, NVL, NVC, LIFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::BYTES);
+    return cudaFuncSetAttribute(k_volume_gl2<NPE, STYPE, PARA, NVL, NVC, LIFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::BYTES + gl2_smem_pad());
   }
   static cudaError_t launch(const VolArgs& a, int nBlocks, cudaStream_t s) {
     VolArgs2<NPE> aa;
@@ -78,7 +88,7 @@ struct GL2 {
     aa.b.lhm0 = b[Dim<NPE>::O_LHM];
     aa.b.lhpN = b[Dim<NPE>::O_LHP + NPE - 1];
     aa.b.lm0 = b[Dim<NPE>::O_LM];
-    k_volume_gl2<NPE, STYPE, PARA, NVL, NVC, LIFT><<<nBlocks, C::NT, C::BYTES, s>>>(aa);
+    k_volume_gl2<NPE, STYPE, PARA, NVL, NVC, LIFT><<<nBlocks, C::NT, C::BYTES + gl2_smem_pad(), s>>>(aa);
     return cudaGetLastError();
   }
 };
@@ -141,6 +151,7 @@ cudaError_t setup() {
     FX_SPLIT_TYPES(X)
 #undef X
   }
+  if ((e = cudaFuncSetAttribute(k_update<NP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(k_update<NP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem)) != cudaSuccess) return e;
   const int pro = (int)(sizeof(double) * (D::NBASIS + 6 * D::NP3));
   if ((e = cudaFuncSetAttribute(k_prolong<NP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pro)) != cudaSuccess) return e;
@@ -222,7 +233,7 @@ cudaError_t flux(const FluxArgs& a, cudaStream_t s) {
 cudaError_t update(bool gl, const UpdArgs& a, int nBlocks, cudaStream_t s) {
   if (nBlocks <= 0) return cudaSuccess;
   if (gl)
-    k_update_gl<NP><<<nBlocks, D::NP3, 0, s>>>(a);
+    k_update<NP, true><<<nBlocks, D::NP3, upd_smem, s>>>(a);
   else
     k_update<NP, false><<<nBlocks, D::NP3, upd_smem, s>>>(a);
   return cudaGetLastError();

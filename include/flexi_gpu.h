@@ -200,7 +200,10 @@ int flexi_gpu_get_array(flexi_gpu_handle* h, int32_t which, double* out);
 
 /* Volume gradients normally never leave the SM; with on != 0 every later evaluation also stores gradUx/y/z in device memory so
  * that FLEXI_ARR_GRADU{X,Y,Z} return "the gradients left by the last DG operator call" like the module arrays do
- * (testcase/taylorgreenvortex/testcase.f90:249).  Without it the first FLEXI_ARR_GRADU* request recomputes them from the current U. */
+ * (testcase/taylorgreenvortex/testcase.f90:249).  Without it the first FLEXI_ARR_GRADU* request recomputes them from the current U.
+ * The gradient TRACES (FLEXI_ARR_GRADU?_MASTER/SLAVE) follow the same rule: flexi_gpu_dg_time_derivative leaves all of them, the RK
+ * stages of flexi_gpu_timestep write them on boundary-condition sides only (the split-form Gauss-Lobatto kernels hand n.F_visc of
+ * each side to the side kernel instead), and a request after a time step recomputes them from the current U at the last stage time. */
 int flexi_gpu_keep_gradients(flexi_gpu_handle* h, int32_t on);
 
 /* Operator-level entry points (what the reference's own unit tests drive, unitTests/ProlongToFace.f90, SurfInt.f90).
