@@ -133,7 +133,17 @@ def run_cpu(args, steps, warmup, nel, cores):
     return ndof * nst * steps / el / 1e9, el, nranks, ndof
 
 
+def emit(line, fd):
+    """Write the one JSON line to the real stdout (fd saved before anything could print there)."""
+    os.write(fd, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    # stdout carries exactly ONE JSON line: everything else that prints to fd 1 (NCCL's version banner at NCCL_DEBUG=VERSION,
+    # torchrun notices, library chatter) is sent to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -170,7 +180,7 @@ def main():
                 "config": {"workload": workload, "cpu_sample_nel": args.cpu_nel},
                 "cpu_baseline": {"value": val, "unit": "GDOF/s", "cores": nr, "kind": "port", "sample": sample},
                 "e2e": {"value": val, "unit": "GDOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line), flush=True)
+        emit(line, real_stdout)
         return
 
     import torch
@@ -184,6 +194,9 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # stdout carries exactly one JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION/INFO
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE") and not os.environ.get("FLEXI_BENCH_KEEP_NCCL_DEBUG"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group(backend="cpu:gloo,cuda:nccl", rank=rank, world_size=world)
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}"
 
@@ -323,7 +336,7 @@ def main():
                         "d2h_bytes_per_step": ubytes / args.steps + 24,
                         "what": "set_state(pinned host U) + steps x (CalcTimeStep + TimeStep) + get_state(pinned host U) through the C ABI"},
                 "roofline": roofline, "cpu_baseline": cpu}
-        print(json.dumps(line), flush=True)
+        emit(line, real_stdout)
     if world > 1:
         dist.destroy_process_group()
 

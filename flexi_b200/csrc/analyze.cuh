@@ -1,0 +1,145 @@
+// analyze.cuh -- AnalyzeTestcase of the Taylor-Green vortex test case on the device, steps 1-4 of
+// /root/reference/src/testcase/taylorgreenvortex/testcase.f90:241-420 (nullify, interpolate U / sJ / GradVel to the analyze
+// mesh with Vdm_GaussN_NAnalyze (ChangeBasis3D), ConsToPrim + gradient-based quantities, integrate with wGPVolAnalyze/sJ).
+// Steps 5-7 (MPI_REDUCE, normalisation with Vol and rho0, file output) stay in the host.  SURVEY.md section 8(f) rank 1: the
+// analysis runs every nAnalyzeTestCase (10) steps and otherwise forces U and three gradient arrays (4.5 GB at config 2) over
+// PCIe each time; here 12 doubles come back.
+#pragma once
+#include "layout.cuh"
+
+namespace fx {
+
+enum { TGV_T_MEAN = 0, TGV_ENTROPY, TGV_EKIN, TGV_EKIN_COMP, TGV_ENSTR, TGV_DR_U, TGV_DR_S, TGV_DR_SD, TGV_DR_P, TGV_ED_S, TGV_ED_D,
+       TGV_VORT_MAX, TGV_NSUMS };
+
+struct TgvArgs {
+  Eqn q;
+  int np, na1, nvl, parabolic;  // N+1, NAnalyze+1, nVarLifting
+  const double* U;         // [e][5][NP3]
+  const double* sJ;        // [e][NP3]
+  const double* gvol[3];   // gradU{x,y,z} [e][nvl][NP3]
+  const double* vdm;       // Vdm_GaussN_NAnalyze as [iOut][iIn]
+  const double* wVol;      // wGPVolAnalyze [k][j][i]
+  double* out;             // [e][TGV_NSUMS]
+};
+
+// one CTA per element, one thread per (i,j) of the analyze mesh; the analyze mesh is walked slab by slab in zeta so that a thread
+// holds one analyze point (15 interpolated fields) at a time
+__global__ void k_tgv_analyze(TgvArgs A) {
+  extern __shared__ double sm[];
+  const int np = A.np, na1 = A.na1, np2 = np * np, np3 = np2 * np;
+  const int nf = A.parabolic ? 15 : 6;  // sJ, U(5), GradVel(3x3)
+  double* sX = sm;                      // [nf][np3]
+  double* sV = sX + nf * np3;           // [na1][np]
+  double* sT1 = sV + na1 * np;          // [nf][np2]      zeta pass of the current slab
+  double* sT2 = sT1 + nf * np2;         // [nf][na1*np]   + xi pass
+  double* sRed = sT2 + nf * na1 * np;   // [TGV_NSUMS][32]
+  const int tid = threadIdx.x, nt = blockDim.x, e = blockIdx.x;
+  const int v0 = (A.nvl == 5) ? 1 : 0;  // LIFT_VELV
+  for (int t = tid; t < np3; t += nt) {
+    sX[t] = A.sJ[(size_t)e * np3 + t];
+    for (int v = 0; v < 5; ++v) sX[(1 + v) * np3 + t] = A.U[((size_t)e * 5 + v) * np3 + t];
+    if (A.parabolic)
+      for (int d = 0; d < 3; ++d)
+        for (int c = 0; c < 3; ++c) sX[(6 + 3 * d + c) * np3 + t] = A.gvol[d][((size_t)e * A.nvl + v0 + c) * np3 + t];
+  }
+  for (int t = tid; t < na1 * np; t += nt) sV[t] = A.vdm[t];
+  __syncthreads();
+  const int iO = tid % na1, jO = tid / na1;
+  const Eqn& q = A.q;
+  double acc[TGV_NSUMS];
+  for (int s = 0; s < TGV_NSUMS; ++s) acc[s] = 0.;
+  for (int k = 0; k < na1; ++k) {
+    for (int t = tid; t < nf * np2; t += nt) {  // zeta pass
+      const int f = t / np2, ij = t % np2;
+      double s = 0.;
+      for (int l = 0; l < np; ++l) s = s + sV[k * np + l] * sX[f * np3 + ij + np2 * l];
+      sT1[t] = s;
+    }
+    __syncthreads();
+    for (int t = tid; t < nf * na1 * np; t += nt) {  // xi pass
+      const int f = t / (na1 * np), r = t % (na1 * np), io = r % na1, j = r / na1;
+      double s = 0.;
+      for (int l = 0; l < np; ++l) s = s + sV[io * np + l] * sT1[f * np2 + l + np * j];
+      sT2[t] = s;
+    }
+    __syncthreads();
+    double val[15];
+    for (int f = 0; f < nf; ++f) {  // eta pass: the thread's analyze point
+      double s = 0.;
+      for (int l = 0; l < np; ++l) s = s + sV[jO * np + l] * sT2[f * na1 * np + iO + na1 * l];
+      val[f] = s;
+    }
+    double P[6];
+    cons_to_prim(q, val + 1, P);
+    const double w = A.wVol[iO + na1 * (jO + na1 * k)] / val[0];  // IntFactor, testcase.f90:381
+    const double v2 = P[VEL1] * P[VEL1] + P[VEL2] * P[VEL2] + P[VEL3] * P[VEL3];
+    acc[TGV_T_MEAN] += w * P[TEMP];
+    acc[TGV_ENTROPY] += w * (-q.sKappaM1) * P[DENS] * (log(P[PRES]) - q.kappa * log(P[DENS]));
+    acc[TGV_EKIN] += w * 0.5 * v2;
+    acc[TGV_EKIN_COMP] += w * 0.5 * P[DENS] * v2;
+    if (A.parabolic) {
+      // GradVel(c,d) = d v_c / d x_d = val[6 + 3*d + c]   (testcase.f90:352-354)
+      double G[3][3];
+      for (int d = 0; d < 3; ++d)
+        for (int c = 0; c < 3; ++c) G[c][d] = val[6 + 3 * d + c];
+      const double divU = G[0][0] + G[1][1] + G[2][2];
+      double sumG = 0., sumS = 0., sumSd = 0.;
+      for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) {
+          const double S = 0.5 * (G[a][b] + G[b][a]);
+          const double Sd = (a == b) ? S - 1. / 3. * divU : S;
+          sumG += G[a][b] * G[a][b];
+          sumS += S * S;
+          sumSd += Sd * Sd;
+        }
+      const double o1 = G[2][1] - G[1][2], o2 = G[0][2] - G[2][0], o3 = G[1][0] - G[0][1];
+      const double oo = o1 * o1 + o2 * o2 + o3 * o3;
+      acc[TGV_VORT_MAX] = fmax(acc[TGV_VORT_MAX], sqrt(oo));
+      acc[TGV_ENSTR] += w * 0.5 * P[DENS] * oo;
+      acc[TGV_DR_U] += w * sumG;
+      acc[TGV_DR_S] += w * sumS;
+      acc[TGV_DR_SD] += w * sumSd;
+      acc[TGV_DR_P] += w * P[PRES] * divU;
+      acc[TGV_ED_S] += w * q.mu0 * oo;  // VISCOSITY_TEMPERATURE = mu0 for PP_VISC=0 (eos.h:73-79)
+      acc[TGV_ED_D] += w * q.mu0 * divU * divU;
+    }
+    __syncthreads();  // the next slab overwrites sT1 / sT2
+  }
+  // block reduction: sums in a fixed order (deterministic), the vorticity as a max
+  const int lane = tid & 31, wid = tid >> 5, nw = (nt + 31) >> 5;
+  for (int s = 0; s < TGV_NSUMS; ++s) {
+    double v = acc[s];
+    for (int o = 16; o > 0; o >>= 1) {
+      const double u = __shfl_down_sync(0xffffffffu, v, o);
+      v = (s == TGV_VORT_MAX) ? fmax(v, u) : v + u;
+    }
+    if (lane == 0) sRed[s * 32 + wid] = v;
+  }
+  __syncthreads();
+  if (tid < TGV_NSUMS) {
+    double v = sRed[tid * 32];
+    for (int w2 = 1; w2 < nw; ++w2) v = (tid == TGV_VORT_MAX) ? fmax(v, sRed[tid * 32 + w2]) : v + sRed[tid * 32 + w2];
+    A.out[(size_t)e * TGV_NSUMS + tid] = v;
+  }
+}
+
+// sum (max for the vorticity) over the elements of the rank, fixed order
+__global__ void k_tgv_reduce(const double* in, int nElems, double* out) {
+  __shared__ double s[256];
+  const int tid = threadIdx.x;
+  for (int q = 0; q < TGV_NSUMS; ++q) {
+    double v = 0.;
+    for (int e = tid; e < nElems; e += 256) v = (q == TGV_VORT_MAX) ? fmax(v, in[(size_t)e * TGV_NSUMS + q]) : v + in[(size_t)e * TGV_NSUMS + q];
+    s[tid] = v;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if (tid < o) s[tid] = (q == TGV_VORT_MAX) ? fmax(s[tid], s[tid + o]) : s[tid] + s[tid + o];
+      __syncthreads();
+    }
+    if (tid == 0) out[q] = s[0];
+    __syncthreads();
+  }
+}
+
+}  // namespace fx

@@ -10,6 +10,7 @@
 #include <string>
 #include <vector>
 
+#include "analyze.cuh"
 #include "common_kernels.cuh"
 #include "nccl_dyn.h"
 #include "np_ops.h"
@@ -959,6 +960,59 @@ int flexi_gpu_get_array(flexi_gpu_handle* h, int32_t which, double* out) {
       return download_aos(h, h->gs[which - FLEXI_ARR_GRADUX_SLAVE], out, h->nvl, np2, h->nSides);
     default: return fail(FLEXI_GPU_ERR_ARG, "unknown array id %d", which);
   }
+}
+
+int flexi_gpu_analyze_tgv(flexi_gpu_handle* h, int32_t NAnalyze, const double* Vdm_GaussN_NAnalyze, const double* wGPVolAnalyze, double* sums) {
+  ENTER(h);
+  if (!Vdm_GaussN_NAnalyze || !wGPVolAnalyze || !sums) return fail(FLEXI_GPU_ERR_ARG, "null argument");
+  if (NAnalyze < 1 || NAnalyze > 31) return fail(FLEXI_GPU_ERR_ARG, "NAnalyze=%d outside 1..31", NAnalyze);
+  const int np = h->np, na1 = NAnalyze + 1;
+  if (h->para && !h->keepGrad) {  // gradients are not kept: recompute them from the current U (like FLEXI_ARR_GRADU*)
+    CKR(flexi_gpu_keep_gradients(h, 1));
+    if (!h->Ut) CKR(dalloc(h, &h->Ut, (size_t)h->nElems * 5 * h->np3));
+    CKR(rhs(h, h->lastT, 0, 0., 0.));
+  }
+  // tables: Vdm as [iOut][iIn], wGPVolAnalyze as is ((i,j,k) with i fastest)
+  std::vector<double> tab((size_t)na1 * np + (size_t)na1 * na1 * na1);
+  for (int io = 0; io < na1; ++io)
+    for (int ii = 0; ii < np; ++ii) tab[(size_t)io * np + ii] = Vdm_GaussN_NAnalyze[(size_t)ii * na1 + io];
+  memcpy(tab.data() + (size_t)na1 * np, wGPVolAnalyze, sizeof(double) * na1 * na1 * na1);
+  const size_t need = tab.size() + (size_t)h->nElems * TGV_NSUMS + TGV_NSUMS;
+  CKR(ensure_stage(h, need));
+  double* dTab = h->stage;
+  double* dPart = dTab + tab.size();
+  double* dOut = dPart + (size_t)h->nElems * TGV_NSUMS;
+  CK(cudaMemcpyAsync(dTab, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice, h->sc));
+  h->h2d += (int64_t)(tab.size() * 8);
+  TgvArgs a{};
+  a.q = h->q;
+  a.np = np;
+  a.na1 = na1;
+  a.nvl = h->nvl;
+  a.parabolic = h->para ? 1 : 0;
+  a.U = h->U;
+  a.sJ = h->m.sJ;
+  for (int d = 0; d < 3; ++d) a.gvol[d] = h->gvol[d];
+  a.vdm = dTab;
+  a.wVol = dTab + (size_t)na1 * np;
+  a.out = dPart;
+  const int nf = h->para ? 15 : 6;
+  const size_t smem = sizeof(double) * ((size_t)nf * h->np3 + (size_t)na1 * np + (size_t)nf * h->np2 + (size_t)nf * na1 * np + TGV_NSUMS * 32);
+  CK(cudaFuncSetAttribute(k_tgv_analyze, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  {
+    Timer tm(h, KC_DT, h->sc);
+    k_tgv_analyze<<<h->nElems, na1 * na1, smem, h->sc>>>(a);
+  }
+  CK(cudaGetLastError());
+  {
+    Timer tm(h, KC_DT, h->sc);
+    k_tgv_reduce<<<1, 256, 0, h->sc>>>(dPart, h->nElems, dOut);
+  }
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(sums, dOut, TGV_NSUMS * 8, cudaMemcpyDeviceToHost, h->sc));
+  h->d2h += TGV_NSUMS * 8;
+  CK(cudaStreamSynchronize(h->sc));
+  return 0;
 }
 
 int flexi_gpu_prolong_to_face(flexi_gpu_handle* h, const double* Uvol, double* Uface_master, double* Uface_slave, int32_t doMPISides) {

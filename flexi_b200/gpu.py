@@ -30,7 +30,7 @@ KERNEL_CLASSES = ("volume", "flux", "update", "prolong", "calc_timestep", "layou
 EXPORTS = ("flexi_gpu_last_error", "flexi_gpu_abi_version", "flexi_gpu_nccl_unique_id", "flexi_gpu_init", "flexi_gpu_finalize",
            "flexi_gpu_set_state", "flexi_gpu_get_state", "flexi_gpu_dg_time_derivative", "flexi_gpu_timestep",
            "flexi_gpu_timestep_n", "flexi_gpu_calc_timestep", "flexi_gpu_get_array", "flexi_gpu_keep_gradients",
-           "flexi_gpu_prolong_to_face", "flexi_gpu_surf_int", "flexi_gpu_counters", "flexi_gpu_kernel_times",
+           "flexi_gpu_prolong_to_face", "flexi_gpu_surf_int", "flexi_gpu_analyze_tgv", "flexi_gpu_counters", "flexi_gpu_kernel_times",
            "flexi_gpu_set_profiling", "flexi_gpu_synchronize", "flexi_gpu_stream")
 
 
@@ -69,6 +69,7 @@ def lib():
     L.flexi_gpu_keep_gradients.argtypes = [P, I32]
     L.flexi_gpu_prolong_to_face.argtypes = [P, PD, PD, PD, I32]
     L.flexi_gpu_surf_int.argtypes = [P, PD, PD, PD, I32]
+    L.flexi_gpu_analyze_tgv.argtypes = [P, I32, PD, PD, PD]
     L.flexi_gpu_counters.argtypes = [P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.flexi_gpu_kernel_times.argtypes = [P, PD, C.POINTER(C.c_int64), I32, I32]
     L.flexi_gpu_set_profiling.argtypes = [P, I32]
@@ -132,6 +133,30 @@ class FlexiGpu:
     def get_array(self, name):
         out = np.empty(self._shape(name))
         self._ck(self.L.flexi_gpu_get_array(self.h, ARRAYS[name], _pd(out)))
+        return out
+
+    TGV_SUMS = ("T_mean", "Entropy", "Ekin", "Ekin_comp", "Enstr", "DR_u", "DR_S", "DR_Sd", "DR_p", "ED_S", "ED_D", "Vorticity_max")
+
+    def AnalyzeTestcase_sums(self, Vdm_GaussN_NAnalyze, wGPVolAnalyze):
+        """Steps 1-4 of the TGV AnalyzeTestcase (testcase.f90:241-420) on the device: the un-normalised per-rank integrals.
+        Vdm_GaussN_NAnalyze: numpy [NAnalyze+1, N+1] (row = analyze point); wGPVolAnalyze: numpy [k, j, i]."""
+        na1 = Vdm_GaussN_NAnalyze.shape[0]
+        vdm_f = np.ascontiguousarray(Vdm_GaussN_NAnalyze.T, dtype=np.float64)  # Fortran (0:NAnalyze,0:N): first index fastest
+        w = np.ascontiguousarray(wGPVolAnalyze, dtype=np.float64)
+        assert vdm_f.shape == (self.np, na1) and w.shape == (na1, na1, na1)
+        out = np.zeros(len(self.TGV_SUMS))
+        self._ck(self.L.flexi_gpu_analyze_tgv(self.h, na1 - 1, _pd(vdm_f), _pd(w), _pd(out)))
+        return dict(zip(self.TGV_SUMS, out))
+
+    @staticmethod
+    def tgv_normalise(sums_per_rank, vol, mu0, rho0=1.0):
+        """Steps 5-6 of AnalyzeTestcase (testcase.f90:422-474), kept by the host: reduce over ranks, normalise."""
+        tot = {k: (max(s[k] for s in sums_per_rank) if k == "Vorticity_max" else sum(s[k] for s in sums_per_rank)) for k in sums_per_rank[0]}
+        out = dict(T_mean=tot["T_mean"] / vol, Entropy=tot["Entropy"] / vol, Ekin=tot["Ekin"] / vol, Ekin_comp=tot["Ekin_comp"] / (vol * rho0),
+                   Enstr=tot["Enstr"] / (rho0 * vol), DR_u=tot["DR_u"] * mu0 / vol, DR_S=tot["DR_S"] * 2.0 * mu0 / (rho0 * vol),
+                   DR_Sd=tot["DR_Sd"] * 2.0 * mu0 / (rho0 * vol), DR_p=-tot["DR_p"] / (rho0 * vol), Vorticity_max=tot["Vorticity_max"],
+                   ED_S=tot["ED_S"] / vol, ED_D=tot["ED_D"] * 4.0 / 3.0 / vol)
+        out["uPrime"] = np.sqrt(2.0 / 3.0 * out["Ekin"])
         return out
 
     def keep_gradients(self, on=True):

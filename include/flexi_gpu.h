@@ -7,6 +7,7 @@
  *   flexi_gpu_calc_timestep       replaces  CalcTimeStep(errType)                  equations/navierstokes/calctimestep.f90:89-227
  *   flexi_gpu_prolong_to_face     replaces  ProlongToFaceCons                      interpolation/prolongtoface.t90:21-144
  *   flexi_gpu_surf_int            replaces  SurfIntCons                            dg/surfint.t90:21-239,475-616
+ *   flexi_gpu_analyze_tgv         replaces  AnalyzeTestcase steps 1-4 (TGV)        testcase/taylorgreenvortex/testcase.f90:241-420
  *   halo exchange inside          replaces  Start{Receive,Send}MPIData/Finish...   mpi/mpi.f90:244-445  (NCCL send/recv)
  *
  * The Fortran host keeps everything else (ini parsing, mesh/metrics, HDF5 I/O) and hands its module arrays over ONCE through
@@ -205,6 +206,20 @@ int flexi_gpu_get_array(flexi_gpu_handle* h, int32_t which, double* out);
  * stages of flexi_gpu_timestep write them on boundary-condition sides only (the split-form Gauss-Lobatto kernels hand n.F_visc of
  * each side to the side kernel instead), and a request after a time step recomputes them from the current U at the last stage time. */
 int flexi_gpu_keep_gradients(flexi_gpu_handle* h, int32_t on);
+
+/* AnalyzeTestcase of the Taylor-Green vortex test case, steps 1-4 (testcase/taylorgreenvortex/testcase.f90:241-420): the per-rank
+ * integrals over the analyze mesh, computed on the device from U and the lifted gradients left by the last DG operator call
+ * (flexi_gpu_keep_gradients; recomputed from the current U if they are not kept).  The host keeps steps 5-7 (MPI_REDUCE,
+ * normalisation with Vol / rho0, file output).  Vdm_GaussN_NAnalyze(0:NAnalyze,0:N) and wGPVolAnalyze(0:NAnalyze,0:NAnalyze,
+ * 0:NAnalyze) are MOD_Analyze_Vars arrays in Fortran order (analyze.f90:224-278).  sums[FLEXI_TGV_NSUMS] in the order below,
+ * un-normalised; FLEXI_TGV_VORT_MAX is the per-rank maximum. */
+enum {
+  FLEXI_TGV_T_MEAN = 0, FLEXI_TGV_ENTROPY = 1, FLEXI_TGV_EKIN = 2, FLEXI_TGV_EKIN_COMP = 3, FLEXI_TGV_ENSTR = 4, FLEXI_TGV_DR_U = 5,
+  FLEXI_TGV_DR_S = 6, FLEXI_TGV_DR_SD = 7, FLEXI_TGV_DR_P = 8, FLEXI_TGV_ED_S = 9, FLEXI_TGV_ED_D = 10, FLEXI_TGV_VORT_MAX = 11,
+  FLEXI_TGV_NSUMS = 12
+};
+int flexi_gpu_analyze_tgv(flexi_gpu_handle* h, int32_t NAnalyze, const double* Vdm_GaussN_NAnalyze, const double* wGPVolAnalyze,
+                          double* sums);
 
 /* Operator-level entry points (what the reference's own unit tests drive, unitTests/ProlongToFace.f90, SurfInt.f90).
  * Host arrays in Fortran order; the handle supplies mesh + basis.  doMPISides selects the side range like the reference. */

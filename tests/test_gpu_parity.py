@@ -254,3 +254,52 @@ def test_nan_state_reports_errtype():
     with FlexiGpu(r) as g:
         g.set_state(U0)
         assert g.CalcTimeStep()[3] != 0
+
+
+def test_gpu_reproduces_reference_tgv_regression_csv():
+    """The reference's own end-to-end pin (regressioncheck/checks/tgv/split/TGVAnalysis_Reference.csv) replayed on
+    the CUDA path: 8^3 elements, LGL N=7, split form (PI), RoeEntropyFix, BR1 with nVarLifting=4, carpenterrk4-5, CFL/DFL 0.8,
+    NAnalyze=10, dt recomputed every step.  Row 1 = t=0 (analytic), row 2 = after 10 steps; the intermediate AnalyzeTestCase sees
+    the gradients left by the last RK stage (timedisc_func.f90:323-338), hence keep_gradients."""
+    from flexi_b200.hostmesh.analyze import AnalyzeBasis, tgv_analyze
+    from test_oracle_tgv_regression import ROW1, ROW2
+
+    eqn = dict(parabolic=True, split_dg=True, split_dg_type="pi", riemann="roeentropyfix", cfl_scale=0.8, dfl_scale=0.8,
+               n_var_lifting=4, **TGV_EQN)
+    r = build_case(tgv_box(8), 7, GL, eqn)[0]
+    ab = AnalyzeBasis(r.basis, n_analyze=10)
+    vol = ab.volume(r.mesh.sJ)
+    g = FlexiGpu(r)
+    try:
+        g.keep_gradients(True)
+        g.set_state(r.eqn.tgv_state(r.mesh.Elem_xGP))
+
+        def analyze():
+            # the host-side analysis of the downloaded arrays, and the on-device analysis (flexi_gpu_analyze_tgv): both must
+            # reproduce the reference rows, and each other
+            out = tgv_analyze(ab, r.eqn, r.mesh, g.get_state(), g.get_array("gradUx"), g.get_array("gradUy"), g.get_array("gradUz"), vol)
+            out["uPrime"] = np.sqrt(2.0 / 3.0 * out["Ekin"])
+            dev = g.tgv_normalise([g.AnalyzeTestcase_sums(ab.Vdm, ab.w3)], vol, r.eqn.mu0)
+            for k, v in out.items():
+                tol = {"ED_D": 1e-7, "DR_p": 1e-7}.get(k, 1e-12)  # differences of nearly equal numbers ...
+                floor = {"DR_p": 1e-13, "ED_D": 1e-16}.get(k, 1e-18)  # ... that vanish at t=0 (p ~ 71 times div u ~ 1e-15)
+                assert abs(dev[k] - v) <= tol * max(abs(v), 1e-30) + floor, (k, dev[k], v)
+            return dev
+
+        g.DGTimeDerivative_weakForm(0.0)
+        row1 = analyze()
+        for k, ref in ROW1.items():
+            assert abs(row1[k] - ref) <= 2e-13 * max(1.0, abs(ref)) + 1e-13 * abs(ref), (k, row1[k], ref)
+        t = 0.0
+        for _ in range(10):
+            dt, _, _, err = g.CalcTimeStep()
+            assert err == 0
+            g.TimeStep(t, dt)
+            t += dt
+        row2 = analyze()
+        row2["Time"] = t
+        for k, ref in ROW2.items():
+            tol = {"ED_D": 1e-9, "DR_p": 1e-9, "Vorticity_max": 1e-11}.get(k, 5e-13)
+            assert abs(row2[k] - ref) <= tol * max(abs(ref), 1e-30) + 1e-18, (k, row2[k], ref)
+    finally:
+        g.close()
