@@ -79,15 +79,23 @@ def wall_farfield_box(curved=True):
     return BoxSpec((3, 2, 2), periodic=(False, False, True), bc_of_face=bc, **kw)
 
 
-@pytest.mark.parametrize("N,node,lifting,wall,riemann", [
-    (5, G, 2, 3, "hllc"),     # BASELINE config 4: N=5, HLLC + BR2, adiabatic wall
-    (5, GL, 2, 4, "roe"),     # isothermal wall
-    (4, G, 1, 4, "lf"),
-    (3, GL, 1, 3, "roeentropyfix"),
+SPLIT_PI, SPLIT_KG = dict(split_dg=True, split_dg_type="pi"), dict(split_dg=True, split_dg_type="kg", n_var_lifting=4)
+
+
+@pytest.mark.parametrize("N,node,lifting,wall,riemann,extra", [
+    (5, G, 2, 3, "hllc", {}),     # BASELINE config 4: N=5, HLLC + BR2, adiabatic wall
+    (5, GL, 2, 4, "roe", {}),     # isothermal wall
+    (4, G, 1, 4, "lf", {}),
+    (3, GL, 1, 3, "roeentropyfix", {}),
+    # split form on LGL nodes (line-sweep element kernel): boundary sides keep their gradient traces while inner sides carry
+    # n.F_visc only (viscous-trace protocol)
+    (7, GL, 1, 3, "lf", SPLIT_PI),
+    (5, GL, 2, 4, "roe", SPLIT_KG),
+    (3, GL, 2, 3, "roeentropyfix", SPLIT_PI),
 ])
-def test_walls_and_farfield_on_curved_mesh(N, node, lifting, wall, riemann):
+def test_walls_and_farfield_on_curved_mesh(N, node, lifting, wall, riemann, extra):
     eqn = dict(parabolic=True, lifting=lifting, riemann=riemann, mu0=1e-2, eta_br2=2.0, eta_br2_wall=3.0,
-               boundary_type=[(wall, 2, 0), (9, 0, 0), (2, 1, 0)], ref_state_prim=[REF, (1.0, 0.0, 0.0, 0.0, 0.9)])
+               boundary_type=[(wall, 2, 0), (9, 0, 0), (2, 1, 0)], ref_state_prim=[REF, (1.0, 0.0, 0.0, 0.0, 0.9)], **extra)
     ranks = build_case(wall_farfield_box(), N, node, eqn)
     r = ranks[0]
     check(ranks, r.eqn.smooth_state(r.mesh.Elem_xGP, length=2.0))

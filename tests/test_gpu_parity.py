@@ -78,6 +78,11 @@ SPLIT = [
     (7, GL, dict(parabolic=True, split_dg=True, split_dg_type="pi", riemann="lf", mu0=1e-2)),
     (7, GL, dict(parabolic=True, split_dg=True, split_dg_type="pi", riemann="roeentropyfix", mu0=1e-2, n_var_lifting=4)),
     (9, GL, dict(parabolic=True, split_dg=True, split_dg_type="pi", riemann="roel2", mu0=1e-2)),
+    (1, GL, dict(parabolic=False, split_dg=True, split_dg_type="sd", riemann="lf")),
+    (1, GL, dict(parabolic=True, split_dg=True, split_dg_type="pi", riemann="lf", mu0=1e-2)),
+    (7, GL, dict(parabolic=False, split_dg=True, split_dg_type="du", riemann="roe")),
+    (7, GL, dict(parabolic=True, split_dg=True, split_dg_type="kg", riemann="roe", mu0=1e-2)),
+    (7, GL, dict(parabolic=True, split_dg=True, split_dg_type="sd", riemann="lf", mu0=1e-2, n_var_lifting=4)),
 ]
 
 
