@@ -307,6 +307,10 @@ int launch_volume(H* h, const int32_t* list, int n, bool fullGrad) {
   a.fvs = h->fvs;
   a.fullGrad = fullGrad ? 1 : 0;
   a.prefetchAhead = h->prefetchAhead;
+  {
+    static const int dbg = getenv("FLEXI_GPU_DBG") ? atoi(getenv("FLEXI_GPU_DBG")) : 0;  // timing experiments only (results are wrong)
+    a.dbg = dbg;
+  }
   Timer tm(h, KC_VOLUME, h->sc);
   CK(h->ops->volume(h->gl, h->split, h->q.splitType, h->para, h->nvl, a, n, h->sc));
   return 0;

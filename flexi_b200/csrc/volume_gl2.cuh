@@ -244,6 +244,7 @@ __global__ void __launch_bounds__(VolGL2Cfg<NP, PARA>::NT, VolGL2Cfg<NP, PARA>::
   double* sX = sm + C::O_F;   // face staging (lifting fluxes + normals), later the Ut hand-over planes
   double* sUT = sX;
   const int tid = threadIdx.x;
+  if (A.dbg & 8) return;  // timing experiment: the cost of scheduling one CTA per element
   const int e = A.elems ? A.elems[blockIdx.x] : blockIdx.x;
   const int hb = tid / D::NP2, r = tid % D::NP2;  // half index (warp-uniform for NP = 8) and position inside the NP x NP sheet
   const int r0 = r % NP, r1 = r / NP;
@@ -268,9 +269,11 @@ __global__ void __launch_bounds__(VolGL2Cfg<NP, PARA>::NT, VolGL2Cfg<NP, PARA>::
     for (int m = 0; m < 9; ++m) Mn[m] = __ldg(gM + m * D::NP3 + n);
     sJn = __ldg(A.m.sJ + (size_t)e * D::NP3 + n);
   }
+  SideRef nsr{-1, 0};  // side of face tid/21 of the element one wave later (its traces + geometry are prefetched after S1)
   if (A.prefetchAhead > 0 && (int)blockIdx.x + A.prefetchAhead < A.nList) {
     // pull the element that will run in this CTA slot one wave later (U, metrics, Jacobian: 60 KB) from HBM into L2 now
     const int en = A.elems ? A.elems[blockIdx.x + A.prefetchAhead] : (int)blockIdx.x + A.prefetchAhead;
+    if (PARA && tid < 126) nsr = A.m.e2s[en * 6 + tid / 21];
     const char* pu = reinterpret_cast<const char*>(A.U + (size_t)en * 5 * D::NP3);
     const char* pm = reinterpret_cast<const char*>(A.m.Met + (size_t)en * 9 * D::NP3);
     const char* pj = reinterpret_cast<const char*>(A.m.sJ + (size_t)en * D::NP3);
@@ -345,12 +348,23 @@ __global__ void __launch_bounds__(VolGL2Cfg<NP, PARA>::NT, VolGL2Cfg<NP, PARA>::
   }
   __syncthreads();  // S1: primitive planes complete
 
+  if (PARA && nsr.side >= 0) {
+    // L2 prefetch of the six faces of the element one wave later (neighbour trace 20 lines, normal vector 12, SurfElem 4 per
+    // face; 21 threads per face): without it the start of every element waits on the chain ElemToSide -> S2V2 -> HBM
+    const char* tr = reinterpret_cast<const char*>(((nsr.flip == 0) ? A.U_slave : A.U_master) + (size_t)nsr.side * 5 * D::NP2);
+    const char* ge = reinterpret_cast<const char*>(A.m.Geo + (size_t)nsr.side * 10 * D::NP2);
+    constexpr int LT = 5 * D::NP2 * 8 / 128, LG = 3 * D::NP2 * 8 / 128, LS = D::NP2 * 8 / 128;
+    for (int l = tid % 21; l < LT + LG + LS; l += 21) {
+      const char* p = l < LT ? tr + (size_t)l * 128 : l < LT + LG ? ge + (size_t)(l - LT) * 128 : ge + (size_t)9 * D::NP2 * 8 + (size_t)(l - LT - LG) * 128;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+    }
+  }
   if (PARA) {
     // ---- reference-space derivatives of the lifting variables (lifting_volint.t90:67-83), one line sweep per direction:
     //      xi and eta results change owner through the planes G1, G2; the zeta result stays with this thread ----
     double gzt[HALF][NVC];
 #pragma unroll 1
-    for (int dir = 0; dir < 3; ++dir) {
+    for (int dir = (A.dbg & 2) ? 3 : 0; dir < 3; ++dir) {
       int sa[NP];
 #pragma unroll
       for (int p = 0; p < NP; ++p) sa[p] = gl2_sa<NP>(dir, gl2_ap<NP>(hb, p), r0, r1);
@@ -404,7 +418,7 @@ __global__ void __launch_bounds__(VolGL2Cfg<NP, PARA>::NT, VolGL2Cfg<NP, PARA>::
     __syncthreads();  // S2: G1, G2 and the face lifting fluxes complete
 
     // ---- zeta ownership: metric combination, surface part, Jacobian, traces for the side kernel, viscous flux ----
-    {
+    if (!(A.dbg & 4)) {
       constexpr int LV = (NVC == 5) ? 1 : 0;
       const int i = r0, j = r1;
 #pragma unroll
@@ -557,7 +571,7 @@ __global__ void __launch_bounds__(VolGL2Cfg<NP, PARA>::NT, VolGL2Cfg<NP, PARA>::
   // ---- three direction sweeps (zeta, xi, eta) of ONE copy of the sweep code; the partial sums change owner through the Ut
   //      hand-over planes, the last sweep sends the raw volume integral to HBM ----
 #pragma unroll 1
-  for (int it = 0; it < 3; ++it) {
+  for (int it = (A.dbg & 1) ? 3 : 0; it < 3; ++it) {
     const int dir = (it == 0) ? 2 : it - 1;
     int sa[NP], gn[NP];  // indexed by canonical position
 #pragma unroll
