@@ -94,7 +94,8 @@ struct flexi_gpu_handle {
   double *U = nullptr, *UtVol = nullptr, *UtTmp = nullptr, *Ut = nullptr;
   double *Um = nullptr, *Us = nullptr, *Flux = nullptr;
   double *gm[3] = {nullptr, nullptr, nullptr}, *gs[3] = {nullptr, nullptr, nullptr}, *gvol[3] = {nullptr, nullptr, nullptr};
-  double *MetAdv = nullptr, *MetVisc = nullptr, *dtElem = nullptr, *dt3 = nullptr;
+  double *dtElem = nullptr, *dt3 = nullptr;
+  double KappasPr_max = 0.;
   double* dt3_host = nullptr;  // pinned
   double* stage = nullptr;     // AoS staging buffer
   size_t stageDoubles = 0;
@@ -776,23 +777,11 @@ static int init_impl(const flexi_gpu_desc* d, H* h) {
       CK(cudaMemset(h->fvs, 0, nS * 4 * np2 * 8));
     }
   }
-  // ---- CalcTimeStep tables ----
-  CKR(dalloc(h, &h->MetAdv, nE * 3 * np3));
-  CKR(dalloc(h, &h->MetVisc, nE * 3 * np3));
+  // ---- CalcTimeStep (MetricsAdv / MetricsVisc are formed on the fly, kernels.cuh:k_dt) ----
   CKR(dalloc(h, &h->dtElem, nE * 3));
   CKR(dalloc(h, &h->dt3, 3));
   CK(cudaMallocHost((void**)&h->dt3_host, 3 * sizeof(double)));
-  {
-    DtInitArgs a{};
-    a.Met = Met;
-    a.sJ = sJ;
-    a.MetAdv = h->MetAdv;
-    a.MetVisc = h->MetVisc;
-    a.KappasPr_max = fmax(4. / 3., d->kappa / d->Pr);
-    a.nElems = h->nElems;
-    CK(h->ops->dt_init(a, h->sc));
-    h->launches++;
-  }
+  h->KappasPr_max = fmax(4. / 3., d->kappa / d->Pr);
   // ---- partition ----
   h->myRank = d->myRank;
   h->nProcs = d->nProcs < 1 ? 1 : d->nProcs;
@@ -892,8 +881,7 @@ int flexi_gpu_calc_timestep(flexi_gpu_handle* h, double* dt_min, double* dt_conv
   a.m = h->m;
   a.q = h->q;
   a.U = h->U;
-  a.MetAdv = h->MetAdv;
-  a.MetVisc = h->MetVisc;
+  a.KappasPr_max = h->KappasPr_max;
   a.CFLScale = h->CFLScale;
   a.DFLScale = h->DFLScale;
   a.parabolic = h->para;

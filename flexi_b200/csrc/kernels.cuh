@@ -799,32 +799,24 @@ __global__ void __launch_bounds__(Dim<NP>::NP3) k_surfint(SurfArgs A) {
 
 // ---------------------------------------------------------------------------------------------------------------------------
 // k_dt: CalcTimeStep, calctimestep.f90:89-227.  One block per element; writes per-element (dtConv, dtVisc, errFlag).
+// MetricsAdv / MetricsVisc of InitCalctimestep (calctimestep.f90:42-83) are formed on the fly from the metric terms the kernel
+// reads anyway (same expressions, same values) instead of being read from two more 3-plane tables: 120 instead of 168 bytes per
+// DOF.  The seven block reductions share one shuffle + one shared-memory stage.
 struct DtArgs {
   Mesh m;
   Eqn q;
   const double* U;
-  const double* MetAdv;   // [e][3][NP3]  sJ*|Metrics_d|        (InitCalctimestep, calctimestep.f90:42-83)
-  const double* MetVisc;  // [e][3][NP3]
+  double KappasPr_max;  // MAX(4/3, kappa/Pr), calctimestep.f90:66
   double CFLScale, DFLScale;
   int parabolic;
   double* out;  // [e][3]
 };
 
-__device__ __forceinline__ double block_max(double v, double* red, int tid, int nthreads) {
-  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-  __syncthreads();
-  if ((tid & 31) == 0) red[tid >> 5] = v;
-  __syncthreads();
-  const int nw = (nthreads + 31) >> 5;
-  double r = red[0];
-  for (int w = 1; w < nw; ++w) r = fmax(r, red[w]);
-  return r;
-}
-
 template <int NP>
 __global__ void __launch_bounds__(Dim<NP>::NP3) k_dt(DtArgs A) {
   using D = Dim<NP>;
-  __shared__ double red[32];
+  constexpr int NW = (D::NP3 + 31) / 32;
+  __shared__ double red[7][NW];
   const int tid = threadIdx.x, e = blockIdx.x, n = tid;
   const Eqn& q = A.q;
   double U[5], P[6], M[9];
@@ -837,57 +829,39 @@ __global__ void __launch_bounds__(Dim<NP>::NP3) k_dt(DtArgs A) {
 #pragma unroll
   for (int cI = 0; cI < 9; ++cI) M[cI] = A.m.Met[((size_t)e * 9 + cI) * D::NP3 + n];
   const double vs[3] = {P[VEL1] * sJ, P[VEL2] * sJ, P[VEL3] * sJ};
-  double lam[3], lamv[3];
-  // NaN in the density flags errType 1 (calctimestep.f90:157-160); NaN propagates through fmax-free sums below
-  const double nanflag = (U[0] != U[0]) ? 1. : 0.;
+  double r[7];  // max over the element of: lambda_adv(3), lambda_visc(3), NaN flag
+  // NaN in the density flags errType 1 (calctimestep.f90:157-160); NaN propagates through the fmax-free sums below
+  r[6] = (U[0] != U[0]) ? 1. : 0.;
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
-    lam[d] = fabs(M[3 * d] * vs[0] + M[3 * d + 1] * vs[1] + M[3 * d + 2] * vs[2]) + c * A.MetAdv[((size_t)e * 3 + d) * D::NP3 + n];
-    lamv[d] = A.parabolic ? q.mu0 * srho * A.MetVisc[((size_t)e * 3 + d) * D::NP3 + n] : 0.;
+    const double m0 = M[3 * d], m1 = M[3 * d + 1], m2 = M[3 * d + 2];
+    const double metAdv = sJ * sqrt(m0 * m0 + m1 * m1 + m2 * m2);                                                   // MetricsAdv
+    const double metVisc = A.KappasPr_max * ((m0 * sJ) * (m0 * sJ) + (m1 * sJ) * (m1 * sJ) + (m2 * sJ) * (m2 * sJ));  // MetricsVisc
+    r[d] = fabs(m0 * vs[0] + m1 * vs[1] + m2 * vs[2]) + c * metAdv;
+    r[3 + d] = A.parabolic ? q.mu0 * srho * metVisc : 0.;
+    // Fortran MAX may or may not propagate a NaN operand; NaN is flagged separately
+    if (r[d] != r[d] || r[3 + d] != r[3 + d]) r[6] = fmax(r[6], 2.);
   }
-  // Fortran MAX ignores nothing: a NaN operand may or may not propagate; we flag NaN separately
-  double anynan = nanflag;
 #pragma unroll
-  for (int d = 0; d < 3; ++d)
-    if (lam[d] != lam[d] || lamv[d] != lamv[d]) anynan = fmax(anynan, 2.);
-  double mx[3], mv[3];
-#pragma unroll
-  for (int d = 0; d < 3; ++d) {
-    mx[d] = block_max(lam[d], red, tid, D::NP3);
-    mv[d] = block_max(lamv[d], red, tid, D::NP3);
+  for (int s = 0; s < 7; ++s) {
+    double v = r[s];
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((tid & 31) == 0) red[s][tid >> 5] = v;
   }
-  const double nn = block_max(anynan, red, tid, D::NP3);
+  __syncthreads();
   if (tid == 0) {
+    double mx[7];
+    for (int s = 0; s < 7; ++s) {
+      mx[s] = red[s][0];
+      for (int w = 1; w < NW; ++w) mx[s] = fmax(mx[s], red[s][w]);
+    }
     const double dtc = A.CFLScale * 2. / (mx[0] + mx[1] + mx[2]);
     double dtv = HUGE_VAL;
-    const double sv = mv[0] + mv[1] + mv[2];
+    const double sv = mx[3] + mx[4] + mx[5];
     if (A.parabolic && sv > 0.) dtv = A.DFLScale * 4. / sv;
     A.out[(size_t)e * 3 + 0] = dtc;
     A.out[(size_t)e * 3 + 1] = dtv;
-    A.out[(size_t)e * 3 + 2] = nn;
-  }
-}
-
-// InitCalctimestep, calctimestep.f90:42-83
-struct DtInitArgs {
-  const double* Met;
-  const double* sJ;
-  double* MetAdv;
-  double* MetVisc;
-  double KappasPr_max;
-  int nElems;
-};
-template <int NP>
-__global__ void k_dt_init(DtInitArgs A) {
-  using D = Dim<NP>;
-  const int e = blockIdx.x, n = threadIdx.x;
-  const double sJ = A.sJ[(size_t)e * D::NP3 + n];
-#pragma unroll
-  for (int d = 0; d < 3; ++d) {
-    const double m0 = A.Met[((size_t)e * 9 + 3 * d) * D::NP3 + n], m1 = A.Met[((size_t)e * 9 + 3 * d + 1) * D::NP3 + n],
-                 m2 = A.Met[((size_t)e * 9 + 3 * d + 2) * D::NP3 + n];
-    A.MetAdv[((size_t)e * 3 + d) * D::NP3 + n] = sJ * sqrt(m0 * m0 + m1 * m1 + m2 * m2);
-    A.MetVisc[((size_t)e * 3 + d) * D::NP3 + n] = A.KappasPr_max * ((m0 * sJ) * (m0 * sJ) + (m1 * sJ) * (m1 * sJ) + (m2 * sJ) * (m2 * sJ));
+    A.out[(size_t)e * 3 + 2] = mx[6];
   }
 }
 

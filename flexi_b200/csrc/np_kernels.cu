@@ -253,12 +253,7 @@ cudaError_t dt(const DtArgs& a, int nElems, cudaStream_t s) {
   return cudaGetLastError();
 }
 
-cudaError_t dt_init(const DtInitArgs& a, cudaStream_t s) {
-  k_dt_init<NP><<<a.nElems, D::NP3, 0, s>>>(a);
-  return cudaGetLastError();
-}
-
-const NpOps ops = {NP, setup, prolong, volume, flux, update, surfint, dt, dt_init, bc_pre, flux_bc};
+const NpOps ops = {NP, setup, prolong, volume, flux, update, surfint, dt, bc_pre, flux_bc};
 }  // namespace
 }  // namespace fx
 

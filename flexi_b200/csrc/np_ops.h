@@ -17,7 +17,6 @@ struct NpOps {
   cudaError_t (*update)(bool gl, const UpdArgs& a, int nBlocks, cudaStream_t s);
   cudaError_t (*surfint)(bool gl, const SurfArgs& a, int nElems, cudaStream_t s);
   cudaError_t (*dt)(const DtArgs& a, int nElems, cudaStream_t s);
-  cudaError_t (*dt_init)(const DtInitArgs& a, cudaStream_t s);
   cudaError_t (*bc_pre)(const BCArgs& a, cudaStream_t s);
   cudaError_t (*flux_bc)(const BCArgs& a, cudaStream_t s);
 };
