@@ -23,6 +23,34 @@ struct TgvArgs {
   double* out;             // [e][TGV_NSUMS]
 };
 
+// ChangeBasis3D (changeBasis.t90) of nf fields of one element to the analyze mesh, one zeta slab of the analyze mesh at a time:
+// zeta pass for slab k, xi pass, then the eta pass delivers the thread's analyze point (iO,jO,k) for every field.  The caller
+// must __syncthreads() before the next slab (sT1 / sT2 are reused).
+__device__ __forceinline__ void interp_slab(int nf, int np, int na1, int k, const double* sX, const double* sV, double* sT1,
+                                            double* sT2, double* val) {
+  const int np2 = np * np, np3 = np2 * np, tid = threadIdx.x, nt = blockDim.x;
+  const int iO = tid % na1, jO = tid / na1;
+  for (int t = tid; t < nf * np2; t += nt) {  // zeta pass
+    const int f = t / np2, ij = t % np2;
+    double s = 0.;
+    for (int l = 0; l < np; ++l) s = s + sV[k * np + l] * sX[f * np3 + ij + np2 * l];
+    sT1[t] = s;
+  }
+  __syncthreads();
+  for (int t = tid; t < nf * na1 * np; t += nt) {  // xi pass
+    const int f = t / (na1 * np), r = t % (na1 * np), io = r % na1, j = r / na1;
+    double s = 0.;
+    for (int l = 0; l < np; ++l) s = s + sV[io * np + l] * sT1[f * np2 + l + np * j];
+    sT2[t] = s;
+  }
+  __syncthreads();
+  for (int f = 0; f < nf; ++f) {  // eta pass: the thread's analyze point
+    double s = 0.;
+    for (int l = 0; l < np; ++l) s = s + sV[jO * np + l] * sT2[f * na1 * np + iO + na1 * l];
+    val[f] = s;
+  }
+}
+
 // one CTA per element, one thread per (i,j) of the analyze mesh; the analyze mesh is walked slab by slab in zeta so that a thread
 // holds one analyze point (15 interpolated fields) at a time
 __global__ void k_tgv_analyze(TgvArgs A) {
@@ -50,26 +78,8 @@ __global__ void k_tgv_analyze(TgvArgs A) {
   double acc[TGV_NSUMS];
   for (int s = 0; s < TGV_NSUMS; ++s) acc[s] = 0.;
   for (int k = 0; k < na1; ++k) {
-    for (int t = tid; t < nf * np2; t += nt) {  // zeta pass
-      const int f = t / np2, ij = t % np2;
-      double s = 0.;
-      for (int l = 0; l < np; ++l) s = s + sV[k * np + l] * sX[f * np3 + ij + np2 * l];
-      sT1[t] = s;
-    }
-    __syncthreads();
-    for (int t = tid; t < nf * na1 * np; t += nt) {  // xi pass
-      const int f = t / (na1 * np), r = t % (na1 * np), io = r % na1, j = r / na1;
-      double s = 0.;
-      for (int l = 0; l < np; ++l) s = s + sV[io * np + l] * sT1[f * np2 + l + np * j];
-      sT2[t] = s;
-    }
-    __syncthreads();
     double val[15];
-    for (int f = 0; f < nf; ++f) {  // eta pass: the thread's analyze point
-      double s = 0.;
-      for (int l = 0; l < np; ++l) s = s + sV[jO * np + l] * sT2[f * na1 * np + iO + na1 * l];
-      val[f] = s;
-    }
+    interp_slab(nf, np, na1, k, sX, sV, sT1, sT2, val);
     double P[6];
     cons_to_prim(q, val + 1, P);
     const double w = A.wVol[iO + na1 * (jO + na1 * k)] / val[0];  // IntFactor, testcase.f90:381
@@ -124,17 +134,81 @@ __global__ void k_tgv_analyze(TgvArgs A) {
   }
 }
 
-// sum (max for the vorticity) over the elements of the rank, fixed order
-__global__ void k_tgv_reduce(const double* in, int nElems, double* out) {
+// CalcErrorNorms, analyze/analyze.f90:391-485, per-element part: interpolate U, Elem_xGP and J = 1/sJ to the analyze mesh,
+// evaluate ExactFunc there, accumulate (U-U_exact)^2 * wGPVolAnalyze * J and max|U-U_exact| per variable.
+struct ErrArgs {
+  Eqn q;
+  BCData bc;   // carries IniExactFunc and its parameters
+  double t;
+  int np, na1;
+  const double* U;    // [e][5][NP3]
+  const double* sJ;   // [e][NP3]
+  const double* xGP;  // [e][3][NP3]
+  const double* vdm;
+  const double* wVol;
+  double* out;        // [e][10]: L2 sums (5), Linf (5)
+};
+
+__global__ void k_error_norms(ErrArgs A) {
+  extern __shared__ double sm[];
+  const int np = A.np, na1 = A.na1, np2 = np * np, np3 = np2 * np;
+  const int nf = 9;  // J, U(5), x(3)
+  double* sX = sm;
+  double* sV = sX + nf * np3;
+  double* sT1 = sV + na1 * np;
+  double* sT2 = sT1 + nf * np2;
+  double* sRed = sT2 + nf * na1 * np;  // [10][32]
+  const int tid = threadIdx.x, nt = blockDim.x, e = blockIdx.x;
+  for (int t = tid; t < np3; t += nt) {
+    sX[t] = 1. / A.sJ[(size_t)e * np3 + t];  // J_N, analyze.f90:437
+    for (int v = 0; v < 5; ++v) sX[(1 + v) * np3 + t] = A.U[((size_t)e * 5 + v) * np3 + t];
+    for (int c = 0; c < 3; ++c) sX[(6 + c) * np3 + t] = A.xGP[((size_t)e * 3 + c) * np3 + t];
+  }
+  for (int t = tid; t < na1 * np; t += nt) sV[t] = A.vdm[t];
+  __syncthreads();
+  const int iO = tid % na1, jO = tid / na1;
+  double l2[5] = {0., 0., 0., 0., 0.}, li[5] = {0., 0., 0., 0., 0.};
+  for (int k = 0; k < na1; ++k) {
+    double val[15];
+    interp_slab(nf, np, na1, k, sX, sV, sT1, sT2, val);
+    double Uex[5];
+    exact_func(A.q, A.bc, A.t, val + 6, Uex);
+    const double w = A.wVol[iO + na1 * (jO + na1 * k)] * val[0];
+    for (int v = 0; v < 5; ++v) {
+      const double d = val[1 + v] - Uex[v];
+      li[v] = fmax(li[v], fabs(d));
+      l2[v] += d * d * w;
+    }
+    __syncthreads();
+  }
+  const int lane = tid & 31, wid = tid >> 5, nw = (nt + 31) >> 5;
+  for (int s = 0; s < 10; ++s) {
+    double v = s < 5 ? l2[s] : li[s - 5];
+    for (int o = 16; o > 0; o >>= 1) {
+      const double u = __shfl_down_sync(0xffffffffu, v, o);
+      v = s < 5 ? v + u : fmax(v, u);
+    }
+    if (lane == 0) sRed[s * 32 + wid] = v;
+  }
+  __syncthreads();
+  if (tid < 10) {
+    double v = sRed[tid * 32];
+    for (int w2 = 1; w2 < nw; ++w2) v = tid < 5 ? v + sRed[tid * 32 + w2] : fmax(v, sRed[tid * 32 + w2]);
+    A.out[(size_t)e * 10 + tid] = v;
+  }
+}
+
+// sum (first nSum entries) / max (the rest) over the elements of the rank, fixed order
+__global__ void k_norm_reduce(const double* in, int nElems, int nVal, int nSum, double* out) {
   __shared__ double s[256];
   const int tid = threadIdx.x;
-  for (int q = 0; q < TGV_NSUMS; ++q) {
+  for (int q = 0; q < nVal; ++q) {
     double v = 0.;
-    for (int e = tid; e < nElems; e += 256) v = (q == TGV_VORT_MAX) ? fmax(v, in[(size_t)e * TGV_NSUMS + q]) : v + in[(size_t)e * TGV_NSUMS + q];
+    for (int e = tid; e < nElems; e += 256) v = (q >= nSum) ? fmax(v, in[(size_t)e * nVal + q]) : v + in[(size_t)e * nVal + q];
     s[tid] = v;
     __syncthreads();
     for (int o = 128; o > 0; o >>= 1) {
-      if (tid < o) s[tid] = (q == TGV_VORT_MAX) ? fmax(s[tid], s[tid + o]) : s[tid] + s[tid + o];
+      if (tid < o) s[tid] = (q >= nSum) ? fmax(s[tid], s[tid + o]) : s[tid] + s[tid + o];
       __syncthreads();
     }
     if (tid == 0) out[q] = s[0];

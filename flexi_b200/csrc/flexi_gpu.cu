@@ -998,12 +998,72 @@ int flexi_gpu_analyze_tgv(flexi_gpu_handle* h, int32_t NAnalyze, const double* V
   CK(cudaGetLastError());
   {
     Timer tm(h, KC_DT, h->sc);
-    k_tgv_reduce<<<1, 256, 0, h->sc>>>(dPart, h->nElems, dOut);
+    k_norm_reduce<<<1, 256, 0, h->sc>>>(dPart, h->nElems, TGV_NSUMS, TGV_VORT_MAX, dOut);
   }
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(sums, dOut, TGV_NSUMS * 8, cudaMemcpyDeviceToHost, h->sc));
   h->d2h += TGV_NSUMS * 8;
   CK(cudaStreamSynchronize(h->sc));
+  return 0;
+}
+
+int flexi_gpu_calc_error_norms(flexi_gpu_handle* h, double Time, int32_t AnalyzeExactFunc, int32_t NAnalyze,
+                               const double* Vdm_GaussN_NAnalyze, const double* wGPVolAnalyze, const double* Elem_xGP,
+                               double* L_2_sum, double* L_Inf) {
+  ENTER(h);
+  if (!Vdm_GaussN_NAnalyze || !wGPVolAnalyze || !L_2_sum || !L_Inf) return fail(FLEXI_GPU_ERR_ARG, "null argument");
+  if (NAnalyze < 1 || NAnalyze > 31) return fail(FLEXI_GPU_ERR_ARG, "NAnalyze=%d outside 1..31", NAnalyze);
+  if (AnalyzeExactFunc != 1 && AnalyzeExactFunc != 4)
+    return fail(FLEXI_GPU_ERR_UNSUPPORTED, "ExactFunc %d is not implemented on the device (1: RefState, 4: oblique sine wave)", AnalyzeExactFunc);
+  const int np = h->np, na1 = NAnalyze + 1;
+  if (!h->xGP) {  // Elem_xGP is only uploaded at init when a source term needs it; keep it from the first analysis on
+    if (!Elem_xGP) return fail(FLEXI_GPU_ERR_ARG, "Elem_xGP is required (it was not kept at init)");
+    CKR(dalloc(h, &h->xGP, (size_t)h->nElems * 3 * h->np3));
+    CKR(upload_aos(h, Elem_xGP, h->xGP, 3, h->np3, (long)h->nElems));
+  }
+  std::vector<double> tab((size_t)na1 * np + (size_t)na1 * na1 * na1);
+  for (int io = 0; io < na1; ++io)
+    for (int ii = 0; ii < np; ++ii) tab[(size_t)io * np + ii] = Vdm_GaussN_NAnalyze[(size_t)ii * na1 + io];
+  memcpy(tab.data() + (size_t)na1 * np, wGPVolAnalyze, sizeof(double) * na1 * na1 * na1);
+  CKR(ensure_stage(h, tab.size() + (size_t)h->nElems * 10 + 10));
+  double* dTab = h->stage;
+  double* dPart = dTab + tab.size();
+  double* dOut = dPart + (size_t)h->nElems * 10;
+  CK(cudaMemcpyAsync(dTab, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice, h->sc));
+  h->h2d += (int64_t)(tab.size() * 8);
+  ErrArgs a{};
+  a.q = h->q;
+  a.bc = h->bc;
+  a.bc.iniExactFunc = AnalyzeExactFunc;
+  a.t = Time;
+  a.np = np;
+  a.na1 = na1;
+  a.U = h->U;
+  a.sJ = h->m.sJ;
+  a.xGP = h->xGP;
+  a.vdm = dTab;
+  a.wVol = dTab + (size_t)na1 * np;
+  a.out = dPart;
+  const size_t smem = sizeof(double) * ((size_t)9 * h->np3 + (size_t)na1 * np + (size_t)9 * h->np2 + (size_t)9 * na1 * np + 10 * 32);
+  CK(cudaFuncSetAttribute(k_error_norms, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  {
+    Timer tm(h, KC_DT, h->sc);
+    k_error_norms<<<h->nElems, na1 * na1, smem, h->sc>>>(a);
+  }
+  CK(cudaGetLastError());
+  {
+    Timer tm(h, KC_DT, h->sc);
+    k_norm_reduce<<<1, 256, 0, h->sc>>>(dPart, h->nElems, 10, 5, dOut);
+  }
+  CK(cudaGetLastError());
+  double out[10];
+  CK(cudaMemcpyAsync(out, dOut, 10 * 8, cudaMemcpyDeviceToHost, h->sc));
+  h->d2h += 10 * 8;
+  CK(cudaStreamSynchronize(h->sc));
+  for (int v = 0; v < 5; ++v) {
+    L_2_sum[v] = out[v];
+    L_Inf[v] = out[5 + v];
+  }
   return 0;
 }
 

@@ -30,7 +30,7 @@ KERNEL_CLASSES = ("volume", "flux", "update", "prolong", "calc_timestep", "layou
 EXPORTS = ("flexi_gpu_last_error", "flexi_gpu_abi_version", "flexi_gpu_nccl_unique_id", "flexi_gpu_init", "flexi_gpu_finalize",
            "flexi_gpu_set_state", "flexi_gpu_get_state", "flexi_gpu_dg_time_derivative", "flexi_gpu_timestep",
            "flexi_gpu_timestep_n", "flexi_gpu_calc_timestep", "flexi_gpu_get_array", "flexi_gpu_keep_gradients",
-           "flexi_gpu_prolong_to_face", "flexi_gpu_surf_int", "flexi_gpu_analyze_tgv", "flexi_gpu_counters", "flexi_gpu_kernel_times",
+           "flexi_gpu_prolong_to_face", "flexi_gpu_surf_int", "flexi_gpu_analyze_tgv", "flexi_gpu_calc_error_norms", "flexi_gpu_counters", "flexi_gpu_kernel_times",
            "flexi_gpu_set_profiling", "flexi_gpu_synchronize", "flexi_gpu_stream")
 
 
@@ -70,6 +70,7 @@ def lib():
     L.flexi_gpu_prolong_to_face.argtypes = [P, PD, PD, PD, I32]
     L.flexi_gpu_surf_int.argtypes = [P, PD, PD, PD, I32]
     L.flexi_gpu_analyze_tgv.argtypes = [P, I32, PD, PD, PD]
+    L.flexi_gpu_calc_error_norms.argtypes = [P, C.c_double, I32, I32, PD, PD, PD, PD, PD]
     L.flexi_gpu_counters.argtypes = [P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.flexi_gpu_kernel_times.argtypes = [P, PD, C.POINTER(C.c_int64), I32, I32]
     L.flexi_gpu_set_profiling.argtypes = [P, I32]
@@ -147,6 +148,18 @@ class FlexiGpu:
         out = np.zeros(len(self.TGV_SUMS))
         self._ck(self.L.flexi_gpu_analyze_tgv(self.h, na1 - 1, _pd(vdm_f), _pd(w), _pd(out)))
         return dict(zip(self.TGV_SUMS, out))
+
+    def CalcErrorNorms_sums(self, Time, AnalyzeExactFunc, Vdm_GaussN_NAnalyze, wGPVolAnalyze, Elem_xGP):
+        """CalcErrorNorms (analyze.f90:391-485) per rank on the device: (sum of squared L2 contributions, Linf) per variable;
+        the host reduces over ranks and takes sqrt(./Vol)."""
+        na1 = Vdm_GaussN_NAnalyze.shape[0]
+        vdm_f = np.ascontiguousarray(Vdm_GaussN_NAnalyze.T, dtype=np.float64)
+        w = np.ascontiguousarray(wGPVolAnalyze, dtype=np.float64)
+        x = np.ascontiguousarray(Elem_xGP, dtype=np.float64)
+        l2, li = np.zeros(5), np.zeros(5)
+        self._ck(self.L.flexi_gpu_calc_error_norms(self.h, float(Time), int(AnalyzeExactFunc), na1 - 1, _pd(vdm_f), _pd(w), _pd(x), _pd(l2),
+                                                   _pd(li)))
+        return l2, li
 
     @staticmethod
     def tgv_normalise(sums_per_rank, vol, mu0, rho0=1.0):

@@ -8,6 +8,7 @@
  *   flexi_gpu_prolong_to_face     replaces  ProlongToFaceCons                      interpolation/prolongtoface.t90:21-144
  *   flexi_gpu_surf_int            replaces  SurfIntCons                            dg/surfint.t90:21-239,475-616
  *   flexi_gpu_analyze_tgv         replaces  AnalyzeTestcase steps 1-4 (TGV)        testcase/taylorgreenvortex/testcase.f90:241-420
+ *   flexi_gpu_calc_error_norms    replaces  CalcErrorNorms (per-rank part)         analyze/analyze.f90:391-485
  *   halo exchange inside          replaces  Start{Receive,Send}MPIData/Finish...   mpi/mpi.f90:244-445  (NCCL send/recv)
  *
  * The Fortran host keeps everything else (ini parsing, mesh/metrics, HDF5 I/O) and hands its module arrays over ONCE through
@@ -220,6 +221,15 @@ enum {
 };
 int flexi_gpu_analyze_tgv(flexi_gpu_handle* h, int32_t NAnalyze, const double* Vdm_GaussN_NAnalyze, const double* wGPVolAnalyze,
                           double* sums);
+
+/* CalcErrorNorms (analyze/analyze.f90:391-485), per-rank part: U, Elem_xGP and 1/sJ are interpolated to the analyze mesh on the
+ * device, ExactFunc(AnalyzeExactFunc, Time, x) is evaluated there (implemented: 1 = RefState, 4 = oblique sine wave, exactfunc.f90:
+ * 225-362).  L_2_sum(PP_nVar) = sum (U-U_exact)^2 * wGPVolAnalyze * J (the host reduces over ranks and takes SQRT(./Vol), :478-483),
+ * L_Inf(PP_nVar) = per-rank maximum.  Elem_xGP (3,0:N,0:N,0:N,nElems) is uploaded on the first call unless a source term already
+ * keeps it on the device (then it may be NULL). */
+int flexi_gpu_calc_error_norms(flexi_gpu_handle* h, double Time, int32_t AnalyzeExactFunc, int32_t NAnalyze,
+                               const double* Vdm_GaussN_NAnalyze, const double* wGPVolAnalyze, const double* Elem_xGP,
+                               double* L_2_sum, double* L_Inf);
 
 /* Operator-level entry points (what the reference's own unit tests drive, unitTests/ProlongToFace.f90, SurfInt.f90).
  * Host arrays in Fortran order; the handle supplies mesh + basis.  doMPISides selects the side range like the reference. */

@@ -119,3 +119,47 @@ def test_unsupported_boundary_type_is_refused():
     r = build_case(BoxSpec((2, 2, 2), periodic=(False, True, True), bc_of_face=bc, **BOX), 2, G, eqn)[0]
     with pytest.raises(Exception, match="boundary type 27"):
         FlexiGpu(r)
+
+
+@pytest.mark.parametrize("N,node,split", [(5, GL, True), (4, G, False), (7, GL, True)])
+def test_error_norms_after_rk_steps_on_device(N, node, split):
+    """BASELINE north star: 'L2/Linf error norms after a fixed number of RK steps must match to 1e-10'.  convtest flavour
+    (ExactFunc 4 + CalcSource, exact-function Dirichlet BCs), 5 LSERK steps at fixed dt on GPU and oracle, then CalcErrorNorms
+    (analyze.f90:391-485) three ways: host routine on the oracle state, host routine on the downloaded GPU state, and
+    flexi_gpu_calc_error_norms on the device."""
+    from flexi_b200.hostmesh.analyze import AnalyzeBasis, calc_error_norms
+
+    bc = {(a, s): 1 for a in range(3) for s in (-1, 1)}
+    eqn = dict(parabolic=True, riemann="lf" if split else "roeentropyfix", mu0=1e-3, boundary_type=[(2, 0, 0)], ref_state_prim=[REF],
+               ini_exact_func=4, do_calc_source=True, adv_vel=(0.3, 0.3, 0.3))
+    if split:
+        eqn.update(split_dg=True, split_dg_type="pi")
+    r = build_case(BoxSpec((2, 2, 2), periodic=(False,) * 3, bc_of_face=bc, **BOX), N, node, eqn)[0]
+    U0 = r.eqn.exact_func4(r.mesh.Elem_xGP, 0.0)
+    w = O.OracleWorld([(r.desc, r.keep)])
+    w.set_state([U0])
+    g = FlexiGpu(r)
+    try:
+        g.set_state(U0)
+        dt = 0.5 * w.calc_timestep()[0]
+        t = 0.0
+        for _ in range(5):
+            w.timestep(t, dt)
+            g.TimeStep(t, dt)
+            t += dt
+        ab = AnalyzeBasis(r.basis)
+        vol = ab.volume(r.mesh.sJ)
+        exact = lambda x: r.eqn.exact_func4(x, t)  # noqa: E731
+        l2o, lio = calc_error_norms(ab, r.mesh, w.ranks[0].array("U"), exact, vol)
+        l2h, lih = calc_error_norms(ab, r.mesh, g.get_state(), exact, vol)
+        l2d, lid = g.CalcErrorNorms_sums(t, 4, ab.Vdm, ab.w3, r.mesh.Elem_xGP)
+        L2o, L2h, L2d = np.sqrt(l2o / vol), np.sqrt(l2h / vol), np.sqrt(l2d / vol)
+        assert np.all(L2o > 0) and np.all(L2o < 1e-2)  # a real discretisation error, not zero
+        # 1e-10 relative to the norm, floored at 1e-13 of the solution magnitude: at N=7 the discretisation error (2e-5) is so
+        # small that the norm of U-U_exact inherits the 1e-14 round-off differences of U itself
+        floor = 1e-13 * np.max(np.abs(U0))
+        for a, b in ((L2h, L2o), (L2d, L2o), (lih, lio), (lid, lio)):
+            assert np.all(np.abs(a - b) <= 1e-10 * np.abs(b) + floor), (a, b)
+    finally:
+        g.close()
+        w.close()
