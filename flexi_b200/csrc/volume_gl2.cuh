@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(VolGL2Cfg<NP, PARA>::NT, VolGL2Cfg<NP, PARA>::
     sJn = __ldg(A.m.sJ + (size_t)e * D::NP3 + n);
   }
   SideRef nsr{-1, 0};  // side of face tid/21 of the element one wave later (its traces + geometry are prefetched after S1)
-  if (A.prefetchAhead > 0 && (int)blockIdx.x + A.prefetchAhead < A.nList) {
+  if (A.prefetchAhead > 0 && (int)blockIdx.x + A.prefetchAhead < A.nList && !(A.dbg & 32)) {
     // pull the element that will run in this CTA slot one wave later (U, metrics, Jacobian: 60 KB) from HBM into L2 now
     const int en = A.elems ? A.elems[blockIdx.x + A.prefetchAhead] : (int)blockIdx.x + A.prefetchAhead;
     if (PARA && tid < 126) nsr = A.m.e2s[en * 6 + tid / 21];
@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(VolGL2Cfg<NP, PARA>::NT, VolGL2Cfg<NP, PARA>::
   int faceSlot[FACE_IT];
   bool faceLh[FACE_IT];  // plus side: L_HatPlus(N) (BR1)
   double faceSgn[FACE_IT];
-  if (PARA) {
+  if (PARA && !(A.dbg & 16)) {
 #pragma unroll
     for (int it = 0; it < FACE_IT; ++it) {
       const int t = tid + it * NT;
@@ -399,7 +399,7 @@ __global__ void __launch_bounds__(VolGL2Cfg<NP, PARA>::NT, VolGL2Cfg<NP, PARA>::
     cp_async_wait_all();
 #pragma unroll
     for (int it = 0; it < FACE_IT; ++it) {
-      if (faceSlot[it] >= 0) {
+      if (faceSlot[it] >= 0 && !(A.dbg & 16)) {
         double* o = sX + (faceSlot[it] & 0xffff);
         const int nF = faceSlot[it] >> 16;
         double Un[5], Pb[6];
