@@ -681,6 +681,15 @@ __global__ void __launch_bounds__(Dim<NP>::NP3) k_update(UpdArgs A) {
 #pragma unroll
   for (int v = 0; v < 5; ++v) ut[v] = A.UtVol[((size_t)e * 5 + v) * D::NP3 + n];
   const double sJ = A.m.sJ[(size_t)e * D::NP3 + n];
+  // the RK register and the state are read here, together with everything else, and not next to their stores below: the
+  // stores may alias the loads as far as the compiler knows, which would serialise five load/store round trips per thread
+  double uOld[5], rkOld[5];
+#pragma unroll
+  for (int v = 0; v < 5; ++v) {
+    const size_t g = ((size_t)e * 5 + v) * D::NP3 + n;
+    uOld[v] = (A.mode != 0) ? A.U[g] : 0.;
+    rkOld[v] = (A.mode == 2) ? A.UtTmp[g] : 0.;
+  }
   __syncthreads();
   const double* lhm = sB + D::O_LHM;
   const double* lhp = sB + D::O_LHP;
@@ -730,9 +739,9 @@ __global__ void __launch_bounds__(Dim<NP>::NP3) k_update(UpdArgs A) {
   for (int v = 0; v < 5; ++v) {
     const size_t g = ((size_t)e * 5 + v) * D::NP3 + n;
     double tmp = ut[v];
-    if (A.mode == 2) tmp = A.UtTmp[g] * (-A.rkA) + ut[v];
+    if (A.mode == 2) tmp = rkOld[v] * (-A.rkA) + ut[v];
     A.UtTmp[g] = tmp;
-    const double u = A.U[g] + tmp * A.b_dt;
+    const double u = uOld[v] + tmp * A.b_dt;
     A.U[g] = u;
     sU[v * D::NP3 + n] = u;
   }
