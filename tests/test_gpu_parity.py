@@ -308,3 +308,59 @@ def test_gpu_reproduces_reference_tgv_regression_csv():
             assert abs(row2[k] - ref) <= tol * max(abs(ref), 1e-30) + 1e-18, (k, row2[k], ref)
     finally:
         g.close()
+
+
+@pytest.mark.parametrize("nel,N,node,eqn", [
+    ((2, 2, 2), 3, GL, dict(parabolic=True, split_dg=True, split_dg_type="pi", riemann="lf", mu0=1e-2)),
+    ((2, 2, 2), 7, GL, dict(parabolic=True, split_dg=True, split_dg_type="pi", riemann="roe", mu0=1e-2)),
+    ((2, 2, 2), 4, G, dict(parabolic=True, riemann="hllc", mu0=1e-2)),
+    ((2, 2, 2), 2, GL, dict(parabolic=False, riemann="lf")),
+])
+def test_smallest_periodic_meshes(nel, N, node, eqn):
+    """Edge case of the side bookkeeping: two elements per periodic direction (the smallest box the host mesh, like HOPR,
+    allows), so both neighbours of an element in a direction are the same element, joined by two different sides; the grid is
+    far smaller than one CTA wave."""
+    r, w, g, _ = run_pair(BoxSpec(nel, **CURVED), N, node, eqn)
+    try:
+        w.dg_time_derivative(0.0)
+        ut = g.DGTimeDerivative_weakForm(0.0)
+        assert np.all(rel(ut, w.ranks[0].array("Ut")) < TOL_UT), rel(ut, w.ranks[0].array("Ut"))
+        dt, *_ = w.calc_timestep()
+        assert abs(g.CalcTimeStep()[0] - dt) <= 1e-13 * dt
+        for k in range(2):
+            w.timestep(k * dt, dt)
+            g.TimeStep(k * dt, dt)
+        assert np.all(rel(g.get_state(), w.ranks[0].array("U")) < 1e-12)
+    finally:
+        g.close()
+        w.close()
+
+
+def test_p_convergence_through_the_gpu_path():
+    """convtest/p_3D flavour (ExactFunc 4 with source, exact Dirichlet BCs, LF, mu0=1e-3): the L2 error of the density after a
+    short run drops spectrally with N (the reference expects EOC >= 0.8 (N+1) in its h/p convergence checks); norms computed by
+    flexi_gpu_calc_error_norms."""
+    from flexi_b200.hostmesh.analyze import AnalyzeBasis
+
+    bc = {(a, s): 1 for a in range(3) for s in (-1, 1)}
+    errs = []
+    for N in (2, 3, 4, 5, 6):
+        eqn = dict(parabolic=True, riemann="lf", mu0=1e-3, boundary_type=[(2, 0, 0)], ref_state_prim=[(1.0, 0.3, 0.0, 0.0, 0.71428571)],
+                   ini_exact_func=4, do_calc_source=True, adv_vel=(0.3, 0.3, 0.3), split_dg=True, split_dg_type="pi")
+        r = build_case(BoxSpec((2, 2, 2), periodic=(False,) * 3, bc_of_face=bc, x0=(-1.0, -1.0, -1.0), length=(2.0, 2.0, 2.0)), N, GL, eqn)[0]
+        g = FlexiGpu(r)
+        try:
+            g.set_state(r.eqn.exact_func4(r.mesh.Elem_xGP, 0.0))
+            t, tend = 0.0, 0.05
+            while t < tend - 1e-14:
+                dt = min(g.CalcTimeStep()[0], tend - t)
+                g.TimeStep(t, dt)
+                t += dt
+            ab = AnalyzeBasis(r.basis)
+            l2, _ = g.CalcErrorNorms_sums(t, 4, ab.Vdm, ab.w3, r.mesh.Elem_xGP)
+            errs.append(float(np.sqrt(l2[0] / ab.volume(r.mesh.sJ))))
+        finally:
+            g.close()
+    ratios = [errs[i] / errs[i + 1] for i in range(len(errs) - 1)]
+    assert all(x > 2.5 for x in ratios), (errs, ratios)
+    assert errs[-1] < 1e-5, errs
