@@ -24,7 +24,16 @@ CASES = {
     "split": (5, B.NODE_GAUSS_LOBATTO, dict(parabolic=True, split_dg=True, split_dg_type="pi", riemann="lf", mu0=1e-2)),
     "weakG": (4, B.NODE_GAUSS, dict(parabolic=True, riemann="roe", mu0=1e-2, n_var_lifting=4)),
     "euler": (3, B.NODE_GAUSS_LOBATTO, dict(parabolic=False, riemann="hllc")),
+    # BASELINE configs[3] flavour: curved mesh with no-slip / slip walls and a Dirichlet far field, N=5, HLLC + BR2, partitioned
+    "config4": (5, B.NODE_GAUSS, dict(parabolic=True, lifting=2, riemann="hllc", mu0=1e-2, eta_br2=2.0, eta_br2_wall=3.0,
+                                      boundary_type=[(3, 2, 0), (9, 0, 0), (2, 1, 0)],
+                                      ref_state_prim=[(1.0, 0.3, 0.0, 0.0, 0.71428571), (1.0, 0.0, 0.0, 0.0, 0.9)])),
+    # the same boundaries under the split-form LGL kernel (viscous-trace protocol: boundary sides keep gradient traces)
+    "splitwall": (5, B.NODE_GAUSS_LOBATTO, dict(parabolic=True, lifting=1, riemann="lf", mu0=1e-2, split_dg=True, split_dg_type="pi",
+                                                boundary_type=[(4, 2, 0), (9, 0, 0), (2, 1, 0)],
+                                                ref_state_prim=[(1.0, 0.3, 0.0, 0.0, 0.71428571), (1.0, 0.0, 0.0, 0.0, 0.9)])),
 }
+WALL_BC = {(1, -1): 1, (1, 1): 2, (0, -1): 3, (0, 1): 3}  # walls in y, far field in x, periodic in z
 
 
 def main():
@@ -37,7 +46,10 @@ def main():
     else:
         dist.init_process_group("gloo", rank=rank, world_size=world)
     N, node, eqn = CASES[case]
-    spec = BoxSpec((4, 3, 2), **CURVED)
+    if "boundary_type" in eqn:
+        spec = BoxSpec((4, 3, 2), periodic=(False, False, True), bc_of_face=WALL_BC, **CURVED)
+    else:
+        spec = BoxSpec((4, 3, 2), **CURVED)
     part = dict(partition="linear") if world != 4 else dict(partition="block", blocks=(2, 2, 1))
     ranks = build_case(spec, N, node, eqn, nranks=world, **part)  # every rank builds all partitions (tiny mesh) for the oracle world
     me = ranks[rank]
