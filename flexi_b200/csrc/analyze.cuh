@@ -216,4 +216,76 @@ __global__ void k_norm_reduce(const double* in, int nElems, int nVal, int nSum, 
   }
 }
 
+// CalcBodyForces, equations/navierstokes/calcbodyforces.f90:46-250, per BC side: pressure force / moment (CalcPressureForce
+// :117-151) and viscous force / moment (CalcViscousForce :158-240) integrated over the side with wGPSurf*SurfElem.  One CTA per BC
+// side; the host adds the sides of each wall BC in SideID order like the reference loop (:75-100).
+struct BodyForceArgs {
+  Eqn q;
+  int np, nvl, parabolic;
+  const double* U_master;  // [s][5][NP2]
+  const double* gm[3];     // gradU{x,y,z}_master [s][nvl][NP2]
+  const double* Geo;       // [s][10][NP2]
+  const double* faceX;     // Face_xGP of the BC sides [s][3][NP2] (NULL: moments are not computed)
+  const double* wSurf;     // wGPSurf [NP2]
+  double momOrigin[3];
+  double* out;             // [s][12]: Fp(3), Fv(3), Mp(3), Mv(3)
+};
+
+__global__ void k_body_forces(BodyForceArgs A) {
+  __shared__ double sRed[12][32];
+  const int np2 = A.np * A.np, tid = threadIdx.x, s = blockIdx.x;
+  double acc[12];
+  for (int c = 0; c < 12; ++c) acc[c] = 0.;
+  if (tid < np2) {
+    const int pq = tid;
+    double Uc[5], P[6];
+    for (int v = 0; v < 5; ++v) Uc[v] = A.U_master[((size_t)s * 5 + v) * np2 + pq];
+    cons_to_prim(A.q, Uc, P);  // UPrim_master, equation.f90:189-216
+    const double* g = A.Geo + (size_t)s * 10 * np2 + pq;
+    const double nv[3] = {g[0], g[np2], g[2 * np2]};
+    const double dA = A.wSurf[pq] * g[9 * np2];
+    double r[3] = {0., 0., 0.};
+    if (A.faceX)
+      for (int c = 0; c < 3; ++c) r[c] = A.faceX[((size_t)s * 3 + c) * np2 + pq] - A.momOrigin[c];
+    double df[3];
+    for (int c = 0; c < 3; ++c) {
+      df[c] = P[PRES] * nv[c] * dA;
+      acc[c] = df[c];
+    }
+    acc[6] = r[1] * df[2] - r[2] * df[1];
+    acc[7] = r[2] * df[0] - r[0] * df[2];
+    acc[8] = r[0] * df[1] - r[1] * df[0];
+    if (A.parabolic) {
+      const int v0 = (A.nvl == 5) ? 1 : 0;  // LIFT_VELV
+      double G[3][3];                        // GradV(c,d) = d v_c / d x_d
+      for (int d = 0; d < 3; ++d)
+        for (int c = 0; c < 3; ++c) G[c][d] = A.gm[d][((size_t)s * A.nvl + v0 + c) * np2 + pq];
+      const double muS = A.q.mu0, divV = G[0][0] + G[1][1] + G[2][2];
+      double tau[3][3];
+      for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) tau[a][b] = muS * (G[a][b] + G[b][a]);
+      for (int a = 0; a < 3; ++a) tau[a][a] = tau[a][a] - 2. / 3. * muS * divV;
+      double dfv[3];
+      for (int a = 0; a < 3; ++a) dfv[a] = (tau[a][0] * nv[0] + tau[a][1] * nv[1] + tau[a][2] * nv[2]) * A.wSurf[pq] * g[9 * np2];
+      // Fv = -Fv, Mv = -Mv: the force acting on the wall (calcbodyforces.f90:236-237)
+      for (int c = 0; c < 3; ++c) acc[3 + c] = -dfv[c];
+      acc[9] = -(r[1] * dfv[2] - r[2] * dfv[1]);
+      acc[10] = -(r[2] * dfv[0] - r[0] * dfv[2]);
+      acc[11] = -(r[0] * dfv[1] - r[1] * dfv[0]);
+    }
+  }
+  const int lane = tid & 31, wid = tid >> 5, nw = (blockDim.x + 31) >> 5;
+  for (int c = 0; c < 12; ++c) {
+    double v = acc[c];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) sRed[c][wid] = v;
+  }
+  __syncthreads();
+  if (tid < 12) {
+    double v = sRed[tid][0];
+    for (int w = 1; w < nw; ++w) v += sRed[tid][w];
+    A.out[(size_t)s * 12 + tid] = v;
+  }
+}
+
 }  // namespace fx

@@ -106,6 +106,8 @@ struct flexi_gpu_handle {
   bool vt = false;             // viscous-trace protocol between k_volume_gl2 and k_flux (kernels.cuh: VolArgs::fvm)
   bool gradTracesFull = true;  // gradU?_master/slave hold the traces of every side (else only of the BC sides)
   double *fvm = nullptr, *fvs = nullptr;
+  std::vector<int32_t> bcIndex, bcTypeOfBC;  // BC(SideID)-1 per BC side; BoundaryType(:,BC_TYPE) per BC
+  int nBCs = 0;
   int prefetchAhead = 0;  // resident CTAs of the element kernel (2 per SM): distance of its L2 prefetch
   bool tracesValid = false;
   double lastT = 0.;  // time of the last DG operator evaluation (boundary states / source are time dependent)
@@ -677,9 +679,14 @@ static int init_impl(const flexi_gpu_desc* d, H* h) {
     if (h->nBCSides > 0 && !h->bcTablesMissing) {
       std::vector<int32_t> bt(h->nBCSides), bs(h->nBCSides);
       bool needX = false;
+      h->nBCs = d->nBCs;
+      h->bcIndex.resize(h->nBCSides);
+      h->bcTypeOfBC.resize(d->nBCs);
+      for (int b = 0; b < d->nBCs; ++b) h->bcTypeOfBC[b] = d->BoundaryType[(size_t)0 * d->nBCs + b];
       for (int s = 0; s < h->nBCSides; ++s) {
         const int ibc = d->BC[s];
         if (ibc < 1 || ibc > d->nBCs) return fail(FLEXI_GPU_ERR_ARG, "BC(%d)=%d outside 1..nBCs", s + 1, ibc);
+        h->bcIndex[s] = ibc - 1;
         bt[s] = d->BoundaryType[(size_t)0 * d->nBCs + (ibc - 1)];
         bs[s] = d->BoundaryType[(size_t)1 * d->nBCs + (ibc - 1)];
         switch (bt[s]) {
@@ -1063,6 +1070,58 @@ int flexi_gpu_calc_error_norms(flexi_gpu_handle* h, double Time, int32_t Analyze
   for (int v = 0; v < 5; ++v) {
     L_2_sum[v] = out[v];
     L_Inf[v] = out[5 + v];
+  }
+  return 0;
+}
+
+int flexi_gpu_calc_body_forces(flexi_gpu_handle* h, const double* wGPSurf, const double* Face_xGP, const double* MomOrigin, double* Fp,
+                               double* Fv, double* Mp, double* Mv) {
+  ENTER(h);
+  if (!wGPSurf || !Fp || !Fv || !Mp || !Mv) return fail(FLEXI_GPU_ERR_ARG, "null argument");
+  if (h->bcTablesMissing) return fail(FLEXI_GPU_ERR_ARG, "BC sides without BC / BoundaryType tables");
+  for (int i = 0; i < 3 * h->nBCs; ++i) Fp[i] = Fv[i] = Mp[i] = Mv[i] = 0.;
+  if (h->nBCSides <= 0) return 0;
+  const int np2 = h->np2;
+  if (!h->bc.faceX && Face_xGP) {  // kept from the first call on (the BC sides come first in the side list)
+    double* dx = nullptr;
+    CKR(dalloc(h, &dx, (size_t)h->nBCSides * 3 * np2));
+    CKR(upload_aos(h, Face_xGP, dx, 3, np2, h->nBCSides));
+    h->bc.faceX = dx;
+  }
+  CKR(ensure_stage(h, (size_t)np2 + (size_t)h->nBCSides * 12));
+  double* dW = h->stage;
+  double* dPart = dW + np2;
+  CK(cudaMemcpyAsync(dW, wGPSurf, np2 * 8, cudaMemcpyHostToDevice, h->sc));
+  BodyForceArgs a{};
+  a.q = h->q;
+  a.np = h->np;
+  a.nvl = h->nvl;
+  a.parabolic = h->para ? 1 : 0;
+  a.U_master = h->Um;
+  for (int d = 0; d < 3; ++d) a.gm[d] = h->gm[d];
+  a.Geo = h->m.Geo;
+  a.faceX = h->bc.faceX;
+  a.wSurf = dW;
+  for (int c = 0; c < 3; ++c) a.momOrigin[c] = MomOrigin ? MomOrigin[c] : 0.;
+  a.out = dPart;
+  {
+    Timer tm(h, KC_DT, h->sc);
+    k_body_forces<<<h->nBCSides, ((np2 + 31) / 32) * 32, 0, h->sc>>>(a);
+  }
+  CK(cudaGetLastError());
+  std::vector<double> part((size_t)h->nBCSides * 12);
+  CK(cudaMemcpyAsync(part.data(), dPart, part.size() * 8, cudaMemcpyDeviceToHost, h->sc));
+  h->d2h += (int64_t)(part.size() * 8);
+  CK(cudaStreamSynchronize(h->sc));
+  for (int s = 0; s < h->nBCSides; ++s) {  // calcbodyforces.f90:75-100: wall BCs only, sides in SideID order
+    const int b = h->bcIndex[s], bt = h->bcTypeOfBC[b];
+    if (!(bt == 3 || bt == 4 || bt == 9)) continue;
+    for (int c = 0; c < 3; ++c) {
+      Fp[b * 3 + c] += part[(size_t)s * 12 + c];
+      Fv[b * 3 + c] += part[(size_t)s * 12 + 3 + c];
+      Mp[b * 3 + c] += part[(size_t)s * 12 + 6 + c];
+      Mv[b * 3 + c] += part[(size_t)s * 12 + 9 + c];
+    }
   }
   return 0;
 }

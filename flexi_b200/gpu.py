@@ -30,7 +30,7 @@ KERNEL_CLASSES = ("volume", "flux", "update", "prolong", "calc_timestep", "layou
 EXPORTS = ("flexi_gpu_last_error", "flexi_gpu_abi_version", "flexi_gpu_nccl_unique_id", "flexi_gpu_init", "flexi_gpu_finalize",
            "flexi_gpu_set_state", "flexi_gpu_get_state", "flexi_gpu_dg_time_derivative", "flexi_gpu_timestep",
            "flexi_gpu_timestep_n", "flexi_gpu_calc_timestep", "flexi_gpu_get_array", "flexi_gpu_keep_gradients",
-           "flexi_gpu_prolong_to_face", "flexi_gpu_surf_int", "flexi_gpu_analyze_tgv", "flexi_gpu_calc_error_norms", "flexi_gpu_counters", "flexi_gpu_kernel_times",
+           "flexi_gpu_prolong_to_face", "flexi_gpu_surf_int", "flexi_gpu_analyze_tgv", "flexi_gpu_calc_error_norms", "flexi_gpu_calc_body_forces", "flexi_gpu_counters", "flexi_gpu_kernel_times",
            "flexi_gpu_set_profiling", "flexi_gpu_synchronize", "flexi_gpu_stream")
 
 
@@ -71,6 +71,7 @@ def lib():
     L.flexi_gpu_surf_int.argtypes = [P, PD, PD, PD, I32]
     L.flexi_gpu_analyze_tgv.argtypes = [P, I32, PD, PD, PD]
     L.flexi_gpu_calc_error_norms.argtypes = [P, C.c_double, I32, I32, PD, PD, PD, PD, PD]
+    L.flexi_gpu_calc_body_forces.argtypes = [P, PD, PD, PD, PD, PD, PD, PD]
     L.flexi_gpu_counters.argtypes = [P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.flexi_gpu_kernel_times.argtypes = [P, PD, C.POINTER(C.c_int64), I32, I32]
     L.flexi_gpu_set_profiling.argtypes = [P, I32]
@@ -160,6 +161,15 @@ class FlexiGpu:
         self._ck(self.L.flexi_gpu_calc_error_norms(self.h, float(Time), int(AnalyzeExactFunc), na1 - 1, _pd(vdm_f), _pd(w), _pd(x), _pd(l2),
                                                    _pd(li)))
         return l2, li
+
+    def CalcBodyForces(self, wGPSurf, Face_xGP_bc, nBCs, MomOrigin=(0.0, 0.0, 0.0)):
+        """CalcBodyForces (calcbodyforces.f90:46-250) per rank on the device: (Fp, Fv, Mp, Mv), each [nBCs, 3]."""
+        w = np.ascontiguousarray(wGPSurf, dtype=np.float64)
+        x = np.ascontiguousarray(Face_xGP_bc, dtype=np.float64)
+        mo = np.ascontiguousarray(MomOrigin, dtype=np.float64)
+        out = [np.zeros((nBCs, 3)) for _ in range(4)]
+        self._ck(self.L.flexi_gpu_calc_body_forces(self.h, _pd(w), _pd(x), _pd(mo), *[_pd(o) for o in out]))
+        return out
 
     @staticmethod
     def tgv_normalise(sums_per_rank, vol, mu0, rho0=1.0):

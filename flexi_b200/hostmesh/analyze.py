@@ -71,3 +71,34 @@ def calc_error_norms(ab, mesh, U, exact_fn, vol):
     linf = np.max(np.abs(err).reshape(-1, err.shape[-1]), axis=0)
     l2sq = np.einsum("ekjiv,ekji->v", err * err, ab.w3[None] * J_A)
     return l2sq, linf
+
+
+def calc_body_forces(basis, eqn, mesh, boundary_type, U_master, gradUx_master, gradUy_master, gradUz_master, mom_origin=(0.0, 0.0, 0.0)):
+    """CalcBodyForces (equations/navierstokes/calcbodyforces.f90:46-250) for one rank: (Fp, Fv, Mp, Mv), each [nBCs, 3].
+    Wall BCs are the boundary types 3, 4, 9 (analyze_equation.f90:104-112).  Arrays as [side, q, p, var]."""
+    nBCs = len(boundary_type)
+    Fp, Fv, Mp, Mv = (np.zeros((nBCs, 3)) for _ in range(4))
+    wS = np.einsum("q,p->qp", basis.wGP, basis.wGP)
+    nvl = gradUx_master.shape[-1]
+    v0 = 1 if nvl == 5 else 0
+    mo = np.asarray(mom_origin, dtype=float)
+    for s in range(mesh.nBCSides):
+        b = int(mesh.BC[s]) - 1
+        if boundary_type[b][0] not in (3, 4, 9):
+            continue
+        P = eqn.cons_to_prim(U_master[s])
+        dA = wS * mesh.SurfElem[s]
+        nv = mesh.NormVec[s]
+        r = mesh.Face_xGP[s] - mo
+        df = P[..., 4, None] * nv * dA[..., None]
+        Fp[b] += df.sum(axis=(0, 1))
+        Mp[b] += np.cross(r, df).sum(axis=(0, 1))
+        G = np.stack([gradUx_master[s][..., v0:v0 + 3], gradUy_master[s][..., v0:v0 + 3], gradUz_master[s][..., v0:v0 + 3]], axis=-1)
+        div = G[..., 0, 0] + G[..., 1, 1] + G[..., 2, 2]
+        tau = eqn.mu0 * (G + np.swapaxes(G, -1, -2))
+        for a in range(3):
+            tau[..., a, a] -= 2.0 / 3.0 * eqn.mu0 * div
+        dfv = np.einsum("qpab,qpb->qpa", tau, nv) * dA[..., None]
+        Fv[b] -= dfv.sum(axis=(0, 1))
+        Mv[b] -= np.cross(r, dfv).sum(axis=(0, 1))
+    return Fp, Fv, Mp, Mv

@@ -9,6 +9,7 @@
  *   flexi_gpu_surf_int            replaces  SurfIntCons                            dg/surfint.t90:21-239,475-616
  *   flexi_gpu_analyze_tgv         replaces  AnalyzeTestcase steps 1-4 (TGV)        testcase/taylorgreenvortex/testcase.f90:241-420
  *   flexi_gpu_calc_error_norms    replaces  CalcErrorNorms (per-rank part)         analyze/analyze.f90:391-485
+ *   flexi_gpu_calc_body_forces    replaces  CalcBodyForces (per-rank part)         equations/navierstokes/calcbodyforces.f90:46-250
  *   halo exchange inside          replaces  Start{Receive,Send}MPIData/Finish...   mpi/mpi.f90:244-445  (NCCL send/recv)
  *
  * The Fortran host keeps everything else (ini parsing, mesh/metrics, HDF5 I/O) and hands its module arrays over ONCE through
@@ -230,6 +231,16 @@ int flexi_gpu_analyze_tgv(flexi_gpu_handle* h, int32_t NAnalyze, const double* V
 int flexi_gpu_calc_error_norms(flexi_gpu_handle* h, double Time, int32_t AnalyzeExactFunc, int32_t NAnalyze,
                                const double* Vdm_GaussN_NAnalyze, const double* wGPVolAnalyze, const double* Elem_xGP,
                                double* L_2_sum, double* L_Inf);
+
+/* CalcBodyForces (equations/navierstokes/calcbodyforces.f90:46-250), per-rank part: pressure and friction force / moment on every
+ * wall BC (BoundaryType 3, 4, 9; analyze_equation.f90:104-112) from U_master and gradU?_master of the BC sides as left by the last
+ * DG operator call.  wGPSurf(0:N,0:N) (MOD_Analyze_Vars), Face_xGP(3,0:N,0:N,1:nBCSides) (may be NULL: no moments; uploaded on the
+ * first call unless exact-function BCs already keep it), MomOrigin(3) (NULL = origin).  Outputs (3,nBCs) in Fortran order; the host
+ * keeps the MPI_REDUCE and BodyForce = Fv + Fp (:102-114).  Call it where the reference does: after flexi_gpu_dg_time_derivative at
+ * an analyze step (timedisc_func.f90:323-326) -- between RK steps U_master/U_slave on the device already hold the traces of the
+ * UPDATED state (the stage update prolongs them for the next stage), one stage ahead of the reference's module arrays. */
+int flexi_gpu_calc_body_forces(flexi_gpu_handle* h, const double* wGPSurf, const double* Face_xGP, const double* MomOrigin, double* Fp,
+                               double* Fv, double* Mp, double* Mv);
 
 /* Operator-level entry points (what the reference's own unit tests drive, unitTests/ProlongToFace.f90, SurfInt.f90).
  * Host arrays in Fortran order; the handle supplies mesh + basis.  doMPISides selects the side range like the reference. */

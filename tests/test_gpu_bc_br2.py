@@ -163,3 +163,53 @@ def test_error_norms_after_rk_steps_on_device(N, node, split):
     finally:
         g.close()
         w.close()
+
+
+@pytest.mark.parametrize("N,node,lifting,extra", [(5, G, 2, {}), (7, GL, 1, SPLIT_PI), (4, GL, 1, {})])
+def test_body_forces_on_device(N, node, lifting, extra):
+    """CalcBodyForces (calcbodyforces.f90) on the device against the host routine fed with the ORACLE's traces, after one DG
+    operator call and after time steps (under the viscous-trace protocol the BC sides keep their gradient traces)."""
+    from flexi_b200.hostmesh.analyze import calc_body_forces
+
+    btype = [(4, 2, 0), (9, 0, 0), (2, 1, 0)]
+    eqn = dict(parabolic=True, lifting=lifting, riemann="lf", mu0=1e-2, boundary_type=btype,
+               ref_state_prim=[REF, (1.0, 0.0, 0.0, 0.0, 0.9)], **extra)
+    r = build_case(wall_farfield_box(), N, node, eqn)[0]
+    U0 = r.eqn.smooth_state(r.mesh.Elem_xGP, length=2.0)
+    w = O.OracleWorld([(r.desc, r.keep)])
+    w.set_state([U0])
+    g = FlexiGpu(r)
+    try:
+        g.set_state(U0)
+        wS = np.einsum("q,p->qp", r.basis.wGP, r.basis.wGP)
+        xbc = r.mesh.Face_xGP[:r.mesh.nBCSides]
+        mo = (0.1, -0.2, 0.3)
+
+        def compare(where):
+            o = w.ranks[0]
+            ref = calc_body_forces(r.basis, r.eqn, r.mesh, btype, o.array("U_master"), o.array("gradUx_master"), o.array("gradUy_master"),
+                                   o.array("gradUz_master"), mo)
+            dev = g.CalcBodyForces(wS, xbc, len(btype), mo)
+            for a, b, name in zip(dev, ref, ("Fp", "Fv", "Mp", "Mv")):
+                scale = max(np.max(np.abs(b)), 1e-30)
+                assert np.max(np.abs(a - b)) <= 1e-12 * scale, (where, name, a, b)
+                assert np.all(a[2] == 0.0), name  # the far-field BC is no wall
+            assert np.max(np.abs(ref[1])) > 1e-4  # a real friction force
+
+        w.dg_time_derivative(0.0)
+        g.DGTimeDerivative_weakForm(0.0, want_ut=False)
+        compare("t=0")
+        t = 0.0
+        for _ in range(2):
+            dt = w.calc_timestep()[0]
+            w.timestep(t, dt)
+            g.TimeStep(t, dt)
+            t += dt
+        # analyze step: the reference re-evaluates the DG operator before AnalyzeEquation (timedisc_func.f90:323-326); this also
+        # checks that the boundary sides keep valid gradient traces across RK stages under the viscous-trace protocol
+        w.dg_time_derivative(t)
+        g.DGTimeDerivative_weakForm(t, want_ut=False)
+        compare("after 2 steps")
+    finally:
+        g.close()
+        w.close()
