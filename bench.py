@@ -77,7 +77,7 @@ class ClockSampler:
                     self.rows.append([x.strip() for x in o.split(",")])
             except Exception:
                 pass
-            self.stop.wait(0.2)
+            self.stop.wait(0.1)
 
     def __enter__(self):
         self.t.start()
