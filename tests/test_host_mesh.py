@@ -137,3 +137,27 @@ def test_partition_bookkeeping(partition, blocks, nranks):
             # lower rank owns floor(n/2) MINE sides (prepare_mesh.f90:247-254)
             n = (a1 - a0) + (m.offsetMPISides_YOUR[inb + 1] - m.offsetMPISides_YOUR[inb])
             assert (a1 - a0) == (n // 2 if r < nb else n - n // 2)
+
+
+def test_host_body_forces_of_a_uniform_state_are_pressure_times_wall_area():
+    """Checker of the GPU CalcBodyForces test: on a Cartesian box with walls at y = -1 / +1 (2 x 2 each) a uniform state at rest
+    gives Fp = p * n * A per wall BC, no friction, and a moment about the wall centre of zero."""
+    from flexi_b200.hostmesh.analyze import calc_body_forces
+    from flexi_b200.hostmesh.case import build_case
+    from flexi_b200.hostmesh.mesh import BoxSpec
+
+    btype = [(4, 1, 0), (9, 0, 0), (2, 1, 0)]
+    bc = {(1, -1): 1, (1, 1): 2, (0, -1): 3, (0, 1): 3}
+    eqn = dict(parabolic=True, riemann="lf", mu0=1e-2, boundary_type=btype, ref_state_prim=[(1.0, 0.0, 0.0, 0.0, 0.9)])
+    r = build_case(BoxSpec((3, 2, 2), periodic=(False, False, True), bc_of_face=bc, x0=(-1.0, -1.0, -1.0), length=(2.0, 2.0, 2.0)),
+                   3, "gauss-lobatto", eqn)[0]
+    m = r.mesh
+    p0 = 0.9
+    U = np.zeros((m.nSides, 4, 4, 5))
+    U[..., 0] = 1.0
+    U[..., 4] = p0 / (r.eqn.kappa - 1.0)
+    g0 = np.zeros((m.nSides, 4, 4, 5))
+    Fp, Fv, Mp, Mv = calc_body_forces(r.basis, r.eqn, m, btype, U, g0, g0, g0, mom_origin=(0.0, -1.0, 0.0))
+    assert np.allclose(Fp[0], (0.0, -p0 * 4.0, 0.0), atol=1e-13) and np.allclose(Fp[1], (0.0, p0 * 4.0, 0.0), atol=1e-13)
+    assert np.all(Fp[2] == 0.0) and np.all(Fv == 0.0) and np.all(Mv == 0.0)
+    assert np.allclose(Mp[0], 0.0, atol=1e-13)  # symmetric wall about the moment origin
