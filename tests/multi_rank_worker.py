@@ -115,6 +115,27 @@ def main():
         Ug, Uo = g.get_state(), w.ranks[rank].array("U")
         sc = np.max(np.abs(Uo).reshape(-1, 5), axis=0)
         assert np.all(np.max(np.abs(Ug - Uo).reshape(-1, 5), axis=0) <= 1e-12 * sc), "multi-rank state mismatch after 3 steps"
+        if eqn.get("parabolic") and "boundary_type" not in eqn:
+            # on-device TGV AnalyzeTestcase (steps 1-4) per rank + the host's reduction (steps 5-6) against the host analysis of
+            # the oracle world: the integrals of the partitioned run
+            from flexi_b200.hostmesh.analyze import AnalyzeBasis, tgv_analyze
+
+            ab = AnalyzeBasis(me.basis)
+            vol = sum(ab.volume(r.mesh.sJ) for r in ranks)
+            g.keep_gradients(True)
+            g.DGTimeDerivative_weakForm(t, want_ut=False)
+            w.dg_time_derivative(t)
+            parts = [None] * world
+            dist.all_gather_object(parts, {k: float(v) for k, v in g.AnalyzeTestcase_sums(ab.Vdm, ab.w3).items()})
+            dev = G.FlexiGpu.tgv_normalise(parts, vol, me.eqn.mu0)
+            host = [tgv_analyze(ab, r.eqn, r.mesh, o.array("U"), o.array("gradUx"), o.array("gradUy"), o.array("gradUz"), vol)
+                    for r, o in zip(ranks, w.ranks)]
+            for k in host[0]:
+                if k == "uPrime":
+                    continue
+                ref = max(h[k] for h in host) if k == "Vorticity_max" else sum(h[k] for h in host)
+                tol = 1e-8 if k in ("DR_p", "ED_D") else 1e-11
+                assert abs(dev[k] - ref) <= tol * max(abs(ref), 1e-30) + 1e-14, (k, dev[k], ref)
         g.close()
     w.close()
     dist.barrier()
