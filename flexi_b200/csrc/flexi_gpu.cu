@@ -1126,6 +1126,25 @@ int flexi_gpu_calc_body_forces(flexi_gpu_handle* h, const double* wGPSurf, const
   return 0;
 }
 
+int flexi_gpu_pin_host_array(void* ptr, int64_t nbytes) {
+  if (!ptr || nbytes <= 0) return fail(FLEXI_GPU_ERR_ARG, "null / empty host array");
+  const cudaError_t e = cudaHostRegister(ptr, (size_t)nbytes, cudaHostRegisterDefault);
+  if (e != cudaSuccess) {
+    cudaGetLastError();  // a refused registration must not poison the next kernel-launch check
+    return fail(FLEXI_GPU_ERR_CUDA, "cudaHostRegister: %s", cudaGetErrorString(e));
+  }
+  return 0;
+}
+int flexi_gpu_unpin_host_array(void* ptr) {
+  if (!ptr) return fail(FLEXI_GPU_ERR_ARG, "null host array");
+  const cudaError_t e = cudaHostUnregister(ptr);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(FLEXI_GPU_ERR_CUDA, "cudaHostUnregister: %s", cudaGetErrorString(e));
+  }
+  return 0;
+}
+
 int flexi_gpu_prolong_to_face(flexi_gpu_handle* h, const double* Uvol, double* Uface_master, double* Uface_slave, int32_t doMPISides) {
   ENTER(h);
   if (!Uvol || !Uface_master || !Uface_slave) return fail(FLEXI_GPU_ERR_ARG, "null argument");

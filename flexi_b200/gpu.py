@@ -30,7 +30,7 @@ KERNEL_CLASSES = ("volume", "flux", "update", "prolong", "calc_timestep", "layou
 EXPORTS = ("flexi_gpu_last_error", "flexi_gpu_abi_version", "flexi_gpu_nccl_unique_id", "flexi_gpu_init", "flexi_gpu_finalize",
            "flexi_gpu_set_state", "flexi_gpu_get_state", "flexi_gpu_dg_time_derivative", "flexi_gpu_timestep",
            "flexi_gpu_timestep_n", "flexi_gpu_calc_timestep", "flexi_gpu_get_array", "flexi_gpu_keep_gradients",
-           "flexi_gpu_prolong_to_face", "flexi_gpu_surf_int", "flexi_gpu_analyze_tgv", "flexi_gpu_calc_error_norms", "flexi_gpu_calc_body_forces", "flexi_gpu_counters", "flexi_gpu_kernel_times",
+           "flexi_gpu_prolong_to_face", "flexi_gpu_surf_int", "flexi_gpu_analyze_tgv", "flexi_gpu_calc_error_norms", "flexi_gpu_calc_body_forces", "flexi_gpu_pin_host_array", "flexi_gpu_unpin_host_array", "flexi_gpu_counters", "flexi_gpu_kernel_times",
            "flexi_gpu_set_profiling", "flexi_gpu_synchronize", "flexi_gpu_stream")
 
 
@@ -72,6 +72,8 @@ def lib():
     L.flexi_gpu_analyze_tgv.argtypes = [P, I32, PD, PD, PD]
     L.flexi_gpu_calc_error_norms.argtypes = [P, C.c_double, I32, I32, PD, PD, PD, PD, PD]
     L.flexi_gpu_calc_body_forces.argtypes = [P, PD, PD, PD, PD, PD, PD, PD]
+    L.flexi_gpu_pin_host_array.argtypes = [P, C.c_int64]
+    L.flexi_gpu_unpin_host_array.argtypes = [P]
     L.flexi_gpu_counters.argtypes = [P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.flexi_gpu_kernel_times.argtypes = [P, PD, C.POINTER(C.c_int64), I32, I32]
     L.flexi_gpu_set_profiling.argtypes = [P, I32]

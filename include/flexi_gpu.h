@@ -249,6 +249,11 @@ int flexi_gpu_prolong_to_face(flexi_gpu_handle* h, const double* Uvol, double* U
 int flexi_gpu_surf_int(flexi_gpu_handle* h, const double* Flux_master, const double* Flux_slave, double* Ut,
                        int32_t doMPISides);
 
+/* Page-lock a host array (cudaHostRegister) so that flexi_gpu_set_state / get_state / get_array move it at full PCIe speed and
+ * asynchronously; the Fortran host calls this once for MOD_DG_Vars:U after allocation (dg.f90:94) and unpins before DEALLOCATE. */
+int flexi_gpu_pin_host_array(void* ptr, int64_t nbytes);
+int flexi_gpu_unpin_host_array(void* ptr);
+
 /* counters for bench.py: kernels launched by this library since init, bytes moved by host<->device copies */
 int flexi_gpu_counters(flexi_gpu_handle* h, int64_t* kernel_launches, int64_t* h2d_bytes, int64_t* d2h_bytes);
 /* device time [ms] accumulated by CUDA events around each hot-path kernel class since the last reset (index = kernel class) */

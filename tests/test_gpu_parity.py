@@ -364,3 +364,29 @@ def test_p_convergence_through_the_gpu_path():
     ratios = [errs[i] / errs[i + 1] for i in range(len(errs) - 1)]
     assert all(x > 2.5 for x in ratios), (errs, ratios)
     assert errs[-1] < 1e-5, errs
+
+
+def test_pinned_host_array_roundtrip():
+    """flexi_gpu_pin_host_array (cudaHostRegister of the host's U array): set_state / get_state through a page-locked numpy
+    array give back the same bits; double registration is reported, not ignored."""
+    import ctypes as C
+
+    from flexi_b200.gpu import FlexiGpuError, lib
+
+    eqn = dict(parabolic=False, riemann="lf")
+    r = build_case(BoxSpec((2, 2, 2), **CURVED), 3, GL, eqn)[0]
+    U0 = np.ascontiguousarray(r.eqn.smooth_state(r.mesh.Elem_xGP, length=2.0))
+    out = np.empty_like(U0)
+    L = lib()
+    g = FlexiGpu(r)
+    try:
+        for a in (U0, out):
+            assert L.flexi_gpu_pin_host_array(C.c_void_p(a.ctypes.data), a.nbytes) == 0, L.flexi_gpu_last_error()
+        assert L.flexi_gpu_pin_host_array(C.c_void_p(U0.ctypes.data), U0.nbytes) != 0  # already registered
+        g.set_state(U0)
+        g.get_state(out)
+        assert np.array_equal(out, U0)
+    finally:
+        for a in (U0, out):
+            L.flexi_gpu_unpin_host_array(C.c_void_p(a.ctypes.data))
+        g.close()
