@@ -269,9 +269,9 @@ __global__ void __launch_bounds__(VolGL2Cfg<NP, PARA>::NT, VolGL2Cfg<NP, PARA>::
     for (int m = 0; m < 9; ++m) Mn[m] = __ldg(gM + m * D::NP3 + n);
     sJn = __ldg(A.m.sJ + (size_t)e * D::NP3 + n);
   }
-  SideRef nsr{-1, 0};  // side of face tid/21 of the element one wave later (its traces + geometry are prefetched after S1)
+  SideRef nsr{-1, 0};  // side of face tid/21 of that later element (its traces + geometry are prefetched after S1)
   if (A.prefetchAhead > 0 && (int)blockIdx.x + A.prefetchAhead < A.nList && !(A.dbg & 32)) {
-    // pull the element that will run in this CTA slot one wave later (U, metrics, Jacobian: 60 KB) from HBM into L2 now
+    // pull the element that starts half a wave of CTAs later (U, metrics, Jacobian: 60 KB) from HBM into L2 now
     const int en = A.elems ? A.elems[blockIdx.x + A.prefetchAhead] : (int)blockIdx.x + A.prefetchAhead;
     if (PARA && tid < 126) nsr = A.m.e2s[en * 6 + tid / 21];
     const char* pu = reinterpret_cast<const char*>(A.U + (size_t)en * 5 * D::NP3);
