@@ -1,4 +1,5 @@
-// volume_gl.cuh -- the Gauss-Lobatto element kernel (hot kernel of BASELINE configs[1]): ConsToPrim + BR1 lifting +
+// volume_gl.cuh -- the first Gauss-Lobatto element kernel; since volume_gl2.cuh took over the split form on even N+1 (the headline
+// configuration) it serves the GL weak form and the split form on odd N+1: ConsToPrim + BR1/BR2 lifting +
 // ApplyJacobianLifting + ProlongToFaceLifting + VolInt (split or weak form) of one element per CTA.
 //
 // Replaces, for PP_NodeType = GAUSS-LOBATTO (file:line under /root/reference/src):
