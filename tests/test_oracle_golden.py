@@ -93,9 +93,15 @@ def test_prolong_to_face_bin(elem_data, node_type, fname):
         assert almost_equal_abs_or_rel(mine, ref), (fname, v)
 
 
-@pytest.mark.parametrize("node_type,fname", [(1, "SurfInt_G3D.bin"), (2, "SurfInt_GL3D.bin")])
+@pytest.mark.parametrize("node_type,fname", [(1, "SurfInt_G3D.bin"), (2, "SurfInt_GL3D.bin"), (1, "SurfInt_G3D_Split.bin")])
 def test_surf_int_bin(elem_data, node_type, fname):
     """unitTests/SurfInt.f90:96-191: same random flux as master and slave flux, Ut=0 start, expected Ut(1,:,:,:,1).
+
+    SurfInt_G3D_Split.bin is the reference's fixture for the Gauss-node split form (SPLIT_DG, surfint.t90:90-137) with
+    U = UPrim = Metrics = Ja = 1 (unitTests/SurfInt.f90:129-147): for a constant state every two-point flux FluxB(:,l) is the same
+    and sum_l Leg(l) = 1, so the correction -(1/2)(FluxB_sum - FluxB)*NormalSign*LegHat vanishes and the expected Ut is the plain
+    Gauss surface integral -- which is what this (non-split) oracle routine must reproduce.  The fixture therefore pins the
+    surface integral, not the split correction (noted for the Gauss split form of SURVEY.md 8f).
 
     Both node types consume the (Gauss) L_HatMinus/L_HatPlus stored in the fixture -- a quirk of the reference's fixture
     that is reproduced, not fixed."""
