@@ -35,7 +35,9 @@ def test_prolong_to_face_bin_gpu(node_type, fname):
     assert np.all(us == 7.0)  # no slave element on these sides: untouched, like in the reference
 
 
-@pytest.mark.parametrize("node_type,fname", [(1, "SurfInt_G3D.bin"), (2, "SurfInt_GL3D.bin")])
+# SurfInt_G3D_Split.bin: the Gauss split-form fixture with a constant state, where the two-point correction vanishes (see
+# tests/test_oracle_golden.py): expected Ut = the plain Gauss surface integral
+@pytest.mark.parametrize("node_type,fname", [(1, "SurfInt_G3D.bin"), (2, "SurfInt_GL3D.bin"), (1, "SurfInt_G3D_Split.bin")])
 def test_surf_int_bin_gpu(node_type, fname):
     g, d = _gpu(node_type)
     (fl,) = read_records("SurfIntFlux.bin")
