@@ -251,6 +251,8 @@ int start_exchange(H* h, int kind) {
     if (h->vt) {  // viscous-trace protocol: the slave element's n.F_v replaces the three gradient messages
       double* a1[1] = {h->fvs};
       CKR(exchange_group(h, a1, 1, 4 * h->np2, false));
+      // a full DG-operator evaluation also leaves gradU?_slave of the MPI_MINE sides like the reference does (C3)
+      if (h->gradTracesFull) CKR(exchange_group(h, h->gs, 3, szG, false));
     } else {
       CKR(exchange_group(h, h->gs, 3, szG, false));
     }

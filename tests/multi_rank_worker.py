@@ -104,6 +104,16 @@ def main():
         ut = g.DGTimeDerivative_weakForm(0.0)
         scale = np.max(np.abs(ut_ref).reshape(-1, 5), axis=0)
         assert np.all(np.max(np.abs(ut - ut_ref).reshape(-1, 5), axis=0) <= 1e-12 * scale), "multi-rank Ut mismatch"
+        if eqn.get("parabolic"):
+            # side arrays after a full DG operator call, incl. what arrives from the neighbour rank: gradU?_slave on MPI_MINE sides
+            o = w.ranks[rank]
+            gsc = max(np.max(np.abs(o.array(n))) for n in ("gradUx", "gradUy", "gradUz"))
+            lo, hi = m.nBCSides, m.firstMPISide_YOUR - 1  # slave arrays of inner + MPI_MINE sides (0-based [lo, hi))
+            for name in ("gradUx_slave", "gradUy_slave", "gradUz_slave"):
+                assert np.max(np.abs(g.get_array(name)[lo:hi] - o.array(name)[lo:hi])) <= 1e-12 * gsc, name
+            hi_m = m.lastMPISide_MINE
+            for name in ("gradUx_master", "gradUy_master", "gradUz_master"):
+                assert np.max(np.abs(g.get_array(name)[:hi_m] - o.array(name)[:hi_m])) <= 1e-12 * gsc, name
         t = 0.0
         for _ in range(3):
             dt_o = w.calc_timestep()[0]
