@@ -94,6 +94,33 @@ class Equation:
         prim[..., 5] = prim[..., 4] * srho / self.R
         return prim
 
+    # ---- entropy variables (groundwork for the split form on Gauss nodes) ------------------------------
+    def prim_to_entropy(self, prim):
+        """PrimToEntropy (eos.f90:401-420): w = ((kappa-s)/(kappa-1) - rho|v|^2/(2p), rho v/p, -rho/p), s = ln p - kappa ln rho."""
+        k = self.kappa
+        s = np.log(prim[..., 4]) - k * np.log(prim[..., 0])
+        rho_p = prim[..., 0] / prim[..., 4]
+        w = np.empty(prim.shape[:-1] + (5,))
+        w[..., 0] = (k - s) / (k - 1.0) - rho_p * 0.5 * np.sum(prim[..., 1:4] ** 2, axis=-1)
+        w[..., 1:4] = rho_p[..., None] * prim[..., 1:4]
+        w[..., 4] = -rho_p
+        return w
+
+    def entropy_to_cons(self, w):
+        """EntropyToCons (eos.f90:499-531), the inverse map used after prolonging entropy variables to the faces
+        (ProlongToFaceEntropy, prolongtoface.t90:151-204)."""
+        k = self.kappa
+        km1 = k - 1.0
+        w2 = w * km1
+        ekin = 0.5 * np.sum(w2[..., 1:4] ** 2, axis=-1) / w2[..., 4]
+        s = k - w2[..., 0] + ekin
+        rhoe = km1 ** (1.0 / km1) * (-w2[..., 4]) ** (-k / km1) * np.exp(-s / km1)
+        cons = np.empty_like(w)
+        cons[..., 0] = -rhoe * w2[..., 4]
+        cons[..., 1:4] = rhoe[..., None] * w2[..., 1:4]
+        cons[..., 4] = rhoe * (1.0 - ekin)
+        return cons
+
     # ---- initial states ------------------------------------------------------------------------------------------------
     def tgv_state(self, x, mach=0.1, ini_const_dens=True):
         """ExactFuncTestcase of the Taylor-Green vortex (testcase.f90:176-219), U0 = rho0 = 1."""

@@ -161,3 +161,29 @@ def test_host_body_forces_of_a_uniform_state_are_pressure_times_wall_area():
     assert np.allclose(Fp[0], (0.0, -p0 * 4.0, 0.0), atol=1e-13) and np.allclose(Fp[1], (0.0, p0 * 4.0, 0.0), atol=1e-13)
     assert np.all(Fp[2] == 0.0) and np.all(Fv == 0.0) and np.all(Mv == 0.0)
     assert np.allclose(Mp[0], 0.0, atol=1e-13)  # symmetric wall about the moment origin
+
+
+def test_entropy_variables_round_trip_and_symmetrise_the_flux_jacobian():
+    """PrimToEntropy / EntropyToCons (eos.f90:401-531; groundwork for the Gauss split form): the maps are inverse to each other,
+    and dU/dw is symmetric positive definite (what makes w the entropy variables of s = ln p - kappa ln rho)."""
+    from flexi_b200.hostmesh.case import TGV_EQN
+    from flexi_b200.hostmesh.equation import Equation
+
+    eq = Equation(3, "gauss", parabolic=False, **TGV_EQN)
+    rng = np.random.default_rng(7)
+    prim = np.empty((50, 6))
+    prim[:, 0] = rng.uniform(0.5, 1.5, 50)
+    prim[:, 1:4] = rng.uniform(-0.5, 0.5, (50, 3))
+    prim[:, 4] = rng.uniform(0.5, 1.5, 50)
+    prim[:, 5] = prim[:, 4] / (prim[:, 0] * eq.R)
+    cons = np.empty((50, 5))
+    cons[:, 0] = prim[:, 0]
+    cons[:, 1:4] = prim[:, 0:1] * prim[:, 1:4]
+    cons[:, 4] = prim[:, 4] / (eq.kappa - 1.0) + 0.5 * prim[:, 0] * np.sum(prim[:, 1:4] ** 2, axis=1)
+    w = eq.prim_to_entropy(prim)
+    assert np.max(np.abs(eq.entropy_to_cons(w) - cons)) < 1e-13
+    # finite-difference Jacobian dU/dw at one state
+    w0, h = w[0], 1e-6
+    J = np.stack([(eq.entropy_to_cons(w0 + h * e) - eq.entropy_to_cons(w0 - h * e)) / (2 * h) for e in np.eye(5)], axis=1)
+    assert np.max(np.abs(J - J.T)) < 1e-7 * np.max(np.abs(J))
+    assert np.all(np.linalg.eigvalsh(0.5 * (J + J.T)) > 0)
