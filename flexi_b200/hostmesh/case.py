@@ -19,14 +19,15 @@ class HostRank:
         self.desc, self.keep = make_desc(self.mesh, self.basis, self.eqn, self.S2V2, nccl_id=nccl_id, device=device)
 
 
-def build_case(spec, N, node_type, eqn_kwargs=None, nranks=1, partition="linear", blocks=None, ranks=None):
-    """Build HostRank objects for the requested ranks (default: all)."""
+def build_case(spec, N, node_type, eqn_kwargs=None, nranks=1, partition="linear", blocks=None, ranks=None, with_ja_face=False):
+    """Build HostRank objects for the requested ranks (default: all).  with_ja_face also fills mesh.Ja_Face / Ja_slave (only the
+    split form on Gauss nodes reads them)."""
     eqn_kwargs = dict(eqn_kwargs or {})
     basis = B.DGBasis(N, node_type, split_dg=eqn_kwargs.get("split_dg", False))
     _, _, S2V2 = MP.build_mappings(N)
     out = []
     for r in (range(nranks) if ranks is None else ranks):
-        mesh = build_mesh(spec, N, node_type, rank=r, nranks=nranks, partition=partition, blocks=blocks)
+        mesh = build_mesh(spec, N, node_type, rank=r, nranks=nranks, partition=partition, blocks=blocks, with_ja_face=with_ja_face)
         eqn = Equation(N, node_type, **eqn_kwargs)
         out.append(HostRank(mesh, basis, eqn, S2V2))
     return out

@@ -51,6 +51,9 @@ typedef struct oracle {
   double *gradUx_master, *gradUy_master, *gradUz_master, *gradUx_slave, *gradUy_slave, *gradUz_slave;
   double *FluxX, *FluxY, *FluxZ; /* BR2 */
   double *MetricsAdv, *MetricsVisc; /* InitCalctimestep */
+  /* split form on Gauss nodes (PP_EntropyVars=1, src/CMakeLists.txt:64-71): entropy variables and face metrics */
+  double *V, *V_master, *V_slave; /* dg_vars.f90:59 */
+  double *Ja_Face, *Ja_slave;     /* (3,3,0:N,0:N,nSides), mesh_vars.f90:70-78; set by oracle_set_face_metrics */
   /* owned copies of descriptor arrays */
   void* owned[64];
   int n_owned;
@@ -681,6 +684,91 @@ static void surf_int(const oracle* o, int nv, const double* Flux_master, const d
     }
   }
   free(FluxTmp);
+}
+
+/* SurfInt with SPLIT_DG on Gauss nodes, dg/surfint.t90:21-239 (Mateo-Gabin et al., JCP 2023, eq. 5): besides the numerical flux
+ * every interior node of the line behind a face node receives the two-point fluxes between the line's nodes and the face state,
+ *   Ut(line node l) += (+-Flux - 1/2 (sum_k Leg(k) FluxB(k) - FluxB(l)) * NormalSign) * LegHat(l).
+ * S2V(:,l,p,q,flip,locSide) is rebuilt from S2V2: the line behind volume-face node (a,b) runs along the side's normal direction. */
+static void surf_int_split_gauss(const oracle* o, const double* Flux_master, const double* Flux_slave, double* Ut, int doMPISides) {
+  const int np = o->np, st = o->d.splitDGType;
+  static const int NormalDirs[6] = {3, 2, 1, 2, 1, 3};
+  static const double NormalSigns[6] = {-1., -1., 1., 1., -1., 1.};
+  int firstSideID, lastSideID;
+  if (doMPISides) {
+    firstSideID = o->firstMPISide_YOUR;
+    lastSideID = o->d.nSides;
+  } else {
+    firstSideID = 1;
+    lastSideID = o->lastMPISide_MINE;
+  }
+  double* FluxB = (double*)xcalloc((size_t)np * NVAR, sizeof(double));
+  for (int SideID = firstSideID; SideID <= lastSideID; ++SideID) {
+    const int s = SideID - 1;
+    for (int pass = 0; pass < 2; ++pass) { /* 0: master element, 1: slave element */
+      const int elem = S2E(pass, s);
+      if (elem <= 0) continue;
+      const int e = elem - 1;
+      const int locSide = S2E(2 + pass, s), flip = pass ? S2E(4, s) : 0;
+      const int idx = NormalDirs[locSide - 1]; /* 1 xi, 2 eta, 3 zeta */
+      const int minus = (locSide == 5 || locSide == 2 || locSide == 1);
+      const double* Leg = minus ? o->d.L_Minus : o->d.L_Plus;
+      const double* LegHat = minus ? o->d.L_HatMinus : o->d.L_HatPlus;
+      const double* Met = idx == 1 ? o->d.Metrics_fTilde : idx == 2 ? o->d.Metrics_gTilde : o->d.Metrics_hTilde;
+      const double* Uf = pass ? o->U_slave : o->U_master;
+      const double* Pf = pass ? o->UPrim_slave : o->UPrim_master;
+      const double* Ja = pass ? o->Ja_slave : o->Ja_Face;
+      const double* Fl = pass ? Flux_slave : Flux_master;
+      const double fsgn = pass ? -1. : 1.;
+      for (int q = 0; q < np; ++q)
+        for (int p = 0; p < np; ++p) {
+          const int a = S2V2(0, p, q, flip, locSide), b = S2V2(1, p, q, flip, locSide);
+          const double* JaRow = Ja + ((((size_t)s * np + q) * np + p) * 3) * 3; /* Ja(1:3 dd fastest? see below) */
+          double Jv[3];
+          for (int c = 0; c < 3; ++c) Jv[c] = JaRow[c * 3 + (idx - 1)]; /* Fortran Ja(dd,c,p,q,side): dd fastest */
+          double FluxB_sum[NVAR] = {0., 0., 0., 0., 0.};
+          for (int l = 0; l < np; ++l) {
+            const int i = idx == 1 ? l : a, j = idx == 1 ? a : (idx == 2 ? l : b), k = idx == 3 ? l : b;
+            split_volume_flux(st, &VOL(o->U, NVAR, 0, i, j, k, e), &VOL(o->UPrim, NPRIM, 0, i, j, k, e), &SID(Uf, NVAR, 0, p, q, s),
+                              &SID(Pf, NPRIM, 0, p, q, s), &VOL(Met, 3, 0, i, j, k, e), Jv, FluxB + (size_t)l * NVAR);
+            for (int v = 0; v < NVAR; ++v) FluxB_sum[v] = FluxB_sum[v] + FluxB[(size_t)l * NVAR + v] * Leg[l];
+          }
+          for (int l = 0; l < np; ++l) {
+            const int i = idx == 1 ? l : a, j = idx == 1 ? a : (idx == 2 ? l : b), k = idx == 3 ? l : b;
+            for (int v = 0; v < NVAR; ++v)
+              VOL(Ut, NVAR, v, i, j, k, e) = VOL(Ut, NVAR, v, i, j, k, e) +
+                                           (fsgn * SID(Fl, NVAR, v, p, q, s) - 1. / 2. * (FluxB_sum[v] - FluxB[(size_t)l * NVAR + v]) * NormalSigns[locSide - 1]) * LegHat[l];
+          }
+        }
+    }
+  }
+  free(FluxB);
+}
+
+/* eos.f90:401-420 PrimToEntropy */
+static void prim_to_entropy(const oracle* o, double* entropy, const double* prim) {
+  const double kappa = o->d.kappa;
+  const double s = log(prim[4]) - kappa * log(prim[0]);
+  const double rho_p = prim[0] / prim[4];
+  entropy[0] = (kappa - s) * o->sKappaM1 - rho_p * 0.5 * (prim[1] * prim[1] + prim[2] * prim[2] + prim[3] * prim[3]);
+  entropy[1] = rho_p * prim[1];
+  entropy[2] = rho_p * prim[2];
+  entropy[3] = rho_p * prim[3];
+  entropy[4] = -rho_p;
+}
+/* eos.f90:499-531 EntropyToCons */
+static void entropy_to_cons(const oracle* o, const double* entropy, double* cons) {
+  const double kappa = o->d.kappa, kappaM1 = o->kappaM1;
+  double e2[NVAR];
+  for (int v = 0; v < NVAR; ++v) e2[v] = entropy[v] * kappaM1;
+  const double ekin = 0.5 * (e2[1] * e2[1] + e2[2] * e2[2] + e2[3] * e2[3]) / e2[4];
+  const double s = kappa - e2[0] + ekin;
+  const double rhoe = pow(kappaM1, o->sKappaM1) * pow(-e2[4], -(kappa / kappaM1)) * exp(-s * o->sKappaM1);
+  cons[0] = -rhoe * e2[4];
+  cons[1] = rhoe * e2[1];
+  cons[2] = rhoe * e2[2];
+  cons[3] = rhoe * e2[3];
+  cons[4] = rhoe * (1. - ekin);
 }
 
 /* ------------------------------------------------------------------------------------------------------------------ */
@@ -1347,6 +1435,31 @@ static void lifting_br2_world(oracle_world* w, double t) {
   exchange(w, OFF(gradUz_slave), szg, 2);
 }
 
+/* PP_EntropyVars = 1 <=> SPLIT_DG on Gauss nodes (src/CMakeLists.txt:64-71) */
+static int entropy_vars(const oracle* o) { return o->d.splitDG && o->d.nodeType == FLEXI_NODETYPE_GAUSS; }
+
+/* eos.f90:423-441 ConsToPrimToEntropy_Volume (UPrim is already there) */
+static void cons_to_entropy_volume(oracle* o) {
+  const size_t n = (size_t)o->d.nElems * o->np * o->np * o->np;
+  for (size_t i = 0; i < n; ++i) prim_to_entropy(o, o->V + i * NVAR, o->UPrim + i * NPRIM);
+}
+
+/* prolongtoface.t90:151-204 ProlongToFaceEntropy: prolong the entropy variables, convert back to conservative on the faces */
+static void prolong_to_face_entropy(oracle* o, int doMPISides) {
+  const int np = o->np;
+  const size_t fs = (size_t)np * np;
+  prolong_to_face(o, NVAR, o->V, o->V_master, o->V_slave, doMPISides);
+  const int firstSideID = doMPISides ? o->firstMPISide_YOUR : 1;
+  const int lastSideID = doMPISides ? o->d.nSides : o->lastMPISide_MINE;
+  for (int SideID = firstSideID; SideID <= lastSideID; ++SideID) {
+    const int s = SideID - 1;
+    if (S2E(0, s) > 0)
+      for (size_t i = 0; i < fs; ++i) entropy_to_cons(o, o->V_master + ((size_t)s * fs + i) * NVAR, o->U_master + ((size_t)s * fs + i) * NVAR);
+    if (S2E(1, s) > 0)
+      for (size_t i = 0; i < fs; ++i) entropy_to_cons(o, o->V_slave + ((size_t)s * fs + i) * NVAR, o->U_slave + ((size_t)s * fs + i) * NVAR);
+  }
+}
+
 /* dg.f90:221-678 DGTimeDerivative_weakForm */
 void oracle_world_dg_time_derivative(oracle_world* w, double t) {
   const int np = w->r[0]->np;
@@ -1354,12 +1467,20 @@ void oracle_world_dg_time_derivative(oracle_world* w, double t) {
   FOR_RANKS {
     oracle* o = w->r[r];
     cons_to_prim_volume(o);                                  /* 2. */
-    prolong_to_face(o, NVAR, o->U, o->U_master, o->U_slave, 1); /* 3. MPI YOUR sides first */
+    if (entropy_vars(o)) {
+      cons_to_entropy_volume(o);                             /* ConsToPrimToEntropy, dg.f90:333-337 */
+      prolong_to_face_entropy(o, 1);                         /* dg.f90:371-375 */
+    } else {
+      prolong_to_face(o, NVAR, o->U, o->U_master, o->U_slave, 1); /* 3. MPI YOUR sides first */
+    }
   }
   exchange(w, OFF(U_slave), szs, 2);
   FOR_RANKS {
     oracle* o = w->r[r];
-    prolong_to_face(o, NVAR, o->U, o->U_master, o->U_slave, 0);
+    if (entropy_vars(o))
+      prolong_to_face_entropy(o, 0);                         /* dg.f90:409-413 */
+    else
+      prolong_to_face(o, NVAR, o->U, o->U_master, o->U_slave, 0);
     get_primitive_state_surface(o); /* 4. */
   }
   if (w->r[0]->d.parabolic) { /* 6. */
@@ -1380,8 +1501,13 @@ void oracle_world_dg_time_derivative(oracle_world* w, double t) {
   FOR_RANKS {
     oracle* o = w->r[r];
     fill_flux(o, t, 0);
-    surf_int(o, NVAR, o->Flux_master, o->Flux_slave, o->Ut, 0, o->d.L_HatMinus, o->d.L_HatPlus, -1.);
-    surf_int(o, NVAR, o->Flux_master, o->Flux_slave, o->Ut, 1, o->d.L_HatMinus, o->d.L_HatPlus, -1.);
+    if (entropy_vars(o)) { /* SPLIT_DG on Gauss nodes: surface integral with the two-point correction, surfint.t90:90-137,190-209 */
+      surf_int_split_gauss(o, o->Flux_master, o->Flux_slave, o->Ut, 0);
+      surf_int_split_gauss(o, o->Flux_master, o->Flux_slave, o->Ut, 1);
+    } else {
+      surf_int(o, NVAR, o->Flux_master, o->Flux_slave, o->Ut, 0, o->d.L_HatMinus, o->d.L_HatPlus, -1.);
+      surf_int(o, NVAR, o->Flux_master, o->Flux_slave, o->Ut, 1, o->d.L_HatMinus, o->d.L_HatPlus, -1.);
+    }
     finish_ut(o, t); /* 12.-14. */
   }
 }
@@ -1582,8 +1708,25 @@ oracle* oracle_create(const flexi_gpu_desc* d) {
     o->FluxY = (double*)xcalloc(nsid * o->nvl, 8);
     o->FluxZ = (double*)xcalloc(nsid * o->nvl, 8);
   }
+  if (d->splitDG && d->nodeType == FLEXI_NODETYPE_GAUSS) { /* PP_EntropyVars = 1, dg.f90:80-87 */
+    o->V = (double*)xcalloc(nvol * NVAR, 8);
+    o->V_master = (double*)xcalloc(nsid * NVAR, 8);
+    o->V_slave = (double*)xcalloc(nsid * NVAR, 8);
+  }
   init_calc_timestep(o);
   return o;
+}
+
+/* Ja_Face / Ja_slave (3,3,0:N,0:N,nSides) of MOD_Mesh_Vars (metrics.f90:681-705): only the split form on Gauss nodes reads them, and
+ * the C ABI descriptor of the GPU library does not carry them yet, so the oracle takes them through this extra entry. */
+void oracle_set_face_metrics(oracle* o, const double* Ja_Face, const double* Ja_slave) {
+  const size_t n = (size_t)o->d.nSides * o->np * o->np * 9;
+  free(o->Ja_Face);
+  free(o->Ja_slave);
+  o->Ja_Face = (double*)xcalloc(n, 8);
+  o->Ja_slave = (double*)xcalloc(n, 8);
+  memcpy(o->Ja_Face, Ja_Face, n * 8);
+  memcpy(o->Ja_slave, Ja_slave, n * 8);
 }
 
 void oracle_destroy(oracle* o) {
@@ -1591,7 +1734,8 @@ void oracle_destroy(oracle* o) {
   for (int i = 0; i < o->n_owned; ++i) free(o->owned[i]);
   double* st[] = {o->U, o->Ut, o->Ut_tmp, o->UPrim, o->U_master, o->U_slave, o->UPrim_master, o->UPrim_slave, o->Flux_master,
                   o->Flux_slave, o->gradUx, o->gradUy, o->gradUz, o->gradUx_master, o->gradUy_master, o->gradUz_master,
-                  o->gradUx_slave, o->gradUy_slave, o->gradUz_slave, o->FluxX, o->FluxY, o->FluxZ, o->MetricsAdv, o->MetricsVisc};
+                  o->gradUx_slave, o->gradUy_slave, o->gradUz_slave, o->FluxX, o->FluxY, o->FluxZ, o->MetricsAdv, o->MetricsVisc,
+                  o->V, o->V_master, o->V_slave, o->Ja_Face, o->Ja_slave};
   for (size_t i = 0; i < sizeof st / sizeof st[0]; ++i) free(st[i]);
   free(o);
 }

@@ -45,6 +45,7 @@ def _load(fast=False):
     lib.oracle_riemann_point.argtypes = [P, C.c_int, PD, PD, PD, PD, PD, PD]
     lib.oracle_split_volume_flux.argtypes = [P, C.c_int, PD, PD, PD, PD, PD]
     lib.oracle_eval_flux3d.argtypes = [P, PD, PD, PD, PD]
+    lib.oracle_set_face_metrics.argtypes = [P, PD, PD]
     lib.oracle_desc_bytes.restype = C.c_int
     _LIBS[name] = lib
     return lib
@@ -67,6 +68,13 @@ class OracleRank:
         if not self.h:
             raise RuntimeError("oracle_create failed")
         self.np = desc.N + 1
+
+    def set_face_metrics(self, Ja_Face, Ja_slave):
+        """Ja_Face / Ja_slave of the host mesh ([side, q, p, c, dd] = Fortran (dd,c,p,q,side)) for the split form on Gauss nodes."""
+        a = np.ascontiguousarray(Ja_Face, dtype=np.float64)
+        b = np.ascontiguousarray(Ja_slave, dtype=np.float64)
+        assert a.shape == b.shape == (self.desc.nSides, self.np, self.np, 3, 3), a.shape
+        self.lib.oracle_set_face_metrics(self.h, _pd(a), _pd(b))
 
     def array(self, name):
         """numpy VIEW of a module array (Fortran memory; shape is the reversed Fortran shape)."""
