@@ -10,8 +10,12 @@ from oracle import oracle as O
 
 
 def world(spec, N, node, eqn, nranks=1, **kw):
-    ranks = build_case(spec, N, node, eqn, nranks=nranks, **kw)
+    gauss_split = bool(eqn.get("split_dg")) and node == B.NODE_GAUSS  # PP_EntropyVars = 1: needs Ja_Face / Ja_slave
+    ranks = build_case(spec, N, node, eqn, nranks=nranks, with_ja_face=gauss_split, **kw)
     w = O.OracleWorld([(r.desc, r.keep) for r in ranks])
+    if gauss_split:
+        for r, o in zip(ranks, w.ranks):
+            o.set_face_metrics(r.mesh.Ja_Face, r.mesh.Ja_slave)
     return ranks, w
 
 
@@ -84,6 +88,9 @@ CONFIGS = [
     (B.NODE_GAUSS_LOBATTO, dict(parabolic=True, split_dg=True, split_dg_type="pi", riemann="lf", mu0=1e-2)),
     (B.NODE_GAUSS_LOBATTO, dict(parabolic=True, split_dg=True, split_dg_type="kg", riemann="roeentropyfix", mu0=1e-2)),
     (B.NODE_GAUSS, dict(parabolic=False, riemann="roeentropyfix")),
+    # split form on Gauss nodes (entropy-projected traces + two-point surface correction; oracle only so far)
+    (B.NODE_GAUSS, dict(parabolic=True, split_dg=True, split_dg_type="pi", riemann="lf", mu0=1e-2)),
+    (B.NODE_GAUSS, dict(parabolic=False, split_dg=True, split_dg_type="kg", riemann="roeentropyfix")),
 ]
 
 
