@@ -103,6 +103,8 @@ struct flexi_gpu_handle {
   int nElemsInner = 0, nElemsBnd = 0;
   bool keepGrad = false;
   bool bcTablesMissing = false;
+  bool entropy = false;             // split form on Gauss nodes: entropy-projected traces + two-point surface correction
+  double *JaF = nullptr, *JaS = nullptr;  // Ja_Face / Ja_slave [s][9][NP2]
   bool vt = false;             // viscous-trace protocol between k_volume_gl2 and k_flux (kernels.cuh: VolArgs::fvm)
   bool gradTracesFull = true;  // gradU?_master/slave hold the traces of every side (else only of the BC sides)
   double *fvm = nullptr, *fvs = nullptr;
@@ -279,6 +281,8 @@ int launch_prolong_U(H* h) {
   a.nv = 5;
   a.firstSide = 0;
   a.lastSide = h->nSides - 1;
+  a.entropy = h->entropy ? 1 : 0;
+  a.q = h->q;
   Timer tm(h, KC_PROLONG, h->sc);
   CK(h->ops->prolong(h->gl, a, h->nElems, h->sc));
   return 0;
@@ -318,6 +322,25 @@ int launch_volume(H* h, const int32_t* list, int n, bool fullGrad) {
   }
   Timer tm(h, KC_VOLUME, h->sc);
   CK(h->ops->volume(h->gl, h->split, h->q.splitType, h->para, h->nvl, a, n, h->sc));
+  return 0;
+}
+
+// split form on Gauss nodes: two-point surface correction (surfint.t90:90-137,190-209) added to the raw volume integral
+int launch_surfcorr(H* h, const int32_t* list, int n) {
+  if (!h->entropy || n <= 0) return 0;
+  SurfCorrArgs a{};
+  a.m = h->m;
+  a.q = h->q;
+  a.elems = list;
+  a.nList = n;
+  a.U = h->U;
+  a.U_master = h->Um;
+  a.U_slave = h->Us;
+  a.JaF = h->JaF;
+  a.JaS = h->JaS;
+  a.Ut = h->UtVol;
+  Timer tm(h, KC_VOLUME, h->sc);
+  CK(h->ops->surfcorr(a, n, h->sc));
   return 0;
 }
 
@@ -365,6 +388,8 @@ int launch_update(H* h, const int32_t* list, int n, int mode, double rkA, double
   a.mode = mode;
   a.rkA = rkA;
   a.b_dt = b_dt;
+  a.entropy = h->entropy ? 1 : 0;
+  a.q = h->q;
   if (n <= 0) return 0;
   Timer tm(h, KC_UPDATE, h->sc);
   CK(h->ops->update(h->gl, a, n, h->sc));
@@ -393,6 +418,7 @@ int launch_bc(H* h, bool pre, double t) {
 
 int rhs(H* h, double t, int mode, double rkA, double b_dt) {
   if (h->bcTablesMissing) return fail(FLEXI_GPU_ERR_ARG, "BC sides without BC / BoundaryType tables");
+  if (h->entropy && !h->JaF) return fail(FLEXI_GPU_ERR_ARG, "split form on Gauss nodes: call flexi_gpu_set_face_metrics (Ja_Face, Ja_slave) first");
   h->lastT = t;
   if (!h->tracesValid) CKR(refresh_traces(h));
   const bool multi = h->nProcs > 1;
@@ -402,6 +428,7 @@ int rhs(H* h, double t, int mode, double rkA, double b_dt) {
   if (h->para) CKR(launch_bc(h, true, t));
   if (!multi) {
     CKR(launch_volume(h, nullptr, h->nElems, fullGrad));
+    CKR(launch_surfcorr(h, nullptr, h->nElems));
     CKR(launch_bc(h, false, t));
     CKR(launch_flux(h, h->firstInner, h->nInnerSides));
     CKR(launch_update(h, nullptr, h->nElems, mode, rkA, b_dt, t));
@@ -410,6 +437,8 @@ int rhs(H* h, double t, int mode, double rkA, double b_dt) {
   CKR(launch_volume(h, h->elemsInner, h->nElemsInner, fullGrad));
   CKR(finish_exchange(h, X_TRACE));
   CKR(launch_volume(h, h->elemsBnd, h->nElemsBnd, fullGrad));
+  CKR(launch_surfcorr(h, h->elemsInner, h->nElemsInner));
+  CKR(launch_surfcorr(h, h->elemsBnd, h->nElemsBnd));
   if (h->para) CKR(start_exchange(h, X_GRAD));
   CKR(launch_bc(h, false, t));
   CKR(launch_flux(h, h->firstInner, h->nInnerSides));
@@ -471,7 +500,8 @@ static int init_impl(const flexi_gpu_desc* d, H* h) {
   if (d->N < 1 || d->N > 9) return fail(FLEXI_GPU_ERR_ARG, "N=%d outside 1..9", d->N);
   if (d->nodeType != FLEXI_NODETYPE_GAUSS && d->nodeType != FLEXI_NODETYPE_GAUSS_LOBATTO) return fail(FLEXI_GPU_ERR_ARG, "bad nodeType %d", d->nodeType);
   if (d->doWeakLifting || d->doConservativeLifting) return fail(FLEXI_GPU_ERR_UNSUPPORTED, "only the strong, non-conservative lifting (the reference default, lifting.f90:72-76) is implemented");
-  if (d->splitDG && d->nodeType != FLEXI_NODETYPE_GAUSS_LOBATTO) return fail(FLEXI_GPU_ERR_UNSUPPORTED, "split form on Gauss nodes is not implemented");
+  // split form on Gauss nodes (PP_EntropyVars = 1): implemented, but it needs Ja_Face / Ja_slave, which the descriptor does not
+  // carry: flexi_gpu_set_face_metrics must follow flexi_gpu_init
   if (d->splitDG && !(d->splitDGType == FLEXI_SPLITDG_SD || d->splitDGType == FLEXI_SPLITDG_DU || d->splitDGType == FLEXI_SPLITDG_KG || d->splitDGType == FLEXI_SPLITDG_PI))
     return fail(FLEXI_GPU_ERR_UNSUPPORTED, "SplitDG formulation %d is not implemented", d->splitDGType);
   if (d->splitDG && d->riemann == FLEXI_RIEMANN_HLLC) return fail(FLEXI_GPU_ERR_ARG, "HLLC is not selectable with SPLIT_DG (riemann.f90:206-227)");
@@ -491,6 +521,7 @@ static int init_impl(const flexi_gpu_desc* d, H* h) {
   h->np3 = h->np2 * h->np;
   h->gl = d->nodeType == FLEXI_NODETYPE_GAUSS_LOBATTO;
   h->split = d->splitDG != 0;
+  h->entropy = h->split && !h->gl;
   h->para = d->parabolic != 0;
   h->nvl = h->para ? d->nVarLifting : 5;
   h->lifting = d->lifting;
@@ -1125,6 +1156,19 @@ int flexi_gpu_calc_body_forces(flexi_gpu_handle* h, const double* wGPSurf, const
       Mv[b * 3 + c] += part[(size_t)s * 12 + 9 + c];
     }
   }
+  return 0;
+}
+
+int flexi_gpu_set_face_metrics(flexi_gpu_handle* h, const double* Ja_Face, const double* Ja_slave) {
+  ENTER(h);
+  if (!Ja_Face || !Ja_slave) return fail(FLEXI_GPU_ERR_ARG, "null argument");
+  const size_t n = (size_t)h->nSides * 9 * h->np2;
+  if (!h->JaF) {
+    CKR(dalloc(h, &h->JaF, n));
+    CKR(dalloc(h, &h->JaS, n));
+  }
+  CKR(upload_aos(h, Ja_Face, h->JaF, 9, h->np2, h->nSides));  // Fortran (dd,c,p,q,side): plane dd + 3*c
+  CKR(upload_aos(h, Ja_slave, h->JaS, 9, h->np2, h->nSides));
   return 0;
 }
 

@@ -67,6 +67,8 @@ struct UpdArgs {
   double rkA;  // RKA(iStage)
   double b_dt; // RKb(iStage)*dt
   // CalcSource, exactfunc.f90:727-815 (case 4), evaluated at the stage time t
+  int entropy;  // traces of the new state through entropy variables (ProlongToFaceEntropy); needs q
+  Eqn q;
   int doSource;
   const double* xGP;  // Elem_xGP as [e][3][NP3]
   double t, srcOmega, srcA, srcTmp[6];
@@ -79,6 +81,8 @@ struct ProArgs {
   double* slave;
   int nv;
   int firstSide, lastSide;  // inclusive 0-based side range that is written
+  int entropy;  // ProlongToFaceEntropy (prolongtoface.t90:151-204): V holds U (nv = 5), entropy variables are prolonged
+  Eqn q;
 };
 
 // ---------------------------------------------------------------------------------------------------------------------------
@@ -99,6 +103,13 @@ __global__ void __launch_bounds__(Dim<NP>::NP3) k_prolong(ProArgs A) {
   const int e = blockIdx.x;
   load_basis<NP>(sB, A.m.basis, tid, D::NP3);
   for (int v = 0; v < A.nv; ++v) sV[v * D::NP3 + tid] = A.V[((size_t)e * A.nv + v) * D::NP3 + tid];
+  if (A.entropy) {  // own node: cons -> prim -> entropy variables, in place
+    double Uc[5], P[6], w[5];
+    for (int v = 0; v < 5; ++v) Uc[v] = sV[v * D::NP3 + tid];
+    cons_to_prim(A.q, Uc, P);
+    prim_to_entropy(A.q, P, w);
+    for (int v = 0; v < 5; ++v) sV[v * D::NP3 + tid] = w[v];
+  }
   __syncthreads();
   for (int t = tid; t < 6 * D::NP2; t += D::NP3) {
     const int ls = t / D::NP2 + 1, pq = t % D::NP2;
@@ -107,8 +118,15 @@ __global__ void __launch_bounds__(Dim<NP>::NP3) k_prolong(ProArgs A) {
     const int ab = A.m.s2v2[(sr.flip * 6 + ls - 1) * D::NP2 + pq];
     const int a = ab % NP, b = ab / NP;
     double* dst = (sr.flip == 0) ? A.master : A.slave;
-    for (int v = 0; v < A.nv; ++v)
-      dst[((size_t)sr.side * A.nv + v) * D::NP2 + pq] = face_eval<NP, GL>(sV + v * D::NP3, sB, ls, a, b);
+    if (A.entropy) {
+      double w[5], Uc[5];
+      for (int v = 0; v < 5; ++v) w[v] = face_eval<NP, GL>(sV + v * D::NP3, sB, ls, a, b);
+      entropy_to_cons(A.q, w, Uc);
+      for (int v = 0; v < 5; ++v) dst[((size_t)sr.side * 5 + v) * D::NP2 + pq] = Uc[v];
+    } else {
+      for (int v = 0; v < A.nv; ++v)
+        dst[((size_t)sr.side * A.nv + v) * D::NP2 + pq] = face_eval<NP, GL>(sV + v * D::NP3, sB, ls, a, b);
+    }
   }
 }
 
@@ -666,7 +684,8 @@ __global__ void __launch_bounds__(128) k_flux_bc(BCArgs A) {
 // state, so that the traces leave the SM as whole 512-byte planes.  (A barrier-free Gauss-Lobatto variant in which the owner of a
 // boundary node wrote its trace entries directly was measured 19 % slower at 48^3, N=7: 3.41 vs 2.87 ms; the scattered 8-byte
 // stores cost more than the staging.)
-template <int NP, bool GL>
+// ENT: the traces of the new state are prolonged in entropy variables (split form on Gauss nodes, ProlongToFaceEntropy)
+template <int NP, bool GL, bool ENT = false>
 __global__ void __launch_bounds__(Dim<NP>::NP3) k_update(UpdArgs A) {
   using D = Dim<NP>;
   extern __shared__ double sm[];
@@ -745,6 +764,15 @@ __global__ void __launch_bounds__(Dim<NP>::NP3) k_update(UpdArgs A) {
     A.U[g] = u;
     sU[v * D::NP3 + n] = u;
   }
+  if (ENT) {  // own node: cons -> prim -> entropy variables, in place (only this thread touches its node before the barrier)
+    double Uc[5], P[6], w[5];
+#pragma unroll
+    for (int v = 0; v < 5; ++v) Uc[v] = sU[v * D::NP3 + n];
+    cons_to_prim(A.q, Uc, P);
+    prim_to_entropy(A.q, P, w);
+#pragma unroll
+    for (int v = 0; v < 5; ++v) sU[v * D::NP3 + n] = w[v];
+  }
   __syncthreads();
   for (int t = tid; t < 6 * D::NP2; t += D::NP3) {
     const int ls = t / D::NP2 + 1, pq = t % D::NP2;
@@ -752,8 +780,101 @@ __global__ void __launch_bounds__(Dim<NP>::NP3) k_update(UpdArgs A) {
     const int ab = A.m.s2v2[(sr.flip * 6 + ls - 1) * D::NP2 + pq];
     const int a = ab % NP, b = ab / NP;
     double* dst = (sr.flip == 0) ? A.U_master : A.U_slave;
+    if (ENT) {
+      double w[5], Uc[5];
 #pragma unroll
-    for (int v = 0; v < 5; ++v) dst[((size_t)sr.side * 5 + v) * D::NP2 + pq] = face_eval<NP, GL>(sU + v * D::NP3, sB, ls, a, b);
+      for (int v = 0; v < 5; ++v) w[v] = face_eval<NP, GL>(sU + v * D::NP3, sB, ls, a, b);
+      entropy_to_cons(A.q, w, Uc);
+#pragma unroll
+      for (int v = 0; v < 5; ++v) dst[((size_t)sr.side * 5 + v) * D::NP2 + pq] = Uc[v];
+    } else {
+#pragma unroll
+      for (int v = 0; v < 5; ++v) dst[((size_t)sr.side * 5 + v) * D::NP2 + pq] = face_eval<NP, GL>(sU + v * D::NP3, sB, ls, a, b);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// k_surfcorr: the two-point surface correction of the split form on Gauss nodes, dg/surfint.t90:90-137 (master) and :190-209
+// (slave), as an element gather added to the raw volume integral (k_update then adds the numerical flux like on any Gauss
+// element):  Ut(l) -= 1/2 (sum_k Leg(k) FluxB(k) - FluxB(l)) * NormalSign * LegHat(l)  for every line behind a face node, with
+// FluxB(k) the two-point volume flux between line node k and the face state (metrics of the node and Ja_Face / Ja_slave).
+struct SurfCorrArgs {
+  Mesh m;
+  Eqn q;
+  const int32_t* elems;
+  int nList;
+  const double* U;         // [e][5][NP3]
+  const double* U_master;  // [s][5][NP2]
+  const double* U_slave;
+  const double* JaF;       // Ja_Face  [s][9][NP2], plane dd + 3*c = Ja(dd,c)
+  const double* JaS;       // Ja_slave
+  double* Ut;              // raw volume integral, updated in place
+};
+
+template <int NP>
+__global__ void __launch_bounds__(Dim<NP>::NP3) k_surfcorr(SurfCorrArgs A) {
+  using D = Dim<NP>;
+  extern __shared__ double sm[];
+  double* sB = sm;
+  double* sFB = sm + D::NBASIS;  // Leg(l)*FluxB(l) of the current local side, [5][NP3]
+  const int tid = threadIdx.x, n = tid;
+  const int e = A.elems ? A.elems[blockIdx.x] : blockIdx.x;
+  const int i = tid % NP, j = (tid / NP) % NP, k = tid / D::NP2;
+  const Eqn& q = A.q;
+  load_basis<NP>(sB, A.m.basis, tid, D::NP3);
+  double Uc[5], P[6], M[9];
+#pragma unroll
+  for (int v = 0; v < 5; ++v) Uc[v] = A.U[((size_t)e * 5 + v) * D::NP3 + n];
+  cons_to_prim(q, Uc, P);
+#pragma unroll
+  for (int c = 0; c < 9; ++c) M[c] = A.m.Met[((size_t)e * 9 + c) * D::NP3 + n];
+  const Node nd{P[DENS], P[VEL1], P[VEL2], P[VEL3], P[PRES], Uc[ENER]};
+  double corr[5] = {0., 0., 0., 0., 0.};
+  __syncthreads();
+  for (int ls = 1; ls <= 6; ++ls) {
+    // line through this node along the side's normal direction; (a,b) = volume-face coordinates, l = own position on the line
+    const int idx = (ls == XI_MINUS || ls == XI_PLUS) ? 0 : (ls == ETA_MINUS || ls == ETA_PLUS) ? 1 : 2;
+    const int ab = idx == 0 ? j + NP * k : idx == 1 ? i + NP * k : i + NP * j;
+    const int l = idx == 0 ? i : idx == 1 ? j : k;
+    const int stride = idx == 0 ? 1 : idx == 1 ? NP : D::NP2;
+    const bool minus = is_minus_side(ls);
+    const double* Leg = sB + (minus ? D::O_LM : D::O_LP);
+    const double* LegHat = sB + (minus ? D::O_LHM : D::O_LHP);
+    const double nsign = minus ? -1. : 1.;  // NormalSigns (mesh_vars.f90:105-111)
+    const SideRef sr = A.m.e2s[e * 6 + ls - 1];
+    const int pq = A.m.v2s[(sr.flip * 6 + ls - 1) * D::NP2 + ab];
+    const double* Uf = ((sr.flip == 0) ? A.U_master : A.U_slave) + (size_t)sr.side * 5 * D::NP2 + pq;
+    const double* Ja = ((sr.flip == 0) ? A.JaF : A.JaS) + (size_t)sr.side * 9 * D::NP2 + pq;
+    double Ufc[5], Pf[6];
+#pragma unroll
+    for (int v = 0; v < 5; ++v) Ufc[v] = Uf[v * D::NP2];
+    cons_to_prim(q, Ufc, Pf);  // UPrim_master / UPrim_slave, equation.f90:189-216
+    const Node nf{Pf[DENS], Pf[VEL1], Pf[VEL2], Pf[VEL3], Pf[PRES], Ufc[ENER]};
+    const double Jv[3] = {Ja[(idx + 0) * D::NP2], Ja[(idx + 3) * D::NP2], Ja[(idx + 6) * D::NP2]};
+    double FB[5];
+    switch (q.splitType) {  // SplitDGVolume_pointer(U, UPrim, U_face, UPrim_face, Metrics, Ja_face), surfint.t90:118-121
+      case FLEXI_SPLITDG_SD: split_volume_flux<FLEXI_SPLITDG_SD>(nd, nf, M + 3 * idx, Jv, FB); break;
+      case FLEXI_SPLITDG_DU: split_volume_flux<FLEXI_SPLITDG_DU>(nd, nf, M + 3 * idx, Jv, FB); break;
+      case FLEXI_SPLITDG_KG: split_volume_flux<FLEXI_SPLITDG_KG>(nd, nf, M + 3 * idx, Jv, FB); break;
+      default: split_volume_flux<FLEXI_SPLITDG_PI>(nd, nf, M + 3 * idx, Jv, FB);
+    }
+#pragma unroll
+    for (int v = 0; v < 5; ++v) sFB[v * D::NP3 + n] = FB[v] * Leg[l];
+    __syncthreads();
+    const int base = n - l * stride;
+#pragma unroll
+    for (int v = 0; v < 5; ++v) {
+      double sum = 0.;
+      for (int kk = 0; kk < NP; ++kk) sum = sum + sFB[v * D::NP3 + base + kk * stride];
+      corr[v] = corr[v] + (-1. / 2. * (sum - FB[v]) * nsign) * LegHat[l];
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int v = 0; v < 5; ++v) {
+    const size_t g = ((size_t)e * 5 + v) * D::NP3 + n;
+    A.Ut[g] = A.Ut[g] + corr[v];
   }
 }
 

@@ -29,6 +29,20 @@ cudaError_t volume_setup() {
   if (e == cudaSuccess && PARA) e = volume_setup1<PARA, NVL, 2>();
   return e;
 }
+// split form on Gauss nodes: the generic element kernel with the two-point volume fluxes (DVolSurf = (D - 1/2 M^-1 V^T B V)^T)
+template <bool PARA, int NVL, int LIFT>
+cudaError_t volume_gs_setup1() {
+  return cudaFuncSetAttribute(k_volume<NP, false, true, PARA, NVL, LIFT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)VolSmem<NP, false, true, PARA, LIFT>::BYTES);
+}
+template <bool PARA, int NVL>
+cudaError_t volume_gs_launch(int lift, const VolArgs& a, int nBlocks, cudaStream_t s) {
+  if (PARA && lift == 2)
+    k_volume<NP, false, true, PARA, NVL, 2><<<nBlocks, D::NP3, VolSmem<NP, false, true, PARA, 2>::BYTES, s>>>(a);
+  else
+    k_volume<NP, false, true, PARA, NVL, 1><<<nBlocks, D::NP3, VolSmem<NP, false, true, PARA, 1>::BYTES, s>>>(a);
+  return cudaGetLastError();
+}
 template <bool PARA, int NVL>
 cudaError_t volume_launch(int lift, const VolArgs& a, int nBlocks, cudaStream_t s) {
   if (PARA && lift == 2)
@@ -132,6 +146,11 @@ cudaError_t setup() {
   if ((e = volume_setup<false, 5>()) != cudaSuccess) return e;
   if ((e = volume_setup<true, 5>()) != cudaSuccess) return e;
   if ((e = volume_setup<true, 4>()) != cudaSuccess) return e;
+  if ((e = volume_gs_setup1<false, 5, 1>()) != cudaSuccess) return e;
+  if ((e = volume_gs_setup1<true, 5, 1>()) != cudaSuccess) return e;
+  if ((e = volume_gs_setup1<true, 5, 2>()) != cudaSuccess) return e;
+  if ((e = volume_gs_setup1<true, 4, 1>()) != cudaSuccess) return e;
+  if ((e = volume_gs_setup1<true, 4, 2>()) != cudaSuccess) return e;
   if ((e = volume_gl_setup<false, 0, false, 5>()) != cudaSuccess) return e;
   if ((e = volume_gl_setup<false, 0, true, 5>()) != cudaSuccess) return e;
   if ((e = volume_gl_setup<false, 0, true, 4>()) != cudaSuccess) return e;
@@ -153,6 +172,8 @@ cudaError_t setup() {
   }
   if ((e = cudaFuncSetAttribute(k_update<NP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(k_update<NP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_update<NP, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_surfcorr<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (D::NBASIS + 5 * D::NP3)))) != cudaSuccess) return e;
   const int pro = (int)(sizeof(double) * (D::NBASIS + 6 * D::NP3));
   if ((e = cudaFuncSetAttribute(k_prolong<NP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pro)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(k_prolong<NP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pro)) != cudaSuccess) return e;
@@ -171,8 +192,11 @@ cudaError_t prolong(bool gl, const ProArgs& a, int nElems, cudaStream_t s) {
 
 cudaError_t volume(bool gl, bool split, int stype, bool para, int nvl, const VolArgs& a, int nBlocks, cudaStream_t s) {
   if (nBlocks <= 0) return cudaSuccess;
-  if (split && !gl) return cudaErrorNotSupported;
   const int lift = a.q.lifting;
+  if (split && !gl) {
+    if (!para) return volume_gs_launch<false, 5>(lift, a, nBlocks, s);
+    return nvl == 5 ? volume_gs_launch<true, 5>(lift, a, nBlocks, s) : volume_gs_launch<true, 4>(lift, a, nBlocks, s);
+  }
   if (!gl) {
     if (!para) return volume_launch<false, 5>(lift, a, nBlocks, s);
     return nvl == 5 ? volume_launch<true, 5>(lift, a, nBlocks, s) : volume_launch<true, 4>(lift, a, nBlocks, s);
@@ -234,8 +258,16 @@ cudaError_t update(bool gl, const UpdArgs& a, int nBlocks, cudaStream_t s) {
   if (nBlocks <= 0) return cudaSuccess;
   if (gl)
     k_update<NP, true><<<nBlocks, D::NP3, upd_smem, s>>>(a);
+  else if (a.entropy)
+    k_update<NP, false, true><<<nBlocks, D::NP3, upd_smem, s>>>(a);
   else
     k_update<NP, false><<<nBlocks, D::NP3, upd_smem, s>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t surfcorr(const SurfCorrArgs& a, int nBlocks, cudaStream_t s) {
+  if (nBlocks <= 0) return cudaSuccess;
+  k_surfcorr<NP><<<nBlocks, D::NP3, sizeof(double) * (D::NBASIS + 5 * D::NP3), s>>>(a);
   return cudaGetLastError();
 }
 
@@ -253,7 +285,7 @@ cudaError_t dt(const DtArgs& a, int nElems, cudaStream_t s) {
   return cudaGetLastError();
 }
 
-const NpOps ops = {NP, setup, prolong, volume, flux, update, surfint, dt, bc_pre, flux_bc};
+const NpOps ops = {NP, setup, prolong, volume, flux, update, surfcorr, surfint, dt, bc_pre, flux_bc};
 }  // namespace
 }  // namespace fx
 

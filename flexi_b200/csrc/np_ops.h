@@ -15,6 +15,7 @@ struct NpOps {
   cudaError_t (*volume)(bool gl, bool split, int stype, bool para, int nvl, const VolArgs& a, int nBlocks, cudaStream_t s);
   cudaError_t (*flux)(const FluxArgs& a, cudaStream_t s);
   cudaError_t (*update)(bool gl, const UpdArgs& a, int nBlocks, cudaStream_t s);
+  cudaError_t (*surfcorr)(const SurfCorrArgs& a, int nBlocks, cudaStream_t s);
   cudaError_t (*surfint)(bool gl, const SurfArgs& a, int nElems, cudaStream_t s);
   cudaError_t (*dt)(const DtArgs& a, int nElems, cudaStream_t s);
   cudaError_t (*bc_pre)(const BCArgs& a, cudaStream_t s);

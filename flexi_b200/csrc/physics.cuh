@@ -61,6 +61,30 @@ __device__ __forceinline__ double cons_to_prim_srho(const Eqn& q, const double* 
   return sRho;
 }
 
+// eos.f90:401-420 PrimToEntropy and :499-531 EntropyToCons (PP_EntropyVars = 1: split form on Gauss nodes)
+__device__ __forceinline__ void prim_to_entropy(const Eqn& q, const double* __restrict__ prim, double* __restrict__ w) {
+  const double s = log(prim[PRES]) - q.kappa * log(prim[DENS]);
+  const double rho_p = prim[DENS] / prim[PRES];
+  w[0] = (q.kappa - s) * q.sKappaM1 - rho_p * 0.5 * (prim[VEL1] * prim[VEL1] + prim[VEL2] * prim[VEL2] + prim[VEL3] * prim[VEL3]);
+  w[1] = rho_p * prim[VEL1];
+  w[2] = rho_p * prim[VEL2];
+  w[3] = rho_p * prim[VEL3];
+  w[4] = -rho_p;
+}
+__device__ __forceinline__ void entropy_to_cons(const Eqn& q, const double* __restrict__ w, double* __restrict__ c) {
+  double e2[5];
+#pragma unroll
+  for (int v = 0; v < 5; ++v) e2[v] = w[v] * q.kappaM1;
+  const double ekin = 0.5 * (e2[1] * e2[1] + e2[2] * e2[2] + e2[3] * e2[3]) / e2[4];
+  const double s = q.kappa - e2[0] + ekin;
+  const double rhoe = pow(q.kappaM1, q.sKappaM1) * pow(-e2[4], -(q.kappa / q.kappaM1)) * exp(-s * q.sKappaM1);
+  c[0] = -rhoe * e2[4];
+  c[1] = rhoe * e2[1];
+  c[2] = rhoe * e2[2];
+  c[3] = rhoe * e2[3];
+  c[4] = rhoe * (1. - ekin);
+}
+
 // eos.f90:308-330 PrimToCons
 __device__ __forceinline__ void prim_to_cons(const Eqn& q, const double* __restrict__ p, double* __restrict__ c) {
   c[DENS] = p[DENS];

@@ -249,6 +249,11 @@ int flexi_gpu_prolong_to_face(flexi_gpu_handle* h, const double* Uvol, double* U
 int flexi_gpu_surf_int(flexi_gpu_handle* h, const double* Flux_master, const double* Flux_slave, double* Ut,
                        int32_t doMPISides);
 
+/* Split form on Gauss nodes (SPLIT_DG with PP_NodeType = GAUSS, i.e. PP_EntropyVars = 1: entropy-projected traces
+ * prolongtoface.t90:151-204, two-point surface correction surfint.t90:90-137,190-209): hand over MOD_Mesh_Vars Ja_Face and Ja_slave,
+ * (3,3,0:N,0:N,nSides) each, after flexi_gpu_init and before the first DG operator call (the descriptor does not carry them). */
+int flexi_gpu_set_face_metrics(flexi_gpu_handle* h, const double* Ja_Face, const double* Ja_slave);
+
 /* Page-lock a host array (cudaHostRegister) so that flexi_gpu_set_state / get_state / get_array move it at full PCIe speed and
  * asynchronously; the Fortran host calls this once for MOD_DG_Vars:U after allocation (dg.f90:94) and unpins before DEALLOCATE. */
 int flexi_gpu_pin_host_array(void* ptr, int64_t nbytes);
