@@ -1717,8 +1717,8 @@ oracle* oracle_create(const flexi_gpu_desc* d) {
   return o;
 }
 
-/* Ja_Face / Ja_slave (3,3,0:N,0:N,nSides) of MOD_Mesh_Vars (metrics.f90:681-705): only the split form on Gauss nodes reads them, and
- * the C ABI descriptor of the GPU library does not carry them yet, so the oracle takes them through this extra entry. */
+/* Ja_Face / Ja_slave (3,3,0:N,0:N,nSides) of MOD_Mesh_Vars (metrics.f90:681-705): only the split form on Gauss nodes reads them; like
+ * the GPU library (flexi_gpu_set_face_metrics) the oracle takes them through an extra entry, the descriptor does not carry them. */
 void oracle_set_face_metrics(oracle* o, const double* Ja_Face, const double* Ja_slave) {
   const size_t n = (size_t)o->d.nSides * o->np * o->np * 9;
   free(o->Ja_Face);

@@ -74,8 +74,8 @@ def test_tgv_row2_after_10_steps(tgv_run):
 
 # ---- regressioncheck/checks/tgv/splitGauss: Gauss nodes, N=5, 8^3 elements, SPLIT_DG (PI) => PP_EntropyVars=1 (entropy-projected
 #      traces, prolongtoface.t90:151-204) and the two-point surface correction of surfint.t90:90-137; rows 1 and 2 of
-#      TGV_Re1600_Split_TGVAnalysis_Reference.csv.  The CUDA library does not implement this flavour yet; the
-#      oracle for it is pinned here so that the GPU work of the next round starts from a checked reference.
+#      TGV_Re1600_Split_TGVAnalysis_Reference.csv pin the oracle of this flavour; the CUDA path is checked
+#      against the oracle and against the same rows in tests/test_gpu_gauss_split.py.
 GROW1 = dict(DR_S=0.46874997597598E-03, Ekin=0.125, Ekin_comp=0.125, Enstr=0.37500001858576, DR_u=0.46874999960409E-03,
              DR_Sd=0.46874997597387E-03, Vorticity_max=0.20000268012901E+01, T_mean=0.10000000200000E+01, uPrime=0.28867513459481,
              Entropy=-.10671740566753E+02, ED_S=0.46875002323220E-03)
