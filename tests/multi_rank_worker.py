@@ -33,6 +33,7 @@ CASES = {
                                                 boundary_type=[(4, 2, 0), (9, 0, 0), (2, 1, 0)],
                                                 ref_state_prim=[(1.0, 0.3, 0.0, 0.0, 0.71428571), (1.0, 0.0, 0.0, 0.0, 0.9)])),
 }
+CASES["splitG"] = (4, B.NODE_GAUSS, dict(parabolic=True, split_dg=True, split_dg_type="pi", riemann="lf", mu0=1e-2))  # PP_EntropyVars=1
 WALL_BC = {(1, -1): 1, (1, 1): 2, (0, -1): 3, (0, 1): 3}  # walls in y, far field in x, periodic in z
 
 
@@ -51,7 +52,8 @@ def main():
     else:
         spec = BoxSpec((4, 3, 2), **CURVED)
     part = dict(partition="linear") if world != 4 else dict(partition="block", blocks=(2, 2, 1))
-    ranks = build_case(spec, N, node, eqn, nranks=world, **part)  # every rank builds all partitions (tiny mesh) for the oracle world
+    gauss_split = bool(eqn.get("split_dg")) and node == B.NODE_GAUSS  # needs Ja_Face / Ja_slave
+    ranks = build_case(spec, N, node, eqn, nranks=world, with_ja_face=gauss_split, **part)  # every rank builds all partitions (tiny mesh)
     me = ranks[rank]
     m = me.mesh
 
@@ -79,12 +81,17 @@ def main():
     # ---- oracle world on this partition vs the single-rank oracle (partition invariance, SURVEY 8c identity 7) ----
     U0s = [r.eqn.smooth_state(r.mesh.Elem_xGP, length=2.0) for r in ranks]
     w = O.OracleWorld([(r.desc, r.keep) for r in ranks])
+    if gauss_split:
+        for r, o in zip(ranks, w.ranks):
+            o.set_face_metrics(r.mesh.Ja_Face, r.mesh.Ja_slave)
     w.set_state(U0s)
     w.dg_time_derivative(0.0)
     ut_ref = w.ranks[rank].array("Ut").copy()
     if rank == 0:
-        one = build_case(spec, N, node, eqn)[0]
+        one = build_case(spec, N, node, eqn, with_ja_face=gauss_split)[0]
         w1 = O.OracleWorld([(one.desc, one.keep)])
+        if gauss_split:
+            w1.ranks[0].set_face_metrics(one.mesh.Ja_Face, one.mesh.Ja_slave)
         w1.set_state([one.eqn.smooth_state(one.mesh.Elem_xGP, length=2.0)])
         w1.dg_time_derivative(0.0)
         full = w1.ranks[0].array("Ut")
@@ -100,6 +107,8 @@ def main():
         dist.broadcast(idt, src=0)
         me.remake_desc(nccl_id=bytes(idt.numpy().tobytes()), device=local)
         g = G.FlexiGpu(me)
+        if gauss_split:
+            g.set_face_metrics(m.Ja_Face, m.Ja_slave)
         g.set_state(U0s[rank])
         ut = g.DGTimeDerivative_weakForm(0.0)
         scale = np.max(np.abs(ut_ref).reshape(-1, 5), axis=0)
