@@ -502,9 +502,14 @@ static int init_impl(const flexi_gpu_desc* d, H* h) {
   if (d->doWeakLifting || d->doConservativeLifting) return fail(FLEXI_GPU_ERR_UNSUPPORTED, "only the strong, non-conservative lifting (the reference default, lifting.f90:72-76) is implemented");
   // split form on Gauss nodes (PP_EntropyVars = 1): implemented, but it needs Ja_Face / Ja_slave, which the descriptor does not
   // carry: flexi_gpu_set_face_metrics must follow flexi_gpu_init
-  if (d->splitDG && !(d->splitDGType == FLEXI_SPLITDG_SD || d->splitDGType == FLEXI_SPLITDG_DU || d->splitDGType == FLEXI_SPLITDG_KG || d->splitDGType == FLEXI_SPLITDG_PI))
-    return fail(FLEXI_GPU_ERR_UNSUPPORTED, "SplitDG formulation %d is not implemented", d->splitDGType);
-  if (d->splitDG && d->riemann == FLEXI_RIEMANN_HLLC) return fail(FLEXI_GPU_ERR_ARG, "HLLC is not selectable with SPLIT_DG (riemann.f90:206-227)");
+  if (d->splitDG && (d->splitDGType < FLEXI_SPLITDG_SD || d->splitDGType > FLEXI_SPLITDG_IR))
+    return fail(FLEXI_GPU_ERR_ARG, "SplitDG formulation not defined! (%d, splitflux.f90:150-152)", d->splitDGType);
+  {  // SPLIT_DG builds offer LF, Roe, RoeL2, RoeEntropyFix, Average, CH, IR only (riemann.f90:204-246)
+    const int rs[2] = {d->riemann, d->riemannBC};
+    for (int t = 0; t < 2; ++t)
+      if (d->splitDG && (rs[t] == FLEXI_RIEMANN_HLLC || rs[t] == FLEXI_RIEMANN_HLL || rs[t] == FLEXI_RIEMANN_HLLE || rs[t] == FLEXI_RIEMANN_HLLEM))
+        return fail(FLEXI_GPU_ERR_ARG, "Riemann solver %d is not selectable with SPLIT_DG (riemann.f90:204-246)", rs[t]);
+  }
   if (d->parabolic && d->lifting != 1 && d->lifting != 2) return fail(FLEXI_GPU_ERR_ARG, "lifting must be 1 (BR1) or 2 (BR2)");
   if (d->parabolic && d->nVarLifting != 5 && d->nVarLifting != 4) return fail(FLEXI_GPU_ERR_ARG, "nVarLifting must be 4 or 5");
   if (d->nElems < 1 || d->nSides < 1) return fail(FLEXI_GPU_ERR_ARG, "empty mesh");
@@ -567,6 +572,9 @@ static int init_impl(const flexi_gpu_desc* d, H* h) {
   switch (q.riemann) {
     case FLEXI_RIEMANN_LF: case FLEXI_RIEMANN_HLLC: case FLEXI_RIEMANN_ROE: case FLEXI_RIEMANN_ROEL2: case FLEXI_RIEMANN_ROEENTROPYFIX:
     case FLEXI_RIEMANN_HLL: case FLEXI_RIEMANN_HLLE: case FLEXI_RIEMANN_HLLEM: break;
+    case FLEXI_RIEMANN_AVERAGE: case FLEXI_RIEMANN_CH: case FLEXI_RIEMANN_IR:  // exist in SPLIT_DG builds only (riemann.f90:54-58,211-220)
+      if (q.splitDG) break;
+      // fall through
     default: return fail(FLEXI_GPU_ERR_ARG, "unknown Riemann solver %d", q.riemann);
   }
 
@@ -742,6 +750,9 @@ static int init_impl(const flexi_gpu_desc* d, H* h) {
       switch (bc.riemannBC) {
         case FLEXI_RIEMANN_LF: case FLEXI_RIEMANN_HLLC: case FLEXI_RIEMANN_ROE: case FLEXI_RIEMANN_ROEL2: case FLEXI_RIEMANN_ROEENTROPYFIX:
         case FLEXI_RIEMANN_HLL: case FLEXI_RIEMANN_HLLE: case FLEXI_RIEMANN_HLLEM: break;
+        case FLEXI_RIEMANN_AVERAGE: case FLEXI_RIEMANN_CH: case FLEXI_RIEMANN_IR:  // riemann.f90:236-245
+          if (q.splitDG) break;
+          // fall through
         default: return fail(FLEXI_GPU_ERR_ARG, "unknown RiemannBC %d", bc.riemannBC);
       }
       int32_t *dbt = nullptr, *dbs = nullptr;

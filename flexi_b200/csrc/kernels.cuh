@@ -147,7 +147,7 @@ struct VolSmem {
 // pairwise two-point volume fluxes of one node along its three lines, volint.f90:211-371 (advective part)
 template <int NP, int STYPE>
 __device__ __forceinline__ void split_lines(const double* sP, const double* sM, const double* sB, int i, int j, int k, int n,
-                                            const double* M, double* ut) {
+                                            const double* M, double* ut, const double kappa) {
   using D = Dim<NP>;
   const double* dv = sB + D::O_DV;
   Node a;
@@ -174,7 +174,7 @@ __device__ __forceinline__ void split_lines(const double* sP, const double* sM, 
       b.E = sP[6 * D::NP3 + nl];
       const double Mb[3] = {sM[(3 * dir + 0) * D::NP3 + nl], sM[(3 * dir + 1) * D::NP3 + nl], sM[(3 * dir + 2) * D::NP3 + nl]};
       double F[5];
-      split_volume_flux<STYPE>(a, b, M + 3 * dir, Mb, F);
+      split_volume_flux<STYPE>(a, b, M + 3 * dir, Mb, F, kappa);
       const double d = (l == me) ? 0. : dv[l * NP + me];  // DVolSurf(l,me); self pair weighted with zero (no divergent skip)
 #pragma unroll
       for (int v = 0; v < 5; ++v) ut[v] = ut[v] + d * F[v];
@@ -484,10 +484,13 @@ __global__ void __launch_bounds__(Dim<NP>::NP3) k_volume(VolArgs A) {
     for (int c = 0; c < 9; ++c) sW[c * D::NP3 + n] = M[c];
     __syncthreads();
     switch (q.splitType) {
-      case FLEXI_SPLITDG_SD: split_lines<NP, FLEXI_SPLITDG_SD>(sP, sW, sB, i, j, k, n, M, ut); break;
-      case FLEXI_SPLITDG_DU: split_lines<NP, FLEXI_SPLITDG_DU>(sP, sW, sB, i, j, k, n, M, ut); break;
-      case FLEXI_SPLITDG_KG: split_lines<NP, FLEXI_SPLITDG_KG>(sP, sW, sB, i, j, k, n, M, ut); break;
-      default: split_lines<NP, FLEXI_SPLITDG_PI>(sP, sW, sB, i, j, k, n, M, ut);
+      case FLEXI_SPLITDG_SD: split_lines<NP, FLEXI_SPLITDG_SD>(sP, sW, sB, i, j, k, n, M, ut, q.kappa); break;
+      case FLEXI_SPLITDG_MO: split_lines<NP, FLEXI_SPLITDG_MO>(sP, sW, sB, i, j, k, n, M, ut, q.kappa); break;
+      case FLEXI_SPLITDG_DU: split_lines<NP, FLEXI_SPLITDG_DU>(sP, sW, sB, i, j, k, n, M, ut, q.kappa); break;
+      case FLEXI_SPLITDG_KG: split_lines<NP, FLEXI_SPLITDG_KG>(sP, sW, sB, i, j, k, n, M, ut, q.kappa); break;
+      case FLEXI_SPLITDG_CH: split_lines<NP, FLEXI_SPLITDG_CH>(sP, sW, sB, i, j, k, n, M, ut, q.kappa); break;
+      case FLEXI_SPLITDG_IR: split_lines<NP, FLEXI_SPLITDG_IR>(sP, sW, sB, i, j, k, n, M, ut, q.kappa); break;
+      default: split_lines<NP, FLEXI_SPLITDG_PI>(sP, sW, sB, i, j, k, n, M, ut, q.kappa);
     }
   }
 #pragma unroll
@@ -854,10 +857,13 @@ __global__ void __launch_bounds__(Dim<NP>::NP3) k_surfcorr(SurfCorrArgs A) {
     const double Jv[3] = {Ja[(idx + 0) * D::NP2], Ja[(idx + 3) * D::NP2], Ja[(idx + 6) * D::NP2]};
     double FB[5];
     switch (q.splitType) {  // SplitDGVolume_pointer(U, UPrim, U_face, UPrim_face, Metrics, Ja_face), surfint.t90:118-121
-      case FLEXI_SPLITDG_SD: split_volume_flux<FLEXI_SPLITDG_SD>(nd, nf, M + 3 * idx, Jv, FB); break;
-      case FLEXI_SPLITDG_DU: split_volume_flux<FLEXI_SPLITDG_DU>(nd, nf, M + 3 * idx, Jv, FB); break;
-      case FLEXI_SPLITDG_KG: split_volume_flux<FLEXI_SPLITDG_KG>(nd, nf, M + 3 * idx, Jv, FB); break;
-      default: split_volume_flux<FLEXI_SPLITDG_PI>(nd, nf, M + 3 * idx, Jv, FB);
+      case FLEXI_SPLITDG_SD: split_volume_flux<FLEXI_SPLITDG_SD>(nd, nf, M + 3 * idx, Jv, FB, q.kappa); break;
+      case FLEXI_SPLITDG_MO: split_volume_flux<FLEXI_SPLITDG_MO>(nd, nf, M + 3 * idx, Jv, FB, q.kappa); break;
+      case FLEXI_SPLITDG_DU: split_volume_flux<FLEXI_SPLITDG_DU>(nd, nf, M + 3 * idx, Jv, FB, q.kappa); break;
+      case FLEXI_SPLITDG_KG: split_volume_flux<FLEXI_SPLITDG_KG>(nd, nf, M + 3 * idx, Jv, FB, q.kappa); break;
+      case FLEXI_SPLITDG_CH: split_volume_flux<FLEXI_SPLITDG_CH>(nd, nf, M + 3 * idx, Jv, FB, q.kappa); break;
+      case FLEXI_SPLITDG_IR: split_volume_flux<FLEXI_SPLITDG_IR>(nd, nf, M + 3 * idx, Jv, FB, q.kappa); break;
+      default: split_volume_flux<FLEXI_SPLITDG_PI>(nd, nf, M + 3 * idx, Jv, FB, q.kappa);
     }
 #pragma unroll
     for (int v = 0; v < 5; ++v) sFB[v * D::NP3 + n] = FB[v] * Leg[l];

@@ -139,7 +139,8 @@ cudaError_t gl2_launch(int lift, const VolArgs& a, int nBlocks, cudaStream_t s) 
 
 constexpr size_t upd_smem = sizeof(double) * (D::NBASIS + 5 * D::NP3);
 
-#define FX_SPLIT_TYPES(X) X(FLEXI_SPLITDG_SD) X(FLEXI_SPLITDG_DU) X(FLEXI_SPLITDG_KG) X(FLEXI_SPLITDG_PI)
+#define FX_SPLIT_TYPES(X) \
+  X(FLEXI_SPLITDG_SD) X(FLEXI_SPLITDG_MO) X(FLEXI_SPLITDG_DU) X(FLEXI_SPLITDG_KG) X(FLEXI_SPLITDG_PI) X(FLEXI_SPLITDG_CH) X(FLEXI_SPLITDG_IR)
 
 cudaError_t setup() {
   cudaError_t e;

@@ -7,6 +7,9 @@
 
 #include "../../include/flexi_gpu.h"
 
+// host+device so that tests/host_physics.cu can run the very same point functions on the CPU against the oracle
+#define FX_HD __host__ __device__ __forceinline__
+
 namespace fx {
 
 // scalar equation/solver parameters handed to every kernel by value (constant bank)
@@ -40,7 +43,7 @@ enum { DENS = 0, MOM1 = 1, MOM2 = 2, MOM3 = 3, ENER = 4 };
 enum { VEL1 = 1, VEL2 = 2, VEL3 = 3, PRES = 4, TEMP = 5 };
 
 // eos.f90:203-231 ConsToPrim
-__device__ __forceinline__ void cons_to_prim(const Eqn& q, const double* __restrict__ c, double* __restrict__ p) {
+FX_HD void cons_to_prim(const Eqn& q, const double* __restrict__ c, double* __restrict__ p) {
   const double sRho = 1. / c[DENS];
   p[DENS] = c[DENS];
   p[VEL1] = c[MOM1] * sRho;
@@ -50,7 +53,7 @@ __device__ __forceinline__ void cons_to_prim(const Eqn& q, const double* __restr
   p[TEMP] = p[PRES] * sRho * q.sR;  // the reference divides by R (eos.f90:229); 1/R is formed once on the host (<= 1 ulp)
 }
 // same, also returning 1/rho for callers that need it again
-__device__ __forceinline__ double cons_to_prim_srho(const Eqn& q, const double* __restrict__ c, double* __restrict__ p) {
+FX_HD double cons_to_prim_srho(const Eqn& q, const double* __restrict__ c, double* __restrict__ p) {
   const double sRho = 1. / c[DENS];
   p[DENS] = c[DENS];
   p[VEL1] = c[MOM1] * sRho;
@@ -62,7 +65,7 @@ __device__ __forceinline__ double cons_to_prim_srho(const Eqn& q, const double* 
 }
 
 // eos.f90:401-420 PrimToEntropy and :499-531 EntropyToCons (PP_EntropyVars = 1: split form on Gauss nodes)
-__device__ __forceinline__ void prim_to_entropy(const Eqn& q, const double* __restrict__ prim, double* __restrict__ w) {
+FX_HD void prim_to_entropy(const Eqn& q, const double* __restrict__ prim, double* __restrict__ w) {
   const double s = log(prim[PRES]) - q.kappa * log(prim[DENS]);
   const double rho_p = prim[DENS] / prim[PRES];
   w[0] = (q.kappa - s) * q.sKappaM1 - rho_p * 0.5 * (prim[VEL1] * prim[VEL1] + prim[VEL2] * prim[VEL2] + prim[VEL3] * prim[VEL3]);
@@ -71,7 +74,7 @@ __device__ __forceinline__ void prim_to_entropy(const Eqn& q, const double* __re
   w[3] = rho_p * prim[VEL3];
   w[4] = -rho_p;
 }
-__device__ __forceinline__ void entropy_to_cons(const Eqn& q, const double* __restrict__ w, double* __restrict__ c) {
+FX_HD void entropy_to_cons(const Eqn& q, const double* __restrict__ w, double* __restrict__ c) {
   double e2[5];
 #pragma unroll
   for (int v = 0; v < 5; ++v) e2[v] = w[v] * q.kappaM1;
@@ -86,7 +89,7 @@ __device__ __forceinline__ void entropy_to_cons(const Eqn& q, const double* __re
 }
 
 // eos.f90:308-330 PrimToCons
-__device__ __forceinline__ void prim_to_cons(const Eqn& q, const double* __restrict__ p, double* __restrict__ c) {
+FX_HD void prim_to_cons(const Eqn& q, const double* __restrict__ p, double* __restrict__ c) {
   c[DENS] = p[DENS];
   c[MOM1] = p[VEL1] * p[DENS];
   c[MOM2] = p[VEL2] * p[DENS];
@@ -95,7 +98,7 @@ __device__ __forceinline__ void prim_to_cons(const Eqn& q, const double* __restr
 }
 
 // flux.f90:66-119 EvalFlux3D_Point
-__device__ __forceinline__ void eval_flux3d(const double* U, const double* P, double* f, double* g, double* h) {
+FX_HD void eval_flux3d(const double* U, const double* P, double* f, double* g, double* h) {
   const double Ep = U[ENER] + P[PRES];
   f[DENS] = U[MOM1];
   f[MOM1] = U[MOM1] * P[VEL1] + P[PRES];
@@ -116,7 +119,7 @@ __device__ __forceinline__ void eval_flux3d(const double* U, const double* P, do
 
 // flux.f90:149-241 EvalDiffFlux3D_Point.  gv* = gradient of (v1,v2,v3), gT* = gradient of T; (x,y,z) components.
 // Only the four non-zero rows (momentum, energy) are returned: f[0..2] momentum, f[3] energy.
-__device__ __forceinline__ void eval_diff_flux3d(const Eqn& q, double v1, double v2, double v3, const double* gx, const double* gy,
+FX_HD void eval_diff_flux3d(const Eqn& q, double v1, double v2, double v3, const double* gx, const double* gy,
                                                  const double* gz, double* f, double* g, double* h) {
   // gx = d(v1,v2,v3,T)/dx etc.
   const double s23 = 2. / 3., s43 = 4. / 3.;
@@ -147,12 +150,108 @@ struct Node {
   double rho, v1, v2, v3, p, E;  // E = rho*E (cons energy)
 };
 
-// SplitVolumeFlux{SD,DU,KG,PI}: physical fluxes with the factor 2 folded in (splitflux.f90:21-22), then the metric
-// average contraction of splitflux.f90 (0.5*(MRef+M)).  Returns the contravariant two-point flux.
+// splitflux.f90:994-1020 GetLogMean: (a+b)/g, g = ln(chi)/f with its series around chi = 1
+FX_HD double log_mean(double U_L, double U_R) {
+  const double chi = U_L / U_R, f = (chi - 1.) / (chi + 1.);
+  double g;
+  if (fabs(f) < 0.1) {
+    const double u = f * f;
+    g = 2. + 2. / 3. * u + 0.4 * u * u + 2. / 7. * u * u * u;
+  } else {
+    g = log(chi) / f;
+  }
+  return (U_L + U_R) / g;
+}
+
+// Ismail-Roe parameter-vector averages shared by SplitVolumeFluxIR / SplitSurfaceFluxIR / Riemann_IR
+// (splitflux.f90:875-905,948-978, riemann.f90:1352-1378); a = "Ref"/"LL" state, b = the other one
+struct IRMean {
+  double rhoHat, uHat, vHat, wHat, pHat, p2Hat, hHat;
+};
+FX_HD IRMean ir_mean(double kappa, double a_rho, double a_v1, double a_v2, double a_v3, double a_p, double b_rho, double b_v1, double b_v2,
+                     double b_v3, double b_p, bool b_first) {
+  // the volume flux forms z(U) before z(URef) and averages in the order z + zRef; the surface versions LL before RR
+  double za[5], zb[5];
+  za[0] = sqrt(a_rho / a_p); za[1] = za[0] * a_v1; za[2] = za[0] * a_v2; za[3] = za[0] * a_v3; za[4] = sqrt(a_rho * a_p);
+  zb[0] = sqrt(b_rho / b_p); zb[1] = zb[0] * b_v1; zb[2] = zb[0] * b_v2; zb[3] = zb[0] * b_v3; zb[4] = sqrt(b_rho * b_p);
+  const double* z1 = b_first ? zb : za;
+  const double* z2 = b_first ? za : zb;
+  const double z1LogMean = log_mean(z1[0], z2[0]);
+  const double z5LogMean = log_mean(z1[4], z2[4]);
+  const double z1Mean = 0.5 * (z1[0] + z2[0]);
+  IRMean m;
+  m.rhoHat = z1Mean * z5LogMean;
+  m.pHat = 0.5 * (z1[4] + z2[4]) / z1Mean;
+  m.p2Hat = 1. / (2. * kappa) * ((kappa + 1.) * z5LogMean / z1LogMean + (kappa - 1.) * m.pHat);
+  m.uHat = 0.5 * (z1[1] + z2[1]) / z1Mean;
+  m.vHat = 0.5 * (z1[2] + z2[2]) / z1Mean;
+  m.wHat = 0.5 * (z1[3] + z2[3]) / z1Mean;
+  m.hHat = kappa * m.p2Hat / (m.rhoHat * (kappa - 1.)) + 0.5 * (m.uHat * m.uHat + m.vHat * m.vHat + m.wHat * m.wHat);
+  return m;
+}
+
+// SplitVolumeFlux{SD,MO,DU,KG,PI,CH,IR}: physical fluxes with the factor 2 folded in (splitflux.f90:21-22), then the metric
+// average contraction of splitflux.f90 (0.5*(MRef+M)).  Returns the contravariant two-point flux.  a = "Ref" node.
 template <int TYPE>
-__device__ __forceinline__ void split_volume_flux(const Node& a, const Node& b, const double* Ma, const double* Mb, double* Flux) {
+FX_HD void split_volume_flux(const Node& a, const Node& b, const double* Ma, const double* Mb, double* Flux, const double kappa) {
   double fT[5], gT[5], hT[5];
-  if (TYPE == FLEXI_SPLITDG_SD) {  // splitflux.f90:160-222
+  if (TYPE == FLEXI_SPLITDG_IR) {  // splitflux.f90:857-927; carries no factor 2 in the reference -- kept as it stands
+    const IRMean m = ir_mean(kappa, a.rho, a.v1, a.v2, a.v3, a.p, b.rho, b.v1, b.v2, b.v3, b.p, true);
+    const double M0 = 0.5 * (Ma[0] + Mb[0]), M1 = 0.5 * (Ma[1] + Mb[1]), M2 = 0.5 * (Ma[2] + Mb[2]);
+    const double qeff = m.rhoHat * (m.uHat * M0 + m.vHat * M1 + m.wHat * M2);
+    Flux[0] = qeff;
+    Flux[1] = qeff * m.uHat + m.pHat * M0;
+    Flux[2] = qeff * m.vHat + m.pHat * M1;
+    Flux[3] = qeff * m.wHat + m.pHat * M2;
+    Flux[4] = qeff * m.hHat;
+    return;
+  }
+  if (TYPE == FLEXI_SPLITDG_CH) {  // splitflux.f90:711-795
+    const double uMean = 0.5 * (a.v1 + b.v1), vMean = 0.5 * (a.v2 + b.v2), wMean = 0.5 * (a.v3 + b.v3);
+    const double betaRef = 0.5 * a.rho / a.p, beta = 0.5 * b.rho / b.p;
+    const double rhoLogMean = log_mean(a.rho, b.rho);
+    const double betaLogMean = log_mean(betaRef, beta);
+    const double pHatMean = 0.5 * (a.rho + b.rho) / (betaRef + beta);
+    const double HMean = 0.5 * (1. / (kappa - 1.)) / betaLogMean + pHatMean / rhoLogMean + 0.5 * (a.v1 * b.v1 + a.v2 * b.v2 + a.v3 * b.v3);
+    fT[0] = rhoLogMean * uMean;
+    fT[1] = rhoLogMean * uMean * uMean + pHatMean;
+    fT[2] = rhoLogMean * uMean * vMean;
+    fT[3] = rhoLogMean * uMean * wMean;
+    fT[4] = rhoLogMean * HMean * uMean;
+    gT[0] = rhoLogMean * vMean;
+    gT[1] = rhoLogMean * vMean * uMean;
+    gT[2] = rhoLogMean * vMean * vMean + pHatMean;
+    gT[3] = rhoLogMean * vMean * wMean;
+    gT[4] = rhoLogMean * HMean * vMean;
+    hT[0] = rhoLogMean * wMean;
+    hT[1] = rhoLogMean * wMean * uMean;
+    hT[2] = rhoLogMean * wMean * vMean;
+    hT[3] = rhoLogMean * wMean * wMean + pHatMean;
+    hT[4] = rhoLogMean * HMean * wMean;
+    const double m0 = 0.5 * (Ma[0] + Mb[0]), m1 = 0.5 * (Ma[1] + Mb[1]), m2 = 0.5 * (Ma[2] + Mb[2]);
+#pragma unroll
+    for (int v = 0; v < 5; ++v) Flux[v] = (m0 * fT[v] + m2 * hT[v] + m1 * gT[v]) * 2.;  // :794
+    return;
+  }
+  if (TYPE == FLEXI_SPLITDG_MO) {  // splitflux.f90:471-552
+    const double av[3] = {a.v1, a.v2, a.v3}, bv[3] = {b.v1, b.v2, b.v3};
+    const double rhoepRef = a.E - 0.5 * a.rho * (a.v1 * a.v1 + a.v2 * a.v2 + a.v3 * a.v3) + a.p;
+    const double rhoep = b.E - 0.5 * b.rho * (b.v1 * b.v1 + b.v2 * b.v2 + b.v3 * b.v3) + b.p;
+    double* T[3] = {fT, gT, hT};
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const double mR = a.rho * av[d], m = b.rho * bv[d];
+      double* t = T[d];
+      t[0] = (mR + m);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) t[1 + c] = 0.5 * (mR + m) * (av[c] + bv[c]);
+      t[1 + d] = t[1 + d] + (a.p + b.p);
+      t[4] = (rhoepRef * av[d] + rhoep * bv[d]) + 0.5 * (mR * av[0] + m * bv[0]) * (av[0] + bv[0]) +
+             0.5 * (mR * av[1] + m * bv[1]) * (av[1] + bv[1]) + 0.5 * (mR * av[2] + m * bv[2]) * (av[2] + bv[2]) -
+             0.5 * (mR * av[0] * av[0] + m * bv[0] * bv[0]) - 0.5 * (mR * av[1] * av[1] + m * bv[1] * bv[1]) -
+             0.5 * (mR * av[2] * av[2] + m * bv[2] * bv[2]);
+    }
+  } else if (TYPE == FLEXI_SPLITDG_SD) {  // splitflux.f90:160-222
     const double am1 = a.rho * a.v1, am2 = a.rho * a.v2, am3 = a.rho * a.v3;
     const double bm1 = b.rho * b.v1, bm2 = b.rho * b.v2, bm3 = b.rho * b.v3;
     const double aEp = a.E + a.p, bEp = b.E + b.p;
@@ -216,7 +315,7 @@ struct Ext {
 };
 
 // flux.f90:396-417 EvalEulerFlux1D_fast
-__device__ __forceinline__ void euler_flux1d(const Ext& U, double* F) {
+FX_HD void euler_flux1d(const Ext& U, double* F) {
   F[0] = U.m1;
   F[1] = U.m1 * U.v1 + U.p;
   F[2] = U.m1 * U.v2;
@@ -224,9 +323,42 @@ __device__ __forceinline__ void euler_flux1d(const Ext& U, double* F) {
   F[4] = (U.E + U.p) * U.v1;
 }
 
-// SplitSurfaceFlux{SD,DU,KG,PI}, splitflux.f90:228-252,326-349,431-460,672-700
-__device__ __forceinline__ void split_surface_flux(int type, const Ext& L, const Ext& R, double* F) {
+// SplitSurfaceFlux{SD,DU,KG,PI,MO,CH,IR}, splitflux.f90:228-252,326-349,431-460,672-700,558-593,803-852,932-989
+FX_HD void split_surface_flux(int type, const Ext& L, const Ext& R, double* F, const double kappa) {
   switch (type) {
+    case FLEXI_SPLITDG_MO: {
+      const double rhoep_LL = L.E - 0.5 * L.rho * (L.v1 * L.v1 + L.v2 * L.v2 + L.v3 * L.v3) + L.p;
+      const double rhoep_RR = R.E - 0.5 * R.rho * (R.v1 * R.v1 + R.v2 * R.v2 + R.v3 * R.v3) + R.p;
+      F[0] = 0.5 * (L.m1 + R.m1);
+      F[1] = 0.25 * (L.m1 + R.m1) * (L.v1 + R.v1) + 0.5 * (L.p + R.p);
+      F[2] = 0.25 * (L.m1 + R.m1) * (L.v2 + R.v2);
+      F[3] = 0.25 * (L.m1 + R.m1) * (L.v3 + R.v3);
+      F[4] = 0.5 * (rhoep_LL * L.v1 + rhoep_RR * R.v1) + 0.25 * (L.m1 * L.v1 + R.m1 * R.v1) * (L.v1 + R.v1) +
+             0.25 * (L.m1 * L.v2 + R.m1 * R.v2) * (L.v2 + R.v2) + 0.25 * (L.m1 * L.v3 + R.m1 * R.v3) * (L.v3 + R.v3) -
+             0.25 * (L.m1 * L.v1 * L.v1 + R.m1 * R.v1 * R.v1) - 0.25 * (L.m1 * L.v2 * L.v2 + R.m1 * R.v2 * R.v2) -
+             0.25 * (L.m1 * L.v3 * L.v3 + R.m1 * R.v3 * R.v3);
+    } break;
+    case FLEXI_SPLITDG_CH: {
+      const double uMean = 0.5 * (L.v1 + R.v1), vMean = 0.5 * (L.v2 + R.v2), wMean = 0.5 * (L.v3 + R.v3);
+      const double beta_LL = 0.5 * L.rho / L.p, beta_RR = 0.5 * R.rho / R.p;
+      const double rhoLogMean = log_mean(L.rho, R.rho);
+      const double betaLogMean = log_mean(beta_LL, beta_RR);
+      const double pHatMean = 0.5 * (L.rho + R.rho) / (beta_LL + beta_RR);
+      const double HMean = 0.5 * (1. / (kappa - 1.)) / betaLogMean + pHatMean / rhoLogMean + 0.5 * (L.v1 * R.v1 + L.v2 * R.v2 + L.v3 * R.v3);
+      F[0] = rhoLogMean * uMean;
+      F[1] = F[0] * uMean + pHatMean;
+      F[2] = F[0] * vMean;
+      F[3] = F[0] * wMean;
+      F[4] = F[0] * HMean;
+    } break;
+    case FLEXI_SPLITDG_IR: {
+      const IRMean m = ir_mean(kappa, L.rho, L.v1, L.v2, L.v3, L.p, R.rho, R.v1, R.v2, R.v3, R.p, false);
+      F[0] = m.rhoHat * m.uHat;
+      F[1] = F[0] * m.uHat + m.pHat;
+      F[2] = F[0] * m.vHat;
+      F[3] = F[0] * m.wHat;
+      F[4] = F[0] * m.hHat;
+    } break;
     case FLEXI_SPLITDG_SD:
       F[0] = 0.5 * (L.m1 + R.m1);
       F[1] = 0.5 * (L.m1 * L.v1 + L.p + R.m1 * R.v1 + R.p);
@@ -260,7 +392,7 @@ struct RoeMean {
   double v1, v2, v3, H, c, absVel;
 };
 // Roe averages as used by riemann.f90:613-627,688-700 (ROEC_RIEMANN_H, eos.h:50)
-__device__ __forceinline__ RoeMean roe_average(const Eqn& q, const Ext& L, const Ext& R) {
+FX_HD RoeMean roe_average(const Eqn& q, const Ext& L, const Ext& R) {
   RoeMean m;
   const double H_L = (L.E + L.p) * L.srho, H_R = (R.E + R.p) * R.srho;
   const double sl = sqrt(L.rho), sr = sqrt(R.rho);
@@ -273,10 +405,10 @@ __device__ __forceinline__ RoeMean roe_average(const Eqn& q, const Ext& L, const
   m.c = sqrt(q.kappaM1 * (m.H - 0.5 * m.absVel));
   return m;
 }
-__device__ __forceinline__ double sound_speed(const Eqn& q, const Ext& U) { return sqrt(q.kappa * U.p * U.srho); }
+FX_HD double sound_speed(const Eqn& q, const Ext& U) { return sqrt(q.kappa * U.p * U.srho); }
 
 // sum_k alpha_k |a_k| r_k of the Roe decomposition (eigenvectors riemann.f90:705-711)
-__device__ __forceinline__ void roe_dissipation(const RoeMean& m, const double* al, const double* a, double* D) {
+FX_HD void roe_dissipation(const RoeMean& m, const double* al, const double* a, double* D) {
   const double a1 = al[0] * a[0], a2 = al[1] * a[1], a3 = al[2] * a[2], a4 = al[3] * a[3], a5 = al[4] * a[4];
   D[0] = a1 + a2 + a5;
   D[1] = a1 * (m.v1 - m.c) + a2 * m.v1 + a5 * (m.v1 + m.c);
@@ -287,7 +419,7 @@ __device__ __forceinline__ void roe_dissipation(const RoeMean& m, const double* 
 
 // The solver proper in the rotated frame; riemann.f90:558-1228.  With SPLIT_DG the central part is the two-point
 // surface flux (riemann.f90:584-587,731-738) and F_L/F_R are never formed (riemann.f90:333-336).
-__device__ __forceinline__ void riemann_solver(const Eqn& q, int solver, const Ext& L, const Ext& R, double* F) {
+FX_HD void riemann_solver(const Eqn& q, int solver, const Ext& L, const Ext& R, double* F) {
   const bool split = q.splitDG != 0;
   const double dU[5] = {R.rho - L.rho, R.m1 - L.m1, R.m2 - L.m2, R.m3 - L.m3, R.E - L.E};
   double FL[5], FR[5];
@@ -302,7 +434,7 @@ __device__ __forceinline__ void riemann_solver(const Eqn& q, int solver, const E
 #pragma unroll
         for (int v = 0; v < 5; ++v) F[v] = 0.5 * ((FL[v] + FR[v]) - lam * dU[v]);
       } else {
-        split_surface_flux(q.splitType, L, R, F);
+        split_surface_flux(q.splitType, L, R, F, q.kappa);
 #pragma unroll
         for (int v = 0; v < 5; ++v) F[v] = F[v] - 0.5 * lam * dU[v];
       }
@@ -361,7 +493,7 @@ __device__ __forceinline__ void riemann_solver(const Eqn& q, int solver, const E
 #pragma unroll
         for (int v = 0; v < 5; ++v) F[v] = 0.5 * ((FL[v] + FR[v]) - D[v]);
       } else {
-        split_surface_flux(q.splitType, L, R, F);
+        split_surface_flux(q.splitType, L, R, F, q.kappa);
 #pragma unroll
         for (int v = 0; v < 5; ++v) F[v] = F[v] - 0.5 * D[v];
       }
@@ -396,10 +528,62 @@ __device__ __forceinline__ void riemann_solver(const Eqn& q, int solver, const E
 #pragma unroll
         for (int v = 0; v < 5; ++v) F[v] = 0.5 * ((FL[v] + FR[v]) - D[v]);
       } else {
-        split_surface_flux(q.splitType, L, R, F);
+        split_surface_flux(q.splitType, L, R, F, q.kappa);
 #pragma unroll
         for (int v = 0; v < 5; ++v) F[v] = F[v] - 0.5 * D[v];
       }
+    } break;
+    case FLEXI_RIEMANN_AVERAGE:  // riemann.f90:1236-1253 Riemann_FluxAverage (SPLIT_DG builds only; checked at init)
+      split_surface_flux(q.splitType, L, R, F, q.kappa);
+      break;
+    case FLEXI_RIEMANN_CH: {  // riemann.f90:1261-1310
+      const double lam = fmax(fabs(R.v1), fabs(L.v1)) + fmax(sound_speed(q, L), sound_speed(q, R));
+      const double rhoMean = 0.5 * (L.rho + R.rho);
+      const double uMean = 0.5 * (L.v1 + R.v1), vMean = 0.5 * (L.v2 + R.v2), wMean = 0.5 * (L.v3 + R.v3);
+      const double beta_LL = 0.5 * L.rho / L.p, beta_RR = 0.5 * R.rho / R.p;
+      const double betaLogMean = log_mean(beta_LL, beta_RR);
+      split_surface_flux(q.splitType, L, R, F, q.kappa);
+#pragma unroll
+      for (int v = 0; v < 4; ++v) F[v] = F[v] - 0.5 * lam * dU[v];
+      F[4] = F[4] - 0.5 * lam * ((R.rho - L.rho) * (0.5 * q.sKappaM1 / betaLogMean + 0.5 * (R.v1 * L.v1 + R.v2 * L.v2 + R.v3 * L.v3)) +
+                                 rhoMean * uMean * (R.v1 - L.v1) + rhoMean * vMean * (R.v2 - L.v2) + rhoMean * wMean * (R.v3 - L.v3) +
+                                 0.5 * rhoMean * q.sKappaM1 * (1. / beta_RR - 1. / beta_LL));
+    } break;
+    case FLEXI_RIEMANN_IR: {  // riemann.f90:1315-1402: F# - 1/2 R |Lambda| T R^T [v], v = entropy variables
+      const double kappa = q.kappa, kappaM1 = q.kappaM1;
+      const double sR = log(R.p) - kappa * log(R.rho), sL = log(L.p) - kappa * log(L.rho);
+      const double rho_pR = R.rho / R.p, rho_pL = L.rho / L.p;
+      double vJ[5];
+      vJ[0] = ((kappa - sR) / kappaM1 - 0.5 * rho_pR * (R.v1 * R.v1 + R.v2 * R.v2 + R.v3 * R.v3)) -
+              ((kappa - sL) / kappaM1 - 0.5 * rho_pL * (L.v1 * L.v1 + L.v2 * L.v2 + L.v3 * L.v3));
+      vJ[1] = rho_pR * R.v1 - rho_pL * L.v1;
+      vJ[2] = rho_pR * R.v2 - rho_pL * L.v2;
+      vJ[3] = rho_pR * R.v3 - rho_pL * L.v3;
+      vJ[4] = -rho_pR - (-rho_pL);
+      const IRMean m = ir_mean(kappa, L.rho, L.v1, L.v2, L.v3, L.p, R.rho, R.v1, R.v2, R.v3, R.p, false);
+      const double aHat = sqrt(kappa * m.p2Hat / m.rhoHat);
+      const double ek = 0.5 * (m.uHat * m.uHat + m.vHat * m.vHat + m.wHat * m.wHat);
+      // columns of RHat (riemann.f90:1381-1385); the zero/one entries are kept as multiplications so that the sums round like the
+      // reference's array expressions
+      const double Rh[5][5] = {{1., 1., 0., 0., 1.},
+                               {m.uHat - aHat, m.uHat, 0., 0., m.uHat + aHat},
+                               {m.vHat, m.vHat, 1., 0., m.vHat},
+                               {m.wHat, m.wHat, 0., 1., m.wHat},
+                               {m.hHat - m.uHat * aHat, ek, m.vHat, m.wHat, m.hHat + m.uHat * aHat}};
+      double Dh[5];
+      Dh[0] = 0.5 * fabs(m.uHat - aHat) * m.rhoHat / kappa;
+      Dh[1] = fabs(m.uHat) * (kappaM1 / kappa) * m.rhoHat;
+      Dh[2] = fabs(m.uHat) * m.pHat;
+      Dh[3] = Dh[2];
+      Dh[4] = 0.5 * fabs(m.uHat + aHat) * m.rhoHat / kappa;
+      double t[5];
+#pragma unroll
+      for (int c = 0; c < 5; ++c)
+        t[c] = Dh[c] * (Rh[0][c] * vJ[0] + Rh[1][c] * vJ[1] + Rh[2][c] * vJ[2] + Rh[3][c] * vJ[3] + Rh[4][c] * vJ[4]);
+      split_surface_flux(q.splitType, L, R, F, q.kappa);
+#pragma unroll
+      for (int r = 0; r < 5; ++r)
+        F[r] = F[r] - 0.5 * (Rh[r][0] * t[0] + Rh[r][1] * t[1] + Rh[r][2] * t[2] + Rh[r][3] * t[3] + Rh[r][4] * t[4]);
     } break;
     default: {  // HLL riemann.f90:1067-1113, HLLE :1119-1164, HLLEM :1170-1228
       const RoeMean m = roe_average(q, L, R);
@@ -438,7 +622,7 @@ __device__ __forceinline__ void riemann_solver(const Eqn& q, int solver, const E
 }
 
 // riemann.f90:360-440 Riemann_Point: rotate into (n,t1,t2), solve, rotate back.  U_*: cons, P_*: prim of the traces.
-__device__ __forceinline__ void riemann_point(const Eqn& q, int solver, const double* U_L, const double* U_R, const double* P_L,
+FX_HD void riemann_point(const Eqn& q, int solver, const double* U_L, const double* U_R, const double* P_L,
                                               const double* P_R, const double* nv, const double* t1, const double* t2, double* FOut) {
   Ext L, R;
   L.rho = U_L[DENS];
@@ -472,7 +656,7 @@ __device__ __forceinline__ void riemann_point(const Eqn& q, int solver, const do
 
 // ---- boundary conditions: idealgas/exactfunc.f90, idealgas/getboundaryflux.f90 -------------------------------------------------
 // exactfunc.f90:225-362 ExactFunc, cases 1 (constant RefState) and 4 (oblique sine wave)
-__device__ __forceinline__ void exact_func(const Eqn& q, const BCData& bc, double t, const double* x, double* cons) {
+FX_HD void exact_func(const Eqn& q, const BCData& bc, double t, const double* x, double* cons) {
   if (bc.iniExactFunc == 4) {
     const double Omega = 3.14159265358979323846 * bc.iniFrequency, a = bc.advVel0 * 2. * 3.14159265358979323846;
     const double r = 2. + bc.iniAmplitude * sin(Omega * (x[0] + x[1] + x[2]) - a * t);
@@ -484,7 +668,7 @@ __device__ __forceinline__ void exact_func(const Eqn& q, const BCData& bc, doubl
 }
 
 // eos.f90:561-583 PRESSURE_RIEMANN (state in the face-normal system)
-__device__ __forceinline__ double pressure_riemann(const Eqn& q, const double* P) {
+FX_HD double pressure_riemann(const Eqn& q, const double* P) {
   const double kappaFac = 2. * q.kappa * q.sKappaM1, sKappaP1 = 1. / (q.kappa + 1.);
   if (P[VEL1] <= 0.) return P[PRES] * pow(fmax(0.0001, (1. + 0.5 * q.kappaM1 * P[VEL1] / sqrt(q.kappa * P[PRES] / P[DENS]))), kappaFac);
   const double ar = 2. * sKappaP1 / P[DENS], br = q.kappaM1 * sKappaP1 * P[PRES];
@@ -492,7 +676,7 @@ __device__ __forceinline__ double pressure_riemann(const Eqn& q, const double* P
 }
 
 // getboundaryflux.f90:224-470 GetBoundaryState for one face node: types 2, 3, 4, 9
-__device__ __forceinline__ void boundary_state(const Eqn& q, const BCData& bc, int type, int state, double t, const double* Pm,
+FX_HD void boundary_state(const Eqn& q, const BCData& bc, int type, int state, double t, const double* Pm,
                                                const double* nv, const double* t1, const double* t2, const double* xf, double* Pb) {
   if (type == 2) {
     if (state == 0) {

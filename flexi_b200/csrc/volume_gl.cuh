@@ -120,17 +120,17 @@ struct PiPair {
   }
 };
 
-// generic two-point flux for SD / DU / KG in reference order; a[] = (rho,u,v,w,p,x5) with x5 = rhoE (SD,DU) or E (KG)
+// generic two-point flux for SD / MO / DU / KG / CH / IR in reference order; a[] = (rho,u,v,w,p,x5) with x5 = rhoE or E (KG)
 template <int STYPE>
 __device__ __forceinline__ void split_pair_generic(const double* a, const double* Ma, double br, double bu, double bv, double bw, double bp,
-                                                   double bx, double b0, double b1, double b2, double* F) {
+                                                   double bx, double b0, double b1, double b2, double* F, const double kappa) {
   Node na{a[0], a[1], a[2], a[3], a[4], a[5]}, nb{br, bu, bv, bw, bp, bx};
   if (STYPE == FLEXI_SPLITDG_KG) {  // Node.E is read as rho*E by split_volume_flux: rebuild it (x5 holds E = rhoE/rho)
     na.E = a[5] * a[0];
     nb.E = bx * br;
   }
   const double Mb[3] = {b0, b1, b2};
-  split_volume_flux<STYPE>(na, nb, Ma, Mb, F);
+  split_volume_flux<STYPE>(na, nb, Ma, Mb, F, kappa);
 }
 
 template <int NP, int KPT, bool SPLIT, int STYPE, bool PARA, int NVL, int LIFT>
@@ -516,7 +516,7 @@ __global__ void __launch_bounds__(VolGLCfg<NP, KPT, SPLIT, PARA>::NT, VolGLCfg<N
             double Fl[5];
             split_pair_generic<STYPE>(a[c], Ma, sP[nl], sP[D::NP3 + nl], sP[2 * D::NP3 + nl], sP[3 * D::NP3 + nl], sP[4 * D::NP3 + nl],
                                       sP[5 * D::NP3 + nl], sM[(3 * dir + 0) * D::NP3 + nl], sM[(3 * dir + 1) * D::NP3 + nl],
-                                      sM[(3 * dir + 2) * D::NP3 + nl], Fl);
+                                      sM[(3 * dir + 2) * D::NP3 + nl], Fl, q.kappa);
 #pragma unroll
             for (int v = 0; v < 5; ++v) ut[c][v] = ut[c][v] + dl * Fl[v];
           }
@@ -543,7 +543,7 @@ __global__ void __launch_bounds__(VolGLCfg<NP, KPT, SPLIT, PARA>::NT, VolGLCfg<N
           pr.add(acc[c2], d21);
         } else {
           double Fl[5];
-          split_pair_generic<STYPE>(a[c], Mz[c], a[c2][0], a[c2][1], a[c2][2], a[c2][3], a[c2][4], a[c2][5], Mz[c2][0], Mz[c2][1], Mz[c2][2], Fl);
+          split_pair_generic<STYPE>(a[c], Mz[c], a[c2][0], a[c2][1], a[c2][2], a[c2][3], a[c2][4], a[c2][5], Mz[c2][0], Mz[c2][1], Mz[c2][2], Fl, q.kappa);
 #pragma unroll
           for (int v = 0; v < 5; ++v) {
             ut[c][v] = ut[c][v] + d12 * Fl[v];
@@ -569,7 +569,7 @@ __global__ void __launch_bounds__(VolGLCfg<NP, KPT, SPLIT, PARA>::NT, VolGLCfg<N
             pr.add(acc[c], dl);
           } else {
             double Fl[5];
-            split_pair_generic<STYPE>(a[c], Mz[c], br, bu, bv, bw, bp, bx, b0, b1, b2, Fl);
+            split_pair_generic<STYPE>(a[c], Mz[c], br, bu, bv, bw, bp, bx, b0, b1, b2, Fl, q.kappa);
 #pragma unroll
             for (int v = 0; v < 5; ++v) ut[c][v] = ut[c][v] + dl * Fl[v];
           }

@@ -99,7 +99,7 @@ __device__ __forceinline__ int gl2_gn(int dir, int p, int r0, int r1) {
 template <int NP, int STYPE, bool PARA>
 __device__ __forceinline__ void gl2_pair_sweep(const GL2Basis<NP>& B, const double* __restrict__ sP, const double* __restrict__ sWd,
                                                const double* __restrict__ gMd, const int (&sa)[NP], const int (&gn)[NP],
-                                               double (&ut)[NP / 2][5]) {
+                                               double (&ut)[NP / 2][5], const double kappa) {
   constexpr int HALF = NP / 2, PL = NP * NP * NP;
   constexpr bool PI = (STYPE == FLEXI_SPLITDG_PI);
   constexpr int PX = PARA ? 6 : 5;
@@ -182,7 +182,7 @@ __device__ __forceinline__ void gl2_pair_sweep(const GL2Basis<NP>& B, const doub
         }
       } else {
         double Fl[5];
-        split_pair_generic<STYPE>(a[c], Mo[c], a[c2][0], a[c2][1], a[c2][2], a[c2][3], a[c2][4], a[c2][5], Mo[c2][0], Mo[c2][1], Mo[c2][2], Fl);
+        split_pair_generic<STYPE>(a[c], Mo[c], a[c2][0], a[c2][1], a[c2][2], a[c2][3], a[c2][4], a[c2][5], Mo[c2][0], Mo[c2][1], Mo[c2][2], Fl, kappa);
 #pragma unroll
         for (int v = 0; v < 5; ++v) {
           ut[c][v] = ut[c][v] + d12 * Fl[v];
@@ -214,7 +214,7 @@ __device__ __forceinline__ void gl2_pair_sweep(const GL2Basis<NP>& B, const doub
         ut[c][3] += dp * mm2;
       } else {
         double Fl[5];
-        split_pair_generic<STYPE>(a[c], Mo[c], br, bu, bv, bw, bp, bx, Mp[c2][0], Mp[c2][1], Mp[c2][2], Fl);
+        split_pair_generic<STYPE>(a[c], Mo[c], br, bu, bv, bw, bp, bx, Mp[c2][0], Mp[c2][1], Mp[c2][2], Fl, kappa);
 #pragma unroll
         for (int v = 0; v < 5; ++v) ut[c][v] = ut[c][v] + dl * Fl[v];
       }
@@ -580,7 +580,7 @@ __global__ void __launch_bounds__(VolGL2Cfg<NP, PARA>::NT, VolGL2Cfg<NP, PARA>::
       gn[p] = gl2_gn<NP>(dir, gl2_ap<NP>(hb, p), r0, r1);
     }
     double ut[HALF][5];
-    gl2_pair_sweep<NP, STYPE, PARA>(B, sP, sW + dir * 4 * PL, gM + dir * 3 * D::NP3, sa, gn, ut);
+    gl2_pair_sweep<NP, STYPE, PARA>(B, sP, sW + dir * 4 * PL, gM + dir * 3 * D::NP3, sa, gn, ut, A.q.kappa);
     if (it < 2) {
 #pragma unroll
       for (int c = 0; c < HALF; ++c)

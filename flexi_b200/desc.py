@@ -8,8 +8,9 @@ import numpy as np
 
 ABI_VERSION = 1
 NODETYPE = {"gauss": 1, "gauss-lobatto": 2}
-RIEMANN = {"same": -1, "lf": 1, "hllc": 2, "roe": 3, "roel2": 32, "roeentropyfix": 33, "hll": 4, "hlle": 5, "hllem": 6}
-SPLITDG = {"sd": 0, "mo": 1, "du": 2, "kg": 3, "pi": 4}
+RIEMANN = {"same": -1, "lf": 1, "hllc": 2, "roe": 3, "roel2": 32, "roeentropyfix": 33, "hll": 4, "hlle": 5, "hllem": 6,
+           "average": 0, "ch": 7, "ir": 8}  # the last three: SPLIT_DG builds only (riemann.f90:54-58)
+SPLITDG = {"sd": 0, "mo": 1, "du": 2, "kg": 3, "pi": 4, "ch": 5, "ir": 6}
 
 _PD = C.POINTER(C.c_double)
 _PI = C.POINTER(C.c_int32)

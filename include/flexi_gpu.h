@@ -46,6 +46,10 @@ extern "C" {
 #define FLEXI_RIEMANN_HLL 4
 #define FLEXI_RIEMANN_HLLE 5
 #define FLEXI_RIEMANN_HLLEM 6
+/* SPLIT_DG only (riemann.f90:54-58): bare two-point surface flux, Chandrashekar and Ismail-Roe dissipation */
+#define FLEXI_RIEMANN_AVERAGE 0
+#define FLEXI_RIEMANN_CH 7
+#define FLEXI_RIEMANN_IR 8
 
 /* PRM_SPLITDG_* (equations/navierstokes/splitflux.f90:63-69) */
 #define FLEXI_SPLITDG_SD 0
@@ -53,6 +57,8 @@ extern "C" {
 #define FLEXI_SPLITDG_DU 2
 #define FLEXI_SPLITDG_KG 3
 #define FLEXI_SPLITDG_PI 4
+#define FLEXI_SPLITDG_CH 5
+#define FLEXI_SPLITDG_IR 6 /* not a selectable SplitDG string in the reference (splitflux.f90:96-102), InitSplitDG(SplitDG_in) only */
 
 /* error codes */
 #define FLEXI_GPU_OK 0

@@ -175,8 +175,21 @@ static inline void eval_euler_flux1d_fast(const double* U, double* F) {
 /* ------------------------------------------------------------------------------------------------------------------ */
 /* split fluxes: splitflux.f90                                                                                        */
 /* ------------------------------------------------------------------------------------------------------------------ */
+/* splitflux.f90:994-1020 GetLogMean (Ismail & Roe): (U_L+U_R)/g with the series of ln(chi)/f around chi = 1 */
+static inline double get_log_mean(double U_L, double U_R) {
+  const double sqrt_epsilon = 0.1;
+  double chi = U_L / U_R, f = (chi - 1.) / (chi + 1.), g;
+  if (fabs(f) < sqrt_epsilon) {
+    double u = f * f;
+    g = 2. + 2. / 3. * u + 0.4 * u * u + 2. / 7. * u * u * u;
+  } else {
+    g = log(chi) / f;
+  }
+  return (U_L + U_R) / g;
+}
+
 /* physical-space two-point fluxes fT,gT,hT of the chosen split form (factor 2 folded in, splitflux.f90:21-22) */
-static void split_volume_flux(int type, const double* UR, const double* PR, const double* U, const double* P, const double* MR,
+static void split_volume_flux(const oracle* o, int type, const double* UR, const double* PR, const double* U, const double* P, const double* MR,
                               const double* M, double* Flux) {
   double fT[5], gT[5], hT[5];
   switch (type) {
@@ -245,6 +258,86 @@ static void split_volume_flux(int type, const double* UR, const double* PR, cons
         hT[ENER] = 0.25 * sr * sw * (HRef + H);
       }
     } break;
+    case FLEXI_SPLITDG_MO: { /* splitflux.f90:471-552 (Morinishi) */
+      double rhoepRef = UR[ENER] - 0.5 * UR[DENS] * (PR[VEL1] * PR[VEL1] + PR[VEL2] * PR[VEL2] + PR[VEL3] * PR[VEL3]) + PR[PRES];
+      double rhoep = U[ENER] - 0.5 * U[DENS] * (P[VEL1] * P[VEL1] + P[VEL2] * P[VEL2] + P[VEL3] * P[VEL3]) + P[PRES];
+      double* T[3] = {fT, gT, hT};
+      for (int d = 0; d < 3; ++d) { /* direction d: mass flux rho*v_d */
+        double mR = UR[MOM1 + d], m = U[MOM1 + d];
+        double* t = T[d];
+        t[DENS] = (mR + m);
+        for (int c = 0; c < 3; ++c) t[MOM1 + c] = 0.5 * (mR + m) * (PR[VEL1 + c] + P[VEL1 + c]);
+        t[MOM1 + d] = t[MOM1 + d] + (PR[PRES] + P[PRES]);
+        t[ENER] = (rhoepRef * PR[VEL1 + d] + rhoep * P[VEL1 + d]) +
+                  0.5 * (mR * PR[VEL1] + m * P[VEL1]) * (PR[VEL1] + P[VEL1]) +
+                  0.5 * (mR * PR[VEL2] + m * P[VEL2]) * (PR[VEL2] + P[VEL2]) +
+                  0.5 * (mR * PR[VEL3] + m * P[VEL3]) * (PR[VEL3] + P[VEL3]) -
+                  0.5 * (mR * PR[VEL1] * PR[VEL1] + m * P[VEL1] * P[VEL1]) -
+                  0.5 * (mR * PR[VEL2] * PR[VEL2] + m * P[VEL2] * P[VEL2]) -
+                  0.5 * (mR * PR[VEL3] * PR[VEL3] + m * P[VEL3] * P[VEL3]);
+      }
+    } break;
+    case FLEXI_SPLITDG_CH: { /* splitflux.f90:711-795 (Chandrashekar): entropy conserving + kinetic energy preserving */
+      double uMean = 0.5 * (PR[VEL1] + P[VEL1]), vMean = 0.5 * (PR[VEL2] + P[VEL2]), wMean = 0.5 * (PR[VEL3] + P[VEL3]);
+      double betaRef = 0.5 * UR[DENS] / PR[PRES], beta = 0.5 * U[DENS] / P[PRES];
+      double rhoLogMean = get_log_mean(UR[DENS], U[DENS]);
+      double betaLogMean = get_log_mean(betaRef, beta);
+      double pHatMean = 0.5 * (UR[DENS] + U[DENS]) / (betaRef + beta);
+      double HMean = 0.5 * o->sKappaM1 / betaLogMean + pHatMean / rhoLogMean +
+                     0.5 * (PR[VEL1] * P[VEL1] + PR[VEL2] * P[VEL2] + PR[VEL3] * P[VEL3]);
+      fT[DENS] = rhoLogMean * uMean;
+      fT[MOM1] = rhoLogMean * uMean * uMean + pHatMean;
+      fT[MOM2] = rhoLogMean * uMean * vMean;
+      fT[MOM3] = rhoLogMean * uMean * wMean;
+      fT[ENER] = rhoLogMean * HMean * uMean;
+      gT[DENS] = rhoLogMean * vMean;
+      gT[MOM1] = rhoLogMean * vMean * uMean;
+      gT[MOM2] = rhoLogMean * vMean * vMean + pHatMean;
+      gT[MOM3] = rhoLogMean * vMean * wMean;
+      gT[ENER] = rhoLogMean * HMean * vMean;
+      hT[DENS] = rhoLogMean * wMean;
+      hT[MOM1] = rhoLogMean * wMean * uMean;
+      hT[MOM2] = rhoLogMean * wMean * vMean;
+      hT[MOM3] = rhoLogMean * wMean * wMean + pHatMean;
+      hT[ENER] = rhoLogMean * HMean * wMean;
+      for (int v = 0; v < 5; ++v) /* :794 the factor 2 is applied after the metric contraction */
+        Flux[v] = (0.5 * (MR[0] + M[0]) * fT[v] + 0.5 * (MR[2] + M[2]) * hT[v] + 0.5 * (MR[1] + M[1]) * gT[v]) * 2.;
+      return;
+    }
+    case FLEXI_SPLITDG_IR: { /* splitflux.f90:857-927 (Ismail & Roe).  As in the reference: NO factor 2 in this volume flux (every
+                                other formulation carries it, :21-22), and 'ir' is not a selectable SplitDG string (:96-102) -- it is
+                                reachable through InitSplitDG(SplitDG_in) only.  Restated as it stands. */
+      const double kappa = o->d.kappa, kappaM1 = o->kappaM1, kappaP1 = kappa + 1.;
+      double z[5], zRef[5];
+      z[0] = sqrt(U[DENS] / P[PRES]);
+      z[1] = z[0] * P[VEL1];
+      z[2] = z[0] * P[VEL2];
+      z[3] = z[0] * P[VEL3];
+      z[4] = sqrt(U[DENS] * P[PRES]);
+      zRef[0] = sqrt(UR[DENS] / PR[PRES]);
+      zRef[1] = zRef[0] * PR[VEL1];
+      zRef[2] = zRef[0] * PR[VEL2];
+      zRef[3] = zRef[0] * PR[VEL3];
+      zRef[4] = sqrt(UR[DENS] * PR[PRES]);
+      double z1LogMean = get_log_mean(z[0], zRef[0]);
+      double z5LogMean = get_log_mean(z[4], zRef[4]);
+      double z1Mean = 0.5 * (z[0] + zRef[0]);
+      double rhoHat = z1Mean * z5LogMean;
+      double pHat = 0.5 * (z[4] + zRef[4]) / z1Mean;
+      double p2Hat = 1. / (2. * kappa) * (kappaP1 * z5LogMean / z1LogMean + kappaM1 * pHat);
+      double uHat = 0.5 * (z[1] + zRef[1]) / z1Mean;
+      double vHat = 0.5 * (z[2] + zRef[2]) / z1Mean;
+      double wHat = 0.5 * (z[3] + zRef[3]) / z1Mean;
+      double hHat = kappa * p2Hat / (rhoHat * kappaM1) + 0.5 * (uHat * uHat + vHat * vHat + wHat * wHat);
+      double Meff[3] = {0.5 * (MR[0] + M[0]), 0.5 * (MR[1] + M[1]), 0.5 * (MR[2] + M[2])};
+      double qeff = rhoHat * (uHat * Meff[0] + vHat * Meff[1] + wHat * Meff[2]);
+      Flux[0] = qeff;
+      Flux[1] = qeff * uHat + pHat * Meff[0];
+      Flux[2] = qeff * vHat + pHat * Meff[1];
+      Flux[3] = qeff * wHat + pHat * Meff[2];
+      Flux[4] = qeff * hHat;
+      return;
+    }
     default:
       fprintf(stderr, "oracle: SplitDG formulation %d not restated\n", type);
       abort();
@@ -253,7 +346,7 @@ static void split_volume_flux(int type, const double* UR, const double* PR, cons
     Flux[v] = 0.5 * (MR[0] + M[0]) * fT[v] + 0.5 * (MR[2] + M[2]) * hT[v] + 0.5 * (MR[1] + M[1]) * gT[v];
 }
 
-static void split_surface_flux(int type, const double* L, const double* R, double* F) {
+static void split_surface_flux(const oracle* o, int type, const double* L, const double* R, double* F) {
   switch (type) {
     case FLEXI_SPLITDG_SD: /* splitflux.f90:228-252 */
       F[DENS] = 0.5 * (L[EXT_MOM1] + R[EXT_MOM1]);
@@ -283,6 +376,64 @@ static void split_surface_flux(int type, const double* L, const double* R, doubl
         double H_LL = (L[EXT_ENER] + L[EXT_PRES]) / L[EXT_DENS], H_RR = (R[EXT_ENER] + R[EXT_PRES]) / R[EXT_DENS];
         F[ENER] = 0.125 * sr * (H_LL + H_RR) * su;
       }
+    } break;
+    case FLEXI_SPLITDG_MO: { /* splitflux.f90:558-593 */
+      double rhoep_LL = L[EXT_ENER] - 0.5 * L[EXT_DENS] * (L[EXT_VEL1] * L[EXT_VEL1] + L[EXT_VEL2] * L[EXT_VEL2] + L[EXT_VEL3] * L[EXT_VEL3]) + L[EXT_PRES];
+      double rhoep_RR = R[EXT_ENER] - 0.5 * R[EXT_DENS] * (R[EXT_VEL1] * R[EXT_VEL1] + R[EXT_VEL2] * R[EXT_VEL2] + R[EXT_VEL3] * R[EXT_VEL3]) + R[EXT_PRES];
+      F[DENS] = 0.5 * (L[EXT_MOM1] + R[EXT_MOM1]);
+      F[MOM1] = 0.25 * (L[EXT_MOM1] + R[EXT_MOM1]) * (L[EXT_VEL1] + R[EXT_VEL1]) + 0.5 * (L[EXT_PRES] + R[EXT_PRES]);
+      F[MOM2] = 0.25 * (L[EXT_MOM1] + R[EXT_MOM1]) * (L[EXT_VEL2] + R[EXT_VEL2]);
+      F[MOM3] = 0.25 * (L[EXT_MOM1] + R[EXT_MOM1]) * (L[EXT_VEL3] + R[EXT_VEL3]);
+      F[ENER] = 0.5 * (rhoep_LL * L[EXT_VEL1] + rhoep_RR * R[EXT_VEL1]) +
+                0.25 * (L[EXT_MOM1] * L[EXT_VEL1] + R[EXT_MOM1] * R[EXT_VEL1]) * (L[EXT_VEL1] + R[EXT_VEL1]) +
+                0.25 * (L[EXT_MOM1] * L[EXT_VEL2] + R[EXT_MOM1] * R[EXT_VEL2]) * (L[EXT_VEL2] + R[EXT_VEL2]) +
+                0.25 * (L[EXT_MOM1] * L[EXT_VEL3] + R[EXT_MOM1] * R[EXT_VEL3]) * (L[EXT_VEL3] + R[EXT_VEL3]) -
+                0.25 * (L[EXT_MOM1] * L[EXT_VEL1] * L[EXT_VEL1] + R[EXT_MOM1] * R[EXT_VEL1] * R[EXT_VEL1]) -
+                0.25 * (L[EXT_MOM1] * L[EXT_VEL2] * L[EXT_VEL2] + R[EXT_MOM1] * R[EXT_VEL2] * R[EXT_VEL2]) -
+                0.25 * (L[EXT_MOM1] * L[EXT_VEL3] * L[EXT_VEL3] + R[EXT_MOM1] * R[EXT_VEL3] * R[EXT_VEL3]);
+    } break;
+    case FLEXI_SPLITDG_CH: { /* splitflux.f90:803-852 */
+      double uMean = 0.5 * (L[EXT_VEL1] + R[EXT_VEL1]), vMean = 0.5 * (L[EXT_VEL2] + R[EXT_VEL2]), wMean = 0.5 * (L[EXT_VEL3] + R[EXT_VEL3]);
+      double beta_LL = 0.5 * L[EXT_DENS] / L[EXT_PRES], beta_RR = 0.5 * R[EXT_DENS] / R[EXT_PRES];
+      double rhoLogMean = get_log_mean(L[EXT_DENS], R[EXT_DENS]);
+      double betaLogMean = get_log_mean(beta_LL, beta_RR);
+      double pHatMean = 0.5 * (L[EXT_DENS] + R[EXT_DENS]) / (beta_LL + beta_RR);
+      double HMean = 0.5 * o->sKappaM1 / betaLogMean + pHatMean / rhoLogMean +
+                     0.5 * (L[EXT_VEL1] * R[EXT_VEL1] + L[EXT_VEL2] * R[EXT_VEL2] + L[EXT_VEL3] * R[EXT_VEL3]);
+      F[DENS] = rhoLogMean * uMean;
+      F[MOM1] = F[DENS] * uMean + pHatMean;
+      F[MOM2] = F[DENS] * vMean;
+      F[MOM3] = F[DENS] * wMean;
+      F[ENER] = F[DENS] * HMean;
+    } break;
+    case FLEXI_SPLITDG_IR: { /* splitflux.f90:932-989 */
+      const double kappa = o->d.kappa, kappaM1 = o->kappaM1, kappaP1 = kappa + 1.;
+      double z_LL[5], z_RR[5];
+      z_LL[0] = sqrt(L[EXT_DENS] / L[EXT_PRES]);
+      z_LL[1] = z_LL[0] * L[EXT_VEL1];
+      z_LL[2] = z_LL[0] * L[EXT_VEL2];
+      z_LL[3] = z_LL[0] * L[EXT_VEL3];
+      z_LL[4] = sqrt(L[EXT_DENS] * L[EXT_PRES]);
+      z_RR[0] = sqrt(R[EXT_DENS] / R[EXT_PRES]);
+      z_RR[1] = z_RR[0] * R[EXT_VEL1];
+      z_RR[2] = z_RR[0] * R[EXT_VEL2];
+      z_RR[3] = z_RR[0] * R[EXT_VEL3];
+      z_RR[4] = sqrt(R[EXT_DENS] * R[EXT_PRES]);
+      double z1LogMean = get_log_mean(z_LL[0], z_RR[0]);
+      double z5LogMean = get_log_mean(z_LL[4], z_RR[4]);
+      double z1Mean = 0.5 * (z_LL[0] + z_RR[0]);
+      double rhoHat = z1Mean * z5LogMean;
+      double pHat = 0.5 * (z_LL[4] + z_RR[4]) / z1Mean;
+      double p2Hat = 1. / (2. * kappa) * (kappaP1 * z5LogMean / z1LogMean + kappaM1 * pHat);
+      double uHat = 0.5 * (z_LL[1] + z_RR[1]) / z1Mean;
+      double vHat = 0.5 * (z_LL[2] + z_RR[2]) / z1Mean;
+      double wHat = 0.5 * (z_LL[3] + z_RR[3]) / z1Mean;
+      double hHat = kappa * p2Hat / (rhoHat * kappaM1) + 0.5 * (uHat * uHat + vHat * vHat + wHat * wHat);
+      F[0] = rhoHat * uHat;
+      F[1] = F[0] * uHat + pHat;
+      F[2] = F[0] * vHat;
+      F[3] = F[0] * wHat;
+      F[4] = F[0] * hHat;
     } break;
     default:
       fprintf(stderr, "oracle: SplitDG formulation %d not restated\n", type);
@@ -333,7 +484,7 @@ static void riemann_solver(const oracle* o, int solver, const double* F_L, const
       if (!split) {
         for (int v = 0; v < 5; ++v) F[v] = 0.5 * ((F_L[v] + F_R[v]) - LambdaMax * (R[v] - L[v]));
       } else {
-        split_surface_flux(stype, L, R, F);
+        split_surface_flux(o, stype, L, R, F);
         for (int v = 0; v < 5; ++v) F[v] = F[v] - 0.5 * LambdaMax * (R[v] - L[v]);
       }
     } break;
@@ -386,7 +537,7 @@ static void riemann_solver(const oracle* o, int solver, const double* F_L, const
           F[v] = 0.5 * ((F_L[v] + F_R[v]) - Alpha1 * fabs(a[0]) * r1[v] - Alpha2 * fabs(a[1]) * r2[v] - Alpha3 * fabs(a[2]) * r3[v] -
                         Alpha4 * fabs(a[3]) * r4[v] - Alpha5 * fabs(a[4]) * r5[v]);
       } else {
-        split_surface_flux(stype, L, R, F);
+        split_surface_flux(o, stype, L, R, F);
         for (int v = 0; v < 5; ++v)
           F[v] = F[v] - 0.5 * (Alpha1 * fabs(a[0]) * r1[v] + Alpha2 * fabs(a[1]) * r2[v] + Alpha3 * fabs(a[2]) * r3[v] +
                                Alpha4 * fabs(a[3]) * r4[v] + Alpha5 * fabs(a[4]) * r5[v]);
@@ -423,7 +574,7 @@ static void riemann_solver(const oracle* o, int solver, const double* F_L, const
           F[v] = 0.5 * ((F_L[v] + F_R[v]) - Alpha[0] * a[0] * r1[v] - Alpha[1] * a[1] * r2[v] - Alpha[2] * a[2] * r3[v] -
                         Alpha[3] * a[3] * r4[v] - Alpha[4] * a[4] * r5[v]);
       } else {
-        split_surface_flux(stype, L, R, F);
+        split_surface_flux(o, stype, L, R, F);
         for (int v = 0; v < 5; ++v)
           F[v] = F[v] - 0.5 * (Alpha[0] * a[0] * r1[v] + Alpha[1] * a[1] * r2[v] + Alpha[2] * a[2] * r3[v] + Alpha[3] * a[3] * r4[v] +
                                Alpha[4] * a[4] * r5[v]);
@@ -460,7 +611,82 @@ static void riemann_solver(const oracle* o, int solver, const double* F_L, const
           F[v] = (Ssr * F_L[v] - Ssl * F_R[v] + Ssl * Ssr * (R[v] - L[v] - delta * (r2[v] * A2 + r3[v] * A3 + r4[v] * A4))) / (Ssr - Ssl);
       }
     } break;
+    case FLEXI_RIEMANN_AVERAGE: /* riemann.f90:1236-1253 Riemann_FluxAverage (SPLIT_DG only): the bare two-point surface flux */
+      if (!split) goto unknown;
+      split_surface_flux(o, stype, L, R, F);
+      break;
+    case FLEXI_RIEMANN_CH: { /* riemann.f90:1261-1310 (SPLIT_DG only): kinetic-energy consistent scalar dissipation */
+      if (!split) goto unknown;
+      double LambdaMax = fmax(fabs(R[EXT_VEL1]), fabs(L[EXT_VEL1])) + fmax(speed_of_sound_he(o, L), speed_of_sound_he(o, R));
+      double rhoMean = 0.5 * (L[EXT_DENS] + R[EXT_DENS]);
+      double uMean = 0.5 * (L[EXT_VEL1] + R[EXT_VEL1]), vMean = 0.5 * (L[EXT_VEL2] + R[EXT_VEL2]), wMean = 0.5 * (L[EXT_VEL3] + R[EXT_VEL3]);
+      double beta_LL = 0.5 * L[EXT_DENS] / L[EXT_PRES], beta_RR = 0.5 * R[EXT_DENS] / R[EXT_PRES];
+      double betaLogMean = get_log_mean(beta_LL, beta_RR);
+      split_surface_flux(o, stype, L, R, F);
+      for (int v = 0; v < 4; ++v) F[v] = F[v] - 0.5 * LambdaMax * (R[v] - L[v]);
+      F[ENER] = F[ENER] - 0.5 * LambdaMax * ((R[EXT_DENS] - L[EXT_DENS]) * (0.5 * o->sKappaM1 / betaLogMean +
+                                                 0.5 * (R[EXT_VEL1] * L[EXT_VEL1] + R[EXT_VEL2] * L[EXT_VEL2] + R[EXT_VEL3] * L[EXT_VEL3])) +
+                                             rhoMean * uMean * (R[EXT_VEL1] - L[EXT_VEL1]) + rhoMean * vMean * (R[EXT_VEL2] - L[EXT_VEL2]) +
+                                             rhoMean * wMean * (R[EXT_VEL3] - L[EXT_VEL3]) +
+                                             0.5 * rhoMean * o->sKappaM1 * (1. / beta_RR - 1. / beta_LL));
+    } break;
+    case FLEXI_RIEMANN_IR: { /* riemann.f90:1315-1402 (SPLIT_DG only): entropy-stable matrix dissipation R |Lambda| T R^T [v] */
+      if (!split) goto unknown;
+      const double kappa = o->d.kappa, kappaM1 = o->kappaM1, kappaP1 = kappa + 1.;
+      double sR = log(R[EXT_PRES]) - kappa * log(R[EXT_DENS]), sL = log(L[EXT_PRES]) - kappa * log(L[EXT_DENS]);
+      double rho_pR = R[EXT_DENS] / R[EXT_PRES], rho_pL = L[EXT_DENS] / L[EXT_PRES];
+      double vR[5], vL[5];
+      vR[0] = (kappa - sR) / kappaM1 - 0.5 * rho_pR * (R[EXT_VEL1] * R[EXT_VEL1] + R[EXT_VEL2] * R[EXT_VEL2] + R[EXT_VEL3] * R[EXT_VEL3]);
+      vL[0] = (kappa - sL) / kappaM1 - 0.5 * rho_pL * (L[EXT_VEL1] * L[EXT_VEL1] + L[EXT_VEL2] * L[EXT_VEL2] + L[EXT_VEL3] * L[EXT_VEL3]);
+      vR[1] = rho_pR * R[EXT_VEL1]; vL[1] = rho_pL * L[EXT_VEL1];
+      vR[2] = rho_pR * R[EXT_VEL2]; vL[2] = rho_pL * L[EXT_VEL2];
+      vR[3] = rho_pR * R[EXT_VEL3]; vL[3] = rho_pL * L[EXT_VEL3];
+      vR[4] = -rho_pR;              vL[4] = -rho_pL;
+      double z_LL[5], z_RR[5];
+      z_LL[0] = sqrt(L[EXT_DENS] / L[EXT_PRES]);
+      z_LL[1] = z_LL[0] * L[EXT_VEL1];
+      z_LL[2] = z_LL[0] * L[EXT_VEL2];
+      z_LL[3] = z_LL[0] * L[EXT_VEL3];
+      z_LL[4] = sqrt(L[EXT_DENS] * L[EXT_PRES]);
+      z_RR[0] = sqrt(R[EXT_DENS] / R[EXT_PRES]);
+      z_RR[1] = z_RR[0] * R[EXT_VEL1];
+      z_RR[2] = z_RR[0] * R[EXT_VEL2];
+      z_RR[3] = z_RR[0] * R[EXT_VEL3];
+      z_RR[4] = sqrt(R[EXT_DENS] * R[EXT_PRES]);
+      double z1LogMean = get_log_mean(z_LL[0], z_RR[0]);
+      double z5LogMean = get_log_mean(z_LL[4], z_RR[4]);
+      double z1Mean = 0.5 * (z_LL[0] + z_RR[0]);
+      double rhoHat = z1Mean * z5LogMean;
+      double uHat = 0.5 * (z_LL[1] + z_RR[1]) / z1Mean;
+      double vHat = 0.5 * (z_LL[2] + z_RR[2]) / z1Mean;
+      double wHat = 0.5 * (z_LL[3] + z_RR[3]) / z1Mean;
+      double pHat = 0.5 * (z_LL[4] + z_RR[4]) / z1Mean;
+      double p2Hat = 1. / (2. * kappa) * (kappaP1 * z5LogMean / z1LogMean + kappaM1 * pHat);
+      double aHat = sqrt(kappa * p2Hat / rhoHat);
+      double hHat = kappa * p2Hat / (rhoHat * kappaM1) + 0.5 * (uHat * uHat + vHat * vHat + wHat * wHat);
+      double RHat[5][5] = {{1., 1., 0., 0., 1.},
+                           {uHat - aHat, uHat, 0., 0., uHat + aHat},
+                           {vHat, vHat, 1., 0., vHat},
+                           {wHat, wHat, 0., 1., wHat},
+                           {hHat - uHat * aHat, 0.5 * (uHat * uHat + vHat * vHat + wHat * wHat), vHat, wHat, hHat + uHat * aHat}};
+      double DHat[5];
+      DHat[0] = 0.5 * fabs(uHat - aHat) * rhoHat / kappa;
+      DHat[1] = fabs(uHat) * (kappaM1 / kappa) * rhoHat;
+      DHat[2] = fabs(uHat) * pHat;
+      DHat[3] = DHat[2];
+      DHat[4] = 0.5 * fabs(uHat + aHat) * rhoHat / kappa;
+      double vJump[5], diss[5], out[5];
+      for (int v = 0; v < 5; ++v) vJump[v] = vR[v] - vL[v];
+      for (int c = 0; c < 5; ++c) /* R^T [v]: RHat(r,:)*vJump(r) summed over rows r */
+        diss[c] = RHat[0][c] * vJump[0] + RHat[1][c] * vJump[1] + RHat[2][c] * vJump[2] + RHat[3][c] * vJump[3] + RHat[4][c] * vJump[4];
+      for (int c = 0; c < 5; ++c) diss[c] = DHat[c] * diss[c];
+      for (int r = 0; r < 5; ++r)
+        out[r] = RHat[r][0] * diss[0] + RHat[r][1] * diss[1] + RHat[r][2] * diss[2] + RHat[r][3] * diss[3] + RHat[r][4] * diss[4];
+      split_surface_flux(o, stype, L, R, F);
+      for (int v = 0; v < 5; ++v) F[v] = F[v] - 0.5 * out[v];
+    } break;
     default:
+    unknown:
       fprintf(stderr, "oracle: Riemann solver %d not restated\n", solver);
       abort();
   }
@@ -729,7 +955,7 @@ static void surf_int_split_gauss(const oracle* o, const double* Flux_master, con
           double FluxB_sum[NVAR] = {0., 0., 0., 0., 0.};
           for (int l = 0; l < np; ++l) {
             const int i = idx == 1 ? l : a, j = idx == 1 ? a : (idx == 2 ? l : b), k = idx == 3 ? l : b;
-            split_volume_flux(st, &VOL(o->U, NVAR, 0, i, j, k, e), &VOL(o->UPrim, NPRIM, 0, i, j, k, e), &SID(Uf, NVAR, 0, p, q, s),
+            split_volume_flux(o, st, &VOL(o->U, NVAR, 0, i, j, k, e), &VOL(o->UPrim, NPRIM, 0, i, j, k, e), &SID(Uf, NVAR, 0, p, q, s),
                               &SID(Pf, NPRIM, 0, p, q, s), &VOL(Met, 3, 0, i, j, k, e), Jv, FluxB + (size_t)l * NVAR);
             for (int v = 0; v < NVAR; ++v) FluxB_sum[v] = FluxB_sum[v] + FluxB[(size_t)l * NVAR + v] * Leg[l];
           }
@@ -958,7 +1184,7 @@ static void volint_split_form(oracle* o) {
         for (int i = 0; i < np; ++i) {
           double Flux[5];
           for (int l = i + 1; l <= N; ++l) {
-            split_volume_flux(st, &VOL(o->U, NVAR, 0, i, j, k, e), &VOL(o->UPrim, NPRIM, 0, i, j, k, e), &VOL(o->U, NVAR, 0, l, j, k, e),
+            split_volume_flux(o, st, &VOL(o->U, NVAR, 0, i, j, k, e), &VOL(o->UPrim, NPRIM, 0, i, j, k, e), &VOL(o->U, NVAR, 0, l, j, k, e),
                               &VOL(o->UPrim, NPRIM, 0, l, j, k, e), &VOL(o->d.Metrics_fTilde, 3, 0, i, j, k, e),
                               &VOL(o->d.Metrics_fTilde, 3, 0, l, j, k, e), Flux);
             for (int v = 0; v < 5; ++v) {
@@ -972,7 +1198,7 @@ static void volint_split_form(oracle* o) {
               }
           }
           for (int l = j + 1; l <= N; ++l) {
-            split_volume_flux(st, &VOL(o->U, NVAR, 0, i, j, k, e), &VOL(o->UPrim, NPRIM, 0, i, j, k, e), &VOL(o->U, NVAR, 0, i, l, k, e),
+            split_volume_flux(o, st, &VOL(o->U, NVAR, 0, i, j, k, e), &VOL(o->UPrim, NPRIM, 0, i, j, k, e), &VOL(o->U, NVAR, 0, i, l, k, e),
                               &VOL(o->UPrim, NPRIM, 0, i, l, k, e), &VOL(o->d.Metrics_gTilde, 3, 0, i, j, k, e),
                               &VOL(o->d.Metrics_gTilde, 3, 0, i, l, k, e), Flux);
             for (int v = 0; v < 5; ++v) {
@@ -986,7 +1212,7 @@ static void volint_split_form(oracle* o) {
               }
           }
           for (int l = k + 1; l <= N; ++l) {
-            split_volume_flux(st, &VOL(o->U, NVAR, 0, i, j, k, e), &VOL(o->UPrim, NPRIM, 0, i, j, k, e), &VOL(o->U, NVAR, 0, i, j, l, e),
+            split_volume_flux(o, st, &VOL(o->U, NVAR, 0, i, j, k, e), &VOL(o->UPrim, NPRIM, 0, i, j, k, e), &VOL(o->U, NVAR, 0, i, j, l, e),
                               &VOL(o->UPrim, NPRIM, 0, i, j, l, e), &VOL(o->d.Metrics_hTilde, 3, 0, i, j, k, e),
                               &VOL(o->d.Metrics_hTilde, 3, 0, i, j, l, e), Flux);
             for (int v = 0; v < 5; ++v) {
@@ -1804,7 +2030,7 @@ void oracle_split_volume_flux(oracle* o, int type, const double* URef, const dou
   double PR[6], P[6];
   cons_to_prim(o, PR, URef);
   cons_to_prim(o, P, U);
-  split_volume_flux(type, URef, PR, U, P, MRef, M, Flux);
+  split_volume_flux(o, type, URef, PR, U, P, MRef, M, Flux);
 }
 void oracle_eval_flux3d(oracle* o, const double* U, double* f, double* g, double* h) {
   double P[6];

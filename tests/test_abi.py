@@ -61,3 +61,32 @@ def test_unsupported_options_are_refused(lib):
     r.desc.doWeakLifting = 1
     h = C.c_void_p()
     assert lib.flexi_gpu_init(C.byref(r.desc), C.byref(h)) == -4
+
+
+@pytest.mark.parametrize("riemann", ["hll", "hlle", "hllem", "hllc"])
+def test_split_dg_rejects_hll_family(lib, riemann):
+    """SPLIT_DG builds do not offer the HLL family (riemann.f90:204-246): flexi_gpu_init refuses the descriptor before it touches
+    the device, as the reference's CollectiveStop('Riemann solver not defined!') does."""
+    from flexi_b200.gpu import FlexiGpu, FlexiGpuError
+    eqn = dict(parabolic=False, split_dg=True, split_dg_type="pi", riemann=riemann)
+    r = build_case(tgv_box(2), 3, B.NODE_GAUSS_LOBATTO, eqn)[0]
+    with pytest.raises(FlexiGpuError, match="not selectable with SPLIT_DG"):
+        FlexiGpu(r)
+
+
+@pytest.mark.parametrize("riemann", ["average", "ch", "ir"])
+def test_split_only_solvers_rejected_without_split_dg(lib, riemann):
+    """Riemann_FluxAverage / _CH / _IR exist in SPLIT_DG builds only (riemann.f90:54-58,211-220)."""
+    from flexi_b200.gpu import FlexiGpu, FlexiGpuError
+    r = build_case(tgv_box(2), 3, B.NODE_GAUSS_LOBATTO, dict(parabolic=False, riemann=riemann))[0]
+    with pytest.raises(FlexiGpuError, match="unknown Riemann solver"):
+        FlexiGpu(r)
+
+
+def test_undefined_split_formulation_is_rejected(lib):
+    """splitflux.f90:150-152: 'SplitDG formulation not defined!'"""
+    from flexi_b200.gpu import FlexiGpu, FlexiGpuError
+    r = build_case(tgv_box(2), 3, B.NODE_GAUSS_LOBATTO, dict(parabolic=False, split_dg=True, split_dg_type="pi", riemann="lf"))[0]
+    r.desc.splitDGType = 7
+    with pytest.raises(FlexiGpuError, match="SplitDG formulation not defined"):
+        FlexiGpu(r)
