@@ -34,6 +34,10 @@ CASES = {
                                                 ref_state_prim=[(1.0, 0.3, 0.0, 0.0, 0.71428571), (1.0, 0.0, 0.0, 0.0, 0.9)])),
 }
 CASES["splitG"] = (4, B.NODE_GAUSS, dict(parabolic=True, split_dg=True, split_dg_type="pi", riemann="lf", mu0=1e-2))  # PP_EntropyVars=1
+# entropy-conserving CH formulation with its own dissipation on inner, MPI and boundary sides (RiemannBC = same)
+CASES["splitCH"] = (5, B.NODE_GAUSS_LOBATTO, dict(parabolic=True, lifting=1, riemann="ch", mu0=1e-2, split_dg=True, split_dg_type="ch",
+                                                  boundary_type=[(4, 2, 0), (9, 0, 0), (2, 1, 0)],
+                                                  ref_state_prim=[(1.0, 0.3, 0.0, 0.0, 0.71428571), (1.0, 0.0, 0.0, 0.0, 0.9)]))
 WALL_BC = {(1, -1): 1, (1, 1): 2, (0, -1): 3, (0, 1): 3}  # walls in y, far field in x, periodic in z
 
 

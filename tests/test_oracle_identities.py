@@ -250,7 +250,7 @@ def test_weak_equals_split_sd_on_lgl_euler():
 
 
 @pytest.mark.parametrize("nranks,partition,blocks", [(2, "linear", None), (3, "linear", None), (4, "block", (2, 2, 1))])
-@pytest.mark.parametrize("node,eqn", [CONFIGS[0], CONFIGS[3]])
+@pytest.mark.parametrize("node,eqn", [CONFIGS[0], CONFIGS[3], CONFIGS[8]])
 def test_partition_invariance(node, eqn, nranks, partition, blocks):
     """(7) 1-rank vs k-rank results agree to round-off (what reggie's MPI=1,2 runs assert with one reference file)."""
     N = 3

@@ -74,3 +74,14 @@ def test_split_formulation_matches_oracle(N, node, eqn):
     finally:
         g.close()
         w.close()
+
+
+@pytest.mark.parametrize("N,stype,riemann,lifting,wall", [(5, "ch", "ch", 1, 3), (7, "ch", "ir", 1, 3), (5, "ch", "ir", 2, 4), (4, "mo", "average", 1, 3)])
+def test_split_formulations_with_walls_and_farfield(N, stype, riemann, lifting, wall):
+    """RiemannBC = same: the SPLIT_DG-only solvers also serve the Dirichlet far-field sides (getboundaryflux.f90:561-578)."""
+    from test_gpu_bc_br2 import REF, check, wall_farfield_box
+    eqn = dict(parabolic=True, lifting=lifting, riemann=riemann, mu0=1e-2, eta_br2=2.0, eta_br2_wall=3.0, split_dg=True,
+               split_dg_type=stype, boundary_type=[(wall, 2, 0), (9, 0, 0), (2, 1, 0)], ref_state_prim=[REF, (1.0, 0.0, 0.0, 0.0, 0.9)])
+    ranks = build_case(wall_farfield_box(), N, GL, eqn)
+    r = ranks[0]
+    check(ranks, r.eqn.smooth_state(r.mesh.Elem_xGP, length=2.0))
