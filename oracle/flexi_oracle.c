@@ -2037,4 +2037,13 @@ void oracle_eval_flux3d(oracle* o, const double* U, double* f, double* g, double
   cons_to_prim(o, P, U);
   eval_flux3d(U, P, f, g, h);
 }
+/* gx,gy,gz in the oracle's lifting-variable layout (nVarLifting entries); f,g,h full 5-vectors (row DENS = 0) */
+void oracle_eval_diff_flux3d(oracle* o, const double* UPrim, const double* gx, const double* gy, const double* gz, double* f, double* g,
+                             double* h) {
+  eval_diff_flux3d(o, UPrim, gx, gy, gz, f, g, h);
+}
+void oracle_prim_to_entropy(oracle* o, const double* prim, double* entropy) { prim_to_entropy(o, entropy, prim); }
+void oracle_entropy_to_cons(oracle* o, const double* entropy, double* cons) { entropy_to_cons(o, entropy, cons); }
+int oracle_lv_vel1(oracle* o) { return o->lv_vel1; }
+int oracle_lv_temp(oracle* o) { return o->lv_temp; }
 int oracle_desc_bytes(void) { return (int)sizeof(flexi_gpu_desc); }

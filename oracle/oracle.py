@@ -45,6 +45,11 @@ def _load(fast=False):
     lib.oracle_riemann_point.argtypes = [P, C.c_int, PD, PD, PD, PD, PD, PD]
     lib.oracle_split_volume_flux.argtypes = [P, C.c_int, PD, PD, PD, PD, PD]
     lib.oracle_eval_flux3d.argtypes = [P, PD, PD, PD, PD]
+    lib.oracle_eval_diff_flux3d.argtypes = [P, PD, PD, PD, PD, PD, PD, PD]
+    lib.oracle_prim_to_entropy.argtypes = [P, PD, PD]
+    lib.oracle_entropy_to_cons.argtypes = [P, PD, PD]
+    lib.oracle_lv_vel1.argtypes = [P]
+    lib.oracle_lv_temp.argtypes = [P]
     lib.oracle_set_face_metrics.argtypes = [P, PD, PD]
     lib.oracle_desc_bytes.restype = C.c_int
     _LIBS[name] = lib

@@ -41,6 +41,26 @@ int hp_split_volume_flux(int type, double kappa, double R, const double* URef, c
   }
   return -1;
 }
+// gv = (d/dx, d/dy, d/dz) of (v1, v2, v3, T), 4 entries each; f,g,h = rows MOM1..ENER of the viscous flux
+int hp_eval_diff_flux3d(double kappa, double R, double mu0, double Pr, const double* prim, const double* gx, const double* gy, const double* gz,
+                        double* f, double* g, double* h) {
+  fx::Eqn q = make_eqn(kappa, R, 0, 0, FLEXI_RIEMANN_LF);
+  q.mu0 = mu0;
+  const double cp = R * kappa / (kappa - 1.);  // eos.f90:160-163
+  q.lambda = mu0 * cp / Pr;
+  fx::eval_diff_flux3d(q, prim[1], prim[2], prim[3], gx, gy, gz, f, g, h);
+  return 0;
+}
+int hp_prim_to_entropy(double kappa, double R, const double* prim, double* w) {
+  const fx::Eqn q = make_eqn(kappa, R, 1, 0, FLEXI_RIEMANN_LF);
+  fx::prim_to_entropy(q, prim, w);
+  return 0;
+}
+int hp_entropy_to_cons(double kappa, double R, const double* w, double* cons) {
+  const fx::Eqn q = make_eqn(kappa, R, 1, 0, FLEXI_RIEMANN_LF);
+  fx::entropy_to_cons(q, w, cons);
+  return 0;
+}
 int hp_riemann_point(double kappa, double R, int splitDG, int splitType, int solver, const double* U_L, const double* U_R, const double* nv,
                      const double* t1, const double* t2, double* F) {
   const fx::Eqn q = make_eqn(kappa, R, splitDG, splitType, solver);

@@ -107,3 +107,50 @@ def test_riemann_matches_oracle(hp, solver):
         hp.hp_riemann_point(eq.kappa, eq.R, 0, 0, RIEMANN[solver], _pd(UL), _pd(UR), _pd(n), _pd(t1), _pd(t2), _pd(F))
         assert np.max(np.abs(F - ref)) <= 2e-14 * max(1.0, np.max(np.abs(ref))), (solver, F, ref)
     w.close()
+
+
+@pytest.mark.parametrize("nvl", [5, 4])
+def test_viscous_flux_matches_oracle(hp, nvl):
+    """EvalDiffFlux3D_Point (flux.f90:149-241) of physics.cuh vs the oracle, for both lifting-variable layouts
+    (PP_nVarLifting = 5: full prim set, 4: (v1,v2,v3,T); eos.h:110-131)."""
+    hp.hp_eval_diff_flux3d.argtypes = [C.c_double] * 4 + [PD] * 7
+    ranks = build_case(tgv_box(2), 2, B.NODE_GAUSS, dict(parabolic=True, mu0=1.3e-2, n_var_lifting=nvl))
+    w = O.OracleWorld([(r.desc, r.keep) for r in ranks])
+    o, eq = w.ranks[0], ranks[0].eqn
+    v1, tt = o.lib.oracle_lv_vel1(o.h), o.lib.oracle_lv_temp(o.h)
+    rng = np.random.default_rng(31)
+    for _ in range(30):
+        U = eq.random_state((1,), seed=int(rng.integers(1 << 30)))[0]
+        prim = np.ascontiguousarray(eq.cons_to_prim(U))
+        G = [rng.normal(size=nvl) for _ in range(3)]  # oracle layout
+        ref = [np.zeros(5) for _ in range(3)]
+        o.lib.oracle_eval_diff_flux3d(o.h, _pd(prim), *[_pd(g) for g in G], *[_pd(r) for r in ref])
+        g4 = [np.ascontiguousarray(np.array([g[v1], g[v1 + 1], g[v1 + 2], g[tt]])) for g in G]
+        out = [np.zeros(4) for _ in range(3)]
+        hp.hp_eval_diff_flux3d(eq.kappa, eq.R, eq.mu0, eq.Pr, _pd(prim), *[_pd(g) for g in g4], *[_pd(x) for x in out])
+        for a, b in zip(out, ref):
+            assert b[0] == 0.0
+            assert np.max(np.abs(a - b[1:])) <= 4e-15 * max(1.0, np.max(np.abs(b)))
+    w.close()
+
+
+def test_entropy_variables_match_oracle(hp):
+    """PrimToEntropy / EntropyToCons (eos.f90:401-420,499-531) of physics.cuh vs the oracle (split form on Gauss nodes)."""
+    hp.hp_prim_to_entropy.argtypes = [C.c_double, C.c_double, PD, PD]
+    hp.hp_entropy_to_cons.argtypes = [C.c_double, C.c_double, PD, PD]
+    ranks = build_case(tgv_box(2), 2, B.NODE_GAUSS, dict(parabolic=False))
+    w = O.OracleWorld([(r.desc, r.keep) for r in ranks])
+    o, eq = w.ranks[0], ranks[0].eqn
+    rng = np.random.default_rng(37)
+    for _ in range(30):
+        U = eq.random_state((1,), seed=int(rng.integers(1 << 30)))[0]
+        prim = np.ascontiguousarray(eq.cons_to_prim(U))
+        wa, wb, ca, cb = np.zeros(5), np.zeros(5), np.zeros(5), np.zeros(5)
+        o.lib.oracle_prim_to_entropy(o.h, _pd(prim), _pd(wb))
+        hp.hp_prim_to_entropy(eq.kappa, eq.R, _pd(prim), _pd(wa))
+        assert np.max(np.abs(wa - wb)) <= 4e-15 * np.max(np.abs(wb))
+        o.lib.oracle_entropy_to_cons(o.h, _pd(wb), _pd(cb))
+        hp.hp_entropy_to_cons(eq.kappa, eq.R, _pd(wb), _pd(ca))
+        assert np.max(np.abs(ca - cb)) <= 4e-15 * np.max(np.abs(cb))
+        assert np.max(np.abs(cb - U)) <= 1e-13 * np.max(np.abs(U))
+    w.close()
