@@ -105,6 +105,8 @@ struct flexi_gpu_handle {
   bool bcTablesMissing = false;
   bool entropy = false;             // split form on Gauss nodes: entropy-projected traces + two-point surface correction
   double *JaF = nullptr, *JaS = nullptr;  // Ja_Face / Ja_slave [s][9][NP2]
+  double* filtMat = nullptr;              // OverintegrationMat [out][in] (allocated on first use)
+  bool filtOn = false;                    // OverintegrationType == cutoff
   bool vt = false;             // viscous-trace protocol between k_volume_gl2 and k_flux (kernels.cuh: VolArgs::fvm)
   bool gradTracesFull = true;  // gradU?_master/slave hold the traces of every side (else only of the BC sides)
   double *fvm = nullptr, *fvs = nullptr;
@@ -390,6 +392,7 @@ int launch_update(H* h, const int32_t* list, int n, int mode, double rkA, double
   a.b_dt = b_dt;
   a.entropy = h->entropy ? 1 : 0;
   a.q = h->q;
+  a.filt = h->filtOn ? h->filtMat : nullptr;
   if (n <= 0) return 0;
   Timer tm(h, KC_UPDATE, h->sc);
   CK(h->ops->update(h->gl, a, n, h->sc));
@@ -1180,6 +1183,25 @@ int flexi_gpu_set_face_metrics(flexi_gpu_handle* h, const double* Ja_Face, const
   }
   CKR(upload_aos(h, Ja_Face, h->JaF, 9, h->np2, h->nSides));  // Fortran (dd,c,p,q,side): plane dd + 3*c
   CKR(upload_aos(h, Ja_slave, h->JaS, 9, h->np2, h->nSides));
+  return 0;
+}
+
+int flexi_gpu_set_overintegration(flexi_gpu_handle* h, int overintegrationType, const double* OverintegrationMat) {
+  ENTER(h);
+  if (overintegrationType == 0) {
+    h->filtOn = false;
+    return 0;
+  }
+  if (overintegrationType != 1)
+    return fail(FLEXI_GPU_ERR_UNSUPPORTED, "OverintegrationType %d is not implemented (0 = none, 1 = cutoff are)", overintegrationType);
+  if (!OverintegrationMat) return fail(FLEXI_GPU_ERR_ARG, "null argument");
+  const int np = h->N + 1;
+  std::vector<double> m((size_t)np * np);
+  for (int o = 0; o < np; ++o)  // Fortran (0:N,0:N): Mat(out,in) at out + np*in  ->  [out][in]
+    for (int i = 0; i < np; ++i) m[(size_t)o * np + i] = OverintegrationMat[o + (size_t)np * i];
+  if (!h->filtMat) CKR(dalloc(h, &h->filtMat, m.size()));
+  CK(cudaMemcpy(h->filtMat, m.data(), m.size() * 8, cudaMemcpyHostToDevice));
+  h->filtOn = true;
   return 0;
 }
 

@@ -72,6 +72,7 @@ struct UpdArgs {
   int doSource;
   const double* xGP;  // Elem_xGP as [e][3][NP3]
   double t, srcOmega, srcA, srcTmp[6];
+  const double* filt;  // OverintegrationMat as [out][in], NP*NP doubles; nullptr = OverintegrationType 0 (k_update<.,.,.,true> reads it)
 };
 
 struct ProArgs {
@@ -688,7 +689,10 @@ __global__ void __launch_bounds__(128) k_flux_bc(BCArgs A) {
 // boundary node wrote its trace entries directly was measured 19 % slower at 48^3, N=7: 3.41 vs 2.87 ms; the scattered 8-byte
 // stores cost more than the staging.)
 // ENT: the traces of the new state are prolonged in entropy variables (split form on Gauss nodes, ProlongToFaceEntropy)
-template <int NP, bool GL, bool ENT = false>
+// FILT: OVERINTEGRATIONTYPE_CUTOFF (dg.f90:663-676, dg/overintegration.f90:162-187): Ut is filtered with OverintegrationMat along
+// xi, eta, zeta (filter.f90:264-288 -> ChangeBasis3D) between the source term and ApplyJacobian, in the shared planes that
+// later stage the new state.  A separate instantiation: the unfiltered kernels are not touched by it.
+template <int NP, bool GL, bool ENT = false, bool FILT = false>
 __global__ void __launch_bounds__(Dim<NP>::NP3) k_update(UpdArgs A) {
   using D = Dim<NP>;
   extern __shared__ double sm[];
@@ -737,7 +741,43 @@ __global__ void __launch_bounds__(Dim<NP>::NP3) k_update(UpdArgs A) {
 #pragma unroll
     for (int v = 0; v < 5; ++v) ut[v] = ut[v] + (sgn * A.Flux[((size_t)sr.side * 5 + v) * D::NP2 + pq]) * lh;
   }
-  if (A.doSource) {  // Ut = -Ut; Ut += src/sJ; Ut *= sJ  (dg.f90:656-675, exactfunc.f90:809-813)
+  if (FILT) {
+    double w[5];
+#pragma unroll
+    for (int v = 0; v < 5; ++v) w[v] = -ut[v];  // dg.f90:656
+    if (A.doSource) {                           // exactfunc.f90:809-813: Ut += src/sJ
+      const double* x = A.xGP + (size_t)e * 3 * D::NP3 + n;
+      const double arg = A.srcOmega * (x[0] + x[D::NP3] + x[2 * D::NP3]) - A.srcA * A.t;
+      const double cosX = cos(arg), sinX = sin(arg), sinX2 = 2. * sinX * cosX;
+      double src[5];
+      src[0] = A.srcTmp[0] * cosX;
+      src[1] = src[2] = src[3] = A.srcTmp[1] * cosX + A.srcTmp[2] * sinX2;
+      src[4] = A.srcTmp[3] * cosX + A.srcTmp[4] * sinX2 + A.srcTmp[5] * sinX;
+#pragma unroll
+      for (int v = 0; v < 5; ++v) w[v] = w[v] + src[v] / sJ;
+    }
+    // three 1-D sweeps through the 5 shared planes; sums start from zero and run over ascending input index (changeBasis.t90)
+#pragma unroll
+    for (int dir = 0; dir < 3; ++dir) {
+      const int me = (dir == 0) ? i : (dir == 1) ? j : k;
+      const int stride = (dir == 0) ? 1 : (dir == 1) ? NP : D::NP2;
+      const int base = n - me * stride;
+#pragma unroll
+      for (int v = 0; v < 5; ++v) sU[v * D::NP3 + n] = w[v];
+      __syncthreads();
+      const double* row = A.filt + me * NP;
+#pragma unroll
+      for (int v = 0; v < 5; ++v) {
+        double acc = 0.;
+#pragma unroll
+        for (int l = 0; l < NP; ++l) acc = acc + __ldg(row + l) * sU[v * D::NP3 + base + l * stride];
+        w[v] = acc;
+      }
+      __syncthreads();  // every read of this sweep is done before the planes are overwritten (next sweep / new state below)
+    }
+#pragma unroll
+    for (int v = 0; v < 5; ++v) ut[v] = w[v] * sJ;  // ApplyJacobianCons, dg.f90:672
+  } else if (A.doSource) {  // Ut = -Ut; Ut += src/sJ; Ut *= sJ  (dg.f90:656-675, exactfunc.f90:809-813)
     const double* x = A.xGP + (size_t)e * 3 * D::NP3 + n;
     const double arg = A.srcOmega * (x[0] + x[D::NP3] + x[2 * D::NP3]) - A.srcA * A.t;
     const double cosX = cos(arg), sinX = sin(arg), sinX2 = 2. * sinX * cosX;

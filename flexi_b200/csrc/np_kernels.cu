@@ -174,6 +174,9 @@ cudaError_t setup() {
   if ((e = cudaFuncSetAttribute(k_update<NP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(k_update<NP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(k_update<NP, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_update<NP, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_update<NP, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_update<NP, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(k_surfcorr<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (D::NBASIS + 5 * D::NP3)))) != cudaSuccess) return e;
   const int pro = (int)(sizeof(double) * (D::NBASIS + 6 * D::NP3));
   if ((e = cudaFuncSetAttribute(k_prolong<NP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pro)) != cudaSuccess) return e;
@@ -257,6 +260,15 @@ cudaError_t flux(const FluxArgs& a, cudaStream_t s) {
 
 cudaError_t update(bool gl, const UpdArgs& a, int nBlocks, cudaStream_t s) {
   if (nBlocks <= 0) return cudaSuccess;
+  if (a.filt) {  // OverintegrationType = cutoff
+    if (gl)
+      k_update<NP, true, false, true><<<nBlocks, D::NP3, upd_smem, s>>>(a);
+    else if (a.entropy)
+      k_update<NP, false, true, true><<<nBlocks, D::NP3, upd_smem, s>>>(a);
+    else
+      k_update<NP, false, false, true><<<nBlocks, D::NP3, upd_smem, s>>>(a);
+    return cudaGetLastError();
+  }
   if (gl)
     k_update<NP, true><<<nBlocks, D::NP3, upd_smem, s>>>(a);
   else if (a.entropy)

@@ -216,6 +216,15 @@ def build_legendre_vdm(x_in):
     return V, np.linalg.inv(V)
 
 
+def overintegration_mat(x_gp, n_under):
+    """dg/overintegration.f90:104-116 (OVERINTEGRATIONTYPE_CUTOFF): Vdm_Leg * diag(1 for modes 0..NUnder, else 0) * sVdm_Leg,
+    the modal cut-off projector as a nodal matrix OverintegrationMat[out, in]."""
+    V, sV = build_legendre_vdm(x_gp)
+    d = np.zeros(len(x_gp))
+    d[: n_under + 1] = 1.0
+    return (V * d[None, :]) @ sV
+
+
 def get_vandermonde(n_in, type_in, n_out, type_out, modal=False):
     """interpolation.f90:293-366. Returns Vdm_In_Out[0:n_out, 0:n_in]."""
     if type_in.lower() == type_out.lower() and n_in == n_out:

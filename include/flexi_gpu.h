@@ -260,6 +260,13 @@ int flexi_gpu_surf_int(flexi_gpu_handle* h, const double* Flux_master, const dou
  * (3,3,0:N,0:N,nSides) each, after flexi_gpu_init and before the first DG operator call (the descriptor does not carry them). */
 int flexi_gpu_set_face_metrics(flexi_gpu_handle* h, const double* Ja_Face, const double* Ja_slave);
 
+/* Overintegration by modal cut-off (MOD_Overintegration, dg/overintegration.f90:40-47,104-116,162-187; dg.f90:663-676):
+ * overintegrationType 0 = none, 1 = OVERINTEGRATIONTYPE_CUTOFF -- Ut is filtered with OverintegrationMat (0:N,0:N) (Fortran order,
+ * the host's MOD_Overintegration_Vars array) between the source term and ApplyJacobian of every DG operator evaluation, fused into
+ * the update kernel.  2 (conservative cut-off, needs sJNUnder) returns FLEXI_GPU_ERR_UNSUPPORTED.  The initial Overintegration(U)
+ * of timedisc.f90:117-122 and the CFL/DFL scaling for NUnder (timedisc_func.f90:142) stay with the host. */
+int flexi_gpu_set_overintegration(flexi_gpu_handle* h, int overintegrationType, const double* OverintegrationMat);
+
 /* Page-lock a host array (cudaHostRegister) so that flexi_gpu_set_state / get_state / get_array move it at full PCIe speed and
  * asynchronously; the Fortran host calls this once for MOD_DG_Vars:U after allocation (dg.f90:94) and unpins before DEALLOCATE. */
 int flexi_gpu_pin_host_array(void* ptr, int64_t nbytes);

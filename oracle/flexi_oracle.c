@@ -53,6 +53,7 @@ typedef struct oracle {
   double *MetricsAdv, *MetricsVisc; /* InitCalctimestep */
   /* split form on Gauss nodes (PP_EntropyVars=1, src/CMakeLists.txt:64-71): entropy variables and face metrics */
   double *V, *V_master, *V_slave; /* dg_vars.f90:59 */
+  double* OverintegrationMat;     /* (0:N,0:N) Fortran order, NULL = OverintegrationType 0; set by oracle_set_overintegration */
   double *Ja_Face, *Ja_slave;     /* (3,3,0:N,0:N,nSides), mesh_vars.f90:70-78; set by oracle_set_face_metrics */
   /* owned copies of descriptor arrays */
   void* owned[64];
@@ -1480,10 +1481,48 @@ static void fill_flux(oracle* o, double t, int doMPISides) {
 /* ------------------------------------------------------------------------------------------------------------------ */
 /* source term / sign / Jacobian: dg.f90:656-676                                                                      */
 /* ------------------------------------------------------------------------------------------------------------------ */
+/* filter.f90:264-288 Filter -> changeBasis.t90 ChangeBasis3D(nVar,N,N,FilterMat,U): the 1-D matrix along xi, eta, zeta, every sum
+   accumulated from zero in ascending input index */
+static void filter_volume(const oracle* o, const double* Mat, double* U) {
+  const int np = o->np;
+  const size_t ne = (size_t)np * np * np * NVAR;
+  double* b1 = (double*)xcalloc(ne, 8);
+  double* b2 = (double*)xcalloc(ne, 8);
+#define E5(A, v, i, j, k) (A)[(v) + NVAR * ((i) + (size_t)np * ((j) + (size_t)np * (k)))]
+#define FM(io, ii) Mat[(io) + (size_t)np * (ii)]
+  for (int e = 0; e < o->d.nElems; ++e) {
+    double* Ue = U + (size_t)e * ne;
+    memset(b1, 0, ne * 8);
+    for (int k = 0; k < np; ++k)
+      for (int j = 0; j < np; ++j)
+        for (int ii = 0; ii < np; ++ii)
+          for (int io = 0; io < np; ++io)
+            for (int v = 0; v < NVAR; ++v) E5(b1, v, io, j, k) = E5(b1, v, io, j, k) + FM(io, ii) * E5(Ue, v, ii, j, k);
+    memset(b2, 0, ne * 8);
+    for (int k = 0; k < np; ++k)
+      for (int ji = 0; ji < np; ++ji)
+        for (int jo = 0; jo < np; ++jo)
+          for (int i = 0; i < np; ++i)
+            for (int v = 0; v < NVAR; ++v) E5(b2, v, i, jo, k) = E5(b2, v, i, jo, k) + FM(jo, ji) * E5(b1, v, i, ji, k);
+    memset(Ue, 0, ne * 8);
+    for (int ki = 0; ki < np; ++ki)
+      for (int ko = 0; ko < np; ++ko)
+        for (int j = 0; j < np; ++j)
+          for (int i = 0; i < np; ++i)
+            for (int v = 0; v < NVAR; ++v) E5(Ue, v, i, j, ko) = E5(Ue, v, i, j, ko) + FM(ko, ki) * E5(b2, v, i, j, ki);
+  }
+#undef E5
+#undef FM
+  free(b1);
+  free(b2);
+}
+
 static void finish_ut(oracle* o, double t) {
   const size_t n = (size_t)o->d.nElems * o->np * o->np * o->np;
   for (size_t i = 0; i < n * NVAR; ++i) o->Ut[i] = -o->Ut[i];
   if (o->d.doCalcSource) calc_source(o, t);
+  /* dg.f90:663-676: OVERINTEGRATIONTYPE_CUTOFF filters Ut before the Jacobian is applied (dg/overintegration.f90:162-187) */
+  if (o->OverintegrationMat) filter_volume(o, o->OverintegrationMat, o->Ut);
   apply_jacobian(o, NVAR, o->Ut);
 }
 
@@ -1955,8 +1994,24 @@ void oracle_set_face_metrics(oracle* o, const double* Ja_Face, const double* Ja_
   memcpy(o->Ja_slave, Ja_slave, n * 8);
 }
 
+/* OverintegrationType (dg/overintegration.f90:40-47): 0 none, 1 cutoff (OverintegrationMat = Vdm_Leg diag(1..1,0..0) sVdm_Leg,
+   :104-116).  2 (conservative cutoff) is not restated. */
+int oracle_set_overintegration(oracle* o, int type, const double* Mat) {
+  free(o->OverintegrationMat);
+  o->OverintegrationMat = NULL;
+  if (type == 0) return 0;
+  if (type != 1 || !Mat) return -1;
+  const size_t n = (size_t)o->np * o->np;
+  o->OverintegrationMat = (double*)xcalloc(n, 8);
+  memcpy(o->OverintegrationMat, Mat, n * 8);
+  return 0;
+}
+/* Filter(U_in, FilterMat) on any (5,0:N,0:N,0:N,nElems) array, e.g. the initial Overintegration(U) of timedisc.f90:117-122 */
+void oracle_filter(oracle* o, const double* Mat, double* U) { filter_volume(o, Mat, U); }
+
 void oracle_destroy(oracle* o) {
   if (!o) return;
+  free(o->OverintegrationMat);
   for (int i = 0; i < o->n_owned; ++i) free(o->owned[i]);
   double* st[] = {o->U, o->Ut, o->Ut_tmp, o->UPrim, o->U_master, o->U_slave, o->UPrim_master, o->UPrim_slave, o->Flux_master,
                   o->Flux_slave, o->gradUx, o->gradUy, o->gradUz, o->gradUx_master, o->gradUy_master, o->gradUz_master,

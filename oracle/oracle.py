@@ -51,6 +51,8 @@ def _load(fast=False):
     lib.oracle_lv_vel1.argtypes = [P]
     lib.oracle_lv_temp.argtypes = [P]
     lib.oracle_set_face_metrics.argtypes = [P, PD, PD]
+    lib.oracle_set_overintegration.argtypes = [P, C.c_int, PD]
+    lib.oracle_filter.argtypes = [P, PD, PD]
     lib.oracle_desc_bytes.restype = C.c_int
     _LIBS[name] = lib
     return lib
@@ -80,6 +82,19 @@ class OracleRank:
         b = np.ascontiguousarray(Ja_slave, dtype=np.float64)
         assert a.shape == b.shape == (self.desc.nSides, self.np, self.np, 3, 3), a.shape
         self.lib.oracle_set_face_metrics(self.h, _pd(a), _pd(b))
+
+    def set_overintegration(self, otype, mat=None):
+        """OverintegrationType 0/1 and OverintegrationMat[out, in] (dg/overintegration.f90:104-116)."""
+        m = None if mat is None else np.asfortranarray(mat, dtype=np.float64)
+        rc = self.lib.oracle_set_overintegration(self.h, int(otype), None if m is None else _pd(m))
+        assert rc == 0, "OverintegrationType not restated"
+
+    def filter(self, mat, U):
+        """Filter(U, FilterMat) (filter.f90:264-288); U in the module-array layout [e, k, j, i, v]; returns a new array."""
+        m = np.asfortranarray(mat, dtype=np.float64)
+        out = np.array(U, dtype=np.float64, order="C", copy=True)
+        self.lib.oracle_filter(self.h, _pd(m), _pd(out))
+        return out
 
     def array(self, name):
         """numpy VIEW of a module array (Fortran memory; shape is the reversed Fortran shape)."""

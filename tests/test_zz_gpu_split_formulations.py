@@ -85,3 +85,55 @@ def test_split_formulations_with_walls_and_farfield(N, stype, riemann, lifting, 
     ranks = build_case(wall_farfield_box(), N, GL, eqn)
     r = ranks[0]
     check(ranks, r.eqn.smooth_state(r.mesh.Elem_xGP, length=2.0))
+
+
+@pytest.mark.parametrize("N,NU,node,eqn", [
+    (7, 5, GL, dict(parabolic=True, split_dg=True, split_dg_type="pi", riemann="lf", mu0=1e-2)),
+    (5, 3, G, dict(parabolic=True, riemann="roe", mu0=1e-2)),
+    (4, 2, GL, dict(parabolic=False, riemann="hllc")),
+    (4, 3, G, dict(parabolic=False, split_dg=True, split_dg_type="kg", riemann="lf")),
+], ids=["N7-GL-split", "N5-G-weak", "N4-GL-euler", "N4-G-split"])
+def test_overintegration_cutoff_matches_oracle(N, NU, node, eqn):
+    """OverintegrationType = cutoff (flexi_gpu_set_overintegration; dg.f90:663-676): Ut filtered before ApplyJacobian inside the
+    update kernel, one operator evaluation and 2 LSERK steps on the curved mesh; switching it off restores the plain operator."""
+    gauss_split = node == G and eqn.get("split_dg")
+    r = build_case(BoxSpec((3, 2, 2), **CURVED), N, node, eqn, with_ja_face=bool(gauss_split))[0]
+    U0 = r.eqn.smooth_state(r.mesh.Elem_xGP, length=2.0)
+    mat = B.overintegration_mat(r.basis.xGP, NU)
+    w = O.OracleWorld([(r.desc, r.keep)])
+    o = w.ranks[0]
+    if gauss_split:
+        o.set_face_metrics(r.mesh.Ja_Face, r.mesh.Ja_slave)
+    w.set_state([U0])
+    g = FlexiGpu(r)
+    try:
+        if gauss_split:
+            g.set_face_metrics(r.mesh.Ja_Face, r.mesh.Ja_slave)
+        g.set_state(U0)
+        w.dg_time_derivative(0.0)
+        plain = np.array(o.array("Ut"))
+        o.set_overintegration(1, mat)
+        g.set_overintegration(1, mat)
+        w.dg_time_derivative(0.0)
+        ut, ref = g.DGTimeDerivative_weakForm(0.0), o.array("Ut")
+        scale = np.max(np.abs(ref).reshape(-1, 5), axis=0)
+        assert np.all(np.max(np.abs(ut - ref).reshape(-1, 5), axis=0) <= 1e-12 * scale)
+        assert np.max(np.abs(ref - plain)) > 1e-6 * np.max(np.abs(plain))  # the filter does act on this state
+        t = 0.0
+        for _ in range(2):
+            dt = w.calc_timestep()[0]
+            w.timestep(t, dt)
+            g.TimeStep(t, dt)
+            t += dt
+        Ug, Uo = g.get_state(), o.array("U")
+        sc = np.max(np.abs(Uo).reshape(-1, 5), axis=0)
+        assert np.all(np.max(np.abs(Ug - Uo).reshape(-1, 5), axis=0) <= 1e-12 * sc)
+        g.set_overintegration(0)
+        g.set_state(U0)
+        ut0 = g.DGTimeDerivative_weakForm(0.0)
+        assert np.all(np.max(np.abs(ut0 - plain).reshape(-1, 5), axis=0) <= 1e-12 * np.max(np.abs(plain).reshape(-1, 5), axis=0))
+        with pytest.raises(Exception, match="OverintegrationType 2"):
+            g.set_overintegration(2, mat)
+    finally:
+        g.close()
+        w.close()
