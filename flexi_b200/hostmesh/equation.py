@@ -48,7 +48,7 @@ class Equation:
                  riemann_bc="same", lifting=1, n_var_lifting=5, kappa=1.4, R=287.058, Pr=0.72, mu0=0.0,
                  time_disc="carpenterrk4-5", cfl_scale=0.9, dfl_scale=0.9, eta_br2=2.0, eta_br2_wall=-1.0,
                  boundary_type=(), ref_state_prim=(), ini_ref_state=1, ini_exact_func=0, do_calc_source=False,
-                 ini_amplitude=0.1, ini_frequency=1.0, adv_vel=(0.0, 0.0, 0.0)):
+                 ini_amplitude=0.1, ini_frequency=1.0, adv_vel=(0.0, 0.0, 0.0), overintegration="none", n_under=None):
         self.N = N
         self.node_type = node_type.lower()
         self.parabolic = parabolic
@@ -72,8 +72,17 @@ class Equation:
         self.RKA, self.RKb, self.RKc = np.array(tab["RKA"]), np.array(tab["RKb"]), np.array(tab["RKc"])
         # FillCFL_DFL, timedisc_func.f90:491-519
         gl = self.node_type == "gauss-lobatto"
-        alpha = (tab["CFLScaleAlpha_GL"] if gl else tab["CFLScaleAlpha_G"])[min(15, N) - 1]
-        self.CFLScale = cfl_scale * alpha / (2.0 * N + 1.0)
+        # OverintegrationType (dg/overintegration.f90:40-47,97-116): modal cut-off of Ut to NUnder <= N (the cut-off branch keeps
+        # the type even for NUnder = N; only the conservative variant disables itself, :139-141)
+        self.n_under = N if n_under is None else int(n_under)
+        assert 0 <= self.n_under <= N
+        self.overintegration = {"none": 0, "cutoff": 1}[overintegration.lower()]
+        # NEff = MIN(PP_N,NFilter,NUnder) enters the advective scaling only (timedisc_func.f90:142-144,481); overintegration on
+        # Gauss-Lobatto nodes is a projection DG scheme and takes the Gauss table (timedisc_vars.f90:153-160)
+        n_eff = min(N, self.n_under) if self.overintegration else N
+        gl_cfl = gl and not self.overintegration
+        alpha = (tab["CFLScaleAlpha_GL"] if gl_cfl else tab["CFLScaleAlpha_G"])[min(15, n_eff) - 1]
+        self.CFLScale = cfl_scale * alpha / (2.0 * n_eff + 1.0)
         alpha_d = (DFL_SCALE_ALPHA_GL if gl else DFL_SCALE_ALPHA_G)[min(10, N) - 1] * tab["RelativeDFL"]
         self.DFLScale = dfl_scale * alpha_d / (2.0 * N + 1.0) ** 2
 

@@ -141,3 +141,30 @@ def test_dg_basis_identities(node):
         # dg.f90:196-201: DVolSurf has a zero diagonal on LGL nodes
         assert np.max(np.abs(np.diag(b.DVolSurf))) < 1e-12
         assert b.L_Minus[0] == 1.0 and np.all(b.L_Minus[1:] == 0.0)
+
+
+def test_overintegration_mat_and_cfl_scaling():
+    """Host mirror of InitOverintegration (cut-off, dg/overintegration.f90:104-116) and of the time-step scaling it implies:
+    NEff = MIN(PP_N, NUnder) in the advective part only, Gauss table on Gauss-Lobatto nodes (timedisc_func.f90:142-144,
+    timedisc_vars.f90:153-160), viscous part on PP_N (timedisc_func.f90:481)."""
+    from flexi_b200.hostmesh.equation import Equation
+
+    N, NU = 7, 5
+    x, w, _ = B.get_nodes_and_weights(N, B.NODE_GAUSS_LOBATTO)
+    M = B.overintegration_mat(x, NU)
+    V, sV = B.build_legendre_vdm(x)
+    # a polynomial of degree <= NUnder passes unchanged, Legendre modes above NUnder are removed
+    for deg in range(N + 1):
+        f = V[:, deg]
+        assert np.max(np.abs(M @ f - (f if deg <= NU else 0.0))) < 1e-13
+    # the projector is L2-orthogonal with respect to Gauss quadrature, not to the LGL quadrature; it always keeps the mean
+    xg, wg, _ = B.get_nodes_and_weights(N, B.NODE_GAUSS)
+    Mg = B.overintegration_mat(xg, NU)
+    assert np.max(np.abs(wg @ Mg - wg)) < 1e-14
+    assert np.max(np.abs(Mg.T * wg[None, :] - (Mg.T * wg[None, :]).T)) < 1e-14  # W M symmetric on Gauss nodes
+    plain = Equation(N, B.NODE_GAUSS_LOBATTO, cfl_scale=0.9, dfl_scale=0.9)
+    over = Equation(N, B.NODE_GAUSS_LOBATTO, cfl_scale=0.9, dfl_scale=0.9, overintegration="cutoff", n_under=NU)
+    assert over.overintegration == 1 and plain.overintegration == 0
+    assert abs(plain.CFLScale - 0.9 * 1.8225 / 15.0) < 1e-15      # GL table of carpenterrk4-5, N = 7 (timedisc_vars.f90:175-190)
+    assert abs(over.CFLScale - 0.9 * 1.2375 / 11.0) < 1e-15       # Gauss table, NEff = 5
+    assert over.DFLScale == plain.DFLScale
