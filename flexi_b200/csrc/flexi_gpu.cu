@@ -107,6 +107,8 @@ struct flexi_gpu_handle {
   double *JaF = nullptr, *JaS = nullptr;  // Ja_Face / Ja_slave [s][9][NP2]
   double* filtMat = nullptr;              // OverintegrationMat [out][in] (allocated on first use)
   bool filtOn = false;                    // OverintegrationType == cutoff
+  double* filtUMat = nullptr;             // FilterMat [out][in] of the solution filter (FilterType cutoff / modal)
+  bool filtUOn = false;
   bool vt = false;             // viscous-trace protocol between k_volume_gl2 and k_flux (kernels.cuh: VolArgs::fvm)
   bool gradTracesFull = true;  // gradU?_master/slave hold the traces of every side (else only of the BC sides)
   double *fvm = nullptr, *fvs = nullptr;
@@ -423,6 +425,16 @@ int rhs(H* h, double t, int mode, double rkA, double b_dt) {
   if (h->bcTablesMissing) return fail(FLEXI_GPU_ERR_ARG, "BC sides without BC / BoundaryType tables");
   if (h->entropy && !h->JaF) return fail(FLEXI_GPU_ERR_ARG, "split form on Gauss nodes: call flexi_gpu_set_face_metrics (Ja_Face, Ja_slave) first");
   h->lastT = t;
+  if (h->filtUOn) {  // dg.f90:329-330: IF(FilterType.GT.0) CALL Filter_Pointer(U,FilterMat) -- in place, then everything reads the filtered U
+    FiltArgs fa{};
+    fa.U = h->U;
+    fa.mat = h->filtUMat;
+    {
+      Timer tm(h, KC_LAYOUT, h->sc);
+      CK(h->ops->filter(fa, h->nElems, h->sc));
+    }
+    h->tracesValid = false;  // the traces k_update left behind belong to the unfiltered state
+  }
   if (!h->tracesValid) CKR(refresh_traces(h));
   const bool multi = h->nProcs > 1;
   const bool fullGrad = !h->vt || mode == 0 || h->keepGrad;
@@ -1202,6 +1214,26 @@ int flexi_gpu_set_overintegration(flexi_gpu_handle* h, int overintegrationType, 
   if (!h->filtMat) CKR(dalloc(h, &h->filtMat, m.size()));
   CK(cudaMemcpy(h->filtMat, m.data(), m.size() * 8, cudaMemcpyHostToDevice));
   h->filtOn = true;
+  return 0;
+}
+
+int flexi_gpu_set_filter(flexi_gpu_handle* h, int filterType, const double* FilterMat) {
+  ENTER(h);
+  if (filterType == 0) {
+    h->filtUOn = false;
+    return 0;
+  }
+  if (filterType != 1 && filterType != 2)
+    return fail(FLEXI_GPU_ERR_UNSUPPORTED, "FilterType %d is not implemented (0 = none, 1 = cutoff, 2 = modal are)", filterType);
+  if (h->nProcs > 1) return fail(FLEXI_GPU_ERR_UNSUPPORTED, "the solution filter is single-rank so far (the trace exchange of the previous stage is still in flight when U is filtered)");
+  if (!FilterMat) return fail(FLEXI_GPU_ERR_ARG, "null argument");
+  const int np = h->N + 1;
+  std::vector<double> m((size_t)np * np);
+  for (int o = 0; o < np; ++o)  // Fortran (0:N,0:N): Mat(out,in) at out + np*in  ->  [out][in]
+    for (int i = 0; i < np; ++i) m[(size_t)o * np + i] = FilterMat[o + (size_t)np * i];
+  if (!h->filtUMat) CKR(dalloc(h, &h->filtUMat, m.size()));
+  CK(cudaMemcpy(h->filtUMat, m.data(), m.size() * 8, cudaMemcpyHostToDevice));
+  h->filtUOn = true;
   return 0;
 }
 

@@ -75,6 +75,11 @@ struct UpdArgs {
   const double* filt;  // OverintegrationMat as [out][in], NP*NP doubles; nullptr = OverintegrationType 0 (k_update<.,.,.,true> reads it)
 };
 
+struct FiltArgs {
+  double* U;          // [e][5][NP3], filtered in place
+  const double* mat;  // FilterMat as [out][in]
+};
+
 struct ProArgs {
   Mesh m;
   const double* V;  // [e][nv][NP3]
@@ -85,6 +90,42 @@ struct ProArgs {
   int entropy;  // ProlongToFaceEntropy (prolongtoface.t90:151-204): V holds U (nv = 5), entropy variables are prolonged
   Eqn q;
 };
+
+// k_filter: Filter(U, FilterMat) in place (filter.f90:264-288 -> ChangeBasis3D), the solution filter the reference applies at the
+// start of every DG operator evaluation when FilterType > 0 (dg.f90:329-330).  One CTA per element, one thread per node, three
+// 1-D sweeps through 5 shared planes; sums start from zero and run over ascending input index like changeBasis.t90.  A plain
+// extra pass over U (HBM-bound: 80 B/DOF); the fused form is described in DESIGN.md section 7.
+template <int NP>
+__global__ void __launch_bounds__(Dim<NP>::NP3) k_filter(FiltArgs A) {
+  using D = Dim<NP>;
+  extern __shared__ double sm[];
+  const int n = threadIdx.x;
+  const size_t e = blockIdx.x;
+  const int i = n % NP, j = (n / NP) % NP, k = n / D::NP2;
+  double w[5];
+#pragma unroll
+  for (int v = 0; v < 5; ++v) w[v] = A.U[(e * 5 + v) * D::NP3 + n];
+#pragma unroll
+  for (int dir = 0; dir < 3; ++dir) {
+    const int me = (dir == 0) ? i : (dir == 1) ? j : k;
+    const int stride = (dir == 0) ? 1 : (dir == 1) ? NP : D::NP2;
+    const int base = n - me * stride;
+#pragma unroll
+    for (int v = 0; v < 5; ++v) sm[v * D::NP3 + n] = w[v];
+    __syncthreads();
+    const double* row = A.mat + me * NP;
+#pragma unroll
+    for (int v = 0; v < 5; ++v) {
+      double acc = 0.;
+#pragma unroll
+      for (int l = 0; l < NP; ++l) acc = acc + __ldg(row + l) * sm[v * D::NP3 + base + l * stride];
+      w[v] = acc;
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int v = 0; v < 5; ++v) A.U[(e * 5 + v) * D::NP3 + n] = w[v];
+}
 
 // ---------------------------------------------------------------------------------------------------------------------------
 template <int NP>

@@ -298,7 +298,13 @@ cudaError_t dt(const DtArgs& a, int nElems, cudaStream_t s) {
   return cudaGetLastError();
 }
 
-const NpOps ops = {NP, setup, prolong, volume, flux, update, surfcorr, surfint, dt, bc_pre, flux_bc};
+cudaError_t filter(const FiltArgs& a, int nElems, cudaStream_t s) {
+  if (nElems <= 0) return cudaSuccess;
+  k_filter<NP><<<nElems, D::NP3, sizeof(double) * 5 * D::NP3, s>>>(a);  // <= 40 KB at NP = 10: no opt-in needed
+  return cudaGetLastError();
+}
+
+const NpOps ops = {NP, setup, prolong, volume, flux, update, surfcorr, surfint, dt, bc_pre, flux_bc, filter};
 }  // namespace
 }  // namespace fx
 

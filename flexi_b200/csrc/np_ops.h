@@ -20,6 +20,7 @@ struct NpOps {
   cudaError_t (*dt)(const DtArgs& a, int nElems, cudaStream_t s);
   cudaError_t (*bc_pre)(const BCArgs& a, cudaStream_t s);
   cudaError_t (*flux_bc)(const BCArgs& a, cudaStream_t s);
+  cudaError_t (*filter)(const FiltArgs& a, int nElems, cudaStream_t s);
 };
 
 }  // namespace fx

@@ -267,6 +267,11 @@ int flexi_gpu_set_face_metrics(flexi_gpu_handle* h, const double* Ja_Face, const
  * of timedisc.f90:117-122 and the CFL/DFL scaling for NUnder (timedisc_func.f90:142) stay with the host. */
 int flexi_gpu_set_overintegration(flexi_gpu_handle* h, int overintegrationType, const double* OverintegrationMat);
 
+/* Solution filter (MOD_Filter, filter/filter.f90:67-72,135-196,264-288; dg.f90:329-330): filterType 0 = none, 1 = cutoff,
+ * 2 = modal (Hesthaven) -- both apply the host's FilterMat (0:N,0:N) (Fortran order) to U in place at the start of every DG
+ * operator evaluation, as the reference does.  3 (LAF) and multi-rank runs return FLEXI_GPU_ERR_UNSUPPORTED. */
+int flexi_gpu_set_filter(flexi_gpu_handle* h, int filterType, const double* FilterMat);
+
 /* Page-lock a host array (cudaHostRegister) so that flexi_gpu_set_state / get_state / get_array move it at full PCIe speed and
  * asynchronously; the Fortran host calls this once for MOD_DG_Vars:U after allocation (dg.f90:94) and unpins before DEALLOCATE. */
 int flexi_gpu_pin_host_array(void* ptr, int64_t nbytes);

@@ -53,6 +53,7 @@ typedef struct oracle {
   double *MetricsAdv, *MetricsVisc; /* InitCalctimestep */
   /* split form on Gauss nodes (PP_EntropyVars=1, src/CMakeLists.txt:64-71): entropy variables and face metrics */
   double *V, *V_master, *V_slave; /* dg_vars.f90:59 */
+  double* FilterMat;              /* (0:N,0:N) Fortran order, NULL = FilterType none; set by oracle_set_filter */
   double* OverintegrationMat;     /* (0:N,0:N) Fortran order, NULL = OverintegrationType 0; set by oracle_set_overintegration */
   double *Ja_Face, *Ja_slave;     /* (3,3,0:N,0:N,nSides), mesh_vars.f90:70-78; set by oracle_set_face_metrics */
   /* owned copies of descriptor arrays */
@@ -1731,6 +1732,7 @@ void oracle_world_dg_time_derivative(oracle_world* w, double t) {
   const int szs = NVAR * np * np;
   FOR_RANKS {
     oracle* o = w->r[r];
+    if (o->FilterMat) filter_volume(o, o->FilterMat, o->U);  /* 1. dg.f90:329-330: Filter_Pointer(U,FilterMat), in place */
     cons_to_prim_volume(o);                                  /* 2. */
     if (entropy_vars(o)) {
       cons_to_entropy_volume(o);                             /* ConsToPrimToEntropy, dg.f90:333-337 */
@@ -2006,12 +2008,25 @@ int oracle_set_overintegration(oracle* o, int type, const double* Mat) {
   memcpy(o->OverintegrationMat, Mat, n * 8);
   return 0;
 }
+/* FilterType (filter/filter.f90:67-72,135-196): 0 none; 1 cutoff and 2 modal (Hesthaven) both point Filter_Pointer at Filter with
+   the host-built FilterMat (:138-190); 3 (LAF) is not restated. */
+int oracle_set_filter(oracle* o, int type, const double* Mat) {
+  free(o->FilterMat);
+  o->FilterMat = NULL;
+  if (type == 0) return 0;
+  if ((type != 1 && type != 2) || !Mat) return -1;
+  const size_t n = (size_t)o->np * o->np;
+  o->FilterMat = (double*)xcalloc(n, 8);
+  memcpy(o->FilterMat, Mat, n * 8);
+  return 0;
+}
 /* Filter(U_in, FilterMat) on any (5,0:N,0:N,0:N,nElems) array, e.g. the initial Overintegration(U) of timedisc.f90:117-122 */
 void oracle_filter(oracle* o, const double* Mat, double* U) { filter_volume(o, Mat, U); }
 
 void oracle_destroy(oracle* o) {
   if (!o) return;
   free(o->OverintegrationMat);
+  free(o->FilterMat);
   for (int i = 0; i < o->n_owned; ++i) free(o->owned[i]);
   double* st[] = {o->U, o->Ut, o->Ut_tmp, o->UPrim, o->U_master, o->U_slave, o->UPrim_master, o->UPrim_slave, o->Flux_master,
                   o->Flux_slave, o->gradUx, o->gradUy, o->gradUz, o->gradUx_master, o->gradUy_master, o->gradUz_master,

@@ -53,6 +53,7 @@ def _load(fast=False):
     lib.oracle_set_face_metrics.argtypes = [P, PD, PD]
     lib.oracle_set_overintegration.argtypes = [P, C.c_int, PD]
     lib.oracle_filter.argtypes = [P, PD, PD]
+    lib.oracle_set_filter.argtypes = [P, C.c_int, PD]
     lib.oracle_desc_bytes.restype = C.c_int
     _LIBS[name] = lib
     return lib
@@ -88,6 +89,13 @@ class OracleRank:
         m = None if mat is None else np.asfortranarray(mat, dtype=np.float64)
         rc = self.lib.oracle_set_overintegration(self.h, int(otype), None if m is None else _pd(m))
         assert rc == 0, "OverintegrationType not restated"
+
+    def set_filter(self, ftype, mat=None):
+        """FilterType 0 (none) / 1 (cutoff) / 2 (modal) and FilterMat[out, in]: U is filtered in place at the start of every
+        DG operator evaluation (dg.f90:329-330)."""
+        m = None if mat is None else np.asfortranarray(mat, dtype=np.float64)
+        rc = self.lib.oracle_set_filter(self.h, int(ftype), None if m is None else _pd(m))
+        assert rc == 0, "FilterType not restated"
 
     def filter(self, mat, U):
         """Filter(U, FilterMat) (filter.f90:264-288); U in the module-array layout [e, k, j, i, v]; returns a new array."""

@@ -318,3 +318,30 @@ def test_overintegration_cutoff(node):
     w.dg_time_derivative(0.0)
     assert np.array_equal(np.array(o.array("Ut")), ut_plain)
     w.close()
+
+
+def test_solution_filter_at_operator_start():
+    """FilterType cutoff (filter.f90:135-196, dg.f90:329-330): U itself is filtered in place at the start of every operator
+    evaluation -- the operator of the filtered state, and the module array U holds the filtered state afterwards."""
+    N, NF = 5, 3
+    eqn = dict(parabolic=True, riemann="roe", mu0=1e-2)
+    ranks, w = world(tgv_box(2), N, B.NODE_GAUSS, eqn)
+    r, o = ranks[0], w.ranks[0]
+    U = r.eqn.smooth_state(r.mesh.Elem_xGP, length=2 * np.pi)
+    mat = B.overintegration_mat(r.basis.xGP, NF)  # the cut-off FilterMat has the same form (filter.f90:140-146)
+    Uf = B.change_basis_3d(mat, U)
+    w.set_state([Uf])
+    w.dg_time_derivative(0.0)
+    ref = np.array(o.array("Ut"))
+    o.set_filter(1, mat)
+    w.set_state([U])
+    w.dg_time_derivative(0.0)
+    assert np.max(np.abs(np.array(o.array("U")) - Uf)) <= 1e-13 * np.max(np.abs(Uf))
+    assert np.max(np.abs(np.array(o.array("Ut")) - ref)) <= 1e-11 * np.max(np.abs(ref))
+    # a time step keeps working on the filtered state: after it, one more filter changes U only at round-off level in the
+    # retained modes' complement of what the last stage added
+    dt = w.calc_timestep()[0]
+    w.timestep(0.0, dt)
+    assert np.isfinite(o.array("U")).all()
+    o.set_filter(0)
+    w.close()

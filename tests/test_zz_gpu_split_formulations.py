@@ -137,3 +137,45 @@ def test_overintegration_cutoff_matches_oracle(N, NU, node, eqn):
     finally:
         g.close()
         w.close()
+
+
+@pytest.mark.parametrize("N,NF,node,eqn", [
+    (7, 4, GL, dict(parabolic=True, split_dg=True, split_dg_type="pi", riemann="lf", mu0=1e-2)),
+    (4, 2, G, dict(parabolic=True, riemann="roe", mu0=1e-2)),
+], ids=["N7-GL-split", "N4-G-weak"])
+def test_solution_filter_matches_oracle(N, NF, node, eqn):
+    """FilterType cutoff (flexi_gpu_set_filter; dg.f90:329-330): U filtered in place at the start of every operator evaluation
+    (stand-alone k_filter pass + trace refresh); one operator, then 2 LSERK steps."""
+    r = build_case(BoxSpec((3, 2, 2), **CURVED), N, node, eqn)[0]
+    U0 = r.eqn.smooth_state(r.mesh.Elem_xGP, length=2.0)
+    mat = B.overintegration_mat(r.basis.xGP, NF)
+    w = O.OracleWorld([(r.desc, r.keep)])
+    o = w.ranks[0]
+    o.set_filter(1, mat)
+    w.set_state([U0])
+    g = FlexiGpu(r)
+    try:
+        g.set_filter(1, mat)
+        g.set_state(U0)
+        w.dg_time_derivative(0.0)
+        ut, ref = g.DGTimeDerivative_weakForm(0.0), o.array("Ut")
+        scale = np.max(np.abs(ref).reshape(-1, 5), axis=0)
+        assert np.all(np.max(np.abs(ut - ref).reshape(-1, 5), axis=0) <= 1e-12 * scale)
+        Ug, Uo = g.get_state(), o.array("U")
+        assert np.max(np.abs(Ug - Uo)) <= 1e-13 * np.max(np.abs(Uo))  # the state itself is filtered
+        assert np.max(np.abs(Uo - U0)) > 1e-6
+        t = 0.0
+        for _ in range(2):
+            dt = w.calc_timestep()[0]
+            assert abs(g.CalcTimeStep()[0] - dt) <= 1e-13 * dt
+            w.timestep(t, dt)
+            g.TimeStep(t, dt)
+            t += dt
+        Ug, Uo = g.get_state(), o.array("U")
+        sc = np.max(np.abs(Uo).reshape(-1, 5), axis=0)
+        assert np.all(np.max(np.abs(Ug - Uo).reshape(-1, 5), axis=0) <= 1e-12 * sc)
+        with pytest.raises(Exception, match="FilterType 3"):
+            g.set_filter(3, mat)
+    finally:
+        g.close()
+        w.close()
