@@ -99,6 +99,13 @@ class ClockSampler:
                 "samples": len(self.rows), "reasons": reasons}
 
 
+def mem_available_gb():
+    try:
+        return int([ln.split()[1] for ln in open("/proc/meminfo") if ln.startswith("MemAvailable")][0]) / 1048576.0
+    except Exception:
+        return 0.0
+
+
 def host_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -133,6 +140,110 @@ def run_cpu(args, steps, warmup, nel, cores):
     return ndof * nst * steps / el / 1e9, el, nranks, ndof
 
 
+def ut_scale(ut):
+    """Per-variable magnitude of Ut that a difference is judged against: max|Ut_v|, with one common scale for the three momenta and
+    the density judged against the momentum scale too (TGV: div(rho u) = 0, so max|Ut_rho| is itself at truncation-error level and
+    says nothing about the size of the terms that were summed)."""
+    sc = np.max(np.abs(ut).reshape(-1, 5), axis=0)
+    sc[0:4] = sc[1:4].max()
+    return sc
+
+
+def parity_gate(args, node, eqn, world, rank, local_rank, dist, torch, G):
+    """Parity of the benchmarked code path with the CPU oracle, outside the timed region ('parity gates run with every
+    measurement'): same flavour, same partition shape, `--parity-nel`^3 elements per GPU.  Every rank runs its partition on its GPU
+    (NCCL side exchange included) and compares its slice with the oracle world of all ranks, which it computes itself on the host.
+    Returns max-over-ranks of: one Ut (max|diff|/max|ref| per variable, and the same in units of the gate = max(1e-12*scale,
+    4 x the oracle's own strict-vs-FMA build noise)), the state after K fixed-dt LSERK steps (gate 1e-12) and dt (gate 1e-13)."""
+    from flexi_b200.hostmesh.case import build_case, tgv_box
+    from oracle import oracle as O
+
+    blocks = BLOCKS[world]
+    nel = tuple(args.parity_nel * b for b in blocks)
+    spec = tgv_box(nel)
+    spec.length = np.array([2 * np.pi * b * args.parity_nel / args.nel for b in blocks])  # same element size as the benchmarked mesh
+    ranks = build_case(spec, args.N, node, eqn, nranks=world, partition="block", blocks=blocks)
+    me = ranks[rank]
+    U0s = [r.eqn.tgv_state(r.mesh.Elem_xGP) for r in ranks]
+    os.environ["OMP_NUM_THREADS"] = str(max(1, min(world, host_cores() // world)))
+    dk = [(r.desc, r.keep) for r in ranks]
+    noise, ut_strict = O.ut_noise_floor(dk, U0s)
+    nccl_id = None
+    if world > 1:
+        idt = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            idt = torch.frombuffer(bytearray(G.nccl_unique_id()), dtype=torch.uint8).clone()
+        dist.broadcast(idt, src=0)
+        nccl_id = bytes(idt.numpy().tobytes())
+    me.remake_desc(nccl_id=nccl_id, device=local_rank)
+    w = O.OracleWorld(dk)
+    w.set_state(U0s)
+    out = {}
+    with G.FlexiGpu(me) as g:
+        g.set_state(U0s[rank])
+        ut = g.DGTimeDerivative_weakForm(0.0)
+        ref = ut_strict[rank]
+        scale = ut_scale(np.concatenate([u.reshape(-1, 5) for u in ut_strict]))
+        d = np.max(np.abs(ut - ref).reshape(-1, 5), axis=0)
+        gate = np.maximum(1e-12 * scale, 4.0 * noise)
+        out["ut_rel"] = float(np.max(d / scale))
+        out["ut_over_gate"] = float(np.max(d / gate))
+        out["noise_abs"] = [float(x) for x in noise]
+        dt_o = w.calc_timestep()[0]
+        dt_g = g.CalcTimeStep()[0]
+        out["dt_rel"] = abs(dt_g - dt_o) / dt_o
+        t = 0.0
+        for _ in range(args.parity_steps):
+            w.timestep(t, dt_o)
+            g.TimeStep(t, dt_o)
+            t += dt_o
+        Ug, Uo = g.get_state(), w.ranks[rank].array("U")
+        sc = np.max(np.abs(np.concatenate([r.array("U").reshape(-1, 5) for r in w.ranks])), axis=0)
+        sc[1:4] = sc[1:4].max()  # TGV: judge the momenta against the common momentum scale
+        out["state_rel"] = float(np.max(np.max(np.abs(Ug - Uo).reshape(-1, 5), axis=0) / sc))
+    w.close()
+    if world > 1:
+        keys = ("ut_rel", "ut_over_gate", "dt_rel", "state_rel")
+        tt = torch.tensor([out[k] for k in keys], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        out.update(dict(zip(keys, [float(x) for x in tt.tolist()])))
+    out["ok"] = bool(out["ut_over_gate"] <= 1.0 and out["state_rel"] <= 1e-12 and out["dt_rel"] <= 1e-13)
+    out["what"] = (f"same flavour and partition shape, {args.parity_nel}^3 elements per GPU, GPU (C ABI, NCCL exchange at N>1) vs CPU oracle: one Ut "
+                   f"(gate max(1e-12*scale, 4x oracle strict-vs-FMA noise)), dt (1e-13), state after {args.parity_steps} LSERK steps (1e-12)")
+    return out
+
+
+def parity_fullsize(args, g, r, U0, noise):
+    """Checks on the benchmarked mesh itself: discrete conservation of one Ut on the periodic box (sum_elem sum_ijk w_ijk Ut / sJ = 0,
+    relative to sum w |Ut| / sJ of the momenta) and, when the host has the memory (~30 GB), that same Ut against the single-rank
+    oracle (-O3 build; gate max(1e-12*scale, 8 x the strict-vs-FMA noise measured on the small case: same element size and state))."""
+    from oracle import oracle as O
+
+    out = {}
+    g.set_state(U0)
+    ut = g.DGTimeDerivative_weakForm(0.0)
+    w3 = np.einsum("k,j,i->kji", r.basis.wGP, r.basis.wGP, r.basis.wGP)[None] / r.mesh.sJ
+    cons = np.einsum("ekjiv,ekji->v", ut, w3)
+    mag = np.einsum("ekjiv,ekji->v", np.abs(ut), w3)
+    mag[0:4] = mag[1:4].max()
+    out["conservation_rel"] = float(np.max(np.abs(cons) / mag))
+    if mem_available_gb() > 96.0 and not args.no_fullsize_oracle:
+        t0 = time.perf_counter()
+        w = O.OracleWorld([(r.desc, r.keep)], fast=True)
+        w.set_state([U0])
+        w.dg_time_derivative(0.0)
+        ref = w.ranks[0].array("Ut")
+        scale = ut_scale(ref)
+        d = np.max(np.abs(ut - ref).reshape(-1, 5), axis=0)
+        out["ut_rel_fullsize"] = float(np.max(d / scale))
+        out["ut_over_gate_fullsize"] = float(np.max(d / np.maximum(1e-12 * scale, 8.0 * np.asarray(noise))))
+        out["fullsize_oracle_s"] = time.perf_counter() - t0
+        w.close()
+    else:
+        out["ut_rel_fullsize"] = out["ut_over_gate_fullsize"] = None
+    return out
+
+
 def emit(line, fd):
     """Write the one JSON line to the real stdout (fd saved before anything could print there)."""
     os.write(fd, (json.dumps(line) + "\n").encode())
@@ -152,8 +263,12 @@ def main():
     ap.add_argument("--nel", type=int, default=48, help="elements per direction PER GPU (BASELINE configs[1]: 48)")
     ap.add_argument("--N", type=int, default=7)
     ap.add_argument("--flavour", default="split", choices=["split", "weak"], help="split: configs[1]; weak: configs[0] flavour")
-    ap.add_argument("--cpu-nel", type=int, default=16, help="box size of the bounded CPU sample")
+    ap.add_argument("--cpu-nel", type=int, default=0, help="box size of the CPU run; 0 = --impl reference: the benchmarked box (--nel) when the "
+                    "host has the memory, else 16; cpu_baseline leg of the repo arm: 16")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--parity-nel", type=int, default=6, help="elements per direction per GPU of the parity gate (0 = skip)")
+    ap.add_argument("--parity-steps", type=int, default=5)
+    ap.add_argument("--no-fullsize-oracle", action="store_true", help="skip the single-rank oracle Ut on the benchmarked mesh (N=1)")
     ap.add_argument("--profile-steps", type=int, default=2, help="extra steps with per-kernel CUDA events for the roofline object")
     args = ap.parse_args()
 
@@ -169,15 +284,23 @@ def main():
         if rank != 0:
             return
         cores = host_cores()
-        steps = max(1, min(args.steps, 40))  # 16^3 elements at N=7: ~0.4 s per LSERK step on 16 cores
-        val, el, nr, ndof = run_cpu(args, steps, min(args.warmup, 3), args.cpu_nel, cores)
-        sample = (f"same flavour on a {args.cpu_nel}^3-element box ({ndof} DOF), {steps} timed LSERK steps, {nr} emulated MPI ranks "
-                  f"(one per OpenMP thread), C port of the reference (oracle/flexi_oracle.c, -O3 -march=x86-64-v3); no Fortran compiler in the image")
+        cpu_nel = args.cpu_nel
+        if cpu_nel == 0:  # the benchmarked configuration itself needs ~0.6 KB per DOF on the host (oracle arrays + host mesh)
+            need_gb = args.nel ** 3 * (args.N + 1) ** 3 * 900.0 / 2 ** 30
+            cpu_nel = args.nel if mem_available_gb() > need_gb + 16.0 else 16
+        # the whole run has to end within a few minutes: ~0.18 us per DOF and stage and core
+        est_step_s = cpu_nel ** 3 * (args.N + 1) ** 3 * nst * 0.6e-6 / max(1, min(cores, cpu_nel ** 3 // 8))
+        steps = max(1, min(args.steps, int(150.0 / est_step_s)))
+        warmup = max(0, min(args.warmup, int(30.0 / est_step_s)))
+        val, el, nr, ndof = run_cpu(args, steps, warmup, cpu_nel, cores)
+        same = "the benchmarked box itself" if cpu_nel == args.nel else "a bounded sample of the workload"
+        sample = (f"{same}: same flavour, {cpu_nel}^3 elements ({ndof} DOF), {steps} timed LSERK steps after {warmup} warm-up ({el:.1f} s), {nr} emulated "
+                  f"MPI ranks (one per OpenMP thread), C port of the reference (oracle/flexi_oracle.c, -O3 -march=x86-64-v3); no Fortran compiler in the image")
         line = {"impl": "reference", "metric": "GDOF/s (DOF*RK-stages per second), PID = 1/(value*1e9) s/DOF/stage", "value": val,
-                "unit": "GDOF/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 3), "ms_per_step": el / steps * 1e3,
+                "unit": "GDOF/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": el / steps * 1e3,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "pid_s_per_dof_stage": 1.0 / (val * 1e9), "pid_core_s": nr / (val * 1e9),
-                "config": {"workload": workload, "cpu_sample_nel": args.cpu_nel},
+                "config": {"workload": workload, "cpu_sample_nel": cpu_nel, "same_box_as_gpu_arm": cpu_nel == args.nel},
                 "cpu_baseline": {"value": val, "unit": "GDOF/s", "cores": nr, "kind": "port", "sample": sample},
                 "e2e": {"value": val, "unit": "GDOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         emit(line, real_stdout)
@@ -194,13 +317,16 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # stdout carries exactly one JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION/INFO
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE") and not os.environ.get("FLEXI_BENCH_KEEP_NCCL_DEBUG"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # NCCL_DEBUG is left as the caller set it: its output goes to fd 1, which main() redirected to stderr
         dist.init_process_group(backend="cpu:gloo,cuda:nccl", rank=rank, world_size=world)
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}"
 
     node, eqn = eqn_for(args)
+    parity = None
+    if args.parity_nel > 0:
+        parity = parity_gate(args, node, eqn, world, rank, local_rank, dist if world > 1 else None, torch, G)
+        if not parity["ok"]:
+            raise SystemExit(f"bench.py: parity gate failed, no number is reported: {parity}")
     blocks = BLOCKS[world]
     nel = tuple(args.nel * b for b in blocks)
     spec = tgv_box(nel)
@@ -315,12 +441,17 @@ def main():
         except Exception:
             pass
 
+    if parity is not None and world == 1:
+        parity.update(parity_fullsize(args, g, r, U0.numpy(), parity["noise_abs"]))
+        if parity["conservation_rel"] > 1e-12 or (parity["ut_over_gate_fullsize"] is not None and parity["ut_over_gate_fullsize"] > 1.0):
+            raise SystemExit(f"bench.py: full-size parity check failed: {parity}")
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = host_cores()
-        val, el, nr, nd = run_cpu(args, 30, 2, args.cpu_nel, cores)
+        cnel = args.cpu_nel or 16
+        val, el, nr, nd = run_cpu(args, 30, 2, cnel, cores)
         cpu = {"value": val, "unit": "GDOF/s", "cores": nr, "kind": "port",
-               "sample": f"same flavour on a {args.cpu_nel}^3-element box ({nd} DOF), 30 timed LSERK steps in {el:.1f} s, {nr} emulated MPI ranks, "
+               "sample": f"same flavour on a {cnel}^3-element box ({nd} DOF), 30 timed LSERK steps in {el:.1f} s, {nr} emulated MPI ranks, "
                          "C port of the reference (-O3 -march=x86-64-v3)"}
     g.close()
     if rank == 0:
@@ -335,7 +466,7 @@ def main():
                 "e2e": {"value": e2e_val, "unit": "GDOF/s", "h2d_bytes_per_step": ubytes / args.steps,
                         "d2h_bytes_per_step": ubytes / args.steps + 24,
                         "what": "set_state(pinned host U) + steps x (CalcTimeStep + TimeStep) + get_state(pinned host U) through the C ABI"},
-                "roofline": roofline, "cpu_baseline": cpu}
+                "roofline": roofline, "cpu_baseline": cpu, "parity": parity}
         emit(line, real_stdout)
     if world > 1:
         dist.destroy_process_group()

@@ -320,10 +320,12 @@ int launch_volume(H* h, const int32_t* list, int n, bool fullGrad) {
   a.fvs = h->fvs;
   a.fullGrad = fullGrad ? 1 : 0;
   a.prefetchAhead = h->prefetchAhead;
+#ifdef FLEXI_GPU_DEV
   {
     static const int dbg = getenv("FLEXI_GPU_DBG") ? atoi(getenv("FLEXI_GPU_DBG")) : 0;  // timing experiments only (results are wrong)
     a.dbg = dbg;
   }
+#endif
   Timer tm(h, KC_VOLUME, h->sc);
   CK(h->ops->volume(h->gl, h->split, h->q.splitType, h->para, h->nvl, a, n, h->sc));
   return 0;
@@ -441,6 +443,26 @@ int rhs(H* h, double t, int mode, double rkA, double b_dt) {
   h->gradTracesFull = fullGrad;
   // boundary sides: the lifting boundary flux enters the element kernel as a virtual slave trace (k_bc_pre)
   if (h->para) CKR(launch_bc(h, true, t));
+#ifdef FLEXI_GPU_DEV
+  {  // concurrency experiment (results are wrong): the HBM-bound side + update kernels on the second stream, with no dependency
+     // on the element kernel, to see how well the hardware co-schedules them.  1: update side on the high-priority stream, 2: volume
+    static const int ovl = getenv("FLEXI_GPU_OVL") ? atoi(getenv("FLEXI_GPU_OVL")) : 0;
+    if (ovl && !multi) {
+      CK(cudaEventRecord(h->evProd, h->sc));
+      CK(cudaStreamWaitEvent(h->sx, h->evProd, 0));
+      if (ovl == 2) std::swap(h->sc, h->sx);
+      CKR(launch_volume(h, nullptr, h->nElems, fullGrad));
+      std::swap(h->sc, h->sx);
+      CKR(launch_bc(h, false, t));
+      CKR(launch_flux(h, h->firstInner, h->nInnerSides));
+      CKR(launch_update(h, nullptr, h->nElems, mode, rkA, b_dt, t));
+      if (ovl != 2) std::swap(h->sc, h->sx);
+      CK(cudaEventRecord(h->evX[0], h->sx));
+      CK(cudaStreamWaitEvent(h->sc, h->evX[0], 0));
+      return 0;
+    }
+  }
+#endif
   if (!multi) {
     CKR(launch_volume(h, nullptr, h->nElems, fullGrad));
     CKR(launch_surfcorr(h, nullptr, h->nElems));
@@ -606,7 +628,11 @@ static int init_impl(const flexi_gpu_desc* d, H* h) {
     h->prefetchAhead = pf ? atoi(pf) : nsm;  // measured flat between 1/4 and 1.3 waves of CTAs, 3 % worse at 2 (profiles/README.md)
   }
   CK(cudaStreamCreateWithFlags(&h->sc, cudaStreamNonBlocking));
-  CK(cudaStreamCreateWithFlags(&h->sx, cudaStreamNonBlocking));
+  {  // the communication stream runs at the highest priority: its (small) NCCL kernels must not queue behind the element kernels
+    int lo = 0, hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CK(cudaStreamCreateWithPriority(&h->sx, cudaStreamNonBlocking, hi));
+  }
   CK(cudaEventCreateWithFlags(&h->evProd, cudaEventDisableTiming));
   for (auto& e : h->evX) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 

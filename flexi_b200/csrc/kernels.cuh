@@ -33,7 +33,7 @@ struct VolArgs {
   double* fvm;
   double* fvs;
   int fullGrad;
-  int dbg;            // k_volume_gl2 timing experiments (FLEXI_GPU_DBG): 1 skip two-point sweeps, 2 skip lifting sweeps, 4 skip node phase
+  int dbg;            // development build only (FLEXI_GPU_DEV): phase-skipping bits of the k_volume_gl2 timing experiments; 0 in the release library
   int prefetchAhead;  // k_volume_gl2: CTA b prefetches the element of CTA b+prefetchAhead into L2 (0 = off)
 };
 

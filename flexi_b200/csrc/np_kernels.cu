@@ -72,8 +72,9 @@ cudaError_t volume_gl_launch(int lift, const VolArgs& a, int nBlocks, cudaStream
 // line-resident split-form GL kernel (volume_gl2.cuh) for even NP; odd NP keeps k_volume_gl
 constexpr bool HAS_GL2 = (NP % 2 == 0);
 bool g_use_gl2 = HAS_GL2;
-// measurement hook: FLEXI_GPU_SMEM_PAD=<bytes> of extra dynamic shared memory per CTA of k_volume_gl2 (forces 1 CTA/SM to
+// measurement hook (development build only): FLEXI_GPU_SMEM_PAD=<bytes> of extra dynamic shared memory per CTA of k_volume_gl2 (forces 1 CTA/SM to
 // separate what the second resident element buys from what contention costs; profiles/README.md)
+#ifdef FLEXI_GPU_DEV
 int gl2_smem_pad() {
   static int pad = -1;
   if (pad < 0) {
@@ -82,10 +83,13 @@ int gl2_smem_pad() {
   }
   return pad;
 }
+#else
+constexpr int gl2_smem_pad() { return 0; }
+#endif
 template <int STYPE, bool PARA, int NVL, int NVC, int LIFT>
 struct GL2 {
   static constexpr int NPE = HAS_GL2 ? NP : 2;  // odd NP never instantiates the real kernel
-  using C = VolGL2Cfg<NPE, PARA>;
+  using C = VolGL2Cfg<NPE, PARA, NVC>;
   static cudaError_t setup() {
     return cudaFuncSetAttribute(k_volume_gl2<NPE, STYPE, PARA, NVL, NVC, LIFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::BYTES + gl2_smem_pad());
   }
@@ -139,8 +143,12 @@ cudaError_t gl2_launch(int lift, const VolArgs& a, int nBlocks, cudaStream_t s) 
 
 constexpr size_t upd_smem = sizeof(double) * (D::NBASIS + 5 * D::NP3);
 
+#if defined(FLEXI_GPU_DEV) && defined(FX_DEV_ONLY_PI)  // development build: compile the Pirozzoli kernels only (minutes -> seconds)
+#define FX_SPLIT_TYPES(X) X(FLEXI_SPLITDG_PI)
+#else
 #define FX_SPLIT_TYPES(X) \
   X(FLEXI_SPLITDG_SD) X(FLEXI_SPLITDG_MO) X(FLEXI_SPLITDG_DU) X(FLEXI_SPLITDG_KG) X(FLEXI_SPLITDG_PI) X(FLEXI_SPLITDG_CH) X(FLEXI_SPLITDG_IR)
+#endif
 
 cudaError_t setup() {
   cudaError_t e;

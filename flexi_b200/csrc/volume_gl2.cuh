@@ -27,6 +27,14 @@ namespace fx {
 
 __device__ __forceinline__ void cp_async_wait_group1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
+// Phase-skipping switches for timing experiments (tools/phase_timing.py): they produce wrong results and exist only in the
+// development build (make dev: -DFLEXI_GPU_DEV -> libflexi_gpu_dev.so); the release library has no such branch.
+#ifdef FLEXI_GPU_DEV
+#define FX_DBG(A, bit) (((A).dbg & (bit)) != 0)
+#else
+#define FX_DBG(A, bit) false
+#endif
+// FX_DEV_MINB=<n> (development build) overrides the resident-CTA target of __launch_bounds__.
 template <int NP>
 struct GL2Basis {
   double dt[NP * NP];   // D_T(l,i)      at [l*NP+i]  (lifting derivative, lifting_volint.t90:67-83)
@@ -46,26 +54,48 @@ __device__ __forceinline__ int gl2_phys(int i, int j, int k) {
   return i + NP * (j + NP * k);
 }
 
-template <int NP, bool PARA>
+// Shared-memory budget (NP = 8, Navier-Stokes, 4 lifted variables): 18 planes of 4 KB + the face table = 73.5 KB, so that THREE
+// elements are resident per SM (12 warps; the 25-plane layout of round 1 allowed two, and the kernel is latency-bound):
+//   P  7 planes  rho,u,v,w,p,T,X5        T is dead after the lifting phase: its plane becomes the hand-over plane of Ut(5)
+//   W  2*NVC     G1|G2 (xi-, eta-derivatives of the lifting variables), overwritten in place by f~|g~ (4+4 planes)
+//   F  3 planes  lifting flux * L_Hat of the six faces [6][NVC][NP2]; dead after the node phase: hand-over planes of Ut(2..4)
+// What round 1 kept in shared memory on top of that and where it went:
+//   * neighbour traces + face geometry (cp.async staging, 9 values per face node): the face thread now holds the raw trace in
+//     registers across the lifting sweeps and stores only the NVC lifting fluxes; the normal vector of a boundary node is read
+//     from L2 (prefetched one wave ahead) by the node's owner;
+//   * h~ (4 planes): the node phase runs in zeta ownership, so the zeta derivative of h~ is formed from registers: a thread
+//     adds the contributions of its own half line to ALL eight nodes of the line -- its own four stay with it, the other four go
+//     to the partner through the hand-over planes (same number of DFMAs as before, 16 fewer shared-memory loads per thread);
+//   * the hand-over plane of Ut(1): the density has no viscous part and is handed from sweep to sweep through the (L2-resident)
+//     output array itself.
+template <int NP, bool PARA, int NVC>
 struct VolGL2Cfg {
   using D = Dim<NP>;
   static_assert(NP % 2 == 0, "line halves need an even number of nodes");
   static constexpr int HALF = NP / 2;
   static constexpr int NT = 2 * D::NP2;
   static constexpr int PL = D::NP3;
-  static constexpr int P_PLANES = PARA ? 7 : 6;  // rho,u,v,w,p,[T],X5
-  static constexpr int W_PLANES = PARA ? 12 : 0;  // contravariant viscous fluxes f~,g~,h~ (4 each); the 2*nVarLift lifting planes alias them
-  static constexpr int F_FACE = PARA ? 6 * 9 * D::NP2 : 0;
-  static constexpr int F_DOUBLES = ((F_FACE > 5 * PL ? F_FACE : 5 * PL) + 1) & ~1;  // face staging, later the Ut hand-over planes
-  static constexpr int NFD = PARA ? ((3 * D::NP2 + 1) & ~1) : 0;                     // int table [6][NP2]
+  static constexpr int P_PLANES = PARA ? 7 : 6;      // rho,u,v,w,p,[T],X5
+  static constexpr int W_PLANES = PARA ? 2 * NVC : 0;
+  static constexpr int F_FACE = PARA ? 6 * NVC * D::NP2 : 0;
+  // hand-over planes of Ut(2..4) alias the face fluxes; Ut(5) goes to the T plane (Navier-Stokes) or a fourth plane (Euler)
+  static constexpr int F_UT = PARA ? 3 * PL : 4 * PL;
+  static constexpr int F_DOUBLES = ((F_FACE > F_UT ? F_FACE : F_UT) + 1) & ~1;
+  static constexpr int NFD = PARA ? ((3 * D::NP2 + 1) & ~1) : 0;  // int table [6][NP2]
   static constexpr int O_FDST = 0;
   static constexpr int O_ETA = O_FDST + NFD;
   static constexpr int O_P = O_ETA + (PARA ? 6 : 0);
   static constexpr int O_W = O_P + P_PLANES * PL;
   static constexpr int O_F = O_W + W_PLANES * PL;
+  static constexpr int O_UT5 = PARA ? O_P + 5 * PL : O_F + 3 * PL;
   static constexpr int DOUBLES = O_F + F_DOUBLES;
   static constexpr size_t BYTES = sizeof(double) * DOUBLES;
-  static constexpr int MINB = (BYTES <= 113000) ? 2 : 1;
+#if defined(FLEXI_GPU_DEV) && defined(FX_DEV_MINB)
+  static constexpr int MINB = FX_DEV_MINB;
+#else
+  // resident CTAs per SM the register allocation aims at: (227 KB - 1 KB reserved per CTA) / 3 = 76458 bytes
+  static constexpr int MINB = (BYTES <= 76000 && NT <= 256) ? 3 : (BYTES <= 113000) ? 2 : 1;
+#endif
 };
 
 // Canonical line positions: a thread of half 0 owns positions 0..HALF-1 and meets HALF..N as partners; a thread of half 1 walks
@@ -95,9 +125,10 @@ __device__ __forceinline__ int gl2_gn(int dir, int p, int r0, int r1) {
 
 // One direction sweep of the advective two-point fluxes (+ the weak-form derivative of the viscous flux of that direction).
 //   sa[q] / gn[q]  shared-memory address / natural node index of canonical line position q
+//   vp[v]          plane of the contravariant viscous flux of this direction, variable v+1
 //   ut[c][v]       result for the own nodes c (HALF of them), WITHOUT the half sign (the caller applies it)
 template <int NP, int STYPE, bool PARA>
-__device__ __forceinline__ void gl2_pair_sweep(const GL2Basis<NP>& B, const double* __restrict__ sP, const double* __restrict__ sWd,
+__device__ __forceinline__ void gl2_pair_sweep(const GL2Basis<NP>& B, const double* __restrict__ sP, const double* const (&vp)[4],
                                                const double* __restrict__ gMd, const int (&sa)[NP], const int (&gn)[NP],
                                                double (&ut)[NP / 2][5], const double kappa) {
   constexpr int HALF = NP / 2, PL = NP * NP * NP;
@@ -113,13 +144,15 @@ __device__ __forceinline__ void gl2_pair_sweep(const GL2Basis<NP>& B, const doub
       Mp[c][m] = __ldg(gMd + m * PL + gn[HALF + c]);
     }
 #pragma unroll
-  for (int c = 0; c < HALF; ++c) ut[c][0] = 0.;
+  for (int c = 0; c < HALF; ++c)
+#pragma unroll
+    for (int v = 0; v < 5; ++v) ut[c][v] = 0.;
   if (PARA) {  // volint.f90:310-315: Ut += D_Hat_T(l,i) * f~visc(l)
 #pragma unroll
     for (int v = 0; v < 4; ++v) {
       double L[NP];
 #pragma unroll
-      for (int p = 0; p < NP; ++p) L[p] = sWd[v * PL + sa[p]];
+      for (int p = 0; p < NP; ++p) L[p] = vp[v][sa[p]];
 #pragma unroll
       for (int c = 0; c < HALF; ++c) {  // two partial sums per node: twice the independent FP64 chains
         double s0 = B.dh[c] * L[0], s1 = B.dh[HALF * NP + c] * L[HALF];
@@ -131,11 +164,6 @@ __device__ __forceinline__ void gl2_pair_sweep(const GL2Basis<NP>& B, const doub
         ut[c][v + 1] = s0 + s1;
       }
     }
-  } else {
-#pragma unroll
-    for (int c = 0; c < HALF; ++c)
-#pragma unroll
-      for (int v = 1; v < 5; ++v) ut[c][v] = 0.;
   }
   // own half line
   double a[HALF][6];
@@ -226,10 +254,10 @@ __device__ __forceinline__ void gl2_pair_sweep(const GL2Basis<NP>& B, const doub
 // lifted: NVL, or 4 = (v1,v2,v3,T) on the time-stepping path, where nothing reads the density gradient (EvalDiffFlux3D does
 // not use it and no gradient array is handed out).
 template <int NP, int STYPE, bool PARA, int NVL, int NVC, int LIFT>
-__global__ void __launch_bounds__(VolGL2Cfg<NP, PARA>::NT, VolGL2Cfg<NP, PARA>::MINB)
+__global__ void __launch_bounds__(VolGL2Cfg<NP, PARA, NVC>::NT, VolGL2Cfg<NP, PARA, NVC>::MINB)
     k_volume_gl2(const __grid_constant__ VolArgs2<NP> AA) {
   using D = Dim<NP>;
-  using C = VolGL2Cfg<NP, PARA>;
+  using C = VolGL2Cfg<NP, PARA, NVC>;
   constexpr int HALF = C::HALF, NT = C::NT, PL = C::PL, N = NP - 1;
   constexpr bool PI = (STYPE == FLEXI_SPLITDG_PI);
   constexpr int PX = PARA ? 6 : 5;
@@ -240,11 +268,12 @@ __global__ void __launch_bounds__(VolGL2Cfg<NP, PARA>::NT, VolGL2Cfg<NP, PARA>::
   int* sFD = reinterpret_cast<int*>(sm + C::O_FDST);
   double* sEta = sm + C::O_ETA;
   double* sP = sm + C::O_P;
-  double* sW = sm + C::O_W;   // G1 | G2 lifting planes, later f~ | g~ | h~
-  double* sX = sm + C::O_F;   // face staging (lifting fluxes + normals), later the Ut hand-over planes
-  double* sUT = sX;
+  double* sW = sm + C::O_W;   // G1 | G2 lifting planes, later f~ | g~
+  double* sF = sm + C::O_F;   // lifting fluxes of the six faces, later the hand-over planes of Ut(2..4)
+  // hand-over plane of Ut(v+1), v = 1..4 (the density goes through the output array)
+  auto ut_plane = [&](int v) -> double* { return v < 4 ? sF + (v - 1) * PL : sm + C::O_UT5; };
   const int tid = threadIdx.x;
-  if (A.dbg & 8) return;  // timing experiment: the cost of scheduling one CTA per element
+  if (FX_DBG(A, 8)) return;  // timing experiment: the cost of scheduling one CTA per element
   const int e = A.elems ? A.elems[blockIdx.x] : blockIdx.x;
   const int hb = tid / D::NP2, r = tid % D::NP2;  // half index (warp-uniform for NP = 8) and position inside the NP x NP sheet
   const int r0 = r % NP, r1 = r / NP;
@@ -252,10 +281,11 @@ __global__ void __launch_bounds__(VolGL2Cfg<NP, PARA>::NT, VolGL2Cfg<NP, PARA>::
   const Eqn& q = A.q;
   const double* gU = A.U + (size_t)e * 5 * D::NP3;
   const double* gM = A.m.Met + (size_t)e * 9 * D::NP3;
+  double* gUt = A.Ut + (size_t)e * 5 * D::NP3;
   constexpr int FACE_IT = (6 * D::NP2 + NT - 1) / NT;
 
-  // ---- phase A (zeta ownership): own conservative state on its way first, then neighbour traces + face geometry (cp.async),
-  //      then ConsToPrim of the own nodes ----
+  // ---- phase A (zeta ownership): own conservative state on its way first, then the neighbour traces of the face nodes this
+  //      thread converts (registers), then ConsToPrim of the own nodes ----
   double Uc[HALF][5];
 #pragma unroll
   for (int c = 0; c < HALF; ++c)
@@ -270,8 +300,8 @@ __global__ void __launch_bounds__(VolGL2Cfg<NP, PARA>::NT, VolGL2Cfg<NP, PARA>::
     sJn = __ldg(A.m.sJ + (size_t)e * D::NP3 + n);
   }
   SideRef nsr{-1, 0};  // side of face tid/21 of that later element (its traces + geometry are prefetched after S1)
-  if (A.prefetchAhead > 0 && (int)blockIdx.x + A.prefetchAhead < A.nList && !(A.dbg & 32)) {
-    // pull the element that starts half a wave of CTAs later (U, metrics, Jacobian: 60 KB) from HBM into L2 now
+  if (A.prefetchAhead > 0 && (int)blockIdx.x + A.prefetchAhead < A.nList && !FX_DBG(A, 32)) {
+    // pull the element that starts a wave of CTAs later (U, metrics, Jacobian: 60 KB) from HBM into L2 now
     const int en = A.elems ? A.elems[blockIdx.x + A.prefetchAhead] : (int)blockIdx.x + A.prefetchAhead;
     if (PARA && tid < 126) nsr = A.m.e2s[en * 6 + tid / 21];
     const char* pu = reinterpret_cast<const char*>(A.U + (size_t)en * 5 * D::NP3);
@@ -286,26 +316,25 @@ __global__ void __launch_bounds__(VolGL2Cfg<NP, PARA>::NT, VolGL2Cfg<NP, PARA>::
   int faceSlot[FACE_IT];
   bool faceLh[FACE_IT];  // plus side: L_HatPlus(N) (BR1)
   double faceSgn[FACE_IT];
-  if (PARA && !(A.dbg & 16)) {
+  double fU[FACE_IT][5], fSurf[FACE_IT];  // raw neighbour trace + SurfElem of the face node, held until the lifting sweeps are done
+  if (PARA && !FX_DBG(A, 16)) {
 #pragma unroll
     for (int it = 0; it < FACE_IT; ++it) {
       const int t = tid + it * NT;
       faceSlot[it] = -1;
       faceLh[it] = false;
       faceSgn[it] = 0.;
+      fSurf[it] = 0.;
+#pragma unroll
+      for (int v = 0; v < 5; ++v) fU[it][v] = 1.;
       if (t < 6 * D::NP2) {
         const int ls = t / D::NP2 + 1, pq = t % D::NP2;
         const SideRef sr = A.m.e2s[e * 6 + ls - 1];
         const int ab = A.m.s2v2[(sr.flip * 6 + ls - 1) * D::NP2 + pq];
         const double* nbTrace = ((sr.flip == 0) ? A.U_slave : A.U_master) + (size_t)sr.side * 5 * D::NP2 + pq;
-        const double* g = A.m.Geo + (size_t)sr.side * 10 * D::NP2 + pq;
-        double* o = sX + (ls - 1) * 9 * D::NP2 + ab;
 #pragma unroll
-        for (int v = 0; v < 5; ++v) cp_async8(o + v * D::NP2, nbTrace + v * D::NP2);
-        cp_async8(o + 5 * D::NP2, g);
-        cp_async8(o + 6 * D::NP2, g + D::NP2);
-        cp_async8(o + 7 * D::NP2, g + 2 * D::NP2);
-        cp_async8(o + 8 * D::NP2, g + 9 * D::NP2);
+        for (int v = 0; v < 5; ++v) fU[it][v] = __ldg(nbTrace + v * D::NP2);
+        fSurf[it] = __ldg(A.m.Geo + (size_t)sr.side * 10 * D::NP2 + 9 * D::NP2 + pq);
         // destination of this face node's traces: side*NP2 + pq, bit 31 = slave arrays, bit 30 = boundary-condition side
         sFD[(ls - 1) * D::NP2 + ab] =
             (sr.side * D::NP2 + pq) | (sr.flip == 0 ? 0 : (int)0x80000000) | (sr.side < A.m.nBCSides ? 0x40000000 : 0);
@@ -326,12 +355,11 @@ __global__ void __launch_bounds__(VolGL2Cfg<NP, PARA>::NT, VolGL2Cfg<NP, PARA>::
           vn = gl2_phys<NP>(fa, fd, fb);
         else
           vn = gl2_phys<NP>(fa, fb, fd);
-        faceSlot[it] = ((ls - 1) * 9 * D::NP2 + ab) | (vn << 16);
+        faceSlot[it] = ((ls - 1) * NVC * D::NP2 + ab) | (vn << 16);
         faceSgn[it] = (sr.flip == 0) ? 1. : -1.;
         faceLh[it] = !is_minus_side(ls);
       }
     }
-    cp_async_commit();
   }
 #pragma unroll
   for (int c = 0; c < HALF; ++c) {
@@ -364,7 +392,7 @@ __global__ void __launch_bounds__(VolGL2Cfg<NP, PARA>::NT, VolGL2Cfg<NP, PARA>::
     //      xi and eta results change owner through the planes G1, G2; the zeta result stays with this thread ----
     double gzt[HALF][NVC];
 #pragma unroll 1
-    for (int dir = (A.dbg & 2) ? 3 : 0; dir < 3; ++dir) {
+    for (int dir = FX_DBG(A, 2) ? 3 : 0; dir < 3; ++dir) {
       int sa[NP];
 #pragma unroll
       for (int p = 0; p < NP; ++p) sa[p] = gl2_sa<NP>(dir, gl2_ap<NP>(hb, p), r0, r1);
@@ -393,32 +421,32 @@ __global__ void __launch_bounds__(VolGL2Cfg<NP, PARA>::NT, VolGL2Cfg<NP, PARA>::
       }
     }
     // ---- lifting flux of the six faces (lifting_fillflux.t90:81-107, strong form):
-    //      0.5*(UPrim_slave-UPrim_master)*SurfElem per lifting variable, already times L_Hat of the face, in place of the
-    //      prefetched neighbour trace.  Every thread converts the face nodes it fetched itself, so its own wait is enough; the
-    //      loads had the line sweeps above to arrive. ----
-    cp_async_wait_all();
+    //      0.5*(UPrim_slave-UPrim_master)*SurfElem per lifting variable, already times L_Hat of the face.  The neighbour trace
+    //      had the line sweeps above to arrive. ----
 #pragma unroll
     for (int it = 0; it < FACE_IT; ++it) {
-      if (faceSlot[it] >= 0 && !(A.dbg & 16)) {
-        double* o = sX + (faceSlot[it] & 0xffff);
+      if (faceSlot[it] >= 0 && !FX_DBG(A, 16)) {
+        double* o = sF + (faceSlot[it] & 0xffff);
         const int nF = faceSlot[it] >> 16;
-        double Un[5], Pb[6];
-#pragma unroll
-        for (int v = 0; v < 5; ++v) Un[v] = o[v * D::NP2];
-        const double surf = o[8 * D::NP2];
+        double Pb[6];
         const double lh = (LIFT == 1 && faceLh[it]) ? B.lhpN : B.lhm0;
-        cons_to_prim(q, Un, Pb);
+        cons_to_prim(q, fU[it], Pb);
 #pragma unroll
         for (int v = 0; v < NVC; ++v) {
           const int pv = lift_prim(NVC, v);
-          o[v * D::NP2] = (0.5 * (faceSgn[it] * (Pb[pv] - sP[pv * PL + nF])) * surf) * lh;
+          o[v * D::NP2] = (0.5 * (faceSgn[it] * (Pb[pv] - sP[pv * PL + nF])) * fSurf[it]) * lh;
         }
       }
     }
     __syncthreads();  // S2: G1, G2 and the face lifting fluxes complete
 
     // ---- zeta ownership: metric combination, surface part, Jacobian, traces for the side kernel, viscous flux ----
-    if (!(A.dbg & 4)) {
+    double hvc[HALF][4];  // h~ of the own nodes: its zeta derivative is formed from registers after S3
+#pragma unroll
+    for (int c = 0; c < HALF; ++c)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) hvc[c][v] = 0.;
+    if (!FX_DBG(A, 4)) {
       constexpr int LV = (NVC == 5) ? 1 : 0;
       const int i = r0, j = r1;
 #pragma unroll
@@ -436,6 +464,26 @@ __global__ void __launch_bounds__(VolGL2Cfg<NP, PARA>::NT, VolGL2Cfg<NP, PARA>::
           for (int m = 0; m < 9; ++m) Mn[m] = __ldg(gM + m * D::NP3 + n1);
           sJn = __ldg(A.m.sJ + (size_t)e * D::NP3 + n1);
         }
+        // ---- boundary nodes.  One (partially active) block per sheet direction instead of one per local side: the lanes of a
+        //      warp that sit on xi- and xi+ run the same code with their own side index.  The zeta faces belong to the line
+        //      end c == 0 of every thread (k = 0 for half 0, k = N for half 1), a warp-uniform condition. ----
+        const bool onI = (i == 0) | (i == N), onJ = (j == 0) | (j == N), onK = (c == 0);
+        const int lsI = (i == 0) ? XI_MINUS : XI_PLUS, lsJ = (j == 0) ? ETA_MINUS : ETA_PLUS, lsK = hb ? ZETA_PLUS : ZETA_MINUS;
+        const int abI = j + NP * k, abJ = i + NP * k, abK = i + NP * j;
+        // trace destination + normal vector of the (up to three) faces of this node; the vector comes from L2 (prefetched)
+        int fdI = 0, fdJ = 0, fdK = 0;
+        double nI[3] = {0., 0., 0.}, nJ[3] = {0., 0., 0.}, nK[3] = {0., 0., 0.};
+        auto face_geo = [&](int ls, int ab, int& fd, double (&nv)[3]) {
+          fd = sFD[(ls - 1) * D::NP2 + ab];
+          const int fl = fd & 0x3fffffff;
+          const double* g = A.m.Geo + (size_t)(fl / D::NP2) * 10 * D::NP2 + fl % D::NP2;
+          nv[0] = __ldg(g);
+          nv[1] = __ldg(g + D::NP2);
+          nv[2] = __ldg(g + 2 * D::NP2);
+        };
+        if (onI) face_geo(lsI, abI, fdI, nI);
+        if (onJ) face_geo(lsJ, abJ, fdJ, nJ);
+        if (onK) face_geo(lsK, abK, fdK, nK);
         double gx[NVC], gy[NVC], gz[NVC];
 #pragma unroll
         for (int v = 0; v < NVC; ++v) {
@@ -444,35 +492,28 @@ __global__ void __launch_bounds__(VolGL2Cfg<NP, PARA>::NT, VolGL2Cfg<NP, PARA>::
           gy[v] = Mc[1] * gxi + Mc[4] * geta + Mc[7] * gzeta;
           gz[v] = Mc[2] * gxi + Mc[5] * geta + Mc[8] * gzeta;
         }
-        // ---- boundary nodes.  One (partially active) block per sheet direction instead of one per local side: the lanes of a
-        //      warp that sit on xi- and xi+ run the same code with their own side index.  The zeta faces belong to the line
-        //      end c == 0 of every thread (k = 0 for half 0, k = N for half 1), a warp-uniform condition. ----
-        const bool onI = (i == 0) | (i == N), onJ = (j == 0) | (j == N), onK = (c == 0);
-        const int lsI = (i == 0) ? XI_MINUS : XI_PLUS, lsJ = (j == 0) ? ETA_MINUS : ETA_PLUS, lsK = hb ? ZETA_PLUS : ZETA_MINUS;
-        const int abI = j + NP * k, abJ = i + NP * k, abK = i + NP * j;
         double gxo[NVC], gyo[NVC], gzo[NVC];  // BR2: gradients without the surface part (what the faces are prolonged from)
         // lifting, surface part (BR1 lifting_br1.t90:195-292; BR2 lifting_br2.t90:194-311)
-        auto surf_in = [&](int ls, int ab) {
-          const double* o = sX + (ls - 1) * 9 * D::NP2 + ab;
-          const double n0 = o[5 * D::NP2], n1 = o[6 * D::NP2], n2 = o[7 * D::NP2];
+        auto surf_in = [&](int ls, int ab, const double (&nv)[3]) {
+          const double* o = sF + (ls - 1) * NVC * D::NP2 + ab;
 #pragma unroll
           for (int v = 0; v < NVC; ++v) {
             const double f = o[v * D::NP2];  // Flux * L_Hat
             if (LIFT == 1) {
-              gx[v] = gx[v] + f * n0;
-              gy[v] = gy[v] + f * n1;
-              gz[v] = gz[v] + f * n2;
+              gx[v] = gx[v] + f * nv[0];
+              gy[v] = gy[v] + f * nv[1];
+              gz[v] = gz[v] + f * nv[2];
             } else {
-              gx[v] = gx[v] + sJc * (f * n0);
-              gy[v] = gy[v] + sJc * (f * n1);
-              gz[v] = gz[v] + sJc * (f * n2);
+              gx[v] = gx[v] + sJc * (f * nv[0]);
+              gy[v] = gy[v] + sJc * (f * nv[1]);
+              gz[v] = gz[v] + sJc * (f * nv[2]);
             }
           }
         };
         if (LIFT == 1) {  // BR1: surface part, then ApplyJacobianLifting
-          if (onI) surf_in(lsI, abI);
-          if (onJ) surf_in(lsJ, abJ);
-          if (onK) surf_in(lsK, abK);
+          if (onI) surf_in(lsI, abI, nI);
+          if (onJ) surf_in(lsJ, abJ, nJ);
+          if (onK) surf_in(lsK, abK, nK);
 #pragma unroll
           for (int v = 0; v < NVC; ++v) {
             gx[v] = gx[v] * sJc;
@@ -489,9 +530,9 @@ __global__ void __launch_bounds__(VolGL2Cfg<NP, PARA>::NT, VolGL2Cfg<NP, PARA>::
             gyo[v] = gy[v];
             gzo[v] = gz[v];
           }
-          if (onI) surf_in(lsI, abI);
-          if (onJ) surf_in(lsJ, abJ);
-          if (onK) surf_in(lsK, abK);
+          if (onI) surf_in(lsI, abI, nI);
+          if (onJ) surf_in(lsJ, abJ, nJ);
+          if (onK) surf_in(lsK, abK, nK);
         }
         if (A.gvol[0]) {
 #pragma unroll
@@ -511,21 +552,19 @@ __global__ void __launch_bounds__(VolGL2Cfg<NP, PARA>::NT, VolGL2Cfg<NP, PARA>::
         //      writes n.F_v of its own side (4 doubles per face node) instead of the 3*nVarLifting gradient traces.  The
         //      gradient traces themselves are still written for boundary-condition sides (GetBoundaryFlux needs them) and, when
         //      the host asked for a full DG operator evaluation, for every side. ----
-        auto face_out = [&](int ls, int ab) {
-          const int fd = sFD[(ls - 1) * D::NP2 + ab];
+        auto face_out = [&](int ls, int ab, int fd, const double (&nv)[3]) {
           const bool master = fd >= 0;
           const int fl = fd & 0x3fffffff, side = fl / D::NP2, pq = fl % D::NP2;
-          const double* of = sX + (ls - 1) * 9 * D::NP2 + ab;
-          const double n0 = of[5 * D::NP2], n1 = of[6 * D::NP2], n2 = of[7 * D::NP2];
           double gfx[NVC], gfy[NVC], gfz[NVC];
           if (LIFT == 2) {  // BR2 face gradient: volume-only value + eta*L_Minus(0)*sJ*Flux*L_HatMinus(0) of the side itself
+            const double* of = sF + (ls - 1) * NVC * D::NP2 + ab;
             const double w = sEta[ls - 1] * B.lm0;
 #pragma unroll
             for (int v = 0; v < NVC; ++v) {
               const double f = of[v * D::NP2];
-              gfx[v] = gxo[v] + w * (sJc * (f * n0));
-              gfy[v] = gyo[v] + w * (sJc * (f * n1));
-              gfz[v] = gzo[v] + w * (sJc * (f * n2));
+              gfx[v] = gxo[v] + w * (sJc * (f * nv[0]));
+              gfy[v] = gyo[v] + w * (sJc * (f * nv[1]));
+              gfz[v] = gzo[v] + w * (sJc * (f * nv[2]));
             }
           }
           if (A.fullGrad || (fd & 0x40000000)) {
@@ -546,32 +585,44 @@ __global__ void __launch_bounds__(VolGL2Cfg<NP, PARA>::NT, VolGL2Cfg<NP, PARA>::
             double ff[4], gf[4], hf[4];
             eval_diff_flux3d(q, v1, v2, v3, gfx + LV, gfy + LV, gfz + LV, ff, gf, hf);
 #pragma unroll
-            for (int v = 0; v < 4; ++v) dv[v * D::NP2] = n0 * ff[v] + n1 * gf[v] + n2 * hf[v];
+            for (int v = 0; v < 4; ++v) dv[v * D::NP2] = nv[0] * ff[v] + nv[1] * gf[v] + nv[2] * hf[v];
           } else {
 #pragma unroll
-            for (int v = 0; v < 4; ++v) dv[v * D::NP2] = n0 * fv[v] + n1 * gv[v] + n2 * hv[v];
+            for (int v = 0; v < 4; ++v) dv[v * D::NP2] = nv[0] * fv[v] + nv[1] * gv[v] + nv[2] * hv[v];
           }
         };
-        if (onI) face_out(lsI, abI);
-        if (onJ) face_out(lsJ, abJ);
-        if (onK) face_out(lsK, abK);
-        // ---- contravariant components (volint.f90:378-422), written over the node's own G1/G2 slots (only this thread reads
-        //      them) ----
+        if (onI) face_out(lsI, abI, fdI, nI);
+        if (onJ) face_out(lsJ, abJ, fdJ, nJ);
+        if (onK) face_out(lsK, abK, fdK, nK);
+        // ---- contravariant components (volint.f90:378-422): f~, g~ over the node's own G1/G2 slots (only this thread reads
+        //      them), h~ stays in registers ----
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
           sW[(0 + v) * PL + s] = fv[v] * Mc[0] + gv[v] * Mc[1] + hv[v] * Mc[2];
           sW[(4 + v) * PL + s] = fv[v] * Mc[3] + gv[v] * Mc[4] + hv[v] * Mc[5];
-          sW[(8 + v) * PL + s] = fv[v] * Mc[6] + gv[v] * Mc[7] + hv[v] * Mc[8];
+          hvc[c][v] = fv[v] * Mc[6] + gv[v] * Mc[7] + hv[v] * Mc[8];
         }
       }
     }
-    __syncthreads();  // S3: viscous flux planes complete; face staging is free from here on
+    __syncthreads();  // S3: f~, g~ complete; the face fluxes and the T plane are free from here on
+
+    // ---- h~ of the own nodes goes to the (now free) hand-over planes: the zeta sweep, which comes first, reads it from there
+    //      like the other two sweeps read f~ and g~ ----
+#pragma unroll
+    for (int c = 0; c < HALF; ++c) {
+      const int s = gl2_sa<NP>(2, gl2_ap<NP>(hb, c), r0, r1);
+#pragma unroll
+      for (int v = 0; v < 4; ++v) ut_plane(v + 1)[s] = hvc[c][v];
+    }
+    __syncthreads();  // S3b
   }
 
-  // ---- three direction sweeps (zeta, xi, eta) of ONE copy of the sweep code; the partial sums change owner through the Ut
-  //      hand-over planes, the last sweep sends the raw volume integral to HBM ----
+  // ---- three direction sweeps (zeta, xi, eta) of ONE copy of the sweep code.  The partial sums change owner twice: after the
+  //      zeta sweep through the output array itself (it stays in L2; the hand-over planes still hold h~ while partners read it),
+  //      after the xi sweep through the hand-over planes (density: output array again); the eta sweep sends the raw volume
+  //      integral to HBM ----
 #pragma unroll 1
-  for (int it = (A.dbg & 1) ? 3 : 0; it < 3; ++it) {
+  for (int it = FX_DBG(A, 1) ? 3 : 0; it < 3; ++it) {
     const int dir = (it == 0) ? 2 : it - 1;
     int sa[NP], gn[NP];  // indexed by canonical position
 #pragma unroll
@@ -579,24 +630,27 @@ __global__ void __launch_bounds__(VolGL2Cfg<NP, PARA>::NT, VolGL2Cfg<NP, PARA>::
       sa[p] = gl2_sa<NP>(dir, gl2_ap<NP>(hb, p), r0, r1);
       gn[p] = gl2_gn<NP>(dir, gl2_ap<NP>(hb, p), r0, r1);
     }
+    const double* vp[4];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) vp[v] = (dir < 2) ? sW + (dir * 4 + v) * PL : ut_plane(v + 1);
     double ut[HALF][5];
-    gl2_pair_sweep<NP, STYPE, PARA>(B, sP, sW + dir * 4 * PL, gM + dir * 3 * D::NP3, sa, gn, ut, A.q.kappa);
-    if (it < 2) {
+    gl2_pair_sweep<NP, STYPE, PARA>(B, sP, vp, gM + dir * 3 * D::NP3, sa, gn, ut, A.q.kappa);
 #pragma unroll
-      for (int c = 0; c < HALF; ++c)
+    for (int c = 0; c < HALF; ++c) {
+      if (it == 0) {
 #pragma unroll
-        for (int v = 0; v < 5; ++v) {
-          double* p = sUT + v * PL + sa[c];
-          const double prev = (it == 0) ? 0. : *p;
-          *p = prev + sg * ut[c][v];
-        }
-      __syncthreads();  // S4, S5
-    } else {
+        for (int v = 0; v < 5; ++v) gUt[v * D::NP3 + gn[c]] = sg * ut[c][v];
+      } else if (it == 1) {
+        gUt[gn[c]] = __ldcg(gUt + gn[c]) + sg * ut[c][0];
 #pragma unroll
-      for (int c = 0; c < HALF; ++c)
+        for (int v = 1; v < 5; ++v) ut_plane(v)[sa[c]] = __ldcg(gUt + v * D::NP3 + gn[c]) + sg * ut[c][v];
+      } else {
+        gUt[gn[c]] = __ldcg(gUt + gn[c]) + sg * ut[c][0];
 #pragma unroll
-        for (int v = 0; v < 5; ++v) A.Ut[((size_t)e * 5 + v) * D::NP3 + gn[c]] = sUT[v * PL + sa[c]] + sg * ut[c][v];
+        for (int v = 1; v < 5; ++v) gUt[v * D::NP3 + gn[c]] = ut_plane(v)[sa[c]] + sg * ut[c][v];
+      }
     }
+    if (it < 2) __syncthreads();  // S4, S5
   }
 }
 

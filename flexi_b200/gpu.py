@@ -19,7 +19,8 @@ import numpy as np
 from .desc import FlexiGpuDesc
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libflexi_gpu.so")
+# FLEXI_GPU_LIB: the development library of the timing tools (tools/*.py); there is no fallback either way
+LIB_PATH = os.environ.get("FLEXI_GPU_LIB") or os.path.join(_HERE, "lib", "libflexi_gpu.so")
 _LIB = None
 
 ARRAYS = dict(U=0, Ut=1, U_master=2, U_slave=3, Flux=4, gradUx=5, gradUy=6, gradUz=7, gradUx_master=8, gradUy_master=9,

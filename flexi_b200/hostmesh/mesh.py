@@ -48,11 +48,91 @@ def conforming_flip(master_loc_side, slave_loc_side):
 _FLIP_TABLE = {(s, _OPPOSITE[s]): conforming_flip(s, _OPPOSITE[s]) for s in range(1, 7)}
 
 
+# ---- element orientations ("unstructured" connectivity on a structured block) --------------------------------------------------
+# A HOPR mesh from an unstructured generator gives every hexahedron its own local frame: neighbouring elements meet with any
+# pair of local sides and any of the flips 0..4 (mappings.f90:188-215).  An orientation is one of the 24 proper rotations of
+# the cube: local axis a (xi, eta, zeta) runs along block axis perm[a] in direction sign[a] (det = +1: positive Jacobians).
+def _rotations():
+    import itertools
+
+    out = []
+    for perm in itertools.permutations(range(3)):
+        for sign in itertools.product((1, -1), repeat=3):
+            R = np.zeros((3, 3))
+            for a in range(3):
+                R[perm[a], a] = sign[a]
+            if np.linalg.det(R) > 0:
+                out.append((perm, sign))
+    out.sort(key=lambda o: (o != ((0, 1, 2), (1, 1, 1))))  # orientation 0 = the block-aligned frame
+    return out
+
+
+ORIENTATIONS = _rotations()
+N_ORIENT = len(ORIENTATIONS)  # 24
+# block direction (axis, sign) of local side s of an element with orientation o, and its inverse
+_ORI_GAXIS = np.zeros((N_ORIENT, 6), dtype=np.int64)
+_ORI_GSIGN = np.zeros((N_ORIENT, 6), dtype=np.int64)
+_ORI_LOCSIDE = np.zeros((N_ORIENT, 3, 2), dtype=np.int64)  # [o, block axis, (sign+1)//2] -> local side (1-based)
+for _o, (_perm, _sign) in enumerate(ORIENTATIONS):
+    for _s in range(1, 7):
+        _ax, _sg = _SIDE_AXIS[_s]
+        _ORI_GAXIS[_o, _s - 1] = _perm[_ax]
+        _ORI_GSIGN[_o, _s - 1] = _sg * _sign[_ax]
+        _ORI_LOCSIDE[_o, _perm[_ax], (_sg * _sign[_ax] + 1) // 2] = _s
+
+
+def _local_to_block_index(o, n, i, j, k):
+    """Block-frame in-cell node index (a0,a1,a2) of local node (i,j,k) of an element with orientation o (n = N)."""
+    perm, sign = ORIENTATIONS[o]
+    loc = (i, j, k)
+    out = [0, 0, 0]
+    for a in range(3):
+        out[perm[a]] = loc[a] if sign[a] > 0 else n - loc[a]
+    return tuple(out)
+
+
+_ORI_FLIP_CACHE = {}
+
+
+def oriented_flip(o_m, ls_m, o_s, ls_s):
+    """Flip of the slave side: the f with S2V2(p,q,f,ls_s) of the slave == S2V2(p,q,0,ls_m) of the master AS PHYSICAL POINTS
+    (mappings.f90:389-397), found by comparing block-frame face-node indices of the two elements (n = 3 suffices)."""
+    key = (o_m, ls_m, o_s, ls_s)
+    if key in _ORI_FLIP_CACHE:
+        return _ORI_FLIP_CACHE[key]
+    n = 3
+    gax = _ORI_GAXIS[o_m, ls_m - 1]
+    assert gax == _ORI_GAXIS[o_s, ls_s - 1] and _ORI_GSIGN[o_m, ls_m - 1] == -_ORI_GSIGN[o_s, ls_s - 1], "sides do not face each other"
+    keep = [a for a in range(3) if a != gax]
+
+    def face_pts(o, ls, f):
+        pts = {}
+        for p in range(n + 1):
+            for q in range(n + 1):
+                a, b = MP.side_to_vol2(n, p, q, f, ls)
+                if ls in (MP.XI_MINUS, MP.XI_PLUS):
+                    ijk = (0 if ls == MP.XI_MINUS else n, a, b)
+                elif ls in (MP.ETA_MINUS, MP.ETA_PLUS):
+                    ijk = (a, 0 if ls == MP.ETA_MINUS else n, b)
+                else:
+                    ijk = (a, b, 0 if ls == MP.ZETA_MINUS else n)
+                blk = _local_to_block_index(o, n, *ijk)
+                pts[(p, q)] = (blk[keep[0]], blk[keep[1]])
+        return pts
+
+    ref = face_pts(o_m, ls_m, 0)
+    for f in range(5):
+        if face_pts(o_s, ls_s, f) == ref:
+            _ORI_FLIP_CACHE[key] = f
+            return f
+    raise RuntimeError("no flip found for %r" % (key,))
+
+
 class BoxSpec:
     """Global description of a structured hexahedral box mesh (what the HOPR file would contain)."""
 
     def __init__(self, nel, x0=(0.0, 0.0, 0.0), length=(2 * np.pi,) * 3, periodic=(True, True, True), ngeo=1,
-                 deform=0.0, bc_of_face=None, mapping=None):
+                 deform=0.0, bc_of_face=None, mapping=None, orient_seed=None):
         self.nel = tuple(int(v) for v in nel)
         self.x0 = np.asarray(x0, dtype=float)
         self.length = np.asarray(length, dtype=float)
@@ -63,6 +143,12 @@ class BoxSpec:
         self.bc_of_face = bc_of_face or {}
         # optional callable X(xhat) mapping the unit cube [0,1]^3 (array [...,3]) to physical space (curved meshes)
         self.mapping = mapping
+        # orient_seed: every element gets a random one of the 24 local frames (None = all block-aligned, the HOPR box mesh)
+        n_glob = self.nel[0] * self.nel[1] * self.nel[2]
+        if orient_seed is None:
+            self.orient = np.zeros(n_glob, dtype=np.int64)
+        else:
+            self.orient = np.random.default_rng(int(orient_seed)).integers(0, N_ORIENT, size=n_glob)
         for a in range(3):
             if self.periodic[a] and self.nel[a] < 2:
                 raise ValueError("periodic directions need at least 2 elements")
@@ -96,12 +182,32 @@ class BoxSpec:
         X[..., 1] = ((iy[:, None] + t[None, :]) * h[1])[:, None, :, None]
         X[..., 2] = ((iz[:, None] + t[None, :]) * h[2])[:, :, None, None]
         if self.mapping is not None:
-            return self.mapping(X)
-        if self.deform != 0.0:
-            xh = 2.0 * X
-            d = self.deform * np.sin(np.pi * xh[..., 0]) * np.sin(np.pi * xh[..., 1]) * np.sin(np.pi * xh[..., 2])
-            X = X + 0.5 * d[..., None]
-        return self.x0 + X * self.length
+            X = self.mapping(X)
+        else:
+            if self.deform != 0.0:
+                xh = 2.0 * X
+                d = self.deform * np.sin(np.pi * xh[..., 0]) * np.sin(np.pi * xh[..., 1]) * np.sin(np.pi * xh[..., 2])
+                X = X + 0.5 * d[..., None]
+            X = self.x0 + X * self.length
+        return self._to_local_frames(X, self.orient[np.asarray(gids)])
+
+    @staticmethod
+    def _to_local_frames(X, orient):
+        """Block-frame node array X[e,k,j,i,3] -> the same nodes indexed in each element's own (xi,eta,zeta) frame."""
+        if not np.any(orient):
+            return X
+        out = np.empty_like(X)
+        for o in np.unique(orient):
+            sel = np.nonzero(orient == o)[0]
+            perm, sign = ORIENTATIONS[o]
+            Y = X[sel]  # axes (e, a2, a1, a0, c): block axis b sits at array axis 3 - b
+            # local axis a runs along block axis perm[a]: array axis (3 - a) of the result takes array axis (3 - perm[a]) of Y
+            Y = np.transpose(Y, (0, 3 - perm[2], 3 - perm[1], 3 - perm[0], 4))
+            for a in range(3):
+                if sign[a] < 0:
+                    Y = np.flip(Y, axis=3 - a)
+            out[sel] = Y
+        return out
 
 
 def partition_owner(spec, nranks, kind="linear", blocks=None):
@@ -149,31 +255,39 @@ def build_mesh(spec, N, node_type, rank=0, nranks=1, partition="linear", blocks=
 
     # ---- neighbour tables over (elem, locSide) -------------------------------------------------------------------------
     ix, iy, iz = spec.ijk(gids)
-    idx = [ix, iy, iz]
+    idx = np.stack([ix, iy, iz], axis=1)
+    ori = spec.orient[gids]
     nb_gid = np.zeros((nE, 6), dtype=np.int64)
+    nb_side = np.zeros((nE, 6), dtype=np.int64)       # local side (1-based) of the neighbour that faces this side
     face_gid = np.zeros((nE, 6), dtype=np.int64)
     bc_idx = np.zeros((nE, 6), dtype=np.int64)
-    npl = [spec.nel[0] + 1, spec.nel[1] + 1, spec.nel[2] + 1]
+    nel = np.asarray(spec.nel)
+    npl = nel + 1
+    per = np.asarray(spec.periodic)
+    bc_lut = np.zeros((3, 2), dtype=np.int64)
+    for (ax_, sg_), b_ in spec.bc_of_face.items():
+        bc_lut[ax_, (sg_ + 1) // 2] = b_
+    ar = np.arange(nE)
     for s in range(1, 7):
-        ax, sg = _SIDE_AXIS[s]
-        j = [ix.copy(), iy.copy(), iz.copy()]
-        j[ax] = idx[ax] + sg
-        plane = idx[ax] + (1 if sg > 0 else 0)          # face plane index along ax, 0..nel
-        outside = (j[ax] < 0) | (j[ax] >= spec.nel[ax])
-        if spec.periodic[ax]:
-            j[ax] = j[ax] % spec.nel[ax]
-            plane = plane % spec.nel[ax]
-            nb = spec.gid(j[0], j[1], j[2])
-        else:
-            nb = np.where(outside, -1, spec.gid(np.clip(j[0], 0, spec.nel[0] - 1), np.clip(j[1], 0, spec.nel[1] - 1),
-                                                np.clip(j[2], 0, spec.nel[2] - 1)))
-            if np.any(outside):
-                bc_idx[outside, s - 1] = spec.bc_of_face[(ax, sg)]
-        f = [ix, iy, iz]
-        f = [f[0], f[1], f[2]]
-        f[ax] = plane
-        face_gid[:, s - 1] = 1 + ax + 3 * (f[0] + npl[0] * (f[1] + npl[1] * f[2]))   # 1-based global side index ("ind")
+        ax, sg = _ORI_GAXIS[ori, s - 1], _ORI_GSIGN[ori, s - 1]   # block direction of this local side, per element
+        j = idx.copy()
+        j[ar, ax] += sg
+        plane = idx[ar, ax] + (sg > 0)                             # face plane index along ax, 0..nel
+        outside = (j[ar, ax] < 0) | (j[ar, ax] >= nel[ax])
+        wrap = per[ax]
+        j[ar, ax] = np.where(wrap, j[ar, ax] % nel[ax], j[ar, ax])
+        plane = np.where(wrap, plane % nel[ax], plane)
+        is_out = outside & ~wrap
+        jc = np.clip(j, 0, nel - 1)
+        nb = np.where(is_out, -1, spec.gid(jc[:, 0], jc[:, 1], jc[:, 2]))
+        if np.any(is_out):
+            bc_idx[is_out, s - 1] = bc_lut[ax[is_out], (sg[is_out] + 1) // 2]
+            assert np.all(bc_idx[is_out, s - 1] > 0), "non-periodic face without a bc_of_face entry"
+        f = idx.copy()
+        f[ar, ax] = plane
+        face_gid[:, s - 1] = 1 + ax + 3 * (f[:, 0] + npl[0] * (f[:, 1] + npl[1] * f[:, 2]))   # 1-based global side index ("ind")
         nb_gid[:, s - 1] = nb
+        nb_side[:, s - 1] = _ORI_LOCSIDE[spec.orient[np.clip(nb, 0, None)], ax, (1 - sg) // 2]
     nb_rank = np.where(nb_gid >= 0, owner[np.clip(nb_gid, 0, None)], -1)
     is_bc = nb_gid < 0
     is_inner = (~is_bc) & (nb_rank == rank)
@@ -207,10 +321,7 @@ def build_mesh(spec, N, node_type, rank=0, nranks=1, partition="linear", blocks=
     me, ms = np.where(a_master, ea, eb), np.where(a_master, sa, sb)
     se, ss = np.where(a_master, eb, ea), np.where(a_master, sb, sa)
     flip[me, ms] = 0
-    flip_lut = np.zeros((7, 7), dtype=np.int64)
-    for (a, b), fv in _FLIP_TABLE.items():
-        flip_lut[a, b] = fv
-    flip[se, ss] = flip_lut[ms + 1, ss + 1]
+    flip[se, ss] = _flips(ori[me], ms + 1, ori[se], ss + 1)
 
     # MPI sides
     nb_procs = sorted(set(nb_rank[is_mpi].tolist()))
@@ -247,7 +358,8 @@ def build_mesh(spec, N, node_type, rank=0, nranks=1, partition="linear", blocks=
             sid = np.where(mine, pos - nYOUR_proc[inb] + off_mine[inb], pos + off_your[inb])
         side_id[e_m, s_m] = sid
         is_mine[e_m, s_m] = mine
-        flip[e_m, s_m] = np.where(mine, 0, flip_lut[_opp_arr(s_m + 1), s_m + 1])
+        rem_o = spec.orient[nb_gid[e_m, s_m]]
+        flip[e_m, s_m] = np.where(mine, 0, _flips(rem_o, nb_side[e_m, s_m], ori[e_m], s_m + 1))
     nSides = off_your[-1]
     m.nSides, m.nBCSides, m.nInnerSides = nSides, nBC, nInner
     m.nMPISides_MINE, m.nMPISides_YOUR = sum(nMINE_proc), sum(nYOUR_proc)
@@ -324,12 +436,25 @@ def build_mesh(spec, N, node_type, rank=0, nranks=1, partition="linear", blocks=
             k = len(rem_gid)
             sid_rem = np.zeros((k, 6), dtype=np.int64)
             sel = np.zeros((k, 6), dtype=bool)
-            rem_side = _opp_arr(s_y[sl] + 1) - 1
+            rem_side = nb_side[e_y[sl], s_y[sl]] - 1
             sid_rem[np.arange(k), rem_side] = side_id[e_y[sl], s_y[sl]]
             sel[np.arange(k), rem_side] = True
             _surface_metrics(m, geo, sid_rem, np.zeros((k, 6), dtype=np.int64), sel, ops, S2V2, with_ja_face)
     m.nb_gid, m.nb_rank, m.face_gid = nb_gid, nb_rank, face_gid
     return m
+
+
+def _flips(o_m, ls_m, o_s, ls_s):
+    """oriented_flip over arrays (orientation of the master element, its local side, the same for the slave)."""
+    o_m, ls_m, o_s, ls_s = np.broadcast_arrays(o_m, ls_m, o_s, ls_s)
+    key = ((o_m * 7 + ls_m) * N_ORIENT + o_s) * 7 + ls_s
+    out = np.zeros(key.shape, dtype=np.int64)
+    for k in np.unique(key):
+        ls_s_, r = k % 7, k // 7
+        o_s_, r = r % N_ORIENT, r // N_ORIENT
+        ls_m_, o_m_ = r % 7, r // 7
+        out[key == k] = oriented_flip(int(o_m_), int(ls_m_), int(o_s_), int(ls_s_))
+    return out
 
 
 def _opp_arr(s):

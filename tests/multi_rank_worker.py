@@ -38,6 +38,8 @@ CASES["splitG"] = (4, B.NODE_GAUSS, dict(parabolic=True, split_dg=True, split_dg
 CASES["splitCH"] = (5, B.NODE_GAUSS_LOBATTO, dict(parabolic=True, lifting=1, riemann="ch", mu0=1e-2, split_dg=True, split_dg_type="ch",
                                                   boundary_type=[(4, 2, 0), (9, 0, 0), (2, 1, 0)],
                                                   ref_state_prim=[(1.0, 0.3, 0.0, 0.0, 0.71428571), (1.0, 0.0, 0.0, 0.0, 0.9)]))
+CASES["config4_unstr"] = CASES["config4"]
+CASES["split_unstr"] = CASES["split"]
 WALL_BC = {(1, -1): 1, (1, 1): 2, (0, -1): 3, (0, 1): 3}  # walls in y, far field in x, periodic in z
 
 
@@ -51,10 +53,11 @@ def main():
     else:
         dist.init_process_group("gloo", rank=rank, world_size=world)
     N, node, eqn = CASES[case]
+    oseed = 9 if case.endswith("_unstr") else None  # "_unstr": every element in a random local frame (all flips on MPI sides too)
     if "boundary_type" in eqn:
-        spec = BoxSpec((4, 3, 2), periodic=(False, False, True), bc_of_face=WALL_BC, **CURVED)
+        spec = BoxSpec((4, 3, 2), periodic=(False, False, True), bc_of_face=WALL_BC, orient_seed=oseed, **CURVED)
     else:
-        spec = BoxSpec((4, 3, 2), **CURVED)
+        spec = BoxSpec((4, 3, 2), orient_seed=oseed, **CURVED)
     part = dict(partition="linear") if world != 4 else dict(partition="block", blocks=(2, 2, 1))
     gauss_split = bool(eqn.get("split_dg")) and node == B.NODE_GAUSS  # needs Ja_Face / Ja_slave
     ranks = build_case(spec, N, node, eqn, nranks=world, with_ja_face=gauss_split, **part)  # every rank builds all partitions (tiny mesh)

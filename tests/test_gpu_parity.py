@@ -113,6 +113,45 @@ def test_ut_and_side_arrays_match_oracle_on_curved_mesh(N, node, eqn):
         w.close()
 
 
+ORIENTED = [WEAK[1], WEAK[2], WEAK[5], WEAK[6], WEAK[10], SPLIT[1], SPLIT[3], SPLIT[4], SPLIT[5], SPLIT[6],
+            (5, G, dict(parabolic=True, riemann="hllc", mu0=1e-2, lifting=2, eta_br2=2.0)),          # BASELINE configs[3] flavour
+            (5, GL, dict(parabolic=True, riemann="roe", mu0=1e-2, lifting=2, eta_br2=2.0, split_dg=True, split_dg_type="pi"))]
+
+
+@pytest.mark.parametrize("N,node,eqn", ORIENTED, ids=_ids(ORIENTED))
+def test_unstructured_orientations_match_oracle(N, node, eqn):
+    """BASELINE configs[3] says "unstructured": every element of the curved periodic box sits in its own randomly rotated local
+    frame, so all five flips and every (master side, slave side) pairing occur (mappings.f90:188-450).  Ut, traces, fluxes and
+    lifted gradients against the oracle, whose own handling of these meshes is pinned by tests/test_host_mesh.py."""
+    r, w, g, _ = run_pair(BoxSpec((3, 3, 2), orient_seed=3, **CURVED), N, node, eqn)
+    try:
+        assert np.all(np.bincount(r.mesh.ElemToSide[:, :, 1].ravel(), minlength=5) > 0)
+        w.dg_time_derivative(0.0)
+        ut = g.DGTimeDerivative_weakForm(0.0)
+        o = w.ranks[0]
+        assert np.all(rel(ut, o.array("Ut")) < TOL_UT), rel(ut, o.array("Ut"))
+        for name in ("U_master", "U_slave"):
+            assert np.all(rel(g.get_array(name), o.array(name)) < 1e-14), name
+        assert np.all(rel(g.get_array("Flux"), o.array("Flux")) < TOL_UT)
+        if eqn.get("parabolic"):
+            scale = max(np.max(np.abs(o.array(n2))) for n2 in ("gradUx", "gradUy", "gradUz"))
+            for name in ("gradUx", "gradUy", "gradUz", "gradUx_master", "gradUy_master", "gradUz_master", "gradUx_slave",
+                         "gradUy_slave", "gradUz_slave"):
+                assert np.max(np.abs(g.get_array(name) - o.array(name))) < 1e-12 * scale, name
+        # and three LSERK steps on top
+        t = 0.0
+        for _ in range(3):
+            dt_o = w.calc_timestep()[0]
+            assert abs(g.CalcTimeStep()[0] - dt_o) <= 1e-13 * dt_o
+            w.timestep(t, dt_o)
+            g.TimeStep(t, dt_o)
+            t += dt_o
+        assert np.all(rel(g.get_state(), o.array("U")) < 1e-12)
+    finally:
+        g.close()
+        w.close()
+
+
 @pytest.mark.parametrize("N,node,eqn", [WEAK[4], WEAK[7], SPLIT[4], SPLIT[5]], ids=_ids([WEAK[4], WEAK[7], SPLIT[4], SPLIT[5]]))
 def test_rk_steps_and_timestep_match_oracle(N, node, eqn):
     """CalcTimeStep + 3 LSERK steps: dt to 1e-14, state to 1e-12, L2/Linf norms against the initial state to 1e-10."""
