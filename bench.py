@@ -426,6 +426,11 @@ def main():
             bytes_per_launch = balg[name] * ndof_local / launches_per_stage
             kern[name] = {"avg_ms": per_launch_ms, "launches_per_stage": launches_per_stage, "alg_bytes_per_dof": balg[name],
                           "achieved_gbs": bytes_per_launch / (per_launch_ms * 1e-3) / 1e9}
+    # multi-GPU: time the compute stream stood still at the three halo-exchange waits (what the inner-element kernels did not
+    # hide), per RK stage, max over ranks
+    xwait = None
+    if world > 1:
+        xwait = {k: max_over_ranks(kt["wait_" + k][0] / (args.profile_steps * nst)) for k in ("trace", "grad", "flux")}
     dom = max(kern, key=lambda k: kern[k]["avg_ms"] * kern[k]["launches_per_stage"])
     stage_ms = sum(v["avg_ms"] * v["launches_per_stage"] for v in kern.values())
     kname = {"volume": "k_volume_gl2" if (args.flavour == "split" and (args.N + 1) % 2 == 0) else "k_volume", "flux": "k_flux", "update": "k_update"}
@@ -467,6 +472,8 @@ def main():
                         "d2h_bytes_per_step": ubytes / args.steps + 24,
                         "what": "set_state(pinned host U) + steps x (CalcTimeStep + TimeStep) + get_state(pinned host U) through the C ABI"},
                 "roofline": roofline, "cpu_baseline": cpu, "parity": parity}
+        if xwait is not None:
+            line["exchange_wait_ms_per_stage"] = xwait
         emit(line, real_stdout)
     if world > 1:
         dist.destroy_process_group()

@@ -69,6 +69,10 @@ struct TimedLaunch {
 
 }  // namespace
 
+// timing classes beyond the kernel classes of kernels.cuh: how long the compute stream stood still at each halo-exchange
+// wait (finish_exchange), i.e. the part of the NCCL exchange that the inner-element kernels did not hide
+enum { KC_WAIT_TRACE = fx::KC_COUNT, KC_WAIT_GRAD, KC_WAIT_FLUX, KC_ALL };
+
 struct flexi_gpu_handle {
   // configuration
   int N = 0, np = 0, np2 = 0, np3 = 0;
@@ -124,8 +128,8 @@ struct flexi_gpu_handle {
   int64_t launches = 0, h2d = 0, d2h = 0;
   bool profiling = false;
   std::vector<TimedLaunch> timed;
-  double kc_ms[KC_COUNT] = {0};
-  int64_t kc_n[KC_COUNT] = {0};
+  double kc_ms[KC_ALL] = {0};
+  int64_t kc_n[KC_ALL] = {0};
 };
 
 namespace {
@@ -158,8 +162,8 @@ struct Timer {
   int kc;
   cudaStream_t s;
   TimedLaunch t{};
-  Timer(H* h_, int kc_, cudaStream_t s_) : h(h_), kc(kc_), s(s_) {
-    h->launches++;
+  Timer(H* h_, int kc_, cudaStream_t s_, bool isLaunch = true) : h(h_), kc(kc_), s(s_) {
+    if (isLaunch) h->launches++;
     if (h->profiling) {
       cudaEventCreate(&t.a);
       cudaEventCreate(&t.b);
@@ -220,17 +224,24 @@ int download_aos(H* h, const double* dev, double* host, int nv, int npts, long n
 }
 
 // ---- halo exchange: contiguous side slices per neighbour rank (mpi.f90:269-314) --------------------------------------------
-// sendMine: send my MINE slices and receive into my YOUR slices (SendID=1, master -> slave); otherwise the other direction.
-int exchange_group(H* h, double* const* arrs, int nArrs, int dataSizeSide, bool sendMine) {
+// One message set: array, doubles per side, direction.  sendMine: send my MINE slices and receive into my YOUR slices (SendID=1,
+// master -> slave); otherwise the other direction.  All sets of one exchange go into ONE NCCL group (one kernel on the wire).
+struct XMsg {
+  double* arr;
+  int dataSizeSide;
+  bool sendMine;
+};
+int exchange_group(H* h, const XMsg* msgs, int nMsgs) {
   Nccl& nc = nccl();
   CKN(nc.GroupStart());
   for (size_t i = 0; i < h->NbProc.size(); ++i) {
     const int nb = h->NbProc[i];
-    const int sOff = sendMine ? h->offMINE[i] : h->offYOUR[i], sN = sendMine ? h->nMINE_Proc[i] : h->nYOUR_Proc[i];
-    const int rOff = sendMine ? h->offYOUR[i] : h->offMINE[i], rN = sendMine ? h->nYOUR_Proc[i] : h->nMINE_Proc[i];
-    for (int a = 0; a < nArrs; ++a) {
-      if (sN > 0) CKN(nc.Send(arrs[a] + (size_t)sOff * dataSizeSide, (size_t)sN * dataSizeSide, NCCL_DOUBLE, nb, h->comm, h->sx));
-      if (rN > 0) CKN(nc.Recv(arrs[a] + (size_t)rOff * dataSizeSide, (size_t)rN * dataSizeSide, NCCL_DOUBLE, nb, h->comm, h->sx));
+    for (int a = 0; a < nMsgs; ++a) {
+      const XMsg& m = msgs[a];
+      const int sOff = m.sendMine ? h->offMINE[i] : h->offYOUR[i], sN = m.sendMine ? h->nMINE_Proc[i] : h->nYOUR_Proc[i];
+      const int rOff = m.sendMine ? h->offYOUR[i] : h->offMINE[i], rN = m.sendMine ? h->nYOUR_Proc[i] : h->nMINE_Proc[i];
+      if (sN > 0) CKN(nc.Send(m.arr + (size_t)sOff * m.dataSizeSide, (size_t)sN * m.dataSizeSide, NCCL_DOUBLE, nb, h->comm, h->sx));
+      if (rN > 0) CKN(nc.Recv(m.arr + (size_t)rOff * m.dataSizeSide, (size_t)rN * m.dataSizeSide, NCCL_DOUBLE, nb, h->comm, h->sx));
     }
   }
   CKN(nc.GroupEnd());
@@ -244,33 +255,29 @@ int start_exchange(H* h, int kind) {
   CK(cudaEventRecord(h->evProd, h->sc));
   CK(cudaStreamWaitEvent(h->sx, h->evProd, 0));
   const int szU = 5 * h->np2, szG = h->nvl * h->np2;
+  XMsg m[4];
+  int n = 0;
   if (kind == X_TRACE) {
     // C1 (dg.f90:360-432): U_slave of YOUR sides -> master rank.  With parabolic terms the slave rank also needs U_master
     // of its YOUR sides for the gathered lifting flux (replaces the lifting-flux message C2, lifting_br1.t90:79-83).
-    double* a1[1] = {h->Us};
-    CKR(exchange_group(h, a1, 1, szU, false));
-    if (h->para) {
-      double* a2[1] = {h->Um};
-      CKR(exchange_group(h, a2, 1, szU, true));
-    }
+    m[n++] = {h->Us, szU, false};
+    if (h->para) m[n++] = {h->Um, szU, true};
   } else if (kind == X_GRAD) {  // C3 (lifting_br1.t90:150-165): gradU{x,y,z}_slave -> master rank
-    if (h->vt) {  // viscous-trace protocol: the slave element's n.F_v replaces the three gradient messages
-      double* a1[1] = {h->fvs};
-      CKR(exchange_group(h, a1, 1, 4 * h->np2, false));
-      // a full DG-operator evaluation also leaves gradU?_slave of the MPI_MINE sides like the reference does (C3)
-      if (h->gradTracesFull) CKR(exchange_group(h, h->gs, 3, szG, false));
-    } else {
-      CKR(exchange_group(h, h->gs, 3, szG, false));
-    }
+    if (h->vt) m[n++] = {h->fvs, 4 * h->np2, false};  // viscous-trace protocol: the slave element's n.F_v replaces the three gradient messages
+    // a full DG-operator evaluation also leaves gradU?_slave of the MPI_MINE sides like the reference does (C3)
+    if (!h->vt || h->gradTracesFull)
+      for (int d = 0; d < 3; ++d) m[n++] = {h->gs[d], szG, false};
   } else {  // C4 (dg.f90:607-641): Flux master -> slave rank
-    double* a1[1] = {h->Flux};
-    CKR(exchange_group(h, a1, 1, szU, true));
+    m[n++] = {h->Flux, szU, true};
   }
+  CKR(exchange_group(h, m, n));
   CK(cudaEventRecord(h->evX[kind], h->sx));
   return 0;
 }
 int finish_exchange(H* h, int kind) {
   if (h->nProcs == 1) return 0;
+  // with profiling on, two events around the wait measure how long the compute stream stood still here
+  Timer tm(h, KC_WAIT_TRACE + kind, h->sc, false);
   CK(cudaStreamWaitEvent(h->sc, h->evX[kind], 0));
   return 0;
 }
@@ -423,11 +430,13 @@ int launch_bc(H* h, bool pre, double t) {
   return 0;
 }
 
-int rhs(H* h, double t, int mode, double rkA, double b_dt) {
+// applyFilter = false: a recomputation behind a getter (gradient arrays, TGV analysis): it must not change U, so the solution
+// filter of dg.f90:329-330 -- applied in place, and not idempotent for FilterType = modal -- is skipped.
+int rhs(H* h, double t, int mode, double rkA, double b_dt, bool applyFilter = true) {
   if (h->bcTablesMissing) return fail(FLEXI_GPU_ERR_ARG, "BC sides without BC / BoundaryType tables");
   if (h->entropy && !h->JaF) return fail(FLEXI_GPU_ERR_ARG, "split form on Gauss nodes: call flexi_gpu_set_face_metrics (Ja_Face, Ja_slave) first");
   h->lastT = t;
-  if (h->filtUOn) {  // dg.f90:329-330: IF(FilterType.GT.0) CALL Filter_Pointer(U,FilterMat) -- in place, then everything reads the filtered U
+  if (h->filtUOn && applyFilter) {  // dg.f90:329-330: IF(FilterType.GT.0) CALL Filter_Pointer(U,FilterMat) -- in place, then everything reads the filtered U
     FiltArgs fa{};
     fa.U = h->U;
     fa.mat = h->filtUMat;
@@ -494,7 +503,7 @@ int rhs(H* h, double t, int mode, double rkA, double b_dt) {
 int ensure_grad_traces(H* h) {
   if (h->gradTracesFull) return 0;
   if (!h->Ut) CKR(dalloc(h, &h->Ut, (size_t)h->nElems * 5 * h->np3));
-  return rhs(h, h->lastT, 0, 0., 0.);
+  return rhs(h, h->lastT, 0, 0., 0., false);
 }
 
 }  // namespace
@@ -1030,7 +1039,7 @@ int flexi_gpu_get_array(flexi_gpu_handle* h, int32_t which, double* out) {
         // and kept from then on for every later evaluation
         CKR(flexi_gpu_keep_gradients(h, 1));
         if (!h->Ut) CKR(dalloc(h, &h->Ut, (size_t)h->nElems * 5 * h->np3));
-        CKR(rhs(h, h->lastT, 0, 0., 0.));
+        CKR(rhs(h, h->lastT, 0, 0., 0., false));
       }
       return download_aos(h, h->gvol[which - FLEXI_ARR_GRADUX], out, h->nvl, np3, h->nElems);
     }
@@ -1054,7 +1063,7 @@ int flexi_gpu_analyze_tgv(flexi_gpu_handle* h, int32_t NAnalyze, const double* V
   if (h->para && !h->keepGrad) {  // gradients are not kept: recompute them from the current U (like FLEXI_ARR_GRADU*)
     CKR(flexi_gpu_keep_gradients(h, 1));
     if (!h->Ut) CKR(dalloc(h, &h->Ut, (size_t)h->nElems * 5 * h->np3));
-    CKR(rhs(h, h->lastT, 0, 0., 0.));
+    CKR(rhs(h, h->lastT, 0, 0., 0., false));
   }
   // tables: Vdm as [iOut][iIn], wGPVolAnalyze as is ((i,j,k) with i fastest)
   std::vector<double> tab((size_t)na1 * np + (size_t)na1 * na1 * na1);
@@ -1358,12 +1367,12 @@ int flexi_gpu_counters(flexi_gpu_handle* h, int64_t* kernel_launches, int64_t* h
 int flexi_gpu_kernel_times(flexi_gpu_handle* h, double* ms_out, int64_t* launches_out, int32_t n_classes, int32_t reset) {
   ENTER(h);
   CKR(collect_times(h));
-  for (int i = 0; i < n_classes && i < KC_COUNT; ++i) {
+  for (int i = 0; i < n_classes && i < KC_ALL; ++i) {
     if (ms_out) ms_out[i] = h->kc_ms[i];
     if (launches_out) launches_out[i] = h->kc_n[i];
   }
   if (reset)
-    for (int i = 0; i < KC_COUNT; ++i) {
+    for (int i = 0; i < KC_ALL; ++i) {
       h->kc_ms[i] = 0;
       h->kc_n[i] = 0;
     }

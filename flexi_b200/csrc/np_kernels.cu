@@ -316,6 +316,16 @@ const NpOps ops = {NP, setup, prolong, volume, flux, update, surfcorr, surfint, 
 }  // namespace
 }  // namespace fx
 
+#if defined(FLEXI_GPU_DEV) && defined(FX_DEV_STAMPS) && FLEXI_NP == 8
+// development build: read (and reset) the per-phase clock sums of k_volume_gl2 (tools/phase_stamps.py)
+extern "C" int flexi_gpu_dev_stamps(unsigned long long* out) {
+  cudaDeviceSynchronize();
+  unsigned long long z[32] = {0};
+  if (cudaMemcpyFromSymbol(out, fx::g_gl2_stamps, sizeof(z)) != cudaSuccess) return -1;
+  return cudaMemcpyToSymbol(fx::g_gl2_stamps, z, sizeof(z)) == cudaSuccess ? 0 : -1;
+}
+#endif
+
 #define FX_CAT2(a, b) a##b
 #define FX_CAT(a, b) FX_CAT2(a, b)
 extern "C" const fx::NpOps* FX_CAT(fx_ops_np, FLEXI_NP)() { return &fx::ops; }

@@ -52,6 +52,32 @@ FX_HD void cons_to_prim(const Eqn& q, const double* __restrict__ c, double* __re
   p[PRES] = q.kappaM1 * (c[ENER] - 0.5 * (c[MOM1] * p[VEL1] + c[MOM2] * p[VEL2] + c[MOM3] * p[VEL3]));
   p[TEMP] = p[PRES] * sRho * q.sR;  // the reference divides by R (eos.f90:229); 1/R is formed once on the host (<= 1 ulp)
 }
+// 1/x without the special-case branch of the IEEE division sequence: MUFU.RCP64H seed + two Newton steps, <= 1 ulp for the
+// normal, finite x it is used on (densities).  A branch in the middle of straight-line code costs more than the division
+// itself in the element kernel (instruction-fetch bubbles, and it keeps independent chains from being interleaved).
+FX_HD double rcp_fast(double x) {
+#ifdef __CUDA_ARCH__
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+#else
+  return 1. / x;
+#endif
+}
+// ConsToPrim with rcp_fast, returning 1/rho (element kernel k_volume_gl2 only)
+FX_HD double cons_to_prim_fast(const Eqn& q, const double* __restrict__ c, double* __restrict__ p) {
+  const double sRho = rcp_fast(c[DENS]);
+  p[DENS] = c[DENS];
+  p[VEL1] = c[MOM1] * sRho;
+  p[VEL2] = c[MOM2] * sRho;
+  p[VEL3] = c[MOM3] * sRho;
+  p[PRES] = q.kappaM1 * (c[ENER] - 0.5 * (c[MOM1] * p[VEL1] + c[MOM2] * p[VEL2] + c[MOM3] * p[VEL3]));
+  p[TEMP] = p[PRES] * sRho * q.sR;
+  return sRho;
+}
 // same, also returning 1/rho for callers that need it again
 FX_HD double cons_to_prim_srho(const Eqn& q, const double* __restrict__ c, double* __restrict__ p) {
   const double sRho = 1. / c[DENS];

@@ -26,13 +26,33 @@
 namespace fx {
 
 __device__ __forceinline__ void cp_async_wait_group1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+// x * (+-1) as an integer operation on the sign bit (sb = 0 or 0x80000000): same bits as the product, no FP64 issue slot
+__device__ __forceinline__ double sgn_apply(double x, int sb) { return __hiloint2double(__double2hiint(x) ^ sb, __double2loint(x)); }
+// store under a predicate, without a branch
+__device__ __forceinline__ void st_global_if(bool on, double* p, double v) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q st.global.f64 [%0], %1;\n\t}" ::"l"(p), "d"(v), "r"((int)on) : "memory");
+}
 
 // Phase-skipping switches for timing experiments (tools/phase_timing.py): they produce wrong results and exist only in the
 // development build (make dev: -DFLEXI_GPU_DEV -> libflexi_gpu_dev.so); the release library has no such branch.
-#ifdef FLEXI_GPU_DEV
+#if defined(FLEXI_GPU_DEV) && defined(FX_DEV_DBG)
 #define FX_DBG(A, bit) (((A).dbg & (bit)) != 0)
 #else
 #define FX_DBG(A, bit) false
+#endif
+// FX_STAMP (development build): per-warp clock64() deltas of the kernel phases, summed over all warps (tools/phase_stamps.py).
+#if defined(FLEXI_GPU_DEV) && defined(FX_DEV_STAMPS)
+static __device__ unsigned long long g_gl2_stamps[32];
+#define FX_STAMP_INIT long long fx_t0_ = clock64();
+#define FX_STAMP(i)                                                                                          \
+  {                                                                                                          \
+    const long long t_ = clock64();                                                                          \
+    if ((threadIdx.x & 31) == 0) atomicAdd(&g_gl2_stamps[i], (unsigned long long)(t_ - fx_t0_));             \
+    fx_t0_ = t_;                                                                                             \
+  }
+#else
+#define FX_STAMP_INIT
+#define FX_STAMP(i)
 #endif
 // FX_DEV_MINB=<n> (development build) overrides the resident-CTA target of __launch_bounds__.
 template <int NP>
@@ -54,20 +74,22 @@ __device__ __forceinline__ int gl2_phys(int i, int j, int k) {
   return i + NP * (j + NP * k);
 }
 
-// Shared-memory budget (NP = 8, Navier-Stokes, 4 lifted variables): 18 planes of 4 KB + the face table = 73.5 KB, so that THREE
-// elements are resident per SM (12 warps; the 25-plane layout of round 1 allowed two, and the kernel is latency-bound):
+// Shared-memory budget (NP = 8, Navier-Stokes, 4 lifted variables): 28 planes of 4 KB = 112 KB, two elements resident per SM.
+// Every operand of the node phase and of the three two-point sweeps comes from shared memory; the only global loads of the
+// kernel are issued in phase A (round 1 re-read the metric terms from L2 in the node phase and in every sweep: seven exposed L2
+// round trips per element with two warps per scheduler to hide them):
+//   R0 1 plane   ElemToSide/S2V2 face table (int [6][NP2]) + etaBR2 until the node phase is done, then hand-over plane of Ut(1)
 //   P  7 planes  rho,u,v,w,p,T,X5        T is dead after the lifting phase: its plane becomes the hand-over plane of Ut(5)
 //   W  2*NVC     G1|G2 (xi-, eta-derivatives of the lifting variables), overwritten in place by f~|g~ (4+4 planes)
 //   F  3 planes  lifting flux * L_Hat of the six faces [6][NVC][NP2]; dead after the node phase: hand-over planes of Ut(2..4)
+//   M  9 planes  metric terms f~,g~,h~Tilde in the swizzled layout, cp.async (LDGSTS) issued first thing in phase A
 // What round 1 kept in shared memory on top of that and where it went:
-//   * neighbour traces + face geometry (cp.async staging, 9 values per face node): the face thread now holds the raw trace in
-//     registers across the lifting sweeps and stores only the NVC lifting fluxes; the normal vector of a boundary node is read
-//     from L2 (prefetched one wave ahead) by the node's owner;
+//   * neighbour traces + face geometry (cp.async staging, 9 values per face node): the face thread holds the raw trace in
+//     registers across the lifting sweeps and stores only the NVC lifting fluxes; the normal vectors of a thread's boundary
+//     nodes are requested right after S1 and have the lifting sweeps to arrive;
 //   * h~ (4 planes): the node phase runs in zeta ownership, so the zeta derivative of h~ is formed from registers: a thread
 //     adds the contributions of its own half line to ALL eight nodes of the line -- its own four stay with it, the other four go
-//     to the partner through the hand-over planes (same number of DFMAs as before, 16 fewer shared-memory loads per thread);
-//   * the hand-over plane of Ut(1): the density has no viscous part and is handed from sweep to sweep through the (L2-resident)
-//     output array itself.
+//     to the partner through the hand-over planes (same number of DFMAs as before, 16 fewer shared-memory loads per thread).
 template <int NP, bool PARA, int NVC>
 struct VolGL2Cfg {
   using D = Dim<NP>;
@@ -81,20 +103,32 @@ struct VolGL2Cfg {
   // hand-over planes of Ut(2..4) alias the face fluxes; Ut(5) goes to the T plane (Navier-Stokes) or a fourth plane (Euler)
   static constexpr int F_UT = PARA ? 3 * PL : 4 * PL;
   static constexpr int F_DOUBLES = ((F_FACE > F_UT ? F_FACE : F_UT) + 1) & ~1;
-  static constexpr int NFD = PARA ? ((3 * D::NP2 + 1) & ~1) : 0;  // int table [6][NP2]
+  static constexpr int NFD = PARA ? ((3 * D::NP2 + 1) & ~1) : 0;  // int table [6][NP2], in doubles
+#if defined(FLEXI_GPU_DEV) && defined(FX_DEV_MGLOBAL)
+  static constexpr bool WANT_MSM = false;  // timing experiment: 18-plane layout, metric terms from L2, Ut(1) handed over through L2
+#else
+  static constexpr bool WANT_MSM = true;
+#endif
+  static constexpr int R0_DOUBLES = (((WANT_MSM && PL > NFD + 6) ? PL : NFD + 6) + 1) & ~1;
   static constexpr int O_FDST = 0;
   static constexpr int O_ETA = O_FDST + NFD;
-  static constexpr int O_P = O_ETA + (PARA ? 6 : 0);
+  static constexpr int O_UT1 = 0;
+  static constexpr int O_P = R0_DOUBLES;
   static constexpr int O_W = O_P + P_PLANES * PL;
   static constexpr int O_F = O_W + W_PLANES * PL;
   static constexpr int O_UT5 = PARA ? O_P + 5 * PL : O_F + 3 * PL;
-  static constexpr int DOUBLES = O_F + F_DOUBLES;
+  static constexpr int O_M = O_F + F_DOUBLES;
+  // metric planes in shared memory unless the element does not fit (NP = 10 with all five lifting variables): then they are
+  // read from global memory as in round 1 (natural layout == plane layout for NP != 8)
+  static constexpr bool MSM = WANT_MSM && sizeof(double) * (O_M + 9 * PL) <= 232448;
+  static constexpr bool UT1S = R0_DOUBLES >= PL;  // hand-over plane of Ut(1) in shared memory (else through the output array in L2)
+  static constexpr int DOUBLES = O_M + (MSM ? 9 * PL : 0);
   static constexpr size_t BYTES = sizeof(double) * DOUBLES;
 #if defined(FLEXI_GPU_DEV) && defined(FX_DEV_MINB)
   static constexpr int MINB = FX_DEV_MINB;
 #else
-  // resident CTAs per SM the register allocation aims at: (227 KB - 1 KB reserved per CTA) / 3 = 76458 bytes
-  static constexpr int MINB = (BYTES <= 76000 && NT <= 256) ? 3 : (BYTES <= 113000) ? 2 : 1;
+  // resident CTAs per SM the register allocation aims at: 228 KB per SM, 1 KB reserved per CTA
+  static constexpr int MINB = (BYTES <= 76000 && NT <= 256) ? 3 : (BYTES <= 115712) ? 2 : 1;
 #endif
 };
 
@@ -124,47 +158,40 @@ __device__ __forceinline__ int gl2_gn(int dir, int p, int r0, int r1) {
 }
 
 // One direction sweep of the advective two-point fluxes (+ the weak-form derivative of the viscous flux of that direction).
-//   sa[q] / gn[q]  shared-memory address / natural node index of canonical line position q
-//   vp[v]          plane of the contravariant viscous flux of this direction, variable v+1
-//   ut[c][v]       result for the own nodes c (HALF of them), WITHOUT the half sign (the caller applies it)
+//   sa[q]          shared-memory address of canonical line position q (state planes and metric planes share the layout)
+//   sMd, ma[q]     the three metric planes of this direction and the address of position q in them (ma == sa when the planes
+//                  live in shared memory, the natural node index when they are read from global memory)
+//   vp[v]          plane of the contravariant viscous flux of this direction, variable v+1 (read when lineVisc)
+//   ut[c][v]       in/out: result for the own nodes c (HALF of them), WITHOUT the half sign (the caller applies it); the caller
+//                  presets it (zero, or the zeta derivative of h~ that the node phase formed from registers)
 template <int NP, int STYPE, bool PARA>
 __device__ __forceinline__ void gl2_pair_sweep(const GL2Basis<NP>& B, const double* __restrict__ sP, const double* const (&vp)[4],
-                                               const double* __restrict__ gMd, const int (&sa)[NP], const int (&gn)[NP],
-                                               double (&ut)[NP / 2][5], const double kappa) {
+                                               const bool lineVisc, const double* __restrict__ sMd, const int (&sa)[NP],
+                                               const int (&ma)[NP], double (&ut)[NP / 2][5], const double kappa) {
   constexpr int HALF = NP / 2, PL = NP * NP * NP;
   constexpr bool PI = (STYPE == FLEXI_SPLITDG_PI);
   constexpr int PX = PARA ? 6 : 5;
-  // metric terms of this direction along the whole line, straight from L2
-  double Mo[HALF][3], Mp[HALF][3];
-#pragma unroll
-  for (int c = 0; c < HALF; ++c)
-#pragma unroll
-    for (int m = 0; m < 3; ++m) {
-      Mo[c][m] = __ldg(gMd + m * PL + gn[c]);
-      Mp[c][m] = __ldg(gMd + m * PL + gn[HALF + c]);
-    }
-#pragma unroll
-  for (int c = 0; c < HALF; ++c)
-#pragma unroll
-    for (int v = 0; v < 5; ++v) ut[c][v] = 0.;
-  if (PARA) {  // volint.f90:310-315: Ut += D_Hat_T(l,i) * f~visc(l)
+  if (PARA && lineVisc) {  // volint.f90:310-315: Ut += D_Hat_T(l,i) * f~visc(l)
 #pragma unroll
     for (int v = 0; v < 4; ++v) {
       double L[NP];
 #pragma unroll
       for (int p = 0; p < NP; ++p) L[p] = vp[v][sa[p]];
 #pragma unroll
-      for (int c = 0; c < HALF; ++c) {  // two partial sums per node: twice the independent FP64 chains
-        double s0 = B.dh[c] * L[0], s1 = B.dh[HALF * NP + c] * L[HALF];
+      for (int c = 0; c < HALF; ++c) {
+        double s0 = B.dh[c] * L[0];
 #pragma unroll
-        for (int p = 1; p < HALF; ++p) {
-          s0 = s0 + B.dh[p * NP + c] * L[p];
-          s1 = s1 + B.dh[(HALF + p) * NP + c] * L[HALF + p];
-        }
-        ut[c][v + 1] = s0 + s1;
+        for (int p = 1; p < NP; ++p) s0 = s0 + B.dh[p * NP + c] * L[p];
+        ut[c][v + 1] = s0;
       }
     }
   }
+  // metric terms of this direction along the whole line
+  double Mo[HALF][3];
+#pragma unroll
+  for (int c = 0; c < HALF; ++c)
+#pragma unroll
+    for (int m = 0; m < 3; ++m) Mo[c][m] = sMd[m * PL + ma[c]];
   // own half line
   double a[HALF][6];
 #pragma unroll
@@ -224,12 +251,13 @@ __device__ __forceinline__ void gl2_pair_sweep(const GL2Basis<NP>& B, const doub
     const int l = HALF + c2;
     const int s = sa[l];
     const double br = sP[s], bu = sP[PL + s], bv = sP[2 * PL + s], bw = sP[3 * PL + s], bp = sP[4 * PL + s], bx = sP[PX * PL + s];
+    const double pm0 = sMd[ma[l]], pm1 = sMd[PL + ma[l]], pm2 = sMd[2 * PL + ma[l]];
 #pragma unroll
     for (int c = 0; c < HALF; ++c) {
       const double dl = B.dvs[l * NP + c];
       if (PI) {
         const double su = a[c][1] + bu, sv = a[c][2] + bv, sw = a[c][3] + bw, sp4 = a[c][4] + bp, sH = a[c][5] + bx;
-        const double m0 = Mo[c][0] + Mp[c2][0], mm1 = Mo[c][1] + Mp[c2][1], mm2 = Mo[c][2] + Mp[c2][2];
+        const double m0 = Mo[c][0] + pm0, mm1 = Mo[c][1] + pm1, mm2 = Mo[c][2] + pm2;
         const double rq = (a[c][0] + br) * (m0 * su + mm1 * sv + mm2 * sw);
         const double w = dl * rq, dp = dl * sp4;
         ut[c][0] += 2. * w;
@@ -242,7 +270,7 @@ __device__ __forceinline__ void gl2_pair_sweep(const GL2Basis<NP>& B, const doub
         ut[c][3] += dp * mm2;
       } else {
         double Fl[5];
-        split_pair_generic<STYPE>(a[c], Mo[c], br, bu, bv, bw, bp, bx, Mp[c2][0], Mp[c2][1], Mp[c2][2], Fl, kappa);
+        split_pair_generic<STYPE>(a[c], Mo[c], br, bu, bv, bw, bp, bx, pm0, pm1, pm2, Fl, kappa);
 #pragma unroll
         for (int v = 0; v < 5; ++v) ut[c][v] = ut[c][v] + dl * Fl[v];
       }
@@ -270,34 +298,45 @@ __global__ void __launch_bounds__(VolGL2Cfg<NP, PARA, NVC>::NT, VolGL2Cfg<NP, PA
   double* sP = sm + C::O_P;
   double* sW = sm + C::O_W;   // G1 | G2 lifting planes, later f~ | g~
   double* sF = sm + C::O_F;   // lifting fluxes of the six faces, later the hand-over planes of Ut(2..4)
-  // hand-over plane of Ut(v+1), v = 1..4 (the density goes through the output array)
-  auto ut_plane = [&](int v) -> double* { return v < 4 ? sF + (v - 1) * PL : sm + C::O_UT5; };
+  double* sM = sm + C::O_M;   // metric terms, 9 planes
+  // hand-over plane of Ut(v+1), v = 0..4
+  auto ut_plane = [&](int v) -> double* { return v == 0 ? sm + C::O_UT1 : v < 4 ? sF + (v - 1) * PL : sm + C::O_UT5; };
   const int tid = threadIdx.x;
+  FX_STAMP_INIT
   if (FX_DBG(A, 8)) return;  // timing experiment: the cost of scheduling one CTA per element
   const int e = A.elems ? A.elems[blockIdx.x] : blockIdx.x;
   const int hb = tid / D::NP2, r = tid % D::NP2;  // half index (warp-uniform for NP = 8) and position inside the NP x NP sheet
   const int r0 = r % NP, r1 = r / NP;
   const double sg = hb ? -1. : 1.;
+  const int sb = hb ? (int)0x80000000 : 0;  // sign bit of sg
   const Eqn& q = A.q;
   const double* gU = A.U + (size_t)e * 5 * D::NP3;
   const double* gM = A.m.Met + (size_t)e * 9 * D::NP3;
   double* gUt = A.Ut + (size_t)e * 5 * D::NP3;
   constexpr int FACE_IT = (6 * D::NP2 + NT - 1) / NT;
+  constexpr bool ALLF = (FACE_IT * NT == 6 * D::NP2);  // every thread converts exactly FACE_IT face nodes (NP = 8: 3)
 
-  // ---- phase A (zeta ownership): own conservative state on its way first, then the neighbour traces of the face nodes this
-  //      thread converts (registers), then ConsToPrim of the own nodes ----
+  // ---- phase A (zeta ownership): own conservative state on its way first, then the metric terms (asynchronous copies into
+  //      their swizzled planes: no register, no wait until S2), then the neighbour traces of the face nodes this thread
+  //      converts (registers), then ConsToPrim of the own nodes ----
   double Uc[HALF][5];
 #pragma unroll
   for (int c = 0; c < HALF; ++c)
 #pragma unroll
     for (int v = 0; v < 5; ++v) Uc[c][v] = __ldg(gU + v * D::NP3 + gl2_gn<NP>(2, gl2_ap<NP>(hb, c), r0, r1));
-  // metric terms + Jacobian of the first own node of the lifting phase: a first touch of HBM, so it starts here
-  double Mn[9], sJn;
-  if (PARA) {
-    const int n = gl2_gn<NP>(2, gl2_ap<NP>(hb, 0), r0, r1);
+  if (C::MSM) {
 #pragma unroll
-    for (int m = 0; m < 9; ++m) Mn[m] = __ldg(gM + m * D::NP3 + n);
-    sJn = __ldg(A.m.sJ + (size_t)e * D::NP3 + n);
+    for (int c = 0; c < HALF; ++c) {
+      const int n = gl2_gn<NP>(2, gl2_ap<NP>(hb, c), r0, r1), s = gl2_sa<NP>(2, gl2_ap<NP>(hb, c), r0, r1);
+#pragma unroll
+      for (int m = 0; m < 9; ++m) cp_async8(sM + m * PL + s, gM + m * D::NP3 + n);
+    }
+    cp_async_commit();
+  }
+  double sJv[HALF];
+  if (PARA) {
+#pragma unroll
+    for (int c = 0; c < HALF; ++c) sJv[c] = __ldg(A.m.sJ + (size_t)e * D::NP3 + gl2_gn<NP>(2, gl2_ap<NP>(hb, c), r0, r1));
   }
   SideRef nsr{-1, 0};  // side of face tid/21 of that later element (its traces + geometry are prefetched after S1)
   if (A.prefetchAhead > 0 && (int)blockIdx.x + A.prefetchAhead < A.nList && !FX_DBG(A, 32)) {
@@ -327,7 +366,7 @@ __global__ void __launch_bounds__(VolGL2Cfg<NP, PARA, NVC>::NT, VolGL2Cfg<NP, PA
       fSurf[it] = 0.;
 #pragma unroll
       for (int v = 0; v < 5; ++v) fU[it][v] = 1.;
-      if (t < 6 * D::NP2) {
+      if (ALLF || t < 6 * D::NP2) {
         const int ls = t / D::NP2 + 1, pq = t % D::NP2;
         const SideRef sr = A.m.e2s[e * 6 + ls - 1];
         const int ab = A.m.s2v2[(sr.flip * 6 + ls - 1) * D::NP2 + pq];
@@ -365,7 +404,7 @@ __global__ void __launch_bounds__(VolGL2Cfg<NP, PARA, NVC>::NT, VolGL2Cfg<NP, PA
   for (int c = 0; c < HALF; ++c) {
     double Pn[6];
     const double* const Ucc = Uc[c];
-    const double sRho = cons_to_prim_srho(q, Ucc, Pn);
+    const double sRho = cons_to_prim_fast(q, Ucc, Pn);
     const int s = gl2_sa<NP>(2, gl2_ap<NP>(hb, c), r0, r1);
 #pragma unroll
     for (int v = 0; v < 4; ++v) sP[v * PL + s] = Pn[v];
@@ -374,25 +413,60 @@ __global__ void __launch_bounds__(VolGL2Cfg<NP, PARA, NVC>::NT, VolGL2Cfg<NP, PA
     // 6th two-point quantity: H = (rhoE+p)/rho (PI), E = rhoE/rho (KG), rhoE (SD, DU)
     sP[PX * PL + s] = PI ? (Ucc[ENER] + Pn[PRES]) * sRho : (STYPE == FLEXI_SPLITDG_KG) ? Ucc[ENER] * sRho : Ucc[ENER];
   }
-  __syncthreads();  // S1: primitive planes complete
+  if (!PARA && C::MSM) cp_async_wait_all();
+  FX_STAMP(0)
+  __syncthreads();  // S1: primitive planes (Euler: and metric planes) and the face table complete
+  FX_STAMP(1)
 
-  if (PARA && nsr.side >= 0) {
-    // L2 prefetch of the six faces of the element one wave later (neighbour trace 20 lines, normal vector 12, SurfElem 4 per
-    // face; 21 threads per face): without it the start of every element waits on the chain ElemToSide -> S2V2 -> HBM
-    const char* tr = reinterpret_cast<const char*>(((nsr.flip == 0) ? A.U_slave : A.U_master) + (size_t)nsr.side * 5 * D::NP2);
-    const char* ge = reinterpret_cast<const char*>(A.m.Geo + (size_t)nsr.side * 10 * D::NP2);
-    constexpr int LT = 5 * D::NP2 * 8 / 128, LG = 3 * D::NP2 * 8 / 128, LS = D::NP2 * 8 / 128;
-    for (int l = tid % 21; l < LT + LG + LS; l += 21) {
-      const char* p = l < LT ? tr + (size_t)l * 128 : l < LT + LG ? ge + (size_t)(l - LT) * 128 : ge + (size_t)9 * D::NP2 * 8 + (size_t)(l - LT - LG) * 128;
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-    }
-  }
+  // the zeta derivative of h~ as this thread's contributions to the eight nodes of its line (own half | partner's half)
+  double cown[HALF][4], cpart[HALF][4];
   if (PARA) {
+    // ---- normal vectors of the (up to 2*HALF+1) face nodes among this thread's own nodes: requested now, used after S2.
+    //      A line sits on the xi faces if i is 0 or N (all its nodes), on the eta faces if j is 0 or N; its end c == 0 sits on
+    //      a zeta face (k = 0 for half 0, k = N for half 1). ----
+    // Interior lanes (no xi / eta face) run the boundary code of the minus side with a zero normal vector: every statement of
+    // the node phase below is unconditional (adding f*0 is exact), which leaves the four nodes of a thread in ONE basic block
+    // that the compiler can interleave.  The divergent version had ~7 short blocks per node, each with its own exposed
+    // shared-memory latency, and cost the same FP64 issue slots (a warp instruction occupies the pipe whatever its mask).
+    const bool onI = (r0 == 0) | (r0 == N), onJ = (r1 == 0) | (r1 == N);
+    const int lsI = (r0 == N) ? XI_PLUS : XI_MINUS, lsJ = (r1 == N) ? ETA_PLUS : ETA_MINUS, lsK = hb ? ZETA_PLUS : ZETA_MINUS;
+    int fdI[HALF], fdJ[HALF], fdK = 0;
+    double nI[HALF][3], nJ[HALF][3], nK[3];
+    auto face_geo = [&](bool on, int ls, int ab, int& fd, double (&nv)[3]) {
+      const int f = sFD[(ls - 1) * D::NP2 + ab];  // every slot of the table is valid: interior lanes load what their row's boundary lane loads
+      const int fl = f & 0x3fffffff;
+      const double* g = A.m.Geo + (size_t)(fl / D::NP2) * 10 * D::NP2 + fl % D::NP2;
+      const double n0 = __ldg(g), n1 = __ldg(g + D::NP2), n2 = __ldg(g + 2 * D::NP2);
+      fd = on ? f : 0;
+      nv[0] = on ? n0 : 0.;
+      nv[1] = on ? n1 : 0.;
+      nv[2] = on ? n2 : 0.;
+    };
+#pragma unroll
+    for (int c = 0; c < HALF; ++c) {
+      const int k = gl2_ap<NP>(hb, c);
+      face_geo(onI && !FX_DBG(A, 16), lsI, r1 + NP * k, fdI[c], nI[c]);
+      face_geo(onJ && !FX_DBG(A, 16), lsJ, r0 + NP * k, fdJ[c], nJ[c]);
+    }
+    face_geo(!FX_DBG(A, 16), lsK, r0 + NP * r1, fdK, nK);
+
+    if (nsr.side >= 0) {
+      // L2 prefetch of the six faces of the element one wave later (neighbour trace 20 lines, normal vector 12, SurfElem 4 per
+      // face; 21 threads per face): without it the start of every element waits on the chain ElemToSide -> S2V2 -> HBM
+      const char* tr = reinterpret_cast<const char*>(((nsr.flip == 0) ? A.U_slave : A.U_master) + (size_t)nsr.side * 5 * D::NP2);
+      const char* ge = reinterpret_cast<const char*>(A.m.Geo + (size_t)nsr.side * 10 * D::NP2);
+      constexpr int LT = 5 * D::NP2 * 8 / 128, LG = 3 * D::NP2 * 8 / 128, LS = D::NP2 * 8 / 128;
+      for (int l = tid % 21; l < LT + LG + LS; l += 21) {
+        const char* p = l < LT ? tr + (size_t)l * 128 : l < LT + LG ? ge + (size_t)(l - LT) * 128 : ge + (size_t)9 * D::NP2 * 8 + (size_t)(l - LT - LG) * 128;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+      }
+    }
     // ---- reference-space derivatives of the lifting variables (lifting_volint.t90:67-83), one line sweep per direction:
     //      xi and eta results change owner through the planes G1, G2; the zeta result stays with this thread ----
     double gzt[HALF][NVC];
-#pragma unroll 1
-    for (int dir = FX_DBG(A, 2) ? 3 : 0; dir < 3; ++dir) {
+#pragma unroll
+    for (int dir = 0; dir < 3; ++dir) {
+      if (FX_DBG(A, 2)) break;
       int sa[NP];
 #pragma unroll
       for (int p = 0; p < NP; ++p) sa[p] = gl2_sa<NP>(dir, gl2_ap<NP>(hb, p), r0, r1);
@@ -403,14 +477,11 @@ __global__ void __launch_bounds__(VolGL2Cfg<NP, PARA, NVC>::NT, VolGL2Cfg<NP, PA
 #pragma unroll
         for (int p = 0; p < NP; ++p) L[p] = pl[sa[p]];
 #pragma unroll
-        for (int c = 0; c < HALF; ++c) {  // two partial sums per node: twice the independent FP64 chains
-          double s0 = B.dt[c] * L[0], s1 = B.dt[HALF * NP + c] * L[HALF];
+        for (int c = 0; c < HALF; ++c) {
+          double s0 = B.dt[c] * L[0];
 #pragma unroll
-          for (int p = 1; p < HALF; ++p) {
-            s0 = s0 + B.dt[p * NP + c] * L[p];
-            s1 = s1 + B.dt[(HALF + p) * NP + c] * L[HALF + p];
-          }
-          gzt[c][v] = sg * (s0 + s1);
+          for (int p = 1; p < NP; ++p) s0 = s0 + B.dt[p * NP + c] * L[p];
+          gzt[c][v] = sgn_apply(s0, sb);
         }
       }
       if (dir < 2) {
@@ -425,12 +496,12 @@ __global__ void __launch_bounds__(VolGL2Cfg<NP, PARA, NVC>::NT, VolGL2Cfg<NP, PA
     //      had the line sweeps above to arrive. ----
 #pragma unroll
     for (int it = 0; it < FACE_IT; ++it) {
-      if (faceSlot[it] >= 0 && !FX_DBG(A, 16)) {
+      if ((ALLF || faceSlot[it] >= 0) && !FX_DBG(A, 16)) {
         double* o = sF + (faceSlot[it] & 0xffff);
         const int nF = faceSlot[it] >> 16;
         double Pb[6];
         const double lh = (LIFT == 1 && faceLh[it]) ? B.lhpN : B.lhm0;
-        cons_to_prim(q, fU[it], Pb);
+        cons_to_prim_fast(q, fU[it], Pb);
 #pragma unroll
         for (int v = 0; v < NVC; ++v) {
           const int pv = lift_prim(NVC, v);
@@ -438,14 +509,22 @@ __global__ void __launch_bounds__(VolGL2Cfg<NP, PARA, NVC>::NT, VolGL2Cfg<NP, PA
         }
       }
     }
-    __syncthreads();  // S2: G1, G2 and the face lifting fluxes complete
+    FX_STAMP(2)
+    if (C::MSM) cp_async_wait_all();
+    // gradient output (volume gradients, gradient traces of BC sides / of all sides) is the rare case: one block-uniform flag,
+    // reduced by the barrier itself, so that the node phase tests a single condition per node
+    int bcBits = fdK;
+#pragma unroll
+    for (int c = 0; c < HALF; ++c) bcBits |= fdI[c] | fdJ[c];
+    // S2: G1, G2, the face lifting fluxes and the metric planes complete
+    const bool rareAny = __syncthreads_or(A.fullGrad || (bcBits & 0x40000000) || A.gvol[0] != nullptr);
+    FX_STAMP(3)
 
     // ---- zeta ownership: metric combination, surface part, Jacobian, traces for the side kernel, viscous flux ----
-    double hvc[HALF][4];  // h~ of the own nodes: its zeta derivative is formed from registers after S3
 #pragma unroll
     for (int c = 0; c < HALF; ++c)
 #pragma unroll
-      for (int v = 0; v < 4; ++v) hvc[c][v] = 0.;
+      for (int v = 0; v < 4; ++v) cown[c][v] = cpart[c][v] = 0.;
     if (!FX_DBG(A, 4)) {
       constexpr int LV = (NVC == 5) ? 1 : 0;
       const int i = r0, j = r1;
@@ -456,34 +535,15 @@ __global__ void __launch_bounds__(VolGL2Cfg<NP, PARA, NVC>::NT, VolGL2Cfg<NP, PA
         const int n = i + NP * (j + NP * k);
         double Mc[9];
 #pragma unroll
-        for (int m = 0; m < 9; ++m) Mc[m] = Mn[m];
-        const double sJc = sJn;
-        if (c + 1 < HALF) {  // metric terms + Jacobian straight from HBM, one node ahead of the arithmetic
-          const int n1 = gl2_gn<NP>(2, gl2_ap<NP>(hb, c + 1), r0, r1);
-#pragma unroll
-          for (int m = 0; m < 9; ++m) Mn[m] = __ldg(gM + m * D::NP3 + n1);
-          sJn = __ldg(A.m.sJ + (size_t)e * D::NP3 + n1);
-        }
-        // ---- boundary nodes.  One (partially active) block per sheet direction instead of one per local side: the lanes of a
-        //      warp that sit on xi- and xi+ run the same code with their own side index.  The zeta faces belong to the line
-        //      end c == 0 of every thread (k = 0 for half 0, k = N for half 1), a warp-uniform condition. ----
-        const bool onI = (i == 0) | (i == N), onJ = (j == 0) | (j == N), onK = (c == 0);
-        const int lsI = (i == 0) ? XI_MINUS : XI_PLUS, lsJ = (j == 0) ? ETA_MINUS : ETA_PLUS, lsK = hb ? ZETA_PLUS : ZETA_MINUS;
+        for (int m = 0; m < 9; ++m) Mc[m] = C::MSM ? sM[m * PL + s] : __ldg(gM + m * D::NP3 + n);
+        const double sJc = sJv[c];
+        // ---- boundary nodes: unconditional code, see the remark at the normal vectors.  The zeta faces belong to the line
+        //      end c == 0 of every thread, a compile-time condition. ----
+        const bool onK = (c == 0);  // compile-time after unrolling
         const int abI = j + NP * k, abJ = i + NP * k, abK = i + NP * j;
-        // trace destination + normal vector of the (up to three) faces of this node; the vector comes from L2 (prefetched)
-        int fdI = 0, fdJ = 0, fdK = 0;
-        double nI[3] = {0., 0., 0.}, nJ[3] = {0., 0., 0.}, nK[3] = {0., 0., 0.};
-        auto face_geo = [&](int ls, int ab, int& fd, double (&nv)[3]) {
-          fd = sFD[(ls - 1) * D::NP2 + ab];
-          const int fl = fd & 0x3fffffff;
-          const double* g = A.m.Geo + (size_t)(fl / D::NP2) * 10 * D::NP2 + fl % D::NP2;
-          nv[0] = __ldg(g);
-          nv[1] = __ldg(g + D::NP2);
-          nv[2] = __ldg(g + 2 * D::NP2);
-        };
-        if (onI) face_geo(lsI, abI, fdI, nI);
-        if (onJ) face_geo(lsJ, abJ, fdJ, nJ);
-        if (onK) face_geo(lsK, abK, fdK, nK);
+        const double* const oI = sF + (lsI - 1) * NVC * D::NP2 + abI;
+        const double* const oJ = sF + (lsJ - 1) * NVC * D::NP2 + abJ;
+        const double* const oK = sF + (lsK - 1) * NVC * D::NP2 + abK;
         double gx[NVC], gy[NVC], gz[NVC];
 #pragma unroll
         for (int v = 0; v < NVC; ++v) {
@@ -493,27 +553,32 @@ __global__ void __launch_bounds__(VolGL2Cfg<NP, PARA, NVC>::NT, VolGL2Cfg<NP, PA
           gz[v] = Mc[2] * gxi + Mc[5] * geta + Mc[8] * gzeta;
         }
         double gxo[NVC], gyo[NVC], gzo[NVC];  // BR2: gradients without the surface part (what the faces are prolonged from)
+        double fI[NVC], fJ[NVC], fK[NVC];     // Flux * L_Hat of the node's faces
+#pragma unroll
+        for (int v = 0; v < NVC; ++v) {
+          fI[v] = oI[v * D::NP2];
+          fJ[v] = oJ[v * D::NP2];
+          fK[v] = onK ? oK[v * D::NP2] : 0.;
+        }
         // lifting, surface part (BR1 lifting_br1.t90:195-292; BR2 lifting_br2.t90:194-311)
-        auto surf_in = [&](int ls, int ab, const double (&nv)[3]) {
-          const double* o = sF + (ls - 1) * NVC * D::NP2 + ab;
+        auto surf_in = [&](const double (&f)[NVC], const double (&nv)[3]) {
 #pragma unroll
           for (int v = 0; v < NVC; ++v) {
-            const double f = o[v * D::NP2];  // Flux * L_Hat
             if (LIFT == 1) {
-              gx[v] = gx[v] + f * nv[0];
-              gy[v] = gy[v] + f * nv[1];
-              gz[v] = gz[v] + f * nv[2];
+              gx[v] = gx[v] + f[v] * nv[0];
+              gy[v] = gy[v] + f[v] * nv[1];
+              gz[v] = gz[v] + f[v] * nv[2];
             } else {
-              gx[v] = gx[v] + sJc * (f * nv[0]);
-              gy[v] = gy[v] + sJc * (f * nv[1]);
-              gz[v] = gz[v] + sJc * (f * nv[2]);
+              gx[v] = gx[v] + sJc * (f[v] * nv[0]);
+              gy[v] = gy[v] + sJc * (f[v] * nv[1]);
+              gz[v] = gz[v] + sJc * (f[v] * nv[2]);
             }
           }
         };
         if (LIFT == 1) {  // BR1: surface part, then ApplyJacobianLifting
-          if (onI) surf_in(lsI, abI, nI);
-          if (onJ) surf_in(lsJ, abJ, nJ);
-          if (onK) surf_in(lsK, abK, nK);
+          surf_in(fI, nI[c]);
+          surf_in(fJ, nJ[c]);
+          if (onK) surf_in(fK, nK);
 #pragma unroll
           for (int v = 0; v < NVC; ++v) {
             gx[v] = gx[v] * sJc;
@@ -530,17 +595,9 @@ __global__ void __launch_bounds__(VolGL2Cfg<NP, PARA, NVC>::NT, VolGL2Cfg<NP, PA
             gyo[v] = gy[v];
             gzo[v] = gz[v];
           }
-          if (onI) surf_in(lsI, abI, nI);
-          if (onJ) surf_in(lsJ, abJ, nJ);
-          if (onK) surf_in(lsK, abK, nK);
-        }
-        if (A.gvol[0]) {
-#pragma unroll
-          for (int v = 0; v < NVC; ++v) {
-            A.gvol[0][((size_t)e * NVL + v + VOFF) * D::NP3 + n] = gx[v];
-            A.gvol[1][((size_t)e * NVL + v + VOFF) * D::NP3 + n] = gy[v];
-            A.gvol[2][((size_t)e * NVL + v + VOFF) * D::NP3 + n] = gz[v];
-          }
+          surf_in(fI, nI[c]);
+          surf_in(fJ, nJ[c]);
+          if (onK) surf_in(fK, nK);
         }
         // ---- viscous flux of this node (flux.f90:149-241) ----
         const double v1 = sP[VEL1 * PL + s], v2 = sP[VEL2 * PL + s], v3 = sP[VEL3 * PL + s];
@@ -551,106 +608,158 @@ __global__ void __launch_bounds__(VolGL2Cfg<NP, PARA, NVC>::NT, VolGL2Cfg<NP, PA
         //      state and (BR1) the face gradient are copies of the boundary node's (prolongtoface.t90:270-303), so the element
         //      writes n.F_v of its own side (4 doubles per face node) instead of the 3*nVarLifting gradient traces.  The
         //      gradient traces themselves are still written for boundary-condition sides (GetBoundaryFlux needs them) and, when
-        //      the host asked for a full DG operator evaluation, for every side. ----
-        auto face_out = [&](int ls, int ab, int fd, const double (&nv)[3]) {
+        //      the host asked for a full DG operator evaluation, for every side (the one rare branch of the node phase). ----
+        auto face_out = [&](bool on, int ls, int fd, const double (&f)[NVC], const double (&nv)[3]) {
           const bool master = fd >= 0;
           const int fl = fd & 0x3fffffff, side = fl / D::NP2, pq = fl % D::NP2;
           double gfx[NVC], gfy[NVC], gfz[NVC];
+          double nf[4];
           if (LIFT == 2) {  // BR2 face gradient: volume-only value + eta*L_Minus(0)*sJ*Flux*L_HatMinus(0) of the side itself
-            const double* of = sF + (ls - 1) * NVC * D::NP2 + ab;
             const double w = sEta[ls - 1] * B.lm0;
 #pragma unroll
             for (int v = 0; v < NVC; ++v) {
-              const double f = of[v * D::NP2];
-              gfx[v] = gxo[v] + w * (sJc * (f * nv[0]));
-              gfy[v] = gyo[v] + w * (sJc * (f * nv[1]));
-              gfz[v] = gzo[v] + w * (sJc * (f * nv[2]));
+              gfx[v] = gxo[v] + w * (sJc * (f[v] * nv[0]));
+              gfy[v] = gyo[v] + w * (sJc * (f[v] * nv[1]));
+              gfz[v] = gzo[v] + w * (sJc * (f[v] * nv[2]));
+            }
+            double ff[4], gf[4], hf[4];
+            eval_diff_flux3d(q, v1, v2, v3, gfx + LV, gfy + LV, gfz + LV, ff, gf, hf);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) nf[v] = nv[0] * ff[v] + nv[1] * gf[v] + nv[2] * hf[v];
+          } else {
+#pragma unroll
+            for (int v = 0; v < 4; ++v) nf[v] = nv[0] * fv[v] + nv[1] * gv[v] + nv[2] * hv[v];
+          }
+          // predicated stores (no branch: see the remark at the normal vectors)
+          double* const dv = (master ? A.fvm : A.fvs) + (size_t)side * 4 * D::NP2 + pq;
+#pragma unroll
+          for (int v = 0; v < 4; ++v) st_global_if(on, dv + v * D::NP2, nf[v]);
+        };
+        face_out(onI, lsI, fdI[c], fI, nI[c]);
+        face_out(onJ, lsJ, fdJ[c], fJ, nJ[c]);
+        if (onK) face_out(true, lsK, fdK, fK, nK);
+        if (__builtin_expect(rareAny, 0)) {  // gradient output: volume gradients on request, gradient traces of BC sides / all sides
+          if (A.gvol[0]) {
+#pragma unroll
+            for (int v = 0; v < NVC; ++v) {
+              A.gvol[0][((size_t)e * NVL + v + VOFF) * D::NP3 + n] = gx[v];
+              A.gvol[1][((size_t)e * NVL + v + VOFF) * D::NP3 + n] = gy[v];
+              A.gvol[2][((size_t)e * NVL + v + VOFF) * D::NP3 + n] = gz[v];
             }
           }
-          if (A.fullGrad || (fd & 0x40000000)) {
+          auto grad_out = [&](bool on, int ls, int fd, const double (&f)[NVC], const double (&nv)[3]) {
+            if (!(on && (A.fullGrad || (fd & 0x40000000)))) return;
+            const bool master = fd >= 0;
+            const int fl = fd & 0x3fffffff, side = fl / D::NP2, pq = fl % D::NP2;
             double* const d0 = master ? A.gm[0] : A.gs[0];
             double* const d1 = master ? A.gm[1] : A.gs[1];
             double* const d2 = master ? A.gm[2] : A.gs[2];
             const size_t o0 = (size_t)side * NVL * D::NP2 + pq;
+            const double w = (LIFT == 2) ? sEta[ls - 1] * B.lm0 : 0.;
 #pragma unroll
             for (int v = 0; v < NVC; ++v) {
               const size_t o = o0 + (size_t)(v + VOFF) * D::NP2;
-              d0[o] = (LIFT == 2) ? gfx[v] : gx[v];
-              d1[o] = (LIFT == 2) ? gfy[v] : gy[v];
-              d2[o] = (LIFT == 2) ? gfz[v] : gz[v];
+              d0[o] = (LIFT == 2) ? gxo[v] + w * (sJc * (f[v] * nv[0])) : gx[v];
+              d1[o] = (LIFT == 2) ? gyo[v] + w * (sJc * (f[v] * nv[1])) : gy[v];
+              d2[o] = (LIFT == 2) ? gzo[v] + w * (sJc * (f[v] * nv[2])) : gz[v];
             }
-          }
-          double* const dv = (master ? A.fvm : A.fvs) + (size_t)side * 4 * D::NP2 + pq;
-          if (LIFT == 2) {
-            double ff[4], gf[4], hf[4];
-            eval_diff_flux3d(q, v1, v2, v3, gfx + LV, gfy + LV, gfz + LV, ff, gf, hf);
-#pragma unroll
-            for (int v = 0; v < 4; ++v) dv[v * D::NP2] = nv[0] * ff[v] + nv[1] * gf[v] + nv[2] * hf[v];
-          } else {
-#pragma unroll
-            for (int v = 0; v < 4; ++v) dv[v * D::NP2] = nv[0] * fv[v] + nv[1] * gv[v] + nv[2] * hv[v];
-          }
-        };
-        if (onI) face_out(lsI, abI, fdI, nI);
-        if (onJ) face_out(lsJ, abJ, fdJ, nJ);
-        if (onK) face_out(lsK, abK, fdK, nK);
+          };
+          grad_out(onI, lsI, fdI[c], fI, nI[c]);
+          grad_out(onJ, lsJ, fdJ[c], fJ, nJ[c]);
+          if (onK) grad_out(true, lsK, fdK, fK, nK);
+        }
         // ---- contravariant components (volint.f90:378-422): f~, g~ over the node's own G1/G2 slots (only this thread reads
-        //      them), h~ stays in registers ----
+        //      them); h~ is spent right away on its zeta derivative (volint.f90:310-315 for the zeta direction):
+        //      D_Hat_T(l = c, i = t) * h~(c) goes to node t of the line, t < HALF own, t >= HALF the partner's ----
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
           sW[(0 + v) * PL + s] = fv[v] * Mc[0] + gv[v] * Mc[1] + hv[v] * Mc[2];
           sW[(4 + v) * PL + s] = fv[v] * Mc[3] + gv[v] * Mc[4] + hv[v] * Mc[5];
-          hvc[c][v] = fv[v] * Mc[6] + gv[v] * Mc[7] + hv[v] * Mc[8];
+          const double hvc = fv[v] * Mc[6] + gv[v] * Mc[7] + hv[v] * Mc[8];
+#pragma unroll
+          for (int t = 0; t < HALF; ++t) {
+            cown[t][v] = cown[t][v] + B.dh[c * NP + t] * hvc;
+            cpart[t][v] = cpart[t][v] + B.dh[c * NP + HALF + t] * hvc;
+          }
         }
       }
     }
-    __syncthreads();  // S3: f~, g~ complete; the face fluxes and the T plane are free from here on
+    FX_STAMP(4)
+    __syncthreads();  // S3: f~, g~ complete; the face table, the face fluxes and the T plane are free from here on
+    FX_STAMP(5)
 
-    // ---- h~ of the own nodes goes to the (now free) hand-over planes: the zeta sweep, which comes first, reads it from there
-    //      like the other two sweeps read f~ and g~ ----
+    // ---- the partner's share of the zeta derivative of h~ goes to the partner's slots of the hand-over planes (true sign) ----
 #pragma unroll
-    for (int c = 0; c < HALF; ++c) {
-      const int s = gl2_sa<NP>(2, gl2_ap<NP>(hb, c), r0, r1);
+    for (int t = 0; t < HALF; ++t) {
+      const int s = gl2_sa<NP>(2, gl2_ap<NP>(hb, HALF + t), r0, r1);
 #pragma unroll
-      for (int v = 0; v < 4; ++v) ut_plane(v + 1)[s] = hvc[c][v];
+      for (int v = 0; v < 4; ++v) ut_plane(v + 1)[s] = sgn_apply(cpart[t][v], sb);
     }
     __syncthreads();  // S3b
+    FX_STAMP(6)
   }
 
-  // ---- three direction sweeps (zeta, xi, eta) of ONE copy of the sweep code.  The partial sums change owner twice: after the
-  //      zeta sweep through the output array itself (it stays in L2; the hand-over planes still hold h~ while partners read it),
-  //      after the xi sweep through the hand-over planes (density: output array again); the eta sweep sends the raw volume
-  //      integral to HBM ----
+  // ---- three direction sweeps (zeta, xi, eta) of ONE copy of the sweep code.  The partial sums change owner twice through the
+  //      hand-over planes; the eta sweep sends the raw volume integral to HBM ----
 #pragma unroll 1
   for (int it = FX_DBG(A, 1) ? 3 : 0; it < 3; ++it) {
     const int dir = (it == 0) ? 2 : it - 1;
-    int sa[NP], gn[NP];  // indexed by canonical position
+    int sa[NP];  // indexed by canonical position
 #pragma unroll
-    for (int p = 0; p < NP; ++p) {
-      sa[p] = gl2_sa<NP>(dir, gl2_ap<NP>(hb, p), r0, r1);
-      gn[p] = gl2_gn<NP>(dir, gl2_ap<NP>(hb, p), r0, r1);
-    }
+    for (int p = 0; p < NP; ++p) sa[p] = gl2_sa<NP>(dir, gl2_ap<NP>(hb, p), r0, r1);
     const double* vp[4];
 #pragma unroll
-    for (int v = 0; v < 4; ++v) vp[v] = (dir < 2) ? sW + (dir * 4 + v) * PL : ut_plane(v + 1);
+    for (int v = 0; v < 4; ++v) vp[v] = sW + ((dir & 1) * 4 + v) * PL;
     double ut[HALF][5];
-    gl2_pair_sweep<NP, STYPE, PARA>(B, sP, vp, gM + dir * 3 * D::NP3, sa, gn, ut, A.q.kappa);
 #pragma unroll
     for (int c = 0; c < HALF; ++c) {
-      if (it == 0) {
+      ut[c][0] = 0.;
 #pragma unroll
-        for (int v = 0; v < 5; ++v) gUt[v * D::NP3 + gn[c]] = sg * ut[c][v];
-      } else if (it == 1) {
-        gUt[gn[c]] = __ldcg(gUt + gn[c]) + sg * ut[c][0];
+      for (int v = 1; v < 5; ++v) ut[c][v] = (PARA && it == 0) ? cown[c][v - 1] + sg * ut_plane(v)[sa[c]] : 0.;
+    }
+    if constexpr (C::MSM) {
+      gl2_pair_sweep<NP, STYPE, PARA>(B, sP, vp, dir < 2, sM + dir * 3 * PL, sa, sa, ut, A.q.kappa);
+    } else {
+      int gn[NP];
 #pragma unroll
-        for (int v = 1; v < 5; ++v) ut_plane(v)[sa[c]] = __ldcg(gUt + v * D::NP3 + gn[c]) + sg * ut[c][v];
-      } else {
-        gUt[gn[c]] = __ldcg(gUt + gn[c]) + sg * ut[c][0];
+      for (int p = 0; p < NP; ++p) gn[p] = gl2_gn<NP>(dir, gl2_ap<NP>(hb, p), r0, r1);
+      gl2_pair_sweep<NP, STYPE, PARA>(B, sP, vp, dir < 2, gM + dir * 3 * D::NP3, sa, gn, ut, A.q.kappa);
+    }
+    // hand-over: v = 0 through the plane R0 or (when R0 is too small for a plane) through the output array, which stays in L2
+    if (it == 0) {
 #pragma unroll
-        for (int v = 1; v < 5; ++v) gUt[v * D::NP3 + gn[c]] = ut_plane(v)[sa[c]] + sg * ut[c][v];
+      for (int c = 0; c < HALF; ++c) {
+        if (C::UT1S)
+          ut_plane(0)[sa[c]] = sgn_apply(ut[c][0], sb);
+        else
+          gUt[gl2_gn<NP>(dir, gl2_ap<NP>(hb, c), r0, r1)] = sgn_apply(ut[c][0], sb);
+#pragma unroll
+        for (int v = 1; v < 5; ++v) ut_plane(v)[sa[c]] = sgn_apply(ut[c][v], sb);
+      }
+    } else if (it == 1) {
+#pragma unroll
+      for (int c = 0; c < HALF; ++c) {
+        if (C::UT1S) {
+          ut_plane(0)[sa[c]] = ut_plane(0)[sa[c]] + sg * ut[c][0];
+        } else {
+          double* const g = gUt + gl2_gn<NP>(dir, gl2_ap<NP>(hb, c), r0, r1);
+          *g = __ldcg(g) + sg * ut[c][0];
+        }
+#pragma unroll
+        for (int v = 1; v < 5; ++v) ut_plane(v)[sa[c]] = ut_plane(v)[sa[c]] + sg * ut[c][v];
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < HALF; ++c) {
+        const int n = gl2_gn<NP>(dir, gl2_ap<NP>(hb, c), r0, r1);
+        gUt[n] = (C::UT1S ? ut_plane(0)[sa[c]] : __ldcg(gUt + n)) + sg * ut[c][0];
+#pragma unroll
+        for (int v = 1; v < 5; ++v) gUt[v * D::NP3 + n] = ut_plane(v)[sa[c]] + sg * ut[c][v];
       }
     }
+    FX_STAMP(7 + it)
     if (it < 2) __syncthreads();  // S4, S5
+    FX_STAMP(10 + it)
   }
 }
 

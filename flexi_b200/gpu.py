@@ -25,7 +25,7 @@ _LIB = None
 
 ARRAYS = dict(U=0, Ut=1, U_master=2, U_slave=3, Flux=4, gradUx=5, gradUy=6, gradUz=7, gradUx_master=8, gradUy_master=9,
               gradUz_master=10, gradUx_slave=11, gradUy_slave=12, gradUz_slave=13)
-KERNEL_CLASSES = ("volume", "flux", "update", "prolong", "calc_timestep", "layout")
+KERNEL_CLASSES = ("volume", "flux", "update", "prolong", "calc_timestep", "layout", "wait_trace", "wait_grad", "wait_flux")
 
 # every symbol include/flexi_gpu.h declares
 EXPORTS = ("flexi_gpu_last_error", "flexi_gpu_abi_version", "flexi_gpu_nccl_unique_id", "flexi_gpu_init", "flexi_gpu_finalize",

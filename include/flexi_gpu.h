@@ -212,7 +212,13 @@ int flexi_gpu_get_array(flexi_gpu_handle* h, int32_t which, double* out);
  * (testcase/taylorgreenvortex/testcase.f90:249).  Without it the first FLEXI_ARR_GRADU* request recomputes them from the current U.
  * The gradient TRACES (FLEXI_ARR_GRADU?_MASTER/SLAVE) follow the same rule: flexi_gpu_dg_time_derivative leaves all of them, the RK
  * stages of flexi_gpu_timestep write them on boundary-condition sides only (the split-form Gauss-Lobatto kernels hand n.F_visc of
- * each side to the side kernel instead), and a request after a time step recomputes them from the current U at the last stage time. */
+ * each side to the side kernel instead), and a request after a time step recomputes them from the current U at the last stage time.
+ *
+ * COLLECTIVE on multi-rank runs: a recomputation is a full DG operator evaluation including the NCCL side exchange, so
+ * flexi_gpu_get_array(FLEXI_ARR_GRADU*), flexi_gpu_analyze_tgv and flexi_gpu_dg_time_derivative must be called by ALL ranks of
+ * the communicator in the same order (as the reference's analysis routines are); a rank-0-only call deadlocks in ncclSend/Recv.
+ * Call flexi_gpu_keep_gradients(h, 1) on every rank to make the getters local.  A recomputation never changes U: the in-place
+ * solution filter (flexi_gpu_set_filter) is skipped, boundary states and the source term are evaluated at the last stage time. */
 int flexi_gpu_keep_gradients(flexi_gpu_handle* h, int32_t on);
 
 /* AnalyzeTestcase of the Taylor-Green vortex test case, steps 1-4 (testcase/taylorgreenvortex/testcase.f90:241-420): the per-rank
