@@ -164,7 +164,10 @@ def parity_gate(args, node, eqn, world, rank, local_rank, dist, torch, G):
     spec.length = np.array([2 * np.pi * b * args.parity_nel / args.nel for b in blocks])  # same element size as the benchmarked mesh
     ranks = build_case(spec, args.N, node, eqn, nranks=world, partition="block", blocks=blocks)
     me = ranks[rank]
-    U0s = [r.eqn.tgv_state(r.mesh.Elem_xGP) for r in ranks]
+    # TGV state with the wavelength of the parity box, so that it is smooth across the periodic boundaries (the 2*pi-periodic state
+    # on this shorter box has O(1) jumps there, and the 2x1x1 box went unstable -- NaN in oracle and GPU alike -- after 4 steps)
+    kx = 2 * np.pi / spec.length
+    U0s = [r.eqn.tgv_state(r.mesh.Elem_xGP * kx) for r in ranks]
     os.environ["OMP_NUM_THREADS"] = str(max(1, min(world, host_cores() // world)))
     dk = [(r.desc, r.keep) for r in ranks]
     noise, ut_strict = O.ut_noise_floor(dk, U0s)

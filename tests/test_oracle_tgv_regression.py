@@ -132,3 +132,68 @@ def test_tgv_split_gauss_row2_after_10_steps(tgv_split_gauss_run):
         # DR_p = -mean(p div u): p ~ 71 times a divergence of 1e-9 -- the 6.5e-16 absolute difference is round-off of the integrand
         tol = {"ED_D": 1e-8, "DR_p": 1e-8, "Vorticity_max": 1e-11}.get(k, 5e-13)
         assert abs(row2[k] - ref) <= tol * max(abs(ref), 1e-30) + 1e-18, (k, row2[k], ref)
+
+
+# ---- regressioncheck/checks/tgv/oInt: the reference's pin of the WEAK form on Gauss nodes and of the cut-off overintegration:
+#      4^3 elements on [0,2pi]^3, N=11, Gauss nodes, SPLIT_DG=OFF (excludeBuild.ini drops the SPLIT_DG=ON builds, builds.ini drops
+#      weak form on Gauss-Lobatto), OverintegrationType=1 (cut-off) with NUnder=7, RoeEntropyFix, BR1 with PP_OPTLIFT=1, CFL/DFL 0.9,
+#      NAnalyze=10, dt recomputed every step; rows 1 and 2 of TGV_Re1600_OInt_TGVAnalysis_Reference.csv, row 2 = state after 10 steps.
+OROW1 = dict(DR_S=0.46875000000027E-03, Ekin=0.125, Ekin_comp=0.125, Enstr=0.37500000000011, DR_u=0.46875000000020E-03,
+             DR_Sd=0.46875000000022E-03, Vorticity_max=0.19999953991265E+01, T_mean=0.10000000200000E+01, uPrime=0.28867513459481,
+             Entropy=-.10671740566753E+02, ED_S=0.46875000000013E-03)
+OROW2 = dict(Time=0.30722876528724E-01, DR_S=0.46874209530762E-03, Ekin=0.12498560830078, Ekin_comp=0.12498560370689,
+             Enstr=0.37499357091821, DR_u=0.46874202435026E-03, DR_Sd=0.46874204800293E-03, DR_p=-.55956766977786E-06,
+             Vorticity_max=0.19994147836265E+01, T_mean=0.10000001006889E+01, uPrime=0.28865851601362,
+             Entropy=-.10671740769504E+02, ED_S=0.46874195339291E-03, ED_D=0.94609365138229E-10)
+OINT_EQN = dict(parabolic=True, riemann="roeentropyfix", cfl_scale=0.9, dfl_scale=0.9, n_var_lifting=4, overintegration="cutoff",
+                n_under=7, **TGV_EQN)
+
+
+@pytest.fixture(scope="module")
+def tgv_oint_run():
+    ranks = build_case(tgv_box(4), 11, B.NODE_GAUSS, OINT_EQN, nranks=2)
+    w = O.OracleWorld([(r.desc, r.keep) for r in ranks])
+    mat = B.overintegration_mat(ranks[0].basis.xGP, 7)
+    for o in w.ranks:
+        o.set_overintegration(1, mat)
+    # timedisc.f90:115-123: with OverintegrationType=1 the host filters the initial solution once before the first DG operator call
+    U0s = [np.ascontiguousarray(np.einsum("li,mj,nk,ekjiv->enmlv", mat, mat, mat, r.eqn.tgv_state(r.mesh.Elem_xGP))) for r in ranks]
+    w.set_state(U0s)
+    ab = AnalyzeBasis(ranks[0].basis, n_analyze=10)
+    vol = sum(ab.volume(r.mesh.sJ) for r in ranks)
+
+    def analyze(refresh):
+        if refresh:
+            w.dg_time_derivative(0.0)
+        parts = [tgv_analyze(ab, r.eqn, r.mesh, o.array("U"), o.array("gradUx"), o.array("gradUy"), o.array("gradUz"), vol)
+                 for r, o in zip(ranks, w.ranks)]
+        tot = {k: (max(p[k] for p in parts) if k == "Vorticity_max" else sum(p[k] for p in parts)) for k in parts[0]}
+        tot["uPrime"] = np.sqrt(2.0 / 3.0 * tot["Ekin"])
+        return tot
+
+    row1 = analyze(True)
+    t = 0.0
+    for _ in range(10):
+        dt, _, _, err = w.calc_timestep()
+        assert err == 0
+        w.timestep(t, dt)
+        t += dt
+    row2 = analyze(False)
+    row2["Time"] = t
+    w.close()
+    return row1, row2
+
+
+def test_tgv_oint_row1(tgv_oint_run):
+    row1, _ = tgv_oint_run
+    for k, ref in OROW1.items():
+        assert abs(row1[k] - ref) <= 5e-13 * max(1.0, abs(ref)), (k, row1[k], ref)
+
+
+def test_tgv_oint_row2_after_10_steps(tgv_oint_run):
+    """Weak form on Gauss nodes (volint.f90:117-205, surfint.t90:21-239, prolongtoface.t90:21-144), N=11, and the cut-off
+    overintegration of Ut (dg.f90:663-676) through CalcTimeStep (NEff scaling) and 50 RHS evaluations against the reference's row."""
+    _, row2 = tgv_oint_run
+    for k, ref in OROW2.items():
+        tol = {"ED_D": 1e-8, "DR_p": 1e-8, "Vorticity_max": 1e-11}.get(k, 5e-13)
+        assert abs(row2[k] - ref) <= tol * max(abs(ref), 1e-30) + 1e-18, (k, row2[k], ref)
