@@ -37,8 +37,34 @@ def b_alg_kernel(N, parabolic):
     return dict(volume=vol, flux=flux, update=upd)
 
 
+def naca_nel(nel, world):
+    """configs[3] mesh: nel elements around the section, nel/3 radial, nel/6 per GPU along the span (z-slabs of the linear partition)."""
+    return (nel, max(2, nel // 3), max(2, nel // 6) * world)
+
+
+def workload_case(args, world, nel, small=False):
+    """(spec, partition kwargs, initial-state function of a HostRank) of the benchmarked workload on `world` ranks with `nel`
+    elements per direction per GPU."""
+    from flexi_b200.hostmesh.case import naca_spec, naca_state, tgv_box
+
+    if args.workload == "naca":
+        spec = naca_spec(naca_nel(nel, world))
+        return spec, dict(partition="linear"), (lambda r: naca_state(r.eqn, r.mesh.Elem_xGP))
+    blocks = BLOCKS[world]
+    spec = tgv_box(tuple(nel * b for b in blocks))
+    if small:  # parity gate: element size of the benchmarked mesh, TGV state with the wavelength of the (smaller) box
+        spec.length = np.array([2 * np.pi * b * nel / args.nel for b in blocks])
+    else:      # same element size at every N: true weak scaling, TGV tiles periodically
+        spec.length = np.array([2 * np.pi * b for b in blocks])
+    kx = 2 * np.pi / spec.length if small else 1.0
+    return spec, dict(partition="block", blocks=blocks), (lambda r: r.eqn.tgv_state(r.mesh.Elem_xGP * kx))
+
+
 def eqn_for(args):
-    from flexi_b200.hostmesh.case import TGV_EQN
+    from flexi_b200.hostmesh.case import NACA_EQN, TGV_EQN
+
+    if args.workload == "naca":  # configs[3]: Gauss nodes, weak form, HLLC + BR2, isothermal wall + Dirichlet far field
+        return "gauss", dict(NACA_EQN, n_var_lifting=5)
 
     if args.flavour == "split":   # configs[1]
         return "gauss-lobatto", dict(parabolic=True, split_dg=True, split_dg_type="pi", riemann="lf", cfl_scale=0.8, dfl_scale=0.8,
@@ -115,15 +141,16 @@ def host_cores():
 
 def run_cpu(args, steps, warmup, nel, cores):
     """The reference algorithm on the host cores: oracle port, -O3 build, one emulated MPI rank per core (OpenMP thread)."""
-    from flexi_b200.hostmesh.case import build_case, tgv_box
+    from flexi_b200.hostmesh.case import build_case
     from oracle import oracle as O
 
     node, eqn = eqn_for(args)
-    nranks = max(1, min(cores, nel ** 3 // 8))
+    spec, _, state = workload_case(args, 1, nel)
+    nranks = max(1, min(cores, spec.n_global_elems // 8))
     os.environ["OMP_NUM_THREADS"] = str(nranks)
-    ranks = build_case(tgv_box(nel), args.N, node, eqn, nranks=nranks)
+    ranks = build_case(spec, args.N, node, eqn, nranks=nranks)
     w = O.OracleWorld([(r.desc, r.keep) for r in ranks], fast=True)
-    w.set_state([r.eqn.tgv_state(r.mesh.Elem_xGP) for r in ranks])
+    w.set_state([state(r) for r in ranks])
     dt = w.calc_timestep()[0]
     t = 0.0
     for _ in range(warmup):
@@ -135,7 +162,7 @@ def run_cpu(args, steps, warmup, nel, cores):
         t += dt
     el = time.perf_counter() - t0
     w.close()
-    ndof = nel ** 3 * (args.N + 1) ** 3
+    ndof = spec.n_global_elems * (args.N + 1) ** 3
     nst = len(ranks[0].eqn.RKb)
     return ndof * nst * steps / el / 1e9, el, nranks, ndof
 
@@ -155,19 +182,15 @@ def parity_gate(args, node, eqn, world, rank, local_rank, dist, torch, G):
     (NCCL side exchange included) and compares its slice with the oracle world of all ranks, which it computes itself on the host.
     Returns max-over-ranks of: one Ut (max|diff|/max|ref| per variable, and the same in units of the gate = max(1e-12*scale,
     4 x the oracle's own strict-vs-FMA build noise)), the state after K fixed-dt LSERK steps (gate 1e-12) and dt (gate 1e-13)."""
-    from flexi_b200.hostmesh.case import build_case, tgv_box
+    from flexi_b200.hostmesh.case import build_case
     from oracle import oracle as O
 
-    blocks = BLOCKS[world]
-    nel = tuple(args.parity_nel * b for b in blocks)
-    spec = tgv_box(nel)
-    spec.length = np.array([2 * np.pi * b * args.parity_nel / args.nel for b in blocks])  # same element size as the benchmarked mesh
-    ranks = build_case(spec, args.N, node, eqn, nranks=world, partition="block", blocks=blocks)
-    me = ranks[rank]
-    # TGV state with the wavelength of the parity box, so that it is smooth across the periodic boundaries (the 2*pi-periodic state
+    # TGV: state with the wavelength of the parity box, so that it is smooth across the periodic boundaries (the 2*pi-periodic state
     # on this shorter box has O(1) jumps there, and the 2x1x1 box went unstable -- NaN in oracle and GPU alike -- after 4 steps)
-    kx = 2 * np.pi / spec.length
-    U0s = [r.eqn.tgv_state(r.mesh.Elem_xGP * kx) for r in ranks]
+    spec, part, state = workload_case(args, world, max(12, 2 * args.parity_nel) if args.workload == "naca" else args.parity_nel, small=True)
+    ranks = build_case(spec, args.N, node, eqn, nranks=world, **part)
+    me = ranks[rank]
+    U0s = [state(r) for r in ranks]
     os.environ["OMP_NUM_THREADS"] = str(max(1, min(world, host_cores() // world)))
     dk = [(r.desc, r.keep) for r in ranks]
     noise, ut_strict = O.ut_noise_floor(dk, U0s)
@@ -188,7 +211,8 @@ def parity_gate(args, node, eqn, world, rank, local_rank, dist, torch, G):
         ref = ut_strict[rank]
         scale = ut_scale(np.concatenate([u.reshape(-1, 5) for u in ut_strict]))
         d = np.max(np.abs(ut - ref).reshape(-1, 5), axis=0)
-        gate = np.maximum(1e-12 * scale, 4.0 * noise)
+        # naca: 8 x noise (the wall layer's 1/J amplifies every rounding difference; the CUDA kernels contract other FMAs than gcc)
+        gate = np.maximum(1e-12 * scale, (8.0 if args.workload == "naca" else 4.0) * noise)
         out["ut_rel"] = float(np.max(d / scale))
         out["ut_over_gate"] = float(np.max(d / gate))
         out["noise_abs"] = [float(x) for x in noise]
@@ -212,7 +236,7 @@ def parity_gate(args, node, eqn, world, rank, local_rank, dist, torch, G):
         out.update(dict(zip(keys, [float(x) for x in tt.tolist()])))
     out["ok"] = bool(out["ut_over_gate"] <= 1.0 and out["state_rel"] <= 1e-12 and out["dt_rel"] <= 1e-13)
     out["what"] = (f"same flavour and partition shape, {args.parity_nel}^3 elements per GPU, GPU (C ABI, NCCL exchange at N>1) vs CPU oracle: one Ut "
-                   f"(gate max(1e-12*scale, 4x oracle strict-vs-FMA noise)), dt (1e-13), state after {args.parity_steps} LSERK steps (1e-12)")
+                   f"(gate max(1e-12*scale, {8 if args.workload == 'naca' else 4}x oracle strict-vs-FMA noise)), dt (1e-13), state after {args.parity_steps} LSERK steps (1e-12)")
     return out
 
 
@@ -229,19 +253,28 @@ def parity_fullsize(args, g, r, U0, noise):
     cons = np.einsum("ekjiv,ekji->v", ut, w3)
     mag = np.einsum("ekjiv,ekji->v", np.abs(ut), w3)
     mag[0:4] = mag[1:4].max()
-    out["conservation_rel"] = float(np.max(np.abs(cons) / mag))
+    # walls and far field exchange mass, momentum and energy with the outside: the identity holds on the periodic box only
+    out["conservation_rel"] = float(np.max(np.abs(cons) / mag)) if args.workload == "tgv" else 0.0
     if mem_available_gb() > 96.0 and not args.no_fullsize_oracle:
         t0 = time.perf_counter()
-        w = O.OracleWorld([(r.desc, r.keep)], fast=True)
-        w.set_state([U0])
-        w.dg_time_derivative(0.0)
-        ref = w.ranks[0].array("Ut")
+        if args.workload == "naca":
+            # 1/J of the wall layer grows with the resolution, and the round-off of Ut with it: the noise floor (strict vs FMA
+            # build of the oracle) is measured on the benchmarked mesh itself instead of being carried over from the small case
+            noise_full, refs = O.ut_noise_floor([(r.desc, r.keep)], [U0])
+            ref = refs[0]
+            gate_noise = 8.0 * noise_full
+        else:
+            w = O.OracleWorld([(r.desc, r.keep)], fast=True)
+            w.set_state([U0])
+            w.dg_time_derivative(0.0)
+            ref = np.array(w.ranks[0].array("Ut"))
+            w.close()
+            gate_noise = 8.0 * np.asarray(noise)
         scale = ut_scale(ref)
         d = np.max(np.abs(ut - ref).reshape(-1, 5), axis=0)
         out["ut_rel_fullsize"] = float(np.max(d / scale))
-        out["ut_over_gate_fullsize"] = float(np.max(d / np.maximum(1e-12 * scale, 8.0 * np.asarray(noise))))
+        out["ut_over_gate_fullsize"] = float(np.max(d / np.maximum(1e-12 * scale, gate_noise)))
         out["fullsize_oracle_s"] = time.perf_counter() - t0
-        w.close()
     else:
         out["ut_rel_fullsize"] = out["ut_over_gate_fullsize"] = None
     return out
@@ -264,7 +297,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="flexi_b200", choices=["flexi_b200", "reference"])
     ap.add_argument("--nel", type=int, default=48, help="elements per direction PER GPU (BASELINE configs[1]: 48)")
-    ap.add_argument("--N", type=int, default=7)
+    ap.add_argument("--workload", default="tgv", choices=["tgv", "naca"],
+                    help="tgv: BASELINE configs[1]/[0]/[4]; naca: configs[3] (NACA0012-style curved O-mesh, randomly oriented elements, "
+                         "N=5, HLLC + BR2, wall + far field; --nel = elements around the section per GPU-slab: nel x nel/3 x nel/6 per GPU)")
+    ap.add_argument("--N", type=int, default=None, help="polynomial degree (default 7; naca: 5)")
     ap.add_argument("--flavour", default="split", choices=["split", "weak"], help="split: configs[1]; weak: configs[0] flavour")
     ap.add_argument("--cpu-nel", type=int, default=0, help="box size of the CPU run; 0 = --impl reference: the benchmarked box (--nel) when the "
                     "host has the memory, else 16; cpu_baseline leg of the repo arm: 16")
@@ -274,6 +310,10 @@ def main():
     ap.add_argument("--no-fullsize-oracle", action="store_true", help="skip the single-rank oracle Ut on the benchmarked mesh (N=1)")
     ap.add_argument("--profile-steps", type=int, default=2, help="extra steps with per-kernel CUDA events for the roofline object")
     args = ap.parse_args()
+    if args.N is None:
+        args.N = 5 if args.workload == "naca" else 7
+    if args.workload == "naca" and args.nel == 48:
+        args.nel = 96
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -282,6 +322,10 @@ def main():
     workload = (f"TGV Navier-Stokes N={args.N}, {args.nel}^3 elements per GPU, "
                 + ("split-form Gauss-Lobatto (Pirozzoli) + Lax-Friedrichs" if args.flavour == "split" else "weak-form Gauss + Roe")
                 + ", BR1, LSERK4-5 (carpenterrk4-5)")
+    if args.workload == "naca":
+        n3 = naca_nel(args.nel, 1)
+        workload = (f"NACA0012-style synthetic curved O-mesh (NGeo=4, every element in a random local frame), Navier-Stokes N={args.N}, "
+                    f"{n3[0]}x{n3[1]}x{n3[2]} elements per GPU (z-slabs), weak-form Gauss, HLLC + BR2, isothermal wall + Dirichlet far field, LSERK4-5")
 
     if args.impl == "reference":
         if rank != 0:
@@ -289,15 +333,17 @@ def main():
         cores = host_cores()
         cpu_nel = args.cpu_nel
         if cpu_nel == 0:  # the benchmarked configuration itself needs ~0.6 KB per DOF on the host (oracle arrays + host mesh)
-            need_gb = args.nel ** 3 * (args.N + 1) ** 3 * 900.0 / 2 ** 30
-            cpu_nel = args.nel if mem_available_gb() > need_gb + 16.0 else 16
+            nE_full = int(np.prod(naca_nel(args.nel, 1))) if args.workload == "naca" else args.nel ** 3
+            need_gb = nE_full * (args.N + 1) ** 3 * 900.0 / 2 ** 30
+            cpu_nel = args.nel if mem_available_gb() > need_gb + 16.0 else (24 if args.workload == "naca" else 16)
         # the whole run has to end within a few minutes: ~0.18 us per DOF and stage and core
-        est_step_s = cpu_nel ** 3 * (args.N + 1) ** 3 * nst * 0.6e-6 / max(1, min(cores, cpu_nel ** 3 // 8))
+        nE_cpu = int(np.prod(naca_nel(cpu_nel, 1))) if args.workload == "naca" else cpu_nel ** 3
+        est_step_s = nE_cpu * (args.N + 1) ** 3 * nst * 0.6e-6 / max(1, min(cores, nE_cpu // 8))
         steps = max(1, min(args.steps, int(150.0 / est_step_s)))
         warmup = max(0, min(args.warmup, int(30.0 / est_step_s)))
         val, el, nr, ndof = run_cpu(args, steps, warmup, cpu_nel, cores)
         same = "the benchmarked box itself" if cpu_nel == args.nel else "a bounded sample of the workload"
-        sample = (f"{same}: same flavour, {cpu_nel}^3 elements ({ndof} DOF), {steps} timed LSERK steps after {warmup} warm-up ({el:.1f} s), {nr} emulated "
+        sample = (f"{same}: same flavour, {nE_cpu} elements ({ndof} DOF), {steps} timed LSERK steps after {warmup} warm-up ({el:.1f} s), {nr} emulated "
                   f"MPI ranks (one per OpenMP thread), C port of the reference (oracle/flexi_oracle.c, -O3 -march=x86-64-v3); no Fortran compiler in the image")
         line = {"impl": "reference", "metric": "GDOF/s (DOF*RK-stages per second), PID = 1/(value*1e9) s/DOF/stage", "value": val,
                 "unit": "GDOF/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": el / steps * 1e3,
@@ -331,11 +377,9 @@ def main():
         if not parity["ok"]:
             raise SystemExit(f"bench.py: parity gate failed, no number is reported: {parity}")
     blocks = BLOCKS[world]
-    nel = tuple(args.nel * b for b in blocks)
-    spec = tgv_box(nel)
-    spec.length = np.array([2 * np.pi * b for b in blocks])  # same element size at every N: true weak scaling, TGV tiles periodically
+    spec, part, state = workload_case(args, world, args.nel)
     t_mesh = time.perf_counter()
-    r = build_case(spec, args.N, node, eqn, nranks=world, partition="block", blocks=blocks, ranks=[rank])[0]
+    r = build_case(spec, args.N, node, eqn, nranks=world, ranks=[rank], **part)[0]
     t_mesh = time.perf_counter() - t_mesh
     nccl_id = None
     if world > 1:
@@ -351,7 +395,7 @@ def main():
     ndof = ndof_local * world
 
     U0 = torch.empty(r.mesh.Elem_xGP.shape[:-1] + (5,), dtype=torch.float64, pin_memory=True)
-    U0.numpy()[...] = r.eqn.tgv_state(r.mesh.Elem_xGP)
+    U0.numpy()[...] = state(r)
     Uout = torch.empty_like(U0, pin_memory=True)
     g.set_state(U0.numpy())
     dt = g.CalcTimeStep()[0]
@@ -436,7 +480,7 @@ def main():
         xwait = {k: max_over_ranks(kt["wait_" + k][0] / (args.profile_steps * nst)) for k in ("trace", "grad", "flux")}
     dom = max(kern, key=lambda k: kern[k]["avg_ms"] * kern[k]["launches_per_stage"])
     stage_ms = sum(v["avg_ms"] * v["launches_per_stage"] for v in kern.values())
-    kname = {"volume": "k_volume_gl2" if (args.flavour == "split" and (args.N + 1) % 2 == 0) else "k_volume", "flux": "k_flux", "update": "k_update"}
+    kname = {"volume": "k_volume_gl2" if (args.workload == "tgv" and args.flavour == "split" and (args.N + 1) % 2 == 0) else "k_volume", "flux": "k_flux", "update": "k_update"}
     roofline = {"bound": "hbm", "kernel": kname[dom], "achieved": kern[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                 "frac": kern[dom]["achieved_gbs"] / peak, "traffic": None, "peak_source": peak_src,
                 "share_of_stage": kern[dom]["avg_ms"] * kern[dom]["launches_per_stage"] / stage_ms, "kernels": kern,
@@ -456,10 +500,10 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = host_cores()
-        cnel = args.cpu_nel or 16
+        cnel = args.cpu_nel or (24 if args.workload == "naca" else 16)
         val, el, nr, nd = run_cpu(args, 30, 2, cnel, cores)
         cpu = {"value": val, "unit": "GDOF/s", "cores": nr, "kind": "port",
-               "sample": f"same flavour on a {cnel}^3-element box ({nd} DOF), 30 timed LSERK steps in {el:.1f} s, {nr} emulated MPI ranks, "
+               "sample": f"same flavour, {'NACA O-mesh nel=' if args.workload == 'naca' else 'box nel='}{cnel} ({nd} DOF), 30 timed LSERK steps in {el:.1f} s, {nr} emulated MPI ranks, "
                          "C port of the reference (-O3 -march=x86-64-v3)"}
     g.close()
     if rank == 0:
@@ -468,7 +512,7 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "pid_s_per_dof_stage": 1.0 / (value * 1e9), "pid_x_ngpu": world / (value * 1e9),
                 "config": {"workload": workload, "n_dof": ndof, "n_elems_per_gpu": r.mesh.nElems, "rk_stages": nst, "dt": dt,
-                           "partition": "x".join(map(str, blocks)) + " blocks", "l2": "working set 20 GB per GPU >> 126 MB L2 (no flush needed)",
+                           "partition": ("x".join(map(str, blocks)) + " blocks") if args.workload == "tgv" else f"{world} z-slabs (linear)", "l2": "working set 20 GB per GPU >> 126 MB L2 (no flush needed)",
                            "mesh_build_s": t_mesh},
                 "clocks": clk.summary(), "gpu_launches": launches,
                 "e2e": {"value": e2e_val, "unit": "GDOF/s", "h2d_bytes_per_step": ubytes / args.steps,

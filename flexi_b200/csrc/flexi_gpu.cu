@@ -98,7 +98,8 @@ struct flexi_gpu_handle {
   double *U = nullptr, *UtVol = nullptr, *UtTmp = nullptr, *Ut = nullptr;
   double *Um = nullptr, *Us = nullptr, *Flux = nullptr;
   double *gm[3] = {nullptr, nullptr, nullptr}, *gs[3] = {nullptr, nullptr, nullptr}, *gvol[3] = {nullptr, nullptr, nullptr};
-  double *dtElem = nullptr, *dt3 = nullptr;
+  double *dtElem = nullptr, *dt3 = nullptr, *dtPart = nullptr;
+  int nDtPart = 0;
   double KappasPr_max = 0.;
   double* dt3_host = nullptr;  // pinned
   double* stage = nullptr;     // AoS staging buffer
@@ -113,6 +114,9 @@ struct flexi_gpu_handle {
   bool filtOn = false;                    // OverintegrationType == cutoff
   double* filtUMat = nullptr;             // FilterMat [out][in] of the solution filter (FilterType cutoff / modal)
   bool filtUOn = false;
+  int32_t* spIdx = nullptr;               // Sponge: element -> index in the sponge list (-1 = none); nullptr = doSponge off
+  double *spMat = nullptr, *spBase = nullptr;
+  bool spOn = false;
   bool vt = false;             // viscous-trace protocol between k_volume_gl2 and k_flux (kernels.cuh: VolArgs::fvm)
   bool gradTracesFull = true;  // gradU?_master/slave hold the traces of every side (else only of the BC sides)
   double *fvm = nullptr, *fvs = nullptr;
@@ -404,6 +408,9 @@ int launch_update(H* h, const int32_t* list, int n, int mode, double rkA, double
   a.entropy = h->entropy ? 1 : 0;
   a.q = h->q;
   a.filt = h->filtOn ? h->filtMat : nullptr;
+  a.spIdx = h->spOn ? h->spIdx : nullptr;
+  a.spMat = h->spMat;
+  a.spBase = h->spBase;
   if (n <= 0) return 0;
   Timer tm(h, KC_UPDATE, h->sc);
   CK(h->ops->update(h->gl, a, n, h->sc));
@@ -880,6 +887,8 @@ static int init_impl(const flexi_gpu_desc* d, H* h) {
   }
   // ---- CalcTimeStep (MetricsAdv / MetricsVisc are formed on the fly, kernels.cuh:k_dt) ----
   CKR(dalloc(h, &h->dtElem, nE * 3));
+  h->nDtPart = (int)std::min<size_t>(296, (nE + 255) / 256);
+  CKR(dalloc(h, &h->dtPart, (size_t)h->nDtPart * 3));
   CKR(dalloc(h, &h->dt3, 3));
   CK(cudaMallocHost((void**)&h->dt3_host, 3 * sizeof(double)));
   h->KappasPr_max = fmax(4. / 3., d->kappa / d->Pr);
@@ -990,8 +999,9 @@ int flexi_gpu_calc_timestep(flexi_gpu_handle* h, double* dt_min, double* dt_conv
   {
     Timer tm(h, KC_DT, h->sc);
     CK(h->ops->dt(a, h->nElems, h->sc));
-    k_dt_reduce<<<1, 256, 0, h->sc>>>(h->dtElem, h->nElems, h->dt3);
-    h->launches++;
+    k_dt_reduce1<<<h->nDtPart, 256, 0, h->sc>>>(h->dtElem, h->nElems, h->dtPart);
+    k_dt_reduce2<<<1, 256, 0, h->sc>>>(h->dtPart, h->nDtPart, h->dt3);
+    h->launches += 2;
   }
   CK(cudaGetLastError());
   if (h->nProcs > 1) {  // MPI_ALLREDUCE(MIN) of (dtConv, dtVisc, -errType), calctimestep.f90:217-222
@@ -1269,6 +1279,33 @@ int flexi_gpu_set_filter(flexi_gpu_handle* h, int filterType, const double* Filt
   if (!h->filtUMat) CKR(dalloc(h, &h->filtUMat, m.size()));
   CK(cudaMemcpy(h->filtUMat, m.data(), m.size() * 8, cudaMemcpyHostToDevice));
   h->filtUOn = true;
+  return 0;
+}
+
+int flexi_gpu_set_sponge(flexi_gpu_handle* h, int32_t nSpongeElems, const int32_t* SpongeMap, const double* SpongeMat, const double* SpBaseFlow) {
+  ENTER(h);
+  if (nSpongeElems <= 0) {
+    h->spOn = false;
+    return 0;
+  }
+  if (!SpongeMap || !SpongeMat || !SpBaseFlow) return fail(FLEXI_GPU_ERR_ARG, "null argument");
+  if (nSpongeElems > h->nElems) return fail(FLEXI_GPU_ERR_ARG, "nSpongeElems %d > nElems %d", nSpongeElems, h->nElems);
+  std::vector<int32_t> idx((size_t)h->nElems, -1);
+  for (int i = 0; i < nSpongeElems; ++i) {
+    const int e = SpongeMap[i] - 1;  // spongeMap(iSpongeElem) = iElem, 1-based (sponge.f90:265-275)
+    if (e < 0 || e >= h->nElems) return fail(FLEXI_GPU_ERR_ARG, "SpongeMap(%d) = %d outside 1..nElems", i + 1, e + 1);
+    idx[(size_t)e] = i;
+  }
+  const size_t nSp = (size_t)nSpongeElems * h->np3, nB = (size_t)h->nElems * 5 * h->np3;
+  // the lists may change between calls (sponge.f90 rebuilds them on restart): reallocate when they grow
+  if (!h->spIdx) CKR(dalloc(h, &h->spIdx, (size_t)h->nElems));
+  if (!h->spBase) CKR(dalloc(h, &h->spBase, nB));
+  if (!h->spMat) CKR(dalloc(h, &h->spMat, (size_t)h->nElems * h->np3));
+  CK(cudaMemcpy(h->spIdx, idx.data(), idx.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->spMat, SpongeMat, nSp * 8, cudaMemcpyHostToDevice));  // (0:N,0:N,0:N,nSpongeElems) == [iSp][NP3]
+  CKR(upload_aos(h, SpBaseFlow, h->spBase, 5, h->np3, h->nElems));      // (5,0:N,0:N,0:N,nElems) -> [e][5][NP3]
+  CK(cudaStreamSynchronize(h->sc));
+  h->spOn = true;
   return 0;
 }
 

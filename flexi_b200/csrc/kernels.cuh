@@ -73,6 +73,11 @@ struct UpdArgs {
   const double* xGP;  // Elem_xGP as [e][3][NP3]
   double t, srcOmega, srcA, srcTmp[6];
   const double* filt;  // OverintegrationMat as [out][in], NP*NP doubles; nullptr = OverintegrationType 0 (k_update<.,.,.,true> reads it)
+  // Sponge(Ut), sponge.f90:612-678: spIdx[e] = index of element e in the sponge list or -1 (nullptr = doSponge off),
+  // spMat [iSponge][NP3] (SpongeMat, pre-multiplied by the Jacobian), spBase [e][5][NP3] (SpBaseFlow)
+  const int32_t* spIdx;
+  const double* spMat;
+  const double* spBase;
 };
 
 struct FiltArgs {
@@ -757,6 +762,17 @@ __global__ void __launch_bounds__(Dim<NP>::NP3) k_update(UpdArgs A) {
     uOld[v] = (A.mode != 0) ? A.U[g] : 0.;
     rkOld[v] = (A.mode == 2) ? A.UtTmp[g] : 0.;
   }
+  // Sponge(Ut) (sponge.f90:612-678, called between CalcSource and ApplyJacobian, dg.f90:659-661): SpongeMat*(U - SpBaseFlow)
+  double sp[5] = {0., 0., 0., 0., 0.};
+  const int iSp = A.spIdx ? A.spIdx[e] : -1;
+  if (iSp >= 0) {
+    const double smat = A.spMat[(size_t)iSp * D::NP3 + n];
+#pragma unroll
+    for (int v = 0; v < 5; ++v) {
+      const size_t g = ((size_t)e * 5 + v) * D::NP3 + n;
+      sp[v] = smat * (((A.mode != 0) ? uOld[v] : A.U[g]) - A.spBase[g]);
+    }
+  }
   __syncthreads();
   const double* lhm = sB + D::O_LHM;
   const double* lhp = sB + D::O_LHP;
@@ -797,6 +813,10 @@ __global__ void __launch_bounds__(Dim<NP>::NP3) k_update(UpdArgs A) {
 #pragma unroll
       for (int v = 0; v < 5; ++v) w[v] = w[v] + src[v] / sJ;
     }
+    if (iSp >= 0) {
+#pragma unroll
+      for (int v = 0; v < 5; ++v) w[v] = w[v] - sp[v];
+    }
     // three 1-D sweeps through the 5 shared planes; sums start from zero and run over ascending input index (changeBasis.t90)
 #pragma unroll
     for (int dir = 0; dir < 3; ++dir) {
@@ -827,7 +847,10 @@ __global__ void __launch_bounds__(Dim<NP>::NP3) k_update(UpdArgs A) {
     src[1] = src[2] = src[3] = A.srcTmp[1] * cosX + A.srcTmp[2] * sinX2;
     src[4] = A.srcTmp[3] * cosX + A.srcTmp[4] * sinX2 + A.srcTmp[5] * sinX;
 #pragma unroll
-    for (int v = 0; v < 5; ++v) ut[v] = ((-ut[v]) + src[v] / sJ) * sJ;
+    for (int v = 0; v < 5; ++v) ut[v] = (((-ut[v]) + src[v] / sJ) - sp[v]) * sJ;
+  } else if (iSp >= 0) {
+#pragma unroll
+    for (int v = 0; v < 5; ++v) ut[v] = ((-ut[v]) - sp[v]) * sJ;
   } else {
 #pragma unroll
     for (int v = 0; v < 5; ++v) ut[v] = (-ut[v]) * sJ;  // dg.f90:656,675
@@ -1029,35 +1052,43 @@ struct DtArgs {
   double* out;  // [e][3]
 };
 
+// The block is NP^3 rounded up to whole warps: the lanes beyond the last node carry neutral values (0) into the warp shuffles
+// (a shuffle from a lane that does not exist returns an undefined value).
 template <int NP>
-__global__ void __launch_bounds__(Dim<NP>::NP3) k_dt(DtArgs A) {
+constexpr int dt_threads() { return (Dim<NP>::NP3 + 31) / 32 * 32; }
+template <int NP>
+__global__ void __launch_bounds__(dt_threads<NP>()) k_dt(DtArgs A) {
   using D = Dim<NP>;
   constexpr int NW = (D::NP3 + 31) / 32;
   __shared__ double red[7][NW];
   const int tid = threadIdx.x, e = blockIdx.x, n = tid;
   const Eqn& q = A.q;
-  double U[5], P[6], M[9];
-#pragma unroll
-  for (int v = 0; v < 5; ++v) U[v] = A.U[((size_t)e * 5 + v) * D::NP3 + n];
-  cons_to_prim(q, U, P);
-  const double srho = 1. / U[0];
-  const double c = sqrt(q.kappa * P[PRES] * srho);
-  const double sJ = A.m.sJ[(size_t)e * D::NP3 + n];
-#pragma unroll
-  for (int cI = 0; cI < 9; ++cI) M[cI] = A.m.Met[((size_t)e * 9 + cI) * D::NP3 + n];
-  const double vs[3] = {P[VEL1] * sJ, P[VEL2] * sJ, P[VEL3] * sJ};
   double r[7];  // max over the element of: lambda_adv(3), lambda_visc(3), NaN flag
-  // NaN in the density flags errType 1 (calctimestep.f90:157-160); NaN propagates through the fmax-free sums below
-  r[6] = (U[0] != U[0]) ? 1. : 0.;
 #pragma unroll
-  for (int d = 0; d < 3; ++d) {
-    const double m0 = M[3 * d], m1 = M[3 * d + 1], m2 = M[3 * d + 2];
-    const double metAdv = sJ * sqrt(m0 * m0 + m1 * m1 + m2 * m2);                                                   // MetricsAdv
-    const double metVisc = A.KappasPr_max * ((m0 * sJ) * (m0 * sJ) + (m1 * sJ) * (m1 * sJ) + (m2 * sJ) * (m2 * sJ));  // MetricsVisc
-    r[d] = fabs(m0 * vs[0] + m1 * vs[1] + m2 * vs[2]) + c * metAdv;
-    r[3 + d] = A.parabolic ? q.mu0 * srho * metVisc : 0.;
-    // Fortran MAX may or may not propagate a NaN operand; NaN is flagged separately
-    if (r[d] != r[d] || r[3 + d] != r[3 + d]) r[6] = fmax(r[6], 2.);
+  for (int s = 0; s < 7; ++s) r[s] = 0.;
+  if (tid < D::NP3) {
+    double U[5], P[6], M[9];
+#pragma unroll
+    for (int v = 0; v < 5; ++v) U[v] = A.U[((size_t)e * 5 + v) * D::NP3 + n];
+    cons_to_prim(q, U, P);
+    const double srho = 1. / U[0];
+    const double c = sqrt(q.kappa * P[PRES] * srho);
+    const double sJ = A.m.sJ[(size_t)e * D::NP3 + n];
+#pragma unroll
+    for (int cI = 0; cI < 9; ++cI) M[cI] = A.m.Met[((size_t)e * 9 + cI) * D::NP3 + n];
+    const double vs[3] = {P[VEL1] * sJ, P[VEL2] * sJ, P[VEL3] * sJ};
+    // NaN in the density flags errType 1 (calctimestep.f90:157-160); NaN propagates through the fmax-free sums below
+    r[6] = (U[0] != U[0]) ? 1. : 0.;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const double m0 = M[3 * d], m1 = M[3 * d + 1], m2 = M[3 * d + 2];
+      const double metAdv = sJ * sqrt(m0 * m0 + m1 * m1 + m2 * m2);                                                   // MetricsAdv
+      const double metVisc = A.KappasPr_max * ((m0 * sJ) * (m0 * sJ) + (m1 * sJ) * (m1 * sJ) + (m2 * sJ) * (m2 * sJ));  // MetricsVisc
+      r[d] = fabs(m0 * vs[0] + m1 * vs[1] + m2 * vs[2]) + c * metAdv;
+      r[3 + d] = A.parabolic ? q.mu0 * srho * metVisc : 0.;
+      // Fortran MAX may or may not propagate a NaN operand; NaN is flagged separately
+      if (r[d] != r[d] || r[3 + d] != r[3 + d]) r[6] = fmax(r[6], 2.);
+    }
   }
 #pragma unroll
   for (int s = 0; s < 7; ++s) {

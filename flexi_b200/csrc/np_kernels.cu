@@ -302,7 +302,7 @@ cudaError_t surfint(bool gl, const SurfArgs& a, int nElems, cudaStream_t s) {
 }
 
 cudaError_t dt(const DtArgs& a, int nElems, cudaStream_t s) {
-  k_dt<NP><<<nElems, D::NP3, 0, s>>>(a);
+  k_dt<NP><<<nElems, dt_threads<NP>(), 0, s>>>(a);
   return cudaGetLastError();
 }
 

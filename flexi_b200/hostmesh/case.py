@@ -41,3 +41,56 @@ def tgv_box(nel, **kw):
 
 
 TGV_EQN = dict(kappa=1.4, R=71.42857, Pr=0.72, mu0=6.25e-4)  # regressioncheck/checks/tgv/split/parameter.ini
+
+
+# ---- BASELINE configs[3]: NACA0012-style synthetic curved mesh ----------------------------------------------------------------
+def naca_mapping(chord=1.0, thickness=0.12, r_far=8.0, stretch=3.0, span=1.0):
+    """Unit cube -> O-grid around a NACA0012-style section: xhat0 runs once around the section (clockwise, so that the frame
+    (around, radial, span) is right-handed), xhat1 from the wall (0) to the far-field circle (1), xhat2 along the span.
+    The section is the smooth teardrop x/c = (1 + cos(theta))/2, y/c = A sin(theta) (1 - 0.55 cos(theta)): 12 % thick with the
+    maximum at 31 % chord like the NACA 0012, but with a rounded trailing edge -- an O-grid around a sharp trailing edge has a
+    degenerate corner there (zero Jacobian on the Gauss-Lobatto node that sits on it)."""
+    c0 = (1.0 - np.sqrt(1.0 + 2.0 * 1.1 * 1.1)) / 2.2          # cos(theta) of the thickest station
+    amp = 0.5 * thickness / (np.sqrt(1.0 - c0 * c0) * (1.0 - 0.55 * c0))
+
+    def f(X):
+        th = -2.0 * np.pi * X[..., 0]
+        bx = chord * 0.5 * (1.0 + np.cos(th))
+        by = chord * amp * np.sin(th) * (1.0 - 0.55 * np.cos(th))
+        ox, oy = 0.5 * chord + r_far * np.cos(th), r_far * np.sin(th)
+        s = np.expm1(stretch * X[..., 1]) / np.expm1(stretch)
+        out = np.empty_like(X)
+        out[..., 0] = (1.0 - s) * bx + s * ox
+        out[..., 1] = (1.0 - s) * by + s * oy
+        out[..., 2] = span * X[..., 2]
+        return out
+    return f
+
+
+NACA_BC = {(1, -1): 1, (1, 1): 2}  # wall at xhat1 = 0, far field at xhat1 = 1; around the section and along the span: periodic
+# HLLC + BR2 (configs[3]); BC 1 = isothermal no-slip wall at the free-stream temperature, BC 2 = Dirichlet far field (RefState 1)
+NACA_EQN = dict(parabolic=True, lifting=2, riemann="hllc", mu0=2e-3, eta_br2=2.0, eta_br2_wall=3.0, cfl_scale=0.8, dfl_scale=0.8,
+                boundary_type=[(4, 1, 0), (2, 1, 0)], ref_state_prim=[(1.0, 0.3, 0.0, 0.0, 0.71428571)])
+
+
+def naca_spec(nel, ngeo=4, orient_seed=12, span_per_elem=0.1, **kw):
+    """O-mesh of nel = (around, radial, span) elements; every element in a random local frame (orient_seed) so that the side
+    connectivity carries all flips and local-side pairings of an unstructured HOPR mesh (mappings.f90:188-450)."""
+    return BoxSpec(nel, periodic=(True, False, True), bc_of_face=NACA_BC, ngeo=ngeo, orient_seed=orient_seed,
+                   mapping=naca_mapping(span=span_per_elem * nel[2], **kw))
+
+
+def naca_state(eqn, x, chord=1.0):
+    """Free stream that is ramped down towards the section (no impulsive start at the no-slip wall)."""
+    rs = eqn.ref_state_prim[0]
+    dx = np.maximum(np.maximum(x[..., 0] - chord, -x[..., 0]), 0.0)
+    d = np.sqrt(dx ** 2 + x[..., 1] ** 2)
+    ramp = np.tanh(4.0 * d / chord)
+    prim = np.zeros(x.shape[:-1] + (6,))
+    prim[..., 0] = rs[0]
+    prim[..., 1] = rs[1] * ramp
+    prim[..., 2] = rs[2] * ramp
+    prim[..., 3] = rs[3] * ramp
+    prim[..., 4] = rs[4]
+    prim[..., 5] = prim[..., 4] / (prim[..., 0] * eqn.R)
+    return eqn.prim_to_cons(prim)

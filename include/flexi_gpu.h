@@ -278,6 +278,14 @@ int flexi_gpu_set_overintegration(flexi_gpu_handle* h, int overintegrationType, 
  * operator evaluation, as the reference does.  3 (LAF) and multi-rank runs return FLEXI_GPU_ERR_UNSUPPORTED. */
 int flexi_gpu_set_filter(flexi_gpu_handle* h, int filterType, const double* FilterMat);
 
+/* Sponge(Ut) (sponge/sponge.f90:612-678; dg.f90:659-661): Ut = Ut - SpongeMat*(U - SpBaseFlow) on the nSpongeElems elements of
+ * SpongeMap (1-based element ids), between CalcSource and ApplyJacobian of every DG operator evaluation.  The host keeps InitSponge
+ * (ramp shapes, base-flow types, sponge.f90:97-400) and passes its results: SpongeMat(0:N,0:N,0:N,nSpongeElems) (already times the
+ * Jacobian), SpBaseFlow(PP_nVar,0:N,0:N,0:N,nElems).  nSpongeElems = 0 switches the sponge off.  Call again after the host changed
+ * the base flow (pressure-time-average base flow, sponge.f90:560-600). */
+int flexi_gpu_set_sponge(flexi_gpu_handle* h, int32_t nSpongeElems, const int32_t* SpongeMap, const double* SpongeMat,
+                         const double* SpBaseFlow);
+
 /* Page-lock a host array (cudaHostRegister) so that flexi_gpu_set_state / get_state / get_array move it at full PCIe speed and
  * asynchronously; the Fortran host calls this once for MOD_DG_Vars:U after allocation (dg.f90:94) and unpins before DEALLOCATE. */
 int flexi_gpu_pin_host_array(void* ptr, int64_t nbytes);

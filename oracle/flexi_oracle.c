@@ -56,6 +56,11 @@ typedef struct oracle {
   double* FilterMat;              /* (0:N,0:N) Fortran order, NULL = FilterType none; set by oracle_set_filter */
   double* OverintegrationMat;     /* (0:N,0:N) Fortran order, NULL = OverintegrationType 0; set by oracle_set_overintegration */
   double *Ja_Face, *Ja_slave;     /* (3,3,0:N,0:N,nSides), mesh_vars.f90:70-78; set by oracle_set_face_metrics */
+  /* sponge (sponge/sponge_vars.f90): SpongeMap(nSpongeElems) 1-based element ids, SpongeMat(0:N,0:N,0:N,nSpongeElems) pre-multiplied
+     by the Jacobian, SpBaseFlow(5,0:N,0:N,0:N,nElems); set by oracle_set_sponge */
+  int nSpongeElems;
+  int* SpongeMap;
+  double *SpongeMat, *SpBaseFlow;
   /* owned copies of descriptor arrays */
   void* owned[64];
   int n_owned;
@@ -1518,10 +1523,27 @@ static void filter_volume(const oracle* o, const double* Mat, double* U) {
   free(b2);
 }
 
+/* sponge.f90:612-678 Sponge(Ut): Ut = Ut - SpongeMat*(U - SpBaseFlow) on the sponge elements (DG elements; SpongeMat already
+   carries the Jacobian, so this happens in reference space, dg.f90:659-661) */
+static void sponge(oracle* o) {
+  const size_t np3 = (size_t)o->np * o->np * o->np;
+  for (int is = 0; is < o->nSpongeElems; ++is) {
+    const size_t e = (size_t)o->SpongeMap[is] - 1;
+    for (size_t n = 0; n < np3; ++n) {
+      const double sm = o->SpongeMat[(size_t)is * np3 + n];
+      for (int v = 0; v < NVAR; ++v) {
+        const size_t k = (e * np3 + n) * NVAR + v;
+        o->Ut[k] = o->Ut[k] - sm * (o->U[k] - o->SpBaseFlow[k]);
+      }
+    }
+  }
+}
+
 static void finish_ut(oracle* o, double t) {
   const size_t n = (size_t)o->d.nElems * o->np * o->np * o->np;
   for (size_t i = 0; i < n * NVAR; ++i) o->Ut[i] = -o->Ut[i];
   if (o->d.doCalcSource) calc_source(o, t);
+  if (o->nSpongeElems > 0) sponge(o);
   /* dg.f90:663-676: OVERINTEGRATIONTYPE_CUTOFF filters Ut before the Jacobian is applied (dg/overintegration.f90:162-187) */
   if (o->OverintegrationMat) filter_volume(o, o->OverintegrationMat, o->Ut);
   apply_jacobian(o, NVAR, o->Ut);
@@ -1996,6 +2018,26 @@ void oracle_set_face_metrics(oracle* o, const double* Ja_Face, const double* Ja_
   memcpy(o->Ja_slave, Ja_slave, n * 8);
 }
 
+/* InitSponge results (sponge.f90:97-400 stay on the host): nSpongeElems = 0 switches the sponge off */
+int oracle_set_sponge(oracle* o, int nSpongeElems, const int* SpongeMap, const double* SpongeMat, const double* SpBaseFlow) {
+  free(o->SpongeMap);
+  free(o->SpongeMat);
+  free(o->SpBaseFlow);
+  o->SpongeMap = NULL;
+  o->SpongeMat = o->SpBaseFlow = NULL;
+  o->nSpongeElems = 0;
+  if (nSpongeElems <= 0) return 0;
+  if (!SpongeMap || !SpongeMat || !SpBaseFlow || nSpongeElems > o->d.nElems) return -1;
+  const size_t np3 = (size_t)o->np * o->np * o->np;
+  o->SpongeMap = (int*)xcalloc((size_t)nSpongeElems, sizeof(int));
+  o->SpongeMat = (double*)xcalloc((size_t)nSpongeElems * np3, 8);
+  o->SpBaseFlow = (double*)xcalloc((size_t)o->d.nElems * np3 * NVAR, 8);
+  memcpy(o->SpongeMap, SpongeMap, (size_t)nSpongeElems * sizeof(int));
+  memcpy(o->SpongeMat, SpongeMat, (size_t)nSpongeElems * np3 * 8);
+  memcpy(o->SpBaseFlow, SpBaseFlow, (size_t)o->d.nElems * np3 * NVAR * 8);
+  o->nSpongeElems = nSpongeElems;
+  return 0;
+}
 /* OverintegrationType (dg/overintegration.f90:40-47): 0 none, 1 cutoff (OverintegrationMat = Vdm_Leg diag(1..1,0..0) sVdm_Leg,
    :104-116).  2 (conservative cutoff) is not restated. */
 int oracle_set_overintegration(oracle* o, int type, const double* Mat) {
@@ -2027,6 +2069,9 @@ void oracle_destroy(oracle* o) {
   if (!o) return;
   free(o->OverintegrationMat);
   free(o->FilterMat);
+  free(o->SpongeMap);
+  free(o->SpongeMat);
+  free(o->SpBaseFlow);
   for (int i = 0; i < o->n_owned; ++i) free(o->owned[i]);
   double* st[] = {o->U, o->Ut, o->Ut_tmp, o->UPrim, o->U_master, o->U_slave, o->UPrim_master, o->UPrim_slave, o->Flux_master,
                   o->Flux_slave, o->gradUx, o->gradUy, o->gradUz, o->gradUx_master, o->gradUy_master, o->gradUz_master,

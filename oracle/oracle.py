@@ -13,9 +13,8 @@ _LIBS = {}
 
 
 def build(force=False):
-    need = force or not all(os.path.exists(os.path.join(_HERE, n)) for n in ("liboracle.so", "liboracle_fast.so"))
-    if need:
-        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    # make decides by time stamps: a stale library after an edit of flexi_oracle.c is rebuilt
+    subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
 
 
 def _load(fast=False):
@@ -54,6 +53,8 @@ def _load(fast=False):
     lib.oracle_set_overintegration.argtypes = [P, C.c_int, PD]
     lib.oracle_filter.argtypes = [P, PD, PD]
     lib.oracle_set_filter.argtypes = [P, C.c_int, PD]
+    lib.oracle_set_sponge.argtypes = [P, C.c_int, C.POINTER(C.c_int32), PD, PD]
+    lib.oracle_set_sponge.restype = C.c_int
     lib.oracle_desc_bytes.restype = C.c_int
     _LIBS[name] = lib
     return lib
@@ -89,6 +90,18 @@ class OracleRank:
         m = None if mat is None else np.asfortranarray(mat, dtype=np.float64)
         rc = self.lib.oracle_set_overintegration(self.h, int(otype), None if m is None else _pd(m))
         assert rc == 0, "OverintegrationType not restated"
+
+    def set_sponge(self, sponge_map=None, sponge_mat=None, base_flow=None):
+        """Sponge(Ut) (sponge/sponge.f90:612-678): SpongeMap 1-based element ids [nSp], SpongeMat [nSp, k, j, i] (times the Jacobian),
+        SpBaseFlow [nElems, k, j, i, 5]; no arguments = off."""
+        if sponge_map is None:
+            assert self.lib.oracle_set_sponge(self.h, 0, None, None, None) == 0
+            return
+        mp = np.ascontiguousarray(sponge_map, dtype=np.int32)
+        sm = np.ascontiguousarray(sponge_mat, dtype=np.float64)
+        bf = np.ascontiguousarray(base_flow, dtype=np.float64)
+        rc = self.lib.oracle_set_sponge(self.h, len(mp), mp.ctypes.data_as(C.POINTER(C.c_int32)), _pd(sm), _pd(bf))
+        assert rc == 0, "sponge arrays rejected"
 
     def set_filter(self, ftype, mat=None):
         """FilterType 0 (none) / 1 (cutoff) / 2 (modal) and FilterMat[out, in]: U is filtered in place at the start of every

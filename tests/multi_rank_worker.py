@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from flexi_b200.hostmesh import basis as B  # noqa: E402
-from flexi_b200.hostmesh.case import build_case  # noqa: E402
+from flexi_b200.hostmesh.case import NACA_EQN, build_case, naca_spec, naca_state  # noqa: E402
 from flexi_b200.hostmesh.mesh import BoxSpec  # noqa: E402
 from oracle import oracle as O  # noqa: E402
 
@@ -38,6 +38,8 @@ CASES["splitG"] = (4, B.NODE_GAUSS, dict(parabolic=True, split_dg=True, split_dg
 CASES["splitCH"] = (5, B.NODE_GAUSS_LOBATTO, dict(parabolic=True, lifting=1, riemann="ch", mu0=1e-2, split_dg=True, split_dg_type="ch",
                                                   boundary_type=[(4, 2, 0), (9, 0, 0), (2, 1, 0)],
                                                   ref_state_prim=[(1.0, 0.3, 0.0, 0.0, 0.71428571), (1.0, 0.0, 0.0, 0.0, 0.9)]))
+# BASELINE configs[3] proper: NACA0012-style O-mesh, every element in a random local frame, N=5, HLLC + BR2, wall + far field
+CASES["naca"] = (5, B.NODE_GAUSS, NACA_EQN)
 CASES["config4_unstr"] = CASES["config4"]
 CASES["split_unstr"] = CASES["split"]
 WALL_BC = {(1, -1): 1, (1, 1): 2, (0, -1): 3, (0, 1): 3}  # walls in y, far field in x, periodic in z
@@ -54,7 +56,9 @@ def main():
         dist.init_process_group("gloo", rank=rank, world_size=world)
     N, node, eqn = CASES[case]
     oseed = 9 if case.endswith("_unstr") else None  # "_unstr": every element in a random local frame (all flips on MPI sides too)
-    if "boundary_type" in eqn:
+    if case == "naca":
+        spec = naca_spec((12, 3, 2))
+    elif "boundary_type" in eqn:
         spec = BoxSpec((4, 3, 2), periodic=(False, False, True), bc_of_face=WALL_BC, orient_seed=oseed, **CURVED)
     else:
         spec = BoxSpec((4, 3, 2), orient_seed=oseed, **CURVED)
@@ -86,7 +90,8 @@ def main():
     assert bytes(idt.numpy().tobytes()) == bytes(range(128))
 
     # ---- oracle world on this partition vs the single-rank oracle (partition invariance, SURVEY 8c identity 7) ----
-    U0s = [r.eqn.smooth_state(r.mesh.Elem_xGP, length=2.0) for r in ranks]
+    smooth = (lambda r: naca_state(r.eqn, r.mesh.Elem_xGP)) if case == "naca" else (lambda r: r.eqn.smooth_state(r.mesh.Elem_xGP, length=2.0))
+    U0s = [smooth(r) for r in ranks]
     w = O.OracleWorld([(r.desc, r.keep) for r in ranks])
     if gauss_split:
         for r, o in zip(ranks, w.ranks):
@@ -99,11 +104,13 @@ def main():
         w1 = O.OracleWorld([(one.desc, one.keep)])
         if gauss_split:
             w1.ranks[0].set_face_metrics(one.mesh.Ja_Face, one.mesh.Ja_slave)
-        w1.set_state([one.eqn.smooth_state(one.mesh.Elem_xGP, length=2.0)])
+        w1.set_state([smooth(one)])
         w1.dg_time_derivative(0.0)
         full = w1.ranks[0].array("Ut")
         for r, ow in zip(ranks, w.ranks):
-            assert np.max(np.abs(ow.array("Ut") - full[r.mesh.elem_gid])) < 1e-12 * np.max(np.abs(full))
+            # naca: 1/J varies over four decades (wall layer), the flux sums cancel to 1e-4 of their terms -> round-off 5e-11
+            ptol = 2e-11 if case == "naca" else 1e-12
+            assert np.max(np.abs(ow.array("Ut") - full[r.mesh.elem_gid])) < ptol * np.max(np.abs(full))
         w1.close()
 
     if mode == "gpu":
@@ -119,7 +126,9 @@ def main():
         g.set_state(U0s[rank])
         ut = g.DGTimeDerivative_weakForm(0.0)
         scale = np.max(np.abs(ut_ref).reshape(-1, 5), axis=0)
-        assert np.all(np.max(np.abs(ut - ut_ref).reshape(-1, 5), axis=0) <= 1e-12 * scale), "multi-rank Ut mismatch"
+        # gate: rel 1e-12, or 4x the oracle's own strict-vs-FMA build noise where that is larger (naca: 1/J spans four decades)
+        noise = O.ut_noise_floor([(r.desc, r.keep) for r in ranks], U0s)[0] if case == "naca" else 0.0
+        assert np.all(np.max(np.abs(ut - ut_ref).reshape(-1, 5), axis=0) <= np.maximum(1e-12 * scale, 4.0 * noise)), "multi-rank Ut mismatch"
         if eqn.get("parabolic"):
             # side arrays after a full DG operator call, incl. what arrives from the neighbour rank: gradU?_slave on MPI_MINE sides
             o = w.ranks[rank]
@@ -140,7 +149,8 @@ def main():
             t += dt_o
         Ug, Uo = g.get_state(), w.ranks[rank].array("U")
         sc = np.max(np.abs(Uo).reshape(-1, 5), axis=0)
-        assert np.all(np.max(np.abs(Ug - Uo).reshape(-1, 5), axis=0) <= 1e-12 * sc), "multi-rank state mismatch after 3 steps"
+        stol = 1e-10 if case == "naca" else 1e-12  # naca: round-off of Ut is amplified by 1/J of the wall layer (see ptol above)
+        assert np.all(np.max(np.abs(Ug - Uo).reshape(-1, 5), axis=0) <= stol * sc), "multi-rank state mismatch after 3 steps"
         if eqn.get("parabolic") and "boundary_type" not in eqn:
             # on-device TGV AnalyzeTestcase (steps 1-4) per rank + the host's reduction (steps 5-6) against the host analysis of
             # the oracle world: the integrals of the partitioned run

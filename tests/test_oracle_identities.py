@@ -345,3 +345,43 @@ def test_solution_filter_at_operator_start():
     assert np.isfinite(o.array("U")).all()
     o.set_filter(0)
     w.close()
+
+
+def _sponge_arrays(r, frac=0.4, seed=3):
+    """A synthetic sponge zone as InitSponge would hand it over (sponge.f90:97-400): the elements whose barycentre lies in the last
+    `frac` of the x range, a smooth ramp times the Jacobian as SpongeMat, a perturbed free stream as SpBaseFlow."""
+    m = r.mesh
+    xb = m.Elem_xGP[..., 0].reshape(m.nElems, -1).mean(axis=1)
+    x0, x1 = m.Elem_xGP[..., 0].min(), m.Elem_xGP[..., 0].max()
+    xs = x1 - frac * (x1 - x0)
+    smap = np.nonzero(xb > xs)[0].astype(np.int32) + 1
+    ramp = np.clip((m.Elem_xGP[smap - 1, ..., 0] - xs) / (x1 - xs), 0.0, 1.0)
+    smat = 5.0 * (6 * ramp ** 5 - 15 * ramp ** 4 + 10 * ramp ** 3) / m.sJ[smap - 1]  # damping*x_star, times the Jacobian 1/sJ
+    rng = np.random.default_rng(seed)
+    base = r.eqn.smooth_state(m.Elem_xGP, length=2.0, amp=0.05) * (1.0 + 0.01 * rng.standard_normal(m.Elem_xGP.shape[:-1] + (5,)))
+    return smap, smat, base
+
+
+def test_sponge_term():
+    """Sponge(Ut) (sponge.f90:612-678, dg.f90:659-661): Ut_with - Ut_without = -sJ * SpongeMat * (U - SpBaseFlow) on the sponge
+    elements (the term is added in reference space before ApplyJacobian) and nothing elsewhere; switching it off restores Ut."""
+    eqn = dict(parabolic=True, riemann="roe", mu0=1e-2)
+    ranks, w = world(BoxSpec((4, 2, 2), x0=(-1.0, -1.0, -1.0), length=(2.0, 2.0, 2.0), ngeo=2, deform=0.1), 4, B.NODE_GAUSS, eqn)
+    r, o = ranks[0], w.ranks[0]
+    U = r.eqn.smooth_state(r.mesh.Elem_xGP, length=2.0)
+    w.set_state([U])
+    w.dg_time_derivative(0.0)
+    plain = np.array(o.array("Ut"))
+    smap, smat, base = _sponge_arrays(r)
+    assert 0 < len(smap) < r.mesh.nElems
+    o.set_sponge(smap, smat, base)
+    w.dg_time_derivative(0.0)
+    ut = np.array(o.array("Ut"))
+    expect = np.zeros_like(plain)
+    expect[smap - 1] = -(r.mesh.sJ[smap - 1] * smat)[..., None] * (U[smap - 1] - base[smap - 1])
+    assert np.max(np.abs((ut - plain) - expect)) <= 1e-12 * np.max(np.abs(plain))
+    assert np.max(np.abs(expect)) > 1e-3 * np.max(np.abs(plain))
+    o.set_sponge()
+    w.dg_time_derivative(0.0)
+    assert np.array_equal(np.array(o.array("Ut")), plain)
+    w.close()

@@ -179,3 +179,58 @@ def test_solution_filter_matches_oracle(N, NF, node, eqn):
     finally:
         g.close()
         w.close()
+
+
+@pytest.mark.parametrize("N,node,eqn", [
+    (7, GL, dict(parabolic=True, split_dg=True, split_dg_type="pi", riemann="lf", mu0=1e-2)),
+    (4, G, dict(parabolic=True, riemann="roe", mu0=1e-2)),
+    (5, GL, dict(parabolic=False, riemann="hllc")),
+], ids=["N7-GL-split", "N4-G-weak", "N5-GL-euler"])
+def test_sponge_matches_oracle(N, node, eqn):
+    """Sponge(Ut) (flexi_gpu_set_sponge; sponge.f90:612-678, dg.f90:659-661) inside the update kernel: one operator evaluation (the
+    kernel has to fetch U itself there) and 2 LSERK steps on the curved mesh with a sponge zone over the last 40 % in x; also
+    together with the cut-off overintegration (the sponge term is filtered with Ut); switching it off restores the plain operator."""
+    from tests.test_oracle_identities import _sponge_arrays
+
+    r = build_case(BoxSpec((4, 2, 2), **CURVED), N, node, eqn)[0]
+    U0 = r.eqn.smooth_state(r.mesh.Elem_xGP, length=2.0)
+    smap, smat, base = _sponge_arrays(r)
+    w = O.OracleWorld([(r.desc, r.keep)])
+    o = w.ranks[0]
+    w.set_state([U0])
+    g = FlexiGpu(r)
+    try:
+        g.set_state(U0)
+        w.dg_time_derivative(0.0)
+        plain = np.array(o.array("Ut"))
+        o.set_sponge(smap, smat, base)
+        g.set_sponge(smap, smat, base)
+        w.dg_time_derivative(0.0)
+        ut, ref = g.DGTimeDerivative_weakForm(0.0), o.array("Ut")
+        scale = np.max(np.abs(ref).reshape(-1, 5), axis=0)
+        assert np.all(np.max(np.abs(ut - ref).reshape(-1, 5), axis=0) <= 1e-12 * scale)
+        assert np.max(np.abs(ref - plain)) > 1e-3 * np.max(np.abs(plain))
+        mat = B.overintegration_mat(r.basis.xGP, N - 2)
+        o.set_overintegration(1, mat)
+        g.set_overintegration(1, mat)
+        w.dg_time_derivative(0.0)
+        ut, ref = g.DGTimeDerivative_weakForm(0.0), o.array("Ut")
+        assert np.all(np.max(np.abs(ut - ref).reshape(-1, 5), axis=0) <= 1e-12 * np.max(np.abs(ref).reshape(-1, 5), axis=0))
+        o.set_overintegration(0)
+        g.set_overintegration(0)
+        t = 0.0
+        for _ in range(2):
+            dt = w.calc_timestep()[0]
+            w.timestep(t, dt)
+            g.TimeStep(t, dt)
+            t += dt
+        Ug, Uo = g.get_state(), o.array("U")
+        sc = np.max(np.abs(Uo).reshape(-1, 5), axis=0)
+        assert np.all(np.max(np.abs(Ug - Uo).reshape(-1, 5), axis=0) <= 1e-12 * sc)
+        g.set_sponge()
+        g.set_state(U0)
+        ut0 = g.DGTimeDerivative_weakForm(0.0)
+        assert np.all(np.max(np.abs(ut0 - plain).reshape(-1, 5), axis=0) <= 1e-12 * np.max(np.abs(plain).reshape(-1, 5), axis=0))
+    finally:
+        g.close()
+        w.close()
