@@ -111,8 +111,9 @@ __global__ void k_tgv_analyze(TgvArgs A) {
       acc[TGV_DR_S] += w * sumS;
       acc[TGV_DR_SD] += w * sumSd;
       acc[TGV_DR_P] += w * P[PRES] * divU;
-      acc[TGV_ED_S] += w * q.mu0 * oo;  // VISCOSITY_TEMPERATURE = mu0 for PP_VISC=0 (eos.h:73-79)
-      acc[TGV_ED_D] += w * q.mu0 * divU * divU;
+      const double muT = viscosity(q, P[TEMP]);  // VISCOSITY_TEMPERATURE(UPrim(TEMP)), testcase.f90:406-408
+      acc[TGV_ED_S] += w * muT * oo;
+      acc[TGV_ED_D] += w * muT * divU * divU;
     }
     __syncthreads();  // the next slab overwrites sT1 / sT2
   }
@@ -260,7 +261,7 @@ __global__ void k_body_forces(BodyForceArgs A) {
       double G[3][3];                        // GradV(c,d) = d v_c / d x_d
       for (int d = 0; d < 3; ++d)
         for (int c = 0; c < 3; ++c) G[c][d] = A.gm[d][((size_t)s * A.nvl + v0 + c) * np2 + pq];
-      const double muS = A.q.mu0, divV = G[0][0] + G[1][1] + G[2][2];
+      const double muS = viscosity(A.q, P[TEMP]), divV = G[0][0] + G[1][1] + G[2][2];
       double tau[3][3];
       for (int a = 0; a < 3; ++a)
         for (int b = 0; b < 3; ++b) tau[a][b] = muS * (G[a][b] + G[b][a]);

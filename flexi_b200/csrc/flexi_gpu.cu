@@ -612,6 +612,9 @@ static int init_impl(const flexi_gpu_desc* d, H* h) {
   q.mu0 = d->mu0;
   const double cp = d->R * d->kappa / (d->kappa - 1.);  // eos.f90:136-163
   q.lambda = d->mu0 * cp / d->Pr;
+  q.cp = cp;
+  q.Pr = d->Pr;
+  q.visc = 0;  // PP_VISC = 0 until flexi_gpu_set_viscosity says otherwise
   q.riemann = d->riemann;
   q.splitDG = d->splitDG;
   q.splitType = d->splitDGType;
@@ -1279,6 +1282,19 @@ int flexi_gpu_set_filter(flexi_gpu_handle* h, int filterType, const double* Filt
   if (!h->filtUMat) CKR(dalloc(h, &h->filtUMat, m.size()));
   CK(cudaMemcpy(h->filtUMat, m.data(), m.size() * 8, cudaMemcpyHostToDevice));
   h->filtUOn = true;
+  return 0;
+}
+
+int flexi_gpu_set_viscosity(flexi_gpu_handle* h, int32_t viscType, double Ts, double Tref, double ExpoSuth, double cSuth) {
+  ENTER(h);
+  if (viscType < 0 || viscType > 2) return fail(FLEXI_GPU_ERR_ARG, "PP_VISC %d (0 = constant, 1 = Sutherland, 2 = power law)", viscType);
+  if (viscType != 0 && !h->para) return fail(FLEXI_GPU_ERR_ARG, "no viscosity law without parabolic terms");
+  if (viscType == 1 && !(Ts > 0. && Tref > 0. && cSuth > 0.)) return fail(FLEXI_GPU_ERR_ARG, "Sutherland: Ts, Tref, cSuth must be positive");
+  h->q.visc = viscType;
+  h->q.Ts = Ts;
+  h->q.Tref = Tref;
+  h->q.expoSuth = ExpoSuth;
+  h->q.cSuth = cSuth;
   return 0;
 }
 

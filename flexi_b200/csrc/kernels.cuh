@@ -467,7 +467,7 @@ __global__ void __launch_bounds__(Dim<NP>::NP3) k_volume(VolArgs A) {
     double F[5], G[5], H[5];
     {
       double fv[4], gv[4], hv[4];
-      eval_diff_flux3d(q, P[VEL1], P[VEL2], P[VEL3], gx + LV, gy + LV, gz + LV, fv, gv, hv);
+      eval_diff_flux3d(q, P[TEMP], P[VEL1], P[VEL2], P[VEL3], gx + LV, gy + LV, gz + LV, fv, gv, hv);
       // eval_diff_flux3d reads g?[0..2] = velocity gradients and g?[3] = temperature gradient: lifting sets keep T right
       // behind the velocities (eos.h:118,127), so the same pointer offset serves both.
       double fa[5] = {0., fv[0], fv[1], fv[2], fv[3]}, ga[5] = {0., gv[0], gv[1], gv[2], gv[3]},
@@ -587,8 +587,8 @@ __global__ void __launch_bounds__(128) k_flux(FluxArgs A) {
         gR[d][c] = A.gs[d][((size_t)s * nvl + o + c) * D::NP2 + pq];
       }
     double fL[4], gLf[4], hL[4], fR[4], gRf[4], hR[4];
-    eval_diff_flux3d(q, PL[VEL1], PL[VEL2], PL[VEL3], gL[0], gL[1], gL[2], fL, gLf, hL);
-    eval_diff_flux3d(q, PR[VEL1], PR[VEL2], PR[VEL3], gR[0], gR[1], gR[2], fR, gRf, hR);
+    eval_diff_flux3d(q, PL[TEMP], PL[VEL1], PL[VEL2], PL[VEL3], gL[0], gL[1], gL[2], fL, gLf, hL);
+    eval_diff_flux3d(q, PR[TEMP], PR[VEL1], PR[VEL2], PR[VEL3], gR[0], gR[1], gR[2], fR, gRf, hR);
 #pragma unroll
     for (int c = 0; c < 4; ++c) F[c + 1] = F[c + 1] + 0.5 * (nv[0] * (fL[c] + fR[c]) + nv[1] * (gLf[c] + gRf[c]) + nv[2] * (hL[c] + hR[c]));
   }
@@ -695,8 +695,8 @@ __global__ void __launch_bounds__(128) k_flux_bc(BCArgs A) {
     riemann_point(q, A.bc.riemannBC, Ucm, Ucb, Pm, Pb, nv, t1, t2, F);
     if (A.parabolic) {
       double fL[4], gL[4], hL[4], fR[4], gR[4], hR[4];
-      eval_diff_flux3d(q, Pm[VEL1], Pm[VEL2], Pm[VEL3], gx, gy, gz, fL, gL, hL);
-      eval_diff_flux3d(q, Pb[VEL1], Pb[VEL2], Pb[VEL3], gx, gy, gz, fR, gR, hR);
+      eval_diff_flux3d(q, Pm[TEMP], Pm[VEL1], Pm[VEL2], Pm[VEL3], gx, gy, gz, fL, gL, hL);
+      eval_diff_flux3d(q, Pb[TEMP], Pb[VEL1], Pb[VEL2], Pb[VEL3], gx, gy, gz, fR, gR, hR);
 #pragma unroll
       for (int c = 0; c < 4; ++c) F[c + 1] = F[c + 1] + 0.5 * (nv[0] * (fL[c] + fR[c]) + nv[1] * (gL[c] + gR[c]) + nv[2] * (hL[c] + hR[c]));
     }
@@ -719,7 +719,7 @@ __global__ void __launch_bounds__(128) k_flux_bc(BCArgs A) {
         }
       }
       double f[4], g[4], h[4];
-      eval_diff_flux3d(q, Pb[VEL1], Pb[VEL2], Pb[VEL3], gx, gy, gz, f, g, h);
+      eval_diff_flux3d(q, Pb[TEMP], Pb[VEL1], Pb[VEL2], Pb[VEL3], gx, gy, gz, f, g, h);
       if (type == 3) f[3] = g[3] = h[3] = 0.;  // adiabatic wall: no energy flux
 #pragma unroll
       for (int c = 0; c < 4; ++c) F[c + 1] = F[c + 1] + nv[0] * f[c] + nv[1] * g[c] + nv[2] * h[c];
@@ -738,7 +738,9 @@ __global__ void __launch_bounds__(128) k_flux_bc(BCArgs A) {
 // FILT: OVERINTEGRATIONTYPE_CUTOFF (dg.f90:663-676, dg/overintegration.f90:162-187): Ut is filtered with OverintegrationMat along
 // xi, eta, zeta (filter.f90:264-288 -> ChangeBasis3D) between the source term and ApplyJacobian, in the shared planes that
 // later stage the new state.  A separate instantiation: the unfiltered kernels are not touched by it.
-template <int NP, bool GL, bool ENT = false, bool FILT = false>
+// SPONGE: Sponge(Ut) between the source term and ApplyJacobian (sponge.f90:612-678).  A separate instantiation as well: with
+// the sponge code in the plain kernel its register count crossed 64 and the kernel lost half its resident warps (+32 % time).
+template <int NP, bool GL, bool ENT = false, bool FILT = false, bool SPONGE = false>
 __global__ void __launch_bounds__(Dim<NP>::NP3) k_update(UpdArgs A) {
   using D = Dim<NP>;
   extern __shared__ double sm[];
@@ -764,8 +766,8 @@ __global__ void __launch_bounds__(Dim<NP>::NP3) k_update(UpdArgs A) {
   }
   // Sponge(Ut) (sponge.f90:612-678, called between CalcSource and ApplyJacobian, dg.f90:659-661): SpongeMat*(U - SpBaseFlow)
   double sp[5] = {0., 0., 0., 0., 0.};
-  const int iSp = A.spIdx ? A.spIdx[e] : -1;
-  if (iSp >= 0) {
+  const int iSp = SPONGE ? A.spIdx[e] : -1;
+  if (SPONGE && iSp >= 0) {
     const double smat = A.spMat[(size_t)iSp * D::NP3 + n];
 #pragma unroll
     for (int v = 0; v < 5; ++v) {
@@ -813,7 +815,7 @@ __global__ void __launch_bounds__(Dim<NP>::NP3) k_update(UpdArgs A) {
 #pragma unroll
       for (int v = 0; v < 5; ++v) w[v] = w[v] + src[v] / sJ;
     }
-    if (iSp >= 0) {
+    if (SPONGE && iSp >= 0) {
 #pragma unroll
       for (int v = 0; v < 5; ++v) w[v] = w[v] - sp[v];
     }
@@ -847,8 +849,8 @@ __global__ void __launch_bounds__(Dim<NP>::NP3) k_update(UpdArgs A) {
     src[1] = src[2] = src[3] = A.srcTmp[1] * cosX + A.srcTmp[2] * sinX2;
     src[4] = A.srcTmp[3] * cosX + A.srcTmp[4] * sinX2 + A.srcTmp[5] * sinX;
 #pragma unroll
-    for (int v = 0; v < 5; ++v) ut[v] = (((-ut[v]) + src[v] / sJ) - sp[v]) * sJ;
-  } else if (iSp >= 0) {
+    for (int v = 0; v < 5; ++v) ut[v] = SPONGE ? (((-ut[v]) + src[v] / sJ) - sp[v]) * sJ : ((-ut[v]) + src[v] / sJ) * sJ;
+  } else if (SPONGE && iSp >= 0) {
 #pragma unroll
     for (int v = 0; v < 5; ++v) ut[v] = ((-ut[v]) - sp[v]) * sJ;
   } else {
@@ -1085,7 +1087,7 @@ __global__ void __launch_bounds__(dt_threads<NP>()) k_dt(DtArgs A) {
       const double metAdv = sJ * sqrt(m0 * m0 + m1 * m1 + m2 * m2);                                                   // MetricsAdv
       const double metVisc = A.KappasPr_max * ((m0 * sJ) * (m0 * sJ) + (m1 * sJ) * (m1 * sJ) + (m2 * sJ) * (m2 * sJ));  // MetricsVisc
       r[d] = fabs(m0 * vs[0] + m1 * vs[1] + m2 * vs[2]) + c * metAdv;
-      r[3 + d] = A.parabolic ? q.mu0 * srho * metVisc : 0.;
+      r[3 + d] = A.parabolic ? viscosity(q, P[TEMP]) * srho * metVisc : 0.;
       // Fortran MAX may or may not propagate a NaN operand; NaN is flagged separately
       if (r[d] != r[d] || r[3 + d] != r[3 + d]) r[6] = fmax(r[6], 2.);
     }

@@ -179,12 +179,13 @@ cudaError_t setup() {
     FX_SPLIT_TYPES(X)
 #undef X
   }
-  if ((e = cudaFuncSetAttribute(k_update<NP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(k_update<NP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(k_update<NP, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(k_update<NP, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(k_update<NP, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(k_update<NP, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem)) != cudaSuccess) return e;
+#define X(GLv, ENTv, FILTv, SPv) \
+  if ((e = cudaFuncSetAttribute(k_update<NP, GLv, ENTv, FILTv, SPv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem)) != cudaSuccess) return e;
+  X(true, false, false, false) X(false, false, false, false) X(false, true, false, false)
+  X(true, false, true, false) X(false, false, true, false) X(false, true, true, false)
+  X(true, false, false, true) X(false, false, false, true) X(false, true, false, true)
+  X(true, false, true, true) X(false, false, true, true) X(false, true, true, true)
+#undef X
   if ((e = cudaFuncSetAttribute(k_surfcorr<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (D::NBASIS + 5 * D::NP3)))) != cudaSuccess) return e;
   const int pro = (int)(sizeof(double) * (D::NBASIS + 6 * D::NP3));
   if ((e = cudaFuncSetAttribute(k_prolong<NP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pro)) != cudaSuccess) return e;
@@ -266,24 +267,22 @@ cudaError_t flux(const FluxArgs& a, cudaStream_t s) {
   return cudaGetLastError();
 }
 
+template <bool GL, bool ENT, bool FILT, bool SPONGE>
+cudaError_t update_launch(const UpdArgs& a, int nBlocks, cudaStream_t s) {
+  k_update<NP, GL, ENT, FILT, SPONGE><<<nBlocks, D::NP3, upd_smem, s>>>(a);
+  return cudaGetLastError();
+}
+template <bool FILT, bool SPONGE>
+cudaError_t update_nodes(bool gl, const UpdArgs& a, int nBlocks, cudaStream_t s) {
+  if (gl) return update_launch<true, false, FILT, SPONGE>(a, nBlocks, s);
+  if (a.entropy) return update_launch<false, true, FILT, SPONGE>(a, nBlocks, s);
+  return update_launch<false, false, FILT, SPONGE>(a, nBlocks, s);
+}
 cudaError_t update(bool gl, const UpdArgs& a, int nBlocks, cudaStream_t s) {
   if (nBlocks <= 0) return cudaSuccess;
-  if (a.filt) {  // OverintegrationType = cutoff
-    if (gl)
-      k_update<NP, true, false, true><<<nBlocks, D::NP3, upd_smem, s>>>(a);
-    else if (a.entropy)
-      k_update<NP, false, true, true><<<nBlocks, D::NP3, upd_smem, s>>>(a);
-    else
-      k_update<NP, false, false, true><<<nBlocks, D::NP3, upd_smem, s>>>(a);
-    return cudaGetLastError();
-  }
-  if (gl)
-    k_update<NP, true><<<nBlocks, D::NP3, upd_smem, s>>>(a);
-  else if (a.entropy)
-    k_update<NP, false, true><<<nBlocks, D::NP3, upd_smem, s>>>(a);
-  else
-    k_update<NP, false><<<nBlocks, D::NP3, upd_smem, s>>>(a);
-  return cudaGetLastError();
+  const bool filt = a.filt != nullptr, sponge = a.spIdx != nullptr;  // OverintegrationType = cutoff; doSponge
+  if (filt) return sponge ? update_nodes<true, true>(gl, a, nBlocks, s) : update_nodes<true, false>(gl, a, nBlocks, s);
+  return sponge ? update_nodes<false, true>(gl, a, nBlocks, s) : update_nodes<false, false>(gl, a, nBlocks, s);
 }
 
 cudaError_t surfcorr(const SurfCorrArgs& a, int nBlocks, cudaStream_t s) {

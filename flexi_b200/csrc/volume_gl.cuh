@@ -408,7 +408,7 @@ __global__ void __launch_bounds__(VolGLCfg<NP, KPT, SPLIT, PARA>::NT, VolGLCfg<N
         }
         // ---- viscous flux of this node (flux.f90:149-241) ----
         double fv[4], gv[4], hv[4];
-        eval_diff_flux3d(q, Pn[c][VEL1], Pn[c][VEL2], Pn[c][VEL3], gx + LV, gy + LV, gz + LV, fv, gv, hv);
+        eval_diff_flux3d(q, Pn[c][TEMP], Pn[c][VEL1], Pn[c][VEL2], Pn[c][VEL3], gx + LV, gy + LV, gz + LV, fv, gv, hv);
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
           F[v + 1] = fv[v];

@@ -601,8 +601,9 @@ __global__ void __launch_bounds__(VolGL2Cfg<NP, PARA, NVC>::NT, VolGL2Cfg<NP, PA
         }
         // ---- viscous flux of this node (flux.f90:149-241) ----
         const double v1 = sP[VEL1 * PL + s], v2 = sP[VEL2 * PL + s], v3 = sP[VEL3 * PL + s];
+        const double Tn = (q.visc != 0) ? sP[TEMP * PL + s] : 0.;  // the T plane is intact until S3; read for PP_VISC != 0 only
         double fv[4], gv[4], hv[4];
-        eval_diff_flux3d(q, v1, v2, v3, gx + LV, gy + LV, gz + LV, fv, gv, hv);
+        eval_diff_flux3d(q, Tn, v1, v2, v3, gx + LV, gy + LV, gz + LV, fv, gv, hv);
         // ---- what the side kernel needs from this element.  ViscousFlux_Side (riemann.f90:448-498) forms
         //      0.5*n.(F_v(U_L,gradU_L) + F_v(U_R,gradU_R)); each half depends on one element only, and on LGL nodes the face
         //      state and (BR1) the face gradient are copies of the boundary node's (prolongtoface.t90:270-303), so the element
@@ -623,7 +624,7 @@ __global__ void __launch_bounds__(VolGL2Cfg<NP, PARA, NVC>::NT, VolGL2Cfg<NP, PA
               gfz[v] = gzo[v] + w * (sJc * (f[v] * nv[2]));
             }
             double ff[4], gf[4], hf[4];
-            eval_diff_flux3d(q, v1, v2, v3, gfx + LV, gfy + LV, gfz + LV, ff, gf, hf);
+            eval_diff_flux3d(q, Tn, v1, v2, v3, gfx + LV, gfy + LV, gfz + LV, ff, gf, hf);
 #pragma unroll
             for (int v = 0; v < 4; ++v) nf[v] = nv[0] * ff[v] + nv[1] * gf[v] + nv[2] * hf[v];
           } else {

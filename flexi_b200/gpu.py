@@ -31,7 +31,7 @@ KERNEL_CLASSES = ("volume", "flux", "update", "prolong", "calc_timestep", "layou
 EXPORTS = ("flexi_gpu_last_error", "flexi_gpu_abi_version", "flexi_gpu_nccl_unique_id", "flexi_gpu_init", "flexi_gpu_finalize",
            "flexi_gpu_set_state", "flexi_gpu_get_state", "flexi_gpu_dg_time_derivative", "flexi_gpu_timestep",
            "flexi_gpu_timestep_n", "flexi_gpu_calc_timestep", "flexi_gpu_get_array", "flexi_gpu_keep_gradients",
-           "flexi_gpu_prolong_to_face", "flexi_gpu_surf_int", "flexi_gpu_analyze_tgv", "flexi_gpu_calc_error_norms", "flexi_gpu_calc_body_forces", "flexi_gpu_set_face_metrics", "flexi_gpu_set_overintegration", "flexi_gpu_set_filter", "flexi_gpu_set_sponge", "flexi_gpu_pin_host_array", "flexi_gpu_unpin_host_array", "flexi_gpu_counters", "flexi_gpu_kernel_times",
+           "flexi_gpu_prolong_to_face", "flexi_gpu_surf_int", "flexi_gpu_analyze_tgv", "flexi_gpu_calc_error_norms", "flexi_gpu_calc_body_forces", "flexi_gpu_set_face_metrics", "flexi_gpu_set_overintegration", "flexi_gpu_set_filter", "flexi_gpu_set_sponge", "flexi_gpu_set_viscosity", "flexi_gpu_pin_host_array", "flexi_gpu_unpin_host_array", "flexi_gpu_counters", "flexi_gpu_kernel_times",
            "flexi_gpu_set_profiling", "flexi_gpu_synchronize", "flexi_gpu_stream")
 
 
@@ -77,6 +77,7 @@ def lib():
     L.flexi_gpu_set_overintegration.argtypes = [P, C.c_int, PD]
     L.flexi_gpu_set_filter.argtypes = [P, C.c_int, PD]
     L.flexi_gpu_set_sponge.argtypes = [P, I32, C.POINTER(C.c_int32), PD, PD]
+    L.flexi_gpu_set_viscosity.argtypes = [P, I32, C.c_double, C.c_double, C.c_double, C.c_double]
     L.flexi_gpu_pin_host_array.argtypes = [P, C.c_int64]
     L.flexi_gpu_unpin_host_array.argtypes = [P]
     L.flexi_gpu_counters.argtypes = [P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
@@ -204,6 +205,10 @@ class FlexiGpu:
         """FilterType (0 none, 1 cutoff, 2 modal) and FilterMat[out, in]; U is filtered at the start of every DG operator call."""
         m = None if mat is None else np.asfortranarray(mat, dtype=np.float64)
         self._ck(self.L.flexi_gpu_set_filter(self.h, int(ftype), None if m is None else _pd(m)))
+
+    def set_viscosity(self, visc_type=0, Ts=0.0, Tref=1.0, ExpoSuth=0.0, cSuth=0.0):
+        """PP_VISC (0 constant, 1 Sutherland, 2 power law) with the MOD_EOS_Vars values after InitEos (see sutherland_params)."""
+        self._ck(self.L.flexi_gpu_set_viscosity(self.h, int(visc_type), float(Ts), float(Tref), float(ExpoSuth), float(cSuth)))
 
     def set_sponge(self, sponge_map=None, sponge_mat=None, base_flow=None):
         """Sponge(Ut) (sponge.f90:612-678): SpongeMap 1-based element ids [nSp], SpongeMat [nSp, k, j, i] (times the Jacobian),

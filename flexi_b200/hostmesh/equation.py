@@ -187,3 +187,12 @@ class Equation:
         prim[..., 4] = 1.0 + amp * np.cos(X) * np.sin(2 * Y + 0.4) * np.cos(Z)
         prim[..., 5] = prim[..., 4] / (prim[..., 0] * self.R)
         return self.prim_to_cons(prim)
+
+
+def sutherland_params(Ts_ini=110.4, Tref_ini=273.15, expo=1.5):
+    """InitEos for PP_VISC = 1 (eos.f90:170-178): returns the module values (Ts, Tref, ExpoSuth, cSuth) with Tref = 1/Tref_ini and
+    Ts = Ts_ini/Tref_ini, as flexi_gpu_set_viscosity / oracle.set_viscosity expect them."""
+    Tref = 1.0 / Tref_ini
+    Ts = Ts_ini * Tref
+    cSuth = Ts ** expo * (1 + Ts) / (2 * Ts * Ts)
+    return dict(Ts=Ts, Tref=Tref, ExpoSuth=expo, cSuth=cSuth)

@@ -278,6 +278,13 @@ int flexi_gpu_set_overintegration(flexi_gpu_handle* h, int overintegrationType, 
  * operator evaluation, as the reference does.  3 (LAF) and multi-rank runs return FLEXI_GPU_ERR_UNSUPPORTED. */
 int flexi_gpu_set_filter(flexi_gpu_handle* h, int filterType, const double* FilterMat);
 
+/* Viscosity law, the reference's build option FLEXI_VISCOSITY / PP_VISC (eos.h:73-87, viscosity.f90:57-90): 0 = constant mu0
+ * (default), 1 = Sutherland, 2 = power law.  Pass the MOD_EOS_Vars values as InitEos leaves them (eos.f90:160-192): for Sutherland
+ * Tref = 1/Tref_ini, Ts = Ts_ini/Tref_ini, cSuth = Ts**ExpoSuth*(1+Ts)/(2*Ts*Ts); for the power law mu0 of the descriptor is already
+ * mu0_ini/Tref**ExpoSuth and only ExpoSuth is read.  Used by EvalDiffFlux3D (volume, sides, boundary sides), CalcTimeStep, the TGV
+ * analysis and CalcBodyForces.  Call once after flexi_gpu_init. */
+int flexi_gpu_set_viscosity(flexi_gpu_handle* h, int32_t viscType, double Ts, double Tref, double ExpoSuth, double cSuth);
+
 /* Sponge(Ut) (sponge/sponge.f90:612-678; dg.f90:659-661): Ut = Ut - SpongeMat*(U - SpBaseFlow) on the nSpongeElems elements of
  * SpongeMap (1-based element ids), between CalcSource and ApplyJacobian of every DG operator evaluation.  The host keeps InitSponge
  * (ramp shapes, base-flow types, sponge.f90:97-400) and passes its results: SpongeMat(0:N,0:N,0:N,nSpongeElems) (already times the

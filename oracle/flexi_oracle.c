@@ -58,6 +58,9 @@ typedef struct oracle {
   double *Ja_Face, *Ja_slave;     /* (3,3,0:N,0:N,nSides), mesh_vars.f90:70-78; set by oracle_set_face_metrics */
   /* sponge (sponge/sponge_vars.f90): SpongeMap(nSpongeElems) 1-based element ids, SpongeMat(0:N,0:N,0:N,nSpongeElems) pre-multiplied
      by the Jacobian, SpBaseFlow(5,0:N,0:N,0:N,nElems); set by oracle_set_sponge */
+  /* PP_VISC (eos.h:73-87): 0 constant, 1 Sutherland, 2 power law; MOD_EOS_Vars values after InitEos; set by oracle_set_viscosity */
+  int visc;
+  double Tref, Ts, ExpoSuth, cSuth;
   int nSpongeElems;
   int* SpongeMap;
   double *SpongeMat, *SpBaseFlow;
@@ -139,12 +142,23 @@ static inline void eval_flux3d(const double* U, const double* P, double* f, doub
   h[ENER] = Ep * P[VEL3];
 }
 
-/* flux.f90:149-241 EvalDiffFlux3D_Point (PP_VISC=0: mu = mu0; lambda = mu*cp/Pr, eos.h:46) */
+/* VISCOSITY_PRIM / VISCOSITY_TEMPERATURE (eos.h:73-87): mu0, muSuth(T) (viscosity.f90:57-90) or mu0*T**ExpoSuth */
+static inline double viscosity_T(const oracle* o, double T) {
+  if (o->visc == 1) {
+    const double TnoDim = T * o->Tref; /* Tref = 1/Tref ! */
+    if (TnoDim >= o->Ts) return o->d.mu0 * pow(TnoDim, o->ExpoSuth) * (1 + o->Ts) / (TnoDim + o->Ts); /* Ts = Ts/Tref ! */
+    return o->d.mu0 * TnoDim * o->cSuth;
+  }
+  if (o->visc == 2) return o->d.mu0 * pow(T, o->ExpoSuth);
+  return o->d.mu0;
+}
+
+/* flux.f90:149-241 EvalDiffFlux3D_Point (mu = VISCOSITY_PRIM(UPrim); lambda = mu*cp/Pr, eos.h:46) */
 static inline void eval_diff_flux3d(const oracle* o, const double* P, const double* gx, const double* gy, const double* gz,
                                     double* f, double* g, double* h) {
   const double s23 = 2. / 3., s43 = 4. / 3.;
   const int V1 = o->lv_vel1, V2 = V1 + 1, V3 = V1 + 2, T = o->lv_temp;
-  double muS = o->d.mu0;
+  double muS = viscosity_T(o, P[TEMP]);
   double lambda = muS * o->cp / o->d.Pr;
   double v1 = P[VEL1], v2 = P[VEL2], v3 = P[VEL3];
   double tau_xx = muS * (s43 * gx[V1] - s23 * gy[V2] - s23 * gz[V3]);
@@ -1866,7 +1880,7 @@ static void calc_timestep_rank(oracle* o, double* TimeStep3) {
       for (int dd = 0; dd < 3; ++dd)
         Max_Lambda[dd] = fmax(Max_Lambda[dd], fabs(M[dd][0] * vsJ[0] + M[dd][1] * vsJ[1] + M[dd][2] * vsJ[2]) + c * o->MetricsAdv[3 * i + dd]);
       if (o->d.parabolic) {
-        double mu = o->d.mu0;
+        double mu = viscosity_T(o, UE[EXT_TEMP]);
         for (int dd = 0; dd < 3; ++dd) Max_Lambda_v[dd] = fmax(Max_Lambda_v[dd], mu * UE[EXT_SRHO] * o->MetricsVisc[3 * i + dd]);
       }
     }
@@ -2018,6 +2032,17 @@ void oracle_set_face_metrics(oracle* o, const double* Ja_Face, const double* Ja_
   memcpy(o->Ja_slave, Ja_slave, n * 8);
 }
 
+/* PP_VISC and the MOD_EOS_Vars values InitEos leaves (eos.f90:160-192): Sutherland: Tref = 1/Tref_ini, Ts = Ts_ini/Tref_ini,
+   cSuth = Ts**ExpoSuth*(1+Ts)/(2*Ts*Ts); power law: mu0 (descriptor) already divided by Tref**ExpoSuth */
+int oracle_set_viscosity(oracle* o, int type, double Ts, double Tref, double ExpoSuth, double cSuth) {
+  if (type < 0 || type > 2) return -1;
+  o->visc = type;
+  o->Ts = Ts;
+  o->Tref = Tref;
+  o->ExpoSuth = ExpoSuth;
+  o->cSuth = cSuth;
+  return 0;
+}
 /* InitSponge results (sponge.f90:97-400 stay on the host): nSpongeElems = 0 switches the sponge off */
 int oracle_set_sponge(oracle* o, int nSpongeElems, const int* SpongeMap, const double* SpongeMat, const double* SpBaseFlow) {
   free(o->SpongeMap);

@@ -53,6 +53,8 @@ def _load(fast=False):
     lib.oracle_set_overintegration.argtypes = [P, C.c_int, PD]
     lib.oracle_filter.argtypes = [P, PD, PD]
     lib.oracle_set_filter.argtypes = [P, C.c_int, PD]
+    lib.oracle_set_viscosity.argtypes = [P, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double]
+    lib.oracle_set_viscosity.restype = C.c_int
     lib.oracle_set_sponge.argtypes = [P, C.c_int, C.POINTER(C.c_int32), PD, PD]
     lib.oracle_set_sponge.restype = C.c_int
     lib.oracle_desc_bytes.restype = C.c_int
@@ -90,6 +92,10 @@ class OracleRank:
         m = None if mat is None else np.asfortranarray(mat, dtype=np.float64)
         rc = self.lib.oracle_set_overintegration(self.h, int(otype), None if m is None else _pd(m))
         assert rc == 0, "OverintegrationType not restated"
+
+    def set_viscosity(self, visc_type=0, Ts=0.0, Tref=1.0, ExpoSuth=0.0, cSuth=0.0):
+        """PP_VISC 0/1/2 with the MOD_EOS_Vars values after InitEos (eos.f90:160-192)."""
+        assert self.lib.oracle_set_viscosity(self.h, int(visc_type), float(Ts), float(Tref), float(ExpoSuth), float(cSuth)) == 0
 
     def set_sponge(self, sponge_map=None, sponge_mat=None, base_flow=None):
         """Sponge(Ut) (sponge/sponge.f90:612-678): SpongeMap 1-based element ids [nSp], SpongeMat [nSp, k, j, i] (times the Jacobian),

@@ -48,7 +48,7 @@ int hp_eval_diff_flux3d(double kappa, double R, double mu0, double Pr, const dou
   q.mu0 = mu0;
   const double cp = R * kappa / (kappa - 1.);  // eos.f90:160-163
   q.lambda = mu0 * cp / Pr;
-  fx::eval_diff_flux3d(q, prim[1], prim[2], prim[3], gx, gy, gz, f, g, h);
+  fx::eval_diff_flux3d(q, prim[5], prim[1], prim[2], prim[3], gx, gy, gz, f, g, h);
   return 0;
 }
 int hp_prim_to_entropy(double kappa, double R, const double* prim, double* w) {

@@ -4,7 +4,7 @@ import pytest
 
 from flexi_b200.desc import RIEMANN, SPLITDG
 from flexi_b200.hostmesh import basis as B
-from flexi_b200.hostmesh.case import TGV_EQN, build_case, tgv_box
+from flexi_b200.hostmesh.case import TGV_EQN, build_case, synthetic_sponge, tgv_box
 from flexi_b200.hostmesh.mesh import BoxSpec
 from oracle import oracle as O
 
@@ -347,21 +347,6 @@ def test_solution_filter_at_operator_start():
     w.close()
 
 
-def _sponge_arrays(r, frac=0.4, seed=3):
-    """A synthetic sponge zone as InitSponge would hand it over (sponge.f90:97-400): the elements whose barycentre lies in the last
-    `frac` of the x range, a smooth ramp times the Jacobian as SpongeMat, a perturbed free stream as SpBaseFlow."""
-    m = r.mesh
-    xb = m.Elem_xGP[..., 0].reshape(m.nElems, -1).mean(axis=1)
-    x0, x1 = m.Elem_xGP[..., 0].min(), m.Elem_xGP[..., 0].max()
-    xs = x1 - frac * (x1 - x0)
-    smap = np.nonzero(xb > xs)[0].astype(np.int32) + 1
-    ramp = np.clip((m.Elem_xGP[smap - 1, ..., 0] - xs) / (x1 - xs), 0.0, 1.0)
-    smat = 5.0 * (6 * ramp ** 5 - 15 * ramp ** 4 + 10 * ramp ** 3) / m.sJ[smap - 1]  # damping*x_star, times the Jacobian 1/sJ
-    rng = np.random.default_rng(seed)
-    base = r.eqn.smooth_state(m.Elem_xGP, length=2.0, amp=0.05) * (1.0 + 0.01 * rng.standard_normal(m.Elem_xGP.shape[:-1] + (5,)))
-    return smap, smat, base
-
-
 def test_sponge_term():
     """Sponge(Ut) (sponge.f90:612-678, dg.f90:659-661): Ut_with - Ut_without = -sJ * SpongeMat * (U - SpBaseFlow) on the sponge
     elements (the term is added in reference space before ApplyJacobian) and nothing elsewhere; switching it off restores Ut."""
@@ -372,7 +357,7 @@ def test_sponge_term():
     w.set_state([U])
     w.dg_time_derivative(0.0)
     plain = np.array(o.array("Ut"))
-    smap, smat, base = _sponge_arrays(r)
+    smap, smat, base = synthetic_sponge(r)
     assert 0 < len(smap) < r.mesh.nElems
     o.set_sponge(smap, smat, base)
     w.dg_time_derivative(0.0)
@@ -385,3 +370,47 @@ def test_sponge_term():
     w.dg_time_derivative(0.0)
     assert np.array_equal(np.array(o.array("Ut")), plain)
     w.close()
+
+
+@pytest.mark.parametrize("T0,branch", [(1.3, "T>=Ts"), (0.3, "T<Ts")])
+def test_sutherland_viscosity_reduces_to_constant_on_isothermal_state(T0, branch):
+    """PP_VISC = 1 (viscosity.f90:57-90, eos.h:73-87) in EvalDiffFlux3D and CalcTimeStep: on a state with uniform temperature the
+    Sutherland operator equals the constant-viscosity operator with mu0' = muSuth(T0), for both branches of the formula; the power
+    law with ExpoSuth = 0 is the constant law bit for bit.  (Gauss-Lobatto nodes: the face states are copies of volume nodes, so the
+    temperature is uniform on the faces too; on Gauss nodes the interpolated traces have their own temperature.)"""
+    from flexi_b200.hostmesh.equation import sutherland_params
+
+    sp = sutherland_params(Ts_ini=0.5, Tref_ini=1.0, expo=1.5)  # non-dimensional: Ts = 0.5, Tref = 1
+    Tn = T0 * sp["Tref"]
+    mu0 = 1e-2
+    mu_ref = mu0 * Tn ** 1.5 * (1 + sp["Ts"]) / (Tn + sp["Ts"]) if Tn >= sp["Ts"] else mu0 * Tn * sp["cSuth"]
+    assert (Tn >= sp["Ts"]) == (branch == "T>=Ts")
+    # continuity of the two branches at T = Ts
+    assert abs(sp["Ts"] ** 1.5 * (1 + sp["Ts"]) / (2 * sp["Ts"]) - sp["Ts"] * sp["cSuth"]) < 1e-15
+    spec = BoxSpec((2, 2, 2), x0=(-1.0, -1.0, -1.0), length=(2.0, 2.0, 2.0), ngeo=2, deform=0.1)
+    eqn = dict(parabolic=True, riemann="roe", mu0=mu0)
+    ranks, w = world(spec, 4, B.NODE_GAUSS_LOBATTO, eqn)
+    r, o = ranks[0], w.ranks[0]
+    U = r.eqn.smooth_state(r.mesh.Elem_xGP, length=2.0)
+    prim = r.eqn.cons_to_prim(U)
+    prim[..., 4] = prim[..., 0] * r.eqn.R * T0  # p = rho R T0: uniform temperature
+    prim[..., 5] = T0
+    U = r.eqn.prim_to_cons(prim)
+    w.set_state([U])
+    o.set_viscosity(1, **sp)
+    w.dg_time_derivative(0.0)
+    ut_s = np.array(o.array("Ut"))
+    dt_s = w.calc_timestep()
+    w.close()
+    ranks2, w2 = world(spec, 4, B.NODE_GAUSS_LOBATTO, dict(eqn, mu0=mu_ref))
+    w2.set_state([U])
+    w2.dg_time_derivative(0.0)
+    ut_c = np.array(w2.ranks[0].array("Ut"))
+    dt_c = w2.calc_timestep()
+    assert np.max(np.abs(ut_s - ut_c)) <= 1e-12 * np.max(np.abs(ut_c))
+    assert abs(dt_s[2] - dt_c[2]) <= 1e-13 * dt_c[2] and abs(dt_s[0] - dt_c[0]) <= 1e-13 * dt_c[0]
+    # power law with exponent 0 == constant viscosity
+    w2.ranks[0].set_viscosity(2, ExpoSuth=0.0)
+    w2.dg_time_derivative(0.0)
+    assert np.array_equal(np.array(w2.ranks[0].array("Ut")), ut_c)
+    w2.close()

@@ -9,7 +9,7 @@ import pytest
 
 from flexi_b200.gpu import FlexiGpu
 from flexi_b200.hostmesh import basis as B
-from flexi_b200.hostmesh.case import build_case
+from flexi_b200.hostmesh.case import build_case, synthetic_sponge
 from flexi_b200.hostmesh.mesh import BoxSpec
 from oracle import oracle as O
 
@@ -190,11 +190,9 @@ def test_sponge_matches_oracle(N, node, eqn):
     """Sponge(Ut) (flexi_gpu_set_sponge; sponge.f90:612-678, dg.f90:659-661) inside the update kernel: one operator evaluation (the
     kernel has to fetch U itself there) and 2 LSERK steps on the curved mesh with a sponge zone over the last 40 % in x; also
     together with the cut-off overintegration (the sponge term is filtered with Ut); switching it off restores the plain operator."""
-    from tests.test_oracle_identities import _sponge_arrays
-
     r = build_case(BoxSpec((4, 2, 2), **CURVED), N, node, eqn)[0]
     U0 = r.eqn.smooth_state(r.mesh.Elem_xGP, length=2.0)
-    smap, smat, base = _sponge_arrays(r)
+    smap, smat, base = synthetic_sponge(r)
     w = O.OracleWorld([(r.desc, r.keep)])
     o = w.ranks[0]
     w.set_state([U0])
@@ -231,6 +229,60 @@ def test_sponge_matches_oracle(N, node, eqn):
         g.set_state(U0)
         ut0 = g.DGTimeDerivative_weakForm(0.0)
         assert np.all(np.max(np.abs(ut0 - plain).reshape(-1, 5), axis=0) <= 1e-12 * np.max(np.abs(plain).reshape(-1, 5), axis=0))
+    finally:
+        g.close()
+        w.close()
+
+
+WALLS = dict(boundary_type=[(4, 2, 0), (9, 0, 0), (2, 1, 0)], ref_state_prim=[(1.0, 0.3, 0.0, 0.0, 0.71428571), (1.0, 0.0, 0.0, 0.0, 0.9)])
+
+
+@pytest.mark.parametrize("visc", [1, 2], ids=["sutherland", "powerlaw"])
+@pytest.mark.parametrize("N,node,eqn,walls", [
+    (7, GL, dict(parabolic=True, split_dg=True, split_dg_type="pi", riemann="lf", mu0=1e-2), False),
+    (5, GL, dict(parabolic=True, split_dg=True, split_dg_type="pi", riemann="lf", mu0=1e-2, lifting=1), True),
+    (4, G, dict(parabolic=True, riemann="roe", mu0=1e-2, lifting=2), True),
+    (3, GL, dict(parabolic=True, riemann="hllc", mu0=1e-2), False),
+], ids=["N7-GL-split", "N5-GL-split-walls", "N4-G-weak-BR2-walls", "N3-GL-weak"])
+def test_viscosity_laws_match_oracle(N, node, eqn, walls, visc):
+    """PP_VISC = 1 / 2 (flexi_gpu_set_viscosity; viscosity.f90:57-90, eos.h:73-87) in EvalDiffFlux3D of the element kernels, the side
+    kernel, the boundary fluxes, and in CalcTimeStep: one operator evaluation (all side arrays), dt, 2 LSERK steps on the curved mesh.
+    The temperature of the test state straddles Ts, so both branches of Sutherland's formula are taken."""
+    from flexi_b200.hostmesh.equation import sutherland_params
+
+    wall_bc = {(1, -1): 1, (1, 1): 2, (0, -1): 3, (0, 1): 3}
+    spec = BoxSpec((3, 2, 2), periodic=(False, False, True), bc_of_face=wall_bc, **CURVED) if walls else BoxSpec((3, 2, 2), **CURVED)
+    r = build_case(spec, N, node, dict(eqn, **(WALLS if walls else {})))[0]
+    U0 = r.eqn.smooth_state(r.mesh.Elem_xGP, length=2.0)
+    T = r.eqn.cons_to_prim(U0)[..., 5]
+    law = sutherland_params(Ts_ini=float(np.median(T)), Tref_ini=float(np.mean(T)), expo=1.5) if visc == 1 else dict(ExpoSuth=0.7)
+    w = O.OracleWorld([(r.desc, r.keep)])
+    o = w.ranks[0]
+    w.set_state([U0])
+    g = FlexiGpu(r)
+    try:
+        g.set_state(U0)
+        w.dg_time_derivative(0.0)
+        plain = np.array(o.array("Ut"))
+        o.set_viscosity(visc, **law)
+        g.set_viscosity(visc, **law)
+        w.dg_time_derivative(0.0)
+        ut, ref = g.DGTimeDerivative_weakForm(0.0), o.array("Ut")
+        scale = np.max(np.abs(ref).reshape(-1, 5), axis=0)
+        assert np.all(np.max(np.abs(ut - ref).reshape(-1, 5), axis=0) <= 1e-12 * scale)
+        assert np.max(np.abs(ref - plain)) > 1e-4 * np.max(np.abs(plain))  # the law does change the operator
+        assert np.max(np.abs(g.get_array("Flux") - o.array("Flux"))) <= 1e-12 * np.max(np.abs(o.array("Flux")))
+        t = 0.0
+        for _ in range(2):
+            dt = w.calc_timestep()
+            dtg = g.CalcTimeStep()
+            assert abs(dtg[0] - dt[0]) <= 1e-13 * dt[0] and abs(dtg[2] - dt[2]) <= 1e-13 * dt[2]
+            w.timestep(t, dt[0])
+            g.TimeStep(t, dt[0])
+            t += dt[0]
+        Ug, Uo = g.get_state(), o.array("U")
+        sc = np.max(np.abs(Uo).reshape(-1, 5), axis=0)
+        assert np.all(np.max(np.abs(Ug - Uo).reshape(-1, 5), axis=0) <= 1e-12 * sc)
     finally:
         g.close()
         w.close()
