@@ -614,6 +614,7 @@ static int init_impl(const flexi_gpu_desc* d, H* h) {
   q.lambda = d->mu0 * cp / d->Pr;
   q.cp = cp;
   q.Pr = d->Pr;
+  q.cpPr = cp / d->Pr;
   q.visc = 0;  // PP_VISC = 0 until flexi_gpu_set_viscosity says otherwise
   q.riemann = d->riemann;
   q.splitDG = d->splitDG;

@@ -86,12 +86,12 @@ int gl2_smem_pad() {
 #else
 constexpr int gl2_smem_pad() { return 0; }
 #endif
-template <int STYPE, bool PARA, int NVL, int NVC, int LIFT>
+template <int STYPE, bool PARA, int NVL, int NVC, int LIFT, bool VVISC = false>
 struct GL2 {
   static constexpr int NPE = HAS_GL2 ? NP : 2;  // odd NP never instantiates the real kernel
   using C = VolGL2Cfg<NPE, PARA, NVC>;
   static cudaError_t setup() {
-    return cudaFuncSetAttribute(k_volume_gl2<NPE, STYPE, PARA, NVL, NVC, LIFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::BYTES + gl2_smem_pad());
+    return cudaFuncSetAttribute(k_volume_gl2<NPE, STYPE, PARA, NVL, NVC, LIFT, VVISC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::BYTES + gl2_smem_pad());
   }
   static cudaError_t launch(const VolArgs& a, int nBlocks, cudaStream_t s) {
     VolArgs2<NPE> aa;
@@ -106,7 +106,7 @@ struct GL2 {
     aa.b.lhm0 = b[Dim<NPE>::O_LHM];
     aa.b.lhpN = b[Dim<NPE>::O_LHP + NPE - 1];
     aa.b.lm0 = b[Dim<NPE>::O_LM];
-    k_volume_gl2<NPE, STYPE, PARA, NVL, NVC, LIFT><<<nBlocks, C::NT, C::BYTES + gl2_smem_pad(), s>>>(aa);
+    k_volume_gl2<NPE, STYPE, PARA, NVL, NVC, LIFT, VVISC><<<nBlocks, C::NT, C::BYTES + gl2_smem_pad(), s>>>(aa);
     return cudaGetLastError();
   }
 };
@@ -124,20 +124,32 @@ bool gl2_antisymmetric(const double* b) {
   }
   return true;
 }
-// all nVarLifting variables are lifted when gradients are handed out; the time-stepping path lifts (v1,v2,v3,T) only
-template <int STYPE, bool PARA, int NVL>
-cudaError_t gl2_setup() {
-  cudaError_t e = GL2<STYPE, PARA, NVL, NVL, 1>::setup();
-  if (e == cudaSuccess && PARA) e = GL2<STYPE, PARA, NVL, NVL, 2>::setup();
-  if (e == cudaSuccess && PARA && NVL == 5) e = GL2<STYPE, PARA, NVL, 4, 1>::setup();
-  if (e == cudaSuccess && PARA && NVL == 5) e = GL2<STYPE, PARA, NVL, 4, 2>::setup();
+// all nVarLifting variables are lifted when gradients are handed out; the time-stepping path lifts (v1,v2,v3,T) only.
+// PP_VISC != 0 has its own instantiations (Navier-Stokes only).
+template <int STYPE, bool PARA, int NVL, bool VV>
+cudaError_t gl2_setup_v() {
+  cudaError_t e = GL2<STYPE, PARA, NVL, NVL, 1, VV>::setup();
+  if (e == cudaSuccess && PARA) e = GL2<STYPE, PARA, NVL, NVL, 2, VV>::setup();
+  if (e == cudaSuccess && PARA && NVL == 5) e = GL2<STYPE, PARA, NVL, 4, 1, VV>::setup();
+  if (e == cudaSuccess && PARA && NVL == 5) e = GL2<STYPE, PARA, NVL, 4, 2, VV>::setup();
   return e;
 }
 template <int STYPE, bool PARA, int NVL>
-cudaError_t gl2_launch(int lift, const VolArgs& a, int nBlocks, cudaStream_t s) {
+cudaError_t gl2_setup() {
+  cudaError_t e = gl2_setup_v<STYPE, PARA, NVL, false>();
+  if (e == cudaSuccess && PARA) e = gl2_setup_v<STYPE, PARA, NVL, true>();
+  return e;
+}
+template <int STYPE, bool PARA, int NVL, bool VV>
+cudaError_t gl2_launch_v(int lift, const VolArgs& a, int nBlocks, cudaStream_t s) {
   const bool all = !PARA || NVL == 4 || a.fullGrad || a.gvol[0];
-  if (PARA && lift == 2) return all ? GL2<STYPE, PARA, NVL, NVL, 2>::launch(a, nBlocks, s) : GL2<STYPE, PARA, NVL, 4, 2>::launch(a, nBlocks, s);
-  return all ? GL2<STYPE, PARA, NVL, NVL, 1>::launch(a, nBlocks, s) : GL2<STYPE, PARA, NVL, 4, 1>::launch(a, nBlocks, s);
+  if (PARA && lift == 2) return all ? GL2<STYPE, PARA, NVL, NVL, 2, VV>::launch(a, nBlocks, s) : GL2<STYPE, PARA, NVL, 4, 2, VV>::launch(a, nBlocks, s);
+  return all ? GL2<STYPE, PARA, NVL, NVL, 1, VV>::launch(a, nBlocks, s) : GL2<STYPE, PARA, NVL, 4, 1, VV>::launch(a, nBlocks, s);
+}
+template <int STYPE, bool PARA, int NVL>
+cudaError_t gl2_launch(int lift, const VolArgs& a, int nBlocks, cudaStream_t s) {
+  if (PARA && a.q.visc != 0) return gl2_launch_v<STYPE, PARA, NVL, PARA>(lift, a, nBlocks, s);
+  return gl2_launch_v<STYPE, PARA, NVL, false>(lift, a, nBlocks, s);
 }
 
 

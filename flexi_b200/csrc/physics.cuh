@@ -25,21 +25,19 @@ struct Eqn {
   // InitEos (eos.f90:160-192): Tref = 1/Tref_ini and Ts = Ts_ini/Tref_ini for Sutherland; mu0 already divided by Tref^ExpoSuth
   // for the power law.  cpPr = cp/Pr forms lambda = mu*cp/Pr (THERMAL_CONDUCTIVITY_H).
   int visc;
-  double Tref, Ts, expoSuth, cSuth, cp, Pr;
+  double Tref, Ts, expoSuth, cSuth, cp, Pr, cpPr;  // cpPr = cp/Pr
 };
 
-// VISCOSITY_TEMPERATURE / VISCOSITY_PRIM (eos.h:73-87) for PP_VISC != 0; kept out of line: pow() is long, and the
-// constant-viscosity kernels must not carry it in their instruction stream
-#ifdef __CUDACC__
-__host__ __device__ __noinline__
-#endif
-inline double viscosity_var(const Eqn& q, double T) {
+// VISCOSITY_TEMPERATURE / VISCOSITY_PRIM (eos.h:73-87) for PP_VISC != 0.  x**y for x > 0 as exp(y*log(x)): both are inlined
+// (a call to pow(), kept out of line, cost the constant-viscosity kernels a stack frame and ~10 registers: +16 % on the element
+// kernel, +65 % on the side kernel); the extra rounding, |y ln x| ulp, is far below the parity tolerance.
+FX_HD double viscosity_var(const Eqn& q, double T) {
   if (q.visc == 1) {  // muSuth, viscosity.f90:76-89
     const double TnoDim = T * q.Tref;
-    if (TnoDim >= q.Ts) return q.mu0 * pow(TnoDim, q.expoSuth) * (1 + q.Ts) / (TnoDim + q.Ts);
+    if (TnoDim >= q.Ts) return q.mu0 * exp(q.expoSuth * log(TnoDim)) * (1 + q.Ts) / (TnoDim + q.Ts);
     return q.mu0 * TnoDim * q.cSuth;
   }
-  return q.mu0 * pow(T, q.expoSuth);  // power law, eos.h:78
+  return q.mu0 * exp(q.expoSuth * log(T));  // power law, eos.h:78
 }
 FX_HD double viscosity(const Eqn& q, double T) { return q.visc == 0 ? q.mu0 : viscosity_var(q, T); }
 
@@ -165,16 +163,11 @@ FX_HD void eval_flux3d(const double* U, const double* P, double* f, double* g, d
 
 // flux.f90:149-241 EvalDiffFlux3D_Point.  gv* = gradient of (v1,v2,v3), gT* = gradient of T; (x,y,z) components.
 // Only the four non-zero rows (momentum, energy) are returned: f[0..2] momentum, f[3] energy.
-// T = UPrim(TEMP): only read for PP_VISC != 0 (muS = VISCOSITY_PRIM(UPrim), lambda = THERMAL_CONDUCTIVITY_H(muS), flux.f90:180-181)
-FX_HD void eval_diff_flux3d(const Eqn& q, double T, double v1, double v2, double v3, const double* gx, const double* gy,
-                                                 const double* gz, double* f, double* g, double* h) {
+// core with the viscosity and the conductivity given (muS = VISCOSITY_PRIM(UPrim), lambda = THERMAL_CONDUCTIVITY_H(muS), flux.f90:180-181)
+FX_HD void eval_diff_flux3d_mu(const double muS, const double lambda, double v1, double v2, double v3, const double* gx,
+                               const double* gy, const double* gz, double* f, double* g, double* h) {
   // gx = d(v1,v2,v3,T)/dx etc.
   const double s23 = 2. / 3., s43 = 4. / 3.;
-  double muS = q.mu0, lambda = q.lambda;
-  if (q.visc != 0) {
-    muS = viscosity_var(q, T);
-    lambda = muS * q.cp / q.Pr;
-  }
   const double tau_xx = muS * (s43 * gx[0] - s23 * gy[1] - s23 * gz[2]);
   const double tau_yy = muS * (-s23 * gx[0] + s43 * gy[1] - s23 * gz[2]);
   const double tau_zz = muS * (-s23 * gx[0] - s23 * gy[1] + s43 * gz[2]);
@@ -193,6 +186,16 @@ FX_HD void eval_diff_flux3d(const Eqn& q, double T, double v1, double v2, double
   h[1] = -tau_yz;
   h[2] = -tau_zz;
   h[3] = -tau_xz * v1 - tau_yz * v2 - tau_zz * v3 - lambda * gz[3];
+}
+// T = UPrim(TEMP): only read for PP_VISC != 0
+FX_HD void eval_diff_flux3d(const Eqn& q, double T, double v1, double v2, double v3, const double* gx, const double* gy,
+                            const double* gz, double* f, double* g, double* h) {
+  double muS = q.mu0, lambda = q.lambda;
+  if (q.visc != 0) {
+    muS = viscosity_var(q, T);
+    lambda = muS * q.cp / q.Pr;
+  }
+  eval_diff_flux3d_mu(muS, lambda, v1, v2, v3, gx, gy, gz, f, g, h);
 }
 
 // ---- split two-point fluxes, splitflux.f90 --------------------------------------------------------------------------------

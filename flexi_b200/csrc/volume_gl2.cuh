@@ -157,6 +157,27 @@ __device__ __forceinline__ int gl2_gn(int dir, int p, int r0, int r1) {
   return i + NP * (j + NP * k);
 }
 
+// Swizzled address of CANONICAL line position p (actual position gl2_ap(hb, p)) of the line of direction dir through (r0, r1).
+// For NP = 8 the swizzle is XOR-linear in the line position: address = base(dir; hb, r0, r1) ^ off(dir, p) with a per-thread base
+// and compile-time offsets -- one LOP3 per address instead of the ~6 integer instructions of gl2_phys (the lifting sweeps spent as
+// many integer as FP64 instructions).  Derivation with h = hb ? 7 : 0 (N - p = p ^ 7):
+//   xi   lines (i = p^h, j = r0, k = r1): (p ^ h ^ s(r0,r1)) | (r0 ^ (r1&1)) << 3 | r1 << 6
+//   eta  lines (j = p^h, i = r0, k = r1): (r0 ^ (r1&1)<<2 ^ h>>1 ^ p>>1) | (h ^ (r1&1) ^ p) << 3 | r1 << 6
+//   zeta lines (k = p^h, i = r0, j = r1): (r0 ^ r1>>1 ^ (h&1)<<2 ^ (p&1)<<2) | (r1 ^ (h&1) ^ (p&1)) << 3 | (h ^ p) << 6
+template <int NP>
+__device__ __forceinline__ int gl2_sac(int dir, int p, int hb, int r0, int r1) {
+  if (NP == 8) {
+    const int h = hb ? 7 : 0;
+    const int b0 = (h ^ (((r0 >> 1) & 3) | ((r1 & 1) << 2))) | ((r0 ^ (r1 & 1)) << 3) | (r1 << 6);
+    const int b1 = (r0 ^ ((r1 & 1) << 2) ^ ((h >> 1) & 3)) | ((h ^ (r1 & 1)) << 3) | (r1 << 6);
+    const int b2 = (r0 ^ ((r1 >> 1) & 3) ^ ((h & 1) << 2)) | ((r1 ^ (h & 1)) << 3) | (h << 6);
+    const int base = (dir == 0) ? b0 : (dir == 1) ? b1 : b2;
+    const int off = (dir == 0) ? p : (dir == 1) ? ((p >> 1) | (p << 3)) : (((p & 1) * 12) | (p << 6));
+    return base ^ off;
+  }
+  return gl2_sa<NP>(dir, gl2_ap<NP>(hb, p), r0, r1);
+}
+
 // One direction sweep of the advective two-point fluxes (+ the weak-form derivative of the viscous flux of that direction).
 //   sa[q]          shared-memory address of canonical line position q (state planes and metric planes share the layout)
 //   sMd, ma[q]     the three metric planes of this direction and the address of position q in them (ma == sa when the planes
@@ -281,7 +302,9 @@ __device__ __forceinline__ void gl2_pair_sweep(const GL2Basis<NP>& B, const doub
 // Template parameters: NVL = nVarLifting of the gradient arrays (their layout), NVC = number of lifting variables actually
 // lifted: NVL, or 4 = (v1,v2,v3,T) on the time-stepping path, where nothing reads the density gradient (EvalDiffFlux3D does
 // not use it and no gradient array is handed out).
-template <int NP, int STYPE, bool PARA, int NVL, int NVC, int LIFT>
+// VVISC: PP_VISC != 0 (Sutherland / power law) -- a separate instantiation, so that the constant-viscosity kernel keeps mu0 and
+// lambda as uniform constant-bank operands (as selects they cost per-thread registers and spills: 5.39 -> 5.70 ms).
+template <int NP, int STYPE, bool PARA, int NVL, int NVC, int LIFT, bool VVISC = false>
 __global__ void __launch_bounds__(VolGL2Cfg<NP, PARA, NVC>::NT, VolGL2Cfg<NP, PARA, NVC>::MINB)
     k_volume_gl2(const __grid_constant__ VolArgs2<NP> AA) {
   using D = Dim<NP>;
@@ -327,7 +350,7 @@ __global__ void __launch_bounds__(VolGL2Cfg<NP, PARA, NVC>::NT, VolGL2Cfg<NP, PA
   if (C::MSM) {
 #pragma unroll
     for (int c = 0; c < HALF; ++c) {
-      const int n = gl2_gn<NP>(2, gl2_ap<NP>(hb, c), r0, r1), s = gl2_sa<NP>(2, gl2_ap<NP>(hb, c), r0, r1);
+      const int n = gl2_gn<NP>(2, gl2_ap<NP>(hb, c), r0, r1), s = gl2_sac<NP>(2, c, hb, r0, r1);
 #pragma unroll
       for (int m = 0; m < 9; ++m) cp_async8(sM + m * PL + s, gM + m * D::NP3 + n);
     }
@@ -405,7 +428,7 @@ __global__ void __launch_bounds__(VolGL2Cfg<NP, PARA, NVC>::NT, VolGL2Cfg<NP, PA
     double Pn[6];
     const double* const Ucc = Uc[c];
     const double sRho = cons_to_prim_fast(q, Ucc, Pn);
-    const int s = gl2_sa<NP>(2, gl2_ap<NP>(hb, c), r0, r1);
+    const int s = gl2_sac<NP>(2, c, hb, r0, r1);
 #pragma unroll
     for (int v = 0; v < 4; ++v) sP[v * PL + s] = Pn[v];
     sP[4 * PL + s] = PI ? 4. * Pn[PRES] : Pn[PRES];
@@ -469,7 +492,7 @@ __global__ void __launch_bounds__(VolGL2Cfg<NP, PARA, NVC>::NT, VolGL2Cfg<NP, PA
       if (FX_DBG(A, 2)) break;
       int sa[NP];
 #pragma unroll
-      for (int p = 0; p < NP; ++p) sa[p] = gl2_sa<NP>(dir, gl2_ap<NP>(hb, p), r0, r1);
+      for (int p = 0; p < NP; ++p) sa[p] = gl2_sac<NP>(dir, p, hb, r0, r1);
 #pragma unroll
       for (int v = 0; v < NVC; ++v) {
         const double* pl = sP + lift_prim(NVC, v) * PL;
@@ -525,13 +548,23 @@ __global__ void __launch_bounds__(VolGL2Cfg<NP, PARA, NVC>::NT, VolGL2Cfg<NP, PA
     for (int c = 0; c < HALF; ++c)
 #pragma unroll
       for (int v = 0; v < 4; ++v) cown[c][v] = cpart[c][v] = 0.;
+    // PP_VISC != 0: the T plane is dead after S2 (until it hands over Ut(5) after S3), so every thread turns the temperature of
+    // its own nodes into their viscosity in place, in one cold block here -- inside the four unrolled node bodies the inlined
+    // exp/log cost the hot path registers and spills
+    if (VVISC) {
+#pragma unroll 1
+      for (int c = 0; c < HALF; ++c) {
+        double* const pT = sP + TEMP * PL + gl2_sac<NP>(2, c, hb, r0, r1);
+        *pT = viscosity_var(q, *pT);
+      }
+    }
     if (!FX_DBG(A, 4)) {
       constexpr int LV = (NVC == 5) ? 1 : 0;
       const int i = r0, j = r1;
 #pragma unroll
       for (int c = 0; c < HALF; ++c) {
         const int k = gl2_ap<NP>(hb, c);
-        const int s = gl2_sa<NP>(2, k, r0, r1);
+        const int s = gl2_sac<NP>(2, c, hb, r0, r1);
         const int n = i + NP * (j + NP * k);
         double Mc[9];
 #pragma unroll
@@ -601,9 +634,9 @@ __global__ void __launch_bounds__(VolGL2Cfg<NP, PARA, NVC>::NT, VolGL2Cfg<NP, PA
         }
         // ---- viscous flux of this node (flux.f90:149-241) ----
         const double v1 = sP[VEL1 * PL + s], v2 = sP[VEL2 * PL + s], v3 = sP[VEL3 * PL + s];
-        const double Tn = (q.visc != 0) ? sP[TEMP * PL + s] : 0.;  // the T plane is intact until S3; read for PP_VISC != 0 only
+        const double muC = VVISC ? sP[TEMP * PL + s] : q.mu0, lamC = VVISC ? muC * q.cpPr : q.lambda;
         double fv[4], gv[4], hv[4];
-        eval_diff_flux3d(q, Tn, v1, v2, v3, gx + LV, gy + LV, gz + LV, fv, gv, hv);
+        eval_diff_flux3d_mu(muC, lamC, v1, v2, v3, gx + LV, gy + LV, gz + LV, fv, gv, hv);
         // ---- what the side kernel needs from this element.  ViscousFlux_Side (riemann.f90:448-498) forms
         //      0.5*n.(F_v(U_L,gradU_L) + F_v(U_R,gradU_R)); each half depends on one element only, and on LGL nodes the face
         //      state and (BR1) the face gradient are copies of the boundary node's (prolongtoface.t90:270-303), so the element
@@ -624,7 +657,7 @@ __global__ void __launch_bounds__(VolGL2Cfg<NP, PARA, NVC>::NT, VolGL2Cfg<NP, PA
               gfz[v] = gzo[v] + w * (sJc * (f[v] * nv[2]));
             }
             double ff[4], gf[4], hf[4];
-            eval_diff_flux3d(q, Tn, v1, v2, v3, gfx + LV, gfy + LV, gfz + LV, ff, gf, hf);
+            eval_diff_flux3d_mu(muC, lamC, v1, v2, v3, gfx + LV, gfy + LV, gfz + LV, ff, gf, hf);
 #pragma unroll
             for (int v = 0; v < 4; ++v) nf[v] = nv[0] * ff[v] + nv[1] * gf[v] + nv[2] * hf[v];
           } else {
@@ -692,7 +725,7 @@ __global__ void __launch_bounds__(VolGL2Cfg<NP, PARA, NVC>::NT, VolGL2Cfg<NP, PA
     // ---- the partner's share of the zeta derivative of h~ goes to the partner's slots of the hand-over planes (true sign) ----
 #pragma unroll
     for (int t = 0; t < HALF; ++t) {
-      const int s = gl2_sa<NP>(2, gl2_ap<NP>(hb, HALF + t), r0, r1);
+      const int s = gl2_sac<NP>(2, HALF + t, hb, r0, r1);
 #pragma unroll
       for (int v = 0; v < 4; ++v) ut_plane(v + 1)[s] = sgn_apply(cpart[t][v], sb);
     }
@@ -707,7 +740,7 @@ __global__ void __launch_bounds__(VolGL2Cfg<NP, PARA, NVC>::NT, VolGL2Cfg<NP, PA
     const int dir = (it == 0) ? 2 : it - 1;
     int sa[NP];  // indexed by canonical position
 #pragma unroll
-    for (int p = 0; p < NP; ++p) sa[p] = gl2_sa<NP>(dir, gl2_ap<NP>(hb, p), r0, r1);
+    for (int p = 0; p < NP; ++p) sa[p] = gl2_sac<NP>(dir, p, hb, r0, r1);
     const double* vp[4];
 #pragma unroll
     for (int v = 0; v < 4; ++v) vp[v] = sW + ((dir & 1) * 4 + v) * PL;

@@ -292,3 +292,15 @@ class DGBasis:
                 self.DVolSurf = dvs
         else:
             self.DVolSurf = np.zeros((n + 1, n + 1))
+
+
+def overintegration_cons(n, node_type, n_under, sJ):
+    """InitOverintegration for OVERINTEGRATIONTYPE_CONSCUTOFF (dg/overintegration.f90:118-135): the modal projection
+    Vdm_N_NUnder [NUnder+1, N+1], the interpolation Vdm_NUnder_N [N+1, NUnder+1] (GetVandermonde(..., modal=.TRUE.)) and
+    sJNUnder [nElems, kU, jU, iU] = 1 / (Jacobian projected to NUnder).  The reference projects DetJac_Ref from NGeoRef; this host
+    stand-in projects the Jacobian 1/sJ from N -- the library and the oracle take sJNUnder as an input either way."""
+    vdm_down = get_vandermonde(n, node_type, n_under, node_type, modal=True)
+    vdm_up = get_vandermonde(n_under, node_type, n, node_type, modal=False)
+    jac = 1.0 / np.asarray(sJ)
+    jac_u = np.einsum("li,mj,nk,ekji->enml", vdm_down, vdm_down, vdm_down, jac)
+    return vdm_down, vdm_up, np.ascontiguousarray(1.0 / jac_u)

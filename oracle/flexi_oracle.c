@@ -55,6 +55,10 @@ typedef struct oracle {
   double *V, *V_master, *V_slave; /* dg_vars.f90:59 */
   double* FilterMat;              /* (0:N,0:N) Fortran order, NULL = FilterType none; set by oracle_set_filter */
   double* OverintegrationMat;     /* (0:N,0:N) Fortran order, NULL = OverintegrationType 0; set by oracle_set_overintegration */
+  /* OverintegrationType 2 (conservative cut-off, overintegration.f90:118-135): NUnder, Vdm_N_NUnder(0:NUnder,0:N),
+     Vdm_NUnder_N(0:N,0:NUnder), sJNUnder(0:NUnder,0:NUnder,0:NUnder,nElems); NUnder < 0 = off */
+  int NUnder;
+  double *Vdm_N_NUnder, *Vdm_NUnder_N, *sJNUnder;
   double *Ja_Face, *Ja_slave;     /* (3,3,0:N,0:N,nSides), mesh_vars.f90:70-78; set by oracle_set_face_metrics */
   /* sponge (sponge/sponge_vars.f90): SpongeMap(nSpongeElems) 1-based element ids, SpongeMat(0:N,0:N,0:N,nSpongeElems) pre-multiplied
      by the Jacobian, SpBaseFlow(5,0:N,0:N,0:N,nElems); set by oracle_set_sponge */
@@ -1537,6 +1541,80 @@ static void filter_volume(const oracle* o, const double* Mat, double* U) {
   free(b2);
 }
 
+/* overintegration.f90:181-330 FilterConservative: JU_t on N -> projection to NUnder (ChangeBasisVolume with Vdm_N_NUnder) -> times
+   sJNUnder -> interpolation back to N (Vdm_NUnder_N).  Sums run over ascending input index like ChangeBasisVolume. */
+static void filter_conservative(const oracle* o, double* U) {
+  const int np = o->np, nu = o->NUnder + 1;
+  const size_t ne = (size_t)np * np * np * NVAR;
+  double* b1 = (double*)xcalloc((size_t)nu * np * np * NVAR, 8);
+  double* b2 = (double*)xcalloc((size_t)nu * nu * np * NVAR, 8);
+  double* ul = (double*)xcalloc((size_t)nu * nu * nu * NVAR, 8);
+  double* b3 = (double*)xcalloc((size_t)np * nu * nu * NVAR, 8);
+  double* b4 = (double*)xcalloc((size_t)np * np * nu * NVAR, 8);
+#define DN(iu, i) o->Vdm_N_NUnder[(iu) + (size_t)nu * (i)]
+#define UP(i, iu) o->Vdm_NUnder_N[(i) + (size_t)np * (iu)]
+#define X5(A, n0, n1, v, a, b, c) (A)[(v) + NVAR * ((a) + (size_t)(n0) * ((b) + (size_t)(n1) * (c)))]
+  for (int e = 0; e < o->d.nElems; ++e) {
+    double* Ue = U + (size_t)e * ne;
+    for (int k = 0; k < np; ++k)
+      for (int j = 0; j < np; ++j)
+        for (int iu = 0; iu < nu; ++iu)
+          for (int v = 0; v < NVAR; ++v) {
+            double s = DN(iu, 0) * X5(Ue, np, np, v, 0, j, k);
+            for (int i = 1; i < np; ++i) s = s + DN(iu, i) * X5(Ue, np, np, v, i, j, k);
+            X5(b1, nu, np, v, iu, j, k) = s;
+          }
+    for (int k = 0; k < np; ++k)
+      for (int ju = 0; ju < nu; ++ju)
+        for (int iu = 0; iu < nu; ++iu)
+          for (int v = 0; v < NVAR; ++v) {
+            double s = DN(ju, 0) * X5(b1, nu, np, v, iu, 0, k);
+            for (int j = 1; j < np; ++j) s = s + DN(ju, j) * X5(b1, nu, np, v, iu, j, k);
+            X5(b2, nu, nu, v, iu, ju, k) = s;
+          }
+    for (int ku = 0; ku < nu; ++ku)
+      for (int ju = 0; ju < nu; ++ju)
+        for (int iu = 0; iu < nu; ++iu)
+          for (int v = 0; v < NVAR; ++v) {
+            double s = 0.;
+            for (int k = 0; k < np; ++k) s = s + DN(ku, k) * X5(b2, nu, nu, v, iu, ju, k);
+            X5(ul, nu, nu, v, iu, ju, ku) = s * o->sJNUnder[((size_t)e * nu + ku) * nu * nu + (size_t)ju * nu + iu];
+          }
+    for (int ku = 0; ku < nu; ++ku)
+      for (int ju = 0; ju < nu; ++ju)
+        for (int i = 0; i < np; ++i)
+          for (int v = 0; v < NVAR; ++v) {
+            double s = UP(i, 0) * X5(ul, nu, nu, v, 0, ju, ku);
+            for (int iu = 1; iu < nu; ++iu) s = s + UP(i, iu) * X5(ul, nu, nu, v, iu, ju, ku);
+            X5(b3, np, nu, v, i, ju, ku) = s;
+          }
+    for (int ku = 0; ku < nu; ++ku)
+      for (int j = 0; j < np; ++j)
+        for (int i = 0; i < np; ++i)
+          for (int v = 0; v < NVAR; ++v) {
+            double s = UP(j, 0) * X5(b3, np, nu, v, i, 0, ku);
+            for (int ju = 1; ju < nu; ++ju) s = s + UP(j, ju) * X5(b3, np, nu, v, i, ju, ku);
+            X5(b4, np, np, v, i, j, ku) = s;
+          }
+    for (int k = 0; k < np; ++k)
+      for (int j = 0; j < np; ++j)
+        for (int i = 0; i < np; ++i)
+          for (int v = 0; v < NVAR; ++v) {
+            double s = 0.;
+            for (int ku = 0; ku < nu; ++ku) s = s + UP(k, ku) * X5(b4, np, np, v, i, j, ku);
+            X5(Ue, np, np, v, i, j, k) = s;
+          }
+  }
+#undef DN
+#undef UP
+#undef X5
+  free(b1);
+  free(b2);
+  free(ul);
+  free(b3);
+  free(b4);
+}
+
 /* sponge.f90:612-678 Sponge(Ut): Ut = Ut - SpongeMat*(U - SpBaseFlow) on the sponge elements (DG elements; SpongeMat already
    carries the Jacobian, so this happens in reference space, dg.f90:659-661) */
 static void sponge(oracle* o) {
@@ -1559,6 +1637,10 @@ static void finish_ut(oracle* o, double t) {
   if (o->d.doCalcSource) calc_source(o, t);
   if (o->nSpongeElems > 0) sponge(o);
   /* dg.f90:663-676: OVERINTEGRATIONTYPE_CUTOFF filters Ut before the Jacobian is applied (dg/overintegration.f90:162-187) */
+  if (o->NUnder >= 0) { /* OVERINTEGRATIONTYPE_CONSCUTOFF: the filter applies sJ on NUnder itself, no ApplyJacobian for DG elements */
+    filter_conservative(o, o->Ut);
+    return;
+  }
   if (o->OverintegrationMat) filter_volume(o, o->OverintegrationMat, o->Ut);
   apply_jacobian(o, NVAR, o->Ut);
 }
@@ -1920,6 +2002,7 @@ oracle* oracle_create(const flexi_gpu_desc* d) {
     return NULL;
   }
   oracle* o = (oracle*)xcalloc(1, sizeof(oracle));
+  o->NUnder = -1; /* no conservative cut-off */
   o->d = *d;
   const int np = d->N + 1;
   o->np = np;
@@ -2075,6 +2158,27 @@ int oracle_set_overintegration(oracle* o, int type, const double* Mat) {
   memcpy(o->OverintegrationMat, Mat, n * 8);
   return 0;
 }
+/* OverintegrationType 2 (conservative cut-off): the arrays InitOverintegration builds (overintegration.f90:118-135), Fortran order;
+   NUnder < 0 switches it off.  The host also filters the initial solution (timedisc.f90:119-122): oracle_filter_conservative. */
+int oracle_set_overintegration_cons(oracle* o, int NUnder, const double* Vdm_N_NUnder, const double* Vdm_NUnder_N, const double* sJNUnder) {
+  free(o->Vdm_N_NUnder);
+  free(o->Vdm_NUnder_N);
+  free(o->sJNUnder);
+  o->Vdm_N_NUnder = o->Vdm_NUnder_N = o->sJNUnder = NULL;
+  o->NUnder = -1;
+  if (NUnder < 0) return 0;
+  if (NUnder >= o->np - 1 || !Vdm_N_NUnder || !Vdm_NUnder_N || !sJNUnder) return -1;
+  const size_t nu = (size_t)NUnder + 1, n1 = nu * o->np, n3 = nu * nu * nu * o->d.nElems;
+  o->Vdm_N_NUnder = (double*)xcalloc(n1, 8);
+  o->Vdm_NUnder_N = (double*)xcalloc(n1, 8);
+  o->sJNUnder = (double*)xcalloc(n3, 8);
+  memcpy(o->Vdm_N_NUnder, Vdm_N_NUnder, n1 * 8);
+  memcpy(o->Vdm_NUnder_N, Vdm_NUnder_N, n1 * 8);
+  memcpy(o->sJNUnder, sJNUnder, n3 * 8);
+  o->NUnder = NUnder;
+  return 0;
+}
+void oracle_filter_conservative(oracle* o, double* JU) { filter_conservative(o, JU); }
 /* FilterType (filter/filter.f90:67-72,135-196): 0 none; 1 cutoff and 2 modal (Hesthaven) both point Filter_Pointer at Filter with
    the host-built FilterMat (:138-190); 3 (LAF) is not restated. */
 int oracle_set_filter(oracle* o, int type, const double* Mat) {
@@ -2097,6 +2201,9 @@ void oracle_destroy(oracle* o) {
   free(o->SpongeMap);
   free(o->SpongeMat);
   free(o->SpBaseFlow);
+  free(o->Vdm_N_NUnder);
+  free(o->Vdm_NUnder_N);
+  free(o->sJNUnder);
   for (int i = 0; i < o->n_owned; ++i) free(o->owned[i]);
   double* st[] = {o->U, o->Ut, o->Ut_tmp, o->UPrim, o->U_master, o->U_slave, o->UPrim_master, o->UPrim_slave, o->Flux_master,
                   o->Flux_slave, o->gradUx, o->gradUy, o->gradUz, o->gradUx_master, o->gradUy_master, o->gradUz_master,

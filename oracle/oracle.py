@@ -53,6 +53,9 @@ def _load(fast=False):
     lib.oracle_set_overintegration.argtypes = [P, C.c_int, PD]
     lib.oracle_filter.argtypes = [P, PD, PD]
     lib.oracle_set_filter.argtypes = [P, C.c_int, PD]
+    lib.oracle_set_overintegration_cons.argtypes = [P, C.c_int, PD, PD, PD]
+    lib.oracle_set_overintegration_cons.restype = C.c_int
+    lib.oracle_filter_conservative.argtypes = [P, PD]
     lib.oracle_set_viscosity.argtypes = [P, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double]
     lib.oracle_set_viscosity.restype = C.c_int
     lib.oracle_set_sponge.argtypes = [P, C.c_int, C.POINTER(C.c_int32), PD, PD]
@@ -92,6 +95,23 @@ class OracleRank:
         m = None if mat is None else np.asfortranarray(mat, dtype=np.float64)
         rc = self.lib.oracle_set_overintegration(self.h, int(otype), None if m is None else _pd(m))
         assert rc == 0, "OverintegrationType not restated"
+
+    def set_overintegration_cons(self, n_under=-1, vdm_n_nunder=None, vdm_nunder_n=None, sj_nunder=None):
+        """OverintegrationType 2 (conservative cut-off, overintegration.f90:118-135,181-330): Vdm_N_NUnder [NUnder+1, N+1],
+        Vdm_NUnder_N [N+1, NUnder+1], sJNUnder [nElems, kU, jU, iU]; n_under < 0 = off."""
+        if n_under < 0:
+            assert self.lib.oracle_set_overintegration_cons(self.h, -1, None, None, None) == 0
+            return
+        a = np.asfortranarray(vdm_n_nunder, dtype=np.float64)
+        b = np.asfortranarray(vdm_nunder_n, dtype=np.float64)
+        c = np.ascontiguousarray(sj_nunder, dtype=np.float64)
+        assert self.lib.oracle_set_overintegration_cons(self.h, int(n_under), _pd(a), _pd(b), _pd(c)) == 0
+
+    def filter_conservative(self, JU):
+        """FilterConservative on a (nElems,k,j,i,5) array holding J*U (timedisc.f90:119-122 filters the initial solution this way)."""
+        out = np.ascontiguousarray(JU, dtype=np.float64).copy()
+        self.lib.oracle_filter_conservative(self.h, _pd(out))
+        return out
 
     def set_viscosity(self, visc_type=0, Ts=0.0, Tref=1.0, ExpoSuth=0.0, cSuth=0.0):
         """PP_VISC 0/1/2 with the MOD_EOS_Vars values after InitEos (eos.f90:160-192)."""

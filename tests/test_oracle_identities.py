@@ -414,3 +414,52 @@ def test_sutherland_viscosity_reduces_to_constant_on_isothermal_state(T0, branch
     w2.dg_time_derivative(0.0)
     assert np.array_equal(np.array(w2.ranks[0].array("Ut")), ut_c)
     w2.close()
+
+
+@pytest.mark.parametrize("node", [B.NODE_GAUSS, B.NODE_GAUSS_LOBATTO])
+def test_overintegration_conservative_cutoff(node):
+    """OverintegrationType = 2 (overintegration.f90:118-135,181-330; dg.f90:664-668): JU_t is projected to NUnder, divided by the
+    Jacobian ON NUnder and interpolated back, and ApplyJacobian is skipped.  On a Cartesian mesh (constant Jacobian) this is the
+    plain cut-off filter; on the curved mesh it keeps the element integral of J*U_t (that is what 'conservative' means: the
+    modal projection preserves the mean) where the plain cut-off does not."""
+    N, NU = 5, 3
+    eqn = dict(parabolic=True, split_dg=(node == B.NODE_GAUSS_LOBATTO), split_dg_type="pi", riemann="lf", mu0=1e-2)
+    # (a) Cartesian: equal to the cut-off filter
+    ranks, w = world(tgv_box(2), N, node, eqn)
+    r, o = ranks[0], w.ranks[0]
+    U = r.eqn.smooth_state(r.mesh.Elem_xGP, length=2 * np.pi)
+    w.set_state([U])
+    o.set_overintegration(1, B.overintegration_mat(r.basis.xGP, NU))
+    w.dg_time_derivative(0.0)
+    ut_cut = np.array(o.array("Ut"))
+    o.set_overintegration(0)
+    o.set_overintegration_cons(NU, *B.overintegration_cons(N, node, NU, r.mesh.sJ))
+    w.dg_time_derivative(0.0)
+    ut_cons = np.array(o.array("Ut"))
+    assert np.max(np.abs(ut_cons - ut_cut)) <= 1e-12 * np.max(np.abs(ut_cut))
+    w.close()
+    # (b) curved: the integral of J*U_t over each element is that of the unfiltered J*U_t
+    spec = BoxSpec((2, 2, 2), x0=(-1.0, -1.0, -1.0), length=(2.0, 2.0, 2.0), ngeo=2, deform=0.1)
+    ranks, w = world(spec, N, node, eqn)
+    r, o = ranks[0], w.ranks[0]
+    U = r.eqn.smooth_state(r.mesh.Elem_xGP, length=2.0)
+    w.set_state([U])
+    w.dg_time_derivative(0.0)
+    ut_plain = np.array(o.array("Ut"))
+    vd, vu, sjnu = B.overintegration_cons(N, node, NU, r.mesh.sJ)
+    o.set_overintegration_cons(NU, vd, vu, sjnu)
+    w.dg_time_derivative(0.0)
+    ut_cons = np.array(o.array("Ut"))
+    assert np.max(np.abs(ut_cons - ut_plain)) > 1e-6 * np.max(np.abs(ut_plain))
+    # J*U_t of the filtered operator on NUnder is U_loc/sJNUnder; its NUnder-quadrature equals the N-quadrature of the unfiltered J*U_t
+    _, w_n, _ = B.get_nodes_and_weights(N, node)
+    _, w_u, _ = B.get_nodes_and_weights(NU, node)
+    ju_n = ut_plain / r.mesh.sJ[..., None]
+    int_n = np.einsum("ekjiv,k,j,i->ev", ju_n, w_n, w_n, w_n)
+    ut_u = np.einsum("li,mj,nk,ekjiv->enmlv", vd, vd, vd, ut_cons)  # the filtered U_t lives in the NUnder space: exact restriction
+    int_u = np.einsum("ekjiv,ekji,k,j,i->ev", ut_u, 1.0 / sjnu, w_u, w_u, w_u)
+    assert np.max(np.abs(int_u - int_n)) <= 1e-11 * np.max(np.abs(int_n))
+    o.set_overintegration_cons(-1)
+    w.dg_time_derivative(0.0)
+    assert np.array_equal(np.array(o.array("Ut")), ut_plain)
+    w.close()
