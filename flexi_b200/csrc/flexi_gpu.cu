@@ -112,6 +112,8 @@ struct flexi_gpu_handle {
   double *JaF = nullptr, *JaS = nullptr;  // Ja_Face / Ja_slave [s][9][NP2]
   double* filtMat = nullptr;              // OverintegrationMat [out][in] (allocated on first use)
   bool filtOn = false;                    // OverintegrationType == cutoff
+  double *filtDown = nullptr, *filtUp = nullptr, *sJNU = nullptr;  // conservative cut-off: padded Vdm_N_NUnder, Vdm_NUnder_N, sJNUnder
+  bool filtCons = false;
   double* filtUMat = nullptr;             // FilterMat [out][in] of the solution filter (FilterType cutoff / modal)
   bool filtUOn = false;
   int32_t* spIdx = nullptr;               // Sponge: element -> index in the sponge list (-1 = none); nullptr = doSponge off
@@ -407,7 +409,9 @@ int launch_update(H* h, const int32_t* list, int n, int mode, double rkA, double
   a.b_dt = b_dt;
   a.entropy = h->entropy ? 1 : 0;
   a.q = h->q;
-  a.filt = h->filtOn ? h->filtMat : nullptr;
+  a.filt = h->filtCons ? h->filtDown : h->filtOn ? h->filtMat : nullptr;
+  a.filt2 = h->filtCons ? h->filtUp : nullptr;
+  a.sJNU = h->filtCons ? h->sJNU : nullptr;
   a.spIdx = h->spOn ? h->spIdx : nullptr;
   a.spMat = h->spMat;
   a.spBase = h->spBase;
@@ -1250,11 +1254,12 @@ int flexi_gpu_set_face_metrics(flexi_gpu_handle* h, const double* Ja_Face, const
 int flexi_gpu_set_overintegration(flexi_gpu_handle* h, int overintegrationType, const double* OverintegrationMat) {
   ENTER(h);
   if (overintegrationType == 0) {
-    h->filtOn = false;
+    h->filtOn = h->filtCons = false;
     return 0;
   }
   if (overintegrationType != 1)
-    return fail(FLEXI_GPU_ERR_UNSUPPORTED, "OverintegrationType %d is not implemented (0 = none, 1 = cutoff are)", overintegrationType);
+    return fail(FLEXI_GPU_ERR_UNSUPPORTED, "OverintegrationType %d through this entry (0 = none, 1 = cutoff; 2 = conservative cut-off: flexi_gpu_set_overintegration_cons)", overintegrationType);
+  h->filtCons = false;
   if (!OverintegrationMat) return fail(FLEXI_GPU_ERR_ARG, "null argument");
   const int np = h->N + 1;
   std::vector<double> m((size_t)np * np);
@@ -1263,6 +1268,37 @@ int flexi_gpu_set_overintegration(flexi_gpu_handle* h, int overintegrationType, 
   if (!h->filtMat) CKR(dalloc(h, &h->filtMat, m.size()));
   CK(cudaMemcpy(h->filtMat, m.data(), m.size() * 8, cudaMemcpyHostToDevice));
   h->filtOn = true;
+  return 0;
+}
+
+int flexi_gpu_set_overintegration_cons(flexi_gpu_handle* h, int32_t NUnder, const double* Vdm_N_NUnder, const double* Vdm_NUnder_N, const double* sJNUnder) {
+  ENTER(h);
+  if (NUnder < 0) {
+    h->filtCons = false;
+    return 0;
+  }
+  const int np = h->N + 1, nu = NUnder + 1;
+  if (NUnder >= h->N) return fail(FLEXI_GPU_ERR_ARG, "NUnder %d >= N %d: the reference switches overintegration off (overintegration.f90:136-139)", NUnder, h->N);
+  if (!Vdm_N_NUnder || !Vdm_NUnder_N || !sJNUnder) return fail(FLEXI_GPU_ERR_ARG, "null argument");
+  // pad to NP x NP [out][in]: Vdm_N_NUnder(0:NUnder,0:N) -> rows > NUnder zero; Vdm_NUnder_N(0:N,0:NUnder) -> columns > NUnder zero
+  std::vector<double> dn((size_t)np * np, 0.), up((size_t)np * np, 0.);
+  for (int o = 0; o < nu; ++o)
+    for (int i = 0; i < np; ++i) dn[(size_t)o * np + i] = Vdm_N_NUnder[o + (size_t)nu * i];
+  for (int o = 0; o < np; ++o)
+    for (int i = 0; i < nu; ++i) up[(size_t)o * np + i] = Vdm_NUnder_N[o + (size_t)np * i];
+  std::vector<double> sj((size_t)h->nElems * h->np3, 0.);
+  for (int e = 0; e < h->nElems; ++e)
+    for (int k = 0; k < nu; ++k)
+      for (int j = 0; j < nu; ++j)
+        for (int i = 0; i < nu; ++i) sj[(size_t)e * h->np3 + i + np * (j + np * k)] = sJNUnder[(((size_t)e * nu + k) * nu + j) * nu + i];
+  if (!h->filtDown) CKR(dalloc(h, &h->filtDown, dn.size()));
+  if (!h->filtUp) CKR(dalloc(h, &h->filtUp, up.size()));
+  if (!h->sJNU) CKR(dalloc(h, &h->sJNU, sj.size()));
+  CK(cudaMemcpy(h->filtDown, dn.data(), dn.size() * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->filtUp, up.data(), up.size() * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->sJNU, sj.data(), sj.size() * 8, cudaMemcpyHostToDevice));
+  h->filtCons = true;
+  h->filtOn = false;
   return 0;
 }
 

@@ -73,6 +73,10 @@ struct UpdArgs {
   const double* xGP;  // Elem_xGP as [e][3][NP3]
   double t, srcOmega, srcA, srcTmp[6];
   const double* filt;  // OverintegrationMat as [out][in], NP*NP doubles; nullptr = OverintegrationType 0 (k_update<.,.,.,true> reads it)
+  // OVERINTEGRATIONTYPE_CONSCUTOFF (overintegration.f90:181-330): filt = Vdm_N_NUnder and filt2 = Vdm_NUnder_N, both padded with
+  // zeros to NP x NP [out][in]; sJNU = sJNUnder padded to [e][NP3] (zero outside the NUnder cube); nullptr = plain cut-off
+  const double* filt2;
+  const double* sJNU;
   // Sponge(Ut), sponge.f90:612-678: spIdx[e] = index of element e in the sponge list or -1 (nullptr = doSponge off),
   // spMat [iSponge][NP3] (SpongeMat, pre-multiplied by the Jacobian), spBase [e][5][NP3] (SpBaseFlow)
   const int32_t* spIdx;
@@ -820,26 +824,40 @@ __global__ void __launch_bounds__(Dim<NP>::NP3) k_update(UpdArgs A) {
       for (int v = 0; v < 5; ++v) w[v] = w[v] - sp[v];
     }
     // three 1-D sweeps through the 5 shared planes; sums start from zero and run over ascending input index (changeBasis.t90)
+    auto sweep3 = [&](const double* mat) {
 #pragma unroll
-    for (int dir = 0; dir < 3; ++dir) {
-      const int me = (dir == 0) ? i : (dir == 1) ? j : k;
-      const int stride = (dir == 0) ? 1 : (dir == 1) ? NP : D::NP2;
-      const int base = n - me * stride;
+      for (int dir = 0; dir < 3; ++dir) {
+        const int me = (dir == 0) ? i : (dir == 1) ? j : k;
+        const int stride = (dir == 0) ? 1 : (dir == 1) ? NP : D::NP2;
+        const int base = n - me * stride;
 #pragma unroll
-      for (int v = 0; v < 5; ++v) sU[v * D::NP3 + n] = w[v];
-      __syncthreads();
-      const double* row = A.filt + me * NP;
+        for (int v = 0; v < 5; ++v) sU[v * D::NP3 + n] = w[v];
+        __syncthreads();
+        const double* row = mat + me * NP;
 #pragma unroll
-      for (int v = 0; v < 5; ++v) {
-        double acc = 0.;
+        for (int v = 0; v < 5; ++v) {
+          double acc = 0.;
 #pragma unroll
-        for (int l = 0; l < NP; ++l) acc = acc + __ldg(row + l) * sU[v * D::NP3 + base + l * stride];
-        w[v] = acc;
+          for (int l = 0; l < NP; ++l) acc = acc + __ldg(row + l) * sU[v * D::NP3 + base + l * stride];
+          w[v] = acc;
+        }
+        __syncthreads();  // every read of this sweep is done before the planes are overwritten (next sweep / new state below)
       }
-      __syncthreads();  // every read of this sweep is done before the planes are overwritten (next sweep / new state below)
-    }
+    };
+    sweep3(A.filt);
+    if (A.filt2) {
+      // conservative cut-off: JU_t projected to NUnder (the padded rows give zero), times sJNUnder, interpolated back to N; the
+      // Jacobian has been applied on NUnder, ApplyJacobianCons is skipped (dg.f90:664-668)
+      const double sj = A.sJNU[(size_t)e * D::NP3 + n];
 #pragma unroll
-    for (int v = 0; v < 5; ++v) ut[v] = w[v] * sJ;  // ApplyJacobianCons, dg.f90:672
+      for (int v = 0; v < 5; ++v) w[v] = w[v] * sj;
+      sweep3(A.filt2);
+#pragma unroll
+      for (int v = 0; v < 5; ++v) ut[v] = w[v];
+    } else {
+#pragma unroll
+      for (int v = 0; v < 5; ++v) ut[v] = w[v] * sJ;  // ApplyJacobianCons, dg.f90:672
+    }
   } else if (A.doSource) {  // Ut = -Ut; Ut += src/sJ; Ut *= sJ  (dg.f90:656-675, exactfunc.f90:809-813)
     const double* x = A.xGP + (size_t)e * 3 * D::NP3 + n;
     const double arg = A.srcOmega * (x[0] + x[D::NP3] + x[2 * D::NP3]) - A.srcA * A.t;

@@ -31,7 +31,7 @@ KERNEL_CLASSES = ("volume", "flux", "update", "prolong", "calc_timestep", "layou
 EXPORTS = ("flexi_gpu_last_error", "flexi_gpu_abi_version", "flexi_gpu_nccl_unique_id", "flexi_gpu_init", "flexi_gpu_finalize",
            "flexi_gpu_set_state", "flexi_gpu_get_state", "flexi_gpu_dg_time_derivative", "flexi_gpu_timestep",
            "flexi_gpu_timestep_n", "flexi_gpu_calc_timestep", "flexi_gpu_get_array", "flexi_gpu_keep_gradients",
-           "flexi_gpu_prolong_to_face", "flexi_gpu_surf_int", "flexi_gpu_analyze_tgv", "flexi_gpu_calc_error_norms", "flexi_gpu_calc_body_forces", "flexi_gpu_set_face_metrics", "flexi_gpu_set_overintegration", "flexi_gpu_set_filter", "flexi_gpu_set_sponge", "flexi_gpu_set_viscosity", "flexi_gpu_pin_host_array", "flexi_gpu_unpin_host_array", "flexi_gpu_counters", "flexi_gpu_kernel_times",
+           "flexi_gpu_prolong_to_face", "flexi_gpu_surf_int", "flexi_gpu_analyze_tgv", "flexi_gpu_calc_error_norms", "flexi_gpu_calc_body_forces", "flexi_gpu_set_face_metrics", "flexi_gpu_set_overintegration", "flexi_gpu_set_overintegration_cons", "flexi_gpu_set_filter", "flexi_gpu_set_sponge", "flexi_gpu_set_viscosity", "flexi_gpu_pin_host_array", "flexi_gpu_unpin_host_array", "flexi_gpu_counters", "flexi_gpu_kernel_times",
            "flexi_gpu_set_profiling", "flexi_gpu_synchronize", "flexi_gpu_stream")
 
 
@@ -76,6 +76,7 @@ def lib():
     L.flexi_gpu_set_face_metrics.argtypes = [P, PD, PD]
     L.flexi_gpu_set_overintegration.argtypes = [P, C.c_int, PD]
     L.flexi_gpu_set_filter.argtypes = [P, C.c_int, PD]
+    L.flexi_gpu_set_overintegration_cons.argtypes = [P, I32, PD, PD, PD]
     L.flexi_gpu_set_sponge.argtypes = [P, I32, C.POINTER(C.c_int32), PD, PD]
     L.flexi_gpu_set_viscosity.argtypes = [P, I32, C.c_double, C.c_double, C.c_double, C.c_double]
     L.flexi_gpu_pin_host_array.argtypes = [P, C.c_int64]
@@ -205,6 +206,17 @@ class FlexiGpu:
         """FilterType (0 none, 1 cutoff, 2 modal) and FilterMat[out, in]; U is filtered at the start of every DG operator call."""
         m = None if mat is None else np.asfortranarray(mat, dtype=np.float64)
         self._ck(self.L.flexi_gpu_set_filter(self.h, int(ftype), None if m is None else _pd(m)))
+
+    def set_overintegration_cons(self, n_under=-1, vdm_n_nunder=None, vdm_nunder_n=None, sj_nunder=None):
+        """OverintegrationType 2 (conservative cut-off): Vdm_N_NUnder [NUnder+1, N+1], Vdm_NUnder_N [N+1, NUnder+1],
+        sJNUnder [nElems, kU, jU, iU]; n_under < 0 = off."""
+        if n_under < 0:
+            self._ck(self.L.flexi_gpu_set_overintegration_cons(self.h, -1, None, None, None))
+            return
+        a = np.asfortranarray(vdm_n_nunder, dtype=np.float64)
+        b = np.asfortranarray(vdm_nunder_n, dtype=np.float64)
+        c = np.ascontiguousarray(sj_nunder, dtype=np.float64)
+        self._ck(self.L.flexi_gpu_set_overintegration_cons(self.h, int(n_under), _pd(a), _pd(b), _pd(c)))
 
     def set_viscosity(self, visc_type=0, Ts=0.0, Tref=1.0, ExpoSuth=0.0, cSuth=0.0):
         """PP_VISC (0 constant, 1 Sutherland, 2 power law) with the MOD_EOS_Vars values after InitEos (see sutherland_params)."""

@@ -272,6 +272,12 @@ int flexi_gpu_set_face_metrics(flexi_gpu_handle* h, const double* Ja_Face, const
  * the update kernel.  2 (conservative cut-off, needs sJNUnder) returns FLEXI_GPU_ERR_UNSUPPORTED.  The initial Overintegration(U)
  * of timedisc.f90:117-122 and the CFL/DFL scaling for NUnder (timedisc_func.f90:142) stay with the host. */
 int flexi_gpu_set_overintegration(flexi_gpu_handle* h, int overintegrationType, const double* OverintegrationMat);
+/* OverintegrationType = 2, conservative cut-off (dg/overintegration.f90:118-135,181-330; dg.f90:664-668): JU_t is projected from N to
+ * NUnder, multiplied by sJNUnder and interpolated back inside the update kernel; ApplyJacobian is skipped.  Pass what
+ * InitOverintegration built: Vdm_N_NUnder(0:NUnder,0:N), Vdm_NUnder_N(0:N,0:NUnder), sJNUnder(0:NUnder,0:NUnder,0:NUnder,nElems).
+ * NUnder < 0 switches it off.  The initial ApplyJacobianCons + Overintegration(U) of timedisc.f90:119-122 stays in the host. */
+int flexi_gpu_set_overintegration_cons(flexi_gpu_handle* h, int32_t NUnder, const double* Vdm_N_NUnder, const double* Vdm_NUnder_N,
+                                       const double* sJNUnder);
 
 /* Solution filter (MOD_Filter, filter/filter.f90:67-72,135-196,264-288; dg.f90:329-330): filterType 0 = none, 1 = cutoff,
  * 2 = modal (Hesthaven) -- both apply the host's FilterMat (0:N,0:N) (Fortran order) to U in place at the start of every DG

@@ -286,3 +286,57 @@ def test_viscosity_laws_match_oracle(N, node, eqn, walls, visc):
     finally:
         g.close()
         w.close()
+
+
+@pytest.mark.parametrize("N,NU,node,eqn", [
+    (7, 4, GL, dict(parabolic=True, split_dg=True, split_dg_type="pi", riemann="lf", mu0=1e-2)),
+    (5, 3, G, dict(parabolic=True, riemann="roe", mu0=1e-2)),
+    (4, 2, GL, dict(parabolic=False, riemann="hllc")),
+], ids=["N7-GL-split", "N5-G-weak", "N4-GL-euler"])
+def test_overintegration_conservative_cutoff_matches_oracle(N, NU, node, eqn):
+    """OverintegrationType = 2 (flexi_gpu_set_overintegration_cons; overintegration.f90:181-330, dg.f90:664-668): projection to NUnder,
+    Jacobian on NUnder, interpolation back inside the update kernel, no ApplyJacobian: one operator evaluation and 2 LSERK steps on the
+    curved mesh; the plain cut-off and 'off' still work afterwards."""
+    r = build_case(BoxSpec((3, 2, 2), **CURVED), N, node, eqn)[0]
+    U0 = r.eqn.smooth_state(r.mesh.Elem_xGP, length=2.0)
+    vd, vu, sjnu = B.overintegration_cons(N, node, NU, r.mesh.sJ)
+    w = O.OracleWorld([(r.desc, r.keep)])
+    o = w.ranks[0]
+    w.set_state([U0])
+    g = FlexiGpu(r)
+    try:
+        g.set_state(U0)
+        w.dg_time_derivative(0.0)
+        plain = np.array(o.array("Ut"))
+        o.set_overintegration_cons(NU, vd, vu, sjnu)
+        g.set_overintegration_cons(NU, vd, vu, sjnu)
+        w.dg_time_derivative(0.0)
+        ut, ref = g.DGTimeDerivative_weakForm(0.0), o.array("Ut")
+        scale = np.max(np.abs(ref).reshape(-1, 5), axis=0)
+        assert np.all(np.max(np.abs(ut - ref).reshape(-1, 5), axis=0) <= 1e-12 * scale)
+        assert np.max(np.abs(ref - plain)) > 1e-6 * np.max(np.abs(plain))
+        t = 0.0
+        for _ in range(2):
+            dt = w.calc_timestep()[0]
+            w.timestep(t, dt)
+            g.TimeStep(t, dt)
+            t += dt
+        Ug, Uo = g.get_state(), o.array("U")
+        sc = np.max(np.abs(Uo).reshape(-1, 5), axis=0)
+        assert np.all(np.max(np.abs(Ug - Uo).reshape(-1, 5), axis=0) <= 1e-12 * sc)
+        # back to the plain cut-off, then off
+        mat = B.overintegration_mat(r.basis.xGP, NU)
+        o.set_overintegration_cons(-1)
+        o.set_overintegration(1, mat)
+        g.set_overintegration(1, mat)
+        g.set_state(U0)
+        w.set_state([U0])
+        w.dg_time_derivative(0.0)
+        ut, ref = g.DGTimeDerivative_weakForm(0.0), o.array("Ut")
+        assert np.all(np.max(np.abs(ut - ref).reshape(-1, 5), axis=0) <= 1e-12 * np.max(np.abs(ref).reshape(-1, 5), axis=0))
+        g.set_overintegration(0)
+        ut0 = g.DGTimeDerivative_weakForm(0.0)
+        assert np.all(np.max(np.abs(ut0 - plain).reshape(-1, 5), axis=0) <= 1e-12 * np.max(np.abs(plain).reshape(-1, 5), axis=0))
+    finally:
+        g.close()
+        w.close()
