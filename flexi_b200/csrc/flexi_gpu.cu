@@ -229,6 +229,18 @@ int download_aos(H* h, const double* dev, double* host, int nv, int npts, long n
   return 0;
 }
 
+// Ja_Face / Ja_slave (descriptor, ABI 2, or flexi_gpu_set_face_metrics): Fortran (dd,c,p,q,side) -> [side][dd + 3*c][NP2]
+int upload_face_metrics(flexi_gpu_handle* h, const double* Ja_Face, const double* Ja_slave) {
+  const size_t n = (size_t)h->nSides * 9 * h->np2;
+  if (!h->JaF) {
+    CKR(dalloc(h, &h->JaF, n));
+    CKR(dalloc(h, &h->JaS, n));
+  }
+  CKR(upload_aos(h, Ja_Face, h->JaF, 9, h->np2, h->nSides));  // Fortran (dd,c,p,q,side): plane dd + 3*c
+  CKR(upload_aos(h, Ja_slave, h->JaS, 9, h->np2, h->nSides));
+  return 0;
+}
+
 // ---- halo exchange: contiguous side slices per neighbour rank (mpi.f90:269-314) --------------------------------------------
 // One message set: array, doubles per side, direction.  sendMine: send my MINE slices and receive into my YOUR slices (SendID=1,
 // master -> slave); otherwise the other direction.  All sets of one exchange go into ONE NCCL group (one kernel on the wire).
@@ -445,7 +457,7 @@ int launch_bc(H* h, bool pre, double t) {
 // filter of dg.f90:329-330 -- applied in place, and not idempotent for FilterType = modal -- is skipped.
 int rhs(H* h, double t, int mode, double rkA, double b_dt, bool applyFilter = true) {
   if (h->bcTablesMissing) return fail(FLEXI_GPU_ERR_ARG, "BC sides without BC / BoundaryType tables");
-  if (h->entropy && !h->JaF) return fail(FLEXI_GPU_ERR_ARG, "split form on Gauss nodes: call flexi_gpu_set_face_metrics (Ja_Face, Ja_slave) first");
+  if (h->entropy && !h->JaF) return fail(FLEXI_GPU_ERR_ARG, "split form on Gauss nodes: the descriptor carries no Ja_Face / Ja_slave and flexi_gpu_set_face_metrics was not called");
   h->lastT = t;
   if (h->filtUOn && applyFilter) {  // dg.f90:329-330: IF(FilterType.GT.0) CALL Filter_Pointer(U,FilterMat) -- in place, then everything reads the filtered U
     FiltArgs fa{};
@@ -925,6 +937,7 @@ static int init_impl(const flexi_gpu_desc* d, H* h) {
   } else if (h->nMINE + h->nYOUR > 0) {
     return fail(FLEXI_GPU_ERR_ARG, "MPI sides present but nProcs == 1");
   }
+  if (d->Ja_Face && d->Ja_slave) CKR(upload_face_metrics(h, d->Ja_Face, d->Ja_slave));  // ABI 2; split form on Gauss nodes reads them
   CK(cudaStreamSynchronize(h->sc));
   CK(cudaDeviceSynchronize());
   return 0;
@@ -1238,17 +1251,11 @@ int flexi_gpu_calc_body_forces(flexi_gpu_handle* h, const double* wGPSurf, const
   return 0;
 }
 
+// kept next to the descriptor fields Ja_Face / Ja_slave (ABI 2) for hosts that build the face metrics after flexi_gpu_init
 int flexi_gpu_set_face_metrics(flexi_gpu_handle* h, const double* Ja_Face, const double* Ja_slave) {
   ENTER(h);
   if (!Ja_Face || !Ja_slave) return fail(FLEXI_GPU_ERR_ARG, "null argument");
-  const size_t n = (size_t)h->nSides * 9 * h->np2;
-  if (!h->JaF) {
-    CKR(dalloc(h, &h->JaF, n));
-    CKR(dalloc(h, &h->JaS, n));
-  }
-  CKR(upload_aos(h, Ja_Face, h->JaF, 9, h->np2, h->nSides));  // Fortran (dd,c,p,q,side): plane dd + 3*c
-  CKR(upload_aos(h, Ja_slave, h->JaS, 9, h->np2, h->nSides));
-  return 0;
+  return upload_face_metrics(h, Ja_Face, Ja_slave);
 }
 
 int flexi_gpu_set_overintegration(flexi_gpu_handle* h, int overintegrationType, const double* OverintegrationMat) {
@@ -1386,10 +1393,14 @@ int flexi_gpu_prolong_to_face(flexi_gpu_handle* h, const double* Uvol, double* U
   if (!Uvol || !Uface_master || !Uface_slave) return fail(FLEXI_GPU_ERR_ARG, "null argument");
   const size_t nV = (size_t)h->nElems * 5 * h->np3, nF = (size_t)h->nSides * 5 * h->np2;
   double *dV = nullptr, *dM = nullptr, *dS = nullptr;
-  CK(cudaMalloc((void**)&dV, nV * 8));
-  CK(cudaMalloc((void**)&dM, nF * 8));
-  CK(cudaMalloc((void**)&dS, nF * 8));
-  int r = upload_aos(h, Uvol, dV, 5, h->np3, h->nElems);
+  // the temporaries are freed on every path below: a failed allocation does not return before the ones that succeeded are released
+  int r = 0;
+  if (cudaMalloc((void**)&dV, nV * 8) != cudaSuccess || cudaMalloc((void**)&dM, nF * 8) != cudaSuccess ||
+      cudaMalloc((void**)&dS, nF * 8) != cudaSuccess) {
+    cudaGetLastError();
+    r = fail(FLEXI_GPU_ERR_CUDA, "cudaMalloc of the temporaries (%zu + 2 x %zu bytes) failed", nV * 8, nF * 8);
+  }
+  if (!r) r = upload_aos(h, Uvol, dV, 5, h->np3, h->nElems);
   if (!r) r = upload_aos(h, Uface_master, dM, 5, h->np2, h->nSides);
   if (!r) r = upload_aos(h, Uface_slave, dS, 5, h->np2, h->nSides);
   if (!r) {
@@ -1419,10 +1430,14 @@ int flexi_gpu_surf_int(flexi_gpu_handle* h, const double* Flux_master, const dou
   if (!Flux_master || !Flux_slave || !Ut) return fail(FLEXI_GPU_ERR_ARG, "null argument");
   const size_t nV = (size_t)h->nElems * 5 * h->np3, nF = (size_t)h->nSides * 5 * h->np2;
   double *dV = nullptr, *dM = nullptr, *dS = nullptr;
-  CK(cudaMalloc((void**)&dV, nV * 8));
-  CK(cudaMalloc((void**)&dM, nF * 8));
-  CK(cudaMalloc((void**)&dS, nF * 8));
-  int r = upload_aos(h, Ut, dV, 5, h->np3, h->nElems);
+  // the temporaries are freed on every path below: a failed allocation does not return before the ones that succeeded are released
+  int r = 0;
+  if (cudaMalloc((void**)&dV, nV * 8) != cudaSuccess || cudaMalloc((void**)&dM, nF * 8) != cudaSuccess ||
+      cudaMalloc((void**)&dS, nF * 8) != cudaSuccess) {
+    cudaGetLastError();
+    r = fail(FLEXI_GPU_ERR_CUDA, "cudaMalloc of the temporaries (%zu + 2 x %zu bytes) failed", nV * 8, nF * 8);
+  }
+  if (!r) r = upload_aos(h, Ut, dV, 5, h->np3, h->nElems);
   if (!r) r = upload_aos(h, Flux_master, dM, 5, h->np2, h->nSides);
   if (!r) r = upload_aos(h, Flux_slave, dS, 5, h->np2, h->nSides);
   if (!r) {

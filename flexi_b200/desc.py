@@ -6,7 +6,7 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 NODETYPE = {"gauss": 1, "gauss-lobatto": 2}
 RIEMANN = {"same": -1, "lf": 1, "hllc": 2, "roe": 3, "roel2": 32, "roeentropyfix": 33, "hll": 4, "hlle": 5, "hllem": 6,
            "average": 0, "ch": 7, "ir": 8}  # the last three: SPLIT_DG builds only (riemann.f90:54-58)
@@ -28,6 +28,7 @@ class FlexiGpuDesc(C.Structure):
         ("nMPISides_MINE", C.c_int32), ("nMPISides_YOUR", C.c_int32),
         ("Metrics_fTilde", _PD), ("Metrics_gTilde", _PD), ("Metrics_hTilde", _PD), ("sJ", _PD), ("Elem_xGP", _PD),
         ("NormVec", _PD), ("TangVec1", _PD), ("TangVec2", _PD), ("SurfElem", _PD), ("Face_xGP", _PD),
+        ("Ja_Face", _PD), ("Ja_slave", _PD),
         ("SideToElem", _PI), ("ElemToSide", _PI), ("S2V2", _PI), ("BC", _PI),
         ("nBCs", C.c_int32), ("BoundaryType", _PI), ("nRefState", C.c_int32), ("RefStatePrim", _PD),
         ("xGP", _PD), ("wGP", _PD), ("D", _PD), ("D_T", _PD), ("D_Hat_T", _PD), ("DVolSurf", _PD),
@@ -104,6 +105,10 @@ def make_desc(mesh, basis, eqn, S2V2, nccl_id=None, device=0):
     d.TangVec2 = pd(mesh.TangVec2)
     d.SurfElem = pd(mesh.SurfElem)
     d.Face_xGP = pd(mesh.Face_xGP)
+    # only the split form on Gauss nodes reads the face metrics; the host mesh builds them on request (with_ja_face)
+    ja = hasattr(mesh, "Ja_Face") and hasattr(mesh, "Ja_slave")  # numpy [side, q, p, c, dd] == Fortran (dd,c,p,q,side)
+    d.Ja_Face = pd(mesh.Ja_Face) if ja else None
+    d.Ja_slave = pd(mesh.Ja_slave) if ja else None
     d.SideToElem = pi(mesh.SideToElem)
     d.ElemToSide = pi(mesh.ElemToSide)
     # numpy S2V2[c,p,q,f,s] -> Fortran memory (c fastest)

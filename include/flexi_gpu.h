@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define FLEXI_GPU_ABI_VERSION 1
+#define FLEXI_GPU_ABI_VERSION 2
 
 /* PP_NodeType (src/CMakeLists.txt) */
 #define FLEXI_NODETYPE_GAUSS 1
@@ -107,6 +107,10 @@ typedef struct flexi_gpu_desc {
   const double* TangVec2;
   const double* SurfElem; /* (0:N,0:N,nSides) */
   const double* Face_xGP; /* (3,0:N,0:N,nSides); may be NULL without BCs */
+  /* ABI 2: Ja_Face / Ja_slave (3,3,0:N,0:N,nSides) of MOD_Mesh_Vars (mesh/metrics.f90:681-705), read by the split form on Gauss
+   * nodes only (surfint.t90:90-137); NULL otherwise (or hand them over later with flexi_gpu_set_face_metrics) */
+  const double* Ja_Face;
+  const double* Ja_slave;
   /* ---- connectivity, mesh_vars.f90:85-119 ---- */
   const int32_t* SideToElem; /* (5,nSides), 1-based ids, -1 = absent, flexi.h:98-102 */
   const int32_t* ElemToSide; /* (2,6,nElems), flexi.h:105-106 */

@@ -2035,6 +2035,13 @@ oracle* oracle_create(const flexi_gpu_desc* d) {
   o->d.TangVec2 = (const double*)own_copy(o, d->TangVec2, nsid * 3 * 8);
   o->d.SurfElem = (const double*)own_copy(o, d->SurfElem, nsid * 8);
   o->d.Face_xGP = (const double*)own_copy(o, d->Face_xGP, nsid * 3 * 8);
+  o->d.Ja_Face = o->d.Ja_slave = NULL; /* the oracle keeps its own (freeable) copies, see oracle_set_face_metrics */
+  if (d->Ja_Face && d->Ja_slave) {
+    o->Ja_Face = (double*)xcalloc(nsid * 9, 8);
+    o->Ja_slave = (double*)xcalloc(nsid * 9, 8);
+    memcpy(o->Ja_Face, d->Ja_Face, nsid * 9 * 8);
+    memcpy(o->Ja_slave, d->Ja_slave, nsid * 9 * 8);
+  }
   o->d.SideToElem = (const int32_t*)own_copy(o, d->SideToElem, (size_t)d->nSides * 5 * 4);
   o->d.ElemToSide = (const int32_t*)own_copy(o, d->ElemToSide, (size_t)d->nElems * 12 * 4);
   o->d.S2V2 = (const int32_t*)own_copy(o, d->S2V2, (size_t)2 * np * np * 5 * 6 * 4);
@@ -2103,8 +2110,8 @@ oracle* oracle_create(const flexi_gpu_desc* d) {
   return o;
 }
 
-/* Ja_Face / Ja_slave (3,3,0:N,0:N,nSides) of MOD_Mesh_Vars (metrics.f90:681-705): only the split form on Gauss nodes reads them; like
- * the GPU library (flexi_gpu_set_face_metrics) the oracle takes them through an extra entry, the descriptor does not carry them. */
+/* Ja_Face / Ja_slave (3,3,0:N,0:N,nSides) of MOD_Mesh_Vars (metrics.f90:681-705): only the split form on Gauss nodes reads them; they
+ * come with the descriptor (ABI 2, copied in oracle_create) or, like in the GPU library, through this extra entry. */
 void oracle_set_face_metrics(oracle* o, const double* Ja_Face, const double* Ja_slave) {
   const size_t n = (size_t)o->d.nSides * o->np * o->np * 9;
   free(o->Ja_Face);

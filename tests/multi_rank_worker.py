@@ -134,11 +134,12 @@ def main():
             o = w.ranks[rank]
             gsc = max(np.max(np.abs(o.array(n))) for n in ("gradUx", "gradUy", "gradUz"))
             lo, hi = m.nBCSides, m.firstMPISide_YOUR - 1  # slave arrays of inner + MPI_MINE sides (0-based [lo, hi))
+            gtol = 1e-11 if case == "naca" else 1e-12  # naca: 1/J of the wall layer amplifies the round-off of the lifting (see ptol)
             for name in ("gradUx_slave", "gradUy_slave", "gradUz_slave"):
-                assert np.max(np.abs(g.get_array(name)[lo:hi] - o.array(name)[lo:hi])) <= 1e-12 * gsc, name
+                assert np.max(np.abs(g.get_array(name)[lo:hi] - o.array(name)[lo:hi])) <= gtol * gsc, name
             hi_m = m.lastMPISide_MINE
             for name in ("gradUx_master", "gradUy_master", "gradUz_master"):
-                assert np.max(np.abs(g.get_array(name)[:hi_m] - o.array(name)[:hi_m])) <= 1e-12 * gsc, name
+                assert np.max(np.abs(g.get_array(name)[:hi_m] - o.array(name)[:hi_m])) <= gtol * gsc, name
         t = 0.0
         for _ in range(3):
             dt_o = w.calc_timestep()[0]
