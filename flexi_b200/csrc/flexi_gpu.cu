@@ -517,7 +517,10 @@ int rhs(H* h, double t, int mode, double rkA, double b_dt, bool applyFilter = tr
   CKR(launch_update(h, h->elemsInner, h->nElemsInner, mode, rkA, b_dt, t));
   CKR(finish_exchange(h, X_FLUX));
   CKR(launch_update(h, h->elemsBnd, h->nElemsBnd, mode, rkA, b_dt, t));
-  if (mode != 0) CKR(start_exchange(h, X_TRACE));  // traces of the updated state for the next stage
+  // traces of the updated state for the next stage -- unless the solution filter is on: the next operator evaluation filters U
+  // first and refreshes (and exchanges) the traces of the filtered state itself (refresh_traces)
+  if (mode != 0 && !h->filtUOn) CKR(start_exchange(h, X_TRACE));
+  if (mode != 0 && h->filtUOn) h->tracesValid = false;  // the halo traces of the new state were not exchanged
   return 0;
 }
 
@@ -1312,12 +1315,15 @@ int flexi_gpu_set_overintegration_cons(flexi_gpu_handle* h, int32_t NUnder, cons
 int flexi_gpu_set_filter(flexi_gpu_handle* h, int filterType, const double* FilterMat) {
   ENTER(h);
   if (filterType == 0) {
+    if (h->filtUOn) h->tracesValid = false;  // multi-rank: the stages did not exchange the traces while the filter was on
     h->filtUOn = false;
     return 0;
   }
   if (filterType != 1 && filterType != 2)
     return fail(FLEXI_GPU_ERR_UNSUPPORTED, "FilterType %d is not implemented (0 = none, 1 = cutoff, 2 = modal are)", filterType);
-  if (h->nProcs > 1) return fail(FLEXI_GPU_ERR_UNSUPPORTED, "the solution filter is single-rank so far (the trace exchange of the previous stage is still in flight when U is filtered)");
+  // multi-rank: an exchange of unfiltered traces may be in flight from the last stage; it has to land before the filtered traces
+  // are exchanged into the same slices (from here on the stages do not start it any more, see rhs())
+  if (h->nProcs > 1 && !h->filtUOn) CKR(finish_exchange(h, X_TRACE));
   if (!FilterMat) return fail(FLEXI_GPU_ERR_ARG, "null argument");
   const int np = h->N + 1;
   std::vector<double> m((size_t)np * np);

@@ -285,7 +285,8 @@ int flexi_gpu_set_overintegration_cons(flexi_gpu_handle* h, int32_t NUnder, cons
 
 /* Solution filter (MOD_Filter, filter/filter.f90:67-72,135-196,264-288; dg.f90:329-330): filterType 0 = none, 1 = cutoff,
  * 2 = modal (Hesthaven) -- both apply the host's FilterMat (0:N,0:N) (Fortran order) to U in place at the start of every DG
- * operator evaluation, as the reference does.  3 (LAF) and multi-rank runs return FLEXI_GPU_ERR_UNSUPPORTED. */
+ * operator evaluation, as the reference does.  3 (LAF) returns FLEXI_GPU_ERR_UNSUPPORTED.  On multi-rank runs the traces of
+ * the filtered state are prolonged and exchanged at the start of the evaluation (the stages then skip their own trace exchange). */
 int flexi_gpu_set_filter(flexi_gpu_handle* h, int filterType, const double* FilterMat);
 
 /* Viscosity law, the reference's build option FLEXI_VISCOSITY / PP_VISC (eos.h:73-87, viscosity.f90:57-90): 0 = constant mu0

@@ -40,6 +40,9 @@ CASES["splitCH"] = (5, B.NODE_GAUSS_LOBATTO, dict(parabolic=True, lifting=1, rie
                                                   ref_state_prim=[(1.0, 0.3, 0.0, 0.0, 0.71428571), (1.0, 0.0, 0.0, 0.0, 0.9)]))
 # BASELINE configs[3] proper: NACA0012-style O-mesh, every element in a random local frame, N=5, HLLC + BR2, wall + far field
 CASES["naca"] = (5, B.NODE_GAUSS, NACA_EQN)
+# the solution filter (FilterType = cutoff, dg.f90:329-330) on a partitioned run: the traces of the filtered state are exchanged at the
+# start of every operator evaluation
+CASES["splitfilt"] = CASES["split"]
 CASES["config4_unstr"] = CASES["config4"]
 CASES["split_unstr"] = CASES["split"]
 WALL_BC = {(1, -1): 1, (1, 1): 2, (0, -1): 3, (0, 1): 3}  # walls in y, far field in x, periodic in z
@@ -96,6 +99,10 @@ def main():
     if gauss_split:
         for r, o in zip(ranks, w.ranks):
             o.set_face_metrics(r.mesh.Ja_Face, r.mesh.Ja_slave)
+    filt = B.overintegration_mat(me.basis.xGP, N - 2) if case == "splitfilt" else None  # the cut-off FilterMat has this form
+    if filt is not None:
+        for o in w.ranks:
+            o.set_filter(1, filt)
     w.set_state(U0s)
     w.dg_time_derivative(0.0)
     ut_ref = w.ranks[rank].array("Ut").copy()
@@ -104,6 +111,8 @@ def main():
         w1 = O.OracleWorld([(one.desc, one.keep)])
         if gauss_split:
             w1.ranks[0].set_face_metrics(one.mesh.Ja_Face, one.mesh.Ja_slave)
+        if filt is not None:
+            w1.ranks[0].set_filter(1, filt)
         w1.set_state([smooth(one)])
         w1.dg_time_derivative(0.0)
         full = w1.ranks[0].array("Ut")
@@ -123,6 +132,8 @@ def main():
         g = G.FlexiGpu(me)
         if gauss_split:
             g.set_face_metrics(m.Ja_Face, m.Ja_slave)
+        if filt is not None:
+            g.set_filter(1, filt)
         g.set_state(U0s[rank])
         ut = g.DGTimeDerivative_weakForm(0.0)
         scale = np.max(np.abs(ut_ref).reshape(-1, 5), axis=0)
