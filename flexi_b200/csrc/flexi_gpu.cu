@@ -58,6 +58,7 @@ const NpOps* ops_for(int np) {
     case 8: return fx_ops_np8();
     case 9: return fx_ops_np9();
     case 10: return fx_ops_np10();
+    case 12: return fx_ops_np12();
     default: return nullptr;
   }
 }
@@ -116,6 +117,10 @@ struct flexi_gpu_handle {
   bool filtCons = false;
   double* filtUMat = nullptr;             // FilterMat [out][in] of the solution filter (FilterType cutoff / modal)
   bool filtUOn = false;
+  // FilterType 3 (LAF): IntegrationWeight [e][NP3] and the per-element state lim / eRatio / r / ekin_avg_old / ekin_fluc_avg_old
+  double *lafIW = nullptr, *lafState = nullptr;  // lafState = 5 arrays of nElems
+  double lafNormMod = 0., lafAlpha = 1.;
+  bool lafOn = false;
   int32_t* spIdx = nullptr;               // Sponge: element -> index in the sponge list (-1 = none); nullptr = doSponge off
   double *spMat = nullptr, *spBase = nullptr;
   bool spOn = false;
@@ -463,6 +468,16 @@ int rhs(H* h, double t, int mode, double rkA, double b_dt, bool applyFilter = tr
     FiltArgs fa{};
     fa.U = h->U;
     fa.mat = h->filtUMat;
+    if (h->lafOn) {
+      fa.iw = h->lafIW;
+      fa.lim = h->lafState;
+      fa.eRatio = h->lafState + (size_t)h->nElems;
+      fa.r = h->lafState + 2 * (size_t)h->nElems;
+      fa.ekinOld = h->lafState + 3 * (size_t)h->nElems;
+      fa.flucOld = h->lafState + 4 * (size_t)h->nElems;
+      fa.normMod = h->lafNormMod;
+      fa.alpha = h->lafAlpha;
+    }
     {
       Timer tm(h, KC_LAYOUT, h->sc);
       CK(h->ops->filter(fa, h->nElems, h->sc));
@@ -569,7 +584,9 @@ int flexi_gpu_finalize(flexi_gpu_handle* h) {
 }
 
 static int init_impl(const flexi_gpu_desc* d, H* h) {
-  if (d->N < 1 || d->N > 9) return fail(FLEXI_GPU_ERR_ARG, "N=%d outside 1..9", d->N);
+  // N = 1..9: one CTA per element; N = 11 (the degree of the reference's tgv/oInt regression check): a cluster of two CTAs per
+  // element (layout.cuh: Dim::PAIR).  N = 10 has an odd number of nodes per element and no instantiation.
+  if (d->N < 1 || (d->N > 9 && d->N != 11)) return fail(FLEXI_GPU_ERR_ARG, "N=%d is not instantiated (1..9 and 11 are)", d->N);
   if (d->nodeType != FLEXI_NODETYPE_GAUSS && d->nodeType != FLEXI_NODETYPE_GAUSS_LOBATTO) return fail(FLEXI_GPU_ERR_ARG, "bad nodeType %d", d->nodeType);
   if (d->doWeakLifting || d->doConservativeLifting) return fail(FLEXI_GPU_ERR_UNSUPPORTED, "only the strong, non-conservative lifting (the reference default, lifting.f90:72-76) is implemented");
   // split form on Gauss nodes (PP_EntropyVars = 1): implemented, but it needs Ja_Face / Ja_slave, which the descriptor does not
@@ -900,7 +917,7 @@ static int init_impl(const flexi_gpu_desc* d, H* h) {
       CK(cudaMemset(h->gs[dd], 0, nS * h->nvl * np2 * 8));
     }
     // the line-resident GL split kernel (even NP) talks to k_flux through n.F_v traces instead of gradient traces
-    h->vt = h->gl && h->split && (h->np % 2 == 0);
+    h->vt = h->gl && h->split && (h->np % 2 == 0) && h->np <= 10;  // N = 11 runs the generic element kernel (gradient traces)
     if (h->vt) {
       CKR(dalloc(h, &h->fvm, nS * 4 * np2));
       CKR(dalloc(h, &h->fvs, nS * 4 * np2));
@@ -1316,11 +1333,12 @@ int flexi_gpu_set_filter(flexi_gpu_handle* h, int filterType, const double* Filt
   ENTER(h);
   if (filterType == 0) {
     if (h->filtUOn) h->tracesValid = false;  // multi-rank: the stages did not exchange the traces while the filter was on
-    h->filtUOn = false;
+    h->filtUOn = h->lafOn = false;
     return 0;
   }
   if (filterType != 1 && filterType != 2)
-    return fail(FLEXI_GPU_ERR_UNSUPPORTED, "FilterType %d is not implemented (0 = none, 1 = cutoff, 2 = modal are)", filterType);
+    return fail(FLEXI_GPU_ERR_UNSUPPORTED, "FilterType %d through this entry (0 = none, 1 = cutoff, 2 = modal; 3 = LAF: flexi_gpu_set_filter_laf)", filterType);
+  h->lafOn = false;
   // multi-rank: an exchange of unfiltered traces may be in flight from the last stage; it has to land before the filtered traces
   // are exchanged into the same slices (from here on the stages do not start it any more, see rhs())
   if (h->nProcs > 1 && !h->filtUOn) CKR(finish_exchange(h, X_TRACE));
@@ -1332,6 +1350,44 @@ int flexi_gpu_set_filter(flexi_gpu_handle* h, int filterType, const double* Filt
   if (!h->filtUMat) CKR(dalloc(h, &h->filtUMat, m.size()));
   CK(cudaMemcpy(h->filtUMat, m.data(), m.size() * 8, cudaMemcpyHostToDevice));
   h->filtUOn = true;
+  return 0;
+}
+
+int flexi_gpu_set_filter_laf(flexi_gpu_handle* h, const double* FilterMat, const double* IntegrationWeight, double normMod, double LAF_alpha) {
+  ENTER(h);
+  if (!FilterMat || !IntegrationWeight) return fail(FLEXI_GPU_ERR_ARG, "null argument");
+  {  // the cut-off matrix of NFilter goes where the other filter types keep theirs (also finishes a trace exchange in flight)
+    const int r = flexi_gpu_set_filter(h, 1, FilterMat);
+    if (r) return r;
+  }
+  const size_t nE = (size_t)h->nElems;
+  if (!h->lafIW) {
+    CKR(dalloc(h, &h->lafIW, nE * h->np3));
+    CKR(dalloc(h, &h->lafState, 5 * nE));
+  }
+  CK(cudaMemcpy(h->lafIW, IntegrationWeight, nE * h->np3 * 8, cudaMemcpyHostToDevice));  // (0:N,0:N,0:N,nElems) == [e][NP3]
+  // InitFilter, filter.f90:184-188: lim = 1e-8, eRatio = 0, r = 0, ekin_avg_old = ekin_fluc_avg_old = 1e-16
+  std::vector<double> st(5 * nE, 0.);
+  for (size_t e = 0; e < nE; ++e) {
+    st[e] = 1E-8;
+    st[3 * nE + e] = 1.E-16;
+    st[4 * nE + e] = 1.E-16;
+  }
+  CK(cudaMemcpy(h->lafState, st.data(), st.size() * 8, cudaMemcpyHostToDevice));
+  h->lafNormMod = normMod;
+  h->lafAlpha = LAF_alpha;
+  h->lafOn = true;
+  return 0;
+}
+
+int flexi_gpu_get_filter_laf(flexi_gpu_handle* h, double* eRatio, double* lim, double* r) {
+  ENTER(h);
+  if (!h->lafOn) return fail(FLEXI_GPU_ERR_ARG, "the LAF filter is not active");
+  CK(cudaStreamSynchronize(h->sc));
+  const size_t nE = (size_t)h->nElems;
+  if (lim) CK(cudaMemcpy(lim, h->lafState, nE * 8, cudaMemcpyDeviceToHost));
+  if (eRatio) CK(cudaMemcpy(eRatio, h->lafState + nE, nE * 8, cudaMemcpyDeviceToHost));
+  if (r) CK(cudaMemcpy(r, h->lafState + 2 * nE, nE * 8, cudaMemcpyDeviceToHost));
   return 0;
 }
 

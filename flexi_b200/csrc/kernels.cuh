@@ -87,6 +87,10 @@ struct UpdArgs {
 struct FiltArgs {
   double* U;          // [e][5][NP3], filtered in place
   const double* mat;  // FilterMat as [out][in]
+  // FilterType 3 (LAF, filter.f90:295-448): iw = IntegrationWeight [e][NP3] (nullptr = plain filter); per-element state
+  const double* iw;
+  double *lim, *eRatio, *r, *ekinOld, *flucOld;
+  double normMod, alpha;
 };
 
 struct ProArgs {
@@ -105,11 +109,12 @@ struct ProArgs {
 // 1-D sweeps through 5 shared planes; sums start from zero and run over ascending input index like changeBasis.t90.  A plain
 // extra pass over U (HBM-bound: 80 B/DOF); the fused form is described in DESIGN.md section 7.
 template <int NP>
-__global__ void __launch_bounds__(Dim<NP>::NP3) k_filter(FiltArgs A) {
+__global__ void __launch_bounds__(Dim<NP>::THREADS) k_filter(FiltArgs A) {
   using D = Dim<NP>;
-  extern __shared__ double sm[];
-  const int n = threadIdx.x;
-  const size_t e = blockIdx.x;
+  extern __shared__ double sm_raw[];
+  auto sm = elem_smem<NP>(sm_raw);
+  const int n = elem_tid<NP>();
+  const size_t e = elem_blk<NP>();
   const int i = n % NP, j = (n / NP) % NP, k = n / D::NP2;
   double w[5];
 #pragma unroll
@@ -121,7 +126,7 @@ __global__ void __launch_bounds__(Dim<NP>::NP3) k_filter(FiltArgs A) {
     const int base = n - me * stride;
 #pragma unroll
     for (int v = 0; v < 5; ++v) sm[v * D::NP3 + n] = w[v];
-    __syncthreads();
+    elem_sync<NP>();
     const double* row = A.mat + me * NP;
 #pragma unroll
     for (int v = 0; v < 5; ++v) {
@@ -130,28 +135,83 @@ __global__ void __launch_bounds__(Dim<NP>::NP3) k_filter(FiltArgs A) {
       for (int l = 0; l < NP; ++l) acc = acc + __ldg(row + l) * sm[v * D::NP3 + base + l * stride];
       w[v] = acc;
     }
-    __syncthreads();
+    elem_sync<NP>();
+  }
+  if (A.iw) {
+    // ---- Filter_LAF: the filtered state replaces U only where the energy of the filtered-out velocity scales, relative to the
+    //      resolved fluctuations, exceeds the element's adaptive limit.  Element sums: tree reduction through the (now free)
+    //      planes, in a fixed order. ----
+    double u[5];
+#pragma unroll
+    for (int v = 0; v < 5; ++v) u[v] = A.U[(e * 5 + v) * D::NP3 + n];
+    const double wgt = A.iw[e * D::NP3 + n], sr = 1. / u[0];
+    auto reduce = [&](int nq) {  // sums of planes 0..nq-1 over the element end up in sm[q * NP3]
+      elem_sync<NP>();
+      int p2 = 1;
+      while (p2 < D::NP3) p2 <<= 1;
+      for (int off = p2 >> 1; off > 0; off >>= 1) {
+        if (n < off && n + off < D::NP3)
+          for (int qq = 0; qq < nq; ++qq) sm[qq * D::NP3 + n] = sm[qq * D::NP3 + n] + sm[qq * D::NP3 + n + off];
+        elem_sync<NP>();
+      }
+    };
+#pragma unroll
+    for (int c = 0; c < 3; ++c) sm[c * D::NP3 + n] = w[1 + c] * sr * wgt;  // U_Avg(2:4)
+    reduce(3);
+    const double a1 = sm[0], a2 = sm[D::NP3], a3 = sm[2 * D::NP3];
+    elem_sync<NP>();
+    const double f1 = u[1] - w[1], f2 = u[2] - w[2], f3 = u[3] - w[3];
+    const double sr2 = sr * sr;
+    sm[n] = (f1 * f1 * sr2 + f3 * f3 * sr2 + f2 * f2 * sr2) * wgt;                                            // ekin_fluc_avg
+    sm[D::NP3 + n] = ((w[1] - a1) * (w[1] - a1) * sr2 + (w[2] - a2) * (w[2] - a2) * sr2 + (w[3] - a3) * (w[3] - a3) * sr2) * wgt;  // ekin_avg
+    reduce(2);
+    if (n == 0) {
+      const double fluc = sm[0], ekin = sm[D::NP3];
+      const double ratio = (fluc / ekin) * A.normMod;
+      double lim = fmax(A.lim[e], 1.0E-8);
+      const double dfluc = fluc - A.flucOld[e];
+      const double dedt = fabs(ekin - A.ekinOld[e]) / dfluc;
+      double doFilter = 0.;
+      if (dedt > 1.0 && dfluc > 0.) {
+        lim = ratio;
+      } else if (dfluc < 0.) {
+        lim = ratio;
+      } else if (ratio > lim * A.alpha) {
+        doFilter = 1.;
+        A.r[e] = A.r[e] + 1.;
+      }
+      A.eRatio[e] = ratio;
+      A.lim[e] = lim;
+      A.ekinOld[e] = ekin;
+      A.flucOld[e] = fluc;
+      sm[2 * D::NP3] = doFilter;
+    }
+    elem_sync<NP>();
+    const bool keep = sm[2 * D::NP3] == 0.;
+    elem_exit<NP>();
+    if (keep) return;
   }
 #pragma unroll
   for (int v = 0; v < 5; ++v) A.U[(e * 5 + v) * D::NP3 + n] = w[v];
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
-template <int NP>
-__device__ __forceinline__ void load_basis(double* sB, const double* g, int tid, int nthreads) {
+template <int NP, class SP>
+__device__ __forceinline__ void load_basis(SP sB, const double* g, int tid, int nthreads) {
   for (int t = tid; t < Dim<NP>::NBASIS; t += nthreads) sB[t] = g[t];
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
 // k_prolong: ProlongToFace for nv variables, element gather.
 template <int NP, bool GL>
-__global__ void __launch_bounds__(Dim<NP>::NP3) k_prolong(ProArgs A) {
+__global__ void __launch_bounds__(Dim<NP>::THREADS) k_prolong(ProArgs A) {
   using D = Dim<NP>;
-  extern __shared__ double sm[];
-  double* sB = sm;
-  double* sV = sm + D::NBASIS;  // nv planes
-  const int tid = threadIdx.x;
-  const int e = blockIdx.x;
+  extern __shared__ double sm_raw[];
+  auto sm = elem_smem<NP>(sm_raw);
+  auto sB = sm;
+  auto sV = sm + D::NBASIS;  // nv planes
+  const int tid = elem_tid<NP>();
+  const int e = elem_blk<NP>();
   load_basis<NP>(sB, A.m.basis, tid, D::NP3);
   for (int v = 0; v < A.nv; ++v) sV[v * D::NP3 + tid] = A.V[((size_t)e * A.nv + v) * D::NP3 + tid];
   if (A.entropy) {  // own node: cons -> prim -> entropy variables, in place
@@ -161,7 +221,7 @@ __global__ void __launch_bounds__(Dim<NP>::NP3) k_prolong(ProArgs A) {
     prim_to_entropy(A.q, P, w);
     for (int v = 0; v < 5; ++v) sV[v * D::NP3 + tid] = w[v];
   }
-  __syncthreads();
+  elem_sync<NP>();
   for (int t = tid; t < 6 * D::NP2; t += D::NP3) {
     const int ls = t / D::NP2 + 1, pq = t % D::NP2;
     const SideRef sr = A.m.e2s[e * 6 + ls - 1];
@@ -179,6 +239,7 @@ __global__ void __launch_bounds__(Dim<NP>::NP3) k_prolong(ProArgs A) {
         dst[((size_t)sr.side * A.nv + v) * D::NP2 + pq] = face_eval<NP, GL>(sV + v * D::NP3, sB, ls, a, b);
     }
   }
+  elem_exit<NP>();
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
@@ -196,11 +257,11 @@ struct VolSmem {
 };
 
 // pairwise two-point volume fluxes of one node along its three lines, volint.f90:211-371 (advective part)
-template <int NP, int STYPE>
-__device__ __forceinline__ void split_lines(const double* sP, const double* sM, const double* sB, int i, int j, int k, int n,
+template <int NP, int STYPE, class SP>
+__device__ __forceinline__ void split_lines(const SP sP, const SP sM, const SP sB, int i, int j, int k, int n,
                                             const double* M, double* ut, const double kappa) {
   using D = Dim<NP>;
-  const double* dv = sB + D::O_DV;
+  const auto dv = sB + D::O_DV;
   Node a;
   a.rho = sP[0 * D::NP3 + n];
   a.v1 = sP[1 * D::NP3 + n];
@@ -237,15 +298,16 @@ __device__ __forceinline__ void split_lines(const double* sP, const double* sM, 
 __host__ __device__ constexpr int lift_prim(int nvl, int v) { return nvl == 5 ? (v < 4 ? v : 5) : (v < 3 ? v + 1 : 5); }
 
 template <int NP, bool GL, bool SPLIT, bool PARA, int NVL, int LIFT>
-__global__ void __launch_bounds__(Dim<NP>::NP3) k_volume(VolArgs A) {
+__global__ void __launch_bounds__(Dim<NP>::THREADS) k_volume(VolArgs A) {
   using D = Dim<NP>;
-  extern __shared__ double sm[];
-  double* sB = sm;
-  double* sP = sm + D::NBASIS;  // rho,v1,v2,v3,p,T,rhoE
-  double* sW = sP + 7 * D::NP3;
-  double* sLF = (LIFT == 2) ? sm + VolSmem<NP, GL, SPLIT, PARA, LIFT>::O_FACE2 : sW;  // staged lifting fluxes of the faces
-  const int tid = threadIdx.x;
-  const int e = A.elems ? A.elems[blockIdx.x] : blockIdx.x;
+  extern __shared__ double sm_raw[];
+  auto sm = elem_smem<NP>(sm_raw);
+  auto sB = sm;
+  auto sP = sm + D::NBASIS;  // rho,v1,v2,v3,p,T,rhoE
+  auto sW = sP + 7 * D::NP3;
+  auto sLF = (LIFT == 2) ? sm + VolSmem<NP, GL, SPLIT, PARA, LIFT>::O_FACE2 : sW;  // staged lifting fluxes of the faces
+  const int tid = elem_tid<NP>();
+  const int e = A.elems ? A.elems[elem_blk<NP>()] : elem_blk<NP>();
   const int i = tid % NP, j = (tid / NP) % NP, k = tid / D::NP2;
   const int n = tid;
   const Eqn& q = A.q;
@@ -261,10 +323,10 @@ __global__ void __launch_bounds__(Dim<NP>::NP3) k_volume(VolArgs A) {
 #pragma unroll
   for (int c = 0; c < 9; ++c) M[c] = A.m.Met[((size_t)e * 9 + c) * D::NP3 + n];
   const double sJ = A.m.sJ[(size_t)e * D::NP3 + n];
-  __syncthreads();
+  elem_sync<NP>();
 
   double ut[5] = {0., 0., 0., 0., 0.};
-  const double* dh = sB + D::O_DH;
+  const auto dh = sB + D::O_DH;
 
   if (PARA) {
     constexpr int nvl = NVL;
@@ -285,7 +347,7 @@ __global__ void __launch_bounds__(Dim<NP>::NP3) k_volume(VolArgs A) {
       cons_to_prim(q, Um, Pm);
       const double* g = A.m.Geo + (size_t)sr.side * 10 * D::NP2 + pq;
       const double surf = g[9 * D::NP2];
-      double* o = sLF + (ls - 1) * 8 * D::NP2 + ab;
+      auto o = sLF + (ls - 1) * 8 * D::NP2 + ab;
       const double sgn = (sr.flip == 0) ? 1. : -1.;  // (slave - master) seen from this element
 #pragma unroll
       for (int v = 0; v < nvl; ++v) {
@@ -299,10 +361,10 @@ __global__ void __launch_bounds__(Dim<NP>::NP3) k_volume(VolArgs A) {
     // ---- 2. volume part, lifting_volint.t90:26-118 (non-conservative)
     double gx[5], gy[5], gz[5];
     {
-      const double* dt = sB + D::O_DT;
+      const auto dt = sB + D::O_DT;
 #pragma unroll
       for (int v = 0; v < nvl; ++v) {
-        const double* pl = sP + lift_prim(nvl, v) * D::NP3;
+        const auto pl = sP + lift_prim(nvl, v) * D::NP3;
         const int bx = n - i, by = n - j * NP, bz = n - k * D::NP2;
         double gxi = dt[i] * pl[bx], geta = dt[j] * pl[by], gzeta = dt[k] * pl[bz];
 #pragma unroll
@@ -316,7 +378,7 @@ __global__ void __launch_bounds__(Dim<NP>::NP3) k_volume(VolArgs A) {
         gz[v] = M[2] * gxi + M[5] * geta + M[8] * gzeta;
       }
     }
-    __syncthreads();
+    elem_sync<NP>();
     if (LIFT == 2) {
       // BR2 (lifting_br2.t90:111-131): Jacobian first, faces are prolonged from the volume-only gradients
 #pragma unroll
@@ -328,7 +390,7 @@ __global__ void __launch_bounds__(Dim<NP>::NP3) k_volume(VolArgs A) {
         sW[(1 * nvl + v) * D::NP3 + n] = gy[v];
         sW[(2 * nvl + v) * D::NP3 + n] = gz[v];
       }
-      __syncthreads();
+      elem_sync<NP>();
       // face gradients: prolonged value + eta * sum_l L_Minus(l) * sJ_l * Flux * L_HatMinus(l)   (lifting_br2.t90:253-307)
       for (int t = tid; t < 6 * D::NP2; t += D::NP3) {
         const int ls = t / D::NP2 + 1, pq = t % D::NP2;
@@ -345,15 +407,15 @@ __global__ void __launch_bounds__(Dim<NP>::NP3) k_volume(VolArgs A) {
         }
         double wsum = 0.;  // sum_l L_Minus(l) * sJ_l * L_HatMinus(l)
         {
-          const double* lm = sB + D::O_LM;
-          const double* lhm = sB + D::O_LHM;
+          const auto lm = sB + D::O_LM;
+          const auto lhm = sB + D::O_LHM;
           const int lmax = GL ? 0 : NP - 1;
           for (int l = 0; l <= lmax; ++l) {
             const int d = minus ? l : NP - 1 - l;
             wsum = wsum + lm[l] * (A.m.sJ[(size_t)e * D::NP3 + base + d * stride] * lhm[l]);
           }
         }
-        const double* o = sLF + (ls - 1) * 8 * D::NP2 + ab;
+        const auto o = sLF + (ls - 1) * 8 * D::NP2 + ab;
         for (int d = 0; d < 3; ++d) {
           double* dst = (sr.flip == 0) ? A.gm[d] : A.gs[d];
           const double nd = o[(5 + d) * D::NP2];
@@ -364,7 +426,7 @@ __global__ void __launch_bounds__(Dim<NP>::NP3) k_volume(VolArgs A) {
       }
       // volume gradients: + sJ * Flux * L_HatMinus(depth)
       {
-        const double* lhm = sB + D::O_LHM;
+        const auto lhm = sB + D::O_LHM;
 #pragma unroll
         for (int ls = 1; ls <= 6; ++ls) {
           int ab, me;
@@ -381,7 +443,7 @@ __global__ void __launch_bounds__(Dim<NP>::NP3) k_volume(VolArgs A) {
           const int depth = is_minus_side(ls) ? me : NP - 1 - me;
           if (GL && depth != 0) continue;
           const double lh = lhm[depth];
-          const double* o = sLF + (ls - 1) * 8 * D::NP2 + ab;
+          const auto o = sLF + (ls - 1) * 8 * D::NP2 + ab;
           const double n0 = o[5 * D::NP2], n1 = o[6 * D::NP2], n2 = o[7 * D::NP2];
 #pragma unroll
           for (int v = 0; v < nvl; ++v) {
@@ -403,8 +465,8 @@ __global__ void __launch_bounds__(Dim<NP>::NP3) k_volume(VolArgs A) {
     } else {
     // ---- 3. surface part, lifting_br1.t90:195-292 (same sign for master and slave element), then *sJ (applyjacobian.t90)
     {
-      const double* lhm = sB + D::O_LHM;
-      const double* lhp = sB + D::O_LHP;
+      const auto lhm = sB + D::O_LHM;
+      const auto lhp = sB + D::O_LHP;
 #pragma unroll
       for (int ls = 1; ls <= 6; ++ls) {
         int ab, me;
@@ -421,7 +483,7 @@ __global__ void __launch_bounds__(Dim<NP>::NP3) k_volume(VolArgs A) {
         const bool minus = is_minus_side(ls);
         if (GL && me != (minus ? 0 : NP - 1)) continue;
         const double lh = minus ? lhm[GL ? 0 : me] : lhp[GL ? NP - 1 : me];
-        const double* o = sW + (ls - 1) * 8 * D::NP2 + ab;
+        const auto o = sW + (ls - 1) * 8 * D::NP2 + ab;
         const double n0 = o[5 * D::NP2], n1 = o[6 * D::NP2], n2 = o[7 * D::NP2];
 #pragma unroll
         for (int v = 0; v < nvl; ++v) {
@@ -438,7 +500,7 @@ __global__ void __launch_bounds__(Dim<NP>::NP3) k_volume(VolArgs A) {
         gz[v] = gz[v] * sJ;
       }
     }
-    __syncthreads();  // everyone is done with the face staging area
+    elem_sync<NP>();  // everyone is done with the face staging area
 #pragma unroll
     for (int v = 0; v < nvl; ++v) {
       sW[(0 * nvl + v) * D::NP3 + n] = gx[v];
@@ -453,7 +515,7 @@ __global__ void __launch_bounds__(Dim<NP>::NP3) k_volume(VolArgs A) {
         A.gvol[2][((size_t)e * nvl + v) * D::NP3 + n] = gz[v];
       }
     }
-    __syncthreads();
+    elem_sync<NP>();
     // ---- 4. ProlongToFaceLifting, lifting_br1.t90:150-174
     for (int t = tid; t < 6 * D::NP2; t += D::NP3) {
       const int ls = t / D::NP2 + 1, pq = t % D::NP2;
@@ -493,14 +555,14 @@ __global__ void __launch_bounds__(Dim<NP>::NP3) k_volume(VolArgs A) {
         H[v] = fa[v] * M[6] + ga[v] * M[7] + ha[v] * M[8];
       }
     }
-    __syncthreads();  // face threads are done reading the gradients
+    elem_sync<NP>();  // face threads are done reading the gradients
 #pragma unroll
     for (int v = 0; v < 5; ++v) {
       sW[(0 + v) * D::NP3 + n] = F[v];
       sW[(5 + v) * D::NP3 + n] = G[v];
       sW[(10 + v) * D::NP3 + n] = H[v];
     }
-    __syncthreads();
+    elem_sync<NP>();
   } else if (!SPLIT) {
     double fe[5], ge[5], he[5];
     eval_flux3d(U, P, fe, ge, he);
@@ -510,7 +572,7 @@ __global__ void __launch_bounds__(Dim<NP>::NP3) k_volume(VolArgs A) {
       sW[(5 + v) * D::NP3 + n] = fe[v] * M[3] + ge[v] * M[4] + he[v] * M[5];
       sW[(10 + v) * D::NP3 + n] = fe[v] * M[6] + ge[v] * M[7] + he[v] * M[8];
     }
-    __syncthreads();
+    elem_sync<NP>();
   }
 
   if (PARA || !SPLIT) {
@@ -519,9 +581,9 @@ __global__ void __launch_bounds__(Dim<NP>::NP3) k_volume(VolArgs A) {
     constexpr int V0 = (SPLIT ? 1 : 0);  // the viscous density flux is identically zero
 #pragma unroll
     for (int v = V0; v < 5; ++v) {
-      const double* f = sW + (0 + v) * D::NP3;
-      const double* g = sW + (5 + v) * D::NP3;
-      const double* h = sW + (10 + v) * D::NP3;
+      const auto f = sW + (0 + v) * D::NP3;
+      const auto g = sW + (5 + v) * D::NP3;
+      const auto h = sW + (10 + v) * D::NP3;
       double s = dh[i] * f[bx] + dh[k] * h[bz] + dh[j] * g[by];
 #pragma unroll
       for (int l = 1; l < NP; ++l) s = s + dh[l * NP + i] * f[bx + l] + dh[l * NP + k] * h[bz + l * D::NP2] + dh[l * NP + j] * g[by + l * NP];
@@ -530,10 +592,10 @@ __global__ void __launch_bounds__(Dim<NP>::NP3) k_volume(VolArgs A) {
   }
 
   if (SPLIT) {
-    if (PARA) __syncthreads();  // weak-form reads of the work area are done
+    if (PARA) elem_sync<NP>();  // weak-form reads of the work area are done
 #pragma unroll
     for (int c = 0; c < 9; ++c) sW[c * D::NP3 + n] = M[c];
-    __syncthreads();
+    elem_sync<NP>();
     switch (q.splitType) {
       case FLEXI_SPLITDG_SD: split_lines<NP, FLEXI_SPLITDG_SD>(sP, sW, sB, i, j, k, n, M, ut, q.kappa); break;
       case FLEXI_SPLITDG_MO: split_lines<NP, FLEXI_SPLITDG_MO>(sP, sW, sB, i, j, k, n, M, ut, q.kappa); break;
@@ -546,6 +608,7 @@ __global__ void __launch_bounds__(Dim<NP>::NP3) k_volume(VolArgs A) {
   }
 #pragma unroll
   for (int v = 0; v < 5; ++v) A.Ut[((size_t)e * 5 + v) * D::NP3 + n] = ut[v];
+  elem_exit<NP>();
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
@@ -745,13 +808,14 @@ __global__ void __launch_bounds__(128) k_flux_bc(BCArgs A) {
 // SPONGE: Sponge(Ut) between the source term and ApplyJacobian (sponge.f90:612-678).  A separate instantiation as well: with
 // the sponge code in the plain kernel its register count crossed 64 and the kernel lost half its resident warps (+32 % time).
 template <int NP, bool GL, bool ENT = false, bool FILT = false, bool SPONGE = false>
-__global__ void __launch_bounds__(Dim<NP>::NP3) k_update(UpdArgs A) {
+__global__ void __launch_bounds__(Dim<NP>::THREADS) k_update(UpdArgs A) {
   using D = Dim<NP>;
-  extern __shared__ double sm[];
-  double* sB = sm;
-  double* sU = sm + D::NBASIS;  // 5 planes
-  const int tid = threadIdx.x;
-  const int e = A.elems ? A.elems[blockIdx.x] : blockIdx.x;
+  extern __shared__ double sm_raw[];
+  auto sm = elem_smem<NP>(sm_raw);
+  auto sB = sm;
+  auto sU = sm + D::NBASIS;  // 5 planes
+  const int tid = elem_tid<NP>();
+  const int e = A.elems ? A.elems[elem_blk<NP>()] : elem_blk<NP>();
   const int i = tid % NP, j = (tid / NP) % NP, k = tid / D::NP2;
   const int n = tid;
   load_basis<NP>(sB, A.m.basis, tid, D::NP3);
@@ -779,9 +843,9 @@ __global__ void __launch_bounds__(Dim<NP>::NP3) k_update(UpdArgs A) {
       sp[v] = smat * (((A.mode != 0) ? uOld[v] : A.U[g]) - A.spBase[g]);
     }
   }
-  __syncthreads();
-  const double* lhm = sB + D::O_LHM;
-  const double* lhp = sB + D::O_LHP;
+  elem_sync<NP>();
+  const auto lhm = sB + D::O_LHM;
+  const auto lhp = sB + D::O_LHP;
 #pragma unroll
   for (int ls = 1; ls <= 6; ++ls) {  // surfint.t90:475-616 / :21-239, DoSurfInt :683-766
     int ab, me;
@@ -832,7 +896,7 @@ __global__ void __launch_bounds__(Dim<NP>::NP3) k_update(UpdArgs A) {
         const int base = n - me * stride;
 #pragma unroll
         for (int v = 0; v < 5; ++v) sU[v * D::NP3 + n] = w[v];
-        __syncthreads();
+        elem_sync<NP>();
         const double* row = mat + me * NP;
 #pragma unroll
         for (int v = 0; v < 5; ++v) {
@@ -841,7 +905,7 @@ __global__ void __launch_bounds__(Dim<NP>::NP3) k_update(UpdArgs A) {
           for (int l = 0; l < NP; ++l) acc = acc + __ldg(row + l) * sU[v * D::NP3 + base + l * stride];
           w[v] = acc;
         }
-        __syncthreads();  // every read of this sweep is done before the planes are overwritten (next sweep / new state below)
+        elem_sync<NP>();  // every read of this sweep is done before the planes are overwritten (next sweep / new state below)
       }
     };
     sweep3(A.filt);
@@ -878,6 +942,7 @@ __global__ void __launch_bounds__(Dim<NP>::NP3) k_update(UpdArgs A) {
   if (A.mode == 0) {
 #pragma unroll
     for (int v = 0; v < 5; ++v) A.UtOut[((size_t)e * 5 + v) * D::NP3 + n] = ut[v];
+    elem_exit<NP>();
     return;
   }
   // timestep.f90:126-131
@@ -900,7 +965,7 @@ __global__ void __launch_bounds__(Dim<NP>::NP3) k_update(UpdArgs A) {
 #pragma unroll
     for (int v = 0; v < 5; ++v) sU[v * D::NP3 + n] = w[v];
   }
-  __syncthreads();
+  elem_sync<NP>();
   for (int t = tid; t < 6 * D::NP2; t += D::NP3) {
     const int ls = t / D::NP2 + 1, pq = t % D::NP2;
     const SideRef sr = A.m.e2s[e * 6 + ls - 1];
@@ -919,6 +984,7 @@ __global__ void __launch_bounds__(Dim<NP>::NP3) k_update(UpdArgs A) {
       for (int v = 0; v < 5; ++v) dst[((size_t)sr.side * 5 + v) * D::NP2 + pq] = face_eval<NP, GL>(sU + v * D::NP3, sB, ls, a, b);
     }
   }
+  elem_exit<NP>();
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
@@ -940,13 +1006,14 @@ struct SurfCorrArgs {
 };
 
 template <int NP>
-__global__ void __launch_bounds__(Dim<NP>::NP3) k_surfcorr(SurfCorrArgs A) {
+__global__ void __launch_bounds__(Dim<NP>::THREADS) k_surfcorr(SurfCorrArgs A) {
   using D = Dim<NP>;
-  extern __shared__ double sm[];
-  double* sB = sm;
-  double* sFB = sm + D::NBASIS;  // Leg(l)*FluxB(l) of the current local side, [5][NP3]
-  const int tid = threadIdx.x, n = tid;
-  const int e = A.elems ? A.elems[blockIdx.x] : blockIdx.x;
+  extern __shared__ double sm_raw[];
+  auto sm = elem_smem<NP>(sm_raw);
+  auto sB = sm;
+  auto sFB = sm + D::NBASIS;  // Leg(l)*FluxB(l) of the current local side, [5][NP3]
+  const int tid = elem_tid<NP>(), n = tid;
+  const int e = A.elems ? A.elems[elem_blk<NP>()] : elem_blk<NP>();
   const int i = tid % NP, j = (tid / NP) % NP, k = tid / D::NP2;
   const Eqn& q = A.q;
   load_basis<NP>(sB, A.m.basis, tid, D::NP3);
@@ -958,7 +1025,7 @@ __global__ void __launch_bounds__(Dim<NP>::NP3) k_surfcorr(SurfCorrArgs A) {
   for (int c = 0; c < 9; ++c) M[c] = A.m.Met[((size_t)e * 9 + c) * D::NP3 + n];
   const Node nd{P[DENS], P[VEL1], P[VEL2], P[VEL3], P[PRES], Uc[ENER]};
   double corr[5] = {0., 0., 0., 0., 0.};
-  __syncthreads();
+  elem_sync<NP>();
   for (int ls = 1; ls <= 6; ++ls) {
     // line through this node along the side's normal direction; (a,b) = volume-face coordinates, l = own position on the line
     const int idx = (ls == XI_MINUS || ls == XI_PLUS) ? 0 : (ls == ETA_MINUS || ls == ETA_PLUS) ? 1 : 2;
@@ -966,8 +1033,8 @@ __global__ void __launch_bounds__(Dim<NP>::NP3) k_surfcorr(SurfCorrArgs A) {
     const int l = idx == 0 ? i : idx == 1 ? j : k;
     const int stride = idx == 0 ? 1 : idx == 1 ? NP : D::NP2;
     const bool minus = is_minus_side(ls);
-    const double* Leg = sB + (minus ? D::O_LM : D::O_LP);
-    const double* LegHat = sB + (minus ? D::O_LHM : D::O_LHP);
+    const auto Leg = sB + (minus ? D::O_LM : D::O_LP);
+    const auto LegHat = sB + (minus ? D::O_LHM : D::O_LHP);
     const double nsign = minus ? -1. : 1.;  // NormalSigns (mesh_vars.f90:105-111)
     const SideRef sr = A.m.e2s[e * 6 + ls - 1];
     const int pq = A.m.v2s[(sr.flip * 6 + ls - 1) * D::NP2 + ab];
@@ -991,7 +1058,7 @@ __global__ void __launch_bounds__(Dim<NP>::NP3) k_surfcorr(SurfCorrArgs A) {
     }
 #pragma unroll
     for (int v = 0; v < 5; ++v) sFB[v * D::NP3 + n] = FB[v] * Leg[l];
-    __syncthreads();
+    elem_sync<NP>();
     const int base = n - l * stride;
 #pragma unroll
     for (int v = 0; v < 5; ++v) {
@@ -999,7 +1066,7 @@ __global__ void __launch_bounds__(Dim<NP>::NP3) k_surfcorr(SurfCorrArgs A) {
       for (int kk = 0; kk < NP; ++kk) sum = sum + sFB[v * D::NP3 + base + kk * stride];
       corr[v] = corr[v] + (-1. / 2. * (sum - FB[v]) * nsign) * LegHat[l];
     }
-    __syncthreads();
+    elem_sync<NP>();
   }
 #pragma unroll
   for (int v = 0; v < 5; ++v) {
@@ -1019,16 +1086,17 @@ struct SurfArgs {
   int firstSide, lastSide;
 };
 template <int NP, bool GL>
-__global__ void __launch_bounds__(Dim<NP>::NP3) k_surfint(SurfArgs A) {
+__global__ void __launch_bounds__(Dim<NP>::THREADS) k_surfint(SurfArgs A) {
   using D = Dim<NP>;
-  extern __shared__ double sm[];
-  double* sB = sm;
-  const int tid = threadIdx.x, e = blockIdx.x;
+  extern __shared__ double sm_raw[];
+  auto sm = elem_smem<NP>(sm_raw);
+  auto sB = sm;
+  const int tid = elem_tid<NP>(), e = elem_blk<NP>();
   const int i = tid % NP, j = (tid / NP) % NP, k = tid / D::NP2;
   load_basis<NP>(sB, A.m.basis, tid, D::NP3);
-  __syncthreads();
-  const double* lhm = sB + D::O_LHM;
-  const double* lhp = sB + D::O_LHP;
+  elem_sync<NP>();
+  const auto lhm = sB + D::O_LHM;
+  const auto lhp = sB + D::O_LHP;
   for (int v = 0; v < A.nv; ++v) {
     double ut = A.Ut[((size_t)e * A.nv + v) * D::NP3 + tid];
     for (int ls = 1; ls <= 6; ++ls) {
@@ -1055,6 +1123,7 @@ __global__ void __launch_bounds__(Dim<NP>::NP3) k_surfint(SurfArgs A) {
     }
     A.Ut[((size_t)e * A.nv + v) * D::NP3 + tid] = ut;
   }
+  elem_exit<NP>();
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
@@ -1075,18 +1144,22 @@ struct DtArgs {
 // The block is NP^3 rounded up to whole warps: the lanes beyond the last node carry neutral values (0) into the warp shuffles
 // (a shuffle from a lane that does not exist returns an undefined value).
 template <int NP>
-constexpr int dt_threads() { return (Dim<NP>::NP3 + 31) / 32 * 32; }
+__host__ __device__ constexpr int dt_threads() { return Dim<NP>::PAIR ? 1024 : (Dim<NP>::NP3 + 31) / 32 * 32; }
 template <int NP>
 __global__ void __launch_bounds__(dt_threads<NP>()) k_dt(DtArgs A) {
   using D = Dim<NP>;
-  constexpr int NW = (D::NP3 + 31) / 32;
+  constexpr int NT = dt_threads<NP>(), NW = NT / 32;
   __shared__ double red[7][NW];
-  const int tid = threadIdx.x, e = blockIdx.x, n = tid;
+  const int tid = threadIdx.x, e = blockIdx.x;
   const Eqn& q = A.q;
   double r[7];  // max over the element of: lambda_adv(3), lambda_visc(3), NaN flag
 #pragma unroll
   for (int s = 0; s < 7; ++s) r[s] = 0.;
-  if (tid < D::NP3) {
+  // one node per thread; the large degrees (Dim::PAIR) walk their nodes with the block as stride and keep the running maxima
+  for (int n = tid; n < D::NP3; n += NT) {
+    double rp[7];
+#pragma unroll
+    for (int s = 0; s < 7; ++s) rp[s] = r[s];
     double U[5], P[6], M[9];
 #pragma unroll
     for (int v = 0; v < 5; ++v) U[v] = A.U[((size_t)e * 5 + v) * D::NP3 + n];
@@ -1108,6 +1181,10 @@ __global__ void __launch_bounds__(dt_threads<NP>()) k_dt(DtArgs A) {
       r[3 + d] = A.parabolic ? viscosity(q, P[TEMP]) * srho * metVisc : 0.;
       // Fortran MAX may or may not propagate a NaN operand; NaN is flagged separately
       if (r[d] != r[d] || r[3 + d] != r[3 + d]) r[6] = fmax(r[6], 2.);
+    }
+    if (D::PAIR) {
+#pragma unroll
+      for (int s = 0; s < 7; ++s) r[s] = fmax(r[s], rp[s]);
     }
   }
 #pragma unroll

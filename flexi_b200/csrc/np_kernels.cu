@@ -3,8 +3,10 @@
 #include <stdlib.h>
 
 #include "np_ops.h"
+#if FLEXI_NP <= 10
 #include "volume_gl.cuh"
 #include "volume_gl2.cuh"
+#endif
 
 #ifndef FLEXI_NP
 #error "compile with -DFLEXI_NP=<N+1>"
@@ -15,42 +17,64 @@ namespace {
 constexpr int NP = FLEXI_NP;
 using D = Dim<NP>;
 
+// ---- launch of an element kernel: one CTA of NP^3 threads per element, or (Dim::PAIR, N = 11) a cluster of two CTAs of NP^3/2
+// threads whose shared memories together hold the element's work planes (layout.cuh: PairPtr) ----
+template <class K>
+cudaError_t elem_smem_attr(K kern, size_t bytes) {
+  if (D::PAIR && bytes > 2 * sizeof(double) * (size_t)D::PAIR_DOUBLES) return cudaErrorInvalidValue;
+  return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, D::PAIR ? (int)(sizeof(double) * D::PAIR_DOUBLES) : (int)bytes);
+}
+template <class K, class A>
+cudaError_t elem_launch(K kern, int nBlocks, size_t bytes, cudaStream_t s, const A& a) {
+  if (D::PAIR) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2u * (unsigned)nBlocks);
+    cfg.blockDim = dim3(D::THREADS);
+    cfg.dynamicSmemBytes = sizeof(double) * D::PAIR_DOUBLES;
+    cfg.stream = s;
+    cudaLaunchAttribute at;
+    at.id = cudaLaunchAttributeClusterDimension;
+    at.val.clusterDim.x = 2;
+    at.val.clusterDim.y = 1;
+    at.val.clusterDim.z = 1;
+    cfg.attrs = &at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, a);
+  }
+  kern<<<nBlocks, D::NP3, bytes, s>>>(a);
+  return cudaGetLastError();
+}
+
 // k-block size of the Gauss-Lobatto element kernel: half a zeta column per thread for even NP, one node otherwise
 constexpr int KPT = (NP % 2 == 0) ? NP / 2 : 1;
+static_assert(KPT >= 1, "");
 
-template <bool PARA, int NVL, int LIFT>
+template <bool PARA, int NVL, int LIFT, bool GLN = false>
 cudaError_t volume_setup1() {
-  return cudaFuncSetAttribute(k_volume<NP, false, false, PARA, NVL, LIFT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)VolSmem<NP, false, false, PARA, LIFT>::BYTES);
+  return elem_smem_attr(k_volume<NP, GLN, false, PARA, NVL, LIFT>, VolSmem<NP, GLN, false, PARA, LIFT>::BYTES);
 }
-template <bool PARA, int NVL>
+template <bool PARA, int NVL, bool GLN = false>
 cudaError_t volume_setup() {
-  cudaError_t e = volume_setup1<PARA, NVL, 1>();
-  if (e == cudaSuccess && PARA) e = volume_setup1<PARA, NVL, 2>();
+  cudaError_t e = volume_setup1<PARA, NVL, 1, GLN>();
+  if (e == cudaSuccess && PARA) e = volume_setup1<PARA, NVL, 2, GLN>();
   return e;
 }
 // split form on Gauss nodes: the generic element kernel with the two-point volume fluxes (DVolSurf = (D - 1/2 M^-1 V^T B V)^T)
-template <bool PARA, int NVL, int LIFT>
+template <bool PARA, int NVL, int LIFT, bool GLN = false>
 cudaError_t volume_gs_setup1() {
-  return cudaFuncSetAttribute(k_volume<NP, false, true, PARA, NVL, LIFT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)VolSmem<NP, false, true, PARA, LIFT>::BYTES);
+  return elem_smem_attr(k_volume<NP, GLN, true, PARA, NVL, LIFT>, VolSmem<NP, GLN, true, PARA, LIFT>::BYTES);
 }
-template <bool PARA, int NVL>
+template <bool PARA, int NVL, bool GLN = false>
 cudaError_t volume_gs_launch(int lift, const VolArgs& a, int nBlocks, cudaStream_t s) {
-  if (PARA && lift == 2)
-    k_volume<NP, false, true, PARA, NVL, 2><<<nBlocks, D::NP3, VolSmem<NP, false, true, PARA, 2>::BYTES, s>>>(a);
-  else
-    k_volume<NP, false, true, PARA, NVL, 1><<<nBlocks, D::NP3, VolSmem<NP, false, true, PARA, 1>::BYTES, s>>>(a);
-  return cudaGetLastError();
+  if (PARA && lift == 2) return elem_launch(k_volume<NP, GLN, true, PARA, NVL, 2>, nBlocks, VolSmem<NP, GLN, true, PARA, 2>::BYTES, s, a);
+  return elem_launch(k_volume<NP, GLN, true, PARA, NVL, 1>, nBlocks, VolSmem<NP, GLN, true, PARA, 1>::BYTES, s, a);
 }
-template <bool PARA, int NVL>
+template <bool PARA, int NVL, bool GLN = false>
 cudaError_t volume_launch(int lift, const VolArgs& a, int nBlocks, cudaStream_t s) {
-  if (PARA && lift == 2)
-    k_volume<NP, false, false, PARA, NVL, 2><<<nBlocks, D::NP3, VolSmem<NP, false, false, PARA, 2>::BYTES, s>>>(a);
-  else
-    k_volume<NP, false, false, PARA, NVL, 1><<<nBlocks, D::NP3, VolSmem<NP, false, false, PARA, 1>::BYTES, s>>>(a);
-  return cudaGetLastError();
+  if (PARA && lift == 2) return elem_launch(k_volume<NP, GLN, false, PARA, NVL, 2>, nBlocks, VolSmem<NP, GLN, false, PARA, 2>::BYTES, s, a);
+  return elem_launch(k_volume<NP, GLN, false, PARA, NVL, 1>, nBlocks, VolSmem<NP, GLN, false, PARA, 1>::BYTES, s, a);
 }
+#if FLEXI_NP <= 10
 template <bool SPLIT, int STYPE, bool PARA, int NVL>
 cudaError_t volume_gl_setup() {
   using C = VolGLCfg<NP, KPT, SPLIT, PARA>;
@@ -152,6 +176,7 @@ cudaError_t gl2_launch(int lift, const VolArgs& a, int nBlocks, cudaStream_t s) 
   return gl2_launch_v<STYPE, PARA, NVL, false>(lift, a, nBlocks, s);
 }
 
+#endif  // FLEXI_NP <= 10
 
 constexpr size_t upd_smem = sizeof(double) * (D::NBASIS + 5 * D::NP3);
 
@@ -172,6 +197,16 @@ cudaError_t setup() {
   if ((e = volume_gs_setup1<true, 5, 2>()) != cudaSuccess) return e;
   if ((e = volume_gs_setup1<true, 4, 1>()) != cudaSuccess) return e;
   if ((e = volume_gs_setup1<true, 4, 2>()) != cudaSuccess) return e;
+#if FLEXI_NP > 10  // large degrees: Gauss-Lobatto nodes run the generic element kernel as well
+  if ((e = volume_setup<false, 5, true>()) != cudaSuccess) return e;
+  if ((e = volume_setup<true, 5, true>()) != cudaSuccess) return e;
+  if ((e = volume_setup<true, 4, true>()) != cudaSuccess) return e;
+  if ((e = volume_gs_setup1<false, 5, 1, true>()) != cudaSuccess) return e;
+  if ((e = volume_gs_setup1<true, 5, 1, true>()) != cudaSuccess) return e;
+  if ((e = volume_gs_setup1<true, 5, 2, true>()) != cudaSuccess) return e;
+  if ((e = volume_gs_setup1<true, 4, 1, true>()) != cudaSuccess) return e;
+  if ((e = volume_gs_setup1<true, 4, 2, true>()) != cudaSuccess) return e;
+#else
   if ((e = volume_gl_setup<false, 0, false, 5>()) != cudaSuccess) return e;
   if ((e = volume_gl_setup<false, 0, true, 5>()) != cudaSuccess) return e;
   if ((e = volume_gl_setup<false, 0, true, 4>()) != cudaSuccess) return e;
@@ -191,28 +226,31 @@ cudaError_t setup() {
     FX_SPLIT_TYPES(X)
 #undef X
   }
+#endif  // FLEXI_NP > 10
 #define X(GLv, ENTv, FILTv, SPv) \
-  if ((e = cudaFuncSetAttribute(k_update<NP, GLv, ENTv, FILTv, SPv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem)) != cudaSuccess) return e;
+  if ((e = elem_smem_attr(k_update<NP, GLv, ENTv, FILTv, SPv>, upd_smem)) != cudaSuccess) return e;
   X(true, false, false, false) X(false, false, false, false) X(false, true, false, false)
   X(true, false, true, false) X(false, false, true, false) X(false, true, true, false)
   X(true, false, false, true) X(false, false, false, true) X(false, true, false, true)
   X(true, false, true, true) X(false, false, true, true) X(false, true, true, true)
 #undef X
-  if ((e = cudaFuncSetAttribute(k_surfcorr<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (D::NBASIS + 5 * D::NP3)))) != cudaSuccess) return e;
-  const int pro = (int)(sizeof(double) * (D::NBASIS + 6 * D::NP3));
-  if ((e = cudaFuncSetAttribute(k_prolong<NP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pro)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(k_prolong<NP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pro)) != cudaSuccess) return e;
+  if ((e = elem_smem_attr(k_surfcorr<NP>, sizeof(double) * (D::NBASIS + 5 * D::NP3))) != cudaSuccess) return e;
+  const size_t pro = sizeof(double) * (D::NBASIS + 6 * D::NP3);
+  if ((e = elem_smem_attr(k_prolong<NP, true>, pro)) != cudaSuccess) return e;
+  if ((e = elem_smem_attr(k_prolong<NP, false>, pro)) != cudaSuccess) return e;
+  if (D::PAIR) {
+    if ((e = elem_smem_attr(k_surfint<NP, true>, sizeof(double) * D::NBASIS)) != cudaSuccess) return e;
+    if ((e = elem_smem_attr(k_surfint<NP, false>, sizeof(double) * D::NBASIS)) != cudaSuccess) return e;
+    if ((e = elem_smem_attr(k_filter<NP>, sizeof(double) * 5 * D::NP3)) != cudaSuccess) return e;
+  }
   return cudaSuccess;
 }
 
 cudaError_t prolong(bool gl, const ProArgs& a, int nElems, cudaStream_t s) {
   if (a.nv > 6) return cudaErrorInvalidValue;
   const size_t sm = sizeof(double) * (D::NBASIS + (size_t)a.nv * D::NP3);
-  if (gl)
-    k_prolong<NP, true><<<nElems, D::NP3, sm, s>>>(a);
-  else
-    k_prolong<NP, false><<<nElems, D::NP3, sm, s>>>(a);
-  return cudaGetLastError();
+  if (gl) return elem_launch(k_prolong<NP, true>, nElems, sm, s, a);
+  return elem_launch(k_prolong<NP, false>, nElems, sm, s, a);
 }
 
 cudaError_t volume(bool gl, bool split, int stype, bool para, int nvl, const VolArgs& a, int nBlocks, cudaStream_t s) {
@@ -226,6 +264,14 @@ cudaError_t volume(bool gl, bool split, int stype, bool para, int nvl, const Vol
     if (!para) return volume_launch<false, 5>(lift, a, nBlocks, s);
     return nvl == 5 ? volume_launch<true, 5>(lift, a, nBlocks, s) : volume_launch<true, 4>(lift, a, nBlocks, s);
   }
+#if FLEXI_NP > 10
+  if (!split) {
+    if (!para) return volume_launch<false, 5, true>(lift, a, nBlocks, s);
+    return nvl == 5 ? volume_launch<true, 5, true>(lift, a, nBlocks, s) : volume_launch<true, 4, true>(lift, a, nBlocks, s);
+  }
+  if (!para) return volume_gs_launch<false, 5, true>(lift, a, nBlocks, s);
+  return nvl == 5 ? volume_gs_launch<true, 5, true>(lift, a, nBlocks, s) : volume_gs_launch<true, 4, true>(lift, a, nBlocks, s);
+#else
   if (!split) {
     if (!para) return volume_gl_launch<false, 0, false, 5>(lift, a, nBlocks, s);
     return nvl == 5 ? volume_gl_launch<false, 0, true, 5>(lift, a, nBlocks, s) : volume_gl_launch<false, 0, true, 4>(lift, a, nBlocks, s);
@@ -254,6 +300,7 @@ cudaError_t volume(bool gl, bool split, int stype, bool para, int nvl, const Vol
 #else
   return cudaErrorNotSupported;  // even NP and the D matrices are not centro-antisymmetric: not Gauss-Lobatto operators
 #endif
+#endif  // FLEXI_NP > 10
 }
 
 cudaError_t bc_pre(const BCArgs& a, cudaStream_t s) {
@@ -281,8 +328,7 @@ cudaError_t flux(const FluxArgs& a, cudaStream_t s) {
 
 template <bool GL, bool ENT, bool FILT, bool SPONGE>
 cudaError_t update_launch(const UpdArgs& a, int nBlocks, cudaStream_t s) {
-  k_update<NP, GL, ENT, FILT, SPONGE><<<nBlocks, D::NP3, upd_smem, s>>>(a);
-  return cudaGetLastError();
+  return elem_launch(k_update<NP, GL, ENT, FILT, SPONGE>, nBlocks, upd_smem, s, a);
 }
 template <bool FILT, bool SPONGE>
 cudaError_t update_nodes(bool gl, const UpdArgs& a, int nBlocks, cudaStream_t s) {
@@ -299,17 +345,13 @@ cudaError_t update(bool gl, const UpdArgs& a, int nBlocks, cudaStream_t s) {
 
 cudaError_t surfcorr(const SurfCorrArgs& a, int nBlocks, cudaStream_t s) {
   if (nBlocks <= 0) return cudaSuccess;
-  k_surfcorr<NP><<<nBlocks, D::NP3, sizeof(double) * (D::NBASIS + 5 * D::NP3), s>>>(a);
-  return cudaGetLastError();
+  return elem_launch(k_surfcorr<NP>, nBlocks, sizeof(double) * (D::NBASIS + 5 * D::NP3), s, a);
 }
 
 cudaError_t surfint(bool gl, const SurfArgs& a, int nElems, cudaStream_t s) {
   const size_t sm = sizeof(double) * D::NBASIS;
-  if (gl)
-    k_surfint<NP, true><<<nElems, D::NP3, sm, s>>>(a);
-  else
-    k_surfint<NP, false><<<nElems, D::NP3, sm, s>>>(a);
-  return cudaGetLastError();
+  if (gl) return elem_launch(k_surfint<NP, true>, nElems, sm, s, a);
+  return elem_launch(k_surfint<NP, false>, nElems, sm, s, a);
 }
 
 cudaError_t dt(const DtArgs& a, int nElems, cudaStream_t s) {
@@ -319,8 +361,7 @@ cudaError_t dt(const DtArgs& a, int nElems, cudaStream_t s) {
 
 cudaError_t filter(const FiltArgs& a, int nElems, cudaStream_t s) {
   if (nElems <= 0) return cudaSuccess;
-  k_filter<NP><<<nElems, D::NP3, sizeof(double) * 5 * D::NP3, s>>>(a);  // <= 40 KB at NP = 10: no opt-in needed
-  return cudaGetLastError();
+  return elem_launch(k_filter<NP>, nElems, sizeof(double) * 5 * D::NP3, s, a);  // <= 40 KB at NP = 10: no opt-in needed
 }
 
 const NpOps ops = {NP, setup, prolong, volume, flux, update, surfcorr, surfint, dt, bc_pre, flux_bc, filter};

@@ -1,6 +1,6 @@
 // np_ops.h -- per-polynomial-degree launch table.  kernels.cuh is instantiated once per NP = N+1 in its own translation
 // unit (np_kernels.cu compiled with -DFLEXI_NP=<NP>), so the degrees build in parallel; the host picks the table at init
-// (the reference fixes PP_N at compile time, src/CMakeLists.txt:23-60 -- here it is a run-time choice among N = 1..9).
+// (the reference fixes PP_N at compile time, src/CMakeLists.txt:23-60 -- here it is a run-time choice among N = 1..9 and 11).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -35,3 +35,4 @@ FX_DECLARE_OPS(7)
 FX_DECLARE_OPS(8)
 FX_DECLARE_OPS(9)
 FX_DECLARE_OPS(10)
+FX_DECLARE_OPS(12)

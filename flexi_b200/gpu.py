@@ -31,7 +31,7 @@ KERNEL_CLASSES = ("volume", "flux", "update", "prolong", "calc_timestep", "layou
 EXPORTS = ("flexi_gpu_last_error", "flexi_gpu_abi_version", "flexi_gpu_nccl_unique_id", "flexi_gpu_init", "flexi_gpu_finalize",
            "flexi_gpu_set_state", "flexi_gpu_get_state", "flexi_gpu_dg_time_derivative", "flexi_gpu_timestep",
            "flexi_gpu_timestep_n", "flexi_gpu_calc_timestep", "flexi_gpu_get_array", "flexi_gpu_keep_gradients",
-           "flexi_gpu_prolong_to_face", "flexi_gpu_surf_int", "flexi_gpu_analyze_tgv", "flexi_gpu_calc_error_norms", "flexi_gpu_calc_body_forces", "flexi_gpu_set_face_metrics", "flexi_gpu_set_overintegration", "flexi_gpu_set_overintegration_cons", "flexi_gpu_set_filter", "flexi_gpu_set_sponge", "flexi_gpu_set_viscosity", "flexi_gpu_pin_host_array", "flexi_gpu_unpin_host_array", "flexi_gpu_counters", "flexi_gpu_kernel_times",
+           "flexi_gpu_prolong_to_face", "flexi_gpu_surf_int", "flexi_gpu_analyze_tgv", "flexi_gpu_calc_error_norms", "flexi_gpu_calc_body_forces", "flexi_gpu_set_face_metrics", "flexi_gpu_set_overintegration", "flexi_gpu_set_overintegration_cons", "flexi_gpu_set_filter", "flexi_gpu_set_filter_laf", "flexi_gpu_get_filter_laf", "flexi_gpu_set_sponge", "flexi_gpu_set_viscosity", "flexi_gpu_pin_host_array", "flexi_gpu_unpin_host_array", "flexi_gpu_counters", "flexi_gpu_kernel_times",
            "flexi_gpu_set_profiling", "flexi_gpu_synchronize", "flexi_gpu_stream")
 
 
@@ -77,6 +77,8 @@ def lib():
     L.flexi_gpu_set_overintegration.argtypes = [P, C.c_int, PD]
     L.flexi_gpu_set_filter.argtypes = [P, C.c_int, PD]
     L.flexi_gpu_set_overintegration_cons.argtypes = [P, I32, PD, PD, PD]
+    L.flexi_gpu_set_filter_laf.argtypes = [P, PD, PD, C.c_double, C.c_double]
+    L.flexi_gpu_get_filter_laf.argtypes = [P, PD, PD, PD]
     L.flexi_gpu_set_sponge.argtypes = [P, I32, C.POINTER(C.c_int32), PD, PD]
     L.flexi_gpu_set_viscosity.argtypes = [P, I32, C.c_double, C.c_double, C.c_double, C.c_double]
     L.flexi_gpu_pin_host_array.argtypes = [P, C.c_int64]
@@ -217,6 +219,19 @@ class FlexiGpu:
         b = np.asfortranarray(vdm_nunder_n, dtype=np.float64)
         c = np.ascontiguousarray(sj_nunder, dtype=np.float64)
         self._ck(self.L.flexi_gpu_set_overintegration_cons(self.h, int(n_under), _pd(a), _pd(b), _pd(c)))
+
+    def set_filter_laf(self, mat, integration_weight, norm_mod, laf_alpha=1.0):
+        """FilterType 3 (LAF): cut-off FilterMat[out, in] of NFilter, IntegrationWeight [nElems,k,j,i], normMod, LAF_alpha."""
+        m = np.asfortranarray(mat, dtype=np.float64)
+        iw = np.ascontiguousarray(integration_weight, dtype=np.float64)
+        self._ck(self.L.flexi_gpu_set_filter_laf(self.h, _pd(m), _pd(iw), float(norm_mod), float(laf_alpha)))
+
+    def get_filter_laf(self):
+        """(eRatio, lim, r) per element: the ElemData arrays LAF_eRatio / LAF_lim / LAF_r."""
+        n = self.nElems
+        a, b, c = np.zeros(n), np.zeros(n), np.zeros(n)
+        self._ck(self.L.flexi_gpu_get_filter_laf(self.h, _pd(a), _pd(b), _pd(c)))
+        return a, b, c
 
     def set_viscosity(self, visc_type=0, Ts=0.0, Tref=1.0, ExpoSuth=0.0, cSuth=0.0):
         """PP_VISC (0 constant, 1 Sutherland, 2 power law) with the MOD_EOS_Vars values after InitEos (see sutherland_params)."""

@@ -304,3 +304,12 @@ def overintegration_cons(n, node_type, n_under, sJ):
     jac = 1.0 / np.asarray(sJ)
     jac_u = np.einsum("li,mj,nk,ekji->enml", vdm_down, vdm_down, vdm_down, jac)
     return vdm_down, vdm_up, np.ascontiguousarray(1.0 / jac_u)
+
+
+def laf_params(n, n_filter, w_gp, sJ):
+    """InitFilter for FILTERTYPE_LAF (filter/filter.f90:149-186): IntegrationWeight [nElems,k,j,i] = wGP(i)wGP(j)wGP(k)/sJ normalised to
+    sum 1 per element, and normMod."""
+    iw = np.einsum("k,j,i->kji", w_gp, w_gp, w_gp)[None] / np.asarray(sJ)
+    iw = iw / iw.reshape(len(iw), -1).sum(axis=1)[:, None, None, None]
+    norm_mod = ((n_filter + 1.0) ** (-2.0 / 3.0) - 2.0 ** (-2.0 / 3.0)) / ((n + 1.0) ** (-2.0 / 3.0) - (n_filter + 1.0) ** (-2.0 / 3.0))
+    return np.ascontiguousarray(iw), norm_mod

@@ -77,7 +77,7 @@ typedef struct flexi_gpu_desc {
   int32_t struct_bytes; /* sizeof(flexi_gpu_desc) as seen by the caller */
 
   /* ---- build options of the reference, run-time here (src/CMakeLists.txt:23-230) ---- */
-  int32_t N;           /* PP_N, 1..9 */
+  int32_t N;           /* PP_N, 1..9 or 11 */
   int32_t nodeType;    /* PP_NodeType */
   int32_t splitDG;     /* SPLIT_DG: 0 = weak form (VolInt_weakForm), 1 = split form (VolInt_splitForm) */
   int32_t parabolic;   /* PARABOLIC: 0 = Euler, 1 = Navier-Stokes */
@@ -285,9 +285,18 @@ int flexi_gpu_set_overintegration_cons(flexi_gpu_handle* h, int32_t NUnder, cons
 
 /* Solution filter (MOD_Filter, filter/filter.f90:67-72,135-196,264-288; dg.f90:329-330): filterType 0 = none, 1 = cutoff,
  * 2 = modal (Hesthaven) -- both apply the host's FilterMat (0:N,0:N) (Fortran order) to U in place at the start of every DG
- * operator evaluation, as the reference does.  3 (LAF) returns FLEXI_GPU_ERR_UNSUPPORTED.  On multi-rank runs the traces of
+ * operator evaluation, as the reference does.  3 (LAF) has its own entry below.  On multi-rank runs the traces of
  * the filtered state are prolonged and exchanged at the start of the evaluation (the stages then skip their own trace exchange). */
 int flexi_gpu_set_filter(flexi_gpu_handle* h, int filterType, const double* FilterMat);
+/* FilterType = 3, LAF (filter/filter.f90:149-186,295-448; Flad et al., JCP 2016): per element, the cut-off filtered state of NFilter
+ * replaces U only where the kinetic energy of the filtered-out velocity scales, relative to that of the resolved fluctuations and
+ * times normMod, exceeds the element's adaptive limit (lim, updated from the energy transfer between two calls).  Pass the cut-off
+ * FilterMat(0:N,0:N) of NFilter, IntegrationWeight(0:N,0:N,0:N,nElems) (normalised per element, filter.f90:166-181), normMod (:184)
+ * and LAF_alpha; the per-element state starts as InitFilter leaves it (lim = 1e-8, r = 0, old energies 1e-16).
+ * flexi_gpu_get_filter_laf returns the ElemData arrays LAF_eRatio, LAF_lim, LAF_r (nElems each; NULL = skip). */
+int flexi_gpu_set_filter_laf(flexi_gpu_handle* h, const double* FilterMat, const double* IntegrationWeight, double normMod,
+                             double LAF_alpha);
+int flexi_gpu_get_filter_laf(flexi_gpu_handle* h, double* eRatio, double* lim, double* r);
 
 /* Viscosity law, the reference's build option FLEXI_VISCOSITY / PP_VISC (eos.h:73-87, viscosity.f90:57-90): 0 = constant mu0
  * (default), 1 = Sutherland, 2 = power law.  Pass the MOD_EOS_Vars values as InitEos leaves them (eos.f90:160-192): for Sutherland

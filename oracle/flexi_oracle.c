@@ -62,6 +62,11 @@ typedef struct oracle {
   double *Ja_Face, *Ja_slave;     /* (3,3,0:N,0:N,nSides), mesh_vars.f90:70-78; set by oracle_set_face_metrics */
   /* sponge (sponge/sponge_vars.f90): SpongeMap(nSpongeElems) 1-based element ids, SpongeMat(0:N,0:N,0:N,nSpongeElems) pre-multiplied
      by the Jacobian, SpBaseFlow(5,0:N,0:N,0:N,nElems); set by oracle_set_sponge */
+  /* FilterType 3, LAF (filter.f90:149-186,295-448): per-element state + IntegrationWeight(0:N,0:N,0:N,nElems), normMod, LAF_alpha;
+     laf != 0 switches Filter_Pointer to Filter_LAF (with FilterMat = the cut-off matrix of NFilter) */
+  int laf;
+  double *laf_lim, *laf_eRatio, *laf_r, *laf_ekin_old, *laf_fluc_old, *laf_iw;
+  double laf_normMod, laf_alpha;
   /* PP_VISC (eos.h:73-87): 0 constant, 1 Sutherland, 2 power law; MOD_EOS_Vars values after InitEos; set by oracle_set_viscosity */
   int visc;
   double Tref, Ts, ExpoSuth, cSuth;
@@ -1541,6 +1546,51 @@ static void filter_volume(const oracle* o, const double* Mat, double* U) {
   free(b2);
 }
 
+/* filter.f90:295-448 Filter_LAF: per element, the cut-off filtered state, the kinetic energy of the filtered-out velocity scales
+   and of the resolved fluctuations, their ratio against an adaptive limit; U is replaced by its filtered version only where the
+   ratio exceeds the limit.  Loop and summation order as in the Fortran. */
+static void filter_laf(oracle* o) {
+  const int np = o->np;
+  const size_t n3 = (size_t)np * np * np, ne = n3 * NVAR;
+  double* Uf = (double*)xcalloc(ne, 8);
+  for (int e = 0; e < o->d.nElems; ++e) {
+    double* Ue = o->U + (size_t)e * ne;
+    memcpy(Uf, Ue, ne * 8);
+    { /* U_filtered = Filter(U_in) of this element (same three sweeps as filter_volume) */
+      oracle one = *o;
+      one.d.nElems = 1;
+      filter_volume(&one, o->FilterMat, Uf);
+    }
+    const double* iw = o->laf_iw + (size_t)e * n3;
+    double Uavg[3] = {0., 0., 0.};
+    for (size_t n = 0; n < n3; ++n)
+      for (int c = 0; c < 3; ++c) Uavg[c] = Uavg[c] + Uf[n * NVAR + 1 + c] / Ue[n * NVAR] * iw[n];
+    double ekin_avg = 0., ekin_fluc_avg = 0.;
+    for (size_t n = 0; n < n3; ++n) {
+      const double rho = Ue[n * NVAR];
+      const double f1 = Ue[n * NVAR + 1] - Uf[n * NVAR + 1], f2 = Ue[n * NVAR + 2] - Uf[n * NVAR + 2], f3 = Ue[n * NVAR + 3] - Uf[n * NVAR + 3];
+      ekin_fluc_avg = ekin_fluc_avg + (f1 * f1 / (rho * rho) + f3 * f3 / (rho * rho) + f2 * f2 / (rho * rho)) * iw[n];
+      const double a1 = Uf[n * NVAR + 1] - Uavg[0], a2 = Uf[n * NVAR + 2] - Uavg[1], a3 = Uf[n * NVAR + 3] - Uavg[2];
+      ekin_avg = ekin_avg + (a1 * a1 / (rho * rho) + a2 * a2 / (rho * rho) + a3 * a3 / (rho * rho)) * iw[n];
+    }
+    o->laf_eRatio[e] = (ekin_fluc_avg / ekin_avg) * o->laf_normMod;
+    o->laf_lim[e] = fmax(o->laf_lim[e], 1.0E-8);
+    const double dfluc = ekin_fluc_avg - o->laf_fluc_old[e];
+    const double dedt_lim = fabs(ekin_avg - o->laf_ekin_old[e]) / dfluc;
+    if (dedt_lim > 1.0 && dfluc > 0.) {
+      o->laf_lim[e] = o->laf_eRatio[e];
+    } else if (dfluc < 0.) {
+      o->laf_lim[e] = o->laf_eRatio[e];
+    } else if (o->laf_eRatio[e] > o->laf_lim[e] * o->laf_alpha) {
+      memcpy(Ue, Uf, ne * 8);
+      o->laf_r[e] = o->laf_r[e] + 1.;
+    }
+    o->laf_ekin_old[e] = ekin_avg;
+    o->laf_fluc_old[e] = ekin_fluc_avg;
+  }
+  free(Uf);
+}
+
 /* overintegration.f90:181-330 FilterConservative: JU_t on N -> projection to NUnder (ChangeBasisVolume with Vdm_N_NUnder) -> times
    sJNUnder -> interpolation back to N (Vdm_NUnder_N).  Sums run over ascending input index like ChangeBasisVolume. */
 static void filter_conservative(const oracle* o, double* U) {
@@ -1850,7 +1900,8 @@ void oracle_world_dg_time_derivative(oracle_world* w, double t) {
   const int szs = NVAR * np * np;
   FOR_RANKS {
     oracle* o = w->r[r];
-    if (o->FilterMat) filter_volume(o, o->FilterMat, o->U);  /* 1. dg.f90:329-330: Filter_Pointer(U,FilterMat), in place */
+    if (o->FilterMat && o->laf) filter_laf(o);               /* 1. dg.f90:329-330 with Filter_Pointer => Filter_LAF */
+    else if (o->FilterMat) filter_volume(o, o->FilterMat, o->U);  /* 1. dg.f90:329-330: Filter_Pointer(U,FilterMat), in place */
     cons_to_prim_volume(o);                                  /* 2. */
     if (entropy_vars(o)) {
       cons_to_entropy_volume(o);                             /* ConsToPrimToEntropy, dg.f90:333-337 */
@@ -2186,6 +2237,39 @@ int oracle_set_overintegration_cons(oracle* o, int NUnder, const double* Vdm_N_N
   return 0;
 }
 void oracle_filter_conservative(oracle* o, double* JU) { filter_conservative(o, JU); }
+/* FilterType 3 (LAF): call oracle_set_filter(o, 1, cut-off FilterMat of NFilter) first, then this with IntegrationWeight
+   (0:N,0:N,0:N,nElems), normMod and LAF_alpha (filter.f90:149-186); the per-element state starts as InitFilter leaves it.
+   IntegrationWeight == NULL switches LAF off again. */
+int oracle_set_filter_laf(oracle* o, const double* IntegrationWeight, double normMod, double LAF_alpha) {
+  free(o->laf_lim); free(o->laf_eRatio); free(o->laf_r); free(o->laf_ekin_old); free(o->laf_fluc_old); free(o->laf_iw);
+  o->laf_lim = o->laf_eRatio = o->laf_r = o->laf_ekin_old = o->laf_fluc_old = o->laf_iw = NULL;
+  o->laf = 0;
+  if (!IntegrationWeight) return 0;
+  const size_t nE = (size_t)o->d.nElems, n3 = (size_t)o->np * o->np * o->np;
+  o->laf_lim = (double*)xcalloc(nE, 8);
+  o->laf_eRatio = (double*)xcalloc(nE, 8);
+  o->laf_r = (double*)xcalloc(nE, 8);
+  o->laf_ekin_old = (double*)xcalloc(nE, 8);
+  o->laf_fluc_old = (double*)xcalloc(nE, 8);
+  o->laf_iw = (double*)xcalloc(nE * n3, 8);
+  memcpy(o->laf_iw, IntegrationWeight, nE * n3 * 8);
+  for (size_t e = 0; e < nE; ++e) {
+    o->laf_lim[e] = 1E-8;
+    o->laf_ekin_old[e] = 1.E-16;
+    o->laf_fluc_old[e] = 1.E-16;
+  }
+  o->laf_normMod = normMod;
+  o->laf_alpha = LAF_alpha;
+  o->laf = 1;
+  return 0;
+}
+/* ElemData of the LAF filter: eRatio, lim, r (nElems each) */
+void oracle_get_filter_laf(const oracle* o, double* eRatio, double* lim, double* r) {
+  const size_t nE = (size_t)o->d.nElems;
+  memcpy(eRatio, o->laf_eRatio, nE * 8);
+  memcpy(lim, o->laf_lim, nE * 8);
+  memcpy(r, o->laf_r, nE * 8);
+}
 /* FilterType (filter/filter.f90:67-72,135-196): 0 none; 1 cutoff and 2 modal (Hesthaven) both point Filter_Pointer at Filter with
    the host-built FilterMat (:138-190); 3 (LAF) is not restated. */
 int oracle_set_filter(oracle* o, int type, const double* Mat) {
@@ -2211,6 +2295,7 @@ void oracle_destroy(oracle* o) {
   free(o->Vdm_N_NUnder);
   free(o->Vdm_NUnder_N);
   free(o->sJNUnder);
+  free(o->laf_lim); free(o->laf_eRatio); free(o->laf_r); free(o->laf_ekin_old); free(o->laf_fluc_old); free(o->laf_iw);
   for (int i = 0; i < o->n_owned; ++i) free(o->owned[i]);
   double* st[] = {o->U, o->Ut, o->Ut_tmp, o->UPrim, o->U_master, o->U_slave, o->UPrim_master, o->UPrim_slave, o->Flux_master,
                   o->Flux_slave, o->gradUx, o->gradUy, o->gradUz, o->gradUx_master, o->gradUy_master, o->gradUz_master,

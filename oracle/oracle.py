@@ -56,6 +56,9 @@ def _load(fast=False):
     lib.oracle_set_overintegration_cons.argtypes = [P, C.c_int, PD, PD, PD]
     lib.oracle_set_overintegration_cons.restype = C.c_int
     lib.oracle_filter_conservative.argtypes = [P, PD]
+    lib.oracle_set_filter_laf.argtypes = [P, PD, C.c_double, C.c_double]
+    lib.oracle_set_filter_laf.restype = C.c_int
+    lib.oracle_get_filter_laf.argtypes = [P, PD, PD, PD]
     lib.oracle_set_viscosity.argtypes = [P, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double]
     lib.oracle_set_viscosity.restype = C.c_int
     lib.oracle_set_sponge.argtypes = [P, C.c_int, C.POINTER(C.c_int32), PD, PD]
@@ -112,6 +115,22 @@ class OracleRank:
         out = np.ascontiguousarray(JU, dtype=np.float64).copy()
         self.lib.oracle_filter_conservative(self.h, _pd(out))
         return out
+
+    def set_filter_laf(self, integration_weight=None, norm_mod=0.0, laf_alpha=1.0):
+        """FilterType 3 (LAF, filter.f90:149-186,295-448): call set_filter(1, cut-off FilterMat of NFilter) first; IntegrationWeight
+        [nElems,k,j,i] (normalised per element), normMod, LAF_alpha; None = off."""
+        if integration_weight is None:
+            assert self.lib.oracle_set_filter_laf(self.h, None, 0.0, 1.0) == 0
+            return
+        iw = np.ascontiguousarray(integration_weight, dtype=np.float64)
+        assert self.lib.oracle_set_filter_laf(self.h, _pd(iw), float(norm_mod), float(laf_alpha)) == 0
+
+    def get_filter_laf(self):
+        """(eRatio, lim, r) per element: the ElemData arrays LAF_eRatio / LAF_lim / LAF_r."""
+        n = self.desc.nElems
+        a, b, c = np.zeros(n), np.zeros(n), np.zeros(n)
+        self.lib.oracle_get_filter_laf(self.h, _pd(a), _pd(b), _pd(c))
+        return a, b, c
 
     def set_viscosity(self, visc_type=0, Ts=0.0, Tref=1.0, ExpoSuth=0.0, cSuth=0.0):
         """PP_VISC 0/1/2 with the MOD_EOS_Vars values after InitEos (eos.f90:160-192)."""

@@ -463,3 +463,68 @@ def test_overintegration_conservative_cutoff(node):
     w.dg_time_derivative(0.0)
     assert np.array_equal(np.array(o.array("Ut")), ut_plain)
     w.close()
+
+
+def _laf_numpy(U, Uf, iw, st, norm_mod, alpha):
+    """Independent vectorised restatement of Filter_LAF's decision (filter.f90:381-446) for one call: returns the new state of U
+    and updates st = dict(lim, ekin_old, fluc_old, r) in place; eRatio is returned too."""
+    rho = U[..., 0]
+    vel_f = Uf[..., 1:4] / rho[..., None]
+    avg = np.einsum("ekjic,ekji->ec", vel_f, iw)
+    fluc = np.einsum("ekjic,ekji->e", ((U[..., 1:4] - Uf[..., 1:4]) / rho[..., None]) ** 2, iw)
+    ekin = np.einsum("ekjic,ekji->e", ((Uf[..., 1:4] - avg[:, None, None, None, :]) / rho[..., None]) ** 2, iw)
+    ratio = fluc / ekin * norm_mod
+    lim = np.maximum(st["lim"], 1e-8)
+    dfluc = fluc - st["fluc_old"]
+    with np.errstate(invalid="ignore", divide="ignore"):  # 0/0 for an unchanged element: NaN compares false like in the Fortran
+        dedt = np.abs(ekin - st["ekin_old"]) / dfluc
+    follow = ((dedt > 1.0) & (dfluc > 0.0)) | (dfluc < 0.0)
+    do = ~follow & (ratio > lim * alpha)
+    st["lim"] = np.where(follow, ratio, lim)
+    st["r"] = st["r"] + do
+    st["ekin_old"], st["fluc_old"] = ekin, fluc
+    out = np.where(do[:, None, None, None, None], Uf, U)
+    return out, ratio, do
+
+
+def test_laf_filter_against_independent_restatement():
+    """FilterType 3, LAF (filter.f90:149-186,295-448): the oracle's Filter_LAF against a vectorised numpy restatement over three
+    consecutive operator evaluations (the per-element limit adapts between calls), on a state with resolved and unresolved
+    elements so that both branches (filter / keep) occur; eRatio, lim, r and the state U itself are compared."""
+    N, NF = 5, 2
+    eqn = dict(parabolic=True, riemann="roe", mu0=1e-2)
+    ranks, w = world(BoxSpec((3, 2, 2), x0=(-1.0, -1.0, -1.0), length=(2.0, 2.0, 2.0), ngeo=2, deform=0.1), N, B.NODE_GAUSS, eqn)
+    r, o = ranks[0], w.ranks[0]
+    U = r.eqn.smooth_state(r.mesh.Elem_xGP, length=2.0)
+    rng = np.random.default_rng(5)
+    nE = U.shape[0]
+    # under-resolved content in every other element: node-to-node noise on the momenta
+    U[::2, ..., 1:4] += 0.05 * rng.normal(size=U[::2, ..., 1:4].shape)
+    mat = B.overintegration_mat(r.basis.xGP, NF)
+    iw, norm_mod = B.laf_params(N, NF, r.basis.wGP, r.mesh.sJ)
+    assert np.allclose(iw.reshape(nE, -1).sum(axis=1), 1.0, rtol=1e-14)
+    alpha = 1.0
+    o.set_filter(1, mat)
+    o.set_filter_laf(iw, norm_mod, alpha)
+    st = dict(lim=np.full(nE, 1e-8), ekin_old=np.full(nE, 1e-16), fluc_old=np.full(nE, 1e-16), r=np.zeros(nE))
+    w.set_state([U])
+    seen = set()
+    for it in range(3):
+        Uin = np.array(o.array("U"))
+        ref, ratio, do = _laf_numpy(Uin, B.change_basis_3d(mat, Uin), iw, st, norm_mod, alpha)
+        w.dg_time_derivative(0.0)
+        e_ratio, lim, rr = o.get_filter_laf()
+        assert np.max(np.abs(e_ratio - ratio)) <= 1e-11 * np.max(np.abs(ratio))
+        assert np.max(np.abs(lim - st["lim"])) <= 1e-11 * np.max(np.abs(st["lim"]))
+        assert np.array_equal(rr, st["r"])
+        assert np.max(np.abs(np.array(o.array("U")) - ref)) <= 1e-13 * np.max(np.abs(ref))
+        seen |= set(do.tolist())
+        # between the calls: perturb the state the way a time step would (new fluctuations in some elements)
+        if it < 2:
+            V = np.array(o.array("U"))
+            V[1::3, ..., 1:4] += 0.02 * (it + 1) * rng.normal(size=V[1::3, ..., 1:4].shape)
+            w.set_state([V])
+    assert seen == {True, False}, "both the filtering and the keeping branch have to occur"
+    o.set_filter_laf(None)
+    o.set_filter(0)
+    w.close()

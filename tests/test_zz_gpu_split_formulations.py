@@ -340,3 +340,76 @@ def test_overintegration_conservative_cutoff_matches_oracle(N, NU, node, eqn):
     finally:
         g.close()
         w.close()
+
+
+@pytest.mark.parametrize("N,NF,node,eqn", [
+    (7, 3, GL, dict(parabolic=True, split_dg=True, split_dg_type="pi", riemann="lf", mu0=1e-2)),
+    (5, 2, G, dict(parabolic=True, riemann="roe", mu0=1e-2)),
+], ids=["N7-GL-split", "N5-G-weak"])
+def test_laf_filter_matches_oracle(N, NF, node, eqn):
+    """FilterType 3, LAF (flexi_gpu_set_filter_laf; filter.f90:295-448): per element the cut-off filtered state replaces U only where
+    the energy ratio exceeds the adaptive limit.  Two operators (the first initialises the limits, before the second some elements get new fluctuations: both branches
+    occur), then 2 LSERK steps (5 filter calls each; the limits adapt from call to call); eRatio / lim / r and the state against the oracle."""
+    r = build_case(BoxSpec((3, 2, 2), **CURVED), N, node, eqn)[0]
+    U0 = r.eqn.smooth_state(r.mesh.Elem_xGP, length=2.0)
+    rng = np.random.default_rng(5)
+    U0[::2, ..., 1:4] += 0.05 * rng.normal(size=U0[::2, ..., 1:4].shape)
+    mat = B.overintegration_mat(r.basis.xGP, NF)
+    iw, norm_mod = B.laf_params(N, NF, r.basis.wGP, r.mesh.sJ)
+    w = O.OracleWorld([(r.desc, r.keep)])
+    o = w.ranks[0]
+    o.set_filter(1, mat)
+    o.set_filter_laf(iw, norm_mod, 1.0)
+    w.set_state([U0])
+    g = FlexiGpu(r)
+    try:
+        g.set_filter_laf(mat, iw, norm_mod, 1.0)
+        g.set_state(U0)
+        w.dg_time_derivative(0.0)
+        ut, ref = g.DGTimeDerivative_weakForm(0.0), o.array("Ut")
+        scale = np.max(np.abs(ref).reshape(-1, 5), axis=0)
+        assert np.all(np.max(np.abs(ut - ref).reshape(-1, 5), axis=0) <= 1e-12 * scale)
+        Ug, Uo = g.get_state(), o.array("U")
+        assert np.max(np.abs(Ug - Uo)) <= 1e-13 * np.max(np.abs(Uo))
+        (ea, la, ra), (eb, lb, rb) = g.get_filter_laf(), o.get_filter_laf()
+        assert np.max(np.abs(ea - eb)) <= 1e-11 * np.max(np.abs(eb))
+        assert np.max(np.abs(la - lb)) <= 1e-11 * np.max(np.abs(lb))
+        assert np.array_equal(ra, rb)
+        # the first call only initialises the limits (old energies 1e-16); new fluctuations in every third element, second call
+        V = np.array(Uo)
+        V[1::3, ..., 1:4] += 0.02 * rng.normal(size=V[1::3, ..., 1:4].shape)
+        w.set_state([V])
+        g.set_state(V)
+        w.dg_time_derivative(0.0)
+        ut, ref = g.DGTimeDerivative_weakForm(0.0), o.array("Ut")
+        scale = np.max(np.abs(ref).reshape(-1, 5), axis=0)
+        assert np.all(np.max(np.abs(ut - ref).reshape(-1, 5), axis=0) <= 1e-12 * scale)
+        (ea, la, ra), (eb, lb, rb) = g.get_filter_laf(), o.get_filter_laf()
+        assert np.array_equal(ra, rb)
+        assert 0 < rb.sum() < len(rb), "both branches of the LAF decision have to occur"
+        assert np.max(np.abs(la - lb)) <= 1e-11 * np.max(np.abs(lb))
+        Ug, Uo = g.get_state(), o.array("U")
+        assert np.max(np.abs(Ug - Uo)) <= 1e-13 * np.max(np.abs(Uo))
+        t = 0.0
+        for _ in range(2):
+            dt = w.calc_timestep()[0]
+            assert abs(g.CalcTimeStep()[0] - dt) <= 1e-13 * dt
+            w.timestep(t, dt)
+            g.TimeStep(t, dt)
+            t += dt
+        (ea, la, ra), (eb, lb, rb) = g.get_filter_laf(), o.get_filter_laf()
+        assert np.array_equal(ra, rb)
+        assert np.max(np.abs(ea - eb)) <= 1e-9 * np.max(np.abs(eb))
+        Ug, Uo = g.get_state(), o.array("U")
+        sc = np.max(np.abs(Uo).reshape(-1, 5), axis=0)
+        assert np.all(np.max(np.abs(Ug - Uo).reshape(-1, 5), axis=0) <= 1e-12 * sc)
+        g.set_filter(0)  # off again: the plain operator
+        o.set_filter_laf(None)
+        o.set_filter(0)
+        w.dg_time_derivative(t)
+        ut, ref = g.DGTimeDerivative_weakForm(t), o.array("Ut")
+        scale = np.max(np.abs(ref).reshape(-1, 5), axis=0)
+        assert np.all(np.max(np.abs(ut - ref).reshape(-1, 5), axis=0) <= 1e-12 * scale)
+    finally:
+        g.close()
+        w.close()
