@@ -102,3 +102,26 @@ def calc_body_forces(basis, eqn, mesh, boundary_type, U_master, gradUx_master, g
         Fv[b] -= dfv.sum(axis=(0, 1))
         Mv[b] -= np.cross(r, dfv).sum(axis=(0, 1))
     return Fp, Fv, Mp, Mv
+
+
+def calc_timestep_elem(eqn, mesh, U):
+    """dtElem(nElems) of CalcTimeStep (equations/navierstokes/calctimestep.f90:140-210; MetricsAdv / MetricsVisc :42-83), the
+    ElemData array 'dt' FLEXI writes into its state files.  Constant viscosity; U as [e,k,j,i,5]."""
+    kappa = eqn.kappa
+    rho = U[..., 0]
+    v = U[..., 1:4] / rho[..., None]
+    p = (kappa - 1.0) * (U[..., 4] - 0.5 * rho * np.sum(v * v, axis=-1))
+    c = np.sqrt(kappa * p / rho)
+    sJ = mesh.sJ
+    lam, lam_v = [], []
+    kappas_pr = max(4.0 / 3.0, kappa / eqn.Pr)
+    for M in (mesh.Metrics_fTilde, mesh.Metrics_gTilde, mesh.Metrics_hTilde):
+        adv = sJ * np.sqrt(np.sum(M * M, axis=-1))
+        lam.append(np.max(np.abs(np.sum(M * (v * sJ[..., None]), axis=-1)) + c * adv, axis=(1, 2, 3)))
+        visc = kappas_pr * np.sum((M * sJ[..., None]) ** 2, axis=-1)
+        lam_v.append(np.max(eqn.mu0 / rho * visc, axis=(1, 2, 3)))
+    dt = eqn.CFLScale * 2.0 / (lam[0] + lam[1] + lam[2])
+    if eqn.parabolic:
+        sv = lam_v[0] + lam_v[1] + lam_v[2]
+        dt = np.where(sv > 0.0, np.minimum(dt, eqn.DFLScale * 4.0 / np.where(sv > 0.0, sv, 1.0)), dt)
+    return dt

@@ -254,40 +254,45 @@ def build_mesh(spec, N, node_type, rank=0, nranks=1, partition="linear", blocks=
     g2l[gids] = np.arange(nE)
 
     # ---- neighbour tables over (elem, locSide) -------------------------------------------------------------------------
-    ix, iy, iz = spec.ijk(gids)
-    idx = np.stack([ix, iy, iz], axis=1)
-    ori = spec.orient[gids]
-    nb_gid = np.zeros((nE, 6), dtype=np.int64)
-    nb_side = np.zeros((nE, 6), dtype=np.int64)       # local side (1-based) of the neighbour that faces this side
-    face_gid = np.zeros((nE, 6), dtype=np.int64)
-    bc_idx = np.zeros((nE, 6), dtype=np.int64)
-    nel = np.asarray(spec.nel)
-    npl = nel + 1
-    per = np.asarray(spec.periodic)
-    bc_lut = np.zeros((3, 2), dtype=np.int64)
-    for (ax_, sg_), b_ in spec.bc_of_face.items():
-        bc_lut[ax_, (sg_ + 1) // 2] = b_
-    ar = np.arange(nE)
-    for s in range(1, 7):
-        ax, sg = _ORI_GAXIS[ori, s - 1], _ORI_GSIGN[ori, s - 1]   # block direction of this local side, per element
-        j = idx.copy()
-        j[ar, ax] += sg
-        plane = idx[ar, ax] + (sg > 0)                             # face plane index along ax, 0..nel
-        outside = (j[ar, ax] < 0) | (j[ar, ax] >= nel[ax])
-        wrap = per[ax]
-        j[ar, ax] = np.where(wrap, j[ar, ax] % nel[ax], j[ar, ax])
-        plane = np.where(wrap, plane % nel[ax], plane)
-        is_out = outside & ~wrap
-        jc = np.clip(j, 0, nel - 1)
-        nb = np.where(is_out, -1, spec.gid(jc[:, 0], jc[:, 1], jc[:, 2]))
-        if np.any(is_out):
-            bc_idx[is_out, s - 1] = bc_lut[ax[is_out], (sg[is_out] + 1) // 2]
-            assert np.all(bc_idx[is_out, s - 1] > 0), "non-periodic face without a bc_of_face entry"
-        f = idx.copy()
-        f[ar, ax] = plane
-        face_gid[:, s - 1] = 1 + ax + 3 * (f[:, 0] + npl[0] * (f[:, 1] + npl[1] * f[:, 2]))   # 1-based global side index ("ind")
-        nb_gid[:, s - 1] = nb
-        nb_side[:, s - 1] = _ORI_LOCSIDE[spec.orient[np.clip(nb, 0, None)], ax, (1 - sg) // 2]
+    unstructured = hasattr(spec, "connectivity")   # a mesh file (hopr.HoprMesh): the tables come from SideInfo
+    if unstructured:
+        nb_gid, nb_side, face_gid, bc_idx, pair_flip, file_master = spec.connectivity(gids)
+        ori = None
+    else:
+        ix, iy, iz = spec.ijk(gids)
+        idx = np.stack([ix, iy, iz], axis=1)
+        ori = spec.orient[gids]
+        nb_gid = np.zeros((nE, 6), dtype=np.int64)
+        nb_side = np.zeros((nE, 6), dtype=np.int64)       # local side (1-based) of the neighbour that faces this side
+        face_gid = np.zeros((nE, 6), dtype=np.int64)
+        bc_idx = np.zeros((nE, 6), dtype=np.int64)
+        nel = np.asarray(spec.nel)
+        npl = nel + 1
+        per = np.asarray(spec.periodic)
+        bc_lut = np.zeros((3, 2), dtype=np.int64)
+        for (ax_, sg_), b_ in spec.bc_of_face.items():
+            bc_lut[ax_, (sg_ + 1) // 2] = b_
+        ar = np.arange(nE)
+        for s in range(1, 7):
+            ax, sg = _ORI_GAXIS[ori, s - 1], _ORI_GSIGN[ori, s - 1]   # block direction of this local side, per element
+            j = idx.copy()
+            j[ar, ax] += sg
+            plane = idx[ar, ax] + (sg > 0)                             # face plane index along ax, 0..nel
+            outside = (j[ar, ax] < 0) | (j[ar, ax] >= nel[ax])
+            wrap = per[ax]
+            j[ar, ax] = np.where(wrap, j[ar, ax] % nel[ax], j[ar, ax])
+            plane = np.where(wrap, plane % nel[ax], plane)
+            is_out = outside & ~wrap
+            jc = np.clip(j, 0, nel - 1)
+            nb = np.where(is_out, -1, spec.gid(jc[:, 0], jc[:, 1], jc[:, 2]))
+            if np.any(is_out):
+                bc_idx[is_out, s - 1] = bc_lut[ax[is_out], (sg[is_out] + 1) // 2]
+                assert np.all(bc_idx[is_out, s - 1] > 0), "non-periodic face without a bc_of_face entry"
+            f = idx.copy()
+            f[ar, ax] = plane
+            face_gid[:, s - 1] = 1 + ax + 3 * (f[:, 0] + npl[0] * (f[:, 1] + npl[1] * f[:, 2]))   # 1-based global side index ("ind")
+            nb_gid[:, s - 1] = nb
+            nb_side[:, s - 1] = _ORI_LOCSIDE[spec.orient[np.clip(nb, 0, None)], ax, (1 - sg) // 2]
     nb_rank = np.where(nb_gid >= 0, owner[np.clip(nb_gid, 0, None)], -1)
     is_bc = nb_gid < 0
     is_inner = (~is_bc) & (nb_rank == rank)
@@ -317,11 +322,15 @@ def build_mesh(spec, N, node_type, rank=0, nranks=1, partition="linear", blocks=
     side_id[ea, sa] = sid_pair
     side_id[eb, sb] = sid_pair
     # master of an inner side = element with the lower global id
-    a_master = gids[ea] < gids[eb]
+    if unstructured:   # the file says which side is the master (SIDE_ID > 0, mesh_readin.f90:352-360) and the flip of the slave
+        a_master = file_master[ea, sa]
+        assert np.all(file_master[ea, sa] != file_master[eb, sb]), "every inner side has exactly one master"
+    else:
+        a_master = gids[ea] < gids[eb]
     me, ms = np.where(a_master, ea, eb), np.where(a_master, sa, sb)
     se, ss = np.where(a_master, eb, ea), np.where(a_master, sb, sa)
     flip[me, ms] = 0
-    flip[se, ss] = _flips(ori[me], ms + 1, ori[se], ss + 1)
+    flip[se, ss] = pair_flip[se, ss] if unstructured else _flips(ori[me], ms + 1, ori[se], ss + 1)
 
     # MPI sides
     nb_procs = sorted(set(nb_rank[is_mpi].tolist()))
@@ -358,8 +367,11 @@ def build_mesh(spec, N, node_type, rank=0, nranks=1, partition="linear", blocks=
             sid = np.where(mine, pos - nYOUR_proc[inb] + off_mine[inb], pos + off_your[inb])
         side_id[e_m, s_m] = sid
         is_mine[e_m, s_m] = mine
-        rem_o = spec.orient[nb_gid[e_m, s_m]]
-        flip[e_m, s_m] = np.where(mine, 0, _flips(rem_o, nb_side[e_m, s_m], ori[e_m], s_m + 1))
+        if unstructured:   # a YOUR side keeps the pair's flip whichever side the file called master (the flips are involutions)
+            flip[e_m, s_m] = np.where(mine, 0, pair_flip[e_m, s_m])
+        else:
+            rem_o = spec.orient[nb_gid[e_m, s_m]]
+            flip[e_m, s_m] = np.where(mine, 0, _flips(rem_o, nb_side[e_m, s_m], ori[e_m], s_m + 1))
     nSides = off_your[-1]
     m.nSides, m.nBCSides, m.nInnerSides = nSides, nBC, nInner
     m.nMPISides_MINE, m.nMPISides_YOUR = sum(nMINE_proc), sum(nYOUR_proc)

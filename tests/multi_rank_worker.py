@@ -40,6 +40,10 @@ CASES["splitCH"] = (5, B.NODE_GAUSS_LOBATTO, dict(parabolic=True, lifting=1, rie
                                                   ref_state_prim=[(1.0, 0.3, 0.0, 0.0, 0.71428571), (1.0, 0.0, 0.0, 0.0, 0.9)]))
 # BASELINE configs[3] proper: NACA0012-style O-mesh, every element in a random local frame, N=5, HLLC + BR2, wall + far field
 CASES["naca"] = (5, B.NODE_GAUSS, NACA_EQN)
+# the reference's own NACA0012 mesh file (652 curved elements, flips 0/1/2/4) and its state at t = 10 (tests/test_hopr_mesh.py)
+from test_hopr_mesh import FARFIELD as HOPR_BC, MESH as HOPR_MESH, NACA_EQN as HOPR_EQN, STATE as HOPR_STATE  # noqa: E402
+from flexi_b200.hostmesh.hopr import HoprMesh, read_state  # noqa: E402
+CASES["hopr"] = (3, B.NODE_GAUSS, HOPR_EQN)
 # the solution filter (FilterType = cutoff, dg.f90:329-330) on a partitioned run: the traces of the filtered state are exchanged at the
 # start of every operator evaluation
 CASES["splitfilt"] = CASES["split"]
@@ -59,7 +63,11 @@ def main():
         dist.init_process_group("gloo", rank=rank, world_size=world)
     N, node, eqn = CASES[case]
     oseed = 9 if case.endswith("_unstr") else None  # "_unstr": every element in a random local frame (all flips on MPI sides too)
-    if case == "naca":
+    if case == "hopr":
+        spec = HoprMesh(HOPR_MESH, boundary_type=HOPR_BC)
+        eqn = dict(eqn, boundary_type=spec.boundary_type)
+        u_file = read_state(HOPR_STATE)[0]
+    elif case == "naca":
         spec = naca_spec((12, 3, 2))
     elif "boundary_type" in eqn:
         spec = BoxSpec((4, 3, 2), periodic=(False, False, True), bc_of_face=WALL_BC, orient_seed=oseed, **CURVED)
@@ -94,6 +102,8 @@ def main():
 
     # ---- oracle world on this partition vs the single-rank oracle (partition invariance, SURVEY 8c identity 7) ----
     smooth = (lambda r: naca_state(r.eqn, r.mesh.Elem_xGP)) if case == "naca" else (lambda r: r.eqn.smooth_state(r.mesh.Elem_xGP, length=2.0))
+    if case == "hopr":
+        smooth = lambda r: np.ascontiguousarray(u_file[r.mesh.elem_gid])  # noqa: E731
     U0s = [smooth(r) for r in ranks]
     w = O.OracleWorld([(r.desc, r.keep) for r in ranks])
     if gauss_split:
@@ -118,7 +128,7 @@ def main():
         full = w1.ranks[0].array("Ut")
         for r, ow in zip(ranks, w.ranks):
             # naca: 1/J varies over four decades (wall layer), the flux sums cancel to 1e-4 of their terms -> round-off 5e-11
-            ptol = 2e-11 if case == "naca" else 1e-12
+            ptol = 2e-11 if case in ("naca", "hopr") else 1e-12
             assert np.max(np.abs(ow.array("Ut") - full[r.mesh.elem_gid])) < ptol * np.max(np.abs(full))
         w1.close()
 
@@ -138,14 +148,14 @@ def main():
         ut = g.DGTimeDerivative_weakForm(0.0)
         scale = np.max(np.abs(ut_ref).reshape(-1, 5), axis=0)
         # gate: rel 1e-12, or 4x the oracle's own strict-vs-FMA build noise where that is larger (naca: 1/J spans four decades)
-        noise = O.ut_noise_floor([(r.desc, r.keep) for r in ranks], U0s)[0] if case == "naca" else 0.0
+        noise = O.ut_noise_floor([(r.desc, r.keep) for r in ranks], U0s)[0] if case in ("naca", "hopr") else 0.0
         assert np.all(np.max(np.abs(ut - ut_ref).reshape(-1, 5), axis=0) <= np.maximum(1e-12 * scale, 4.0 * noise)), "multi-rank Ut mismatch"
         if eqn.get("parabolic"):
             # side arrays after a full DG operator call, incl. what arrives from the neighbour rank: gradU?_slave on MPI_MINE sides
             o = w.ranks[rank]
             gsc = max(np.max(np.abs(o.array(n))) for n in ("gradUx", "gradUy", "gradUz"))
             lo, hi = m.nBCSides, m.firstMPISide_YOUR - 1  # slave arrays of inner + MPI_MINE sides (0-based [lo, hi))
-            gtol = 1e-11 if case == "naca" else 1e-12  # naca: 1/J of the wall layer amplifies the round-off of the lifting (see ptol)
+            gtol = 1e-11 if case in ("naca", "hopr") else 1e-12  # naca: 1/J of the wall layer amplifies the round-off of the lifting (see ptol)
             for name in ("gradUx_slave", "gradUy_slave", "gradUz_slave"):
                 assert np.max(np.abs(g.get_array(name)[lo:hi] - o.array(name)[lo:hi])) <= gtol * gsc, name
             hi_m = m.lastMPISide_MINE
@@ -161,7 +171,9 @@ def main():
             t += dt_o
         Ug, Uo = g.get_state(), w.ranks[rank].array("U")
         sc = np.max(np.abs(Uo).reshape(-1, 5), axis=0)
-        stol = 1e-11 if case == "naca" else 1e-12  # naca: round-off of Ut is amplified by 1/J of the wall layer (see ptol above)
+        stol = 1e-11 if case in ("naca", "hopr") else 1e-12  # naca: round-off of Ut is amplified by 1/J of the wall layer (see ptol above)
+        if case == "hopr":
+            sc[1:4] = sc[1:4].max()  # two-dimensional flow: w-momentum ~ 1e-10, judged against the common momentum scale
         assert np.all(np.max(np.abs(Ug - Uo).reshape(-1, 5), axis=0) <= stol * sc), "multi-rank state mismatch after 3 steps"
         if eqn.get("parabolic") and "boundary_type" not in eqn:
             # on-device TGV AnalyzeTestcase (steps 1-4) per rank + the host's reduction (steps 5-6) against the host analysis of
