@@ -8,10 +8,15 @@
  * (column-major, first index fastest), e.g. U(var,i,j,k,elem) -> U[(((e*np+k)*np+j)*np+i)*5+var].
  *
  * Parity status: ProlongToFace and SurfInt are pinned against the reference's unit-test fixtures (tests/golden/
- * reference_unittests, see tests/test_oracle_golden.py).  VolInt, Riemann solvers, split fluxes, lifting, FillFlux, the RK update
- * and CalcTimeStep have no function-level fixture in the reference ("parity unpinned" at function level);
- * they are validated through identities (consistency, free-stream preservation, conservation, weak==split(SD) on LGL,
- * partition invariance, convergence order) and through the analytic t=0 row of the TGV regression CSV.
+ * reference_unittests, see tests/test_oracle_golden.py).  The whole Navier-Stokes path (weak-form VolInt on Gauss nodes, BR1
+ * lifting with its boundary fluxes, viscous fluxes, Riemann_Side + RoeEntropyFix, GetBoundaryFlux types 2 and 4, CalcTimeStep,
+ * the LSERK update) is pinned end to end on the reference's own golden state of regressioncheck/checks/parabolic/cavity_3D:
+ * 353 time steps from rest reproduce its DG_Solution to 2e-13 absolute (tests/test_reference_cavity3d.py); the TGV regression
+ * CSV rows of tgv/split, tgv/splitGauss and tgv/oInt pin the split forms, the overintegration and N = 11
+ * (tests/test_oracle_tgv_regression.py); CalcTimeStep and the metrics agree with ElemData 'dt' of the reference's NACA0012
+ * state file to round-off (tests/test_hopr_mesh.py).  The other Riemann solvers and split fluxes, BR2 and BC types 3 / 9 have
+ * no reference-held datum ("parity unpinned" at function level); they are validated through identities
+ * (consistency, free-stream preservation, conservation, weak==split(SD) on LGL, partition invariance, convergence order).
  *
  * MPI is emulated inside one process: a "world" holds one oracle per rank; the non-blocking exchanges of mpi/mpi.f90:244-445
  * become slice copies between ranks at the point where the reference calls FinishExchangeMPIData.  With OpenMP the ranks of
