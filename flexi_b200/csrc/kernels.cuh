@@ -297,8 +297,17 @@ __device__ __forceinline__ void split_lines(const SP sP, const SP sM, const SP s
 // prim index of lifting variable v (PRIM_LIFT, eos.h:118,127): nvl=5 -> (rho,v1,v2,v3,T), nvl=4 -> (v1,v2,v3,T)
 __host__ __device__ constexpr int lift_prim(int nvl, int v) { return nvl == 5 ? (v < 4 ? v : 5) : (v < 3 ? v + 1 : 5); }
 
+// Resident CTAs per SM the register allocation of the Navier-Stokes instantiations is sized for (FX_KV_MINB, default 1; timing
+// experiments set it through `make dev DEVFLAGS=-DFX_KV_MINB=2`): N = 7 runs 512 threads per element at ~122 registers, i.e. one
+// element per SM; 2 forces 64 registers (spills) for two resident elements.
+#ifndef FX_KV_MINB
+#define FX_KV_MINB 1
+#endif
+template <int NP, bool PARA>
+constexpr int kv_min_blocks() { return (PARA && !Dim<NP>::PAIR && Dim<NP>::NP3 * FX_KV_MINB <= 1024) ? FX_KV_MINB : 1; }
+
 template <int NP, bool GL, bool SPLIT, bool PARA, int NVL, int LIFT>
-__global__ void __launch_bounds__(Dim<NP>::THREADS) k_volume(VolArgs A) {
+__global__ void __launch_bounds__(Dim<NP>::THREADS, kv_min_blocks<NP, PARA>()) k_volume(VolArgs A) {
   using D = Dim<NP>;
   extern __shared__ double sm_raw[];
   auto sm = elem_smem<NP>(sm_raw);

@@ -2,7 +2,7 @@
 x weak / split form on a TGV box sized to ~17 MDOF (state 0.7 GB >> 126 MB L2).  Device-timed LSERK4-5 steps with the state
 resident in HBM; per flavour: GDOF/s, PID, ms per stage per kernel class, and the stage roofline fraction against B_alg(N) of
 BASELINE.md section 3 and the measured HBM peak.  One JSON object per line.
-usage: python tools/psweep.py [out.json] [--quick]"""
+usage: python tools/psweep.py [out.json] [--quick] [--only=N] [--flavour=substring]"""
 import json
 import os
 import sys
@@ -24,6 +24,8 @@ B_ALG = {True: lambda N: 240.0 + 3.0 / (N + 1) * 720.0, False: lambda N: 240.0 +
 NEL = {3: 64, 5: 42, 7: 32, 9: 26}
 quick = "--quick" in sys.argv
 out_path = next((a for a in sys.argv[1:] if not a.startswith("--")), None)
+only_n = next((int(a.split("=")[1]) for a in sys.argv[1:] if a.startswith("--only=")), None)
+only_f = next((a.split("=")[1] for a in sys.argv[1:] if a.startswith("--flavour=")), None)
 try:
     peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
 except Exception:
@@ -35,10 +37,12 @@ FLAVOURS = [  # (name, node, parabolic, split)
     ("Gauss split NS", B.NODE_GAUSS, True, True),
 ]
 rows = []
-for N in ((7,) if quick else (3, 5, 7, 9)):
+for N in ((only_n,) if only_n else (7,) if quick else (3, 5, 7, 9)):
     nel = NEL[N] // (2 if quick else 1)
     meshes = {}
     for name, node, para, split in FLAVOURS:
+        if only_f and only_f.lower() not in name.lower():
+            continue
         eqn = dict(parabolic=para, split_dg=split, riemann="lf" if split else "roe", cfl_scale=0.8, dfl_scale=0.8, n_var_lifting=5, **TGV_EQN)
         if split:
             eqn["split_dg_type"] = "pi"
