@@ -142,3 +142,30 @@ def test_partitioned_file_mesh_gives_the_same_operator():
         # round-off, amplified by sJ ~ 6e4 next to the wall (the free-stream test above shows the same 5e-11 absolute noise)
         assert np.all(d <= 1e-11 * scale), (d, scale)
     w.close()
+
+
+def test_mortar_meshes_are_refused():
+    """tutorials/convtest/CART_HEX_PERIODIC_MORTAR_002_mesh.h5 (non-conforming): refused like the GPU library refuses mortar sides."""
+    with pytest.raises(NotImplementedError, match="mortar"):
+        HoprMesh(os.path.join(GOLD, "CART_HEX_PERIODIC_MORTAR_002_mesh.h5"))
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="the reference tree is only present in the build container")
+def test_hdf5_reader_on_every_file_of_the_reference_tree():
+    """Every .h5 file the reference ships (meshes incl. mortar and 2-D ones, states, base flows, record-point sets, wall distances):
+    all datasets parse and have the shape their dataspace declares."""
+    import glob
+
+    files = sorted(glob.glob("/root/reference/**/*.h5", recursive=True))
+    assert len(files) > 100
+    for p in files:
+        f = File(p)
+        n = 0
+        for k in f.keys():
+            try:
+                d = f[k]
+            except KeyError:
+                continue  # a group
+            assert d.read().shape == d.shape, (p, k)
+            n += 1
+        assert n > 0, p
