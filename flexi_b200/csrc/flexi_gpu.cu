@@ -1142,6 +1142,8 @@ int flexi_gpu_analyze_tgv(flexi_gpu_handle* h, int32_t NAnalyze, const double* V
   a.out = dPart;
   const int nf = h->para ? 15 : 6;
   const size_t smem = sizeof(double) * ((size_t)nf * h->np3 + (size_t)na1 * np + (size_t)nf * h->np2 + (size_t)nf * na1 * np + TGV_NSUMS * 32);
+  if (smem > 227 * 1024 || na1 * na1 > 1024)  // N = 11 with NAnalyze = 2(N+1): 330 KB of element planes -- the host analysis covers that degree
+    return fail(FLEXI_GPU_ERR_UNSUPPORTED, "on-device TGV analysis: N=%d with NAnalyze=%d needs %zu bytes of shared memory per element (limit 232448)", h->N, NAnalyze, smem);
   CK(cudaFuncSetAttribute(k_tgv_analyze, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   {
     Timer tm(h, KC_DT, h->sc);
@@ -1197,6 +1199,8 @@ int flexi_gpu_calc_error_norms(flexi_gpu_handle* h, double Time, int32_t Analyze
   a.wVol = dTab + (size_t)na1 * np;
   a.out = dPart;
   const size_t smem = sizeof(double) * ((size_t)9 * h->np3 + (size_t)na1 * np + (size_t)9 * h->np2 + (size_t)9 * na1 * np + 10 * 32);
+  if (smem > 227 * 1024 || na1 * na1 > 1024)
+    return fail(FLEXI_GPU_ERR_UNSUPPORTED, "on-device error norms: N=%d with NAnalyze=%d needs %zu bytes of shared memory per element (limit 232448)", h->N, NAnalyze, smem);
   CK(cudaFuncSetAttribute(k_error_norms, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   {
     Timer tm(h, KC_DT, h->sc);

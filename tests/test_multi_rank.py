@@ -16,13 +16,13 @@ def _run(world, mode, case, port):
     assert p.returncode == 0 and "MULTI_RANK_OK" in p.stdout, p.stdout[-3000:] + p.stderr[-3000:]
 
 
-@pytest.mark.parametrize("world,case", [(2, "split"), (3, "weakG"), (2, "config4"), (3, "splitG"), (2, "splitCH"), (3, "config4_unstr"), (3, "naca"), (2, "splitfilt"), (3, "hopr")])
+@pytest.mark.parametrize("world,case", [(2, "split"), (3, "weakG"), (2, "config4"), (3, "splitG"), (2, "splitCH"), (3, "config4_unstr"), (3, "naca"), (2, "splitfilt"), (3, "hopr"), (2, "n11")])
 def test_partition_plumbing_gloo(world, case):
     _run(world, "cpu", case, 29611 + world)
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("case", ["split", "weakG", "euler", "config4", "splitwall", "splitG", "splitCH", "config4_unstr", "split_unstr", "naca", "splitfilt", "hopr"])
+@pytest.mark.parametrize("case", ["split", "weakG", "euler", "config4", "splitwall", "splitG", "splitCH", "config4_unstr", "split_unstr", "naca", "splitfilt", "hopr", "n11"])
 def test_nccl_side_exchange_parity(case):
     import torch
 
