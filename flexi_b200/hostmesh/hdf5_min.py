@@ -1,4 +1,4 @@
-"""Minimal read-only HDF5 parser for the files HOPR and FLEXI write (io_hdf5/hdf5_input.f90 reads them through libhdf5; this image
+"""Minimal HDF5 parser (and, at the end of the file, writer) for the files HOPR and FLEXI write (io_hdf5/hdf5_input.f90 reads them through libhdf5; this image
 has neither libhdf5 nor h5py).  Supported subset -- exactly what those writers produce with the library defaults: superblock
 version 0 (optionally behind a FLEXI userblock), version-1 object headers with continuation blocks, old-style groups (symbol table:
 B-tree v1 + local heap), contiguous or compact dataset layout, fixed-point / IEEE float / fixed-length string datatypes, attribute
@@ -185,3 +185,109 @@ class File:
         if dt is None or shape is None or layout is None:
             raise KeyError(f"{name} is not a dataset")
         return Dataset(self, dt, shape, layout, attrs)
+
+
+# ---- writer: the same subset, laid out the way libhdf5 1.8+ lays out FLEXI's files (io_hdf5/hdf5_output.f90:785-839 WriteState) ----
+def _dtype_msg(dt):
+    dt = np.dtype(dt)
+    if dt.kind == "f" and dt.itemsize == 8:
+        return bytes.fromhex("11203f000800000000004000340b0034ff030000")
+    if dt.kind == "i" and dt.itemsize == 4:
+        return bytes.fromhex("100800000400000000002000")
+    if dt.kind == "S":
+        return bytes.fromhex("13020000") + struct.pack("<I", dt.itemsize)  # Fortran strings: space padded
+    raise NotImplementedError(f"datatype {dt}")
+
+
+def _pad8(b):
+    return b + b"\0" * (-len(b) % 8)
+
+
+def _dspace_msg(shape):
+    shape = tuple(int(x) for x in shape) or (1,)
+    dims = struct.pack("<" + "Q" * len(shape), *shape)
+    return bytes([1, len(shape), 1, 0, 0, 0, 0, 0]) + dims + dims  # version 1, dims + maximum dims
+
+
+def _msg(mtype, data):
+    data = _pad8(data)
+    return struct.pack("<HHB3x", mtype, len(data), 0) + data
+
+
+def _attr_msg(name, value):
+    value = np.asarray(value)
+    if value.dtype.kind == "U":
+        value = value.astype("S")
+    if value.dtype.kind == "i" and value.dtype.itemsize != 4:
+        value = value.astype("<i4")
+    nm = name.encode() + b"\0"
+    dt, ds = _dtype_msg(value.dtype), _dspace_msg(value.shape or (1,))
+    body = struct.pack("<BxHHH", 1, len(nm), len(dt), len(ds)) + _pad8(nm) + _pad8(dt) + _pad8(ds) + value.tobytes()
+    return _msg(0x0C, body)
+
+
+def _ohdr(msgs):
+    body = b"".join(msgs)
+    return struct.pack("<BxHII4x", 1, len(msgs), 1, len(body)) + body
+
+
+def write_file(path, datasets, attrs=None, userblock=b""):
+    """Write root-level datasets {name: array} (float64 / int32 / fixed strings, C order as given) and root attributes
+    {name: array-like} as an HDF5 file of the subset this module reads: superblock 0, old-style root group (B-tree v1, local heap,
+    one symbol-table node: at most 8 datasets), version-1 object headers, contiguous layout.  userblock: bytes stored in front
+    of the superblock (FLEXI keeps its parameter file there), padded to 512 * 2^k."""
+    attrs = attrs or {}
+    names = sorted(datasets)
+    if not 0 < len(names) <= 8:
+        raise NotImplementedError("1..8 root datasets")
+    ub = 0
+    if userblock:
+        ub = 512
+        while ub < len(userblock):
+            ub *= 2
+    # local heap data: the empty name at offset 0, then the dataset names
+    heap, name_off = bytearray(8), {}
+    for n in names:
+        name_off[n] = len(heap)
+        heap += _pad8(n.encode() + b"\0")
+    root_msgs_fixed = [_attr_msg(k, v) for k, v in attrs.items()]
+    a_root = 96
+    root_len = 16 + 24 + sum(len(m) for m in root_msgs_fixed)
+    a_tree = a_root + root_len
+    a_heap = a_tree + 544
+    a_heap_data = a_heap + 32
+    a_snod = a_heap_data + len(heap)
+    pos = a_snod + 328
+    hdrs, blobs = {}, {}
+    for n in names:
+        arr = np.ascontiguousarray(datasets[n])
+        if arr.dtype.kind == "i" and arr.dtype.itemsize != 4:
+            arr = arr.astype("<i4")
+        ds, dt = _dspace_msg(arr.shape), _dtype_msg(arr.dtype)
+        fixed = 16 + (8 + len(_pad8(ds))) + (8 + len(_pad8(dt))) + (8 + 8) + (8 + 24)
+        a_data = pos + fixed
+        layout = bytes([3, 1]) + struct.pack("<QQ", a_data, arr.nbytes)
+        hdrs[n] = (pos, _ohdr([_msg(0x01, ds), _msg(0x03, dt), _msg(0x05, bytes.fromhex("0202020100000000")), _msg(0x08, layout)]))
+        assert len(hdrs[n][1]) == fixed
+        blobs[n] = (a_data, arr.tobytes())
+        pos = a_data + len(_pad8(blobs[n][1]))
+    eof = pos
+    out = bytearray(ub + eof)
+    out[:len(userblock)] = userblock
+    sb = _SIG + bytes([0, 0, 0, 0, 0, 8, 8, 0]) + struct.pack("<HHI", 4, 16, 0) + struct.pack("<QQQQ", 0, _UNDEF, eof, _UNDEF)
+    sb += struct.pack("<QQII", 0, a_root, 1, 0) + struct.pack("<QQ", a_tree, a_heap)
+    assert len(sb) == 96
+    root = _ohdr([_msg(0x11, struct.pack("<QQ", a_tree, a_heap))] + root_msgs_fixed)
+    assert len(root) == root_len
+    tree = b"TREE" + bytes([0, 0]) + struct.pack("<HQQ", 1, _UNDEF, _UNDEF) + struct.pack("<QQQ", 0, a_snod, name_off[names[-1]])
+    hp = b"HEAP" + bytes(4) + struct.pack("<QQQ", len(heap), 1, a_heap_data)  # free-list head 1 = no free block
+    snod = b"SNOD" + bytes([1, 0]) + struct.pack("<H", len(names))
+    for n in names:
+        snod += struct.pack("<QQII16x", name_off[n], hdrs[n][0], 0, 0)
+    for a, b in [(0, sb), (a_root, root), (a_tree, tree), (a_heap, hp), (a_heap_data, bytes(heap)), (a_snod, snod)]:
+        out[ub + a:ub + a + len(b)] = b
+    for n in names:
+        out[ub + hdrs[n][0]:ub + hdrs[n][0] + len(hdrs[n][1])] = hdrs[n][1]
+        out[ub + blobs[n][0]:ub + blobs[n][0] + len(blobs[n][1])] = blobs[n][1]
+    with open(path, "wb") as fh:
+        fh.write(out)

@@ -7,7 +7,8 @@ file -- per element and local side the neighbour element, its local side, the si
 on equidistant points) -- and build_mesh then does what prepare_mesh.f90 / metrics.f90 do with it.  Conforming hexahedral meshes
 only: mortar sides (SIDE_nbElemID < 0 / SIDE_Type < 0) are refused, as the GPU library refuses them.
 
-`read_state` loads `DG_Solution` (and `ElemData`) of a FLEXI state file (io_hdf5/hdf5_output.f90:785-839 writes them).
+`read_state` loads `DG_Solution` (and `ElemData`) of a FLEXI state file (io_hdf5/hdf5_output.f90:785-839 writes them);
+`write_state` writes one.
 
 Host-side harness code; the product library never sees a file."""
 import numpy as np
@@ -81,3 +82,25 @@ def read_state(path):
         ed = f["ElemData"].read()
         elem_data = {n: ed[:, i] for i, n in enumerate(names)}
     return U, f.attrs, elem_data
+
+
+def write_state(path, U, time, N, node_type, mesh_file, project_name="flexi_b200", elem_data=None, userblock=b""):
+    """A FLEXI state file (WriteState, io_hdf5/hdf5_output.f90:785-839, and its header attributes :1060-1130): `DG_Solution`
+    [nElems,k,j,i,5] plus optional `ElemData` {name: array[nElems]}; readable by `read_state` and laid out like the reference's own
+    files (same superblock / object-header / datatype encodings; not validated against libhdf5, which this image lacks)."""
+    from .hdf5_min import write_file
+
+    def s255(x):
+        return np.array([x.ljust(255).encode() for x in ([x] if isinstance(x, str) else x)], dtype="S255")
+
+    data = {"DG_Solution": np.ascontiguousarray(U, dtype=np.float64)}
+    attrs = {"VarNames": s255(["Density", "MomentumX", "MomentumY", "MomentumZ", "EnergyStagnationDensity"]),
+             "Program": np.array([b"Flexi"], dtype="S5"), "File_Type": np.array([b"State"], dtype="S5"),
+             "Project_Name": np.array([project_name.encode()], dtype=f"S{len(project_name)}"), "File_Version": np.array([0.1]),
+             "N": np.array([int(N)], dtype=np.int32), "Dimension": np.array([3], dtype=np.int32), "Time": np.array([float(time)]),
+             "MeshFile": np.array([mesh_file.encode()], dtype=f"S{len(mesh_file)}"), "NodeType": s255(node_type.upper())}
+    if elem_data:
+        names = list(elem_data)
+        data["ElemData"] = np.ascontiguousarray(np.stack([np.asarray(elem_data[n], dtype=np.float64) for n in names], axis=1))
+        attrs["VarNamesAdd"] = s255(names)
+    write_file(path, data, attrs, userblock=userblock)
