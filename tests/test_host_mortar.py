@@ -1,0 +1,78 @@
+"""Mortar interface operators (mortar/mortar.f90, mortar/fillmortar.t90) restated on the host: first step of the mortar plan of
+DESIGN.md section 7.  The reference holds no fixture for them; InitMortar carries its own known-answer check, restated here, the
+rest are the defining properties: interpolation is exact for polynomials, projection is the L2 adjoint, a projected interpolant
+is the original, a constant flux through four small sides is the same flux through the big side (conservation)."""
+import numpy as np
+import pytest
+
+from flexi_b200.hostmesh import basis as B
+from flexi_b200.hostmesh.mortar import flux_mortar, init_mortar_self_check, mortar_basis, u_mortar
+
+NODES = [B.NODE_GAUSS, B.NODE_GAUSS_LOBATTO]
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 7, 9, 11])
+def test_init_mortar_self_check(n):
+    """mortar.f90:77-88: error <= 100 * PP_RealTolerance (= 100 * epsilon)."""
+    assert init_mortar_self_check(n) <= 100 * np.finfo(float).eps
+
+
+@pytest.mark.parametrize("node", NODES)
+@pytest.mark.parametrize("n", [2, 4, 7])
+def test_big_to_small_is_exact_interpolation(n, node):
+    xi, _, _ = B.get_nodes_and_weights(n, node)
+    m01, m02, _, _ = mortar_basis(n, node)
+    c = np.random.default_rng(n).normal(size=n + 1)
+    f = lambda x: np.polyval(c, x)  # noqa: E731  degree n
+    assert np.allclose(m01.T @ f(xi), f(0.5 * (xi - 1.0)), rtol=0, atol=1e-12)
+    assert np.allclose(m02.T @ f(xi), f(0.5 * (xi + 1.0)), rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("n", [2, 4, 7])
+def test_small_to_big_is_the_l2_projection(n):
+    """Gauss nodes (exact mass matrix): sum_p w_p v_p (M_1_0^T a + M_2_0^T b)_p = sum_p w_p ((M_0_1^T v)_p a_p + (M_0_2^T v)_p b_p)
+    for all v, a, b -- the projection is the adjoint of the interpolation WITHOUT the length ratio 1/2 of the intervals, i.e. twice
+    the L2 projection per split direction: the fluxes Flux_Mortar projects carry SurfElem of the small sides, which is half
+    (a quarter) of the big side's (the same convention as InitMortar's own check: 0.25 * sum(...) = 1 for the constants 0.5 / 1.5).
+    Hence projecting the interpolant of a polynomial gives twice the polynomial."""
+    node = B.NODE_GAUSS
+    _, w, _ = B.get_nodes_and_weights(n, node)
+    m01, m02, m10, m20 = mortar_basis(n, node)
+    rng = np.random.default_rng(3 * n)
+    v, a, b = rng.normal(size=(3, n + 1))
+    lhs = np.sum(w * v * (m10.T @ a + m20.T @ b))
+    rhs = np.sum(w * ((m01.T @ v) * a + (m02.T @ v) * b))
+    assert abs(lhs - rhs) <= 1e-13 * max(1.0, abs(rhs))
+    assert np.allclose(m10.T @ (m01.T @ v) + m20.T @ (m02.T @ v), 2.0 * v, rtol=0, atol=1e-13)
+
+
+@pytest.mark.parametrize("node", NODES)
+@pytest.mark.parametrize("mtype", [1, 2, 3])
+def test_face_operators(mtype, node):
+    """U_Mortar on a bivariate polynomial is its evaluation on the small faces; Flux_Mortar after U_Mortar is 2x (types 2, 3) / 4x
+    (type 1) the identity (SurfElem convention, see above); the big-side quadrature of the projected flux is the sum of the
+    small-side quadratures (discrete conservation of SurfElem-weighted fluxes, Gauss weights)."""
+    n = 4
+    xi, w, _ = B.get_nodes_and_weights(n, node)
+    m01, m02, m10, m20 = mortar_basis(n, node)
+    rng = np.random.default_rng(11 + mtype)
+    c = rng.normal(size=(n + 1, n + 1))
+    poly = lambda x, y: np.polynomial.polynomial.polyval2d(x, y, c)  # noqa: E731
+    P, Q = np.meshgrid(xi, xi, indexing="xy")                          # arrays [q, p]: xi along p, eta along q
+    u_big = np.stack([poly(P, Q), 2.0 * poly(P, Q) + 1.0], axis=-1)
+    small = u_mortar(u_big, mtype, m01, m02)
+    lo, hi = (lambda x: 0.5 * (x - 1.0)), (lambda x: 0.5 * (x + 1.0))
+    maps = {1: [(lo, lo), (hi, lo), (lo, hi), (hi, hi)], 2: [(None, lo), (None, hi)], 3: [(lo, None), (hi, None)]}[mtype]
+    assert small.shape[0] == len(maps)
+    for s, (fx, fy) in zip(small, maps):
+        X = fx(P) if fx else P
+        Y = fy(Q) if fy else Q
+        assert np.allclose(s[..., 0], poly(X, Y), rtol=0, atol=1e-11)
+    back = flux_mortar(small, mtype, m10, m20)
+    tol = 1e-12 if node == B.NODE_GAUSS else 1e-11
+    assert np.allclose(back, (4.0 if mtype == 1 else 2.0) * u_big, rtol=0, atol=tol)
+    if node == B.NODE_GAUSS:
+        f_small = rng.normal(size=small.shape)
+        big = flux_mortar(f_small, mtype, m10, m20)
+        w2 = w[:, None] * w[None, :]
+        assert np.allclose(np.einsum("qp,qpv->v", w2, big), np.einsum("qp,sqpv->v", w2, f_small), rtol=0, atol=1e-12)
