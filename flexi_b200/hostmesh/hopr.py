@@ -104,3 +104,43 @@ def write_state(path, U, time, N, node_type, mesh_file, project_name="flexi_b200
         data["ElemData"] = np.ascontiguousarray(np.stack([np.asarray(elem_data[n], dtype=np.float64) for n in names], axis=1))
         attrs["VarNamesAdd"] = s255(names)
     write_file(path, data, attrs, userblock=userblock)
+
+
+def mortar_topology(path):
+    """The non-conforming interfaces of a HOPR mesh as ReadMesh sees them (mesh_readin.f90:333-376): a big side is a SideInfo row with
+    SIDE_nbElemID = -MortarType (1: 4 small sides, 2 / 3: 2), followed by the rows of its small virtual sides, whose SIDE_nbElemID
+    are the small elements; in the small element the matching row has SIDE_Type < 0 and SIDE_Flip = flip (its local side is found by
+    the side index).  Returns (node coordinates [e,k,j,i,3], NGeo, list of dicts {elem, loc_side, type, small: [(elem, loc_side,
+    flip), ...]}), elements 0-based, local sides 1-based.  Bookkeeping only: build_mesh does not take mortar meshes yet."""
+    f = File(path)
+    ngeo = int(f.attrs["Ngeo"][0])
+    ei = f["ElemInfo"].read().astype(np.int64)
+    si = f["SideInfo"].read().astype(np.int64)
+    n1 = ngeo + 1
+    nodes = f["NodeCoords"].read()
+    X = np.stack([nodes[o:o + n1 ** 3].reshape(n1, n1, n1, 3) for o in ei[:, 4]])
+    # local side of every (element, side index) for the small-side lookup
+    loc_of = {}
+    rows = []
+    for e in range(len(ei)):
+        r, loc = ei[e, 2], 0
+        while r < ei[e, 3]:
+            loc += 1
+            nb = si[r, 2]
+            loc_of[(e, abs(si[r, 1]))] = (loc, si[r, 3] % 10, si[r, 0])
+            if nb < 0:
+                mtype = int(-nb)
+                nsmall = 4 if mtype == 1 else 2
+                rows.append((e, loc, mtype, [(int(si[r + 1 + m, 2]) - 1, int(abs(si[r + 1 + m, 1]))) for m in range(nsmall)]))
+                r += nsmall
+            r += 1
+        assert loc == 6, "six local sides per hexahedron"
+    out = []
+    for e, loc, mtype, small in rows:
+        sm = []
+        for se, ind in small:
+            sloc, flip, stype = loc_of[(se, ind)]
+            assert stype < 0, "the small element marks the side as part of a mortar (SIDE_Type < 0)"
+            sm.append((se, sloc, int(flip)))
+        out.append(dict(elem=e, loc_side=loc, type=mtype, small=sm))
+    return X, ngeo, out

@@ -76,3 +76,39 @@ def test_face_operators(mtype, node):
         big = flux_mortar(f_small, mtype, m10, m20)
         w2 = w[:, None] * w[None, :]
         assert np.allclose(np.einsum("qp,qpv->v", w2, big), np.einsum("qp,sqpv->v", w2, f_small), rtol=0, atol=1e-12)
+
+
+def test_mortar_numbering_against_a_reference_mesh():
+    """tutorials/convtest/CART_HEX_PERIODIC_MORTAR_002_mesh.h5 (28 elements, mortar types 1, 2 and 3): the face nodes of every
+    small element coincide with the big side's face nodes interpolated by U_Mortar -- i.e. the small-side numbering of
+    fillmortar.t90 (type 1: (xi-,eta-), (xi+,eta-), (xi-,eta+), (xi+,eta+) in the big side's master orientation), the file layout
+    read by mesh_readin.f90:333-376 and the flip of the small (slave) sides, on the reference's own mesh file."""
+    import os
+
+    from flexi_b200.hostmesh import mappings as MP
+    from flexi_b200.hostmesh.hopr import mortar_topology
+    from test_host_mesh import face_of
+
+    path = os.path.join(os.path.dirname(__file__), "golden", "reference_naca3d", "CART_HEX_PERIODIC_MORTAR_002_mesh.h5")
+    X, ngeo, mortars = mortar_topology(path)
+    assert ngeo == 1 and sorted({m["type"] for m in mortars}) == [1, 2, 3]
+    n = ngeo
+    _, _, S2V2 = MP.build_mappings(n)
+    m01, m02, _, _ = mortar_basis(n, B.NODE_VISU)
+    L = X.reshape(-1, 3).max(axis=0) - X.reshape(-1, 3).min(axis=0)
+    pq = np.arange(n + 1)
+    P, Q = np.meshgrid(pq, pq, indexing="ij")
+
+    def side_points(e, loc, flip):   # [q, p, 3] in the master orientation of the side
+        a, c = S2V2[:, P, Q, flip, loc - 1]
+        return np.transpose(face_of(X[e], loc, n)[c, a], (1, 0, 2))
+
+    for m in mortars:
+        big = side_points(m["elem"], m["loc_side"], 0)
+        small = u_mortar(big, m["type"], m01, m02)
+        assert len(m["small"]) == small.shape[0]
+        for s, (se, sloc, flip) in zip(small, m["small"]):
+            assert flip != 0, "small elements are the slaves of their mortar sides"
+            d = side_points(se, sloc, flip) - s
+            d -= L * np.round(d / L)   # periodic box
+            assert np.max(np.abs(d)) < 1e-13, (m, se)
