@@ -86,3 +86,14 @@ def flux_mortar(flux_small, mortar_type, m10, m20):
     if mortar_type == 3:
         return xi_pair(flux_small[0], flux_small[1])
     raise ValueError(mortar_type)
+
+
+def mortar_surf_metrics(face_ja, face_xgp, mortar_type, m01, m02):
+    """Mortar_CalcSurfMetrics (mortar/mortar_metrics.f90:55-162): surface metrics and face points of the small virtual sides from
+    those of the big side -- the same tensor-product interpolation as U_Mortar, the metrics scaled by 1/2 per split direction
+    (M_0_12_h; the small side's reference square covers half the big one's in that direction).  face_ja [q, p, 3, 3] or any
+    trailing shape, face_xgp [q, p, 3]; returns (Mortar_Ja [iMortar, q, p, ...], Mortar_xGP [iMortar, q, p, 3])."""
+    sh = face_ja.shape
+    ja = u_mortar(face_ja.reshape(sh[0], sh[1], -1), mortar_type, m01, m02)
+    ja = ja.reshape((ja.shape[0],) + sh) * (0.25 if mortar_type == 1 else 0.5)
+    return ja, u_mortar(face_xgp, mortar_type, m01, m02)

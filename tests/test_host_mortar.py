@@ -112,3 +112,68 @@ def test_mortar_numbering_against_a_reference_mesh():
             d = side_points(se, sloc, flip) - s
             d -= L * np.round(d / L)   # periodic box
             assert np.max(np.abs(d)) < 1e-13, (m, se)
+
+
+def test_mortar_surface_metrics_against_the_small_elements():
+    """Mortar_CalcSurfMetrics on the reference's mortar mesh: the mortarized metrics of a big side (contravariant vector of the
+    side's normal direction, i.e. NormVec * SurfElem up to the sign) equal what the small element computes for its own face from
+    its own geometry -- with the opposite sign, it is the slave -- and so do the face points.  Gauss-Lobatto nodes, N = 2."""
+    import os
+
+    from flexi_b200.hostmesh import mappings as MP
+    from flexi_b200.hostmesh.hopr import mortar_topology
+    from flexi_b200.hostmesh.mesh import _element_metrics, _metric_operators
+    from flexi_b200.hostmesh.mortar import mortar_surf_metrics
+    from test_host_mesh import face_of
+
+    path = os.path.join(os.path.dirname(__file__), "golden", "reference_naca3d", "CART_HEX_PERIODIC_MORTAR_002_mesh.h5")
+    X, ngeo, mortars = mortar_topology(path)
+    N = 2
+    geo = _element_metrics(X, _metric_operators(N, B.NODE_GAUSS_LOBATTO, ngeo))
+    _, _, S2V2 = MP.build_mappings(N)
+    m01, m02, _, _ = mortar_basis(N, B.NODE_GAUSS_LOBATTO)
+    L = X.reshape(-1, 3).max(axis=0) - X.reshape(-1, 3).min(axis=0)
+    pq = np.arange(N + 1)
+    P, Q = np.meshgrid(pq, pq, indexing="ij")
+    met_of = {MP.XI_MINUS: "Mf", MP.XI_PLUS: "Mf", MP.ETA_MINUS: "Mg", MP.ETA_PLUS: "Mg", MP.ZETA_MINUS: "Mh", MP.ZETA_PLUS: "Mh"}
+    sign_of = {MP.XI_MINUS: -1.0, MP.ETA_MINUS: -1.0, MP.ZETA_MINUS: -1.0, MP.XI_PLUS: 1.0, MP.ETA_PLUS: 1.0, MP.ZETA_PLUS: 1.0}
+
+    def side(A, e, loc, flip):   # [q, p, c] in the master orientation of the side
+        a, c = S2V2[:, P, Q, flip, loc - 1]
+        return np.transpose(face_of(A[e], loc, N)[c, a], (1, 0, 2))
+
+    n_checked = 0
+    for m in mortars:
+        e, loc = m["elem"], m["loc_side"]
+        nS_big = sign_of[loc] * side(geo[met_of[loc]], e, loc, 0)          # outward normal * SurfElem of the big side
+        ja, xgp = mortar_surf_metrics(nS_big, side(geo["xGP"], e, loc, 0), m["type"], m01, m02)
+        for k, (se, sloc, flip) in enumerate(m["small"]):
+            nS_small = sign_of[sloc] * side(geo[met_of[sloc]], se, sloc, flip)
+            assert np.max(np.abs(nS_small + ja[k])) < 1e-13, (m, k)        # the slave's outward normal is the opposite one
+            d = side(geo["xGP"], se, sloc, flip) - xgp[k]
+            d -= L * np.round(d / L)
+            assert np.max(np.abs(d)) < 1e-13
+            n_checked += 1
+    assert n_checked == 24
+
+
+@pytest.mark.parametrize("node", NODES)
+@pytest.mark.parametrize("mtype", [1, 2, 3])
+def test_free_stream_across_a_mortar(mtype, node):
+    """For a uniform state the numerical flux of a small side is F(U) . (n SurfElem)_small; projected to the big side by Flux_Mortar
+    it must be F(U) . (n SurfElem)_big, or the big element would not preserve the free stream: Flux_Mortar(Mortar_CalcSurfMetrics(Ja))
+    = Ja for any polynomial Ja of degree N (curved big side)."""
+    n = 5
+    xi, _, _ = B.get_nodes_and_weights(n, node)
+    m01, m02, m10, m20 = mortar_basis(n, node)
+    from flexi_b200.hostmesh.mortar import mortar_surf_metrics
+
+    rng = np.random.default_rng(5 + mtype)
+    c = rng.normal(size=(3, n + 1, n + 1))
+    P, Q = np.meshgrid(xi, xi, indexing="xy")
+    nS_big = np.stack([np.polynomial.polynomial.polyval2d(P, Q, c[d]) for d in range(3)], axis=-1)      # [q, p, 3]
+    nS_small, _ = mortar_surf_metrics(nS_big, nS_big, mtype, m01, m02)
+    F = rng.normal(size=(5, 3))                                                                         # F(U): one row per variable
+    flux_small = np.einsum("vd,sqpd->sqpv", F, nS_small)
+    flux_big = flux_mortar(flux_small, mtype, m10, m20)
+    assert np.allclose(flux_big, np.einsum("vd,qpd->qpv", F, nS_big), rtol=0, atol=1e-11)
